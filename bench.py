@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py — UCG-LD throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on host cores
+
+A "step" is one MD timestep of the hot path over the whole synthetic liquid:
+fix nve/ucgld initial_integrate -> skin check (+ neighbor rebuild when it fires) -> ghost
+refresh -> pair table_ucgld -> fix ucgld/langevin -> fix ucgstate ld -> final_integrate.
+Workload at N=1: BASELINE.json configs[1] — the 1 000 188-site UCG-LD liquid (fcc n=63,
+rho*=0.8442, LINEAR tables of 4096 entries, cut 2.5, skin 0.3, dt 0.002).
+value = N_sites * K / t (Matom-steps/s) with everything resident in HBM; e2e = the same step
+driven through the C-ABI with HOST (pinned) buffers going in and out every step.
+Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "UCG-LD Matom-steps/s"
+UNIT = "Matom-steps/s"
+NCELL_1GPU = 63          # 4*63^3 = 1 000 188 sites ("1M")
+TABLENGTH = 4096
+DT = 0.002
+SKIN = 0.3
+CUT = 2.5
+LANGEVIN = dict(t_start=1.0, t_stop=1.0, t_period=1.0, seed=48291)
+
+
+def workload_config(ncell, nranks):
+    return {"workload": "1M-site UCG-LD liquid, table_ucgld LINEAR 4096, fix nve/ucgld + ucgld/langevin + ucgstate ld",
+            "sites": int(4 * np.prod(ncell)) if not np.isscalar(ncell) else int(4 * ncell ** 3),
+            "ncell": list(ncell) if not np.isscalar(ncell) else [ncell] * 3,
+            "tablength": TABLENGTH, "cut": CUT, "skin": SKIN, "dt": DT,
+            "decomposition": "1 brick" if nranks == 1 else f"{nranks} bricks, halo over NCCL",
+            "l2": "inputs larger than L2 (neighbor rows ~0.4 GB + 0.1 GB site records per step; no flush needed)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.samples = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def make_fixtures(td):
+    import __graft_entry__ as g
+    g.load_package()
+    from lammps_ucg_dev_b200 import synth
+    tf = synth.write_table_file(os.path.join(td, "ucg.table"), npts=TABLENGTH)
+    sf = synth.write_state_file(os.path.join(td, "ucg.conf"))
+    return tf, sf
+
+
+# --------------------------------------------------------------------- CPU arm
+def cpu_reference(ncell, steps, warmup, td):
+    """The reference algorithm on the host: oracle/_ref (the reference's own UCG/*.cpp against
+    the LAMMPS-API shim) when it was built, else the C restatement (oracle/).  Serial: the
+    UCG package is single-threaded per MPI rank and no MPI exists on this box."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import __graft_entry__ as g
+    g.load_package()
+    from lammps_ucg_dev_b200 import synth
+    tf, sf = make_fixtures(td)
+    liq = synth.fcc_liquid(ncell)
+    kind = "port"
+    try:
+        import ref_binding as rb
+        if rb.available():
+            kind = "reference"
+    except Exception:
+        rb = None
+    if kind == "reference":
+        sim = rb.RefSim.ucgld_langevin(liq, tf, sf, tablength=TABLENGTH, dt=DT, skin=SKIN, **LANGEVIN)
+    else:
+        import oracle_binding as ob
+        sim = ob.Oracle.single_type(liq, tf, tablength=TABLENGTH, dt=DT, skin=SKIN)
+        sim.fix_nve()
+        sim.fix_langevin(LANGEVIN["t_start"], LANGEVIN["t_stop"], LANGEVIN["t_period"], LANGEVIN["seed"])
+        sim.fix_ucgstate(mode=1)
+    sim.setup()
+    if warmup:
+        sim.run(warmup)
+    t0 = time.perf_counter()
+    sim.run(steps)
+    dt = time.perf_counter() - t0
+    return dict(value=liq.n * steps / dt / 1e6, seconds=dt, sites=liq.n, steps=steps, kind=kind,
+                breakdown=sim.timers())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample of the 1M-site workload: the same liquid at 32 000 sites (configs[0]'s size),
+    # steps chosen so the run takes tens of seconds on one core
+    ncell = 20
+    steps = max(args.steps, 1) * 4
+    with tempfile.TemporaryDirectory() as td:
+        r = cpu_reference(ncell, steps, min(args.warmup, 2), td)
+    cfg = workload_config(NCELL_1GPU, 1)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / r["steps"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": cfg,
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": 1, "kind": r["kind"],
+                             "sample": f"{r['sites']} sites x {r['steps']} steps of the same deck (serial; no MPI on this box)",
+                             "breakdown_s": r["breakdown"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    from lammps_ucg_dev_b200 import engine, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the UCG hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world > 1:
+        from lammps_ucg_dev_b200 import multigpu
+        return multigpu.bench(args, rank, world, local, dist)
+
+    td = tempfile.mkdtemp()
+    tf, sf = make_fixtures(td)
+    liq = synth.fcc_liquid(NCELL_1GPU)
+    stream = torch.cuda.current_stream()
+    ctx = pkg.Context(local, stream=stream.cuda_stream)
+    engine.setup_single_type(ctx, tf, sf, tablength=TABLENGTH, cut=CUT, skin=SKIN, dt=DT, kT=1.0,
+                             box=(liq.box_lo, liq.box_hi))
+    engine.upload_liquid(ctx, liq)
+    ctx.deck_configure(pair_style=0, nve=1, langevin=1, t_start=LANGEVIN["t_start"], t_stop=LANGEVIN["t_stop"],
+                       t_period=LANGEVIN["t_period"], langevin_seed=LANGEVIN["seed"], ucgstate=2, thermo_every=0)
+    ctx.setup()
+    ctx.run(args.warmup)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launch_count()
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    ctx.run(args.steps)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - l0
+    sampler.stop_flag.set()
+    sampler.join()
+    value = liq.n * args.steps / (ms * 1e-3) / 1e6
+    th = ctx.thermo()
+
+    # ---- roofline of the dominant kernel (pair table_ucgld): live CUDA-event timing
+    total_full, maxrow, nbuilds = ctx.neigh_stats()
+    m_half = 0.5 * total_full / liq.n
+    bytes_per_site = 100.0 + 4.0 * m_half          # B_pair = 100 + 4*M
+    ctx.timers(2)
+    pair_ms = []
+    for _ in range(max(5, min(args.steps, 20))):
+        ctx.run(1)
+        pair_ms.append(ctx.last_pair_ms())
+    tms, tl = ctx.timers(0)
+    pair_avg = float(np.mean(pair_ms))
+    achieved = bytes_per_site * liq.n / (pair_avg * 1e-3) / 1e9
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k_pair_ucgld_fast", "kernel_ms": pair_avg,
+                "bytes_per_site": bytes_per_site, "half_neighbors_per_site": m_half,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
+                "stage_ms_per_step": {k: v / len(pair_ms) for k, v in tms.items()}}
+    prof = os.path.join(ROOT, "profiles", "pair_traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: the same step through the C-ABI with HOST buffers every step
+    n = liq.n
+    hx = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    hv = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    hl = torch.empty(n, dtype=torch.float64).pin_memory()
+    hvl = torch.empty(n, dtype=torch.float64).pin_memory()
+    hs = torch.empty(n, dtype=torch.int32).pin_memory()
+    cur = ctx.atoms_download(["x", "v", "ucgl", "ucgvl", "ucgstate"])
+    hx.numpy()[:] = cur["x"]; hv.numpy()[:] = cur["v"]; hl.numpy()[:] = cur["ucgl"]
+    hvl.numpy()[:] = cur["ucgvl"]; hs.numpy()[:] = cur["ucgstate"]
+    out_fields = ["x", "v", "f", "ucgl", "ucgvl", "ucgstate", "ucgp", "ucgforce"]
+    h2d = n * (24 + 24 + 8 + 8 + 4)
+    d2h = n * (24 + 24 + 24 + 8 + 8 + 4 + 8 + 8)
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        ctx.atoms_upload(n, x=hx.numpy(), v=hv.numpy(), ucgl=hl.numpy(), ucgvl=hvl.numpy(), ucgstate=hs.numpy())
+        ctx.run(1)
+        got = ctx.atoms_download(out_fields)
+        hx.numpy()[:] = got["x"]; hv.numpy()[:] = got["v"]; hl.numpy()[:] = got["ucgl"]
+        hvl.numpy()[:] = got["ucgvl"]; hs.numpy()[:] = got["ucgstate"]
+
+    e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e = {"value": n * e2e_steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "steps": e2e_steps, "api": "ucgb200_atoms_upload + ucgb200_run(1) + ucgb200_atoms_download"}
+
+    # ---- CPU baseline beside it (bounded sample, rank 0 only)
+    cpu = None
+    if not args.no_cpu:
+        r = cpu_reference(20, 150, 2, td)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": 1, "kind": r["kind"],
+               "sample": f"{r['sites']} sites x {r['steps']} steps of the same deck, serial (no MPI on this box)",
+               "breakdown_s": r["breakdown"]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(NCELL_1GPU, 1),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "thermo": {"lambda_temp": th[9], "rebuilds_total": int(th[11]), "nghost": int(th[13])}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

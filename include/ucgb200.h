@@ -1,0 +1,274 @@
+/* ucgb200.h — C-ABI of libucgb200.so: the B200 (sm_100a) implementation of the
+ * LAMMPS UCG package's per-timestep hot path.
+ *
+ * This is the drop-in boundary.  Everything the reference's
+ * LAMMPS styles do inside Pair::compute / Fix::initial_integrate /
+ * Fix::post_force / Fix::final_integrate / AtomVec::force_clear and everything
+ * stock LAMMPS does for them inside Neighbor::decide/build and Comm::forward/
+ * reverse/borders is reachable from here with plain pointers and sizes.
+ * The host-side style classes (lammps-ucg-dev_b200/host/) and the Python
+ * ctypes binding (tests, bench) are the only callers.
+ *
+ * Conventions
+ *   - every entry point returns int: 0 = ok, <0 = API misuse / CUDA failure
+ *     (text via ucgb200_last_error), >0 = runtime condition mirrored from the
+ *     reference's error->one() texts (see UCGB200_ERR_*).
+ *   - one context <-> one GPU <-> one calling thread; calls are ordered on the
+ *     context's stream and asynchronous until a *_download/_sync/_status call.
+ *   - host buffers are caller-owned, device memory is context-owned; pointers
+ *     named d_* are DEVICE pointers (for halo exchange plumbing), all others are
+ *     HOST pointers.
+ *   - reals are FP64, ids/types/states are int32, exactly as in the reference
+ *     (atom.h:180-192 of the reference).
+ *   - atom TYPES are "actual" types; "formal" types only index tables and
+ *     chemical potentials (UCG/pair_table_ucgld.cpp:114,176,430).
+ */
+#ifndef UCGB200_H
+#define UCGB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ucgb200_ctx ucgb200_ctx;
+
+/* runtime conditions (positive return codes / status word) */
+#define UCGB200_OK 0
+#define UCGB200_ERR_TABLE_INNER 1  /* "Pair distance < table inner cutoff"  pair_table_ucgld.cpp:223,279,354,437 */
+#define UCGB200_ERR_TABLE_OUTER 2  /* "Pair distance > table outer cutoff"  pair_table_ucgld.cpp:228,... */
+#define UCGB200_ERR_NEIGH_OVERFLOW 3 /* internal: neighbor row capacity exceeded (list is regrown and rebuilt) */
+#define UCGB200_ERR_DENSITY_TYPE 4 /* rleucg/bethe_density: density CV defined for actual type 1 only (Q15) */
+#define UCGB200_ERR_LOST_ATOMS 5   /* an atom left the box by more than one period */
+#define UCGB200_ERR_BOX_TOO_SMALL 6 /* periodic box shorter than cut+skin */
+
+/* table styles: enum{LOOKUP, LINEAR, SPLINE, BITMAP} pair_table_ucgld.h */
+#define UCGB200_TAB_LOOKUP 0
+#define UCGB200_TAB_LINEAR 1
+#define UCGB200_TAB_SPLINE 2
+#define UCGB200_TAB_BITMAP 3
+
+/* field masks for atoms_upload / atoms_download (AtomVecUCG field lists,
+ * UCG/atom_vec_ucg.cpp:48-90) */
+#define UCGB200_F_X        (1u << 0)   /* double[3n] */
+#define UCGB200_F_V        (1u << 1)   /* double[3n] */
+#define UCGB200_F_F        (1u << 2)   /* double[3n] */
+#define UCGB200_F_TYPE     (1u << 3)   /* int[n] */
+#define UCGB200_F_MASK     (1u << 4)   /* int[n] */
+#define UCGB200_F_TAG      (1u << 5)   /* int[n] */
+#define UCGB200_F_MOLECULE (1u << 6)   /* int[n] */
+#define UCGB200_F_UCGSTATE (1u << 7)   /* int[n] */
+#define UCGB200_F_UCGL     (1u << 8)   /* double[n] */
+#define UCGB200_F_UCGVL    (1u << 9)   /* double[n] */
+#define UCGB200_F_UCGML    (1u << 10)  /* double[n] */
+#define UCGB200_F_UCGP     (1u << 11)  /* double[n] */
+#define UCGB200_F_UCGFORCE (1u << 12)  /* double[n] */
+#define UCGB200_F_SCORES   (1u << 13)  /* double[2n]  ucgsoftmaxscores */
+#define UCGB200_F_NUMSTATES (1u << 14) /* int[n]  num_ucgstates (download only) */
+#define UCGB200_F_ALL 0x7fffu
+
+/* host view of the per-atom arrays, AoS exactly as LAMMPS holds them
+ * (double **x is a contiguous [n][3] block).  Unused members may be NULL. */
+typedef struct ucgb200_atoms {
+  double *x, *v, *f;
+  int *type, *mask, *tag, *molecule;
+  int *ucgstate;
+  double *ucgl, *ucgvl, *ucgml, *ucgp, *ucgforce;
+  double *ucgsoftmaxscores;
+  int *num_ucgstates;
+} ucgb200_atoms;
+
+/* ---------------------------------------------------------------- lifecycle */
+int ucgb200_create(int device, ucgb200_ctx **out);
+int ucgb200_destroy(ucgb200_ctx *ctx);
+const char *ucgb200_last_error(const ucgb200_ctx *ctx);
+/* run on an externally owned stream (cudaStream_t as void*); NULL = own stream */
+int ucgb200_set_stream(ucgb200_ctx *ctx, void *cuda_stream);
+int ucgb200_sync(ucgb200_ctx *ctx);
+/* number of kernels this context has launched so far (bench gpu_launches) */
+long long ucgb200_launch_count(const ucgb200_ctx *ctx);
+
+/* ------------------------------------------------------------ global set-up */
+/* force->boltz, ftm2v, mvv2e of the deck's `units` [stock Force] */
+int ucgb200_set_units(ucgb200_ctx *ctx, double boltz, double ftm2v, double mvv2e);
+/* domain->boxlo/boxhi/periodicity [stock Domain]; orthogonal boxes only */
+int ucgb200_set_box(ucgb200_ctx *ctx, const double lo[3], const double hi[3], const int periodic[3]);
+/* sub-domain owned by this context (multi-GPU brick); defaults to the box */
+int ucgb200_set_subdomain(ucgb200_ctx *ctx, const double sublo[3], const double subhi[3]);
+/* update->dt */
+int ucgb200_set_timestep(ucgb200_ctx *ctx, double dt);
+/* force->special_lj[0..3] */
+int ucgb200_set_special_lj(ucgb200_ctx *ctx, const double special_lj[4]);
+
+/* type maps read by read_state_settings (pair_table_ucgld.cpp:565-652):
+ *   n_states[1..n_actual], formal_from_actual[(t)*2 + s] (0 = undefined),
+ *   chem_pot[1..n_formal], mass[1..ntypes] (atom->mass, ntypes == n_formal).
+ * Arrays are 1-based like LAMMPS (element 0 unused). */
+int ucgb200_set_types(ucgb200_ctx *ctx, int n_actual, int n_formal, const int *n_states,
+                      const int *formal_from_actual, const double *chem_pot, const double *mass);
+/* kT = boltz * t_target of the first fix exporting "t_target"
+ * (pair_table_ucgld.cpp:876-881, fix_ucgstate.cpp:148-156) */
+int ucgb200_set_kT(ucgb200_ctx *ctx, double kT);
+
+/* one tabulated potential as built by compute_table (pair_table_ucgld.cpp:1105-1344).
+ * n = number of entries of e/f (tablength for LINEAR/SPLINE, tablength-1 for LOOKUP,
+ * 1<<tablength for BITMAP).  e2/f2 only for SPLINE; rsq/drsq/de/df only for BITMAP
+ * (for LINEAR de/df/rsq are recomputed on the device bit-exactly from e,f,innersq,delta).
+ * Returns the table index (>= 0) in *index. */
+int ucgb200_table_upload(ucgb200_ctx *ctx, int tabstyle, int tablength, int n, double innersq,
+                         double delta, double invdelta, double deltasq6, double cut, int nmask,
+                         int nshiftbits, const double *e, const double *f, const double *e2,
+                         const double *f2, const double *rsq, const double *drsq, const double *de,
+                         const double *df, int *index);
+int ucgb200_tables_clear(ucgb200_ctx *ctx);
+/* tabindex[(n_formal+1)^2] (pair_table_ucgld.cpp:844,892) and
+ * cutsq[(n_actual+1)^2] (init_one :886-895; only actual-type pairs are read, :213) */
+int ucgb200_set_pair_maps(ucgb200_ctx *ctx, const int *tabindex, const double *cutsq);
+
+/* ---------------------------------------------------------------- atom data */
+/* AtomVecUCG arrays -> device.  nlocal owned atoms (ghosts are built on the device). */
+int ucgb200_atoms_upload(ucgb200_ctx *ctx, int nlocal, const ucgb200_atoms *host, unsigned fields);
+/* device -> host, in the ORIGINAL host order of the last full upload (the device
+ * re-sorts atoms by cell at every neighbor rebuild; tags travel with them). */
+int ucgb200_atoms_download(ucgb200_ctx *ctx, int nlocal_capacity, ucgb200_atoms *host, unsigned fields);
+int ucgb200_natoms(const ucgb200_ctx *ctx, int *nlocal, int *nghost);
+/* AtomVecUCG::force_clear (atom_vec_ucg.cpp:131-135) + stock f memset.  The pair
+ * kernels overwrite f/ucgforce/scores, so this is only needed when no pair style runs. */
+int ucgb200_force_clear(ucgb200_ctx *ctx);
+
+/* ----------------------------------------------------------------- neighbor */
+#define UCGB200_NEIGH_FULL 1 /* every neighbor of every owned atom (what the kernels walk) */
+/* `neighbor <skin> bin`; cutneigh = sqrt(max cutsq) + skin.  cut_override > 0 forces the
+ * list cutoff (fix cluster_switch requests its own list). */
+int ucgb200_neigh_configure(ucgb200_ctx *ctx, double skin, double cut_override);
+/* Neighbor::decide/check_distance [stock]: *rebuild = 1 iff any owned atom moved more
+ * than skin/2 since the last build. */
+int ucgb200_neigh_decide(ucgb200_ctx *ctx, int *rebuild);
+/* domain->pbc + cell sort + ghost construction (comm->borders) + list build */
+int ucgb200_neigh_build(ucgb200_ctx *ctx);
+/* comm->forward_comm(): refresh ghost x, ucgstate, ucgl, ucgp from their owners
+ * (fields_comm, atom_vec_ucg.cpp:71) */
+int ucgb200_ghosts_forward(ucgb200_ctx *ctx);
+/* neighbor list download for parity tests: rows are in current DEVICE order;
+ * tag_i[nlocal], numneigh[nlocal], offsets[nlocal+1], neigh_tags[total] (tags of the
+ * neighbors), neigh_shift[total] (0..26 periodic image code, 13 = none).  Pass
+ * NULL pointers with *total to query sizes. */
+int ucgb200_neigh_download(ucgb200_ctx *ctx, int *nlocal, long long *total, int *tag_i, int *numneigh,
+                           long long *offsets, int *neigh_tags, int *neigh_shift);
+int ucgb200_neigh_stats(ucgb200_ctx *ctx, long long *total_pairs, int *max_row, int *nbuilds);
+
+/* --------------------------------------------------------------- pair styles */
+/* PairTable_UCGLD::compute (pair_table_ucgld.cpp:111-541). */
+int ucgb200_pair_ucgld(ucgb200_ctx *ctx, int eflag, int vflag);
+/* PairTable_UCG_Bethe::compute (pair_table_ucg_bethe.cpp:88-630).
+ * method 0 = mean field, 1 = bethe; pseudo 1 = pseudo-likelihood scores, 0 = SCE;
+ * prior 0 = chemical potential, 2 = ucgl (noise prior is stochastic: seed/noise). */
+int ucgb200_pair_bethe(ucgb200_ctx *ctx, int eflag, int vflag, int method, int pseudo, int prior,
+                       double noise_level, int seed);
+/* PairTable_RLEUCG_INTERFACE::compute (pair_table_rleucg_interface.cpp:177-505) */
+int ucgb200_pair_rleucg_configure(ucgb200_ctx *ctx, int n_types, const int *n_states_of_type,
+                                  const double *threshold_radius, const double *density_threshold,
+                                  const int *tabindex, const double *cutsq, double T);
+int ucgb200_pair_rleucg(ucgb200_ctx *ctx, int eflag, int vflag);
+/* PairTable_UCG_Bethe_Density::compute, repaired semantics */
+int ucgb200_pair_bethe_density_configure(ucgb200_ctx *ctx, const int *density_type_flag,
+                                         const double *density_threshold, const double *threshold_radius);
+int ucgb200_pair_bethe_density(ucgb200_ctx *ctx, int eflag, int vflag, int method, int pseudo);
+/* eng_vdwl, virial[6] (xx,yy,zz,xy,xz,yz) of the last pair call with eflag/vflag */
+int ucgb200_pair_energy_virial(ucgb200_ctx *ctx, double *eng_vdwl, double virial[6]);
+
+/* --------------------------------------------------------------------- fixes */
+/* FixNVE_UCGLD::initial_integrate (fix_nve_ucgld.cpp:44-101); wall != 0 adds the
+ * ucgstate = (lambda < 0.5 ? 0 : 1) assignment of FixNVE_UCGLD_Wall_Hard
+ * (fix_nve_ucgld_wall_hard.cpp:125-131). */
+int ucgb200_fix_nve_initial(ucgb200_ctx *ctx, double dtv, double dtf, int groupbit, int wall);
+/* ::final_integrate (fix_nve_ucgld.cpp:104-153); wall != 0 adds the hard-wall
+ * reflection (fix_nve_ucgld_wall_hard.cpp:194-200). */
+int ucgb200_fix_nve_final(ucgb200_ctx *ctx, double dtf, int groupbit, int wall);
+/* FixNVE_UCGLD_Wall_Hard::post_force bias (fix_nve_ucgld_wall_hard.cpp:234-257) */
+int ucgb200_fix_wall_bias(ucgb200_ctx *ctx, double barrier, int groupbit);
+/* FixUCGState::post_force (fix_ucgstate.cpp:88-132). mode 0 = deterministic round,
+ * 1 = ld (probabilities only), 2 = mc(seed, rate).  step = update->ntimestep (RNG counter). */
+int ucgb200_fix_ucgstate(ucgb200_ctx *ctx, int mode, int seed, double rate, long long step);
+/* Fix_UCGLD_Langevin::post_force (fix_ucgld_langevin.cpp:226-297) for the current
+ * t_target; gamma1/gamma2 per ACTUAL type index 1..ntypes as computed in init()
+ * (:164-171).  step feeds the counter-based RNG. */
+int ucgb200_fix_langevin(ucgb200_ctx *ctx, const double *gfactor1, const double *gfactor2, int ntypes,
+                         double tsqrt, int seed, long long step, int groupbit, int zero_v_skip);
+/* Fix_UCGLD_Langevin::end_of_step lambda temperature (:303-312), globally reduced
+ * on this context: returns sum 0.5*ml*vl^2*mvv2e and the group count. */
+int ucgb200_lambda_ke(ucgb200_ctx *ctx, int groupbit, double *ke_sum, long long *count);
+/* particle kinetic energy sum 0.5*m*v^2*mvv2e (thermo) */
+int ucgb200_kinetic_energy(ucgb200_ctx *ctx, int groupbit, double *ke_sum, long long *count);
+
+/* FixClusterSwitch (fix_cluster_switch.cpp:537-839): label connected molecule
+ * clusters over the full list with the type contact map, then MC-flip the ON/OFF
+ * types of molecules outside the seed cluster. */
+int ucgb200_cluster_configure(ucgb200_ctx *ctx, int mol_seed, int mol_offset, double cutoff,
+                              int n_switch_types, const int *type_on, const int *type_off,
+                              const double *prob_on, const double *prob_off, int n_contact_types,
+                              const int *contact_map, int max_mol);
+int ucgb200_cluster_check(ucgb200_ctx *ctx, int *n_in_cluster, int *mol_cluster_out);
+int ucgb200_cluster_switch(ucgb200_ctx *ctx, int seed, long long step, int *n_attempts, int *n_success);
+
+/* ---------------------------------------------------- resident run (no host data) */
+/* deck description for the resident integrator: which fixes are active, in
+ * fix-definition order semantics of SURVEY §3.1. */
+typedef struct ucgb200_deck {
+  int pair_style;        /* 0 ucgld, 1 bethe, 2 rleucg, 3 bethe_density */
+  int nve;               /* 1 = fix nve/ucgld, 2 = fix nve/ucgld/wall/hard */
+  int nve_groupbit;
+  int wall_bias;         /* bias_potential flag */
+  double wall_barrier;
+  int langevin;          /* fix ucgld/langevin present */
+  double t_start, t_stop, t_period;
+  int langevin_seed;
+  int langevin_groupbit;
+  int ucgstate;          /* 0 = absent, 1 = deterministic, 2 = ld, 3 = mc */
+  int ucgstate_seed;
+  double ucgstate_rate;
+  int bethe_method, bethe_pseudo, bethe_prior;
+  int thermo_every;      /* eflag/vflag on steps that are multiples of this (0 = never) */
+  int reserved[8];
+} ucgb200_deck;
+int ucgb200_deck_configure(ucgb200_ctx *ctx, const ucgb200_deck *deck);
+/* Verlet::setup [stock]: pbc, build, force_clear, pair->compute, fix setup() calls */
+int ucgb200_setup(ucgb200_ctx *ctx);
+/* Verlet::run(n) [stock] with every stage on the device; ntimestep continues from
+ * the last call; beginstep/endstep of the run are (current, current+n). */
+int ucgb200_run(ucgb200_ctx *ctx, int nsteps);
+/* thermo scalars of the last thermo step: out[0]=eng_vdwl, out[1..6]=virial,
+ * out[7]=particle KE sum, out[8]=lambda KE sum, out[9]=lambda temperature,
+ * out[10]=ntimestep, out[11]=rebuild count, out[12]=nlocal, out[13]=nghost */
+int ucgb200_thermo(ucgb200_ctx *ctx, double out[16]);
+/* sticky device error word: code (UCGB200_ERR_*), tags of the pair, rsq */
+int ucgb200_status(ucgb200_ctx *ctx, int *code, int *tag_i, int *tag_j, double *rsq);
+/* per-kernel-class CUDA-event timers (ms since last reset): pair, neigh, comm, modify */
+int ucgb200_timers(ucgb200_ctx *ctx, int enable, double out_ms[4], long long out_launches[4]);
+/* duration of the last pair kernel launch in ms (events on the context stream) */
+int ucgb200_last_pair_ms(ucgb200_ctx *ctx, double *ms);
+
+/* ---------------------------------------------------- multi-GPU halo plumbing */
+/* Brick decomposition: this context owns sub-domain (set_subdomain); ghosts within
+ * cut+skin of the faces come from up to 26 neighbor bricks (or periodic self-images).
+ * The pack/unpack kernels work on DEVICE buffers so that any transport (NCCL
+ * send/recv driven by the host layer, or peer-mapped stores) can carry them. */
+int ucgb200_halo_configure(ucgb200_ctx *ctx, int rank, int nranks, const int procgrid[3]);
+/* after neigh_build's local part: number of atoms to send to each of 27 directions */
+int ucgb200_halo_send_counts(ucgb200_ctx *ctx, int counts[27]);
+/* border records (48 B/ghost: x,y,z,ucgl,(type|state|tag),ucgp) for direction dir */
+int ucgb200_halo_pack_border(ucgb200_ctx *ctx, int dir, void *d_buf);
+int ucgb200_halo_set_recv_counts(ucgb200_ctx *ctx, const int counts[27]);
+int ucgb200_halo_unpack_border(ucgb200_ctx *ctx, int dir, const void *d_buf);
+/* per-step forward records (40 B/ghost: x,y,z,ucgl,(state),ucgp) */
+int ucgb200_halo_pack_forward(ucgb200_ctx *ctx, int dir, void *d_buf);
+int ucgb200_halo_unpack_forward(ucgb200_ctx *ctx, int dir, const void *d_buf);
+/* finish a distributed rebuild once all borders are unpacked (bins ghosts, builds rows) */
+int ucgb200_neigh_build_local(ucgb200_ctx *ctx);
+int ucgb200_neigh_build_finish(ucgb200_ctx *ctx);
+/* device pointer of the rebuild flag (int) so the host layer can all-reduce it */
+int ucgb200_neigh_flag_ptr(ucgb200_ctx *ctx, void **d_flag);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UCGB200_H */

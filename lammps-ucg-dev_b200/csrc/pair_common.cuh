@@ -1,0 +1,89 @@
+// pair_common.cuh — table look-up and reduction helpers shared by the pair kernels.
+#pragma once
+#include "ucg_internal.cuh"
+
+namespace ucg {
+
+__device__ __forceinline__ void report_error(ErrWord *err, int code, int tag_i, int tag_j, double rsq) {
+  if (atomicCAS(&err->code, 0, code) == 0) {
+    err->tag_i = tag_i;
+    err->tag_j = tag_j;
+    err->rsq = rsq;
+  }
+}
+
+// One tabulated potential at rsq: the "------- For one table -------" block that the
+// reference repeats at pair_table_ucgld.cpp:223-268, 279-324, 354-399, 437-482 (and the
+// clones in the other pair styles).  Returns 0, or UCGB200_ERR_TABLE_INNER/OUTER where the
+// reference calls error->one().  e,f are NOT yet multiplied by factor_lj.
+__device__ __forceinline__ int table_eval(const TableDev &tb, double rsq, double &e, double &f) {
+  if (rsq < tb.innersq) return UCGB200_ERR_TABLE_INNER;
+  const int tlm1 = tb.tablength - 1;
+  if (tb.style == UCGB200_TAB_LINEAR) {
+    // itable = static_cast<int>((rsq - innersq) * invdelta)            (:447)
+    int it = (int)__dmul_rn(__dadd_rn(rsq, -tb.innersq), tb.invdelta);
+    if (it >= tlm1) return UCGB200_ERR_TABLE_OUTER;
+    // rsq[it] = innersq + it*delta, de = e[it+1]-e[it], df likewise    (compute_table :1157-1174)
+    double rsq_it = __dadd_rn(tb.innersq, __dmul_rn((double)it, tb.delta));
+    double frac = (rsq - rsq_it) * tb.invdelta;
+    double2 a = __ldg(&tb.ef[it]), b = __ldg(&tb.ef[it + 1]);
+    e = a.x + frac * (b.x - a.x);
+    f = a.y + frac * (b.y - a.y);
+  } else if (tb.style == UCGB200_TAB_SPLINE) {
+    int it = (int)__dmul_rn(__dadd_rn(rsq, -tb.innersq), tb.invdelta);
+    if (it >= tlm1) return UCGB200_ERR_TABLE_OUTER;
+    double rsq_it = __dadd_rn(tb.innersq, __dmul_rn((double)it, tb.delta));
+    double b = (rsq - rsq_it) * tb.invdelta;
+    double a = 1.0 - b;
+    double2 y0 = __ldg(&tb.ef[it]), y1 = __ldg(&tb.ef[it + 1]);
+    double2 z0 = __ldg(&tb.ef2[it]), z1 = __ldg(&tb.ef2[it + 1]);
+    double ca = a * a * a - a, cb = b * b * b - b;
+    e = a * y0.x + b * y1.x + (ca * z0.x + cb * z1.x) * tb.deltasq6;
+    f = a * y0.y + b * y1.y + (ca * z0.y + cb * z1.y) * tb.deltasq6;
+  } else if (tb.style == UCGB200_TAB_LOOKUP) {
+    int it = (int)__dmul_rn(__dadd_rn(rsq, -tb.innersq), tb.invdelta);
+    if (it >= tlm1) return UCGB200_ERR_TABLE_OUTER;
+    double2 a = __ldg(&tb.ef[it]);
+    e = a.x; f = a.y;
+  } else {  // BITMAP: index from the float bit pattern of rsq (:466-471)
+    float rf = (float)rsq;
+    int it = (__float_as_int(rf) & tb.nmask) >> tb.nshiftbits;
+    double2 rd = __ldg(&tb.rd[it]);
+    double frac = ((double)rf - rd.x) * rd.y;
+    double2 a = __ldg(&tb.ef[it]), d = __ldg(&tb.dedf[it]);
+    e = a.x + frac * d.x;
+    f = a.y + frac * d.y;
+  }
+  return 0;
+}
+
+// sum `v` over the LPA lanes of a sub-warp group (result valid in every lane)
+template <int LPA>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int o = LPA / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-level reduction of NV per-thread values into partials[blockIdx*NV + k];
+// every thread of the block must call it.  Deterministic (fixed tree).
+template <int NV, int BS>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *partials) {
+  __shared__ double red[NV][BS / 32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    double x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) red[k][wid] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+    for (int w = 0; w < BS / 32; w++) s += red[threadIdx.x][w];
+    partials[(size_t)blockIdx.x * NV + threadIdx.x] = s;
+  }
+}
+
+}  // namespace ucg

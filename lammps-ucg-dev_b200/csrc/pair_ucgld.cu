@@ -1,0 +1,402 @@
+// pair_ucgld.cu — PairTable_UCGLD::compute (UCG/pair_table_ucgld.cpp:111-541) for sm_100a.
+//
+// Schedule: a group of LPA lanes per owned site walks that site's FULL neighbor row
+// (coalesced row read, 32-byte gathers of {x,y,z,lambda} + 4-byte {type,state}); every
+// contribution is accumulated into the CENTRE site only and reduced with warp shuffles,
+// so f / ucgforce / ucgsoftmaxscores are written exactly once per site (force_clear,
+// atom_vec_ucg.cpp:131-135, and the chemical-potential pre-add, :170-180, are folded in)
+// and there are neither FP64 atomics nor a reverse halo.  A pair (i,j) is therefore
+// evaluated from both ends; by the symmetry of tabindex (init_one, :892) both ends see the
+// same four potentials, so the result equals the reference's half-list/newton-on tally.
+//
+// Per visited pair inside the cutoff (scenario 4, :424-519), with a=1-li, b=1-lj:
+//   A  = b*u00 + lj*u01      B  = b*u10 + lj*u11          (u_ss' from 4 table look-ups)
+//   FA = b*f00 + lj*f01      FB = b*f10 + lj*f11
+//   E_ij   = a*A + li*B      fpair = a*FA + li*FB          (:507, :509)
+//   ucgf_i -= B - A          == lj(u11-u01) + (1-lj)(u10-u00)   (:514)
+//   s_i[si] -= u[si][state_j]/kT                           (:492-498)
+// Scenarios 1-3 (:219-421) are the same formulas with one-state sites having weight
+// {1,0}; scenario 2 uses the intended `sj` keying.
+#include "pair_common.cuh"
+
+using namespace ucg;
+
+namespace {
+
+struct PairArgs {
+  const double4 *pos;
+  const int *ts;
+  const int *tag;
+  int nlocal;
+  const int *neigh;
+  int stride;
+  const int *numneigh;
+  const PairInfo *pinfo;
+  const TypeInfo *tinfo;
+  int na;
+  const TableDev *tables;
+  double special_lj[4];
+  double inv_kT;
+  double4 *frc;
+  double2 *scores;
+  double *partials;
+  ErrWord *err;
+};
+
+// ---------------------------------------------------------------- general kernel
+template <int LPA, bool EV, int BS>
+__global__ void __launch_bounds__(BS) k_pair_ucgld(PairArgs p) {
+  const int gid = (blockIdx.x * BS + threadIdx.x) / LPA;
+  const int sub = threadIdx.x % LPA;
+  const bool active = gid < p.nlocal;
+  const int i = active ? gid : 0;
+  const double4 ri = p.pos[i];
+  const int tsi = p.ts[i];
+  const int ti = tsi & 0xffff;
+  const TypeInfo tyi = p.tinfo[ti];
+  const int ni = tyi.nstates;
+  const double li = ri.w, ai = 1.0 - li;
+  const int jnum = active ? p.numneigh[i] : 0;
+  const int *row = p.neigh + (size_t)i * p.stride;
+  const PairInfo *prow = p.pinfo + ti * p.na;
+
+  double fx = 0, fy = 0, fz = 0, accA = 0, accB = 0, S0 = 0, S1 = 0;
+  double vir[6] = {0, 0, 0, 0, 0, 0};
+
+  for (int jj = sub; jj < jnum; jj += LPA) {
+    int jraw = row[jj];
+    const double factor_lj = p.special_lj[(jraw >> UCG_SBBITS) & 3];
+    const int j = jraw & UCG_NEIGHMASK;
+    const double4 rj = p.pos[j];
+    const int tsj = p.ts[j];
+    const int tj = tsj & 0xffff;
+    const double dx = ri.x - rj.x, dy = ri.y - rj.y, dz = ri.z - rj.z;
+    const double rsq = rsq_exact(dx, dy, dz);
+    const PairInfo pi = prow[tj];
+    if (rsq < pi.cutsq) {
+      const int nj = pi.nj;
+      const int sj = (nj == 2) ? ((tsj >> 16) & 1) : 0;
+      const double lj = rj.w;
+      const double wj0 = (nj == 2) ? 1.0 - lj : 1.0, wj1 = (nj == 2) ? lj : 0.0;
+      double u[4] = {0, 0, 0, 0}, f[4] = {0, 0, 0, 0};
+      int ec = 0;
+      for (int a = 0; a < ni; a++)
+        for (int b = 0; b < nj; b++) {
+          int e1 = table_eval(p.tables[pi.tab[a * 2 + b]], rsq, u[a * 2 + b], f[a * 2 + b]);
+          if (e1 && !ec) ec = e1;
+        }
+      if (ec) {
+        report_error(p.err, ec, p.tag[i], p.tag[j], rsq);
+        continue;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) { u[k] *= factor_lj; f[k] *= factor_lj; }
+      const double A = wj0 * u[0] + wj1 * u[1];
+      const double FA = wj0 * f[0] + wj1 * f[1];
+      double fpair;
+      if (ni == 2) {
+        const double B = wj0 * u[2] + wj1 * u[3];
+        const double FB = wj0 * f[2] + wj1 * f[3];
+        accA += A; accB += B;
+        fpair = ai * FA + li * FB;
+        S0 += sj ? u[1] : u[0];
+        S1 += sj ? u[3] : u[2];
+      } else {
+        accA += A;
+        fpair = FA;
+      }
+      fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
+      if (EV) {
+        vir[0] += dx * dx * fpair; vir[1] += dy * dy * fpair; vir[2] += dz * dz * fpair;
+        vir[3] += dx * dy * fpair; vir[4] += dx * dz * fpair; vir[5] += dy * dz * fpair;
+      }
+    }
+  }
+  fx = group_sum<LPA>(fx); fy = group_sum<LPA>(fy); fz = group_sum<LPA>(fz);
+  accA = group_sum<LPA>(accA); accB = group_sum<LPA>(accB);
+  S0 = group_sum<LPA>(S0); S1 = group_sum<LPA>(S1);
+  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+  if (active && sub == 0) {
+    double4 fo;
+    fo.x = fx; fo.y = fy; fo.z = fz;
+    double2 so;
+    double e_i;
+    if (ni == 2) {
+      fo.w = -tyi.dmu - (accB - accA);               // :177, :514
+      so.x = -S0 * p.inv_kT;
+      so.y = -tyi.dmu * p.inv_kT - S1 * p.inv_kT;    // :178, :497
+      e_i = ai * accA + li * accB;
+    } else {
+      fo.w = 0.0; so.x = 0.0; so.y = 0.0;
+      e_i = accA;
+    }
+    p.frc[i] = fo;
+    p.scores[i] = so;
+    if (EV) ev[0] = 0.5 * e_i;
+  }
+  if (EV) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      double v = group_sum<LPA>(vir[k]);
+      if (active && sub == 0) ev[1 + k] = 0.5 * v;
+    }
+    block_reduce_store<7, BS>(ev, p.partials);
+  }
+}
+
+// ------------------------------------------------------------------- fast kernel
+// One 2-state actual type, LINEAR tables on a common rsq grid (the benchmark liquids).
+// The W (3 or 4) unique tables are interleaved row-wise and staged once per CTA in shared
+// memory: row it = {e00,f00, e01,f01, [e10,f10,] e11,f11}; a pair reads rows it and it+1
+// (2*W 16-byte words, contiguous).  CTAs are persistent (one per SM).
+struct FastArgs {
+  const double4 *pos;
+  const int *ts;
+  const int *tag;
+  int nlocal;
+  const int *neigh;
+  int stride;
+  const int *numneigh;
+  const double2 *table;  // [tablen][W]
+  int tablen;
+  double innersq, delta, invdelta, cutsq;
+  double dmu, inv_kT;
+  double4 *frc;
+  double2 *scores;
+  double *partials;
+  ErrWord *err;
+  int smem_table;  // 1: stage table in shared memory, 0: read it through L1/L2
+};
+
+template <int LPA, bool EV, int W, int BS>
+__global__ void __launch_bounds__(BS) k_pair_ucgld_fast(FastArgs p) {
+  extern __shared__ double2 s_tab[];
+  const double2 *tab = p.table;
+  if (p.smem_table) {
+    const int nwords = p.tablen * W;
+    for (int k = threadIdx.x; k < nwords; k += BS) s_tab[k] = p.table[k];
+    __syncthreads();
+    tab = s_tab;
+  }
+  const int sub = threadIdx.x % LPA;
+  const int groups_per_block = BS / LPA;
+  const int tlm1 = p.tablen - 1;
+  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+
+  for (int base = blockIdx.x * groups_per_block; base < p.nlocal; base += gridDim.x * groups_per_block) {
+    const int gid = base + threadIdx.x / LPA;
+    const bool active = gid < p.nlocal;
+    const int i = active ? gid : p.nlocal - 1;
+    const double4 ri = p.pos[i];
+    const double li = ri.w, ai = 1.0 - li;
+    const int jnum = active ? p.numneigh[i] : 0;
+    const int *row = p.neigh + (size_t)i * p.stride;
+    double fx = 0, fy = 0, fz = 0, accA = 0, accB = 0, S0 = 0, S1 = 0;
+    double vir[6] = {0, 0, 0, 0, 0, 0};
+
+    for (int jj = sub; jj < jnum; jj += LPA) {
+      const int j = row[jj] & UCG_NEIGHMASK;
+      const double4 rj = p.pos[j];
+      const int sj = (p.ts[j] >> 16) & 1;
+      const double dx = ri.x - rj.x, dy = ri.y - rj.y, dz = ri.z - rj.z;
+      const double rsq = rsq_exact(dx, dy, dz);
+      if (rsq < p.cutsq) {
+        const int it = (int)__dmul_rn(__dadd_rn(rsq, -p.innersq), p.invdelta);
+        if (rsq < p.innersq || it >= tlm1) {
+          report_error(p.err, rsq < p.innersq ? UCGB200_ERR_TABLE_INNER : UCGB200_ERR_TABLE_OUTER, p.tag[i], p.tag[j], rsq);
+          continue;
+        }
+        const double rsq_it = __dadd_rn(p.innersq, __dmul_rn((double)it, p.delta));
+        const double frac = (rsq - rsq_it) * p.invdelta;
+        const double2 *r0 = tab + it * W;
+        const double2 a00 = r0[0], a01 = r0[1], a11 = r0[W - 1];
+        const double2 b00 = r0[W], b01 = r0[W + 1], b11 = r0[2 * W - 1];
+        const double u00 = a00.x + frac * (b00.x - a00.x), f00 = a00.y + frac * (b00.y - a00.y);
+        const double u01 = a01.x + frac * (b01.x - a01.x), f01 = a01.y + frac * (b01.y - a01.y);
+        const double u11 = a11.x + frac * (b11.x - a11.x), f11 = a11.y + frac * (b11.y - a11.y);
+        double u10, f10;
+        if (W == 4) {
+          const double2 a10 = r0[2], b10 = r0[W + 2];
+          u10 = a10.x + frac * (b10.x - a10.x);
+          f10 = a10.y + frac * (b10.y - a10.y);
+        } else { u10 = u01; f10 = f01; }
+        const double lj = rj.w, bj = 1.0 - lj;
+        const double A = bj * u00 + lj * u01, B = bj * u10 + lj * u11;
+        const double FA = bj * f00 + lj * f01, FB = bj * f10 + lj * f11;
+        accA += A; accB += B;
+        const double fpair = ai * FA + li * FB;
+        S0 += sj ? u01 : u00;
+        S1 += sj ? u11 : u10;
+        fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
+        if (EV) {
+          vir[0] += dx * dx * fpair; vir[1] += dy * dy * fpair; vir[2] += dz * dz * fpair;
+          vir[3] += dx * dy * fpair; vir[4] += dx * dz * fpair; vir[5] += dy * dz * fpair;
+        }
+      }
+    }
+    fx = group_sum<LPA>(fx); fy = group_sum<LPA>(fy); fz = group_sum<LPA>(fz);
+    accA = group_sum<LPA>(accA); accB = group_sum<LPA>(accB);
+    S0 = group_sum<LPA>(S0); S1 = group_sum<LPA>(S1);
+    if (active && sub == 0) {
+      double4 fo;
+      fo.x = fx; fo.y = fy; fo.z = fz;
+      fo.w = -p.dmu - (accB - accA);
+      p.frc[i] = fo;
+      p.scores[i] = make_double2(-S0 * p.inv_kT, -p.dmu * p.inv_kT - S1 * p.inv_kT);
+      if (EV) ev[0] += 0.5 * (ai * accA + li * accB);
+    }
+    if (EV) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        double v = group_sum<LPA>(vir[k]);
+        if (active && sub == 0) ev[1 + k] += 0.5 * v;
+      }
+    }
+  }
+  if (EV) block_reduce_store<7, BS>(ev, p.partials);
+}
+
+__global__ void k_reduce_partials(const double *__restrict__ partials, int nblocks, int nvals, double *__restrict__ out) {
+  // one warp per value, fixed order => deterministic
+  int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (k >= nvals) return;
+  double s = 0.0;
+  for (int b = lane; b < nblocks; b += 32) s += partials[(size_t)b * nvals + k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[k] = s;
+}
+
+}  // namespace
+
+int ucg::reduce_partials(ucgb200_ctx *c, int nblocks, int nvals, int out_offset) {
+  k_reduce_partials<<<1, 32 * nvals, 0, c->stream>>>(c->d_partials.p, nblocks, nvals, c->d_ev.p + out_offset);
+  UCG_LAUNCHED(c);
+  return 0;
+}
+
+static int g_sm_count = 0;
+static int sm_count(int device) {
+  if (!g_sm_count) cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, device);
+  return g_sm_count ? g_sm_count : 148;
+}
+
+// tunables (set through the environment for experiments; defaults chosen by ncu)
+static int env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+template <int LPA, bool EV, int W>
+static int launch_fast(ucgb200_ctx *c, FastArgs &a, int &nblk) {
+  constexpr int BS = 512;
+  size_t smem = a.smem_table ? (size_t)a.tablen * W * sizeof(double2) : 0;
+  auto kern = k_pair_ucgld_fast<LPA, EV, W, BS>;
+  if (smem > 48 * 1024) UCG_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  if (!a.smem_table) per_sm = 3;
+  else if (smem <= 100 * 1024) per_sm = 2;
+  nblk = sm_count(c->device) * per_sm;
+  int groups = BS / LPA;
+  int need = (a.nlocal + groups - 1) / groups;
+  if (nblk > need) nblk = need;
+  if (EV) UCG_CHECK(c, c->d_partials.ensure((size_t)nblk * 8 + 64));
+  a.partials = c->d_partials.p;
+  kern<<<nblk, BS, smem, c->stream>>>(a);
+  UCG_LAUNCHED(c);
+  return 0;
+}
+
+template <int LPA, bool EV>
+static int launch_general(ucgb200_ctx *c, PairArgs &a, int &nblk) {
+  constexpr int BS = 256;
+  long long nthreads = (long long)a.nlocal * LPA;
+  nblk = nblocks(nthreads, BS);
+  if (EV) UCG_CHECK(c, c->d_partials.ensure((size_t)nblk * 8 + 64));
+  a.partials = c->d_partials.p;
+  k_pair_ucgld<LPA, EV, BS><<<nblk, BS, 0, c->stream>>>(a);
+  UCG_LAUNCHED(c);
+  return 0;
+}
+
+extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  int rc = rebuild_maps(c);
+  if (rc) return rc;
+  if (!c->list_valid) return fail(c, "pair_ucgld: neighbor list not built");
+  c->ev_valid = false;
+  if (c->nlocal == 0) return 0;
+  const bool ev = eflag || vflag;
+  int nblk = 0;
+  const bool timed = c->timers_on;
+  if (timed) cudaEventRecord(c->ev_pair0, c->stream);
+  const int force_general = env_int("UCGB200_FORCE_GENERAL", 0);
+  const int lpa_fast = env_int("UCGB200_LPA", 8);
+  const int smem_pref = env_int("UCGB200_SMEM_TABLE", 1);
+  if (c->fast_uniform && !force_general) {
+    FastArgs a{};
+    a.pos = c->pos.p; a.ts = c->ts.p; a.tag = c->tag.p; a.nlocal = c->nlocal;
+    a.neigh = c->neigh.p; a.stride = c->neigh_stride; a.numneigh = c->numneigh.p;
+    a.table = c->d_fast_table.p; a.tablen = c->fast_len;
+    const ucg::TableDev &t0 = c->tables[c->fast_tab[0]];
+    a.innersq = t0.innersq; a.delta = t0.delta; a.invdelta = t0.invdelta;
+    a.cutsq = c->cutsq[1 * (c->n_formal + 1) + 1];
+    a.dmu = c->chem_pot[c->formal_from[2 * 1 + 1]] - c->chem_pot[c->formal_from[2 * 1 + 0]];
+    a.inv_kT = 1.0 / c->kT;
+    a.frc = c->frc.p; a.scores = c->scores.p; a.err = c->d_err.p;
+    size_t smem = (size_t)c->fast_len * c->fast_ntab * sizeof(double2);
+    a.smem_table = (smem_pref && smem <= 220 * 1024) ? 1 : 0;
+#define FAST(L, E, W) rc = launch_fast<L, E, W>(c, a, nblk)
+    if (c->fast_ntab == 3) {
+      if (lpa_fast == 4) { if (ev) FAST(4, true, 3); else FAST(4, false, 3); }
+      else if (lpa_fast == 16) { if (ev) FAST(16, true, 3); else FAST(16, false, 3); }
+      else if (lpa_fast == 32) { if (ev) FAST(32, true, 3); else FAST(32, false, 3); }
+      else { if (ev) FAST(8, true, 3); else FAST(8, false, 3); }
+    } else {
+      if (lpa_fast == 4) { if (ev) FAST(4, true, 4); else FAST(4, false, 4); }
+      else if (lpa_fast == 16) { if (ev) FAST(16, true, 4); else FAST(16, false, 4); }
+      else if (lpa_fast == 32) { if (ev) FAST(32, true, 4); else FAST(32, false, 4); }
+      else { if (ev) FAST(8, true, 4); else FAST(8, false, 4); }
+    }
+#undef FAST
+  } else {
+    PairArgs a{};
+    a.pos = c->pos.p; a.ts = c->ts.p; a.tag = c->tag.p; a.nlocal = c->nlocal;
+    a.neigh = c->neigh.p; a.stride = c->neigh_stride; a.numneigh = c->numneigh.p;
+    a.pinfo = c->d_pairinfo.p; a.tinfo = c->d_typeinfo.p; a.na = c->n_actual + 1; a.tables = c->d_tables.p;
+    for (int k = 0; k < 4; k++) a.special_lj[k] = c->special_lj[k];
+    a.inv_kT = 1.0 / c->kT;
+    a.frc = c->frc.p; a.scores = c->scores.p; a.err = c->d_err.p;
+    if (ev) rc = launch_general<8, true>(c, a, nblk); else rc = launch_general<8, false>(c, a, nblk);
+  }
+  if (rc) return rc;
+  if (timed) { cudaEventRecord(c->ev_pair1, c->stream); c->pair_timed = true; }
+  if (ev) {
+    if ((rc = reduce_partials(c, nblk, 7, 0))) return rc;
+    c->ev_valid = true;
+  }
+  return 0;
+}
+
+extern "C" int ucgb200_pair_energy_virial(ucgb200_ctx *c, double *eng_vdwl, double virial[6]) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  if (!c->ev_valid) return fail(c, "no energy/virial available: last pair call had eflag=vflag=0");
+  double h[7];
+  UCG_CHECK(c, cudaMemcpyAsync(h, c->d_ev.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  UCG_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (eng_vdwl) *eng_vdwl = h[0];
+  if (virial) for (int k = 0; k < 6; k++) virial[k] = h[1 + k];
+  return 0;
+}
+
+extern "C" int ucgb200_last_pair_ms(ucgb200_ctx *c, double *ms) {
+  if (!c || !ms) return -1;
+  if (!c->pair_timed) return fail(c, "pair timing not enabled (ucgb200_timers(ctx,1,...))");
+  UCG_CHECK(c, cudaEventSynchronize(c->ev_pair1));
+  float f = 0;
+  UCG_CHECK(c, cudaEventElapsedTime(&f, c->ev_pair0, c->ev_pair1));
+  *ms = f;
+  return 0;
+}

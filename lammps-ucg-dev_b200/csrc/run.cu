@@ -1,0 +1,226 @@
+// run.cu — device-resident time stepping: the [stock] Verlet::setup / Verlet::run call
+// order with every stage a kernel on the context stream.  The only
+// host<->device traffic per step is the 4-byte rebuild flag (Neighbor::decide needs a
+// host decision) and, on thermo steps, the 7-double energy/virial read-back.
+#include "ucg_internal.cuh"
+
+#include <cmath>
+
+using namespace ucg;
+
+extern "C" int ucgb200_deck_configure(ucgb200_ctx *c, const ucgb200_deck *deck) {
+  if (!c || !deck) return -1;
+  if (deck->pair_style < 0 || deck->pair_style > 3) return fail(c, "unknown pair style");
+  if (deck->langevin) {
+    // ctor checks of Fix_UCGLD_Langevin (fix_ucgld_langevin.cpp:80-81)
+    if (deck->t_period <= 0.0) return fail(c, "Fix langevin period must be > 0.0");
+    if (deck->langevin_seed <= 0) return fail(c, "Illegal fix langevin command");
+  }
+  if (deck->ucgstate) {
+    // FixUCGState::setup (fix_ucgstate.cpp:148-156): a fix exporting t_target must exist;
+    // inside the package that is fix ucgld/langevin, otherwise the host layer supplies kT.
+  }
+  c->deck = *deck;
+  c->deck_set = true;
+  return 0;
+}
+
+// Fix_UCGLD_Langevin::init gfactors (fix_ucgld_langevin.cpp:164-171).  The reference
+// indexes atom->ucgml with the TYPE index (quirk Q20); decks use a uniform lambda mass,
+// for which this equals the per-site value.  ml_of_type[t] must be supplied by the caller
+// of the low-level entry; the resident path reads site (t) like the reference does.
+static int langevin_factors(ucgb200_ctx *c, std::vector<double> &g1, std::vector<double> &g2) {
+  int nt = c->n_formal;
+  g1.assign(nt + 1, 0.0);
+  g2.assign(nt + 1, 0.0);
+  std::vector<double> ml(nt + 1, 0.0);
+  int nread = std::min(nt + 1, c->nlocal);
+  if (nread > 0) {
+    // ucgml[i] for i = 1..ntypes in the ORIGINAL host order == what the reference reads
+    std::vector<double> all(c->nlocal);
+    std::vector<int> orig(c->nlocal);
+    UCG_CHECK(c, cudaMemcpyAsync(all.data(), c->ucgml.p, c->nlocal * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    UCG_CHECK(c, cudaMemcpyAsync(orig.data(), c->orig.p, c->nlocal * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    UCG_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < c->nlocal; s++)
+      if (orig[s] <= nt) ml[orig[s]] = all[s];
+  }
+  for (int i = 1; i <= nt; i++) {
+    double m = (i < c->nlocal) ? ml[i] : ml[0];
+    g1[i] = -m / c->deck.t_period / c->ftm2v;
+    g2[i] = std::sqrt(m) / c->ftm2v;
+    g2[i] *= std::sqrt(24.0 * c->boltz / c->deck.t_period / c->dt / c->mvv2e);
+  }
+  return 0;
+}
+
+static double current_t_target(const ucgb200_ctx *c) {
+  // compute_target, CONSTANT style (fix_ucgld_langevin.cpp:323-331)
+  double delta = (double)(c->ntimestep - c->beginstep);
+  if (delta != 0.0) delta /= (double)(c->endstep - c->beginstep);
+  return c->deck.t_start + delta * (c->deck.t_stop - c->deck.t_start);
+}
+
+static int pair_compute(ucgb200_ctx *c, int ev) {
+  const ucgb200_deck &d = c->deck;
+  switch (d.pair_style) {
+    case 0: return ucgb200_pair_ucgld(c, ev, ev);
+    case 1: return ucgb200_pair_bethe(c, ev, ev, d.bethe_method, d.bethe_pseudo, d.bethe_prior, 0.0, 1);
+    case 2: return ucgb200_pair_rleucg(c, ev, ev);
+    default: return ucgb200_pair_bethe_density(c, ev, ev, d.bethe_method, d.bethe_pseudo);
+  }
+}
+
+struct StageTimer {
+  ucgb200_ctx *c;
+  int slot;
+  long long l0;
+  StageTimer(ucgb200_ctx *ctx, int s) : c(ctx), slot(s), l0(ctx->launches) {
+    if (c->timers_on) cudaEventRecord(c->ev_a, c->stream);
+  }
+  void stop() {
+    if (!c->timers_on) return;
+    cudaEventRecord(c->ev_b, c->stream);
+    cudaEventSynchronize(c->ev_b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
+    c->t_ms[slot] += ms;
+    if (slot != 1) c->t_launch[slot] += c->launches - l0;
+  }
+};
+
+static int post_force(ucgb200_ctx *c, bool at_setup) {
+  const ucgb200_deck &d = c->deck;
+  int rc;
+  // fixes act in definition order: langevin (thermostat) must precede ucgstate
+  // (fix_ucgstate.cpp:143-156); the wall bias belongs to the integrator fix.
+  if (d.langevin) {
+    double tt = current_t_target(c);
+    if (c->lang_g1.empty()) { if ((rc = langevin_factors(c, c->lang_g1, c->lang_g2))) return rc; }
+    if ((rc = ucgb200_fix_langevin(c, c->lang_g1.data(), c->lang_g2.data(), c->n_formal, std::sqrt(tt),
+                                   d.langevin_seed, c->ntimestep, d.langevin_groupbit ? d.langevin_groupbit : 1, 0)))
+      return rc;
+  }
+  if (d.ucgstate) {
+    int mode = d.ucgstate == 1 ? 0 : (d.ucgstate == 2 ? 1 : 2);
+    if ((rc = ucgb200_fix_ucgstate(c, mode, d.ucgstate_seed, d.ucgstate_rate, c->ntimestep))) return rc;
+  }
+  // [stock] Fix::setup() is a no-op for the wall fix, so no bias at step 0
+  if (!at_setup && d.nve == 2 && d.wall_bias) {
+    if ((rc = ucgb200_fix_wall_bias(c, d.wall_barrier, d.nve_groupbit ? d.nve_groupbit : 1))) return rc;
+  }
+  return 0;
+}
+
+extern "C" int ucgb200_setup(ucgb200_ctx *c) {
+  if (!c) return -1;
+  if (!c->deck_set) return fail(c, "deck not configured");
+  cudaSetDevice(c->device);
+  int rc;
+  if (c->deck.langevin) {
+    // pair styles and fix ucgstate take kT from the first fix exporting t_target
+    c->kT = c->boltz * c->deck.t_start;
+  }
+  c->beginstep = c->endstep = c->ntimestep;
+  if ((rc = ucgb200_neigh_build(c))) return rc;
+  c->nbuilds = 0;
+  if ((rc = pair_compute(c, 1))) return rc;
+  c->lang_g1.clear();
+  c->lang_g2.clear();
+  if ((rc = post_force(c, true))) return rc;
+  return 0;
+}
+
+extern "C" int ucgb200_run(ucgb200_ctx *c, int nsteps) {
+  if (!c || nsteps < 0) return -1;
+  if (!c->deck_set) return fail(c, "deck not configured");
+  cudaSetDevice(c->device);
+  const ucgb200_deck &d = c->deck;
+  const int gb = d.nve_groupbit ? d.nve_groupbit : 1;
+  const double dtv = c->dt, dtf = 0.5 * c->dt * c->ftm2v;  // FixNVE_UCGLD::init (fix_nve_ucgld.cpp:35-41)
+  c->beginstep = c->ntimestep;
+  c->endstep = c->ntimestep + nsteps;
+  int rc;
+  for (int n = 0; n < nsteps; n++) {
+    c->ntimestep++;
+    const int ev = d.thermo_every > 0 && (c->ntimestep % d.thermo_every == 0);
+    {
+      StageTimer t(c, 3);
+      if (d.nve) { if ((rc = ucgb200_fix_nve_initial(c, dtv, dtf, gb, d.nve == 2))) return rc; }
+      t.stop();
+    }
+    int flag = 0;
+    {
+      StageTimer t(c, 1);
+      if ((rc = ucgb200_neigh_decide(c, &flag))) return rc;
+      t.stop();
+    }
+    if (flag) { if ((rc = ucgb200_neigh_build(c))) return rc; }
+    else {
+      StageTimer t(c, 2);
+      if ((rc = ucgb200_ghosts_forward(c))) return rc;
+      t.stop();
+    }
+    {
+      StageTimer t(c, 0);
+      if ((rc = pair_compute(c, ev))) return rc;
+      t.stop();
+    }
+    {
+      StageTimer t(c, 3);
+      if ((rc = post_force(c, false))) return rc;
+      if (d.nve) { if ((rc = ucgb200_fix_nve_final(c, dtf, gb, d.nve == 2))) return rc; }
+      t.stop();
+    }
+    if (ev) {
+      double e, v[6];
+      if ((rc = ucgb200_pair_energy_virial(c, &e, v))) return rc;
+      c->thermo[0] = e;
+      for (int k = 0; k < 6; k++) c->thermo[1 + k] = v[k];
+    }
+  }
+  return 0;
+}
+
+extern "C" int ucgb200_thermo(ucgb200_ctx *c, double out[16]) {
+  if (!c || !out) return -1;
+  cudaSetDevice(c->device);
+  int rc;
+  double ke = 0, lke = 0;
+  long long cnt = 0;
+  if (c->nlocal) {
+    if ((rc = ucgb200_kinetic_energy(c, 1, &ke, &cnt))) return rc;
+    int lgb = c->deck.langevin_groupbit ? c->deck.langevin_groupbit : 1;
+    if ((rc = ucgb200_lambda_ke(c, lgb, &lke, &cnt))) return rc;
+  }
+  if (c->ev_valid) {
+    double e, v[6];
+    if ((rc = ucgb200_pair_energy_virial(c, &e, v))) return rc;
+    c->thermo[0] = e;
+    for (int k = 0; k < 6; k++) c->thermo[1 + k] = v[k];
+  }
+  for (int k = 0; k < 16; k++) out[k] = 0.0;
+  for (int k = 0; k < 7; k++) out[k] = c->thermo[k];
+  out[7] = ke;
+  out[8] = lke;
+  // Fix_UCGLD_Langevin::end_of_step (:303-312): lambda temperature, divided by nlocal
+  out[9] = c->nlocal ? lke / (0.5 * c->boltz * c->nlocal) : 0.0;
+  out[10] = (double)c->ntimestep;
+  out[11] = (double)c->nbuilds;
+  out[12] = (double)c->nlocal;
+  out[13] = (double)c->nghost;
+  return 0;
+}
+
+extern "C" int ucgb200_timers(ucgb200_ctx *c, int enable, double out_ms[4], long long out_launches[4]) {
+  if (!c) return -1;
+  if (out_ms) for (int k = 0; k < 4; k++) out_ms[k] = c->t_ms[k];
+  if (out_launches) for (int k = 0; k < 4; k++) out_launches[k] = c->t_launch[k];
+  if (enable >= 0) {
+    if (enable != (int)c->timers_on || enable == 2) {
+      for (int k = 0; k < 4; k++) { c->t_ms[k] = 0; c->t_launch[k] = 0; }
+    }
+    c->timers_on = enable != 0;
+  }
+  return 0;
+}

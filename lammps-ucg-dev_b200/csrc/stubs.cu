@@ -1,0 +1,23 @@
+// stubs.cu — entry points declared in include/ucgb200.h whose kernels are not built yet.
+// They fail loudly (never silently fall back to a CPU path).
+#include "ucg_internal.cuh"
+using namespace ucg;
+#define NOTYET(name) { if (!c) return -1; return fail(c, name ": not implemented in this build"); }
+
+extern "C" int ucgb200_pair_bethe(ucgb200_ctx *c, int, int, int, int, int, double, int) NOTYET("pair_bethe")
+extern "C" int ucgb200_pair_rleucg_configure(ucgb200_ctx *c, int, const int *, const double *, const double *, const int *, const double *, double) NOTYET("pair_rleucg_configure")
+extern "C" int ucgb200_pair_rleucg(ucgb200_ctx *c, int, int) NOTYET("pair_rleucg")
+extern "C" int ucgb200_pair_bethe_density_configure(ucgb200_ctx *c, const int *, const double *, const double *) NOTYET("pair_bethe_density_configure")
+extern "C" int ucgb200_pair_bethe_density(ucgb200_ctx *c, int, int, int, int) NOTYET("pair_bethe_density")
+extern "C" int ucgb200_cluster_configure(ucgb200_ctx *c, int, int, double, int, const int *, const int *, const double *, const double *, int, const int *, int) NOTYET("cluster_configure")
+extern "C" int ucgb200_cluster_check(ucgb200_ctx *c, int *, int *) NOTYET("cluster_check")
+extern "C" int ucgb200_cluster_switch(ucgb200_ctx *c, int, long long, int *, int *) NOTYET("cluster_switch")
+extern "C" int ucgb200_halo_configure(ucgb200_ctx *c, int, int, const int *) NOTYET("halo_configure")
+extern "C" int ucgb200_halo_send_counts(ucgb200_ctx *c, int *) NOTYET("halo_send_counts")
+extern "C" int ucgb200_halo_pack_border(ucgb200_ctx *c, int, void *) NOTYET("halo_pack_border")
+extern "C" int ucgb200_halo_set_recv_counts(ucgb200_ctx *c, const int *) NOTYET("halo_set_recv_counts")
+extern "C" int ucgb200_halo_unpack_border(ucgb200_ctx *c, int, const void *) NOTYET("halo_unpack_border")
+extern "C" int ucgb200_halo_pack_forward(ucgb200_ctx *c, int, void *) NOTYET("halo_pack_forward")
+extern "C" int ucgb200_halo_unpack_forward(ucgb200_ctx *c, int, const void *) NOTYET("halo_unpack_forward")
+extern "C" int ucgb200_neigh_build_local(ucgb200_ctx *c) NOTYET("neigh_build_local")
+extern "C" int ucgb200_neigh_build_finish(ucgb200_ctx *c) NOTYET("neigh_build_finish")

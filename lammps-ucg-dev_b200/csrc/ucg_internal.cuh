@@ -1,0 +1,279 @@
+// ucg_internal.cuh — device context and shared helpers of libucgb200.so (sm_100a only).
+//
+// HBM layout: per-site state is held as arrays of 32-byte vector
+// records so that every gather in the pair kernels is one aligned sector:
+//   pos[i]  = {x, y, z, ucgl}            owned + ghost   (the neighbor gather record)
+//   ts[i]   = type | ucgstate << 16      owned + ghost
+//   vel[i]  = {vx, vy, vz, ucgvl}        owned
+//   frc[i]  = {fx, fy, fz, ucgforce}     owned
+//   scores[i] = {s0, s1}                 owned            (ucgsoftmaxscores)
+//   ucgp, ucgml, mask, tag, molecule     scalar arrays
+// Reference schema: atom.h:180-192, atom.cpp:590-609, UCG/atom_vec_ucg.cpp:48-90.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ucgb200.h"
+
+#define UCG_NEIGHMASK 0x1FFFFFFF  // [stock] lmptype.h NEIGHMASK
+#define UCG_SBBITS 30
+
+namespace ucg {
+
+struct TableDev {
+  int style, n, tablength;
+  int nmask, nshiftbits;
+  double innersq, delta, invdelta, deltasq6, cut;
+  const double2 *ef;    // {e[i], f[i]}
+  const double2 *ef2;   // SPLINE {e2[i], f2[i]}
+  const double2 *dedf;  // BITMAP {de[i], df[i]}
+  const double2 *rd;    // BITMAP {rsq[i], drsq[i]}
+};
+
+// everything the pair kernels need about an (actual type i, actual type j) pair
+struct PairInfo {
+  double cutsq;       // cutsq[itype][jtype]  (pair_table_ucgld.cpp:213)
+  double cutneighsq;  // (sqrt(cutsq)+skin)^2  [stock Neighbor::init]
+  int ni, nj;         // n_states_per_type
+  int tab[4];         // tabindex[formal(i,a)][formal(j,b)] at [a*2+b]
+};
+struct TypeInfo {
+  int nstates;
+  int pad;
+  double dmu;   // chem_pot[formal1]-chem_pot[formal0]  (pair_table_ucgld.cpp:176)
+  double mu0, mu1;
+  double mass;  // atom->mass[type]
+};
+
+struct ErrWord {
+  int code;
+  int tag_i, tag_j;
+  int pad;
+  double rsq;
+};
+
+struct Grid {
+  double lo[3];      // origin of cell (1,1,1) == sub-domain low corner
+  double inv[3];     // 1/cell size
+  int ninner[3];     // inner cells per dim
+  int nc[3];         // ninner + 2 (one halo layer each side)
+  int ncells;
+};
+
+template <class T>
+struct Buf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n, bool keep = false, cudaStream_t st = 0) {
+    if (n <= cap) return cudaSuccess;
+    size_t ncap = n + n / 8 + 256;
+    T *q = nullptr;
+    cudaError_t e = cudaMalloc((void **)&q, ncap * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (keep && p && cap) {
+      e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return e;
+      cudaStreamSynchronize(st);
+    }
+    if (p) cudaFree(p);
+    p = q;
+    cap = ncap;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace ucg
+
+struct ucgb200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string err;
+  long long launches = 0;
+
+  // units / box / dt
+  double boltz = 1, ftm2v = 1, mvv2e = 1, dt = 0.005;
+  double boxlo[3] = {0, 0, 0}, boxhi[3] = {1, 1, 1}, prd[3] = {1, 1, 1};
+  int periodic[3] = {1, 1, 1};
+  double sublo[3] = {0, 0, 0}, subhi[3] = {1, 1, 1};
+  bool sub_set = false;
+  double special_lj[4] = {1, 1, 1, 1};
+
+  // types / tables
+  int n_actual = 0, n_formal = 0;
+  std::vector<int> n_states, formal_from, tabindex;
+  std::vector<double> chem_pot, mass, cutsq;
+  double kT = 1.0;
+  bool maps_dirty = true;
+  std::vector<ucg::TableDev> tables;
+  std::vector<void *> table_allocs;
+  ucg::Buf<ucg::TableDev> d_tables;
+  ucg::Buf<ucg::PairInfo> d_pairinfo;
+  ucg::Buf<ucg::TypeInfo> d_typeinfo;
+  bool fast_uniform = false;   // one 2-state actual type, LINEAR tables on one rsq grid
+  int fast_tab[4] = {0, 0, 0, 0};
+  ucg::Buf<double2> d_fast_table;  // interleaved rows for the shared-memory pair kernel
+  int fast_ntab = 0, fast_len = 0;
+  double max_cut = 0.0;
+
+  // atoms
+  int nlocal = 0, nghost = 0;
+  ucg::Buf<double4> pos, pos_alt, vel, vel_alt, frc, frc_alt, xhold;
+  ucg::Buf<double2> scores, scores_alt;
+  ucg::Buf<double> ucgp, ucgp_alt, ucgml, ucgml_alt;
+  ucg::Buf<int> ts, ts_alt, mask, mask_alt, tag, tag_alt, mol, mol_alt, orig, orig_alt;
+  // ghosts
+  ucg::Buf<int> ghost_owner, ghost_code;
+  ucg::Buf<long long> ghost_key;
+
+  // neighbor
+  double skin = 0.3, cut_override = 0.0, cutneighmax = 0.0;
+  ucg::Grid grid;
+  ucg::Buf<int> cell_count, cell_start, cell_cursor, gcell_count, gcell_start, order, cell_of;
+  ucg::Buf<int> scan_tmp, ghost_cnt, ghost_off;
+  ucg::Buf<int> neigh, numneigh;
+  int neigh_stride = 0;
+  bool list_valid = false;
+  int nbuilds = 0;
+  ucg::Buf<int> d_flags;  // [0] rebuild flag, [1] neighbor overflow (max row), [2] ghost total, [3] lost atoms
+  int *h_flags = nullptr; // pinned mirror
+
+  // results
+  ucg::Buf<double> d_partials, d_ev;  // block partials, final {E, v[6], ke, lke, cnt...}
+  ucg::Buf<ucg::ErrWord> d_err;
+  double h_ev[16] = {0};
+  bool ev_valid = false;
+
+  // deck / run state
+  ucgb200_deck deck{};
+  bool deck_set = false;
+  long long ntimestep = 0, beginstep = 0, endstep = 0;
+  std::vector<double> gfactor1, gfactor2;  // cache key of the last uploaded factors
+  std::vector<double> lang_g1, lang_g2;    // deck langevin factors (init(), :164-171)
+  ucg::Buf<double> d_gfac;
+  double lambda_temp = 0.0;
+  double thermo[16] = {0};
+
+  // timers
+  bool timers_on = false;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_pair0 = nullptr, ev_pair1 = nullptr;
+  double t_ms[4] = {0, 0, 0, 0};
+  long long t_launch[4] = {0, 0, 0, 0};
+  bool pair_timed = false;
+
+  // cluster switch (fix cluster_switch)
+  struct Cluster {
+    int mol_seed = 0, mol_offset = 0, max_mol = 0, n_switch = 0, n_contact_types = 0;
+    double cutoff = 0;
+    std::vector<int> type_on, type_off, contact_map;
+    std::vector<double> prob_on, prob_off;
+    ucg::Buf<int> d_label, d_label2, d_changed, d_typemap, d_contact, d_molflag;
+    ucg::Buf<double> d_prob;
+    bool set = false;
+  } cluster;
+
+  // rleucg / bethe_density configuration
+  struct Density {
+    bool set = false;
+    int n_types = 0;
+    std::vector<int> n_states_of_type, tabindex;
+    std::vector<double> threshold_radius, density_threshold, cutsq;
+    double T = 1.0;
+    ucg::Buf<double> d_prob, d_partial, d_pforce, d_cvforce;
+    ucg::Buf<int> d_tabindex;
+    ucg::Buf<double> d_cutsq;
+  } dens;
+};
+
+namespace ucg {
+
+#define UCG_CHECK(ctx, expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                    \
+      return -2;                                                                          \
+    }                                                                                     \
+  } while (0)
+
+#define UCG_LAUNCHED(ctx)                                                                 \
+  do {                                                                                    \
+    (ctx)->launches++;                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(_e) + " at " +     \
+                   __FILE__ + ":" + std::to_string(__LINE__);                             \
+      return -2;                                                                          \
+    }                                                                                     \
+  } while (0)
+
+inline int fail(ucgb200_ctx *c, const char *msg) {
+  c->err = msg;
+  return -1;
+}
+inline int nblocks(long long n, int bs) { return (int)((n + bs - 1) / bs); }
+
+// exact (non-contracted) squared distance, evaluated in the reference's order
+// delx*delx + dely*dely + delz*delz  (pair_table_ucgld.cpp:211, [stock] npair)
+__device__ __forceinline__ double rsq_exact(double dx, double dy, double dz) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ int cell_coord(double x, double lo, double inv, int nc) {
+  int c = (int)floor((x - lo) * inv) + 1;
+  return c < 0 ? 0 : (c > nc - 1 ? nc - 1 : c);
+}
+__device__ __forceinline__ int cell_index(const Grid &g, double x, double y, double z, bool owned) {
+  int ix = cell_coord(x, g.lo[0], g.inv[0], g.nc[0]);
+  int iy = cell_coord(y, g.lo[1], g.inv[1], g.nc[1]);
+  int iz = cell_coord(z, g.lo[2], g.inv[2], g.nc[2]);
+  if (owned) {  // owned atoms live in the inner cells (rounding at the faces)
+    ix = min(max(ix, 1), g.ninner[0]);
+    iy = min(max(iy, 1), g.ninner[1]);
+    iz = min(max(iz, 1), g.ninner[2]);
+  }
+  return (iz * g.nc[1] + iy) * g.nc[0] + ix;
+}
+
+// Philox4x32-10 counter-based RNG (Salmon et al. 2011): stream-independent draws keyed by
+// (seed, purpose) and counted by (tag, timestep) so results do not depend on atom order
+// or on the domain decomposition.  Replaces the sequential RanMars draws of
+// fix_ucgld_langevin.cpp:280 and fix_ucgstate.cpp:117 (statistical parity only).
+__device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3,
+                                             uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+  uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+  uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+  c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+__device__ __forceinline__ double philox_uniform(uint32_t seed, uint32_t purpose, uint32_t tag,
+                                                 unsigned long long step) {
+  uint32_t c0 = tag, c1 = (uint32_t)step, c2 = (uint32_t)(step >> 32), c3 = purpose;
+  uint32_t k0 = seed, k1 = 0x5bd1e995u ^ purpose;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  // 53-bit uniform in [0,1)
+  unsigned long long m = ((unsigned long long)(c0 >> 5) << 26) | (unsigned long long)(c1 >> 6);
+  return (double)m * (1.0 / 9007199254740992.0);
+}
+
+// host-side launchers implemented across the .cu files
+int rebuild_maps(ucgb200_ctx *c);
+int exclusive_scan(ucgb200_ctx *c, const int *in, int *out, int n, int *d_total);
+int reduce_partials(ucgb200_ctx *c, int nblocks, int nvals, int out_offset);
+
+}  // namespace ucg

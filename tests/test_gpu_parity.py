@@ -1,0 +1,308 @@
+"""GPU parity tests: the sm_100a kernels (through the C-ABI) against the CPU oracle on the
+same seeded inputs.  Tolerances are the north star's: neighbor lists and deterministic state
+assignments bit-exact, per-site forces 1e-6 relative, energy/virial 1e-8 relative."""
+import os
+
+import numpy as np
+import pytest
+
+import decks
+from decks import rel_err
+
+pytestmark = pytest.mark.gpu
+
+F_TOL = 1e-6   # forces, ucgforce, scores (relative to the largest component)
+E_TOL = 1e-8   # energy, virial
+
+
+def _liq(n, **kw):
+    from lammps_ucg_dev_b200 import synth
+    return synth.fcc_liquid(n, **kw)
+
+
+def _pair_sets(nl, n):
+    ti = np.repeat(nl["tag_i"], nl["numneigh"]).astype(np.int64)
+    return np.sort(ti * (n + 1) + nl["neigh_tags"])
+
+
+# ------------------------------------------------------------------ neighbor
+@pytest.mark.parametrize("ncell", [5, 8, (4, 6, 9)])
+def test_neighbor_list_bit_exact(pkg, fixtures, ncell):
+    liq = _liq(ncell)
+    ctx = decks.gpu_single_type(pkg, liq, fixtures)
+    ctx.neigh_build()
+    nl = ctx.neigh_download()
+    of = decks.orc_single_type(liq, fixtures, full=1)
+    of.neigh_build_all()
+    fi, fj = of.neigh_pairs()
+    n = liq.n
+    ref = np.sort(fi.astype(np.int64) * (n + 1) + fj)
+    got = _pair_sets(nl, n)
+    assert got.size == ref.size
+    assert np.array_equal(got, ref)          # identical (tag_i, tag_j) multisets
+    assert ctx.natoms() == (of.nlocal(), of.nghost())
+    # the reference's half list (newton on) is the set of unordered pairs of the same rows
+    oh = decks.orc_single_type(liq, fixtures, full=0)
+    oh.neigh_build_all()
+    hi, hj = oh.neigh_pairs()
+    half_ref = np.sort(np.minimum(hi, hj).astype(np.int64) * (n + 1) + np.maximum(hi, hj))
+    ti = np.repeat(nl["tag_i"], nl["numneigh"]).astype(np.int64)
+    tj = nl["neigh_tags"].astype(np.int64)
+    keep = ti < tj
+    half_got = np.sort(ti[keep] * (n + 1) + tj[keep])
+    assert np.array_equal(half_got, half_ref)
+
+
+def test_neighbor_rebuild_decision_matches(pkg, fixtures):
+    liq = _liq(6)
+    ctx = decks.gpu_single_type(pkg, liq, fixtures)
+    o = decks.orc_single_type(liq, fixtures)
+    ctx.neigh_build()
+    o.neigh_build_all()
+    assert ctx.neigh_decide() == 0 and o.neigh_decide() == 0
+    # move one atom by just under / just over skin/2 = 0.15
+    for d, expect in ((0.1499999, 0), (0.1500001, 1)):
+        x = liq.x.copy()
+        x[17, 1] += d
+        ctx.atoms_upload(liq.n, x=x)
+        o.set_atoms(x, liq.v, liq.type, liq.mask, liq.tag, liq.molecule, liq.ucgstate, liq.ucgl, liq.ucgvl, liq.ucgml)
+        assert ctx.neigh_decide() == expect
+        assert o.neigh_decide() == expect
+
+
+# ---------------------------------------------------------------- pair ucgld
+def _check_pair(ctx, ref, o, tol_f=F_TOL):
+    got = ctx.atoms_download(["f", "ucgforce", "ucgsoftmaxscores", "num_ucgstates"])
+    e, vir = ctx.pair_energy_virial()
+    assert rel_err(got["f"], ref["f"]) <= tol_f
+    assert rel_err(got["ucgforce"], ref["ucgforce"]) <= tol_f
+    assert rel_err(got["ucgsoftmaxscores"], ref["ucgsoftmaxscores"]) <= tol_f
+    assert np.array_equal(got["num_ucgstates"], ref["num_ucgstates"])
+    assert abs(e - o.eng_vdwl()) <= E_TOL * abs(o.eng_vdwl())
+    assert rel_err(vir, o.virial()) <= E_TOL
+    assert ctx.status()[0] == 0
+    return got
+
+
+@pytest.mark.parametrize("variant", ["fast_smem", "fast_global", "general"])
+@pytest.mark.parametrize("lpa", [4, 8, 16, 32])
+def test_pair_ucgld_single_type(pkg, fixtures, variant, lpa, monkeypatch):
+    if variant == "general" and lpa != 8:
+        pytest.skip("general kernel has one schedule")
+    monkeypatch.setenv("UCGB200_FORCE_GENERAL", "1" if variant == "general" else "0")
+    monkeypatch.setenv("UCGB200_SMEM_TABLE", "0" if variant == "fast_global" else "1")
+    monkeypatch.setenv("UCGB200_LPA", str(lpa))
+    liq = _liq(8)
+    ctx = decks.gpu_single_type(pkg, liq, fixtures)
+    ctx.neigh_build()
+    ctx.pair_ucgld(1, 1)
+    o = decks.orc_single_type(liq, fixtures)
+    ref = decks.oracle_forces(o)
+    got = _check_pair(ctx, ref, o)
+    # eflag=0 launch writes the same per-site results
+    ctx.pair_ucgld(0, 0)
+    again = ctx.atoms_download(["f", "ucgforce", "ucgsoftmaxscores"])
+    for k in again:
+        assert np.array_equal(again[k], got[k])
+
+
+def test_pair_ucgld_tablength_25000_uses_l2_path(pkg, fixtures, tmp_path):
+    """the reference's own usage comment quotes `linear 25000` (pair_table_ucg_bethe.cpp:752):
+    1.2 MB of tables cannot sit in shared memory"""
+    liq = _liq(6)
+    ctx = decks.gpu_single_type(pkg, liq, fixtures, tablength=25000)
+    ctx.neigh_build()
+    ctx.pair_ucgld(1, 1)
+    o = decks.orc_single_type(liq, fixtures, tablength=25000)
+    _check_pair(ctx, decks.oracle_forces(o), o)
+
+
+@pytest.mark.parametrize("tabstyle,tablength", [(0, 2000), (2, 1500), (3, 12)])
+def test_pair_ucgld_other_table_styles(pkg, fixtures, tabstyle, tablength):
+    liq = _liq(5)
+    ctx = decks.gpu_single_type(pkg, liq, fixtures, tabstyle=tabstyle, tablength=tablength, cut=2.4)
+    ctx.neigh_build()
+    ctx.pair_ucgld(1, 1)
+    o = decks.orc_single_type(liq, fixtures, tabstyle=tabstyle, tablength=tablength, cut=2.4)
+    _check_pair(ctx, decks.oracle_forces(o), o)
+
+
+def test_pair_ucgld_mixed_cg_ucg_types(pkg, fixtures):
+    """scenarios 1-4 (pair_table_ucgld.cpp:219-519) with the intended sj keying of scenario 2 (Q1)"""
+    liq = decks.mixed_types(_liq(6))
+    ctx = decks.gpu_mixed(pkg, liq, fixtures)
+    ctx.neigh_build()
+    ctx.pair_ucgld(1, 1)
+    o = decks.orc_mixed(liq, fixtures)
+    _check_pair(ctx, decks.oracle_forces(o), o)
+
+
+def test_pair_reports_table_inner_cutoff(pkg, fixtures):
+    liq = _liq(4)
+    liq.x[1] = liq.x[0] + np.array([0.3, 0.0, 0.0])   # r = 0.3 < table inner cutoff 0.5
+    ctx = decks.gpu_single_type(pkg, liq, fixtures)
+    ctx.neigh_build()
+    ctx.pair_ucgld(0, 0)
+    code, ti, tj, rsq = ctx.status()
+    assert code == 1 and {ti, tj} == {1, 2} and rsq == pytest.approx(0.09, rel=1e-9)
+    o = decks.orc_single_type(liq, fixtures)
+    o.neigh_build_all()
+    with pytest.raises(RuntimeError, match="Pair distance < table inner cutoff"):
+        o.pair_ucgld(0, 0)
+
+
+# --------------------------------------------------------------------- fixes
+def test_fix_kernels_teacher_forcing(pkg, fixtures):
+    liq = _liq(6)
+    rng = np.random.default_rng(3)
+    liq.ucgl = rng.uniform(-0.02, 1.02, liq.n)      # some sites outside [0,1] for the wall
+    ctx = decks.gpu_single_type(pkg, liq, fixtures)
+    o = decks.orc_single_type(liq, fixtures)
+    o.neigh_build_all(); o.force_clear(); o.pair_ucgld(0, 0)   # sets num_ucgstates
+    f = rng.normal(0, 5, (liq.n, 3)); uf = rng.normal(0, 3, liq.n); sc = rng.normal(0, 4, (liq.n, 2))
+    sc[0] = (800.0, 900.0); sc[1] = (60.0, -60.0)
+    for wall in (0, 1):
+        ctx.atoms_upload(liq.n, x=liq.x, v=liq.v, ucgl=liq.ucgl, ucgvl=liq.ucgvl, ucgstate=liq.ucgstate,
+                         f=f, ucgforce=uf, ucgsoftmaxscores=sc)
+        o.set_atoms(liq.x, liq.v, liq.type, liq.mask, liq.tag, liq.molecule, liq.ucgstate, liq.ucgl, liq.ucgvl, liq.ucgml)
+        o.pair_ucgld(0, 0)
+        o.set_forces(f, uf, sc)
+        dt = 0.002
+        ctx.fix_nve_initial(dt, 0.5 * dt, 1, wall); o.nve_initial(1, wall)
+        if wall:
+            ctx.fix_wall_bias(0.1); o.wall_bias(0.1)
+        ctx.fix_nve_final(0.5 * dt, 1, wall); o.nve_final(1, wall)
+        got = ctx.atoms_download(["x", "v", "ucgl", "ucgvl", "ucgstate", "ucgforce"])
+        ref = o.get_atoms()
+        for k in ("x", "v", "ucgl", "ucgvl", "ucgforce"):
+            assert rel_err(got[k], ref[k]) <= 1e-14, (wall, k)
+        away = np.abs(ref["ucgl"] - 0.5) > 1e-12
+        assert np.array_equal(got["ucgstate"][away], ref["ucgstate"][away])
+    # fix ucgstate, deterministic and ld
+    for mode in (0, 1):
+        ctx.atoms_upload(liq.n, ucgl=liq.ucgl, ucgstate=liq.ucgstate, ucgsoftmaxscores=sc)
+        o.set_atoms(liq.x, liq.v, liq.type, liq.mask, liq.tag, liq.molecule, liq.ucgstate, liq.ucgl, liq.ucgvl, liq.ucgml)
+        o.pair_ucgld(0, 0)
+        o.set_forces(None, None, sc)
+        ctx.fix_ucgstate(mode=mode); o.ucgstate_post_force(mode=mode)
+        got = ctx.atoms_download(["ucgp", "ucgl", "ucgstate"])
+        ref = o.get_atoms()
+        assert rel_err(got["ucgp"], ref["ucgp"]) <= 1e-10
+        assert rel_err(got["ucgl"], ref["ucgl"]) <= 1e-10
+        away = np.abs(ref["ucgp"] - 0.5) > 1e-9
+        assert away.sum() >= liq.n - 2
+        assert np.array_equal(got["ucgstate"][away], ref["ucgstate"][away])
+        assert got["ucgstate"][0] == 1   # p == 0.5 rounds half away from zero
+
+
+# --------------------------------------------------------------- trajectories
+@pytest.mark.parametrize("deck", ["C1_det", "ld_wall_bias"])
+def test_deterministic_trajectory(pkg, fixtures, deck):
+    """config 1: table_ucgld + nve/ucgld + t_target provider + ucgstate, vs the oracle's Verlet loop"""
+    liq = _liq(8)
+    nsteps = 40
+    ctx = decks.gpu_single_type(pkg, liq, fixtures)
+    o = decks.orc_single_type(liq, fixtures)
+    o.fix_ttarget(1.0)
+    if deck == "C1_det":
+        o.fix_nve(); o.fix_ucgstate(mode=0)
+        ctx.deck_configure(pair_style=0, nve=1, ucgstate=1, thermo_every=nsteps)
+    else:
+        o.fix_nve_wall(1, 1, 0.1); o.fix_ucgstate(mode=1)
+        ctx.deck_configure(pair_style=0, nve=2, wall_bias=1, wall_barrier=0.1, ucgstate=2, thermo_every=nsteps)
+    ctx.setup(); o.setup()
+    ctx.run(nsteps); o.run(nsteps, thermo_every=nsteps)
+    got = ctx.atoms_download(["x", "v", "f", "ucgl", "ucgvl", "ucgp", "ucgstate", "ucgforce"])
+    ref = o.get_atoms()
+    th = ctx.thermo()
+    assert int(th[11]) == o.nbuilds() and o.nbuilds() >= 1      # same rebuild steps
+    # wrapped coordinates: compare modulo the box
+    box = liq.box_hi - liq.box_lo
+    dx = got["x"] - ref["x"]
+    dx -= box * np.round(dx / box)
+    assert np.abs(dx).max() <= 1e-9
+    assert rel_err(got["v"], ref["v"]) <= 1e-8
+    assert rel_err(got["f"], ref["f"]) <= F_TOL
+    assert rel_err(got["ucgforce"], ref["ucgforce"]) <= F_TOL
+    assert rel_err(got["ucgl"], ref["ucgl"]) <= 1e-8
+    assert rel_err(got["ucgp"], ref["ucgp"]) <= 1e-8
+    away = np.abs(ref["ucgp"] - 0.5) > 1e-7 if deck == "C1_det" else np.abs(ref["ucgl"] - 0.5) > 1e-9
+    assert np.array_equal(got["ucgstate"][away], ref["ucgstate"][away])
+    assert abs(th[0] - o.eng_vdwl()) <= 1e-7 * abs(o.eng_vdwl())
+
+
+def test_langevin_statistics(pkg, fixtures):
+    """fix ucgld/langevin: different RNG streams by design -> statistical check: the lambda
+    temperature relaxes to the target (period 0.1 tau, 1500 steps) on both implementations"""
+    liq = _liq(8, T=0.2)            # start the lambda DOF cold: vl ~ N(0, sqrt(0.2/ml))
+    ctx = decks.gpu_single_type(pkg, liq, fixtures)
+    o = decks.orc_single_type(liq, fixtures)
+    o.fix_nve_wall(1, 0, 0.1); o.fix_langevin(1.0, 1.0, 0.1, 4711); o.fix_ucgstate(mode=1)
+    ctx.deck_configure(pair_style=0, nve=2, langevin=1, t_start=1.0, t_stop=1.0, t_period=0.1, langevin_seed=4711,
+                       ucgstate=2)
+    ctx.setup(); o.setup()
+    tg, to = [], []
+    for _ in range(15):
+        ctx.run(100); o.run(100)
+        tg.append(ctx.thermo()[9]); to.append(o.lambda_temp())
+    tg, to = np.array(tg[5:]), np.array(to[5:])
+    # 2048 sites: relative sd of one sample ~ sqrt(2/2048) = 3.1 %; 10 samples -> ~1 %; allow 5 sigma + dt bias
+    assert abs(tg.mean() - 1.0) < 0.08
+    assert abs(to.mean() - 1.0) < 0.08
+    assert abs(tg.mean() - to.mean()) < 0.06
+    # langevin force distribution: uniform noise with variance gamma2^2/12 around the drag term
+    g1 = np.array([0.0, -10.0 / 0.1, -10.0 / 0.1]); g2 = np.sqrt(10.0) * np.sqrt(24.0 / 0.1 / 0.002) * np.ones(3); g2[0] = 0
+    ctx.force_clear()
+    ctx.fix_langevin(g1, g2, 1.0, 99, 12345)
+    got = ctx.atoms_download(["ucgforce", "ucgvl"])
+    noise = (got["ucgforce"] - g1[1] * got["ucgvl"]) / g2[1]
+    assert noise.min() >= -0.5 and noise.max() < 0.5
+    assert abs(noise.mean()) < 5 * np.sqrt(1 / 12 / liq.n)
+    assert abs(noise.var() - 1 / 12) < 0.01
+
+
+def test_ucgstate_mc_statistics(pkg, fixtures):
+    """fix ucgstate mc: literal rule (Q18): state 0 with probability min(ratio,1)*rate"""
+    liq = _liq(10)
+    ctx = decks.gpu_single_type(pkg, liq, fixtures)
+    n = liq.n
+    sc = np.zeros((n, 2)); sc[:, 1] = np.log(3.0)        # p = 0.75 everywhere
+    st = (np.arange(n) % 2).astype(np.int32)
+    ctx.atoms_upload(n, ucgsoftmaxscores=sc, ucgstate=st)
+    ctx.fix_ucgstate(mode=2, seed=77, rate=0.6, step=5)
+    got = ctx.atoms_download(["ucgstate", "ucgp"])
+    assert np.allclose(got["ucgp"], 0.75)
+    # from state 0: factor = min(p/(1-p),1)*rate = 0.6 ; from state 1: (1-p)/p*rate = 0.2
+    f0 = 1.0 - got["ucgstate"][st == 0].mean()
+    f1 = 1.0 - got["ucgstate"][st == 1].mean()
+    sd = np.sqrt(0.25 / (n / 2))
+    assert abs(f0 - 0.6) < 5 * sd and abs(f1 - 0.2) < 5 * sd
+
+
+# ------------------------------------------------- full-size properties (1 M sites)
+def test_full_size_properties_1M(pkg, fixtures):
+    """BASELINE config 2 size: size-independent properties instead of an oracle run:
+    total force vanishes (Newton's 3rd law through the full list), the energy is the same
+    under two kernel schedules and through the shared-memory and L2 table paths, and every
+    site has at least the lattice coordination in its row."""
+    liq = _liq(63)
+    assert liq.n == 1000188
+    ctx = decks.gpu_single_type(pkg, liq, fixtures)
+    ctx.neigh_build()
+    total, maxrow, _ = ctx.neigh_stats()
+    assert 70 * liq.n < total < 85 * liq.n
+    res = {}
+    for lpa, smem in ((8, 1), (32, 1), (8, 0)):
+        os.environ["UCGB200_LPA"] = str(lpa); os.environ["UCGB200_SMEM_TABLE"] = str(smem)
+        ctx.pair_ucgld(1, 1)
+        res[lpa, smem] = (ctx.pair_energy_virial(), ctx.atoms_download(["f", "ucgforce"]))
+    os.environ.pop("UCGB200_LPA"); os.environ.pop("UCGB200_SMEM_TABLE")
+    (e0, v0), a0 = res[8, 1]
+    fscale = np.abs(a0["f"]).max()
+    assert np.abs(a0["f"].sum(0)).max() < 1e-9 * fscale * np.sqrt(liq.n)
+    for key in ((32, 1), (8, 0)):
+        (e, v), a = res[key]
+        assert abs(e - e0) <= 1e-11 * abs(e0)
+        assert rel_err(v, v0) <= 1e-10
+        assert rel_err(a["f"], a0["f"]) <= 1e-11
+    assert ctx.status()[0] == 0
