@@ -172,7 +172,8 @@ def run_gpu(args):
     td = tempfile.mkdtemp()
     tf, sf = make_fixtures(td)
     liq = synth.fcc_liquid(NCELL_1GPU)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream: CUDA events on it bracket every kernel
+    torch.cuda.set_stream(stream)
     ctx = pkg.Context(local, stream=stream.cuda_stream)
     engine.setup_single_type(ctx, tf, sf, tablength=TABLENGTH, cut=CUT, skin=SKIN, dt=DT, kT=1.0,
                              box=(liq.box_lo, liq.box_hi))

@@ -51,7 +51,7 @@ extern "C" int ucgb200_destroy(ucgb200_ctx *c) {
   c->cell_count.release(); c->cell_start.release(); c->cell_cursor.release();
   c->gcell_count.release(); c->gcell_start.release(); c->order.release(); c->cell_of.release();
   c->scan_tmp.release(); c->ghost_cnt.release(); c->ghost_off.release();
-  c->neigh.release(); c->numneigh.release(); c->d_flags.release();
+  c->neigh.release(); c->numneigh.release(); c->statebits.release(); c->d_flags.release();
   c->d_partials.release(); c->d_ev.release(); c->d_err.release(); c->d_gfac.release();
   c->cluster.d_label.release(); c->cluster.d_label2.release(); c->cluster.d_changed.release();
   c->cluster.d_typemap.release(); c->cluster.d_contact.release(); c->cluster.d_molflag.release();

@@ -279,13 +279,19 @@ __global__ void k_ghost_fill(double4 *__restrict__ pos, int *__restrict__ ts, do
 // stored in cell order, so each (dy,dz) row of three x-adjacent cells is one contiguous
 // index range of owned atoms plus one of ghosts; lanes test 32 candidates at a time and
 // ballot-compact the hits, which keeps every row in a deterministic order.
+// Rows are partitioned: neighbors inside the pair cutoff at build time come first (in
+// cell order), the skin shell (cut < r <= cut+skin) after them.  The pair kernels test
+// rsq < cutsq for every entry anyway; the partition only makes the outcome of that test
+// coherent across a warp (lane efficiency 77 % -> ~93 %, profiles/).
 __global__ void __launch_bounds__(256)
 k_build_rows(const double4 *__restrict__ pos, const int *__restrict__ ts, int nlocal, Grid g,
              const int *__restrict__ ostart, const int *__restrict__ gstart, const PairInfo *__restrict__ pinfo,
              int na, int *__restrict__ neigh, int stride, int *__restrict__ numneigh, int *__restrict__ flags) {
+  extern __shared__ int s_outer[];  // [warps per block][stride]
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= nlocal) return;
+  int *outer = s_outer + (threadIdx.x >> 5) * stride;
   int i = warp;
   double4 ri = pos[i];
   int ti = ts[i] & 0xffff;
@@ -293,8 +299,9 @@ k_build_rows(const double4 *__restrict__ pos, const int *__restrict__ ts, int nl
   int iy = min(max(cell_coord(ri.y, g.lo[1], g.inv[1], g.nc[1]), 1), g.ninner[1]);
   int iz = min(max(cell_coord(ri.z, g.lo[2], g.inv[2], g.nc[2]), 1), g.ninner[2]);
   int *row = neigh + (size_t)i * stride;
-  int count = 0;
+  int cnt_in = 0, cnt_out = 0;
   const PairInfo *prow = pinfo + ti * na;
+  const unsigned lt = (1u << lane) - 1;
   for (int dz = -1; dz <= 1; dz++)
     for (int dy = -1; dy <= 1; dy++) {
       int c0 = ((iz + dz) * g.nc[1] + (iy + dy)) * g.nc[0] + (ix - 1);
@@ -304,7 +311,7 @@ k_build_rows(const double4 *__restrict__ pos, const int *__restrict__ ts, int nl
         else { b = gstart[c0]; e = gstart[c0 + 3]; off = nlocal; }
         for (int base = b; base < e; base += 32) {
           int jj = base + lane;
-          bool hit = false;
+          bool hit = false, inner = false;
           int j = -1;
           if (jj < e) {
             j = jj + off;
@@ -312,20 +319,31 @@ k_build_rows(const double4 *__restrict__ pos, const int *__restrict__ ts, int nl
             int tj = ts[j] & 0xffff;
             double dx = ri.x - rj.x, dyv = ri.y - rj.y, dzv = ri.z - rj.z;
             double rsq = rsq_exact(dx, dyv, dzv);
-            hit = (j != i) && (rsq <= prow[tj].cutneighsq);
+            const PairInfo pi = prow[tj];
+            hit = (j != i) && (rsq <= pi.cutneighsq);
+            inner = hit && (rsq < pi.cutsq);
           }
-          unsigned m = __ballot_sync(0xffffffffu, hit);
-          if (hit) {
-            int p = count + __popc(m & ((1u << lane) - 1));
+          unsigned m_in = __ballot_sync(0xffffffffu, inner);
+          unsigned m_out = __ballot_sync(0xffffffffu, hit && !inner);
+          if (inner) {
+            int p = cnt_in + __popc(m_in & lt);
             if (p < stride) row[p] = j;
+          } else if (hit) {
+            int p = cnt_out + __popc(m_out & lt);
+            if (p < stride) outer[p] = j;
           }
-          count += __popc(m);
+          cnt_in += __popc(m_in);
+          cnt_out += __popc(m_out);
         }
       }
     }
+  __syncwarp();
+  const int total = cnt_in + cnt_out;
+  if (total <= stride)
+    for (int k = lane; k < cnt_out; k += 32) row[cnt_in + k] = outer[k];
   if (lane == 0) {
-    numneigh[i] = min(count, stride);
-    if (count > stride) atomicMax(&flags[1], count);
+    numneigh[i] = min(total, stride);
+    if (total > stride) atomicMax(&flags[1], total);
   }
 }
 
@@ -401,7 +419,7 @@ static int build_rows(ucgb200_ctx *c) {
     UCG_CHECK(c, c->neigh.ensure((size_t)nlocal * c->neigh_stride));
     UCG_CHECK(c, cudaMemsetAsync(c->d_flags.p + 1, 0, sizeof(int), c->stream));
     long long nthreads = (long long)nlocal * 32;
-    k_build_rows<<<nblocks(nthreads, 256), 256, 0, c->stream>>>(
+    k_build_rows<<<nblocks(nthreads, 256), 256, 8 * c->neigh_stride * sizeof(int), c->stream>>>(
         c->pos.p, c->ts.p, nlocal, c->grid, c->cell_start.p, c->gcell_start.p, c->d_pairinfo.p, na,
         c->neigh.p, c->neigh_stride, c->numneigh.p, c->d_flags.p);
     UCG_LAUNCHED(c);
@@ -454,13 +472,12 @@ extern "C" int ucgb200_neigh_build(ucgb200_ctx *c) {
   k_sort_cells<int><<<nblocks(ncells, 128), 128, 0, st>>>(c->order.p, c->cell_start.p, ncells);
   UCG_LAUNCHED(c);
   // 4. move every per-site array into cell order
-  size_t nall_cap = c->pos.cap;
-  UCG_CHECK(c, c->pos_alt.ensure(nall_cap)); UCG_CHECK(c, c->ts_alt.ensure(c->ts.cap));
-  UCG_CHECK(c, c->ucgp_alt.ensure(c->ucgp.cap)); UCG_CHECK(c, c->tag_alt.ensure(c->tag.cap));
-  UCG_CHECK(c, c->mol_alt.ensure(c->mol.cap)); UCG_CHECK(c, c->vel_alt.ensure(c->vel.cap));
-  UCG_CHECK(c, c->frc_alt.ensure(c->frc.cap)); UCG_CHECK(c, c->scores_alt.ensure(c->scores.cap));
-  UCG_CHECK(c, c->ucgml_alt.ensure(c->ucgml.cap)); UCG_CHECK(c, c->mask_alt.ensure(c->mask.cap));
-  UCG_CHECK(c, c->orig_alt.ensure(c->orig.cap));
+  UCG_CHECK(c, c->pos_alt.ensure_exact(c->pos.cap)); UCG_CHECK(c, c->ts_alt.ensure_exact(c->ts.cap));
+  UCG_CHECK(c, c->ucgp_alt.ensure_exact(c->ucgp.cap)); UCG_CHECK(c, c->tag_alt.ensure_exact(c->tag.cap));
+  UCG_CHECK(c, c->mol_alt.ensure_exact(c->mol.cap)); UCG_CHECK(c, c->vel_alt.ensure_exact(c->vel.cap));
+  UCG_CHECK(c, c->frc_alt.ensure_exact(c->frc.cap)); UCG_CHECK(c, c->scores_alt.ensure_exact(c->scores.cap));
+  UCG_CHECK(c, c->ucgml_alt.ensure_exact(c->ucgml.cap)); UCG_CHECK(c, c->mask_alt.ensure_exact(c->mask.cap));
+  UCG_CHECK(c, c->orig_alt.ensure_exact(c->orig.cap));
   PermArgs pa{c->pos.p, c->vel.p, c->frc.p, c->scores.p, c->ucgp.p, c->ucgml.p, c->ts.p, c->mask.p,
               c->tag.p, c->mol.p, c->orig.p, c->pos_alt.p, c->vel_alt.p, c->frc_alt.p, c->scores_alt.p,
               c->ucgp_alt.p, c->ucgml_alt.p, c->ts_alt.p, c->mask_alt.p, c->tag_alt.p, c->mol_alt.p,

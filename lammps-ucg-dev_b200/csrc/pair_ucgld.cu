@@ -144,6 +144,23 @@ __global__ void __launch_bounds__(BS) k_pair_ucgld(PairArgs p) {
   }
 }
 
+// 256-bit gather of one {x,y,z,lambda} record (LDG.E.256, sm_100+): one L1 request per
+// neighbor instead of two 128-bit ones.
+__device__ __forceinline__ double4 ld256(const double4 *p) {
+  double4 r;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+
+// ucgstate bits of all owned+ghost sites: the per-neighbor state gather then touches one
+// 128-byte line per 4096 sites instead of one per 32.
+__global__ void k_pack_statebits(const int *__restrict__ ts, int nall, unsigned *__restrict__ bits) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool s = i < nall && ((ts[i] >> 16) & 1);
+  unsigned m = __ballot_sync(0xffffffffu, s);
+  if ((threadIdx.x & 31) == 0 && i < nall) bits[i >> 5] = m;
+}
+
 // ------------------------------------------------------------------- fast kernel
 // One 2-state actual type, LINEAR tables on a common rsq grid (the benchmark liquids).
 // The W (3 or 4) unique tables are interleaved row-wise and staged once per CTA in shared
@@ -152,6 +169,7 @@ __global__ void __launch_bounds__(BS) k_pair_ucgld(PairArgs p) {
 struct FastArgs {
   const double4 *pos;
   const int *ts;
+  const unsigned *sbits;  // ucgstate of every owned+ghost site, 1 bit each
   const int *tag;
   int nlocal;
   const int *neigh;
@@ -168,7 +186,9 @@ struct FastArgs {
   int smem_table;  // 1: stage table in shared memory, 0: read it through L1/L2
 };
 
-template <int LPA, bool EV, int W, int BS>
+// PF = 1 software-pipelines the neighbor gathers: index and {x,y,z,lambda}/state of the
+// next neighbor are in flight while the current pair is evaluated.
+template <int LPA, bool EV, int W, int BS, int PF>
 __global__ void __launch_bounds__(BS) k_pair_ucgld_fast(FastArgs p) {
   extern __shared__ double2 s_tab[];
   const double2 *tab = p.table;
@@ -194,45 +214,57 @@ __global__ void __launch_bounds__(BS) k_pair_ucgld_fast(FastArgs p) {
     double fx = 0, fy = 0, fz = 0, accA = 0, accB = 0, S0 = 0, S1 = 0;
     double vir[6] = {0, 0, 0, 0, 0, 0};
 
-    for (int jj = sub; jj < jnum; jj += LPA) {
-      const int j = row[jj] & UCG_NEIGHMASK;
-      const double4 rj = p.pos[j];
-      const int sj = (p.ts[j] >> 16) & 1;
+    int jj = sub;
+    int j = -1, sj = 0;
+    double4 rj = ri;
+    if (jj < jnum) { j = row[jj] & UCG_NEIGHMASK; rj = ld256(p.pos + j); sj = p.sbits[j >> 5] >> (j & 31); }
+    while (j >= 0) {
+      int jn = -1, sn = 0;
+      double4 rn = rj;
+      jj += LPA;
+      if (PF) {
+        if (jj < jnum) { jn = row[jj] & UCG_NEIGHMASK; rn = ld256(p.pos + jn); sn = p.sbits[jn >> 5] >> (jn & 31); }
+      }
       const double dx = ri.x - rj.x, dy = ri.y - rj.y, dz = ri.z - rj.z;
       const double rsq = rsq_exact(dx, dy, dz);
       if (rsq < p.cutsq) {
         const int it = (int)__dmul_rn(__dadd_rn(rsq, -p.innersq), p.invdelta);
         if (rsq < p.innersq || it >= tlm1) {
           report_error(p.err, rsq < p.innersq ? UCGB200_ERR_TABLE_INNER : UCGB200_ERR_TABLE_OUTER, p.tag[i], p.tag[j], rsq);
-          continue;
-        }
-        const double rsq_it = __dadd_rn(p.innersq, __dmul_rn((double)it, p.delta));
-        const double frac = (rsq - rsq_it) * p.invdelta;
-        const double2 *r0 = tab + it * W;
-        const double2 a00 = r0[0], a01 = r0[1], a11 = r0[W - 1];
-        const double2 b00 = r0[W], b01 = r0[W + 1], b11 = r0[2 * W - 1];
-        const double u00 = a00.x + frac * (b00.x - a00.x), f00 = a00.y + frac * (b00.y - a00.y);
-        const double u01 = a01.x + frac * (b01.x - a01.x), f01 = a01.y + frac * (b01.y - a01.y);
-        const double u11 = a11.x + frac * (b11.x - a11.x), f11 = a11.y + frac * (b11.y - a11.y);
-        double u10, f10;
-        if (W == 4) {
-          const double2 a10 = r0[2], b10 = r0[W + 2];
-          u10 = a10.x + frac * (b10.x - a10.x);
-          f10 = a10.y + frac * (b10.y - a10.y);
-        } else { u10 = u01; f10 = f01; }
-        const double lj = rj.w, bj = 1.0 - lj;
-        const double A = bj * u00 + lj * u01, B = bj * u10 + lj * u11;
-        const double FA = bj * f00 + lj * f01, FB = bj * f10 + lj * f11;
-        accA += A; accB += B;
-        const double fpair = ai * FA + li * FB;
-        S0 += sj ? u01 : u00;
-        S1 += sj ? u11 : u10;
-        fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
-        if (EV) {
-          vir[0] += dx * dx * fpair; vir[1] += dy * dy * fpair; vir[2] += dz * dz * fpair;
-          vir[3] += dx * dy * fpair; vir[4] += dx * dz * fpair; vir[5] += dy * dz * fpair;
+        } else {
+          const double rsq_it = __dadd_rn(p.innersq, __dmul_rn((double)it, p.delta));
+          const double frac = (rsq - rsq_it) * p.invdelta;
+          const double2 *r0 = tab + it * W;
+          const double2 a00 = r0[0], a01 = r0[1], a11 = r0[W - 1];
+          const double2 b00 = r0[W], b01 = r0[W + 1], b11 = r0[2 * W - 1];
+          const double u00 = a00.x + frac * (b00.x - a00.x), f00 = a00.y + frac * (b00.y - a00.y);
+          const double u01 = a01.x + frac * (b01.x - a01.x), f01 = a01.y + frac * (b01.y - a01.y);
+          const double u11 = a11.x + frac * (b11.x - a11.x), f11 = a11.y + frac * (b11.y - a11.y);
+          double u10, f10;
+          if (W == 4) {
+            const double2 a10 = r0[2], b10 = r0[W + 2];
+            u10 = a10.x + frac * (b10.x - a10.x);
+            f10 = a10.y + frac * (b10.y - a10.y);
+          } else { u10 = u01; f10 = f01; }
+          const double lj = rj.w, bj = 1.0 - lj;
+          const double A = bj * u00 + lj * u01, B = bj * u10 + lj * u11;
+          const double FA = bj * f00 + lj * f01, FB = bj * f10 + lj * f11;
+          accA += A; accB += B;
+          const double fpair = ai * FA + li * FB;
+          const bool s1 = sj & 1;
+          S0 += s1 ? u01 : u00;
+          S1 += s1 ? u11 : u10;
+          fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
+          if (EV) {
+            vir[0] += dx * dx * fpair; vir[1] += dy * dy * fpair; vir[2] += dz * dz * fpair;
+            vir[3] += dx * dy * fpair; vir[4] += dx * dz * fpair; vir[5] += dy * dz * fpair;
+          }
         }
       }
+      if (!PF) {
+        if (jj < jnum) { jn = row[jj] & UCG_NEIGHMASK; rn = ld256(p.pos + jn); sn = p.sbits[jn >> 5] >> (jn & 31); }
+      }
+      j = jn; rj = rn; sj = sn;
     }
     fx = group_sum<LPA>(fx); fy = group_sum<LPA>(fy); fz = group_sum<LPA>(fz);
     accA = group_sum<LPA>(accA); accB = group_sum<LPA>(accB);
@@ -287,15 +319,14 @@ static int env_int(const char *name, int dflt) {
   return s ? atoi(s) : dflt;
 }
 
-template <int LPA, bool EV, int W>
+template <int LPA, bool EV, int W, int BS, int PF>
 static int launch_fast(ucgb200_ctx *c, FastArgs &a, int &nblk) {
-  constexpr int BS = 512;
   size_t smem = a.smem_table ? (size_t)a.tablen * W * sizeof(double2) : 0;
-  auto kern = k_pair_ucgld_fast<LPA, EV, W, BS>;
-  if (smem > 48 * 1024) UCG_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = k_pair_ucgld_fast<LPA, EV, W, BS, PF>;
+  if (smem > 32 * 1024) UCG_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
-  if (!a.smem_table) per_sm = 3;
-  else if (smem <= 100 * 1024) per_sm = 2;
+  if (!a.smem_table) per_sm = 2048 / BS > 3 ? 3 : 2048 / BS;
+  else if (smem <= 100 * 1024 && BS <= 512) per_sm = 2;
   nblk = sm_count(c->device) * per_sm;
   int groups = BS / LPA;
   int need = (a.nlocal + groups - 1) / groups;
@@ -305,6 +336,14 @@ static int launch_fast(ucgb200_ctx *c, FastArgs &a, int &nblk) {
   kern<<<nblk, BS, smem, c->stream>>>(a);
   UCG_LAUNCHED(c);
   return 0;
+}
+
+template <int LPA, int W>
+static int dispatch_fast(ucgb200_ctx *c, FastArgs &a, int &nblk, bool ev, int bs, int pf) {
+  // thermo steps are rare: one (BS, PF) variant is enough for EV
+  if (ev) return launch_fast<LPA, true, W, 512, 1>(c, a, nblk);
+  if (bs == 1024) return pf ? launch_fast<LPA, false, W, 1024, 1>(c, a, nblk) : launch_fast<LPA, false, W, 1024, 0>(c, a, nblk);
+  return pf ? launch_fast<LPA, false, W, 512, 1>(c, a, nblk) : launch_fast<LPA, false, W, 512, 0>(c, a, nblk);
 }
 
 template <int LPA, bool EV>
@@ -332,11 +371,17 @@ extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
   const bool timed = c->timers_on;
   if (timed) cudaEventRecord(c->ev_pair0, c->stream);
   const int force_general = env_int("UCGB200_FORCE_GENERAL", 0);
-  const int lpa_fast = env_int("UCGB200_LPA", 8);
+  const int lpa_fast = env_int("UCGB200_LPA", 4);
   const int smem_pref = env_int("UCGB200_SMEM_TABLE", 1);
   if (c->fast_uniform && !force_general) {
     FastArgs a{};
-    a.pos = c->pos.p; a.ts = c->ts.p; a.tag = c->tag.p; a.nlocal = c->nlocal;
+    {
+      const int nall = c->nlocal + c->nghost;
+      UCG_CHECK(c, c->statebits.ensure((size_t)nall / 32 + 8));
+      k_pack_statebits<<<nblocks(nall, 256), 256, 0, c->stream>>>(c->ts.p, nall, c->statebits.p);
+      UCG_LAUNCHED(c);
+    }
+    a.pos = c->pos.p; a.ts = c->ts.p; a.sbits = c->statebits.p; a.tag = c->tag.p; a.nlocal = c->nlocal;
     a.neigh = c->neigh.p; a.stride = c->neigh_stride; a.numneigh = c->numneigh.p;
     a.table = c->d_fast_table.p; a.tablen = c->fast_len;
     const ucg::TableDev &t0 = c->tables[c->fast_tab[0]];
@@ -347,19 +392,18 @@ extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
     a.frc = c->frc.p; a.scores = c->scores.p; a.err = c->d_err.p;
     size_t smem = (size_t)c->fast_len * c->fast_ntab * sizeof(double2);
     a.smem_table = (smem_pref && smem <= 220 * 1024) ? 1 : 0;
-#define FAST(L, E, W) rc = launch_fast<L, E, W>(c, a, nblk)
+    const int bs = env_int("UCGB200_BS", 512), pf = env_int("UCGB200_PF", 1);
     if (c->fast_ntab == 3) {
-      if (lpa_fast == 4) { if (ev) FAST(4, true, 3); else FAST(4, false, 3); }
-      else if (lpa_fast == 16) { if (ev) FAST(16, true, 3); else FAST(16, false, 3); }
-      else if (lpa_fast == 32) { if (ev) FAST(32, true, 3); else FAST(32, false, 3); }
-      else { if (ev) FAST(8, true, 3); else FAST(8, false, 3); }
+      if (lpa_fast == 4) rc = dispatch_fast<4, 3>(c, a, nblk, ev, bs, pf);
+      else if (lpa_fast == 16) rc = dispatch_fast<16, 3>(c, a, nblk, ev, bs, pf);
+      else if (lpa_fast == 32) rc = dispatch_fast<32, 3>(c, a, nblk, ev, bs, pf);
+      else rc = dispatch_fast<8, 3>(c, a, nblk, ev, bs, pf);
     } else {
-      if (lpa_fast == 4) { if (ev) FAST(4, true, 4); else FAST(4, false, 4); }
-      else if (lpa_fast == 16) { if (ev) FAST(16, true, 4); else FAST(16, false, 4); }
-      else if (lpa_fast == 32) { if (ev) FAST(32, true, 4); else FAST(32, false, 4); }
-      else { if (ev) FAST(8, true, 4); else FAST(8, false, 4); }
+      if (lpa_fast == 4) rc = dispatch_fast<4, 4>(c, a, nblk, ev, bs, pf);
+      else if (lpa_fast == 16) rc = dispatch_fast<16, 4>(c, a, nblk, ev, bs, pf);
+      else if (lpa_fast == 32) rc = dispatch_fast<32, 4>(c, a, nblk, ev, bs, pf);
+      else rc = dispatch_fast<8, 4>(c, a, nblk, ev, bs, pf);
     }
-#undef FAST
   } else {
     PairArgs a{};
     a.pos = c->pos.p; a.ts = c->ts.p; a.tag = c->tag.p; a.nlocal = c->nlocal;

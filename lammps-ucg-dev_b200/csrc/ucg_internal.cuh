@@ -84,6 +84,18 @@ struct Buf {
     cap = ncap;
     return cudaSuccess;
   }
+  // exactly n elements when growing (used for the permutation twins, which must not
+  // out-grow their partner and trigger a realloc ping-pong on every rebuild)
+  cudaError_t ensure_exact(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    T *q = nullptr;
+    cudaError_t e = cudaMalloc((void **)&q, n * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (p) cudaFree(p);
+    p = q;
+    cap = n;
+    return cudaSuccess;
+  }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -141,6 +153,7 @@ struct ucgb200_ctx {
   ucg::Buf<int> cell_count, cell_start, cell_cursor, gcell_count, gcell_start, order, cell_of;
   ucg::Buf<int> scan_tmp, ghost_cnt, ghost_off;
   ucg::Buf<int> neigh, numneigh;
+  ucg::Buf<unsigned> statebits;
   int neigh_stride = 0;
   bool list_valid = false;
   int nbuilds = 0;

@@ -1,0 +1,10 @@
+set -x
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+python scripts/profile_step.py > gpurun_out/plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python scripts/profile_step.py > gpurun_out/ncu1.log 2>&1
+tail -2 gpurun_out/plain.log
+STEPS=2 python scripts/profile_step.py > gpurun_out/plain2.log 2>&1 && \
+STEPS=2 ncu --set full --clock-control none --import-source on -k regex:k_pair_ucgld -s 1 -c 2 -o gpurun_out/prof_pair python scripts/profile_step.py > gpurun_out/ncu2.log 2>&1
+tail -3 gpurun_out/ncu2.log

@@ -155,7 +155,7 @@ def test_pair_reports_table_inner_cutoff(pkg, fixtures):
 def test_fix_kernels_teacher_forcing(pkg, fixtures):
     liq = _liq(6)
     rng = np.random.default_rng(3)
-    liq.ucgl = rng.uniform(-0.02, 1.02, liq.n)      # some sites outside [0,1] for the wall
+    liq.ucgvl = rng.normal(0, 60.0, liq.n)          # dt*vl ~ 0.12: many sites leave [0,1] -> wall
     ctx = decks.gpu_single_type(pkg, liq, fixtures)
     o = decks.orc_single_type(liq, fixtures)
     o.neigh_build_all(); o.force_clear(); o.pair_ucgld(0, 0)   # sets num_ucgstates
