@@ -608,6 +608,7 @@ class Respa : public Integrate {
  public:
   explicit Respa(LAMMPS *l) : Integrate(l) {}
   int nlevels = 1;
+  int level_inner = -1, level_middle = -1, level_outer = -1;
   double *step = nullptr;
   void copy_flevel_f(int) {}
   void copy_f_flevel(int) {}

@@ -1,0 +1,683 @@
+// ref_driver.cpp — serial harness that runs the reference's own UCG/*.cpp (compiled verbatim
+// against lammps-ucg-dev_b200/lammps_shim) in the [stock] Verlet call order.
+// TEST INFRASTRUCTURE ONLY: builds into oracle/_ref/libucg_ref.so, which pins the C
+// restatement (oracle/ucg_oracle.c), generates the golden vectors under tests/golden/ and is
+// the CPU baseline ("kind": "reference") of bench.py.  Never linked into the product.
+//
+// What is the reference's and what is ours here: every pair/fix/atom-style computation is
+// the reference's compiled source; this file only supplies what stock LAMMPS would —
+// input-line parsing, atom storage, periodic ghosts (Comm::borders/forward/reverse on one
+// rank), binned half/full neighbor lists, the skin check and the Verlet loop.
+#include <algorithm>
+#include <chrono>
+#include <memory>
+
+#include "lammps_shim.h"
+
+#include "atom_vec_ucg.h"
+#include "fix_cluster_switch.h"
+#include "fix_nve_ucgld.h"
+#include "fix_nve_ucgld_wall_hard.h"
+#include "fix_ucgld_langevin.h"
+#include "fix_ucgstate.h"
+#include "pair_table_rleucg_interface.h"
+#include "pair_table_ucg_bethe.h"
+#include "pair_table_ucg_bethe_density.h"
+#include "pair_table_ucgld.h"
+
+using namespace LAMMPS_NS;
+
+int Pair::instance_total = 0;
+
+namespace {
+
+// deterministic thermostat stand-in: exports t_target and nothing else
+class FixTTargetStub : public Fix {
+ public:
+  double t_target;
+  FixTTargetStub(LAMMPS *l, int narg, char **arg) : Fix(l, narg, arg) {
+    if (narg < 4) error->all(FLERR, "fix ttarget/stub needs a temperature");
+    t_target = utils::numeric(FLERR, arg[3], false, l);
+  }
+  int setmask() override { return 0; }
+  void *extract(const char *str, int &dim) override {
+    dim = 0;
+    if (strcmp(str, "t_target") == 0) return &t_target;
+    return nullptr;
+  }
+};
+
+double now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct Sim {
+  LAMMPS lmp;
+  std::string err;
+  std::vector<int> ghost_owner;
+  std::vector<double> ghost_shift;
+  std::vector<double> xhold;
+  int nbuilds = 0;
+  double timers[4] = {0, 0, 0, 0};
+  std::vector<Fix *> owned_fixes;
+  bool initialized = false;
+  int eflag_last = 0;
+
+  Sim() {
+    lmp.memory = new Memory();
+    lmp.error = new Error();
+    lmp.group = new Group(&lmp);
+    lmp.atom = new Atom(&lmp);
+    lmp.force = new Force(&lmp);
+    lmp.update = new Update(&lmp);
+    lmp.update->integrate = new Integrate(&lmp);
+    lmp.modify = new Modify(&lmp);
+    lmp.neighbor = new Neighbor(&lmp);
+    lmp.comm = new Comm(&lmp);
+    lmp.domain = new Domain(&lmp);
+    lmp.input = new Input(&lmp);
+    lmp.output = new Output(&lmp);
+    lmp.atom->avec = new AtomVecUCG(&lmp);
+    // units lj
+    lmp.force->boltz = lmp.force->ftm2v = lmp.force->mvv2e = 1.0;
+    lmp.force->special_lj[1] = lmp.force->special_lj[2] = lmp.force->special_lj[3] = 0.0;
+    lmp.domain->hook_arg = this;
+    lmp.domain->pbc_hook = [](void *a) { ((Sim *)a)->pbc(); };
+    lmp.neighbor->hook_arg = this;
+    lmp.neighbor->build_hook = [](void *a, int) { ((Sim *)a)->build_all(); };
+    lmp.neighbor->build_one_hook = [](void *a, NeighList *l) { ((Sim *)a)->build_list(l); };
+    auto &h = lmp.comm->hooks;
+    h.arg = this;
+    h.forward = [](void *a) { ((Sim *)a)->forward_comm(); };
+    h.reverse = [](void *a) { ((Sim *)a)->reverse_comm(); };
+    h.forward_pair = [](void *a, Pair *p) { ((Sim *)a)->forward_comm_pair(p); };
+    h.reverse_pair = [](void *a, Pair *p) { ((Sim *)a)->reverse_comm_pair(p); };
+    h.forward_fix = [](void *a, Fix *f) { ((Sim *)a)->forward_comm_fix(f); };
+    h.exchange = [](void *) {};
+    h.borders = [](void *a) { ((Sim *)a)->borders(); };
+  }
+  ~Sim() {
+    for (auto f : owned_fixes) delete f;
+    delete lmp.force->pair;
+    delete lmp.atom->avec;
+    delete lmp.output; delete lmp.input; delete lmp.domain; delete lmp.comm; delete lmp.neighbor;
+    delete lmp.modify; delete lmp.update->integrate; delete lmp.update; delete lmp.force;
+    free_atoms();
+    delete lmp.atom; delete lmp.group; delete lmp.error; delete lmp.memory;
+  }
+
+  // ---------------------------------------------------------------- atom storage
+  void free_atoms() {
+    Atom *a = lmp.atom;
+    Memory *m = lmp.memory;
+    m->destroy(a->x); m->destroy(a->v); m->destroy(a->f);
+    m->destroy(a->tag); m->destroy(a->type); m->destroy(a->mask); m->destroy(a->molecule); m->destroy(a->q);
+    m->destroy(a->ucgstate); m->destroy(a->num_ucgstates); m->destroy(a->ucgl); m->destroy(a->ucgvl);
+    m->destroy(a->ucgml); m->destroy(a->ucgp); m->destroy(a->ucgforce); m->destroy(a->ucgsoftmaxscores);
+    m->destroy(a->num_bond); m->destroy(a->num_angle); m->destroy(a->num_dihedral); m->destroy(a->num_improper);
+    m->destroy(a->nspecial);
+    delete[] a->mass; a->mass = nullptr;
+  }
+  void grow(int nmax) {
+    Atom *a = lmp.atom;
+    if (nmax <= a->nmax) return;
+    nmax = nmax + nmax / 4 + 1024;
+    Memory *m = lmp.memory;
+    m->grow(a->x, nmax, 3, "x"); m->grow(a->v, nmax, 3, "v"); m->grow(a->f, nmax, 3, "f");
+    m->grow(a->tag, nmax, "tag"); m->grow(a->type, nmax, "type"); m->grow(a->mask, nmax, "mask");
+    m->grow(a->molecule, nmax, "molecule"); m->grow(a->q, nmax, "q");
+    m->grow(a->ucgstate, nmax, "ucgstate"); m->grow(a->num_ucgstates, nmax, "num_ucgstates");
+    m->grow(a->ucgl, nmax, "ucgl"); m->grow(a->ucgvl, nmax, "ucgvl"); m->grow(a->ucgml, nmax, "ucgml");
+    m->grow(a->ucgp, nmax, "ucgp"); m->grow(a->ucgforce, nmax, "ucgforce");
+    m->grow(a->ucgsoftmaxscores, nmax, a->max_ucgstates, "scores");
+    m->grow(a->num_bond, nmax, "nb"); m->grow(a->num_angle, nmax, "na"); m->grow(a->num_dihedral, nmax, "nd");
+    m->grow(a->num_improper, nmax, "ni"); m->grow(a->nspecial, nmax, 3, "nspecial");
+    for (int i = a->nmax; i < nmax; i++) {
+      a->ucgforce[i] = 0; a->ucgsoftmaxscores[i][0] = a->ucgsoftmaxscores[i][1] = 0; a->num_ucgstates[i] = 0;
+      a->ucgp[i] = 0; a->ucgvl[i] = 0; a->ucgml[i] = 1; a->q[i] = 0;
+      for (int d = 0; d < 3; d++) a->f[i][d] = a->v[i][d] = 0;
+    }
+    a->nmax = nmax;
+    a->avec->grow_pointers();
+  }
+
+  // ---------------------------------------------------------------- domain / comm
+  double cutghost() const {
+    double c = lmp.force->pair ? lmp.force->pair->cutforce : 0.0;
+    for (auto r : lmp.neighbor->requests) if (r->cut) c = std::max(c, r->cutoff);
+    return c + lmp.neighbor->skin;
+  }
+  void pbc() {  // [stock] Domain::pbc, orthogonal periodic box
+    Atom *a = lmp.atom;
+    Domain *d = lmp.domain;
+    for (int i = 0; i < a->nlocal; i++)
+      for (int k = 0; k < 3; k++) {
+        double &x = a->x[i][k];
+        if (x < d->boxlo[k]) x += d->prd[k];
+        if (x >= d->boxhi[k]) { x -= d->prd[k]; x = std::max(x, d->boxlo[k]); }
+      }
+  }
+  void borders() {  // [stock] CommBrick::borders on one rank, fields_border of AtomVecUCG
+    Atom *a = lmp.atom;
+    Domain *d = lmp.domain;
+    double cg = cutghost();
+    lmp.neighbor->cutneighmax = cg;
+    a->nghost = 0;
+    ghost_owner.clear();
+    ghost_shift.clear();
+    for (int dim = 0; dim < 3; dim++) {
+      int nlast = a->nlocal + a->nghost;
+      for (int side = 0; side < 2; side++) {
+        double lo = side == 0 ? -1e300 : d->boxhi[dim] - cg;
+        double hi = side == 0 ? d->boxlo[dim] + cg : 1e300;
+        double shift = side == 0 ? 1.0 : -1.0;
+        for (int i = 0; i < nlast; i++) {
+          double xi = a->x[i][dim];
+          if (xi >= lo && xi <= hi) {
+            int g = a->nlocal + a->nghost;
+            grow(g + 1);
+            for (int k = 0; k < 3; k++) a->x[g][k] = a->x[i][k];
+            a->x[g][dim] = a->x[i][dim] + shift * d->prd[dim];
+            int gi = i - a->nlocal;
+            ghost_owner.push_back(i < a->nlocal ? i : ghost_owner[gi]);
+            for (int k = 0; k < 3; k++) ghost_shift.push_back(i < a->nlocal ? 0.0 : ghost_shift[3 * gi + k]);
+            ghost_shift[3 * (g - a->nlocal) + dim] = shift;
+            a->tag[g] = a->tag[i]; a->type[g] = a->type[i]; a->mask[g] = a->mask[i];
+            a->q[g] = a->q[i]; a->molecule[g] = a->molecule[i];
+            a->ucgstate[g] = a->ucgstate[i]; a->num_ucgstates[g] = a->num_ucgstates[i];
+            a->ucgl[g] = a->ucgl[i]; a->ucgp[g] = a->ucgp[i];
+            a->nghost++;
+          }
+        }
+      }
+    }
+  }
+  void forward_comm() {  // x + fields_comm {ucgstate, ucgl, ucgp}
+    Atom *a = lmp.atom;
+    Domain *d = lmp.domain;
+    for (int g = 0; g < a->nghost; g++) {
+      int o = ghost_owner[g], k = a->nlocal + g;
+      for (int c = 0; c < 3; c++) {
+        double sh = ghost_shift[3 * g + c];
+        a->x[k][c] = sh == 0.0 ? a->x[o][c] : a->x[o][c] + sh * d->prd[c];
+      }
+      a->ucgstate[k] = a->ucgstate[o]; a->ucgl[k] = a->ucgl[o]; a->ucgp[k] = a->ucgp[o];
+    }
+  }
+  void reverse_comm() {  // f + fields_reverse {ucgforce, ucgsoftmaxscores}
+    Atom *a = lmp.atom;
+    for (int g = a->nghost - 1; g >= 0; g--) {
+      int o = ghost_owner[g], k = a->nlocal + g;
+      for (int c = 0; c < 3; c++) a->f[o][c] += a->f[k][c];
+      a->ucgforce[o] += a->ucgforce[k];
+      a->ucgsoftmaxscores[o][0] += a->ucgsoftmaxscores[k][0];
+      a->ucgsoftmaxscores[o][1] += a->ucgsoftmaxscores[k][1];
+    }
+  }
+  // Pair/Fix forward/reverse through the style's own pack/unpack callbacks, one ghost at a time
+  void forward_comm_pair(Pair *p) {
+    Atom *a = lmp.atom;
+    int n = std::max(p->comm_forward, 1);
+    std::vector<double> buf(n + 8);
+    int pbc[3] = {0, 0, 0};
+    for (int g = 0; g < a->nghost; g++) {
+      int o = ghost_owner[g];
+      p->pack_forward_comm(1, &o, buf.data(), 0, pbc);
+      p->unpack_forward_comm(1, a->nlocal + g, buf.data());
+    }
+  }
+  void reverse_comm_pair(Pair *p) {
+    Atom *a = lmp.atom;
+    int n = std::max(p->comm_reverse, 1);
+    std::vector<double> buf(n + 8);
+    for (int g = a->nghost - 1; g >= 0; g--) {
+      int o = ghost_owner[g];
+      p->pack_reverse_comm(1, a->nlocal + g, buf.data());
+      p->unpack_reverse_comm(1, &o, buf.data());
+    }
+  }
+  void forward_comm_fix(Fix *f) {
+    Atom *a = lmp.atom;
+    int n = std::max(f->comm_forward, 1);
+    std::vector<double> buf(n + 8);
+    int pbc[3] = {0, 0, 0};
+    for (int g = 0; g < a->nghost; g++) {
+      int o = ghost_owner[g];
+      f->pack_forward_comm(1, &o, buf.data(), 0, pbc);
+      f->unpack_forward_comm(1, a->nlocal + g, buf.data());
+    }
+  }
+
+  // ---------------------------------------------------------------- neighbor lists
+  // [stock] NBinStandard + NStencil + NPair{Half,Full}Bin(Newton), same construction as
+  // oracle/ucg_oracle.c:orc_neigh_build
+  void build_list(NeighList *list) {
+    Atom *a = lmp.atom;
+    Domain *d = lmp.domain;
+    int nlocal = a->nlocal, nall = a->nlocal + a->nghost;
+    double skin = lmp.neighbor->skin;
+    double cutneigh = cutghost();
+    double **cutsq = lmp.force->pair->cutsq;
+    double req_cut = 0.0;
+    for (auto r : lmp.neighbor->requests) if (r->list == list && r->cut) req_cut = r->cutoff;
+    double binsize = 0.5 * cutneigh;
+    int mbin[3], mbinlo[3];
+    double bininv[3];
+    for (int k = 0; k < 3; k++) {
+      int nbin = (int)(d->prd[k] / binsize);
+      if (nbin == 0) nbin = 1;
+      bininv[k] = 1.0 / (d->prd[k] / nbin);
+      double lo = d->boxlo[k] - cutneigh - 1e-6 * d->prd[k], hi = d->boxhi[k] + cutneigh + 1e-6 * d->prd[k];
+      mbinlo[k] = (int)floor((lo - d->boxlo[k]) * bininv[k]) - 1;
+      int mbinhi = (int)floor((hi - d->boxlo[k]) * bininv[k]) + 1;
+      mbin[k] = mbinhi - mbinlo[k] + 1;
+    }
+    long long mbins = (long long)mbin[0] * mbin[1] * mbin[2];
+    std::vector<int> binhead(mbins, -1), bins(nall), atom2bin(nall);
+    auto coord2bin = [&](const double *x) {
+      int ib[3];
+      for (int k = 0; k < 3; k++) {
+        ib[k] = (int)floor((x[k] - d->boxlo[k]) * bininv[k]) - mbinlo[k];
+        ib[k] = std::min(std::max(ib[k], 0), mbin[k] - 1);
+      }
+      return (ib[2] * mbin[1] + ib[1]) * mbin[0] + ib[0];
+    };
+    for (int i = nall - 1; i >= nlocal; i--) { int b = coord2bin(a->x[i]); atom2bin[i] = b; bins[i] = binhead[b]; binhead[b] = i; }
+    for (int i = nlocal - 1; i >= 0; i--) { int b = coord2bin(a->x[i]); atom2bin[i] = b; bins[i] = binhead[b]; binhead[b] = i; }
+    int s[3];
+    for (int k = 0; k < 3; k++) { s[k] = (int)(cutneigh * bininv[k]); if (s[k] / bininv[k] < cutneigh) s[k]++; }
+    std::vector<int> stencil;
+    const bool full = list->full;
+    for (int k = (full ? -s[2] : 0); k <= s[2]; k++)
+      for (int j = -s[1]; j <= s[1]; j++)
+        for (int i = -s[0]; i <= s[0]; i++) {
+          if (!full && !(k > 0 || j > 0 || (j == 0 && i > 0))) continue;
+          if (full && i == 0 && j == 0 && k == 0) continue;
+          double dx = i > 0 ? (i - 1) / bininv[0] : (i == 0 ? 0.0 : (i + 1) / bininv[0]);
+          double dy = j > 0 ? (j - 1) / bininv[1] : (j == 0 ? 0.0 : (j + 1) / bininv[1]);
+          double dz = k > 0 ? (k - 1) / bininv[2] : (k == 0 ? 0.0 : (k + 1) / bininv[2]);
+          if (dx * dx + dy * dy + dz * dz < cutneigh * cutneigh) stencil.push_back((k * mbin[1] + j) * mbin[0] + i);
+        }
+    list->store_ilist.resize(nlocal);
+    list->store_num.resize(nlocal);
+    list->store_neigh.clear();
+    std::vector<size_t> first(nlocal);
+    double **x = a->x;
+    int *type = a->type;
+    auto within = [&](int i, int j) {
+      double delx = x[i][0] - x[j][0], dely = x[i][1] - x[j][1], delz = x[i][2] - x[j][2];
+      double rsq = delx * delx + dely * dely + delz * delz;
+      double c = req_cut > 0.0 ? req_cut + skin : sqrt(cutsq[type[i]][type[j]]) + skin;
+      return rsq <= c * c;
+    };
+    for (int i = 0; i < nlocal; i++) {
+      first[i] = list->store_neigh.size();
+      list->store_ilist[i] = i;
+      for (int j = full ? binhead[atom2bin[i]] : bins[i]; j >= 0; j = bins[j]) {
+        if (full) { if (j == i) continue; }
+        else if (j >= nlocal) {
+          if (x[j][2] < x[i][2]) continue;
+          if (x[j][2] == x[i][2]) {
+            if (x[j][1] < x[i][1]) continue;
+            if (x[j][1] == x[i][1] && x[j][0] < x[i][0]) continue;
+          }
+        }
+        if (within(i, j)) list->store_neigh.push_back(j);
+      }
+      for (int st : stencil)
+        for (int j = binhead[atom2bin[i] + st]; j >= 0; j = bins[j])
+          if (within(i, j)) list->store_neigh.push_back(j);
+      list->store_num[i] = (int)(list->store_neigh.size() - first[i]);
+    }
+    list->store_first.resize(nall);
+    for (int i = 0; i < nlocal; i++) list->store_first[i] = list->store_neigh.data() + first[i];
+    list->inum = nlocal;
+    list->ilist = list->store_ilist.data();
+    list->numneigh = list->store_num.data();
+    list->firstneigh = list->store_first.data();
+  }
+  void build_all() {
+    for (auto r : lmp.neighbor->requests) build_list(r->list);
+    Atom *a = lmp.atom;
+    xhold.resize(3 * (size_t)a->nlocal);
+    for (int i = 0; i < a->nlocal; i++)
+      for (int k = 0; k < 3; k++) xhold[3 * i + k] = a->x[i][k];
+    lmp.neighbor->ago = 0;
+    nbuilds++;
+  }
+  int decide() {  // [stock] Neighbor::decide + check_distance, delay 0 every 1 check yes
+    lmp.neighbor->ago++;
+    for (int i = 0; i < lmp.modify->nfix; i++)
+      if (lmp.modify->fix[i]->force_reneighbor && lmp.update->ntimestep == lmp.modify->fix[i]->next_reneighbor) return 1;
+    Atom *a = lmp.atom;
+    double trig = 0.25 * lmp.neighbor->skin * lmp.neighbor->skin;
+    for (int i = 0; i < a->nlocal; i++) {
+      double delx = a->x[i][0] - xhold[3 * i], dely = a->x[i][1] - xhold[3 * i + 1], delz = a->x[i][2] - xhold[3 * i + 2];
+      if (delx * delx + dely * dely + delz * delz > trig) return 1;
+    }
+    return 0;
+  }
+
+  // ---------------------------------------------------------------- Verlet
+  void force_clear() {  // [stock] Verlet::force_clear with avec->forceclearflag
+    Atom *a = lmp.atom;
+    size_t n = a->nlocal + (lmp.force->newton ? a->nghost : 0);
+    if (n) {
+      memset(&a->f[0][0], 0, 3 * n * sizeof(double));
+      if (a->avec->forceclearflag) a->avec->force_clear(0, n * sizeof(double));
+    }
+  }
+  void init() {
+    if (initialized) return;
+    if (!lmp.force->pair) lmp.error->all(FLERR, "no pair style defined");
+    lmp.force->pair->init();
+    for (int i = 0; i < lmp.modify->nfix; i++) lmp.modify->fix[i]->init();
+    for (auto r : lmp.neighbor->requests) {
+      if (r->pair) ((Pair *)r->requestor)->init_list(r->id, r->list);
+      else ((Fix *)r->requestor)->init_list(r->id, r->list);
+    }
+    initialized = true;
+  }
+  void ev_flags(int ev, int &eflag, int &vflag) {
+    eflag = ev ? 1 : 0;
+    vflag = ev ? (lmp.force->newton_pair ? 2 : 1) : 0;  // VIRIAL_FDOTR : VIRIAL_PAIR
+    eflag_last = eflag;
+  }
+  void compute_forces(int ev) {
+    int eflag, vflag;
+    ev_flags(ev, eflag, vflag);
+    force_clear();
+    lmp.force->pair->compute(eflag, vflag);
+    if (lmp.force->newton) reverse_comm();
+  }
+  void setup(int ev) {
+    lmp.update->whichflag = 1;
+    init();
+    lmp.update->beginstep = lmp.update->firststep = lmp.update->ntimestep;
+    lmp.update->endstep = lmp.update->laststep = lmp.update->ntimestep;
+    for (int i = 0; i < lmp.modify->nfix; i++) if (lmp.modify->fmask[i] & FixConst::PRE_EXCHANGE) lmp.modify->fix[i]->setup_pre_exchange();
+    pbc();
+    borders();
+    build_all();
+    nbuilds = 0;
+    compute_forces(ev);
+    for (int i = 0; i < lmp.modify->nfix; i++) lmp.modify->fix[i]->setup(ev ? 1 : 0);
+  }
+  void run(int nsteps, int thermo_every) {
+    Update *u = lmp.update;
+    Modify *m = lmp.modify;
+    u->beginstep = u->firststep = u->ntimestep;
+    u->endstep = u->laststep = u->ntimestep + nsteps;
+    for (int k = 0; k < 4; k++) timers[k] = 0;
+    for (int n = 0; n < nsteps; n++) {
+      u->ntimestep++;
+      int ev = thermo_every > 0 && (u->ntimestep % thermo_every == 0);
+      double t0 = now();
+      for (int i = 0; i < m->nfix; i++) if (m->fmask[i] & FixConst::INITIAL_INTEGRATE) m->fix[i]->initial_integrate(ev);
+      double t1 = now();
+      timers[3] += t1 - t0;
+      int nflag = decide();
+      double t2 = now();
+      timers[1] += t2 - t1;
+      if (nflag == 0) {
+        forward_comm();
+        timers[2] += now() - t2;
+      } else {
+        for (int i = 0; i < m->nfix; i++) if (m->fmask[i] & FixConst::PRE_EXCHANGE) m->fix[i]->pre_exchange();
+        pbc();
+        borders();
+        double t3 = now();
+        timers[2] += t3 - t2;
+        build_all();
+        timers[1] += now() - t3;
+      }
+      double t4 = now();
+      int eflag, vflag;
+      ev_flags(ev, eflag, vflag);
+      force_clear();
+      lmp.force->pair->compute(eflag, vflag);
+      double t5 = now();
+      timers[0] += t5 - t4;
+      if (lmp.force->newton) reverse_comm();
+      double t6 = now();
+      timers[2] += t6 - t5;
+      for (int i = 0; i < m->nfix; i++) if (m->fmask[i] & FixConst::POST_FORCE) m->fix[i]->post_force(ev);
+      for (int i = 0; i < m->nfix; i++) if (m->fmask[i] & FixConst::FINAL_INTEGRATE) m->fix[i]->final_integrate();
+      for (int i = 0; i < m->nfix; i++) if (m->fmask[i] & FixConst::END_OF_STEP) m->fix[i]->end_of_step();
+      timers[3] += now() - t6;
+    }
+  }
+
+  // ---------------------------------------------------------------- input lines
+  void command(const std::string &line) {
+    std::vector<std::string> w;
+    {
+      std::istringstream is(line);
+      std::string t;
+      while (is >> t) w.push_back(t);
+    }
+    if (w.empty()) return;
+    std::vector<char *> arg;
+    for (size_t i = 1; i < w.size(); i++) arg.push_back(const_cast<char *>(w[i].c_str()));
+    int narg = (int)arg.size();
+    const std::string &cmd = w[0];
+    if (cmd == "pair_style") {
+      delete lmp.force->pair;
+      lmp.force->pair = nullptr;
+      initialized = false;
+      const std::string &st = w.at(1);
+      Pair *p = nullptr;
+      if (st == "table_ucgld") p = new PairTable_UCGLD(&lmp);
+      else if (st == "table_ucg_bethe") p = new PairTable_UCG_Bethe(&lmp);
+      else if (st == "table_ucg_bethe_density") p = new PairTable_UCG_Bethe_Density(&lmp);
+      else if (st == "table_rleucg_interface") p = new PairTable_RLEUCG_INTERFACE(&lmp);
+      else lmp.error->all(FLERR, "Unrecognized pair style '{}'", st);
+      lmp.force->pair = p;
+      p->settings(narg - 1, arg.data() + 1);
+    } else if (cmd == "pair_coeff") {
+      if (!lmp.force->pair) lmp.error->all(FLERR, "Pair_coeff command before pair_style is defined");
+      lmp.force->pair->coeff(narg, arg.data());
+    } else if (cmd == "fix") {
+      const std::string &st = w.at(3);
+      Fix *f = nullptr;
+      if (st == "ucgstate") f = new FixUCGState(&lmp, narg, arg.data());
+      else if (st == "nve/ucgld") f = new FixNVE_UCGLD(&lmp, narg, arg.data());
+      else if (st == "nve/ucgld/wall/hard") f = new FixNVE_UCGLD_Wall_Hard(&lmp, narg, arg.data());
+      else if (st == "ucgld/langevin") f = new Fix_UCGLD_Langevin(&lmp, narg, arg.data());
+      else if (st == "cluster_switch") f = new FixClusterSwitch(&lmp, narg, arg.data());
+      else if (st == "ttarget/stub") f = new FixTTargetStub(&lmp, narg, arg.data());
+      else lmp.error->all(FLERR, "Unrecognized fix style '{}'", st);
+      owned_fixes.push_back(f);
+      lmp.modify->add(f);
+      initialized = false;
+    } else if (cmd == "neighbor") {
+      lmp.neighbor->skin = utils::numeric(FLERR, w.at(1), false, &lmp);
+    } else if (cmd == "timestep") {
+      lmp.update->dt = utils::numeric(FLERR, w.at(1), false, &lmp);
+    } else if (cmd == "newton") {
+      lmp.force->newton = lmp.force->newton_pair = lmp.force->newton_bond = (w.at(1) == "on");
+    } else if (cmd == "special_bonds") {
+      for (int k = 1; k <= 3; k++) lmp.force->special_lj[k] = utils::numeric(FLERR, w.at(k), false, &lmp);
+    } else if (cmd == "mass") {
+      int t = utils::inumeric(FLERR, w.at(1), false, &lmp);
+      if (t < 1 || t > lmp.atom->ntypes) lmp.error->all(FLERR, "Invalid type for mass set");
+      lmp.atom->mass[t] = utils::numeric(FLERR, w.at(2), false, &lmp);
+    } else
+      lmp.error->all(FLERR, "Unknown command: {}", line);
+  }
+};
+
+template <class F>
+int guarded(Sim *s, F &&f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception &e) {
+    s->err = e.what();
+    return 1;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+void *ref_create() { return new Sim(); }
+void ref_destroy(void *h) { delete (Sim *)h; }
+const char *ref_error(void *h) { return ((Sim *)h)->err.c_str(); }
+void ref_clear_error(void *h) { ((Sim *)h)->err.clear(); }
+int ref_nwarnings(void *h) { return (int)((Sim *)h)->lmp.error->warnings.size(); }
+
+int ref_box(void *h, const double *lo, const double *hi, int ntypes) {
+  Sim *s = (Sim *)h;
+  return guarded(s, [&] {
+    Domain *d = s->lmp.domain;
+    for (int k = 0; k < 3; k++) {
+      d->boxlo[k] = d->sublo[k] = lo[k]; d->boxhi[k] = d->subhi[k] = hi[k]; d->prd[k] = hi[k] - lo[k];
+    }
+    d->xprd = d->prd[0]; d->yprd = d->prd[1]; d->zprd = d->prd[2];
+    s->lmp.atom->ntypes = ntypes;
+    delete[] s->lmp.atom->mass;
+    s->lmp.atom->mass = new double[ntypes + 1];
+    for (int t = 0; t <= ntypes; t++) s->lmp.atom->mass[t] = 1.0;
+  });
+}
+
+// read_data equivalent: columns of fields_data_atom / fields_data_vel (atom_vec_ucg.cpp:87-90),
+// then AtomVecUCG::data_atom_post per atom
+int ref_atoms(void *h, int n, const double *x, const double *v, const int *type, const int *mask, const int *tag,
+              const int *molecule, const int *ucgstate, const double *ucgl, const double *ucgvl, const double *ucgml,
+              const double *ucgp) {
+  Sim *s = (Sim *)h;
+  return guarded(s, [&] {
+    Atom *a = s->lmp.atom;
+    s->grow(n);
+    a->nlocal = n; a->nghost = 0; a->natoms = n;
+    for (int i = 0; i < n; i++) {
+      for (int k = 0; k < 3; k++) { a->x[i][k] = x[3 * i + k]; a->v[i][k] = v ? v[3 * i + k] : 0.0; a->f[i][k] = 0.0; }
+      a->type[i] = type[i]; a->mask[i] = mask ? mask[i] : 1; a->tag[i] = tag ? tag[i] : i + 1;
+      a->molecule[i] = molecule ? molecule[i] : 0; a->q[i] = 0.0;
+      a->ucgstate[i] = ucgstate ? ucgstate[i] : 0; a->ucgl[i] = ucgl ? ucgl[i] : 0.0;
+      a->ucgvl[i] = ucgvl ? ucgvl[i] : 0.0; a->ucgml[i] = ucgml ? ucgml[i] : 1.0;
+      a->ucgforce[i] = 0.0; a->ucgsoftmaxscores[i][0] = a->ucgsoftmaxscores[i][1] = 0.0; a->num_ucgstates[i] = 0;
+      a->avec->data_atom_post(i);
+      if (ucgp) a->ucgp[i] = ucgp[i];
+    }
+  });
+}
+// overwrite dynamic state without re-running data_atom_post (teacher forcing)
+int ref_set_state(void *h, const double *x, const double *v, const int *ucgstate, const double *ucgl, const double *ucgvl,
+                  const double *ucgp, const double *f, const double *ucgforce, const double *scores) {
+  Sim *s = (Sim *)h;
+  return guarded(s, [&] {
+    Atom *a = s->lmp.atom;
+    for (int i = 0; i < a->nlocal; i++) {
+      for (int k = 0; k < 3; k++) {
+        if (x) a->x[i][k] = x[3 * i + k];
+        if (v) a->v[i][k] = v[3 * i + k];
+        if (f) a->f[i][k] = f[3 * i + k];
+      }
+      if (ucgstate) a->ucgstate[i] = ucgstate[i];
+      if (ucgl) a->ucgl[i] = ucgl[i];
+      if (ucgvl) a->ucgvl[i] = ucgvl[i];
+      if (ucgp) a->ucgp[i] = ucgp[i];
+      if (ucgforce) a->ucgforce[i] = ucgforce[i];
+      if (scores) { a->ucgsoftmaxscores[i][0] = scores[2 * i]; a->ucgsoftmaxscores[i][1] = scores[2 * i + 1]; }
+    }
+  });
+}
+int ref_command(void *h, const char *line) {
+  Sim *s = (Sim *)h;
+  return guarded(s, [&] { s->command(line); });
+}
+int ref_nlocal(void *h) { return ((Sim *)h)->lmp.atom->nlocal; }
+int ref_nghost(void *h) { return ((Sim *)h)->lmp.atom->nghost; }
+int ref_get_atoms(void *h, double *x, double *v, double *f, int *type, int *tag, int *ucgstate, double *ucgl,
+                  double *ucgvl, double *ucgp, double *ucgforce, double *scores, int *num_ucgstates) {
+  Sim *s = (Sim *)h;
+  Atom *a = s->lmp.atom;
+  for (int i = 0; i < a->nlocal; i++) {
+    for (int k = 0; k < 3; k++) {
+      if (x) x[3 * i + k] = a->x[i][k];
+      if (v) v[3 * i + k] = a->v[i][k];
+      if (f) f[3 * i + k] = a->f[i][k];
+    }
+    if (type) type[i] = a->type[i];
+    if (tag) tag[i] = a->tag[i];
+    if (ucgstate) ucgstate[i] = a->ucgstate[i];
+    if (ucgl) ucgl[i] = a->ucgl[i];
+    if (ucgvl) ucgvl[i] = a->ucgvl[i];
+    if (ucgp) ucgp[i] = a->ucgp[i];
+    if (ucgforce) ucgforce[i] = a->ucgforce[i];
+    if (scores) { scores[2 * i] = a->ucgsoftmaxscores[i][0]; scores[2 * i + 1] = a->ucgsoftmaxscores[i][1]; }
+    if (num_ucgstates) num_ucgstates[i] = a->num_ucgstates[i];
+  }
+  return 0;
+}
+int ref_init(void *h) { Sim *s = (Sim *)h; return guarded(s, [&] { s->lmp.update->whichflag = 1; s->init(); }); }
+// rebuild ghosts + lists for the current positions and evaluate the pair style once
+int ref_compute_once(void *h, int ev) {
+  Sim *s = (Sim *)h;
+  return guarded(s, [&] {
+    s->lmp.update->whichflag = 1;
+    s->init();
+    s->pbc();
+    s->borders();
+    s->build_all();
+    s->compute_forces(ev);
+  });
+}
+int ref_setup(void *h, int ev) { Sim *s = (Sim *)h; return guarded(s, [&] { s->setup(ev); }); }
+int ref_run(void *h, int nsteps, int thermo_every) { Sim *s = (Sim *)h; return guarded(s, [&] { s->run(nsteps, thermo_every); }); }
+// single fix hooks on the current arrays
+int ref_fix_call(void *h, int ifix, int what) {
+  Sim *s = (Sim *)h;
+  return guarded(s, [&] {
+    s->init();
+    Fix *f = s->lmp.modify->fix[ifix];
+    if (what == 0) f->initial_integrate(0);
+    else if (what == 1) f->post_force(0);
+    else if (what == 2) f->final_integrate();
+    else if (what == 3) f->end_of_step();
+    else if (what == 4) f->setup(0);
+    else if (what == 5) f->pre_exchange();
+  });
+}
+double ref_fix_scalar(void *h, int ifix) { return ((Sim *)h)->lmp.modify->fix[ifix]->compute_scalar(); }
+double ref_fix_vector(void *h, int ifix, int k) { return ((Sim *)h)->lmp.modify->fix[ifix]->compute_vector(k); }
+double ref_eng_vdwl(void *h) { return ((Sim *)h)->lmp.force->pair->eng_vdwl; }
+void ref_virial(void *h, double *as_shipped, double *tally) {
+  Pair *p = ((Sim *)h)->lmp.force->pair;
+  for (int k = 0; k < 6; k++) { if (as_shipped) as_shipped[k] = p->virial[k]; if (tally) tally[k] = p->virial_tally[k]; }
+}
+long long ref_ntimestep(void *h) { return ((Sim *)h)->lmp.update->ntimestep; }
+int ref_nbuilds(void *h) { return ((Sim *)h)->nbuilds; }
+void ref_timers(void *h, double *out) { for (int k = 0; k < 4; k++) out[k] = ((Sim *)h)->timers[k]; }
+long long ref_neigh_pairs(void *h, int ilist, int *tag_i, int *tag_j, long long cap) {
+  Sim *s = (Sim *)h;
+  if (ilist >= (int)s->lmp.neighbor->requests.size()) return -1;
+  NeighList *l = s->lmp.neighbor->requests[ilist]->list;
+  Atom *a = s->lmp.atom;
+  long long n = 0;
+  for (int ii = 0; ii < l->inum; ii++) {
+    int i = l->ilist[ii];
+    for (int jj = 0; jj < l->numneigh[i]; jj++) {
+      int j = l->firstneigh[i][jj] & NEIGHMASK;
+      if (tag_i && n < cap) { tag_i[n] = a->tag[i]; tag_j[n] = a->tag[j]; }
+      n++;
+    }
+  }
+  return n;
+}
+int ref_get_types(void *h, int *type) {
+  Atom *a = ((Sim *)h)->lmp.atom;
+  for (int i = 0; i < a->nlocal; i++) type[i] = a->type[i];
+  return 0;
+}
+// Pair::single of the current pair style (table known-answer checks)
+int ref_pair_single(void *h, int itype, int jtype, double rsq, double factor_lj, double *phi, double *fforce) {
+  Sim *s = (Sim *)h;
+  return guarded(s, [&] { *phi = s->lmp.force->pair->single(0, 0, itype, jtype, rsq, 1.0, factor_lj, *fforce); });
+}
+
+}  // extern "C"
