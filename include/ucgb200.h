@@ -141,7 +141,8 @@ int ucgb200_force_clear(ucgb200_ctx *ctx);
  * list cutoff (fix cluster_switch requests its own list). */
 int ucgb200_neigh_configure(ucgb200_ctx *ctx, double skin, double cut_override);
 /* Neighbor::decide/check_distance [stock]: *rebuild = 1 iff any owned atom moved more
- * than skin/2 since the last build. */
+ * than skin/2 since the last build.  With several bricks this is the LOCAL flag; the host
+ * layer reduces it with MAX over the ranks (stock LAMMPS: MPI_Allreduce in decide()). */
 int ucgb200_neigh_decide(ucgb200_ctx *ctx, int *rebuild);
 /* domain->pbc + cell sort + ghost construction (comm->borders) + list build */
 int ucgb200_neigh_build(ucgb200_ctx *ctx);
@@ -150,7 +151,8 @@ int ucgb200_neigh_build(ucgb200_ctx *ctx);
 int ucgb200_ghosts_forward(ucgb200_ctx *ctx);
 /* neighbor list download for parity tests: rows are in current DEVICE order;
  * tag_i[nlocal], numneigh[nlocal], offsets[nlocal+1], neigh_tags[total] (tags of the
- * neighbors), neigh_shift[total] (0..26 periodic image code, 13 = none).  Pass
+ * neighbors), neigh_shift[total] (image code: 0 owned, 1..26 local periodic image, 32+ from
+ * another brick).  Pass
  * NULL pointers with *total to query sizes. */
 int ucgb200_neigh_download(ucgb200_ctx *ctx, int *nlocal, long long *total, int *tag_i, int *numneigh,
                            long long *offsets, int *neigh_tags, int *neigh_shift);
@@ -248,24 +250,35 @@ int ucgb200_timers(ucgb200_ctx *ctx, int enable, double out_ms[4], long long out
 int ucgb200_last_pair_ms(ucgb200_ctx *ctx, double *ms);
 
 /* ---------------------------------------------------- multi-GPU halo plumbing */
-/* Brick decomposition: this context owns sub-domain (set_subdomain); ghosts within
- * cut+skin of the faces come from up to 26 neighbor bricks (or periodic self-images).
- * The pack/unpack kernels work on DEVICE buffers so that any transport (NCCL
- * send/recv driven by the host layer, or peer-mapped stores) can carry them. */
+/* Brick decomposition (what stock Comm does over MPI for the reference, with the payloads of
+ * AtomVecUCG's field lists, UCG/atom_vec_ucg.cpp:66-82).  Rank r owns brick
+ * (r % gx, (r/gx) % gy, r/(gx*gy)) of the box.  Ghosts within cut+skin of a brick face come
+ * from the brick on the other side — or are local periodic images when that brick is the
+ * rank itself.  Every exchange is ONE message per peer rank (NVSwitch makes all peers equal:
+ * no staged x/y/z relay); records for rank k are contiguous and ordered by k in the send
+ * buffer, the receive buffer is ordered by source rank.  The pack/unpack kernels work on
+ * DEVICE buffers so that any transport can carry them (NCCL all-to-all driven by the host
+ * layer, or peer-mapped stores).  The device list is full, so there is no reverse halo. */
 int ucgb200_halo_configure(ucgb200_ctx *ctx, int rank, int nranks, const int procgrid[3]);
-/* after neigh_build's local part: number of atoms to send to each of 27 directions */
-int ucgb200_halo_send_counts(ucgb200_ctx *ctx, int counts[27]);
-/* border records (48 B/ghost: x,y,z,ucgl,(type|state|tag),ucgp) for direction dir */
-int ucgb200_halo_pack_border(ucgb200_ctx *ctx, int dir, void *d_buf);
-int ucgb200_halo_set_recv_counts(ucgb200_ctx *ctx, const int counts[27]);
-int ucgb200_halo_unpack_border(ucgb200_ctx *ctx, int dir, const void *d_buf);
-/* per-step forward records (40 B/ghost: x,y,z,ucgl,(state),ucgp) */
-int ucgb200_halo_pack_forward(ucgb200_ctx *ctx, int dir, void *d_buf);
-int ucgb200_halo_unpack_forward(ucgb200_ctx *ctx, int dir, const void *d_buf);
-/* finish a distributed rebuild once all borders are unpacked (bins ghosts, builds rows) */
+/* record sizes in bytes: border (rebuild), forward (every step), migrate (rebuild) */
+int ucgb200_halo_record_bytes(int *border, int *forward, int *migrate);
+/* comm->exchange(): wrap, count the sites that left this brick per destination rank ... */
+int ucgb200_migrate_prepare(ucgb200_ctx *ctx, int *counts /*[nranks]*/);
+/* ... pack them (and compact the stayers) ... */
+int ucgb200_migrate_pack(ucgb200_ctx *ctx, void *d_sendbuf);
+/* ... append the arrivals. */
+int ucgb200_migrate_unpack(ucgb200_ctx *ctx, const void *d_recvbuf, int nrecv);
+/* rebuild, local part: cell sort + image lists; then the border records per destination */
 int ucgb200_neigh_build_local(ucgb200_ctx *ctx);
+int ucgb200_halo_send_counts(ucgb200_ctx *ctx, int *counts /*[nranks]*/);
+int ucgb200_halo_pack_border(ucgb200_ctx *ctx, void *d_sendbuf);
+int ucgb200_halo_unpack_border(ucgb200_ctx *ctx, const void *d_recvbuf, const int *recv_counts /*[nranks]*/);
+/* rebuild, final part: bin ghosts, build rows */
 int ucgb200_neigh_build_finish(ucgb200_ctx *ctx);
-/* device pointer of the rebuild flag (int) so the host layer can all-reduce it */
+/* comm->forward_comm() across bricks, every non-rebuild step (same counts as the borders) */
+int ucgb200_halo_pack_forward(ucgb200_ctx *ctx, void *d_sendbuf);
+int ucgb200_halo_unpack_forward(ucgb200_ctx *ctx, const void *d_recvbuf);
+/* device pointer of the rebuild flag (int32) so the host layer can all-reduce it (MAX) */
 int ucgb200_neigh_flag_ptr(ucgb200_ctx *ctx, void **d_flag);
 
 #ifdef __cplusplus

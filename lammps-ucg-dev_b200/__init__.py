@@ -346,6 +346,53 @@ class Context:
         self._ck(self._l.ucgb200_kinetic_energy(self._h, int(groupbit), C.byref(ke), C.byref(n)))
         return ke.value, n.value
 
+    # ------------------------------------------------------------ multi-GPU halo
+    def halo_configure(self, rank, nranks, procgrid):
+        g = _i(procgrid)
+        self._ck(self._l.ucgb200_halo_configure(self._h, int(rank), int(nranks), _pi(g)))
+        self._nranks = int(nranks)
+
+    @staticmethod
+    def halo_record_bytes():
+        a, b, c_ = C.c_int(), C.c_int(), C.c_int()
+        lib().ucgb200_halo_record_bytes(C.byref(a), C.byref(b), C.byref(c_))
+        return dict(border=a.value, forward=b.value, migrate=c_.value)
+
+    def migrate_prepare(self):
+        counts = np.zeros(self._nranks, np.int32)
+        self._ck(self._l.ucgb200_migrate_prepare(self._h, _pi(counts)))
+        return counts
+
+    def migrate_pack(self, d_ptr):
+        self._ck(self._l.ucgb200_migrate_pack(self._h, C.c_void_p(d_ptr)))
+
+    def migrate_unpack(self, d_ptr, nrecv):
+        self._ck(self._l.ucgb200_migrate_unpack(self._h, C.c_void_p(d_ptr), int(nrecv)))
+
+    def neigh_build_local(self):
+        self._ck(self._l.ucgb200_neigh_build_local(self._h))
+
+    def neigh_build_finish(self):
+        self._ck(self._l.ucgb200_neigh_build_finish(self._h))
+
+    def halo_send_counts(self):
+        counts = np.zeros(self._nranks, np.int32)
+        self._ck(self._l.ucgb200_halo_send_counts(self._h, _pi(counts)))
+        return counts
+
+    def halo_pack_border(self, d_ptr):
+        self._ck(self._l.ucgb200_halo_pack_border(self._h, C.c_void_p(d_ptr)))
+
+    def halo_unpack_border(self, d_ptr, recv_counts):
+        rc = _i(recv_counts)
+        self._ck(self._l.ucgb200_halo_unpack_border(self._h, C.c_void_p(d_ptr), _pi(rc)))
+
+    def halo_pack_forward(self, d_ptr):
+        self._ck(self._l.ucgb200_halo_pack_forward(self._h, C.c_void_p(d_ptr)))
+
+    def halo_unpack_forward(self, d_ptr):
+        self._ck(self._l.ucgb200_halo_unpack_forward(self._h, C.c_void_p(d_ptr)))
+
     # ---------------------------------------------------------- cluster switch
     def cluster_configure(self, mol_seed, mol_offset, cutoff, type_on, type_off, prob_on, prob_off,
                           contact_map, max_mol):

@@ -47,7 +47,9 @@ extern "C" int ucgb200_destroy(ucgb200_ctx *c) {
   c->ucgml.release(); c->ucgml_alt.release(); c->ts.release(); c->ts_alt.release();
   c->mask.release(); c->mask_alt.release(); c->tag.release(); c->tag_alt.release();
   c->mol.release(); c->mol_alt.release(); c->orig.release(); c->orig_alt.release();
-  c->ghost_owner.release(); c->ghost_code.release(); c->ghost_key.release();
+  c->ghost_owner.release(); c->ghost_code.release(); c->ghost_key.release(); c->ghost_src.release(); c->slot_of_src.release();
+  c->img_counters.release(); c->img_owner.release(); c->img_code.release(); c->recv_border.release();
+  c->mig_dest.release(); c->mig_stay.release(); c->mig_scan.release();
   c->cell_count.release(); c->cell_start.release(); c->cell_cursor.release();
   c->gcell_count.release(); c->gcell_start.release(); c->order.release(); c->cell_of.release();
   c->scan_tmp.release(); c->ghost_cnt.release(); c->ghost_off.release();

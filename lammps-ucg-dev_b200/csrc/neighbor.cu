@@ -206,73 +206,239 @@ __global__ void k_permute(PermArgs a, const int *__restrict__ order, int n) {
   a.orig_o[s] = a.orig[i];
 }
 
-// [stock] CommBrick::borders, periodic self-images: an owned atom within cutghost of a
-// low face reappears at +prd, of a high face at -prd, in every combination of the three
-// dimensions (the staged x,y,z exchange of LAMMPS yields exactly these images).
-__device__ __forceinline__ int image_options(double x, double lo, double hi, double cut, int periodic, int opt[3]) {
+// ---------------------------------------------------------------- ghosts / halo
+// [stock] CommBrick::borders generalised to a brick decomposition over GPUs.  An owned
+// atom within cutghost of a low ("L") or high ("H") face of its sub-domain has an image in
+// the neighbouring brick of that direction; all combinations over the three dimensions
+// exist (the staged x,y,z exchange of LAMMPS yields exactly these).  code = cx+3cy+9cz with
+// c in {0 none, 1 L, 2 H}.  If the neighbouring brick is this rank itself (one brick in that
+// dimension) the image is a local periodic ghost; otherwise it is a border record for the
+// rank that owns that brick.  The SENDER applies the periodic shift.
+struct ImageMap {
+  int dest[27];        // destination rank of every code (own rank -> local image)
+  double shift[27][3]; // coordinate shift applied by the sender
+  int self;
+  int nranks;
+  int allow_lo[3], allow_hi[3];  // image exists in that direction (periodic or interior face)
+};
+
+__device__ __forceinline__ int face_options(double x, double lo, double hi, double cut, int allow_lo, int allow_hi, int opt[3]) {
   int n = 0;
   opt[n++] = 0;
-  if (periodic) {
-    if (x <= lo + cut) opt[n++] = 1;
-    if (x >= hi - cut) opt[n++] = -1;
-  }
+  if (allow_lo && x <= lo + cut) opt[n++] = 1;
+  if (allow_hi && x >= hi - cut) opt[n++] = 2;
   return n;
 }
+
+// counters/cursors layout: [0..nranks) remote destinations, [nranks] local images
 template <bool FILL>
-__global__ void k_ghost_images(const double4 *__restrict__ pos, int n, BoxDev box, Grid g,
-                               int *__restrict__ gcell_count, const int *__restrict__ gcell_start,
-                               int *__restrict__ gcursor, long long *__restrict__ gkey) {
+__global__ void k_images(const double4 *__restrict__ pos, int n, BoxDev box, ImageMap im, int *__restrict__ counters,
+                         const int *__restrict__ offsets, int *__restrict__ list_owner, int *__restrict__ list_code) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double4 r = pos[i];
   int ox[3], oy[3], oz[3];
-  int nx = image_options(r.x, box.sublo[0], box.subhi[0], box.cutghost, box.periodic[0], ox);
-  int ny = image_options(r.y, box.sublo[1], box.subhi[1], box.cutghost, box.periodic[1], oy);
-  int nz = image_options(r.z, box.sublo[2], box.subhi[2], box.cutghost, box.periodic[2], oz);
+  int nx = face_options(r.x, box.sublo[0], box.subhi[0], box.cutghost, im.allow_lo[0], im.allow_hi[0], ox);
+  int ny = face_options(r.y, box.sublo[1], box.subhi[1], box.cutghost, im.allow_lo[1], im.allow_hi[1], oy);
+  int nz = face_options(r.z, box.sublo[2], box.subhi[2], box.cutghost, im.allow_lo[2], im.allow_hi[2], oz);
   if (nx * ny * nz == 1) return;
   for (int c = 0; c < nz; c++)
     for (int b = 0; b < ny; b++)
       for (int a = 0; a < nx; a++) {
-        int sx = ox[a], sy = oy[b], sz = oz[c];
-        if (sx == 0 && sy == 0 && sz == 0) continue;
-        double gx = sx ? r.x + sx * box.prd[0] : r.x;
-        double gy = sy ? r.y + sy * box.prd[1] : r.y;
-        double gz = sz ? r.z + sz * box.prd[2] : r.z;
-        int cid = cell_index(g, gx, gy, gz, false);
-        if (!FILL) atomicAdd(&gcell_count[cid], 1);
-        else {
-          int slot = gcell_start[cid] + atomicAdd(&gcursor[cid], 1);
-          int code = (sx + 1) + 3 * (sy + 1) + 9 * (sz + 1);
-          gkey[slot] = (long long)i * 32 + code;
+        int code = ox[a] + 3 * oy[b] + 9 * oz[c];
+        if (code == 0) continue;
+        int d = im.dest[code];
+        int idx = (d == im.self) ? im.nranks : d;
+        int k = atomicAdd(&counters[idx], 1);
+        if (FILL) {
+          int slot = offsets[idx] + k;
+          list_owner[slot] = i;
+          list_code[slot] = code;
         }
       }
 }
 
-// ghost records from their owners: border payload (fields_border, atom_vec_ucg.cpp:66-67)
-// when FULL, per-step forward payload (fields_comm, :71) otherwise.
+struct BorderRec {  // 64 B: fields_border of AtomVecUCG (atom_vec_ucg.cpp:66-67) + tag/type
+  double4 pos;      // x,y,z (shifted), ucgl
+  int ts, tag, mol, code;
+  double ucgp, pad;
+};
+struct ForwardRec {  // 48 B: x + fields_comm {ucgstate, ucgl, ucgp} (atom_vec_ucg.cpp:71)
+  double4 pos;
+  int ts, pad;
+  double ucgp;
+};
+struct MigrateRec {  // 96 B: the UCG part of fields_exchange (atom_vec_ucg.cpp:76-82)
+  double4 pos, vel;
+  int ts, mask, tag, mol;
+  double ucgp, ucgml;
+};
+
+__global__ void k_pack_border(const double4 *__restrict__ pos, const int *__restrict__ ts, const int *__restrict__ tag,
+                              const int *__restrict__ mol, const double *__restrict__ ucgp, const int *__restrict__ owner,
+                              const int *__restrict__ code, int n, ImageMap im, BorderRec *__restrict__ out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int o = owner[k], cd = code[k];
+  double4 r = pos[o];
+  if (im.shift[cd][0] != 0.0) r.x = r.x + im.shift[cd][0];
+  if (im.shift[cd][1] != 0.0) r.y = r.y + im.shift[cd][1];
+  if (im.shift[cd][2] != 0.0) r.z = r.z + im.shift[cd][2];
+  BorderRec b;
+  b.pos = r; b.ts = ts[o]; b.tag = tag[o]; b.mol = mol[o]; b.code = cd; b.ucgp = ucgp[o]; b.pad = 0.0;
+  out[k] = b;
+}
+__global__ void k_pack_forward(const double4 *__restrict__ pos, const int *__restrict__ ts, const double *__restrict__ ucgp,
+                               const int *__restrict__ owner, const int *__restrict__ code, int n, ImageMap im,
+                               ForwardRec *__restrict__ out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int o = owner[k], cd = code[k];
+  double4 r = pos[o];
+  if (im.shift[cd][0] != 0.0) r.x = r.x + im.shift[cd][0];
+  if (im.shift[cd][1] != 0.0) r.y = r.y + im.shift[cd][1];
+  if (im.shift[cd][2] != 0.0) r.z = r.z + im.shift[cd][2];
+  ForwardRec f;
+  f.pos = r; f.ts = ts[o]; f.pad = 0; f.ucgp = ucgp[o];
+  out[k] = f;
+}
+__global__ void k_unpack_forward(double4 *__restrict__ pos, int *__restrict__ ts, double *__restrict__ ucgp, int nlocal,
+                                 const ForwardRec *__restrict__ in, const int *__restrict__ slot_of_src, int nlimg, int n) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int s = nlocal + slot_of_src[nlimg + k];
+  ForwardRec f = in[k];
+  pos[s] = f.pos; ts[s] = f.ts; ucgp[s] = f.ucgp;
+}
+
+// ghost sources = local images [0,nlimg) followed by received border records.
+__device__ __forceinline__ double4 source_pos(int k, int nlimg, const double4 *pos, const int *lo, const int *lc,
+                                              const ImageMap &im, const BorderRec *recv) {
+  if (k < nlimg) {
+    double4 r = pos[lo[k]];
+    int cd = lc[k];
+    if (im.shift[cd][0] != 0.0) r.x = r.x + im.shift[cd][0];
+    if (im.shift[cd][1] != 0.0) r.y = r.y + im.shift[cd][1];
+    if (im.shift[cd][2] != 0.0) r.z = r.z + im.shift[cd][2];
+    return r;
+  }
+  return recv[k - nlimg].pos;
+}
+template <bool FILL>
+__global__ void k_source_cells(const double4 *__restrict__ pos, const int *__restrict__ tag, int nsrc, int nlimg,
+                               const int *__restrict__ lo, const int *__restrict__ lc, ImageMap im,
+                               const BorderRec *__restrict__ recv, Grid g, int *__restrict__ gcell_count,
+                               const int *__restrict__ gcell_start, int *__restrict__ cursor,
+                               long long *__restrict__ gkey, int *__restrict__ gsrc) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nsrc) return;
+  double4 r = source_pos(k, nlimg, pos, lo, lc, im, recv);
+  int cid = cell_index(g, r.x, r.y, r.z, false);
+  if (!FILL) { atomicAdd(&gcell_count[cid], 1); return; }
+  int slot = gcell_start[cid] + atomicAdd(&cursor[cid], 1);
+  int t, cd;
+  if (k < nlimg) { t = tag[lo[k]]; cd = lc[k]; }
+  else { t = recv[k - nlimg].tag; cd = recv[k - nlimg].code; }
+  gkey[slot] = ((long long)t << 6) | (long long)(cd + (k < nlimg ? 0 : 32));
+  gsrc[slot] = k;
+}
+// deterministic order inside every ghost cell: ascending (tag, image code)
+__global__ void k_sort_cells_kv(long long *__restrict__ keys, int *__restrict__ vals, const int *__restrict__ start, int ncells) {
+  int cid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cid >= ncells) return;
+  int b = start[cid], e = start[cid + 1];
+  for (int a = b + 1; a < e; a++) {
+    long long key = keys[a];
+    int v = vals[a];
+    int k = a - 1;
+    while (k >= b && keys[k] > key) { keys[k + 1] = keys[k]; vals[k + 1] = vals[k]; k--; }
+    keys[k + 1] = key; vals[k + 1] = v;
+  }
+}
+// fill ghost slots; FULL also writes tag/molecule and the slot_of_src map (rebuild), otherwise
+// only the per-step payload of the LOCAL images is refreshed (forward_comm to self)
 template <bool FULL>
 __global__ void k_ghost_fill(double4 *__restrict__ pos, int *__restrict__ ts, double *__restrict__ ucgp,
-                             int *__restrict__ tag, int *__restrict__ mol, int nlocal, int nghost,
-                             const long long *__restrict__ gkey, int *__restrict__ gowner, int *__restrict__ gcode,
-                             double px, double py, double pz) {
-  int gi = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gi >= nghost) return;
-  int o, code;
-  if (FULL) {
-    long long key = gkey[gi];
-    o = (int)(key >> 5); code = (int)(key & 31);
-    gowner[gi] = o; gcode[gi] = code;
-  } else { o = gowner[gi]; code = gcode[gi]; }
-  int sx = code % 3 - 1, sy = (code / 3) % 3 - 1, sz = code / 9 - 1;
-  double4 r = pos[o];
-  if (sx) r.x = r.x + sx * px;
-  if (sy) r.y = r.y + sy * py;
-  if (sz) r.z = r.z + sz * pz;
-  int k = nlocal + gi;
-  pos[k] = r;
-  ts[k] = ts[o];
-  ucgp[k] = ucgp[o];
-  if (FULL) { tag[k] = tag[o]; mol[k] = mol[o]; }
+                             int *__restrict__ tag, int *__restrict__ mol, int nlocal, int n, int nlimg,
+                             const int *__restrict__ gsrc, int *__restrict__ slot_of_src, const int *__restrict__ lo,
+                             const int *__restrict__ lc, ImageMap im, const BorderRec *__restrict__ recv,
+                             int *__restrict__ gcode) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  int k, slot;
+  if (FULL) { slot = idx; k = gsrc[slot]; slot_of_src[k] = slot; }
+  else { k = idx; slot = slot_of_src[k]; }   // idx runs over local images only
+  int s = nlocal + slot;
+  if (k < nlimg) {
+    int o = lo[k];
+    pos[s] = source_pos(k, nlimg, pos, lo, lc, im, recv);
+    ts[s] = ts[o];
+    ucgp[s] = ucgp[o];
+    if (FULL) { tag[s] = tag[o]; mol[s] = mol[o]; gcode[slot] = lc[k]; }
+  } else if (FULL) {
+    BorderRec b = recv[k - nlimg];
+    pos[s] = b.pos; ts[s] = b.ts; ucgp[s] = b.ucgp; tag[s] = b.tag; mol[s] = b.mol; gcode[slot] = 32 + b.code;
+  }
+}
+
+// migration: atoms whose (wrapped) position left this brick
+__global__ void k_migrate_classify(const double4 *__restrict__ pos, int n, BoxDev box, int gx, int gy, int gz, int self,
+                                   int *__restrict__ dest, int *__restrict__ stay, int *__restrict__ counters) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 r = pos[i];
+  double x[3] = {r.x, r.y, r.z};
+  int g[3] = {gx, gy, gz}, pc[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    double w = box.prd[d] / g[d];
+    int c = (int)floor((x[d] - box.lo[d]) / w);
+    c = min(max(c, 0), g[d] - 1);
+    // same plane arithmetic as ucgb200_halo_configure: split(c) = lo + c*w
+    while (c > 0 && x[d] < box.lo[d] + c * w) c--;
+    while (c < g[d] - 1 && x[d] >= box.lo[d] + (c + 1) * w) c++;
+    pc[d] = c;
+  }
+  int r_dest = (pc[2] * gy + pc[1]) * gx + pc[0];
+  dest[i] = r_dest;
+  stay[i] = r_dest == self;
+  if (r_dest != self) atomicAdd(&counters[r_dest], 1);
+}
+__global__ void k_migrate_pack(const double4 *__restrict__ pos, const double4 *__restrict__ vel, const int *__restrict__ ts,
+                               const int *__restrict__ mask, const int *__restrict__ tag, const int *__restrict__ mol,
+                               const double *__restrict__ ucgp, const double *__restrict__ ucgml, int n, int self,
+                               const int *__restrict__ dest, const int *__restrict__ offsets, int *__restrict__ cursor,
+                               MigrateRec *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int d = dest[i];
+  if (d == self) return;
+  int slot = offsets[d] + atomicAdd(&cursor[d], 1);
+  MigrateRec m;
+  m.pos = pos[i]; m.vel = vel[i]; m.ts = ts[i]; m.mask = mask[i]; m.tag = tag[i]; m.mol = mol[i];
+  m.ucgp = ucgp[i]; m.ucgml = ucgml[i];
+  out[slot] = m;
+}
+__global__ void k_stay_order(const int *__restrict__ stay, const int *__restrict__ stay_scan, int n, int *__restrict__ order) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && stay[i]) order[stay_scan[i]] = i;
+}
+__global__ void k_migrate_unpack(double4 *__restrict__ pos, double4 *__restrict__ vel, double4 *__restrict__ frc,
+                                 double2 *__restrict__ scores, int *__restrict__ ts, int *__restrict__ mask,
+                                 int *__restrict__ tag, int *__restrict__ mol, double *__restrict__ ucgp,
+                                 double *__restrict__ ucgml, int *__restrict__ orig, int base, int n,
+                                 const MigrateRec *__restrict__ in) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  MigrateRec m = in[k];
+  int s = base + k;
+  pos[s] = m.pos; vel[s] = m.vel; frc[s] = make_double4(0, 0, 0, 0); scores[s] = make_double2(0, 0);
+  ts[s] = m.ts; mask[s] = m.mask; tag[s] = m.tag; mol[s] = m.mol; ucgp[s] = m.ucgp; ucgml[s] = m.ucgml;
+  orig[s] = s;
+}
+__global__ void k_iota2(int *p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
 }
 
 // One warp per owned site walks the 27-cell stencil.  Owned atoms and ghosts are both
@@ -376,8 +542,8 @@ static int setup_grid(ucgb200_ctx *c) {
   long long ncells = 1;
   for (int d = 0; d < 3; d++) {
     double len = c->subhi[d] - c->sublo[d];
-    if (c->periodic[d] && (c->boxhi[d] - c->boxlo[d]) < cutneigh) {
-      c->err = "periodic box shorter than the neighbor cutoff (cut+skin)";
+    if (c->periodic[d] && len < cutneigh) {
+      c->err = "periodic box (or brick) shorter than the neighbor cutoff (cut+skin)";
       return UCGB200_ERR_BOX_TOO_SMALL;
     }
     int n = (int)std::floor(len / cutneigh);
@@ -402,6 +568,33 @@ static BoxDev make_box(const ucgb200_ctx *c) {
   }
   b.cutghost = c->cutneighmax;
   return b;
+}
+
+static ImageMap make_image_map(const ucgb200_ctx *c) {
+  ImageMap im;
+  const auto &h = c->halo;
+  im.self = h.rank; im.nranks = h.nranks;
+  for (int d = 0; d < 3; d++) {
+    im.allow_lo[d] = c->periodic[d] || h.coord[d] > 0;
+    im.allow_hi[d] = c->periodic[d] || h.coord[d] < h.grid[d] - 1;
+  }
+  for (int code = 0; code < 27; code++) {
+    int cc[3] = {code % 3, (code / 3) % 3, code / 9};
+    int pc[3];
+    for (int d = 0; d < 3; d++) {
+      im.shift[code][d] = 0.0;
+      pc[d] = h.coord[d];
+      if (cc[d] == 1) {  // towards the lower neighbour
+        pc[d] = h.coord[d] - 1;
+        if (pc[d] < 0) { pc[d] = h.grid[d] - 1; im.shift[code][d] = c->prd[d]; }
+      } else if (cc[d] == 2) {
+        pc[d] = h.coord[d] + 1;
+        if (pc[d] >= h.grid[d]) { pc[d] = 0; im.shift[code][d] = -c->prd[d]; }
+      }
+    }
+    im.dest[code] = (pc[2] * h.grid[1] + pc[1]) * h.grid[0] + pc[0];
+  }
+  return im;
 }
 
 int ucg_ensure_atom_capacity(ucgb200_ctx *c, size_t nall, size_t nloc);
@@ -432,46 +625,8 @@ static int build_rows(ucgb200_ctx *c) {
   return 0;
 }
 
-extern "C" int ucgb200_neigh_build(ucgb200_ctx *c) {
-  if (!c) return -1;
-  cudaSetDevice(c->device);
-  int rc = rebuild_maps(c);
-  if (rc) return rc;
-  if (c->nlocal == 0) { c->list_valid = true; return 0; }
-  if ((rc = setup_grid(c))) return rc;
-  cudaStream_t st = c->stream;
-  int nlocal = c->nlocal;
-  int ncells = c->grid.ncells;
-  BoxDev box = make_box(c);
-  cudaEvent_t t0 = c->ev_a, t1 = c->ev_b;
-  if (c->timers_on) cudaEventRecord(t0, st);
-  long long l0 = c->launches;
-
-  UCG_CHECK(c, c->cell_count.ensure(ncells + 4));
-  UCG_CHECK(c, c->cell_start.ensure(ncells + 4));
-  UCG_CHECK(c, c->cell_cursor.ensure(ncells + 4));
-  UCG_CHECK(c, c->gcell_count.ensure(ncells + 4));
-  UCG_CHECK(c, c->gcell_start.ensure(ncells + 4));
-  UCG_CHECK(c, c->order.ensure(nlocal));
-  UCG_CHECK(c, c->cell_of.ensure(nlocal));
-  UCG_CHECK(c, c->numneigh.ensure(nlocal));
-  UCG_CHECK(c, cudaMemsetAsync(c->cell_count.p, 0, (ncells + 4) * sizeof(int), st));
-  UCG_CHECK(c, cudaMemsetAsync(c->cell_cursor.p, 0, (ncells + 4) * sizeof(int), st));
-  UCG_CHECK(c, cudaMemsetAsync(c->gcell_count.p, 0, (ncells + 4) * sizeof(int), st));
-  UCG_CHECK(c, cudaMemsetAsync(c->d_flags.p, 0, 8 * sizeof(int), st));
-
-  // 1. pbc wrap + owned-cell histogram
-  k_wrap_count<<<nblocks(nlocal, 256), 256, 0, st>>>(c->pos.p, nlocal, box, c->grid, c->cell_of.p,
-                                                     c->cell_count.p, c->d_flags.p);
-  UCG_LAUNCHED(c);
-  // 2. cell offsets (ncells+3 entries so that start[c0+3] is always readable)
-  if ((rc = exclusive_scan(c, c->cell_count.p, c->cell_start.p, ncells + 4, nullptr))) return rc;
-  // 3. counting sort into cells, deterministic inside each cell
-  k_fill_order<<<nblocks(nlocal, 256), 256, 0, st>>>(c->cell_of.p, nlocal, c->cell_start.p, c->cell_cursor.p, c->order.p);
-  UCG_LAUNCHED(c);
-  k_sort_cells<int><<<nblocks(ncells, 128), 128, 0, st>>>(c->order.p, c->cell_start.p, ncells);
-  UCG_LAUNCHED(c);
-  // 4. move every per-site array into cell order
+// permute every per-site array by order[0..n) into the twin buffers and swap
+static int permute_all(ucgb200_ctx *c, int n) {
   UCG_CHECK(c, c->pos_alt.ensure_exact(c->pos.cap)); UCG_CHECK(c, c->ts_alt.ensure_exact(c->ts.cap));
   UCG_CHECK(c, c->ucgp_alt.ensure_exact(c->ucgp.cap)); UCG_CHECK(c, c->tag_alt.ensure_exact(c->tag.cap));
   UCG_CHECK(c, c->mol_alt.ensure_exact(c->mol.cap)); UCG_CHECK(c, c->vel_alt.ensure_exact(c->vel.cap));
@@ -482,84 +637,393 @@ extern "C" int ucgb200_neigh_build(ucgb200_ctx *c) {
               c->tag.p, c->mol.p, c->orig.p, c->pos_alt.p, c->vel_alt.p, c->frc_alt.p, c->scores_alt.p,
               c->ucgp_alt.p, c->ucgml_alt.p, c->ts_alt.p, c->mask_alt.p, c->tag_alt.p, c->mol_alt.p,
               c->orig_alt.p};
-  k_permute<<<nblocks(nlocal, 256), 256, 0, st>>>(pa, c->order.p, nlocal);
-  UCG_LAUNCHED(c);
+  if (n > 0) {
+    k_permute<<<nblocks(n, 256), 256, 0, c->stream>>>(pa, c->order.p, n);
+    UCG_LAUNCHED(c);
+  }
   std::swap(c->pos, c->pos_alt); std::swap(c->vel, c->vel_alt); std::swap(c->frc, c->frc_alt);
   std::swap(c->scores, c->scores_alt); std::swap(c->ucgp, c->ucgp_alt); std::swap(c->ucgml, c->ucgml_alt);
   std::swap(c->ts, c->ts_alt); std::swap(c->mask, c->mask_alt); std::swap(c->tag, c->tag_alt);
   std::swap(c->mol, c->mol_alt); std::swap(c->orig, c->orig_alt);
+  return 0;
+}
 
-  // 5. periodic ghost images, stored in cell order after the owned atoms
-  k_ghost_images<false><<<nblocks(nlocal, 256), 256, 0, st>>>(c->pos.p, nlocal, box, c->grid, c->gcell_count.p,
-                                                              nullptr, nullptr, nullptr);
-  UCG_LAUNCHED(c);
-  if ((rc = exclusive_scan(c, c->gcell_count.p, c->gcell_start.p, ncells + 4, c->d_flags.p + 2))) return rc;
-  if ((rc = read_flags(c))) return rc;
-  if (c->h_flags[3]) { c->err = "atoms lost: position outside the periodic box by more than one period"; return UCGB200_ERR_LOST_ATOMS; }
-  int nghost = c->h_flags[2];
-  c->nghost = nghost;
-  if ((rc = ucg_ensure_atom_capacity(c, (size_t)nlocal + nghost, nlocal))) return rc;
-  if (nghost > 0) {
-    UCG_CHECK(c, c->ghost_key.ensure(nghost));
-    UCG_CHECK(c, c->ghost_owner.ensure(nghost));
-    UCG_CHECK(c, c->ghost_code.ensure(nghost));
-    UCG_CHECK(c, cudaMemsetAsync(c->cell_cursor.p, 0, (ncells + 4) * sizeof(int), st));
-    k_ghost_images<true><<<nblocks(nlocal, 256), 256, 0, st>>>(c->pos.p, nlocal, box, c->grid, nullptr,
-                                                               c->gcell_start.p, c->cell_cursor.p, c->ghost_key.p);
-    UCG_LAUNCHED(c);
-    k_sort_cells<long long><<<nblocks(ncells, 128), 128, 0, st>>>(c->ghost_key.p, c->gcell_start.p, ncells);
-    UCG_LAUNCHED(c);
-    k_ghost_fill<true><<<nblocks(nghost, 256), 256, 0, st>>>(c->pos.p, c->ts.p, c->ucgp.p, c->tag.p, c->mol.p,
-                                                             nlocal, nghost, c->ghost_key.p, c->ghost_owner.p,
-                                                             c->ghost_code.p, c->prd[0], c->prd[1], c->prd[2]);
-    UCG_LAUNCHED(c);
+struct BuildTimer {
+  ucgb200_ctx *c;
+  long long l0;
+  explicit BuildTimer(ucgb200_ctx *ctx) : c(ctx), l0(ctx->launches) {
+    if (c->timers_on) cudaEventRecord(c->ev_a, c->stream);
   }
-  // 6. neighbor rows
-  if (c->neigh_stride == 0) {
-    double vol = 1.0;
-    for (int d = 0; d < 3; d++) vol *= (c->subhi[d] - c->sublo[d]);
-    double est = 4.18879 * c->cutneighmax * c->cutneighmax * c->cutneighmax * nlocal / vol;
-    int s = (int)(est * 1.35) + 24;
-    c->neigh_stride = ((s + 7) / 8) * 8;
-  }
-  if ((rc = build_rows(c))) return rc;
-  // 7. remember positions for the skin check
-  UCG_CHECK(c, cudaMemcpyAsync(c->xhold.p, c->pos.p, (size_t)nlocal * sizeof(double4), cudaMemcpyDeviceToDevice, st));
-  c->list_valid = true;
-  c->nbuilds++;
-  if (c->timers_on) {
-    cudaEventRecord(t1, st);
-    cudaEventSynchronize(t1);
+  void stop() {
+    if (!c->timers_on) return;
+    cudaEventRecord(c->ev_b, c->stream);
+    cudaEventSynchronize(c->ev_b);
     float ms = 0;
-    cudaEventElapsedTime(&ms, t0, t1);
+    cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
     c->t_ms[1] += ms;
     c->t_launch[1] += c->launches - l0;
   }
+};
+
+// rebuild, local part: pbc wrap, cell sort of the owned sites, image lists (local periodic
+// images + per-rank border send lists)
+extern "C" int ucgb200_neigh_build_local(ucgb200_ctx *c) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  int rc = rebuild_maps(c);
+  if (rc) return rc;
+  if ((rc = setup_grid(c))) return rc;
+  cudaStream_t st = c->stream;
+  const int nlocal = c->nlocal;
+  const int ncells = c->grid.ncells;
+  BoxDev box = make_box(c);
+  auto &h = c->halo;
+  BuildTimer timer(c);
+  c->list_valid = false;
+
+  UCG_CHECK(c, c->cell_count.ensure(ncells + 4));
+  UCG_CHECK(c, c->cell_start.ensure(ncells + 4));
+  UCG_CHECK(c, c->cell_cursor.ensure(ncells + 4));
+  UCG_CHECK(c, c->gcell_count.ensure(ncells + 4));
+  UCG_CHECK(c, c->gcell_start.ensure(ncells + 4));
+  UCG_CHECK(c, c->order.ensure(nlocal + 1));
+  UCG_CHECK(c, c->cell_of.ensure(nlocal + 1));
+  UCG_CHECK(c, c->numneigh.ensure(nlocal + 1));
+  UCG_CHECK(c, cudaMemsetAsync(c->cell_count.p, 0, (ncells + 4) * sizeof(int), st));
+  UCG_CHECK(c, cudaMemsetAsync(c->cell_cursor.p, 0, (ncells + 4) * sizeof(int), st));
+  UCG_CHECK(c, cudaMemsetAsync(c->d_flags.p, 0, 8 * sizeof(int), st));
+  h.nlimg = 0; h.nsend = 0;
+  std::fill(h.send_counts.begin(), h.send_counts.end(), 0);
+  if (nlocal == 0) { timer.stop(); return 0; }
+
+  // 1. pbc wrap + owned-cell histogram
+  k_wrap_count<<<nblocks(nlocal, 256), 256, 0, st>>>(c->pos.p, nlocal, box, c->grid, c->cell_of.p,
+                                                     c->cell_count.p, c->d_flags.p);
+  UCG_LAUNCHED(c);
+  // 2. cell offsets (ncells+4 entries so that start[c0+3] is always readable)
+  if ((rc = exclusive_scan(c, c->cell_count.p, c->cell_start.p, ncells + 4, nullptr))) return rc;
+  // 3. counting sort into cells, deterministic inside each cell
+  k_fill_order<<<nblocks(nlocal, 256), 256, 0, st>>>(c->cell_of.p, nlocal, c->cell_start.p, c->cell_cursor.p, c->order.p);
+  UCG_LAUNCHED(c);
+  k_sort_cells<int><<<nblocks(ncells, 128), 128, 0, st>>>(c->order.p, c->cell_start.p, ncells);
+  UCG_LAUNCHED(c);
+  // 4. move every per-site array into cell order
+  if ((rc = permute_all(c, nlocal))) return rc;
+
+  // 5. image lists: counters [0..nranks) = border records per destination rank, [nranks] = local
+  const int nr = h.nranks;
+  ImageMap im = make_image_map(c);
+  UCG_CHECK(c, c->img_counters.ensure(2 * (nr + 1) + 4));
+  int *counters = c->img_counters.p, *offsets = c->img_counters.p + (nr + 1);
+  UCG_CHECK(c, cudaMemsetAsync(counters, 0, (nr + 1) * sizeof(int), st));
+  k_images<false><<<nblocks(nlocal, 256), 256, 0, st>>>(c->pos.p, nlocal, box, im, counters, nullptr, nullptr, nullptr);
+  UCG_LAUNCHED(c);
+  std::vector<int> hc(nr + 1), ho(nr + 2, 0);
+  UCG_CHECK(c, cudaMemcpyAsync(hc.data(), counters, (nr + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if ((rc = read_flags(c))) return rc;
+  if (c->h_flags[3]) { c->err = "atoms lost: position outside the periodic box by more than one period"; return UCGB200_ERR_LOST_ATOMS; }
+  for (int k = 0; k <= nr; k++) ho[k + 1] = ho[k] + hc[k];
+  const int ntotal = ho[nr + 1];
+  h.nsend = ho[nr];
+  h.nlimg = hc[nr];
+  h.send_counts.assign(hc.begin(), hc.begin() + nr);
+  h.send_offsets.assign(ho.begin(), ho.begin() + nr + 1);
+  UCG_CHECK(c, c->img_owner.ensure(ntotal + 1));
+  UCG_CHECK(c, c->img_code.ensure(ntotal + 1));
+  if (ntotal > 0) {
+    UCG_CHECK(c, cudaMemcpyAsync(offsets, ho.data(), (nr + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    UCG_CHECK(c, cudaMemsetAsync(counters, 0, (nr + 1) * sizeof(int), st));
+    k_images<true><<<nblocks(nlocal, 256), 256, 0, st>>>(c->pos.p, nlocal, box, im, counters, offsets, c->img_owner.p,
+                                                         c->img_code.p);
+    UCG_LAUNCHED(c);
+  }
+  timer.stop();
   return 0;
+}
+
+// rebuild, final part: bin the ghost sources (local images + received border records) into
+// cells, materialise the ghost sites, build the neighbor rows, remember positions
+extern "C" int ucgb200_neigh_build_finish(ucgb200_ctx *c) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  cudaStream_t st = c->stream;
+  auto &h = c->halo;
+  const int nlocal = c->nlocal;
+  const int ncells = c->grid.ncells;
+  BuildTimer timer(c);
+  ImageMap im = make_image_map(c);
+  const int nlimg = h.nlimg, nrecv = h.nrecv, nsrc = nlimg + nrecv;
+  const int *lo = c->img_owner.p + h.nsend, *lc = c->img_code.p + h.nsend;  // local images follow the send lists
+  const BorderRec *recv = (const BorderRec *)c->recv_border.p;
+  int rc;
+  UCG_CHECK(c, cudaMemsetAsync(c->gcell_count.p, 0, (ncells + 4) * sizeof(int), st));
+  if (nsrc > 0) {
+    k_source_cells<false><<<nblocks(nsrc, 256), 256, 0, st>>>(c->pos.p, c->tag.p, nsrc, nlimg, lo, lc, im, recv, c->grid,
+                                                              c->gcell_count.p, nullptr, nullptr, nullptr, nullptr);
+    UCG_LAUNCHED(c);
+  }
+  if ((rc = exclusive_scan(c, c->gcell_count.p, c->gcell_start.p, ncells + 4, nullptr))) return rc;
+  c->nghost = nsrc;
+  if ((rc = ucg_ensure_atom_capacity(c, (size_t)nlocal + nsrc, nlocal))) return rc;
+  if (nsrc > 0) {
+    UCG_CHECK(c, c->ghost_key.ensure(nsrc));
+    UCG_CHECK(c, c->ghost_src.ensure(nsrc));
+    UCG_CHECK(c, c->slot_of_src.ensure(nsrc));
+    UCG_CHECK(c, c->ghost_code.ensure(nsrc));
+    UCG_CHECK(c, cudaMemsetAsync(c->cell_cursor.p, 0, (ncells + 4) * sizeof(int), st));
+    k_source_cells<true><<<nblocks(nsrc, 256), 256, 0, st>>>(c->pos.p, c->tag.p, nsrc, nlimg, lo, lc, im, recv, c->grid,
+                                                             nullptr, c->gcell_start.p, c->cell_cursor.p,
+                                                             c->ghost_key.p, c->ghost_src.p);
+    UCG_LAUNCHED(c);
+    k_sort_cells_kv<<<nblocks(ncells, 128), 128, 0, st>>>(c->ghost_key.p, c->ghost_src.p, c->gcell_start.p, ncells);
+    UCG_LAUNCHED(c);
+    k_ghost_fill<true><<<nblocks(nsrc, 256), 256, 0, st>>>(c->pos.p, c->ts.p, c->ucgp.p, c->tag.p, c->mol.p, nlocal, nsrc,
+                                                           nlimg, c->ghost_src.p, c->slot_of_src.p, lo, lc, im, recv,
+                                                           c->ghost_code.p);
+    UCG_LAUNCHED(c);
+  }
+  if (nlocal > 0) {
+    if (c->neigh_stride == 0) {
+      double vol = 1.0;
+      for (int d = 0; d < 3; d++) vol *= (c->subhi[d] - c->sublo[d]);
+      double est = 4.18879 * c->cutneighmax * c->cutneighmax * c->cutneighmax * nlocal / vol;
+      int s = (int)(est * 1.35) + 24;
+      c->neigh_stride = ((s + 7) / 8) * 8;
+    }
+    if ((rc = build_rows(c))) return rc;
+    UCG_CHECK(c, c->xhold.ensure(nlocal));
+    UCG_CHECK(c, cudaMemcpyAsync(c->xhold.p, c->pos.p, (size_t)nlocal * sizeof(double4), cudaMemcpyDeviceToDevice, st));
+  }
+  c->list_valid = true;
+  c->nbuilds++;
+  timer.stop();
+  return 0;
+}
+
+// single-GPU rebuild: every image is local
+extern "C" int ucgb200_neigh_build(ucgb200_ctx *c) {
+  if (!c) return -1;
+  if (c->halo.nranks > 1) return fail(c, "neigh_build: this context is one brick of several; drive the rebuild through "
+                                         "migrate_* / neigh_build_local / halo_* / neigh_build_finish");
+  int rc = ucgb200_neigh_build_local(c);
+  if (rc) return rc;
+  c->halo.nrecv = 0;
+  return ucgb200_neigh_build_finish(c);
 }
 
 extern "C" int ucgb200_neigh_decide(ucgb200_ctx *c, int *rebuild) {
   if (!c || !rebuild) return -1;
   cudaSetDevice(c->device);
   if (!c->list_valid) { *rebuild = 1; return 0; }
-  if (c->nlocal == 0) { *rebuild = 0; return 0; }
-  double triggersq = 0.25 * c->skin * c->skin;
+  *rebuild = 0;
   UCG_CHECK(c, cudaMemsetAsync(c->d_flags.p, 0, sizeof(int), c->stream));
-  k_check_distance<<<nblocks(c->nlocal, 256), 256, 0, c->stream>>>(c->pos.p, c->xhold.p, c->nlocal, triggersq, c->d_flags.p);
-  UCG_LAUNCHED(c);
+  if (c->nlocal > 0) {
+    double triggersq = 0.25 * c->skin * c->skin;
+    k_check_distance<<<nblocks(c->nlocal, 256), 256, 0, c->stream>>>(c->pos.p, c->xhold.p, c->nlocal, triggersq, c->d_flags.p);
+    UCG_LAUNCHED(c);
+  }
   UCG_CHECK(c, cudaMemcpyAsync(c->h_flags, c->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   UCG_CHECK(c, cudaStreamSynchronize(c->stream));
   *rebuild = c->h_flags[0] ? 1 : 0;
   return 0;
 }
 
+// comm->forward_comm() to self: refresh the local periodic images
 extern "C" int ucgb200_ghosts_forward(ucgb200_ctx *c) {
   if (!c) return -1;
   cudaSetDevice(c->device);
-  if (c->nghost == 0) return 0;
-  k_ghost_fill<false><<<nblocks(c->nghost, 256), 256, 0, c->stream>>>(
-      c->pos.p, c->ts.p, c->ucgp.p, c->tag.p, c->mol.p, c->nlocal, c->nghost, nullptr, c->ghost_owner.p,
-      c->ghost_code.p, c->prd[0], c->prd[1], c->prd[2]);
+  auto &h = c->halo;
+  if (h.nlimg == 0) return 0;
+  ImageMap im = make_image_map(c);
+  k_ghost_fill<false><<<nblocks(h.nlimg, 256), 256, 0, c->stream>>>(
+      c->pos.p, c->ts.p, c->ucgp.p, c->tag.p, c->mol.p, c->nlocal, h.nlimg, h.nlimg, nullptr, c->slot_of_src.p,
+      c->img_owner.p + h.nsend, c->img_code.p + h.nsend, im, nullptr, nullptr);
+  UCG_LAUNCHED(c);
+  return 0;
+}
+
+// ----------------------------------------------------------------- multi-GPU halo
+extern "C" int ucgb200_halo_configure(ucgb200_ctx *c, int rank, int nranks, const int procgrid[3]) {
+  if (!c || !procgrid || nranks < 1 || rank < 0 || rank >= nranks) return -1;
+  if (procgrid[0] * procgrid[1] * procgrid[2] != nranks) return fail(c, "halo_configure: procgrid does not multiply to nranks");
+  auto &h = c->halo;
+  h.rank = rank; h.nranks = nranks;
+  for (int d = 0; d < 3; d++) h.grid[d] = procgrid[d];
+  h.coord[0] = rank % procgrid[0];
+  h.coord[1] = (rank / procgrid[0]) % procgrid[1];
+  h.coord[2] = rank / (procgrid[0] * procgrid[1]);
+  for (int d = 0; d < 3; d++) {
+    double w = c->prd[d] / procgrid[d];
+    c->sublo[d] = c->boxlo[d] + h.coord[d] * w;
+    c->subhi[d] = (h.coord[d] == procgrid[d] - 1) ? c->boxhi[d] : c->boxlo[d] + (h.coord[d] + 1) * w;
+  }
+  c->sub_set = true;
+  h.send_counts.assign(nranks, 0);
+  h.send_offsets.assign(nranks + 1, 0);
+  h.recv_counts.assign(nranks, 0);
+  h.mig_counts.assign(nranks, 0);
+  c->list_valid = false;
+  return 0;
+}
+
+extern "C" int ucgb200_halo_record_bytes(int *border, int *forward, int *migrate) {
+  if (border) *border = (int)sizeof(BorderRec);
+  if (forward) *forward = (int)sizeof(ForwardRec);
+  if (migrate) *migrate = (int)sizeof(MigrateRec);
+  return 0;
+}
+
+// comm->exchange(), part 1: wrap, find the sites that left this brick; counts[nranks]
+extern "C" int ucgb200_migrate_prepare(ucgb200_ctx *c, int *counts) {
+  if (!c || !counts) return -1;
+  cudaSetDevice(c->device);
+  auto &h = c->halo;
+  const int nr = h.nranks, n = c->nlocal;
+  cudaStream_t st = c->stream;
+  int rc = rebuild_maps(c);
+  if (rc) return rc;
+  if ((rc = setup_grid(c))) return rc;
+  BoxDev box = make_box(c);
+  UCG_CHECK(c, c->img_counters.ensure(2 * (nr + 1) + 4));
+  UCG_CHECK(c, cudaMemsetAsync(c->img_counters.p, 0, (2 * (nr + 1) + 4) * sizeof(int), st));
+  UCG_CHECK(c, cudaMemsetAsync(c->d_flags.p, 0, 8 * sizeof(int), st));
+  UCG_CHECK(c, c->cell_of.ensure(n + 1));
+  UCG_CHECK(c, c->order.ensure(n + 1));
+  UCG_CHECK(c, c->mig_dest.ensure(n + 1));
+  UCG_CHECK(c, c->mig_stay.ensure(n + 8));
+  UCG_CHECK(c, c->mig_scan.ensure(n + 8));
+  UCG_CHECK(c, c->cell_count.ensure(c->grid.ncells + 4));
+  if (n > 0) {
+    UCG_CHECK(c, cudaMemsetAsync(c->cell_count.p, 0, (c->grid.ncells + 4) * sizeof(int), st));
+    k_wrap_count<<<nblocks(n, 256), 256, 0, st>>>(c->pos.p, n, box, c->grid, c->cell_of.p, c->cell_count.p, c->d_flags.p);
+    UCG_LAUNCHED(c);
+    k_migrate_classify<<<nblocks(n, 256), 256, 0, st>>>(c->pos.p, n, box, h.grid[0], h.grid[1], h.grid[2], h.rank,
+                                                        c->mig_dest.p, c->mig_stay.p, c->img_counters.p);
+    UCG_LAUNCHED(c);
+  }
+  std::vector<int> hc(nr, 0);
+  UCG_CHECK(c, cudaMemcpyAsync(hc.data(), c->img_counters.p, nr * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if ((rc = read_flags(c))) return rc;
+  if (c->h_flags[3]) { c->err = "atoms lost: position outside the periodic box by more than one period"; return UCGB200_ERR_LOST_ATOMS; }
+  h.mig_counts = hc;
+  for (int k = 0; k < nr; k++) counts[k] = hc[k];
+  return 0;
+}
+
+// part 2: pack the leavers (grouped by destination rank, ascending) and compact the stayers
+extern "C" int ucgb200_migrate_pack(ucgb200_ctx *c, void *d_sendbuf) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  auto &h = c->halo;
+  const int nr = h.nranks, n = c->nlocal;
+  cudaStream_t st = c->stream;
+  std::vector<int> off(nr + 1, 0);
+  for (int k = 0; k < nr; k++) off[k + 1] = off[k] + h.mig_counts[k];
+  const int nleave = off[nr];
+  int rc;
+  if (nleave > 0) {
+    if (!d_sendbuf) return fail(c, "migrate_pack: null send buffer");
+    int *cursor = c->img_counters.p, *offsets = c->img_counters.p + (nr + 1);
+    UCG_CHECK(c, cudaMemsetAsync(cursor, 0, (nr + 1) * sizeof(int), st));
+    UCG_CHECK(c, cudaMemcpyAsync(offsets, off.data(), (nr + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    k_migrate_pack<<<nblocks(n, 256), 256, 0, st>>>(c->pos.p, c->vel.p, c->ts.p, c->mask.p, c->tag.p, c->mol.p, c->ucgp.p,
+                                                    c->ucgml.p, n, h.rank, c->mig_dest.p, offsets, cursor,
+                                                    (MigrateRec *)d_sendbuf);
+    UCG_LAUNCHED(c);
+    // stable compaction of the stayers
+    if ((rc = exclusive_scan(c, c->mig_stay.p, c->mig_scan.p, n, nullptr))) return rc;
+    k_stay_order<<<nblocks(n, 256), 256, 0, st>>>(c->mig_stay.p, c->mig_scan.p, n, c->order.p);
+    UCG_LAUNCHED(c);
+    if ((rc = permute_all(c, n - nleave))) return rc;
+    c->nlocal = n - nleave;
+    UCG_CHECK(c, cudaStreamSynchronize(st));
+  }
+  c->list_valid = false;
+  return 0;
+}
+
+// part 3: append the arrivals
+extern "C" int ucgb200_migrate_unpack(ucgb200_ctx *c, const void *d_recvbuf, int nrecv) {
+  if (!c || nrecv < 0) return -1;
+  cudaSetDevice(c->device);
+  int rc;
+  const int base = c->nlocal;
+  if (nrecv > 0) {
+    if (!d_recvbuf) return fail(c, "migrate_unpack: null receive buffer");
+    if ((rc = ucg_ensure_atom_capacity(c, (size_t)base + nrecv + c->nghost, (size_t)base + nrecv))) return rc;
+    k_migrate_unpack<<<nblocks(nrecv, 256), 256, 0, c->stream>>>(c->pos.p, c->vel.p, c->frc.p, c->scores.p, c->ts.p,
+                                                                 c->mask.p, c->tag.p, c->mol.p, c->ucgp.p, c->ucgml.p,
+                                                                 c->orig.p, base, nrecv, (const MigrateRec *)d_recvbuf);
+    UCG_LAUNCHED(c);
+    c->nlocal = base + nrecv;
+  }
+  // device order is the only order once sites migrate: downloads are identified by tag
+  if (c->nlocal > 0) {
+    k_iota2<<<nblocks(c->nlocal, 256), 256, 0, c->stream>>>(c->orig.p, c->nlocal);
+    UCG_LAUNCHED(c);
+  }
+  c->list_valid = false;
+  return 0;
+}
+
+extern "C" int ucgb200_halo_send_counts(ucgb200_ctx *c, int *counts) {
+  if (!c || !counts) return -1;
+  for (int k = 0; k < c->halo.nranks; k++) counts[k] = c->halo.send_counts[k];
+  return 0;
+}
+
+extern "C" int ucgb200_halo_pack_border(ucgb200_ctx *c, void *d_sendbuf) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  auto &h = c->halo;
+  if (h.nsend == 0) return 0;
+  if (!d_sendbuf) return fail(c, "halo_pack_border: null buffer");
+  ImageMap im = make_image_map(c);
+  k_pack_border<<<nblocks(h.nsend, 256), 256, 0, c->stream>>>(c->pos.p, c->ts.p, c->tag.p, c->mol.p, c->ucgp.p,
+                                                             c->img_owner.p, c->img_code.p, h.nsend, im,
+                                                             (BorderRec *)d_sendbuf);
+  UCG_LAUNCHED(c);
+  return 0;
+}
+
+// received border records (grouped by source rank, ascending) are kept until the next rebuild
+extern "C" int ucgb200_halo_unpack_border(ucgb200_ctx *c, const void *d_recvbuf, const int *recv_counts) {
+  if (!c || !recv_counts) return -1;
+  cudaSetDevice(c->device);
+  auto &h = c->halo;
+  int total = 0;
+  for (int k = 0; k < h.nranks; k++) { h.recv_counts[k] = recv_counts[k]; total += recv_counts[k]; }
+  h.nrecv = total;
+  if (total > 0) {
+    if (!d_recvbuf) return fail(c, "halo_unpack_border: null buffer");
+    UCG_CHECK(c, c->recv_border.ensure((size_t)total * sizeof(BorderRec)));
+    UCG_CHECK(c, cudaMemcpyAsync(c->recv_border.p, d_recvbuf, (size_t)total * sizeof(BorderRec), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  return 0;
+}
+
+extern "C" int ucgb200_halo_pack_forward(ucgb200_ctx *c, void *d_sendbuf) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  auto &h = c->halo;
+  if (h.nsend == 0) return 0;
+  if (!d_sendbuf) return fail(c, "halo_pack_forward: null buffer");
+  ImageMap im = make_image_map(c);
+  k_pack_forward<<<nblocks(h.nsend, 256), 256, 0, c->stream>>>(c->pos.p, c->ts.p, c->ucgp.p, c->img_owner.p, c->img_code.p,
+                                                              h.nsend, im, (ForwardRec *)d_sendbuf);
+  UCG_LAUNCHED(c);
+  return 0;
+}
+
+extern "C" int ucgb200_halo_unpack_forward(ucgb200_ctx *c, const void *d_recvbuf) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  auto &h = c->halo;
+  if (h.nrecv == 0) return 0;
+  if (!d_recvbuf) return fail(c, "halo_unpack_forward: null buffer");
+  k_unpack_forward<<<nblocks(h.nrecv, 256), 256, 0, c->stream>>>(c->pos.p, c->ts.p, c->ucgp.p, c->nlocal,
+                                                                (const ForwardRec *)d_recvbuf, c->slot_of_src.p, h.nlimg,
+                                                                h.nrecv);
   UCG_LAUNCHED(c);
   return 0;
 }
@@ -585,19 +1049,18 @@ extern "C" int ucgb200_neigh_download(ucgb200_ctx *c, int *nlocal_out, long long
   cudaSetDevice(c->device);
   if (!c->list_valid) return fail(c, "neigh_download: no valid list");
   int nlocal = c->nlocal, nall = c->nlocal + c->nghost;
-  std::vector<int> nn(nlocal);
-  if (nlocal) UCG_CHECK(c, cudaMemcpy(nn.data(), c->numneigh.p, nlocal * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<int> nn(std::max(nlocal, 1));
   UCG_CHECK(c, cudaStreamSynchronize(c->stream));
   if (nlocal) UCG_CHECK(c, cudaMemcpy(nn.data(), c->numneigh.p, nlocal * sizeof(int), cudaMemcpyDeviceToHost));
   long long t = 0;
-  for (int v : nn) t += v;
+  for (int i = 0; i < nlocal; i++) t += nn[i];
   if (nlocal_out) *nlocal_out = nlocal;
   if (!neigh_tags) { *total = t; return 0; }
   if (*total < t) return fail(c, "neigh_download: capacity too small");
   *total = t;
-  std::vector<int> tags(nall), rows((size_t)nlocal * c->neigh_stride), gcode(std::max(c->nghost, 1));
-  UCG_CHECK(c, cudaMemcpy(tags.data(), c->tag.p, nall * sizeof(int), cudaMemcpyDeviceToHost));
-  UCG_CHECK(c, cudaMemcpy(rows.data(), c->neigh.p, rows.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<int> tags(std::max(nall, 1)), rows((size_t)nlocal * c->neigh_stride + 1), gcode(std::max(c->nghost, 1));
+  if (nall) UCG_CHECK(c, cudaMemcpy(tags.data(), c->tag.p, nall * sizeof(int), cudaMemcpyDeviceToHost));
+  if (nlocal) UCG_CHECK(c, cudaMemcpy(rows.data(), c->neigh.p, (size_t)nlocal * c->neigh_stride * sizeof(int), cudaMemcpyDeviceToHost));
   if (c->nghost) UCG_CHECK(c, cudaMemcpy(gcode.data(), c->ghost_code.p, c->nghost * sizeof(int), cudaMemcpyDeviceToHost));
   long long off = 0;
   for (int i = 0; i < nlocal; i++) {
@@ -607,7 +1070,8 @@ extern "C" int ucgb200_neigh_download(ucgb200_ctx *c, int *nlocal_out, long long
     for (int k = 0; k < nn[i]; k++) {
       int j = rows[(size_t)i * c->neigh_stride + k] & UCG_NEIGHMASK;
       neigh_tags[off + k] = tags[j];
-      if (neigh_shift) neigh_shift[off + k] = j < nlocal ? 13 : gcode[j - nlocal];
+      // image code of the neighbor: 0 = owned site, 1..26 local periodic image, 32+ = from another brick
+      if (neigh_shift) neigh_shift[off + k] = j < nlocal ? 0 : gcode[j - nlocal];
     }
     off += nn[i];
   }

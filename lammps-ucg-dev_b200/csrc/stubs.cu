@@ -12,12 +12,3 @@ extern "C" int ucgb200_pair_bethe_density(ucgb200_ctx *c, int, int, int, int) NO
 extern "C" int ucgb200_cluster_configure(ucgb200_ctx *c, int, int, double, int, const int *, const int *, const double *, const double *, int, const int *, int) NOTYET("cluster_configure")
 extern "C" int ucgb200_cluster_check(ucgb200_ctx *c, int *, int *) NOTYET("cluster_check")
 extern "C" int ucgb200_cluster_switch(ucgb200_ctx *c, int, long long, int *, int *) NOTYET("cluster_switch")
-extern "C" int ucgb200_halo_configure(ucgb200_ctx *c, int, int, const int *) NOTYET("halo_configure")
-extern "C" int ucgb200_halo_send_counts(ucgb200_ctx *c, int *) NOTYET("halo_send_counts")
-extern "C" int ucgb200_halo_pack_border(ucgb200_ctx *c, int, void *) NOTYET("halo_pack_border")
-extern "C" int ucgb200_halo_set_recv_counts(ucgb200_ctx *c, const int *) NOTYET("halo_set_recv_counts")
-extern "C" int ucgb200_halo_unpack_border(ucgb200_ctx *c, int, const void *) NOTYET("halo_unpack_border")
-extern "C" int ucgb200_halo_pack_forward(ucgb200_ctx *c, int, void *) NOTYET("halo_pack_forward")
-extern "C" int ucgb200_halo_unpack_forward(ucgb200_ctx *c, int, const void *) NOTYET("halo_unpack_forward")
-extern "C" int ucgb200_neigh_build_local(ucgb200_ctx *c) NOTYET("neigh_build_local")
-extern "C" int ucgb200_neigh_build_finish(ucgb200_ctx *c) NOTYET("neigh_build_finish")

@@ -143,9 +143,18 @@ struct ucgb200_ctx {
   ucg::Buf<double2> scores, scores_alt;
   ucg::Buf<double> ucgp, ucgp_alt, ucgml, ucgml_alt;
   ucg::Buf<int> ts, ts_alt, mask, mask_alt, tag, tag_alt, mol, mol_alt, orig, orig_alt;
-  // ghosts
-  ucg::Buf<int> ghost_owner, ghost_code;
+  // ghosts: sources = local periodic images + border records received from other bricks
+  ucg::Buf<int> ghost_owner, ghost_code, ghost_src, slot_of_src;
   ucg::Buf<long long> ghost_key;
+  ucg::Buf<int> img_counters, img_owner, img_code;   // [send lists by dest rank | local images]
+  ucg::Buf<char> recv_border;
+  ucg::Buf<int> mig_dest, mig_stay, mig_scan;
+  struct Halo {
+    int rank = 0, nranks = 1;
+    int grid[3] = {1, 1, 1}, coord[3] = {0, 0, 0};
+    int nsend = 0, nrecv = 0, nlimg = 0;
+    std::vector<int> send_counts{0}, send_offsets{0, 0}, recv_counts{0}, mig_counts{0};
+  } halo;
 
   // neighbor
   double skin = 0.3, cut_override = 0.0, cutneighmax = 0.0;

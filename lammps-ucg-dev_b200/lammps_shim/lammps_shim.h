@@ -452,7 +452,7 @@ class TableFileReader {
 };
 
 // ------------------------------------------------------------------------------------ RNGs
-// [stock] RanMars / RanPark, restated from the published algorithms (see oracle/ucg_oracle.c)
+// [stock] RanMars / RanPark, restated from the published algorithms (Marsaglia; Park-Miller)
 class RanMars : protected Pointers {
   double u[98];
   int i97, j97;

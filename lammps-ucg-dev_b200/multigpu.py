@@ -1,0 +1,406 @@
+"""Brick domain decomposition over several GPUs: the host-side orchestration of what stock
+LAMMPS' Comm does for the reference over MPI (exchange / borders / forward_comm, payloads
+from AtomVecUCG's field lists, UCG/atom_vec_ucg.cpp:66-82).
+
+One process per GPU: every rank owns one brick (``Context.halo_configure``).  All pack/unpack
+work is CUDA kernels behind the C-ABI; this module only moves the packed DEVICE buffers
+between ranks — one all-to-all per exchange, every peer addressed directly over
+NVLink/NVSwitch (no staged x/y/z relay).  Two transports:
+
+* ``DistTransport``      torch.distributed (NCCL on GPUs, gloo in the CPU tests);
+* ``InProcessTransport`` all bricks in ONE process (several contexts on one GPU, or plain
+  numpy "bricks" in CPU tests) — the LAMMPS-style "1 vs P ranks" check without P GPUs.
+
+The device neighbor list is full (no reverse halo), so a step needs exactly one forward
+exchange plus the 4-byte rebuild-flag reduction.
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, List, Sequence
+
+import numpy as np
+
+
+def procgrid_for(nranks: int):
+    """2 -> 2x1x1, 4 -> 2x2x1, 8 -> 2x2x2; general: most cubic factorisation."""
+    best = (nranks, 1, 1)
+    for a in range(1, nranks + 1):
+        if nranks % a:
+            continue
+        for b in range(1, nranks // a + 1):
+            if (nranks // a) % b:
+                continue
+            c = nranks // a // b
+            g = tuple(sorted((a, b, c), reverse=True))
+            if max(g) - min(g) < max(best) - min(best) or (max(g) - min(g) == max(best) - min(best) and g > best):
+                best = g
+    return best
+
+
+def brick_of(x, box_lo, box_hi, grid):
+    """rank owning each position (same plane arithmetic as ucgb200_halo_configure / k_migrate_classify)"""
+    x = np.asarray(x)
+    lo, hi = np.asarray(box_lo, float), np.asarray(box_hi, float)
+    g = np.asarray(grid)
+    w = (hi - lo) / g
+    c = np.floor((x - lo) / w).astype(np.int64)
+    c = np.clip(c, 0, g - 1)
+    for _ in range(2):
+        c = np.where((c > 0) & (x < lo + c * w), c - 1, c)
+        c = np.where((c < g - 1) & (x >= lo + (c + 1) * w), c + 1, c)
+    return (c[:, 2] * g[1] + c[:, 1]) * g[0] + c[:, 0]
+
+
+# ------------------------------------------------------------------------------ transports
+class InProcessTransport:
+    """All ranks live in this process; buffers are torch tensors (CUDA or CPU) or numpy arrays."""
+
+    def __init__(self, nranks):
+        self.nranks = nranks
+        self.local_ranks = list(range(nranks))
+
+    def exchange_counts(self, counts: Dict[int, np.ndarray]) -> Dict[int, np.ndarray]:
+        return {r: np.array([counts[s][r] for s in range(self.nranks)], np.int64) for r in range(self.nranks)}
+
+    def all_to_all(self, send: Dict[int, object], send_counts, recv_counts, rec_bytes, alloc):
+        """send[r]: byte buffer of rank r, grouped by destination; returns recv[r] grouped by source"""
+        out = {}
+        for r in range(self.nranks):
+            total = int(recv_counts[r].sum()) * rec_bytes
+            buf = alloc(r, total)
+            off = 0
+            for s in range(self.nranks):
+                n = int(send_counts[s][r]) * rec_bytes
+                if n:
+                    so = int(send_counts[s][:r].sum()) * rec_bytes
+                    buf[off:off + n] = send[s][so:so + n]
+                off += n
+            out[r] = buf
+        return out
+
+    def allreduce_max(self, vals: Dict[int, int]) -> int:
+        return max(vals.values())
+
+    def allreduce_sum(self, vals: Dict[int, np.ndarray]) -> np.ndarray:
+        return sum(vals.values())
+
+    def barrier(self):
+        pass
+
+
+class DistTransport:
+    """One rank per process over torch.distributed (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self, dist, device):
+        import torch
+        self.dist, self.torch, self.device = dist, torch, device
+        self.rank = dist.get_rank()
+        self.nranks = dist.get_world_size()
+        self.local_ranks = [self.rank]
+
+    def exchange_counts(self, counts):
+        t = self.torch
+        send = t.as_tensor(np.asarray(counts[self.rank], np.int64), device=self.device)
+        recv = t.empty_like(send)
+        self.dist.all_to_all_single(recv, send)
+        return {self.rank: recv.cpu().numpy()}
+
+    def all_to_all(self, send, send_counts, recv_counts, rec_bytes, alloc):
+        r = self.rank
+        nrecv, nsend = int(recv_counts[r].sum()) * rec_bytes, int(send_counts[r].sum()) * rec_bytes
+        out = alloc(r, nrecv)          # buffers may be padded: exchange exact-size views
+        self.dist.all_to_all_single(out[:nrecv], send[r][:nsend], [int(c) * rec_bytes for c in recv_counts[r]],
+                                    [int(c) * rec_bytes for c in send_counts[r]])
+        return {r: out}
+
+    def allreduce_max(self, vals):
+        t = self.torch.tensor([int(vals[self.rank])], dtype=self.torch.int32, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return int(t.item())
+
+    def allreduce_sum(self, vals):
+        t = self.torch.as_tensor(np.asarray(vals[self.rank], np.float64), device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def barrier(self):
+        self.dist.barrier()
+
+
+# --------------------------------------------------------------------------------- cluster
+class BrickCluster:
+    """Drives the bricks owned by this process through rebuilds and time steps.
+
+    ``bricks[r]`` must offer the halo part of :class:`Context` (migrate_*, neigh_build_local,
+    halo_*, neigh_build_finish, neigh_decide, ...).  ``alloc(rank, nbytes)`` returns a byte
+    buffer on that brick's device exposing ``data_ptr()`` and slice assignment."""
+
+    def __init__(self, bricks: Dict[int, object], transport, alloc, rec_bytes, sync=None):
+        self.bricks, self.tr, self.alloc, self.rec = bricks, transport, alloc, rec_bytes
+        self.sync = sync or (lambda: None)
+        self.recv_counts = {}
+        self.send_counts = {}
+        self.fwd_send = {}
+        self.nrebuilds = 0
+        self.bytes_forward = 0
+
+    def _ptr(self, buf):
+        return buf.data_ptr() if buf is not None and hasattr(buf, "data_ptr") else 0
+
+    def rebuild(self):
+        tr, rec = self.tr, self.rec
+        # comm->exchange(): sites that left their brick
+        counts = {r: b.migrate_prepare().astype(np.int64) for r, b in self.bricks.items()}
+        rcounts = tr.exchange_counts(counts)
+        send = {}
+        for r, b in self.bricks.items():
+            send[r] = self.alloc(r, int(counts[r].sum()) * rec["migrate"])
+            b.migrate_pack(self._ptr(send[r]))
+        self.sync()
+        recv = tr.all_to_all(send, counts, rcounts, rec["migrate"], self.alloc)
+        self.sync()
+        for r, b in self.bricks.items():
+            b.migrate_unpack(self._ptr(recv[r]), int(rcounts[r].sum()))
+        # comm->borders(): ghost shells
+        for b in self.bricks.values():
+            b.neigh_build_local()
+        counts = {r: b.halo_send_counts().astype(np.int64) for r, b in self.bricks.items()}
+        rcounts = tr.exchange_counts(counts)
+        send = {}
+        for r, b in self.bricks.items():
+            send[r] = self.alloc(r, int(counts[r].sum()) * rec["border"])
+            b.halo_pack_border(self._ptr(send[r]))
+        self.sync()
+        recv = tr.all_to_all(send, counts, rcounts, rec["border"], self.alloc)
+        self.sync()
+        for r, b in self.bricks.items():
+            b.halo_unpack_border(self._ptr(recv[r]), rcounts[r].astype(np.int32))
+            b.neigh_build_finish()
+        self.send_counts, self.recv_counts = counts, rcounts
+        # persistent forward buffers
+        self.fwd_send = {r: self.alloc(r, int(counts[r].sum()) * rec["forward"]) for r in self.bricks}
+        self.nrebuilds += 1
+
+    def forward(self):
+        tr, rec = self.tr, self.rec
+        for r, b in self.bricks.items():
+            b.halo_pack_forward(self._ptr(self.fwd_send[r]))
+            b.ghosts_forward()
+        self.sync()
+        recv = tr.all_to_all(self.fwd_send, self.send_counts, self.recv_counts, rec["forward"], self.alloc)
+        self.sync()
+        for r, b in self.bricks.items():
+            b.halo_unpack_forward(self._ptr(recv[r]))
+            self.bytes_forward += int(self.send_counts[r].sum()) * rec["forward"]
+
+    def decide(self) -> int:
+        flags = {r: b.neigh_decide_local() for r, b in self.bricks.items()}
+        return self.tr.allreduce_max(flags)
+
+    # -- deck-level stepping (the Verlet order of SURVEY.md §3.1) ---------------------
+    def setup(self, deck):
+        self.deck = deck
+        self.rebuild()
+        for b in self.bricks.values():
+            b.pair_ucgld(1, 1)
+            self._post_force(b, 0)
+        self.ntimestep = 0
+
+    def _post_force(self, b, step):
+        d = self.deck
+        if d.get("langevin"):
+            b.fix_langevin(d["gfactor1"], d["gfactor2"], np.sqrt(d["t_target"]), d["langevin_seed"], step)
+        if d.get("ucgstate") is not None:
+            b.fix_ucgstate(mode=d["ucgstate"], seed=d.get("ucgstate_seed", 1), rate=d.get("ucgstate_rate", 0.01), step=step)
+
+    def run(self, nsteps, ev_last=False):
+        d = self.deck
+        dt = d["dt"]
+        wall = 1 if d.get("wall") else 0
+        for n in range(nsteps):
+            self.ntimestep += 1
+            ev = 1 if (ev_last and n == nsteps - 1) else 0
+            for b in self.bricks.values():
+                b.fix_nve_initial(dt, 0.5 * dt, 1, wall)
+            if self.decide():
+                self.rebuild()
+            else:
+                self.forward()
+            for b in self.bricks.values():
+                b.pair_ucgld(ev, ev)
+                self._post_force(b, self.ntimestep)
+                b.fix_nve_final(0.5 * dt, 1, wall)
+
+    def energy_virial(self):
+        vals = {}
+        for r, b in self.bricks.items():
+            e, v = b.pair_energy_virial()
+            vals[r] = np.concatenate([[e], v])
+        return self.tr.allreduce_sum(vals)
+
+    def gather_atoms(self, fields):
+        """{tag-sorted arrays} of the bricks in this process"""
+        parts = [b.atoms_download(list(fields) + ["tag"]) for b in self.bricks.values()]
+        out = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+        order = np.argsort(out["tag"], kind="stable")
+        return {k: v[order] for k, v in out.items()}
+
+
+# ------------------------------------------------------------- Context as a brick (GPU)
+def make_gpu_brick(pkg, device, stream=None):
+    """Context + the two host-level helpers the cluster needs"""
+    ctx = pkg.Context(device, stream=stream)
+
+    ctx.neigh_decide_local = ctx.neigh_decide
+    return ctx
+
+
+def torch_alloc(device):
+    import torch
+
+    def alloc(rank, nbytes):
+        return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+    return alloc
+
+
+# ------------------------------------------------------------------------------ bench leg
+def bench(args, rank, world, local, dist):
+    """bench.py --gpus N (N > 1): weak scaling, one brick of NCELL_1GPU^3 fcc cells per GPU."""
+    import json
+    import os
+    import tempfile
+
+    import torch
+
+    import bench as B
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    from lammps_ucg_dev_b200 import engine, synth
+
+    grid = procgrid_for(world)
+    per = int(os.environ.get("UCGB200_NCELL_PER_GPU", B.NCELL_1GPU))
+    ncell = (per * grid[0], per * grid[1], per * grid[2])
+    device = torch.device("cuda", local)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    td = tempfile.mkdtemp()
+    tf, sf = B.make_fixtures(td)
+    # every rank generates only its own brick of the lattice (same global jitter seed per cell)
+    liq = synth.fcc_liquid_brick(ncell, grid, rank)
+    ctx = make_gpu_brick(pkg, local, stream=stream.cuda_stream)
+    engine.setup_single_type(ctx, tf, sf, tablength=B.TABLENGTH, cut=B.CUT, skin=B.SKIN, dt=B.DT, kT=1.0,
+                             box=(liq.box_lo, liq.box_hi))
+    ctx.halo_configure(rank, world, grid)
+    engine.upload_liquid(ctx, liq)
+    tr = DistTransport(dist, device)
+    cl = BrickCluster({rank: ctx}, tr, torch_alloc(device), pkg.Context.halo_record_bytes())
+    L = B.LANGEVIN
+    ml = float(liq.ucgml[0])
+    g1 = np.array([0.0, -ml / L["t_period"], -ml / L["t_period"]])
+    g2 = np.array([0.0, 1.0, 1.0]) * np.sqrt(ml) * np.sqrt(24.0 / L["t_period"] / B.DT)
+    deck = dict(dt=B.DT, langevin=1, gfactor1=g1, gfactor2=g2, t_target=L["t_start"], langevin_seed=L["seed"], ucgstate=1)
+    cl.setup(deck)
+    cl.run(args.warmup)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = B.ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ev0.record(stream)
+    cl.run(args.steps)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches = ctx.launch_count() - l0
+    nl = torch.tensor([ctx.natoms()[0]], dtype=torch.int64, device=device)
+    dist.all_reduce(nl)
+    nsites = int(nl.item())
+    if sampler:
+        sampler.stop_flag.set()
+        sampler.join()
+
+    # pair-kernel roofline on rank 0's brick
+    total_full, _, _ = ctx.neigh_stats()
+    nloc = ctx.natoms()[0]
+    m_half = 0.5 * total_full / max(nloc, 1)
+    ctx.timers(2)
+    pms = []
+    for _ in range(5):
+        ctx.pair_ucgld(0, 0)
+        pms.append(ctx.last_pair_ms())
+    ctx.timers(0)
+    pair_avg = float(np.median(pms))
+    bps = 100.0 + 4.0 * m_half
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(B.ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = bps * nloc / (pair_avg * 1e-3) / 1e9
+
+    # e2e: same step with this rank's HOST buffers in and out every step
+    n = nloc
+    cur = ctx.atoms_download(["x", "v", "ucgl", "ucgvl", "ucgstate"])
+    pinned = {k: torch.from_numpy(v.copy()).pin_memory() for k, v in cur.items()}
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        ctx.atoms_upload(n, **{k: v.numpy() for k, v in pinned.items()})
+        cl.run(1)
+        if ctx.natoms()[0] != n:      # a rebuild migrated sites: host arrays follow the new brick population
+            return False
+        got = ctx.atoms_download(["x", "v", "f", "ucgl", "ucgvl", "ucgstate", "ucgp", "ucgforce"])
+        for k in pinned:
+            pinned[k].numpy()[:] = got[k]
+        return True
+
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(e2e_steps):
+        ok = e2e_step()
+        done += 1
+        if not ok:
+            n = ctx.natoms()[0]
+            cur = ctx.atoms_download(["x", "v", "ucgl", "ucgvl", "ucgstate"])
+            pinned = {k: torch.from_numpy(v.copy()).pin_memory() for k, v in cur.items()}
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+
+    if rank == 0:
+        cfg = B.workload_config(ncell, world)
+        cfg["workload"] = cfg["workload"].replace("1M-site", f"{nsites / 1e6:.0f}M-site")
+        cfg["sites_per_gpu"] = nsites // world
+        cfg["procgrid"] = list(grid)
+        line = {"metric": B.METRIC, "value": nsites * args.steps / (ms * 1e-3) / 1e6, "unit": B.UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "kernel": "k_pair_ucgld_fast", "kernel_ms": pair_avg, "bytes_per_site": bps,
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
+                "cpu_baseline": None,
+                "e2e": {"value": nsites * done / e2e_s / 1e6, "unit": B.UNIT, "h2d_bytes_per_step": n * 68 * world,
+                        "d2h_bytes_per_step": n * 108 * world, "steps": done,
+                        "api": "per rank: ucgb200_atoms_upload + one step + ucgb200_atoms_download"},
+                "gpu_launches": int(launches), "clocks": sampler.summary(),
+                "halo": {"forward_bytes_per_step_rank0": int(cl.send_counts[rank].sum()) * cl.rec["forward"],
+                         "rebuilds": cl.nrebuilds, "transport": "NCCL all_to_all_single over NVLink"}}
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()

@@ -67,6 +67,60 @@ def fcc_liquid(ncell, rho=RHO, jitter=0.05, T=1.0, ucgml=10.0, seed=12345, mol_s
                   meta=dict(ncell=ncell, rho=rho, a=a, T=T, seed=seed))
 
 
+def _splitmix64(x):
+    """vectorised SplitMix64: counter -> 64 well-mixed bits (decomposition-independent streams)"""
+    x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def _uniform(ids, stream):
+    with np.errstate(over="ignore"):
+        bits = _splitmix64(ids.astype(np.uint64) * np.uint64(64) + np.uint64(stream))
+    return (bits >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def _normal(ids, stream):
+    u1 = np.maximum(_uniform(ids, stream), 1e-300)
+    u2 = _uniform(ids, stream + 1)
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+
+
+def fcc_liquid_brick(ncell, grid, rank, rho=RHO, jitter=0.05, T=1.0, ucgml=10.0) -> Liquid:
+    """The sites of brick `rank` of the global ncell fcc liquid (grid = bricks per dimension).
+    Every per-site random number is a hash of the GLOBAL site id, so the global system does not
+    depend on the decomposition; jitter may push a site across a brick face — the first
+    rebuild's migration hands it to its owner."""
+    nx, ny, nz = ncell
+    gx, gy, gz = grid
+    cx, cy, cz = rank % gx, (rank // gx) % gy, rank // (gx * gy)
+    a = (4.0 / rho) ** (1.0 / 3.0)
+    rx = np.arange(cx * nx // gx, (cx + 1) * nx // gx)
+    ry = np.arange(cy * ny // gy, (cy + 1) * ny // gy)
+    rz = np.arange(cz * nz // gz, (cz + 1) * nz // gz)
+    ii, jj, kk = np.meshgrid(rx, ry, rz, indexing="ij")
+    cells = np.stack([ii.ravel(), jj.ravel(), kk.ravel()], axis=1)
+    basis = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]], dtype=np.float64)
+    cid = (cells[:, 0].astype(np.int64) * ny + cells[:, 1]) * nz + cells[:, 2]
+    gid = (cid[:, None] * 4 + np.arange(4)[None, :]).reshape(-1)
+    x = (cells[:, None, :].astype(np.float64) + basis[None, :, :]).reshape(-1, 3) * a
+    for d in range(3):
+        x[:, d] += (2.0 * _uniform(gid, 1 + d) - 1.0) * jitter
+    hi = np.array([nx, ny, nz], dtype=np.float64) * a
+    x = np.mod(x, hi)
+    x = np.minimum(x, np.nextafter(hi, 0.0))
+    n = x.shape[0]
+    ucgl = _uniform(gid, 4)
+    v = np.stack([_normal(gid, 10), _normal(gid, 12), _normal(gid, 14)], axis=1) * np.sqrt(T)
+    ucgvl = _normal(gid, 16) * np.sqrt(T / ucgml)
+    return Liquid(n=n, box_lo=np.zeros(3), box_hi=hi, x=np.ascontiguousarray(x), v=np.ascontiguousarray(v),
+                  type=np.ones(n, np.int32), mask=np.ones(n, np.int32), tag=(gid + 1).astype(np.int32),
+                  molecule=np.zeros(n, np.int32), ucgstate=(ucgl >= 0.5).astype(np.int32), ucgl=ucgl, ucgvl=ucgvl,
+                  ucgml=np.full(n, float(ucgml)), meta=dict(ncell=ncell, grid=grid, rank=rank, a=a))
+
+
 def lj_table(eps, sigma, npts, rlo=RLO, rhi=RC):
     """(r, e, f) on the RSQ grid of a LAMMPS `N npts RSQ rlo rhi` section; e shifted to 0 at rhi."""
     i = np.arange(npts, dtype=np.float64)

@@ -1,6 +1,3 @@
-set -x
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 python -m pytest tests -m gpu -x -q 2>&1 | tail -25
-python bench.py --steps 30 --warmup 5 > gpurun_out/bench1.json 2> gpurun_out/bench1.err; tail -3 gpurun_out/bench1.err; cat gpurun_out/bench1.json
