@@ -4,7 +4,6 @@
 using namespace ucg;
 #define NOTYET(name) { if (!c) return -1; return fail(c, name ": not implemented in this build"); }
 
-extern "C" int ucgb200_pair_bethe(ucgb200_ctx *c, int, int, int, int, int, double, int) NOTYET("pair_bethe")
 extern "C" int ucgb200_pair_rleucg_configure(ucgb200_ctx *c, int, const int *, const double *, const double *, const int *, const double *, double) NOTYET("pair_rleucg_configure")
 extern "C" int ucgb200_pair_rleucg(ucgb200_ctx *c, int, int) NOTYET("pair_rleucg")
 extern "C" int ucgb200_pair_bethe_density_configure(ucgb200_ctx *c, const int *, const double *, const double *) NOTYET("pair_bethe_density_configure")

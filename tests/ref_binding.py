@@ -11,17 +11,22 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "oracle", "_ref", "libucg_ref.so")
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
-_lib = None
+HOSTDRV = os.path.join(ROOT, "oracle", "_hostdrv", "libucg_hostdrv.so")   # same driver, product's GPU style classes
+_libs = {}
 
 
 def available() -> bool:
     return os.path.exists(LIB)
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        l = C.CDLL(LIB)
+def hostdrv_available() -> bool:
+    return os.path.exists(HOSTDRV)
+
+
+def lib(path=None):
+    path = path or LIB
+    if path not in _libs:
+        l = C.CDLL(path)
         l.ref_create.restype = C.c_void_p
         l.ref_error.restype = C.c_char_p
         l.ref_eng_vdwl.restype = C.c_double
@@ -29,8 +34,8 @@ def lib():
         l.ref_fix_vector.restype = C.c_double
         l.ref_ntimestep.restype = C.c_longlong
         l.ref_neigh_pairs.restype = C.c_longlong
-        _lib = l
-    return _lib
+        _libs[path] = l
+    return _libs[path]
 
 
 def _d(a):
@@ -52,8 +57,10 @@ def _pi(a):
 class RefSim:
     """A LAMMPS-like session running the reference's classes."""
 
+    LIBPATH = None   # subclass HostSim points this at the product's host-class harness
+
     def __init__(self):
-        self.l = lib()
+        self.l = lib(self.LIBPATH)
         self.h = C.c_void_p(self.l.ref_create())
 
     def __del__(self):
@@ -182,3 +189,9 @@ class RefSim:
         s.command(f"fix 2 all ucgld/langevin {t_start} {t_stop} {t_period} {seed}")
         s.command("fix 3 all ucgstate ld")
         return s
+
+
+class HostSim(RefSim):
+    """The same LAMMPS-like session, but the styles are the product's GPU-backed classes
+    (lammps-ucg-dev_b200/host/styles) calling libucgb200.so through the C-ABI."""
+    LIBPATH = HOSTDRV

@@ -306,3 +306,65 @@ def test_full_size_properties_1M(pkg, fixtures):
         assert rel_err(v, v0) <= 1e-10
         assert rel_err(a["f"], a0["f"]) <= 1e-11
     assert ctx.status()[0] == 0
+
+
+# ---------------------------------------------------------------- pair bethe
+@pytest.mark.parametrize("method,pseudo,prior", [(1, 0, 2), (0, 0, 0), (1, 0, 0), (1, 1, 2)])
+def test_pair_bethe_single_evaluation(pkg, fixtures, method, pseudo, prior):
+    """PairTable_UCG_Bethe::compute vs the (reference-pinned) oracle on the pristine liquid"""
+    liq = _liq(7)
+    ctx = decks.gpu_single_type(pkg, liq, fixtures)
+    ctx.neigh_build()
+    ctx.pair_bethe(1, 1, method=method, pseudo=pseudo, prior=prior)
+    o = decks.orc_single_type(liq, fixtures)
+    o.pair_bethe_config(method, pseudo, prior)
+    ref = decks.oracle_forces(o, pair="bethe")
+    got = ctx.atoms_download(["f", "ucgforce", "ucgsoftmaxscores", "num_ucgstates"])
+    e, vir = ctx.pair_energy_virial()
+    assert rel_err(got["f"], ref["f"]) <= F_TOL
+    assert abs(e - o.eng_vdwl()) <= E_TOL * abs(o.eng_vdwl())
+    assert rel_err(vir, o.virial()) <= E_TOL
+    assert not got["ucgforce"].any() and not ref["ucgforce"].any()
+    if pseudo == 0:      # SCE scores depend on the half-list row owner in the reference (DESIGN.md Q24)
+        assert rel_err(got["ucgsoftmaxscores"], ref["ucgsoftmaxscores"]) <= F_TOL
+    assert ctx.status()[0] == 0
+
+
+def test_pair_bethe_trajectory_with_ucgstate(pkg, fixtures):
+    """bethe + nve/ucgld + ucgstate (deterministic): ucgl = ucgp after every step, the regime in
+    which the reference's prior rule does not depend on the list order"""
+    liq = _liq(7)
+    nsteps = 25
+    ctx = decks.gpu_single_type(pkg, liq, fixtures)
+    o = decks.orc_single_type(liq, fixtures)
+    o.pair_bethe_config(1, 0, 2)
+    o.fix_ttarget(1.0); o.fix_nve(); o.fix_ucgstate(mode=0)
+    ctx.deck_configure(pair_style=1, bethe_method=1, bethe_pseudo=0, bethe_prior=2, nve=1, ucgstate=1, thermo_every=nsteps)
+    ctx.setup(); o.setup()
+    ctx.run(nsteps); o.run(nsteps, thermo_every=nsteps)
+    got = ctx.atoms_download(["x", "v", "f", "ucgl", "ucgp", "ucgstate"])
+    ref = o.get_atoms()
+    box = liq.box_hi - liq.box_lo
+    dx = got["x"] - ref["x"]
+    dx -= box * np.round(dx / box)
+    assert np.abs(dx).max() <= 1e-9
+    assert rel_err(got["f"], ref["f"]) <= F_TOL
+    assert rel_err(got["ucgp"], ref["ucgp"]) <= 1e-8
+    away = np.abs(ref["ucgp"] - 0.5) > 1e-7
+    assert np.array_equal(got["ucgstate"][away], ref["ucgstate"][away])
+    assert abs(ctx.thermo()[0] - o.eng_vdwl()) <= 1e-7 * abs(o.eng_vdwl())
+
+
+def test_pair_bethe_mixed_types(pkg, fixtures):
+    liq = decks.mixed_types(_liq(6))
+    ctx = decks.gpu_mixed(pkg, liq, fixtures)
+    ctx.neigh_build()
+    ctx.pair_bethe(1, 1, method=1, pseudo=0, prior=2)
+    o = decks.orc_mixed(liq, fixtures)
+    o.pair_bethe_config(1, 0, 2)
+    ref = decks.oracle_forces(o, pair="bethe")
+    got = ctx.atoms_download(["f", "ucgsoftmaxscores"])
+    e, vir = ctx.pair_energy_virial()
+    assert rel_err(got["f"], ref["f"]) <= F_TOL
+    assert abs(e - o.eng_vdwl()) <= E_TOL * abs(o.eng_vdwl())
+    assert rel_err(got["ucgsoftmaxscores"], ref["ucgsoftmaxscores"]) <= F_TOL
