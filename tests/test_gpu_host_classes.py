@@ -98,6 +98,9 @@ def test_error_texts(pkg, fixtures, tmp_path):
 
 def test_bethe_deck(pkg, fixtures):
     liq = _liq(6)
+    # lambda at rest: ucgl stays equal to ucgp between steps, the regime in which the reference's
+    # prior rule (ucgl for the row owner, ucgp for the neighbor, quirk Q7) is list-order independent
+    liq.ucgvl[:] = 0.0
     sims = []
     for cls in (rb.RefSim, rb.HostSim):
         s = cls.single_type(liq, fixtures["table4096"], fixtures["state"], pair="table_ucg_bethe",

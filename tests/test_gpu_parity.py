@@ -334,6 +334,7 @@ def test_pair_bethe_trajectory_with_ucgstate(pkg, fixtures):
     """bethe + nve/ucgld + ucgstate (deterministic): ucgl = ucgp after every step, the regime in
     which the reference's prior rule does not depend on the list order"""
     liq = _liq(7)
+    liq.ucgvl[:] = 0.0      # lambda at rest (ucgforce is 0 in this style), so ucgl == ucgp at every evaluation
     nsteps = 25
     ctx = decks.gpu_single_type(pkg, liq, fixtures)
     o = decks.orc_single_type(liq, fixtures)
