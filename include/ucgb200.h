@@ -166,11 +166,19 @@ int ucgb200_pair_ucgld(ucgb200_ctx *ctx, int eflag, int vflag);
  * prior 0 = chemical potential, 2 = ucgl (noise prior is stochastic: seed/noise). */
 int ucgb200_pair_bethe(ucgb200_ctx *ctx, int eflag, int vflag, int method, int pseudo, int prior,
                        double noise_level, int seed);
-/* PairTable_RLEUCG_INTERFACE::compute (pair_table_rleucg_interface.cpp:177-505) */
-int ucgb200_pair_rleucg_configure(ucgb200_ctx *ctx, int n_types, const int *n_states_of_type,
-                                  const double *threshold_radius, const double *density_threshold,
-                                  const int *tabindex, const double *cutsq, double T);
+/* PairTable_RLEUCG_INTERFACE::compute (pair_table_rleucg_interface.cpp:177-505).  In this style
+ * atom types are STATE types (a 2-state site of base type t uses tables of types t, t+1).
+ * Arrays are 1-based: actual_from_state[ntypes+1] (:649-652), n_states/use_entropy/cv_threshold/
+ * threshold_radius[n_actual+1] (:618-640), chem_pot[ntypes+1] (:641-647), tabindex and
+ * cutsq[(ntypes+1)^2] (coeff :736-741, init_one :802-809), mass[ntypes+1]; kT as for the
+ * other styles (init_style :781-792).  Tables come from ucgb200_table_upload. */
+int ucgb200_pair_rleucg_configure(ucgb200_ctx *ctx, int ntypes, const int *actual_from_state, int n_actual,
+                                  const int *n_states, const int *use_entropy, const double *cv_threshold,
+                                  const double *threshold_radius, const double *chem_pot, const int *tabindex,
+                                  const double *cutsq, const double *mass, double kT);
 int ucgb200_pair_rleucg(ucgb200_ctx *ctx, int eflag, int vflag);
+/* substate_probability[i][0] and the CV force F_p*dp/drho of the last evaluation (host order) */
+int ucgb200_pair_rleucg_probabilities(ucgb200_ctx *ctx, int cap, double *prob, double *cvforce);
 /* PairTable_UCG_Bethe_Density::compute, repaired semantics */
 int ucgb200_pair_bethe_density_configure(ucgb200_ctx *ctx, const int *density_type_flag,
                                          const double *density_threshold, const double *threshold_radius);

@@ -298,10 +298,19 @@ class Context:
         self._ck(self._l.ucgb200_pair_bethe(self._h, int(eflag), int(vflag), int(method), int(pseudo),
                                             int(prior), C.c_double(noise), int(seed)))
 
-    def pair_rleucg_configure(self, n_types, n_states_of_type, threshold_radius, density_threshold,
-                              tabindex, cutsq, T):
-        a, b, c_, d, e = _i(n_states_of_type), _d(threshold_radius), _d(density_threshold), _i(tabindex).reshape(-1), _d(cutsq).reshape(-1)
-        self._ck(self._l.ucgb200_pair_rleucg_configure(self._h, int(n_types), _pi(a), _pd(b), _pd(c_), _pi(d), _pd(e), C.c_double(T)))
+    def pair_rleucg_configure(self, ntypes, actual_from_state, n_actual, n_states, use_entropy, cv_threshold,
+                              threshold_radius, chem_pot, tabindex, cutsq, mass, kT):
+        a = [_i(actual_from_state), _i(n_states), _i(use_entropy), _d(cv_threshold), _d(threshold_radius),
+             _d(chem_pot), _i(tabindex).reshape(-1), _d(cutsq).reshape(-1), _d(mass)]
+        self._ck(self._l.ucgb200_pair_rleucg_configure(
+            self._h, int(ntypes), _pi(a[0]), int(n_actual), _pi(a[1]), _pi(a[2]), _pd(a[3]), _pd(a[4]), _pd(a[5]),
+            _pi(a[6]), _pd(a[7]), _pd(a[8]), C.c_double(kT)))
+
+    def pair_rleucg_probabilities(self):
+        n = self.natoms()[0]
+        p, f = np.zeros(n), np.zeros(n)
+        self._ck(self._l.ucgb200_pair_rleucg_probabilities(self._h, int(n), _pd(p), _pd(f)))
+        return p, f
 
     def pair_rleucg(self, eflag=0, vflag=0):
         self._ck(self._l.ucgb200_pair_rleucg(self._h, int(eflag), int(vflag)))

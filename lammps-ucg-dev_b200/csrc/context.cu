@@ -59,7 +59,7 @@ extern "C" int ucgb200_destroy(ucgb200_ctx *c) {
   c->cluster.d_typemap.release(); c->cluster.d_contact.release(); c->cluster.d_molflag.release();
   c->cluster.d_prob.release();
   c->dens.d_prob.release(); c->dens.d_partial.release(); c->dens.d_pforce.release();
-  c->dens.d_cvforce.release(); c->dens.d_tabindex.release(); c->dens.d_cutsq.release();
+  c->dens.d_cvforce.release(); c->dens.d_tabindex.release(); c->dens.d_cutsq.release(); c->dens.d_rt.release();
   if (c->h_flags) cudaFreeHost(c->h_flags);
   cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b);
   cudaEventDestroy(c->ev_pair0); cudaEventDestroy(c->ev_pair1);
@@ -211,8 +211,11 @@ extern "C" int ucgb200_set_pair_maps(ucgb200_ctx *c, const int *tabindex, const 
 
 // Build the device-side type/pair maps and, when the deck qualifies, the interleaved
 // table for the shared-memory pair kernel.
+int ucg_rebuild_rle_maps(ucgb200_ctx *c);
+
 int ucg::rebuild_maps(ucgb200_ctx *c) {
   if (!c->maps_dirty) return 0;
+  if (c->dens.set) { cudaSetDevice(c->device); return ucg_rebuild_rle_maps(c); }
   if (c->n_actual < 1) return fail(c, "types not set");
   if (c->tabindex.empty()) return fail(c, "All pair coeffs are not set");
   cudaSetDevice(c->device);

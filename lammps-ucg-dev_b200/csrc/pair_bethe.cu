@@ -198,6 +198,7 @@ extern "C" int ucgb200_pair_bethe(ucgb200_ctx *c, int eflag, int vflag, int meth
   if (rc) return rc;
   if (!c->list_valid) return fail(c, "pair_bethe: neighbor list not built");
   c->ev_valid = false;
+  c->ev_two_parts = false;
   if (c->nlocal == 0) return 0;
   const bool ev = eflag || vflag;
   constexpr int LPA = 8, BS = 256;

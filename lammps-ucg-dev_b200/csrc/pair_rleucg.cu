@@ -1,0 +1,394 @@
+// pair_rleucg.cu — PairTable_RLEUCG_INTERFACE::compute (UCG/pair_table_rleucg_interface.cpp:177-505)
+// for sm_100a: the original RLE-UCG mean-field local-density style (full list, newton off).
+//
+// Atom types are STATE types: a 2-state site of base type t interacts through tables
+// tabindex[t+a][t'+b] weighted p_a p_b (:339,354,400).  Three sweeps over the full rows:
+//   1. k_rle_density   rho_i = sum_j 1/2 (1 - tanh((r - r_th)/(0.1 r_th)))               (:232-276, :165-168)
+//                      p_i = 1/2 + 1/2 tanh((rho - rho_th)/(0.1 rho_th)), dp/drho       (:88-99)
+//      + ghost refresh of (p, dp/drho)                         == comm->forward_comm(this) (:278)
+//   2. k_rle_pair      one-body probability force -kT ln(p/(1-p)) - mu                      (:296-322)
+//                      f_i += d * sum_ab p_a p_b f_ab, E, virial, pair part of the
+//                      probability force                                                   (:326-442)
+//      + ghost refresh of cvf = F_p * dp/drho
+//   3. k_rle_back      CV back-force: the reference scatters -fpair*d to j and reverse-
+//                      communicates (:448-502); with the full symmetric list the same sum
+//                      arrives at the centre site as
+//                      f_i += sum_j (cvf_i g_i(r) + cvf_j g_j(r))/r * d,  g = |d prox/dr|   (:170-174)
+// As-is quirks reproduced: the density->probability map exists for actual
+// type 1 only (else UCGB200_ERR_DENSITY_TYPE); the pair part of the probability force and the
+// full virial weight are only tallied for GHOST neighbors / halved for ghost neighbors exactly
+// as the reference's branches do, so single-domain results equal the reference's single-rank
+// run.  Deviation (Q16): the pair energy is always evaluated — the reference feeds a stale
+// `evdwl` into the probability force on steps without eflag.
+#include "pair_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+using namespace ucg;
+
+namespace {
+
+struct RleType {   // per STATE type
+  int actual, nstates, entropy, pad;
+  double mu;       // chemical_potentials[t]
+  double cv_th;    // cv_thresholds[actual]
+  double r_th;     // threshold_radii[actual]
+};
+
+struct RleArgs {
+  const double4 *pos;
+  const int *ts;
+  const int *tag;
+  int nlocal;
+  const int *neigh;
+  int stride;
+  const int *numneigh;
+  const PairInfo *pinfo;   // per state-type pair: cutsq, tab[0]
+  const RleType *rt;
+  const int *tabindex;     // [(nt)*(nt)]
+  int nt;                  // ntypes + 1
+  const TableDev *tables;
+  double special_lj[4];
+  double kT;
+  double *prob, *partial, *cvf;   // [nall]
+  double4 *frc;
+  double *partials;
+  ErrWord *err;
+};
+
+__device__ __forceinline__ double prox(double r, double rth) {
+  return 0.5 * (1.0 - tanh((r - rth) / (0.1 * rth)));
+}
+__device__ __forceinline__ double prox_der(double r, double rth) {
+  const double t = tanh((r - rth) / (0.1 * rth));
+  return 0.5 * (1.0 - t * t) / (0.1 * rth);
+}
+
+template <int LPA, int BS>
+__global__ void __launch_bounds__(BS) k_rle_density(RleArgs p) {
+  const int gid = (blockIdx.x * BS + threadIdx.x) / LPA;
+  const int sub = threadIdx.x % LPA;
+  const bool active = gid < p.nlocal;
+  const int i = active ? gid : 0;
+  const double4 ri = p.pos[i];
+  const int ti = p.ts[i] & 0xffff;
+  const RleType rti = p.rt[ti];
+  const int jnum = (active && rti.nstates > 1) ? p.numneigh[i] : 0;
+  const int *row = p.neigh + (size_t)i * p.stride;
+  const PairInfo *prow = p.pinfo + ti * p.nt;
+  double rho = 0.0;
+  for (int jj = sub; jj < jnum; jj += LPA) {
+    const int j = row[jj] & UCG_NEIGHMASK;
+    const double4 rj = p.pos[j];
+    const int tj = p.ts[j] & 0xffff;
+    const double rsq = rsq_exact(ri.x - rj.x, ri.y - rj.y, ri.z - rj.z);
+    if (rsq < prow[tj].cutsq) rho += prox(sqrt(rsq), rti.r_th);
+  }
+  rho = group_sum<LPA>(rho);
+  if (active && sub == 0) {
+    double pr = 1.0, pa = 0.0;
+    if (rti.nstates > 1) {
+      if (rti.actual != 1) report_error(p.err, UCGB200_ERR_DENSITY_TYPE, p.tag[i], 0, rho);
+      const double t = tanh((rho - rti.cv_th) / (0.1 * rti.cv_th));
+      pr = 0.5 + 0.5 * t;
+      pa = 0.5 * (1.0 - t * t) / (0.1 * rti.cv_th);
+    }
+    p.prob[i] = pr;
+    p.partial[i] = pa;
+  }
+}
+
+template <int LPA, int BS>
+__global__ void __launch_bounds__(BS) k_rle_pair(RleArgs p) {
+  const int gid = (blockIdx.x * BS + threadIdx.x) / LPA;
+  const int sub = threadIdx.x % LPA;
+  const bool active = gid < p.nlocal;
+  const int i = active ? gid : 0;
+  const double4 ri = p.pos[i];
+  const int ti = p.ts[i] & 0xffff;
+  const RleType rti = p.rt[ti];
+  const int ni = rti.nstates;
+  const double pi0 = p.prob[i];
+  const int jnum = active ? p.numneigh[i] : 0;
+  const int *row = p.neigh + (size_t)i * p.stride;
+  const PairInfo *prow = p.pinfo + ti * p.nt;
+  double fx = 0, fy = 0, fz = 0, pf = 0, eacc = 0;
+  double vir[6] = {0, 0, 0, 0, 0, 0};
+  for (int jj = sub; jj < jnum; jj += LPA) {
+    const int jraw = row[jj];
+    const double factor_lj = p.special_lj[(jraw >> UCG_SBBITS) & 3];
+    const int j = jraw & UCG_NEIGHMASK;
+    const double4 rj = p.pos[j];
+    const int tj = p.ts[j] & 0xffff;
+    const double dx = ri.x - rj.x, dy = ri.y - rj.y, dz = ri.z - rj.z;
+    const double rsq = rsq_exact(dx, dy, dz);
+    if (rsq < prow[tj].cutsq) {
+      const int nj = p.rt[tj].nstates;
+      const double pj0 = p.prob[j];
+      const bool jlocal = j < p.nlocal;
+      double elj = 0.0, pfv = 0.0;
+      bool bad = false;
+      for (int a = 0; a < ni && !bad; a++) {
+        const double pa = ni > 1 ? (a == 0 ? pi0 : 1.0 - pi0) : 1.0;
+        for (int b = 0; b < nj; b++) {
+          const double pb = nj > 1 ? (b == 0 ? pj0 : 1.0 - pj0) : 1.0;
+          double e, f;
+          const int ec = table_eval(p.tables[p.tabindex[(ti + a) * p.nt + (tj + b)]], rsq, e, f);
+          if (ec) { report_error(p.err, ec, p.tag[i], p.tag[j], rsq); bad = true; break; }
+          e *= factor_lj;
+          const double fp = factor_lj * f * pa * pb;
+          fx += dx * fp; fy += dy * fp; fz += dz * fp;
+          if (jlocal) { elj += e * pa * pb * 0.5; pfv += fp * 0.5; }
+          else {
+            elj += e * pa * pb; pfv += fp;
+            if (ni > 1) pf += (a == 0) ? -pb * e : pb * e;   // (sic) ghost neighbors only, Q17
+          }
+        }
+      }
+      const double w = jlocal ? 1.0 : 0.5;   // ev_tally with newton off
+      eacc += w * elj;
+      vir[0] += w * dx * dx * pfv; vir[1] += w * dy * dy * pfv; vir[2] += w * dz * dz * pfv;
+      vir[3] += w * dx * dy * pfv; vir[4] += w * dx * dz * pfv; vir[5] += w * dy * dz * pfv;
+    }
+  }
+  fx = group_sum<LPA>(fx); fy = group_sum<LPA>(fy); fz = group_sum<LPA>(fz);
+  pf = group_sum<LPA>(pf);
+  eacc = group_sum<LPA>(eacc);
+  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const double v = group_sum<LPA>(vir[k]);
+    if (active && sub == 0) ev[1 + k] = v;
+  }
+  if (active && sub == 0) {
+    double cvf = 0.0;
+    if (ni > 1) {
+      // one-body terms (:296-322)
+      if (rti.entropy) pf -= p.kT * log(pi0);
+      pf -= rti.mu;
+      if (rti.entropy) pf += p.kT * log(1.0 - pi0);
+      cvf = pf * p.partial[i];
+    }
+    p.cvf[i] = cvf;
+    p.frc[i] = make_double4(fx, fy, fz, 0.0);
+    ev[0] = eacc;
+  }
+  block_reduce_store<7, BS>(ev, p.partials);
+}
+
+template <int LPA, int BS>
+__global__ void __launch_bounds__(BS) k_rle_back(RleArgs p) {
+  const int gid = (blockIdx.x * BS + threadIdx.x) / LPA;
+  const int sub = threadIdx.x % LPA;
+  const bool active = gid < p.nlocal;
+  const int i = active ? gid : 0;
+  const double4 ri = p.pos[i];
+  const int ti = p.ts[i] & 0xffff;
+  const RleType rti = p.rt[ti];
+  const double cvf_i = p.cvf[i];
+  const int jnum = active ? p.numneigh[i] : 0;
+  const int *row = p.neigh + (size_t)i * p.stride;
+  const PairInfo *prow = p.pinfo + ti * p.nt;
+  double fx = 0, fy = 0, fz = 0;
+  double vir[6] = {0, 0, 0, 0, 0, 0};
+  for (int jj = sub; jj < jnum; jj += LPA) {
+    const int j = row[jj] & UCG_NEIGHMASK;
+    const double4 rj = p.pos[j];
+    const int tj = p.ts[j] & 0xffff;
+    const double dx = ri.x - rj.x, dy = ri.y - rj.y, dz = ri.z - rj.z;
+    const double rsq = rsq_exact(dx, dy, dz);
+    if (rsq < prow[tj].cutsq) {
+      const double r = sqrt(rsq);
+      const RleType rtj = p.rt[tj];
+      const double own = rti.nstates > 1 ? cvf_i * prox_der(r, rti.r_th) / r : 0.0;     // i's loop (:478-481)
+      const double oth = rtj.nstates > 1 ? p.cvf[j] * prox_der(r, rtj.r_th) / r : 0.0;  // what j's loop scatters to i
+      const double fp = own + oth;
+      fx += fp * dx; fy += fp * dy; fz += fp * dz;
+      const double w = (j < p.nlocal ? 1.0 : 0.5) * own;   // ev_tally(i,j,...,fpair) in i's loop only (:488)
+      vir[0] += w * dx * dx; vir[1] += w * dy * dy; vir[2] += w * dz * dz;
+      vir[3] += w * dx * dy; vir[4] += w * dx * dz; vir[5] += w * dy * dz;
+    }
+  }
+  fx = group_sum<LPA>(fx); fy = group_sum<LPA>(fy); fz = group_sum<LPA>(fz);
+  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const double v = group_sum<LPA>(vir[k]);
+    if (active && sub == 0) ev[1 + k] = v;
+  }
+  if (active && sub == 0) {
+    double4 f = p.frc[i];
+    f.x += fx; f.y += fy; f.z += fz;
+    p.frc[i] = f;
+  }
+  block_reduce_store<7, BS>(ev, p.partials);
+}
+
+// forward_comm(this) to self: copy a per-site scalar from the owners to their local images
+__global__ void k_ghost_scalar(double *__restrict__ a, double *__restrict__ b, int nlocal, int nlimg,
+                               const int *__restrict__ owner, const int *__restrict__ slot_of_src) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nlimg) return;
+  const int s = nlocal + slot_of_src[k], o = owner[k];
+  a[s] = a[o];
+  if (b) b[s] = b[o];
+}
+
+}  // namespace
+
+extern "C" int ucgb200_pair_rleucg_configure(ucgb200_ctx *c, int ntypes, const int *actual_from_state, int n_actual,
+                                             const int *n_states, const int *use_entropy, const double *cv_threshold,
+                                             const double *threshold_radius, const double *chem_pot, const int *tabindex,
+                                             const double *cutsq, const double *mass, double kT) {
+  if (!c || ntypes < 1 || !actual_from_state || !n_states || !cv_threshold || !threshold_radius || !tabindex || !cutsq) return -1;
+  if (!(kT > 0)) return fail(c, "pair_rleucg: kT must be positive (no fix exports t_target?)");
+  auto &d = c->dens;
+  d.n_types = ntypes;
+  d.n_actual = n_actual;
+  d.actual_from_state.assign(actual_from_state, actual_from_state + ntypes + 1);
+  d.n_states_of_type.assign(n_states, n_states + n_actual + 1);
+  d.use_entropy.assign(n_actual + 1, 0);
+  if (use_entropy) d.use_entropy.assign(use_entropy, use_entropy + n_actual + 1);
+  d.density_threshold.assign(cv_threshold, cv_threshold + n_actual + 1);
+  d.threshold_radius.assign(threshold_radius, threshold_radius + n_actual + 1);
+  d.chem_pot.assign(ntypes + 1, 0.0);
+  if (chem_pot) d.chem_pot.assign(chem_pot, chem_pot + ntypes + 1);
+  const int nt = ntypes + 1;
+  d.tabindex.assign(tabindex, tabindex + nt * nt);
+  d.cutsq.assign(cutsq, cutsq + nt * nt);
+  d.mass.assign(nt, 1.0);
+  if (mass) d.mass.assign(mass, mass + nt);
+  d.T = kT;
+  c->kT = kT;
+  for (int t = 1; t <= ntypes; t++) {
+    int a = d.actual_from_state[t];
+    if (a < 1 || a > n_actual) return fail(c, "pair_rleucg: state type without an actual type");
+  }
+  d.set = true;
+  c->maps_dirty = true;
+  return 0;
+}
+
+// device maps for the RLE-UCG mode (called from rebuild_maps)
+int ucg_rebuild_rle_maps(ucgb200_ctx *c) {
+  auto &d = c->dens;
+  const int nt = d.n_types + 1;
+  const int ntab = (int)c->tables.size();
+  std::vector<PairInfo> pi(nt * nt);
+  std::vector<TypeInfo> ti(nt);
+  std::vector<RleType> rt(nt);
+  c->max_cut = 0.0;
+  for (int t = 1; t < nt; t++) {
+    const int a = d.actual_from_state[t];
+    ti[t].nstates = 1; ti[t].mass = d.mass[t]; ti[t].mu0 = ti[t].mu1 = ti[t].dmu = 0.0;
+    rt[t].actual = a; rt[t].nstates = d.n_states_of_type[a]; rt[t].entropy = d.use_entropy[a];
+    rt[t].mu = d.chem_pot[t]; rt[t].cv_th = d.density_threshold[a]; rt[t].r_th = d.threshold_radius[a];
+    // a 2-state base type t uses tables of types t and t+1
+    if (rt[t].nstates > 1 && t + rt[t].nstates - 1 > d.n_types) { c->err = "pair_rleucg: substates exceed ntypes"; return -1; }
+  }
+  for (int i = 1; i < nt; i++)
+    for (int j = 1; j < nt; j++) {
+      PairInfo &p = pi[i * nt + j];
+      p.cutsq = d.cutsq[i * nt + j];
+      double cut = std::sqrt(p.cutsq);
+      if (c->cut_override > 0) cut = std::max(cut, c->cut_override);
+      const double cn = cut + c->skin;
+      p.cutneighsq = cn * cn;
+      c->max_cut = std::max(c->max_cut, cut);
+      p.ni = p.nj = 1;
+      const int tix = d.tabindex[i * nt + j];
+      if (p.cutsq > 0 && (tix < 0 || tix >= ntab)) { c->err = "pair_rleucg: tabindex refers to a table that was not uploaded"; return -1; }
+      for (int k = 0; k < 4; k++) p.tab[k] = tix;
+    }
+  UCG_CHECK(c, c->d_typeinfo.ensure(nt));
+  UCG_CHECK(c, cudaMemcpy(c->d_typeinfo.p, ti.data(), nt * sizeof(TypeInfo), cudaMemcpyHostToDevice));
+  UCG_CHECK(c, c->d_pairinfo.ensure(nt * nt));
+  UCG_CHECK(c, cudaMemcpy(c->d_pairinfo.p, pi.data(), nt * nt * sizeof(PairInfo), cudaMemcpyHostToDevice));
+  UCG_CHECK(c, c->d_tables.ensure(std::max(ntab, 1)));
+  if (ntab) UCG_CHECK(c, cudaMemcpy(c->d_tables.p, c->tables.data(), ntab * sizeof(TableDev), cudaMemcpyHostToDevice));
+  UCG_CHECK(c, d.d_rt.ensure(nt * sizeof(RleType)));
+  UCG_CHECK(c, cudaMemcpy(d.d_rt.p, rt.data(), nt * sizeof(RleType), cudaMemcpyHostToDevice));
+  UCG_CHECK(c, d.d_tabindex.ensure(nt * nt));
+  UCG_CHECK(c, cudaMemcpy(d.d_tabindex.p, d.tabindex.data(), nt * nt * sizeof(int), cudaMemcpyHostToDevice));
+  c->n_actual = d.n_types;   // the neighbor build indexes PairInfo by (state) type
+  c->fast_uniform = false;
+  c->maps_dirty = false;
+  c->list_valid = false;
+  return 0;
+}
+
+extern "C" int ucgb200_pair_rleucg(ucgb200_ctx *c, int eflag, int vflag) {
+  if (!c) return -1;
+  if (!c->dens.set) return fail(c, "pair_rleucg: not configured");
+  if (c->halo.nranks > 1) return fail(c, "pair_rleucg: the extra forward exchanges of (p, dp, cvf) across bricks are not built yet");
+  cudaSetDevice(c->device);
+  int rc = rebuild_maps(c);
+  if (rc) return rc;
+  if (!c->list_valid) return fail(c, "pair_rleucg: neighbor list not built");
+  c->ev_valid = false;
+  if (c->nlocal == 0) return 0;
+  (void)eflag; (void)vflag;
+  auto &d = c->dens;
+  const int nall = c->nlocal + c->nghost;
+  UCG_CHECK(c, d.d_prob.ensure(nall));
+  UCG_CHECK(c, d.d_partial.ensure(nall));
+  UCG_CHECK(c, d.d_cvforce.ensure(nall));
+  constexpr int LPA = 8, BS = 256;
+  const int nblk = nblocks((long long)c->nlocal * LPA, BS);
+  UCG_CHECK(c, c->d_partials.ensure((size_t)nblk * 8 + 64));
+  RleArgs a{};
+  a.pos = c->pos.p; a.ts = c->ts.p; a.tag = c->tag.p; a.nlocal = c->nlocal;
+  a.neigh = c->neigh.p; a.stride = c->neigh_stride; a.numneigh = c->numneigh.p;
+  a.pinfo = c->d_pairinfo.p; a.rt = (const RleType *)d.d_rt.p; a.tabindex = d.d_tabindex.p; a.nt = d.n_types + 1;
+  a.tables = c->d_tables.p;
+  for (int k = 0; k < 4; k++) a.special_lj[k] = c->special_lj[k];
+  a.kT = d.T;
+  a.prob = d.d_prob.p; a.partial = d.d_partial.p; a.cvf = d.d_cvforce.p;
+  a.frc = c->frc.p; a.partials = c->d_partials.p; a.err = c->d_err.p;
+  const auto &h = c->halo;
+  const int *lown = c->img_owner.p + h.nsend;
+  if (c->timers_on) cudaEventRecord(c->ev_pair0, c->stream);
+  k_rle_density<LPA, BS><<<nblk, BS, 0, c->stream>>>(a);
+  UCG_LAUNCHED(c);
+  if (h.nlimg) {
+    k_ghost_scalar<<<nblocks(h.nlimg, 256), 256, 0, c->stream>>>(a.prob, a.partial, c->nlocal, h.nlimg, lown, c->slot_of_src.p);
+    UCG_LAUNCHED(c);
+  }
+  k_rle_pair<LPA, BS><<<nblk, BS, 0, c->stream>>>(a);
+  UCG_LAUNCHED(c);
+  if ((rc = reduce_partials(c, nblk, 7, 0))) return rc;
+  if (h.nlimg) {
+    k_ghost_scalar<<<nblocks(h.nlimg, 256), 256, 0, c->stream>>>(a.cvf, nullptr, c->nlocal, h.nlimg, lown, c->slot_of_src.p);
+    UCG_LAUNCHED(c);
+  }
+  k_rle_back<LPA, BS><<<nblk, BS, 0, c->stream>>>(a);
+  UCG_LAUNCHED(c);
+  if ((rc = reduce_partials(c, nblk, 7, 16))) return rc;   // second virial part -> d_ev[16..22]
+  if (c->timers_on) { cudaEventRecord(c->ev_pair1, c->stream); c->pair_timed = true; }
+  // scores are not used by this style; ucgsoftmaxscores keep their cleared value
+  UCG_CHECK(c, cudaMemsetAsync(c->scores.p, 0, (size_t)c->nlocal * sizeof(double2), c->stream));
+  c->ev_valid = true;
+  c->ev_two_parts = true;
+  return 0;
+}
+
+// per-site substate probabilities of the last evaluation (diagnostics / tests), host order
+extern "C" int ucgb200_pair_rleucg_probabilities(ucgb200_ctx *c, int cap, double *prob, double *cvforce) {
+  if (!c || cap < c->nlocal) return -1;
+  cudaSetDevice(c->device);
+  auto &d = c->dens;
+  const int n = c->nlocal;
+  if (n == 0) return 0;
+  std::vector<double> p(n), f(n);
+  std::vector<int> orig(n);
+  UCG_CHECK(c, cudaMemcpyAsync(p.data(), d.d_prob.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  UCG_CHECK(c, cudaMemcpyAsync(f.data(), d.d_cvforce.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  UCG_CHECK(c, cudaMemcpyAsync(orig.data(), c->orig.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  UCG_CHECK(c, cudaStreamSynchronize(c->stream));
+  for (int s = 0; s < n; s++) {
+    if (prob) prob[orig[s]] = p[s];
+    if (cvforce) cvforce[orig[s]] = f[s];
+  }
+  return 0;
+}

@@ -365,6 +365,7 @@ extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
   if (rc) return rc;
   if (!c->list_valid) return fail(c, "pair_ucgld: neighbor list not built");
   c->ev_valid = false;
+  c->ev_two_parts = false;
   if (c->nlocal == 0) return 0;
   const bool ev = eflag || vflag;
   int nblk = 0;
@@ -427,9 +428,11 @@ extern "C" int ucgb200_pair_energy_virial(ucgb200_ctx *c, double *eng_vdwl, doub
   if (!c) return -1;
   cudaSetDevice(c->device);
   if (!c->ev_valid) return fail(c, "no energy/virial available: last pair call had eflag=vflag=0");
-  double h[7];
+  double h[7], h2[7] = {0, 0, 0, 0, 0, 0, 0};
   UCG_CHECK(c, cudaMemcpyAsync(h, c->d_ev.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (c->ev_two_parts) UCG_CHECK(c, cudaMemcpyAsync(h2, c->d_ev.p + 16, 7 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   UCG_CHECK(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 7; k++) h[k] += h2[k];
   if (eng_vdwl) *eng_vdwl = h[0];
   if (virial) for (int k = 0; k < 6; k++) virial[k] = h[1 + k];
   return 0;

@@ -203,17 +203,19 @@ struct ucgb200_ctx {
     bool set = false;
   } cluster;
 
-  // rleucg / bethe_density configuration
+  // rleucg / bethe_density configuration (types are STATE types in these styles)
   struct Density {
     bool set = false;
-    int n_types = 0;
-    std::vector<int> n_states_of_type, tabindex;
-    std::vector<double> threshold_radius, density_threshold, cutsq;
+    int n_types = 0, n_actual = 0;
+    std::vector<int> actual_from_state, n_states_of_type, use_entropy, tabindex;
+    std::vector<double> threshold_radius, density_threshold, chem_pot, cutsq, mass;
     double T = 1.0;
     ucg::Buf<double> d_prob, d_partial, d_pforce, d_cvforce;
     ucg::Buf<int> d_tabindex;
     ucg::Buf<double> d_cutsq;
+    ucg::Buf<char> d_rt;
   } dens;
+  bool ev_two_parts = false;   // d_ev[16..22] holds a second virial part to be added (rleucg)
 };
 
 namespace ucg {
