@@ -284,8 +284,10 @@ int ucg_rebuild_rle_maps(ucgb200_ctx *c) {
     ti[t].nstates = 1; ti[t].mass = d.mass[t]; ti[t].mu0 = ti[t].mu1 = ti[t].dmu = 0.0;
     rt[t].actual = a; rt[t].nstates = d.n_states_of_type[a]; rt[t].entropy = d.use_entropy[a];
     rt[t].mu = d.chem_pot[t]; rt[t].cv_th = d.density_threshold[a]; rt[t].r_th = d.threshold_radius[a];
-    // a 2-state base type t uses tables of types t and t+1
-    if (rt[t].nstates > 1 && t + rt[t].nstates - 1 > d.n_types) { c->err = "pair_rleucg: substates exceed ntypes"; return -1; }
+    // a 2-state base type t (the first state type of its actual type; sites always carry the
+    // base type, pair_table_rleucg_interface.cpp:238-244) uses tables of types t and t+1
+    const bool base = (t == 1) || d.actual_from_state[t - 1] != a;
+    if (base && rt[t].nstates > 1 && t + rt[t].nstates - 1 > d.n_types) { c->err = "pair_rleucg: substates exceed ntypes"; return -1; }
   }
   for (int i = 1; i < nt; i++)
     for (int j = 1; j < nt; j++) {
