@@ -119,6 +119,8 @@ int ucgb200_table_upload(ucgb200_ctx *ctx, int tabstyle, int tablength, int n, d
                          int nshiftbits, const double *e, const double *f, const double *e2,
                          const double *f2, const double *rsq, const double *drsq, const double *de,
                          const double *df, int *index);
+/* pair_style settings(): drops every table and the style-specific configuration (rleucg /
+ * bethe_density settings); the next pair call needs fresh tables and maps */
 int ucgb200_tables_clear(ucgb200_ctx *ctx);
 /* tabindex[(n_formal+1)^2] (pair_table_ucgld.cpp:844,892) and
  * cutsq[(n_actual+1)^2] (init_one :886-895; only actual-type pairs are read, :213) */
@@ -179,10 +181,19 @@ int ucgb200_pair_rleucg_configure(ucgb200_ctx *ctx, int ntypes, const int *actua
 int ucgb200_pair_rleucg(ucgb200_ctx *ctx, int eflag, int vflag);
 /* substate_probability[i][0] and the CV force F_p*dp/drho of the last evaluation (host order) */
 int ucgb200_pair_rleucg_probabilities(ucgb200_ctx *ctx, int cap, double *prob, double *cvforce);
-/* PairTable_UCG_Bethe_Density::compute, repaired semantics */
-int ucgb200_pair_bethe_density_configure(ucgb200_ctx *ctx, const int *density_type_flag,
-                                         const double *density_threshold, const double *threshold_radius);
-int ucgb200_pair_bethe_density(ucgb200_ctx *ctx, int eflag, int vflag, int method, int pseudo);
+/* PairTable_UCG_Bethe_Density::compute (pair_table_ucg_bethe_density.cpp:133-758), repaired
+ * semantics (SURVEY Q9-Q12,Q14; oracle/repair_bethe_density.py lists every deviation).  Types,
+ * formal-type maps, chemical potentials, tables, cutsq and kT come from ucgb200_set_types exactly as
+ * for table_ucgld; this call adds the per-actual-type density settings read_state_settings parses
+ * (:827-880), all arrays 1-based [n_actual+1]: use_density ("density" keyword), use_entropy
+ * ("entropy" / "no_entropy"), cv_threshold and threshold_radius.  Requires newton off (init_style
+ * :1151) — the host class enforces it.  The style writes atom->f and atom->ucgp. */
+int ucgb200_pair_bethe_density_configure(ucgb200_ctx *ctx, int n_actual, const int *use_density,
+                                         const int *use_entropy, const double *cv_threshold,
+                                         const double *threshold_radius);
+int ucgb200_pair_bethe_density(ucgb200_ctx *ctx, int eflag, int vflag);
+/* prior_prob[i][0] and sum_s prior_prob_force*prior_prob_partial of the last evaluation (host order) */
+int ucgb200_pair_bethe_density_priors(ucgb200_ctx *ctx, int cap, double *prob0, double *cvforce);
 /* eng_vdwl, virial[6] (xx,yy,zz,xy,xz,yz) of the last pair call with eflag/vflag */
 int ucgb200_pair_energy_virial(ucgb200_ctx *ctx, double *eng_vdwl, double virial[6]);
 

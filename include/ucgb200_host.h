@@ -27,7 +27,7 @@ typedef struct ucgb200_statemap ucgb200_statemap;
 #define UCGB200_R_BMP 3
 
 /* Read section `keyword` of a LAMMPS table file and build the run-time table for
- * (tabstyle, tablength, cut).  Error text (the reference's error->one/all message) goes
+ * (tabstyle, tablength, cut); cut < 0 selects the table's own upper end.  Error text (the reference's error->one/all message) goes
  * to errbuf.  Returns 0 or -1. */
 int ucgb200_host_table_from_file(const char *file, const char *keyword, double cut, int tabstyle,
                                  int tablength, ucgb200_table **out, char *errbuf, int errlen);

@@ -315,12 +315,20 @@ class Context:
     def pair_rleucg(self, eflag=0, vflag=0):
         self._ck(self._l.ucgb200_pair_rleucg(self._h, int(eflag), int(vflag)))
 
-    def pair_bethe_density_configure(self, density_type_flag, density_threshold, threshold_radius):
-        a, b, c_ = _i(density_type_flag), _d(density_threshold), _d(threshold_radius)
-        self._ck(self._l.ucgb200_pair_bethe_density_configure(self._h, _pi(a), _pd(b), _pd(c_)))
+    def pair_bethe_density_configure(self, use_density, use_entropy, cv_threshold, threshold_radius):
+        """per-actual-type arrays, 1-based (index 0 unused): pair_table_ucg_bethe_density.cpp:827-880"""
+        a = [_i(use_density), _i(use_entropy), _d(cv_threshold), _d(threshold_radius)]
+        self._ck(self._l.ucgb200_pair_bethe_density_configure(self._h, int(len(a[0]) - 1), _pi(a[0]), _pi(a[1]),
+                                                              _pd(a[2]), _pd(a[3])))
 
-    def pair_bethe_density(self, eflag=0, vflag=0, method=1, pseudo=0):
-        self._ck(self._l.ucgb200_pair_bethe_density(self._h, int(eflag), int(vflag), int(method), int(pseudo)))
+    def pair_bethe_density(self, eflag=0, vflag=0):
+        self._ck(self._l.ucgb200_pair_bethe_density(self._h, int(eflag), int(vflag)))
+
+    def pair_bethe_density_priors(self):
+        n = self.natoms()[0]
+        p, f = np.zeros(n), np.zeros(n)
+        self._ck(self._l.ucgb200_pair_bethe_density_priors(self._h, int(n), _pd(p), _pd(f)))
+        return p, f
 
     def pair_energy_virial(self):
         e, v = C.c_double(), np.zeros(6)

@@ -158,6 +158,10 @@ extern "C" int ucgb200_tables_clear(ucgb200_ctx *c) {
   c->table_allocs.clear();
   c->tables.clear();
   c->maps_dirty = true;
+  // a new pair_style starts from scratch: forget the style-specific configuration
+  c->dens.set = false;
+  c->bdens.set = false;
+  c->list_valid = false;
   return 0;
 }
 

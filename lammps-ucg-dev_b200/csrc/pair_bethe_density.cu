@@ -1,0 +1,395 @@
+// pair_bethe_density.cu — PairTable_UCG_Bethe_Density::compute
+// (UCG/pair_table_ucg_bethe_density.cpp:133-758) for sm_100a: Bethe pair probabilities with
+// density-dependent one-point priors.  Full list, newton off; types are ACTUAL types, formal
+// types index tables / chemical potentials exactly as in table_ucgld (ucgb200_set_types).
+//
+// Three sweeps over the full rows, every result accumulated into the CENTRE site (no atomics):
+//   1. k_bd_prior   rho_i = sum_j 1/2 (1 - tanh((r - r_th)/(0.1 r_th)))                    (:219-252)
+//                   p_i0 = 1/2 + 1/2 tanh((rho - rho_th)/(0.1 rho_th)), dp/drho             (:103-113)
+//                   non-density 2-state types: softmax(-mu/kT); 1-state: p0 = 1            (:255-273)
+//      + ghost refresh of p_0            == comm->forward_comm(this)  (:280, repaired Q12)
+//   2. k_bd_pair    one-body probability forces (:302-317), then per neighbor the 4 tables,
+//                   J, b = exp(-J/kT), a = b - 1, Q, D, p11 (stable root, repaired Q14), E and
+//                   fpair = sum p_ab f_ab, the pseudo-likelihood scores and the two-point
+//                   probability forces -(u10-u00+kT ln(p10/p00)), -(u11-u01+kT ln(p11/p01)) (:604-655);
+//                   posterior ucgp = softmax(scores)[1]                                     (:675-693)
+//   3. k_bd_back    CV back-force with the proximity FUNCTION (sic, Q13): f_i += cvf_i g(r)/r d
+//                   and the reaction -cvf_j g(r)/r d_ji of every LOCAL neighbor j           (:696-726)
+// As-is behaviour kept (it is what the reference computes on one rank, periodic images being
+// ghosts): with newton off the reference only updates f[j] for j < nlocal, so reactions onto
+// ghost neighbors are dropped (pass 3, and the CG-CG / UCG-CG scenarios); the entropy term uses
+// the LIST length numneigh[i] (1 - jnum, :294,309), not the in-cutoff count; the density map
+// exists for actual type 1 only (Q15).  Every visit of a UCG-UCG pair tallies half of E and of
+// the virial (:622-625 with ev_tally newton off), i.e. each pair once in total.
+#include "pair_common.cuh"
+
+#include <cmath>
+
+using namespace ucg;
+
+namespace {
+
+struct BdType {   // per ACTUAL type
+  int use_density, entropy;
+  double cv_th, r_th;
+};
+
+struct BdArgs {
+  const double4 *pos;
+  const int *ts;
+  const int *tag;
+  int nlocal;
+  const int *neigh;
+  int stride;
+  const int *numneigh;
+  const PairInfo *pinfo;
+  const TypeInfo *tinfo;
+  const BdType *bt;
+  int na;
+  const TableDev *tables;
+  double special_lj[4];
+  double kT, inv_kT;
+  double *prob0, *partial0, *cvf;   // [nall] / [nlocal] / [nlocal]
+  double4 *frc;
+  double2 *scores;
+  double *ucgp;
+  double *partials;
+  ErrWord *err;
+};
+
+__device__ __forceinline__ double bd_prox(double r, double rth) {
+  return 0.5 * (1.0 - tanh((r - rth) / (0.1 * rth)));
+}
+
+template <int LPA, int BS>
+__global__ void __launch_bounds__(BS) k_bd_prior(BdArgs p) {
+  const int gid = (blockIdx.x * BS + threadIdx.x) / LPA;
+  const int sub = threadIdx.x % LPA;
+  const bool active = gid < p.nlocal;
+  const int i = active ? gid : 0;
+  const double4 ri = p.pos[i];
+  const int ti = p.ts[i] & 0xffff;
+  const TypeInfo tyi = p.tinfo[ti];
+  const BdType bti = p.bt[ti];
+  const bool dens = bti.use_density == 1 && tyi.nstates > 1;
+  const int jnum = (active && dens) ? p.numneigh[i] : 0;
+  const int *row = p.neigh + (size_t)i * p.stride;
+  const PairInfo *prow = p.pinfo + ti * p.na;
+  double rho = 0.0;
+  for (int jj = sub; jj < jnum; jj += LPA) {
+    const int j = row[jj] & UCG_NEIGHMASK;
+    const double4 rj = p.pos[j];
+    const int tj = p.ts[j] & 0xffff;
+    const double rsq = rsq_exact(ri.x - rj.x, ri.y - rj.y, ri.z - rj.z);
+    if (rsq < prow[tj].cutsq) rho += bd_prox(sqrt(rsq), bti.r_th);
+  }
+  rho = group_sum<LPA>(rho);
+  if (active && sub == 0) {
+    double p0 = 1.0, pa = 0.0;
+    if (dens) {
+      if (ti != 1) report_error(p.err, UCGB200_ERR_DENSITY_TYPE, p.tag[i], 0, rho);
+      const double t = tanh((rho - bti.cv_th) / (0.1 * bti.cv_th));
+      p0 = 0.5 + 0.5 * t;
+      pa = 0.5 * (1.0 - t * t) / (0.1 * bti.cv_th);
+    } else if (tyi.nstates > 1) {
+      const double e0 = exp(-tyi.mu0 / p.kT), e1 = exp(-tyi.mu1 / p.kT);
+      p0 = e0 / (e0 + e1);
+    }
+    p.prob0[i] = p0;
+    p.partial0[i] = pa;
+  }
+}
+
+// forward_comm(this): priors of the owners to their periodic images
+__global__ void k_bd_ghost(double *__restrict__ a, int nlocal, int nlimg, const int *__restrict__ owner,
+                           const int *__restrict__ slot_of_src) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nlimg) return;
+  a[nlocal + slot_of_src[k]] = a[owner[k]];
+}
+
+template <int LPA, int BS>
+__global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
+  const int gid = (blockIdx.x * BS + threadIdx.x) / LPA;
+  const int sub = threadIdx.x % LPA;
+  const bool active = gid < p.nlocal;
+  const int i = active ? gid : 0;
+  const double4 ri = p.pos[i];
+  const int ti = p.ts[i] & 0xffff;
+  const TypeInfo tyi = p.tinfo[ti];
+  const BdType bti = p.bt[ti];
+  const int ni = tyi.nstates;
+  const double pi0 = p.prob0[i], pi1 = 1.0 - pi0;
+  const int jnum = active ? p.numneigh[i] : 0;
+  const int *row = p.neigh + (size_t)i * p.stride;
+  const PairInfo *prow = p.pinfo + ti * p.na;
+  const bool dens_i = ni > 1 && bti.use_density == 1;
+
+  double fx = 0, fy = 0, fz = 0, eacc = 0, S0 = 0, S1 = 0, pf0 = 0, pf1 = 0;
+  double vir[6] = {0, 0, 0, 0, 0, 0};
+
+  for (int jj = sub; jj < jnum; jj += LPA) {
+    const int jraw = row[jj];
+    const double factor_lj = p.special_lj[(jraw >> UCG_SBBITS) & 3];
+    const int j = jraw & UCG_NEIGHMASK;
+    const double4 rj = p.pos[j];
+    const int tsj = p.ts[j];
+    const int tj = tsj & 0xffff;
+    const double dx = ri.x - rj.x, dy = ri.y - rj.y, dz = ri.z - rj.z;
+    const double rsq = rsq_exact(dx, dy, dz);
+    const PairInfo pi = prow[tj];
+    if (rsq < pi.cutsq) {
+      const int nj = pi.nj;
+      const bool jlocal = j < p.nlocal;
+      double u[4] = {0, 0, 0, 0}, f[4] = {0, 0, 0, 0};
+      int ec = 0;
+      for (int a = 0; a < ni; a++)
+        for (int b = 0; b < nj; b++) {
+          int e1 = table_eval(p.tables[pi.tab[a * 2 + b]], rsq, u[a * 2 + b], f[a * 2 + b]);
+          if (e1 && !ec) ec = e1;
+        }
+      if (ec) {
+        report_error(p.err, ec, p.tag[i], p.tag[j], rsq);
+        continue;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) { u[k] *= factor_lj; f[k] *= factor_lj; }
+      double e, fpair, wf, we;   // wf: weight of d*fpair in f_i; we: weight in the E / virial tally
+      if (ni == 2 && nj == 2) {
+        const double pj0 = p.prob0[j], pj1 = 1.0 - pj0;
+        const double J = u[3] + u[0] - u[1] - u[2];
+        const double bij = exp(-J / p.kT), aij = bij - 1.0;
+        const double Q = (pi1 + pj1) * aij + 1.0;
+        const double D = fmax(Q * Q - 4.0 * aij * bij * pi1 * pj1, 0.0);
+        double p11;
+        if (fabs(aij) < 1.0e-6) p11 = pi1 * pj1;
+        else if (Q < 0.0) p11 = (Q - sqrt(D)) / (2.0 * aij);
+        else p11 = (2.0 * bij * pi1 * pj1) / (Q + sqrt(D));
+        const double p00 = 1.0 + p11 - pi1 - pj1, p10 = pi1 - p11, p01 = pj1 - p11;
+        e = p00 * u[0] + p01 * u[1] + p10 * u[2] + p11 * u[3];
+        fpair = p00 * f[0] + p01 * f[1] + p10 * f[2] + p11 * f[3];
+        wf = 1.0; we = 0.5;
+        const int sj = (tsj >> 16) & 1;           // (:596-598) only the neighbor's current state is tallied
+        S0 += sj ? u[1] : u[0];
+        S1 += sj ? u[3] : u[2];
+        if (bti.use_density == 1) {
+          pf0 -= (u[2] - u[0] + p.kT * log(p10 / p00));
+          pf1 -= (u[3] - u[1] + p.kT * log(p11 / p01));
+        }
+      } else if (ni == 2) {                        // centre UCG, neighbor CG (:423-517)
+        e = pi0 * u[0] + pi1 * u[2];
+        fpair = pi0 * f[0] + pi1 * f[2];
+        wf = 1.0; we = jlocal ? 1.0 : 0.5;
+        S0 += u[0];
+        S1 += u[2];
+        if (bti.use_density == 1) {
+          pf0 -= u[0] + p.kT * log(pi0);
+          pf1 -= u[2] + p.kT * log(pi1);
+        }
+      } else if (nj == 2) {                        // centre CG, neighbor UCG: the reference skips this visit
+        // (:411-420) and lets the neighbor's own visit scatter -d*fpair here, which with newton off
+        // happens for LOCAL neighbors only
+        const double pj0 = p.prob0[j], pj1 = 1.0 - pj0;
+        e = 0.0;
+        fpair = pj0 * f[0] + pj1 * f[1];
+        wf = jlocal ? 1.0 : 0.0; we = 0.0;
+      } else {                                     // CG-CG (:331-405): half per visit, reaction to local j only
+        e = u[0];
+        fpair = 0.5 * f[0];
+        wf = jlocal ? 2.0 : 1.0; we = jlocal ? 1.0 : 0.5;
+      }
+      eacc += we * e;
+      const double ff = wf * fpair;
+      fx += dx * ff; fy += dy * ff; fz += dz * ff;
+      const double fv = we * fpair;
+      vir[0] += dx * dx * fv; vir[1] += dy * dy * fv; vir[2] += dz * dz * fv;
+      vir[3] += dx * dy * fv; vir[4] += dx * dz * fv; vir[5] += dy * dz * fv;
+    }
+  }
+  fx = group_sum<LPA>(fx); fy = group_sum<LPA>(fy); fz = group_sum<LPA>(fz);
+  eacc = group_sum<LPA>(eacc);
+  S0 = group_sum<LPA>(S0); S1 = group_sum<LPA>(S1);
+  pf0 = group_sum<LPA>(pf0); pf1 = group_sum<LPA>(pf1);
+  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const double v = group_sum<LPA>(vir[k]);
+    if (active && sub == 0) ev[1 + k] = v;
+  }
+  if (active && sub == 0) {
+    double s0 = -S0 * p.inv_kT, s1 = -S1 * p.inv_kT, cvf = 0.0;
+    if (dens_i) {
+      // one-body terms (:302-317); jnum_f = 1 - numneigh[i] is the LIST length (as-is)
+      const double jnum_f = 1.0 - (double)jnum;
+      if (bti.entropy) {
+        pf0 -= p.kT * log(pi0) * jnum_f;
+        pf1 -= p.kT * log(pi1) * jnum_f;
+      }
+      pf0 -= tyi.mu0; pf1 -= tyi.mu1;
+      s0 -= tyi.mu0 / p.kT; s1 -= tyi.mu1 / p.kT;
+      const double pa = p.partial0[i];
+      cvf = pf0 * pa + pf1 * (-pa);               // sum over si of prior_prob_force*prior_prob_partial (:700)
+    }
+    p.cvf[i] = cvf;
+    p.frc[i] = make_double4(fx, fy, fz, 0.0);
+    // posterior (:675-693, type index per repaired Q11); the style keeps its scores private and
+    // publishes only ucgp — atom->ucgsoftmaxscores stay at their cleared value
+    p.ucgp[i] = ni > 1 ? exp(s1) / (exp(s0) + exp(s1)) : 1.0;
+    p.scores[i] = make_double2(0.0, 0.0);
+    ev[0] = eacc;
+  }
+  block_reduce_store<7, BS>(ev, p.partials);
+}
+
+template <int LPA, int BS>
+__global__ void __launch_bounds__(BS) k_bd_back(BdArgs p) {
+  const int gid = (blockIdx.x * BS + threadIdx.x) / LPA;
+  const int sub = threadIdx.x % LPA;
+  const bool active = gid < p.nlocal;
+  const int i = active ? gid : 0;
+  const double4 ri = p.pos[i];
+  const int ti = p.ts[i] & 0xffff;
+  const BdType bti = p.bt[ti];
+  const bool dens_i = bti.use_density == 1 && p.tinfo[ti].nstates > 1;
+  const double cvf_i = p.cvf[i];
+  const int jnum = active ? p.numneigh[i] : 0;
+  const int *row = p.neigh + (size_t)i * p.stride;
+  const PairInfo *prow = p.pinfo + ti * p.na;
+  double fx = 0, fy = 0, fz = 0;
+  double vir[6] = {0, 0, 0, 0, 0, 0};
+  for (int jj = sub; jj < jnum; jj += LPA) {
+    const int j = row[jj] & UCG_NEIGHMASK;
+    const double4 rj = p.pos[j];
+    const int tj = p.ts[j] & 0xffff;
+    const double dx = ri.x - rj.x, dy = ri.y - rj.y, dz = ri.z - rj.z;
+    const double rsq = rsq_exact(dx, dy, dz);
+    if (rsq < prow[tj].cutsq) {
+      const double r = sqrt(rsq);
+      const bool jlocal = j < p.nlocal;
+      const double own = dens_i ? cvf_i * bd_prox(r, bti.r_th) / r : 0.0;               // i's loop (:713-716)
+      double oth = 0.0;                                                                   // j's loop scatters to i
+      if (jlocal) {
+        const BdType btj = p.bt[tj];
+        if (btj.use_density == 1 && p.tinfo[tj].nstates > 1) oth = p.cvf[j] * bd_prox(r, btj.r_th) / r;
+      }
+      const double fp = own + oth;
+      fx += fp * dx; fy += fp * dy; fz += fp * dz;
+      const double w = (jlocal ? 1.0 : 0.5) * own;   // ev_tally(i,j,nlocal,newton=0,0,0,fpair,...) in i's loop (:722)
+      vir[0] += w * dx * dx; vir[1] += w * dy * dy; vir[2] += w * dz * dz;
+      vir[3] += w * dx * dy; vir[4] += w * dx * dz; vir[5] += w * dy * dz;
+    }
+  }
+  fx = group_sum<LPA>(fx); fy = group_sum<LPA>(fy); fz = group_sum<LPA>(fz);
+  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const double v = group_sum<LPA>(vir[k]);
+    if (active && sub == 0) ev[1 + k] = v;
+  }
+  if (active && sub == 0) {
+    double4 f = p.frc[i];
+    f.x += fx; f.y += fy; f.z += fz;
+    p.frc[i] = f;
+  }
+  block_reduce_store<7, BS>(ev, p.partials);
+}
+
+}  // namespace
+
+extern "C" int ucgb200_pair_bethe_density_configure(ucgb200_ctx *c, int n_actual, const int *use_density,
+                                                    const int *use_entropy, const double *cv_threshold,
+                                                    const double *threshold_radius) {
+  if (!c || n_actual < 1 || !use_density || !use_entropy || !cv_threshold || !threshold_radius) return -1;
+  auto &b = c->bdens;
+  b.n_actual = n_actual;
+  b.use_density.assign(use_density, use_density + n_actual + 1);
+  b.use_entropy.assign(use_entropy, use_entropy + n_actual + 1);
+  b.cv_th.assign(cv_threshold, cv_threshold + n_actual + 1);
+  b.r_th.assign(threshold_radius, threshold_radius + n_actual + 1);
+  for (int t = 1; t <= n_actual; t++)
+    if (b.use_density[t] && !(b.cv_th[t] > 0.0 && b.r_th[t] > 0.0))
+      return fail(c, "pair_bethe_density: density threshold and radius must be positive");
+  b.set = true;
+  b.dirty = true;
+  return 0;
+}
+
+extern "C" int ucgb200_pair_bethe_density(ucgb200_ctx *c, int eflag, int vflag) {
+  if (!c) return -1;
+  auto &b = c->bdens;
+  if (!b.set) return fail(c, "pair_bethe_density: not configured");
+  if (c->dens.set) return fail(c, "pair_bethe_density: context is configured for table_rleucg_interface");
+  if (c->halo.nranks > 1) return fail(c, "pair_bethe_density: the forward exchange of the priors across bricks is not built yet");
+  cudaSetDevice(c->device);
+  int rc = rebuild_maps(c);
+  if (rc) return rc;
+  if (b.n_actual != c->n_actual) return fail(c, "pair_bethe_density: configured for a different number of actual types");
+  if (!c->list_valid) return fail(c, "pair_bethe_density: neighbor list not built");
+  c->ev_valid = false;
+  if (c->nlocal == 0) return 0;
+  (void)eflag; (void)vflag;
+  if (b.dirty) {
+    std::vector<BdType> bt(b.n_actual + 1);
+    for (int t = 0; t <= b.n_actual; t++) {
+      bt[t].use_density = b.use_density[t]; bt[t].entropy = b.use_entropy[t];
+      bt[t].cv_th = b.cv_th[t]; bt[t].r_th = b.r_th[t];
+    }
+    UCG_CHECK(c, b.d_bt.ensure(bt.size() * sizeof(BdType)));
+    UCG_CHECK(c, cudaMemcpy(b.d_bt.p, bt.data(), bt.size() * sizeof(BdType), cudaMemcpyHostToDevice));
+    b.dirty = false;
+  }
+  const int nall = c->nlocal + c->nghost;
+  UCG_CHECK(c, b.d_prob.ensure(nall));
+  UCG_CHECK(c, b.d_partial.ensure(c->nlocal));
+  UCG_CHECK(c, b.d_cvf.ensure(c->nlocal));
+  constexpr int LPA = 8, BS = 256;
+  const int nblk = nblocks((long long)c->nlocal * LPA, BS);
+  UCG_CHECK(c, c->d_partials.ensure((size_t)nblk * 8 + 64));
+  BdArgs a{};
+  a.pos = c->pos.p; a.ts = c->ts.p; a.tag = c->tag.p; a.nlocal = c->nlocal;
+  a.neigh = c->neigh.p; a.stride = c->neigh_stride; a.numneigh = c->numneigh.p;
+  a.pinfo = c->d_pairinfo.p; a.tinfo = c->d_typeinfo.p; a.bt = (const BdType *)b.d_bt.p; a.na = c->n_actual + 1;
+  a.tables = c->d_tables.p;
+  for (int k = 0; k < 4; k++) a.special_lj[k] = c->special_lj[k];
+  a.kT = c->kT; a.inv_kT = 1.0 / c->kT;
+  a.prob0 = b.d_prob.p; a.partial0 = b.d_partial.p; a.cvf = b.d_cvf.p;
+  a.frc = c->frc.p; a.scores = c->scores.p; a.ucgp = c->ucgp.p; a.partials = c->d_partials.p; a.err = c->d_err.p;
+  const auto &h = c->halo;
+  if (c->timers_on) cudaEventRecord(c->ev_pair0, c->stream);
+  k_bd_prior<LPA, BS><<<nblk, BS, 0, c->stream>>>(a);
+  UCG_LAUNCHED(c);
+  if (h.nlimg) {
+    k_bd_ghost<<<nblocks(h.nlimg, 256), 256, 0, c->stream>>>(a.prob0, c->nlocal, h.nlimg, c->img_owner.p + h.nsend, c->slot_of_src.p);
+    UCG_LAUNCHED(c);
+  }
+  k_bd_pair<LPA, BS><<<nblk, BS, 0, c->stream>>>(a);
+  UCG_LAUNCHED(c);
+  if ((rc = reduce_partials(c, nblk, 7, 0))) return rc;
+  k_bd_back<LPA, BS><<<nblk, BS, 0, c->stream>>>(a);
+  UCG_LAUNCHED(c);
+  if ((rc = reduce_partials(c, nblk, 7, 16))) return rc;   // second virial part -> d_ev[16..22]
+  if (c->timers_on) { cudaEventRecord(c->ev_pair1, c->stream); c->pair_timed = true; }
+  c->ev_valid = true;
+  c->ev_two_parts = true;
+  return 0;
+}
+
+// prior probability of substate 0 and the CV force of the last evaluation (diagnostics / tests), host order
+extern "C" int ucgb200_pair_bethe_density_priors(ucgb200_ctx *c, int cap, double *prob0, double *cvforce) {
+  if (!c || cap < c->nlocal) return -1;
+  cudaSetDevice(c->device);
+  auto &b = c->bdens;
+  const int n = c->nlocal;
+  if (!b.set || b.d_prob.cap < (size_t)n) return fail(c, "pair_bethe_density: nothing evaluated yet");
+  std::vector<double> tmp(n);
+  std::vector<int> orig(n);
+  UCG_CHECK(c, cudaMemcpyAsync(orig.data(), c->orig.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  for (int pass = 0; pass < 2; pass++) {
+    double *dst = pass == 0 ? prob0 : cvforce;
+    if (!dst) continue;
+    UCG_CHECK(c, cudaMemcpyAsync(tmp.data(), pass == 0 ? b.d_prob.p : b.d_cvf.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    UCG_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < n; s++) dst[orig[s]] = tmp[s];
+  }
+  return 0;
+}

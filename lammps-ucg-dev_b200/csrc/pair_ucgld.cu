@@ -188,15 +188,14 @@ struct FastArgs {
 
 // PF = 1 software-pipelines the neighbor gathers: index and {x,y,z,lambda}/state of the
 // next neighbor are in flight while the current pair is evaluated.
-template <int LPA, bool EV, int W, int BS, int PF>
+// SM = true: table rows come from shared memory (LDS.128, not generic loads).
+template <int LPA, bool EV, int W, int BS, int PF, bool SM>
 __global__ void __launch_bounds__(BS) k_pair_ucgld_fast(FastArgs p) {
   extern __shared__ double2 s_tab[];
-  const double2 *tab = p.table;
-  if (p.smem_table) {
+  if (SM) {
     const int nwords = p.tablen * W;
     for (int k = threadIdx.x; k < nwords; k += BS) s_tab[k] = p.table[k];
     __syncthreads();
-    tab = s_tab;
   }
   const int sub = threadIdx.x % LPA;
   const int groups_per_block = BS / LPA;
@@ -234,15 +233,23 @@ __global__ void __launch_bounds__(BS) k_pair_ucgld_fast(FastArgs p) {
         } else {
           const double rsq_it = __dadd_rn(p.innersq, __dmul_rn((double)it, p.delta));
           const double frac = (rsq - rsq_it) * p.invdelta;
-          const double2 *r0 = tab + it * W;
-          const double2 a00 = r0[0], a01 = r0[1], a11 = r0[W - 1];
-          const double2 b00 = r0[W], b01 = r0[W + 1], b11 = r0[2 * W - 1];
+          double2 a00, a01, a11, b00, b01, b11, a10, b10;
+          if (SM) {
+            const double2 *r0 = s_tab + it * W;
+            a00 = r0[0]; a01 = r0[1]; a11 = r0[W - 1];
+            b00 = r0[W]; b01 = r0[W + 1]; b11 = r0[2 * W - 1];
+            if (W == 4) { a10 = r0[2]; b10 = r0[W + 2]; }
+          } else {
+            const double2 *r0 = p.table + it * W;
+            a00 = __ldg(r0); a01 = __ldg(r0 + 1); a11 = __ldg(r0 + W - 1);
+            b00 = __ldg(r0 + W); b01 = __ldg(r0 + W + 1); b11 = __ldg(r0 + 2 * W - 1);
+            if (W == 4) { a10 = __ldg(r0 + 2); b10 = __ldg(r0 + W + 2); }
+          }
           const double u00 = a00.x + frac * (b00.x - a00.x), f00 = a00.y + frac * (b00.y - a00.y);
           const double u01 = a01.x + frac * (b01.x - a01.x), f01 = a01.y + frac * (b01.y - a01.y);
           const double u11 = a11.x + frac * (b11.x - a11.x), f11 = a11.y + frac * (b11.y - a11.y);
           double u10, f10;
           if (W == 4) {
-            const double2 a10 = r0[2], b10 = r0[W + 2];
             u10 = a10.x + frac * (b10.x - a10.x);
             f10 = a10.y + frac * (b10.y - a10.y);
           } else { u10 = u01; f10 = f01; }
@@ -322,7 +329,7 @@ static int env_int(const char *name, int dflt) {
 template <int LPA, bool EV, int W, int BS, int PF>
 static int launch_fast(ucgb200_ctx *c, FastArgs &a, int &nblk) {
   size_t smem = a.smem_table ? (size_t)a.tablen * W * sizeof(double2) : 0;
-  auto kern = k_pair_ucgld_fast<LPA, EV, W, BS, PF>;
+  auto kern = a.smem_table ? k_pair_ucgld_fast<LPA, EV, W, BS, PF, true> : k_pair_ucgld_fast<LPA, EV, W, BS, PF, false>;
   if (smem > 32 * 1024) UCG_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   if (!a.smem_table) per_sm = 2048 / BS > 3 ? 3 : 2048 / BS;

@@ -67,7 +67,7 @@ static int pair_compute(ucgb200_ctx *c, int ev) {
     case 0: return ucgb200_pair_ucgld(c, ev, ev);
     case 1: return ucgb200_pair_bethe(c, ev, ev, d.bethe_method, d.bethe_pseudo, d.bethe_prior, 0.0, 1);
     case 2: return ucgb200_pair_rleucg(c, ev, ev);
-    default: return ucgb200_pair_bethe_density(c, ev, ev, d.bethe_method, d.bethe_pseudo);
+    default: return ucgb200_pair_bethe_density(c, ev, ev);
   }
 }
 

@@ -215,6 +215,15 @@ struct ucgb200_ctx {
     ucg::Buf<double> d_cutsq;
     ucg::Buf<char> d_rt;
   } dens;
+  // table_ucg_bethe_density: per-actual-type density settings + scratch (types/tables as for ucgld)
+  struct BetheDensity {
+    bool set = false, dirty = true;
+    int n_actual = 0;
+    std::vector<int> use_density, use_entropy;
+    std::vector<double> cv_th, r_th;
+    ucg::Buf<char> d_bt;
+    ucg::Buf<double> d_prob, d_partial, d_cvf;
+  } bdens;
   bool ev_two_parts = false;   // d_ev[16..22] holds a second virial part to be added (rleucg)
 };
 

@@ -186,6 +186,8 @@ BuiltTable BuiltTable::build(TableInput in, double cut, int tabstyle, int tablen
   if (in.ninput <= 1) throw std::runtime_error("Invalid pair table length");
   const double rlo = in.rflag == UCGB200_R_NONE ? in.r.front() : in.rlo;
   const double rhi = in.rflag == UCGB200_R_NONE ? in.r.back() : in.rhi;
+  // pair_coeff without a cutoff (pair_table_rleucg_interface.cpp:688-690): the table's upper end
+  if (cut < 0.0) cut = rhi;
   if (cut <= rlo || cut > rhi) throw std::runtime_error("Pair table cutoff outside of table");
   if (rlo <= 0.0) throw std::runtime_error("Invalid pair table lower boundary");
   BuiltTable t;

@@ -10,6 +10,7 @@
 // Only declarations the UCG sources actually touch are present (SURVEY.md §8c lists them).
 // Everything here is written from the public LAMMPS class interfaces; nothing is copied.
 #pragma once
+#define LAMMPS_UCG_SHIM 1   // lets the style classes fill shim-only diagnostics (Pair::virial_tally)
 
 #include <cmath>
 #include <cstdint>

@@ -498,6 +498,12 @@ struct Sim {
       lmp.force->newton = lmp.force->newton_pair = lmp.force->newton_bond = (w.at(1) == "on");
     } else if (cmd == "special_bonds") {
       for (int k = 1; k <= 3; k++) lmp.force->special_lj[k] = utils::numeric(FLERR, w.at(k), false, &lmp);
+    } else if (cmd == "num_ucgstates") {
+      // harness-only: atom->num_ucgstates is not a data-file field (atom_vec_ucg.cpp:87) and
+      // table_ucg_bethe_density / table_rleucg_interface never write it, so in LAMMPS its content
+      // is whatever the allocator left; this presets it (quirk Q24)
+      const int v = utils::inumeric(FLERR, w.at(1), false, &lmp);
+      for (int i = 0; i < lmp.atom->nlocal + lmp.atom->nghost; i++) lmp.atom->num_ucgstates[i] = v;
     } else if (cmd == "mass") {
       int t = utils::inumeric(FLERR, w.at(1), false, &lmp);
       if (t < 1 || t > lmp.atom->ntypes) lmp.error->all(FLERR, "Invalid type for mass set");

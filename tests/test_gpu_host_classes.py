@@ -116,3 +116,58 @@ def test_bethe_deck(pkg, fixtures):
     assert rel_err(b["f"], a["f"]) <= 1e-6
     assert rel_err(b["ucgp"], a["ucgp"]) <= 1e-8
     assert abs(gpu.eng_vdwl() - ref.eng_vdwl()) <= 1e-8 * abs(ref.eng_vdwl())
+
+
+def _deck(cls, liq, lines):
+    s = cls()
+    s.box(liq.box_lo, liq.box_hi, 2)
+    s.atoms(liq)
+    for c in lines:
+        s.command(c)
+    return s
+
+
+def test_rleucg_deck(pkg, fixtures, tmp_path):
+    """pair_style table_rleucg_interface + fix nve/ucgld/wall/hard through the drop-in classes"""
+    liq = _liq(6)
+    sf = tmp_path / "rle.conf"
+    sf.write_text("1 2\n2 density use_entropy\n12.0 1.5\n0.3\n")
+    t = fixtures["table4096"]
+    lines = ["newton off", "neighbor 0.3 bin", "timestep 0.002", f"pair_style table_rleucg_interface linear 4096 {sf}",
+             f"pair_coeff 1 1 {t} UCG_00 2.5", f"pair_coeff 1 2 {t} UCG_01 2.5", f"pair_coeff 2 2 {t} UCG_11 2.5",
+             "fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld/wall/hard"]
+    ref, gpu = _deck(rb.RefSim, liq, lines), _deck(rb.HostSim, liq, lines)
+    for s in (ref, gpu):
+        s.setup(1)
+        s.run(20, 1)
+    a, b = ref.get_atoms(), gpu.get_atoms()
+    assert rel_err(b["x"], a["x"]) <= 1e-10
+    assert rel_err(b["v"], a["v"]) <= 1e-8
+    assert rel_err(b["f"], a["f"]) <= 1e-6
+    assert abs(gpu.eng_vdwl() - ref.eng_vdwl()) <= 1e-7 * abs(ref.eng_vdwl())
+    assert rel_err(gpu.virial()[0], ref.virial()[0]) <= 1e-7
+    for cls in (rb.RefSim, rb.HostSim):
+        s = _deck(cls, liq, ["newton on"] + lines[1:])
+        with pytest.raises(RuntimeError, match="Newton pair is turned on"):
+            s.setup(1)
+
+
+def test_bethe_density_deck(pkg, fixtures, tmp_path):
+    """pair_style table_ucg_bethe_density (reference compiled with the documented repair) + nve/ucgld"""
+    liq = _liq(6)
+    sf = tmp_path / "bd.conf"
+    sf.write_text("1 2 2\n1 2\n1 2 density entropy \n12.0 1.5\n0.0 0.5\n")
+    t = fixtures["table4096"]
+    lines = ["newton off", "neighbor 0.3 bin", "timestep 0.002", f"pair_style table_ucg_bethe_density linear 4096 {sf}",
+             f"pair_coeff 1 1 2 2 {t} UCG_00 2.5 {t} UCG_01 2.5 {t} UCG_01 2.5 {t} UCG_11 2.5",
+             "fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld"]
+    ref, gpu = _deck(rb.RefSim, liq, lines), _deck(rb.HostSim, liq, lines)
+    for s in (ref, gpu):
+        s.setup(1)
+        s.run(20, 1)
+    a, b = ref.get_atoms(), gpu.get_atoms()
+    assert rel_err(b["x"], a["x"]) <= 1e-10
+    assert rel_err(b["f"], a["f"]) <= 1e-6
+    assert np.abs(b["ucgp"] - a["ucgp"]).max() <= 1e-9
+    assert abs(gpu.eng_vdwl() - ref.eng_vdwl()) <= 1e-7 * abs(ref.eng_vdwl())
+    assert rel_err(gpu.virial()[0], ref.virial()[0]) <= 1e-7
