@@ -221,15 +221,27 @@ int ucgb200_lambda_ke(ucgb200_ctx *ctx, int groupbit, double *ke_sum, long long 
 /* particle kinetic energy sum 0.5*m*v^2*mvv2e (thermo) */
 int ucgb200_kinetic_energy(ucgb200_ctx *ctx, int groupbit, double *ke_sum, long long *count);
 
-/* FixClusterSwitch (fix_cluster_switch.cpp:537-839): label connected molecule
- * clusters over the full list with the type contact map, then MC-flip the ON/OFF
- * types of molecules outside the seed cluster. */
-int ucgb200_cluster_configure(ucgb200_ctx *ctx, int mol_seed, int mol_offset, double cutoff,
-                              int n_switch_types, const int *type_on, const int *type_off,
-                              const double *prob_on, const double *prob_off, int n_contact_types,
-                              const int *contact_map, int max_mol);
-int ucgb200_cluster_check(ucgb200_ctx *ctx, int *n_in_cluster, int *mol_cluster_out);
-int ucgb200_cluster_switch(ucgb200_ctx *ctx, int seed, long long step, int *n_attempts, int *n_success);
+/* FixClusterSwitch (fix_cluster_switch.cpp).  _configure = the constructor (:36-170): arguments
+ * of the fix line (mol_seed, mol_offset, cutoff, seed), rates file (probON; the switch types and
+ * their ON / OFF atom types, :252-275) and contact file (ordered type pairs, :338-349); it scans the
+ * atoms already on the device for maxmol, nSwitchPerMol and the initial mol_state / mol_restrict.
+ * _check = check_cluster (:537-731) on the current FULL list: connected molecules (contact map,
+ * rsq < cutoff^2, offset partners tied) get the smallest label of their cluster; molecules in the
+ * cluster of mol_seed are restricted and set ON.  _switch = attempt_switch (:733-839): molecules
+ * outside it flip ON<->OFF with probability probON / 1-probON, drawn from the same RanPark stream in
+ * the same (ascending molecule id) order as the reference, then the atom types are rewritten.
+ * Single brick only. */
+int ucgb200_cluster_configure(ucgb200_ctx *ctx, int mol_seed, int mol_offset, double cutoff, int seed,
+                              double prob_on, int n_switch_types, const int *type_on, const int *type_off,
+                              int n_contacts, const int *contact_pairs /*[2*n_contacts]*/, int ntypes, int groupbit);
+int ucgb200_cluster_check(ucgb200_ctx *ctx, int *n_cluster);
+int ucgb200_cluster_switch(ucgb200_ctx *ctx, int *n_attempts, int *n_success);
+/* compute_vector (:923-933): out[0..6] = nAttemptsTotal, nSuccessTotal, nAttemptsON, nAttemptsOFF,
+ * nSuccessON, nSuccessOFF, nCluster; out[7] = labelling rounds of the last check */
+int ucgb200_cluster_stats(ucgb200_ctx *ctx, double out[8]);
+/* per-molecule arrays [0..maxmol] (cluster_assignment.log / state_assignment.log, :711-727) */
+int ucgb200_cluster_get(ucgb200_ctx *ctx, int cap, int *mol_cluster, int *mol_state, int *mol_restrict,
+                        int *mol_accept, int *max_mol);
 
 /* ---------------------------------------------------- resident run (no host data) */
 /* deck description for the resident integrator: which fixes are active, in
@@ -249,7 +261,8 @@ typedef struct ucgb200_deck {
   double ucgstate_rate;
   int bethe_method, bethe_pseudo, bethe_prior;
   int thermo_every;      /* eflag/vflag on steps that are multiples of this (0 = never) */
-  int reserved[8];
+  int cluster_freq;      /* fix cluster_switch rateFreq (0 = absent); configure it with ucgb200_cluster_configure */
+  int reserved[7];
 } ucgb200_deck;
 int ucgb200_deck_configure(ucgb200_ctx *ctx, const ucgb200_deck *deck);
 /* Verlet::setup [stock]: pbc, build, force_clear, pair->compute, fix setup() calls */

@@ -60,7 +60,7 @@ class Deck(C.Structure):
         ("langevin_seed", C.c_int), ("langevin_groupbit", C.c_int),
         ("ucgstate", C.c_int), ("ucgstate_seed", C.c_int), ("ucgstate_rate", C.c_double),
         ("bethe_method", C.c_int), ("bethe_pseudo", C.c_int), ("bethe_prior", C.c_int),
-        ("thermo_every", C.c_int), ("reserved", C.c_int * 8),
+        ("thermo_every", C.c_int), ("cluster_freq", C.c_int), ("reserved", C.c_int * 7),
     ]
 
 
@@ -411,29 +411,41 @@ class Context:
         self._ck(self._l.ucgb200_halo_unpack_forward(self._h, C.c_void_p(d_ptr)))
 
     # ---------------------------------------------------------- cluster switch
-    def cluster_configure(self, mol_seed, mol_offset, cutoff, type_on, type_off, prob_on, prob_off,
-                          contact_map, max_mol):
-        ton, toff, pon, poff = _i(type_on), _i(type_off), _d(prob_on), _d(prob_off)
-        cm = _i(contact_map)
-        nct = cm.shape[0]
-        cm = cm.reshape(-1)
-        self._ck(self._l.ucgb200_cluster_configure(self._h, int(mol_seed), int(mol_offset), C.c_double(cutoff),
-                                                   int(ton.size), _pi(ton), _pi(toff), _pd(pon), _pd(poff),
-                                                   int(nct), _pi(cm), int(max_mol)))
-        self._max_mol = int(max_mol)
+    def cluster_configure(self, mol_seed, mol_offset, cutoff, seed, prob_on, type_on, type_off, contact_pairs,
+                          ntypes, groupbit=1):
+        """fix ID group cluster_switch mol_seed mol_offset cutoff seed rateFreq N rateFile f contactFile f
+        (fix_cluster_switch.cpp:36-170); atoms must be on the device already"""
+        on, off = _i(type_on), _i(type_off)
+        cp = _i(contact_pairs).reshape(-1)
+        assert on.size == off.size and cp.size % 2 == 0
+        self._ck(self._l.ucgb200_cluster_configure(self._h, int(mol_seed), int(mol_offset), C.c_double(cutoff), int(seed),
+                                                   C.c_double(prob_on), int(on.size), _pi(on), _pi(off),
+                                                   int(cp.size // 2), _pi(cp), int(ntypes), int(groupbit)))
 
-    def cluster_check(self):
+    def cluster_check(self) -> int:
         n = C.c_int()
-        out = np.zeros(self._max_mol + 1, np.int32)
-        self._ck(self._l.ucgb200_cluster_check(self._h, C.byref(n), _pi(out)))
-        return n.value, out
+        self._ck(self._l.ucgb200_cluster_check(self._h, C.byref(n)))
+        return n.value
 
-    def cluster_switch(self, seed, step):
-        a, s = C.c_int(), C.c_int()
-        self._ck(self._l.ucgb200_cluster_switch(self._h, int(seed), C.c_longlong(step), C.byref(a), C.byref(s)))
-        return a.value, s.value
+    def cluster_switch(self):
+        a, s_ = C.c_int(), C.c_int()
+        self._ck(self._l.ucgb200_cluster_switch(self._h, C.byref(a), C.byref(s_)))
+        return a.value, s_.value
 
-    # ------------------------------------------------------------ resident run
+    def cluster_stats(self) -> np.ndarray:
+        out = np.zeros(8)
+        self._ck(self._l.ucgb200_cluster_stats(self._h, _pd(out)))
+        return out
+
+    def cluster_get(self) -> dict:
+        mm = C.c_int()
+        self._ck(self._l.ucgb200_cluster_get(self._h, 0, None, None, None, None, C.byref(mm)))
+        n = mm.value + 1
+        a = {k: np.zeros(n, np.int32) for k in ("mol_cluster", "mol_state", "mol_restrict", "mol_accept")}
+        self._ck(self._l.ucgb200_cluster_get(self._h, n, _pi(a["mol_cluster"]), _pi(a["mol_state"]), _pi(a["mol_restrict"]),
+                                             _pi(a["mol_accept"]), C.byref(mm)))
+        return a
+
     def deck_configure(self, **kw):
         d = Deck()
         for k, v in kw.items():

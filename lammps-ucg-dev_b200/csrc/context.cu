@@ -55,9 +55,13 @@ extern "C" int ucgb200_destroy(ucgb200_ctx *c) {
   c->scan_tmp.release(); c->ghost_cnt.release(); c->ghost_off.release();
   c->neigh.release(); c->numneigh.release(); c->statebits.release(); c->d_flags.release();
   c->d_partials.release(); c->d_ev.release(); c->d_err.release(); c->d_gfac.release();
-  c->cluster.d_label.release(); c->cluster.d_label2.release(); c->cluster.d_changed.release();
-  c->cluster.d_typemap.release(); c->cluster.d_contact.release(); c->cluster.d_molflag.release();
-  c->cluster.d_prob.release();
+  {
+    auto &k = c->cluster;
+    k.d_state.release(); k.d_restrict.release(); k.d_label.release(); k.d_accept.release(); k.d_present.release();
+    k.d_sum.release(); k.d_draws.release(); k.d_rank.release(); k.d_gmask.release(); k.d_scratch.release();
+    k.d_edges.release(); k.d_contact.release();
+    c->bdens.d_bt.release(); c->bdens.d_prob.release(); c->bdens.d_partial.release(); c->bdens.d_cvf.release();
+  }
   c->dens.d_prob.release(); c->dens.d_partial.release(); c->dens.d_pforce.release();
   c->dens.d_cvforce.release(); c->dens.d_tabindex.release(); c->dens.d_cutsq.release(); c->dens.d_rt.release();
   if (c->h_flags) cudaFreeHost(c->h_flags);

@@ -155,6 +155,17 @@ extern "C" int ucgb200_run(ucgb200_ctx *c, int nsteps) {
       if ((rc = ucgb200_neigh_decide(c, &flag))) return rc;
       t.stop();
     }
+    // fix cluster_switch: force_reneighbor at next_reneighbor; pre_exchange() rebuilds, labels the
+    // clusters and switches types (fix_cluster_switch.cpp:464-481), then Verlet rebuilds again
+    if (d.cluster_freq > 0 && c->cluster.set && c->cluster.next_reneighbor == c->ntimestep) {
+      StageTimer t(c, 3);
+      if ((rc = ucgb200_neigh_build(c))) return rc;
+      if ((rc = ucgb200_cluster_check(c, nullptr))) return rc;
+      if ((rc = ucgb200_cluster_switch(c, nullptr, nullptr))) return rc;
+      c->cluster.next_reneighbor = c->ntimestep + d.cluster_freq;
+      flag = 1;
+      t.stop();
+    }
     if (flag) { if ((rc = ucgb200_neigh_build(c))) return rc; }
     else {
       StageTimer t(c, 2);

@@ -192,15 +192,19 @@ struct ucgb200_ctx {
   long long t_launch[4] = {0, 0, 0, 0};
   bool pair_timed = false;
 
-  // cluster switch (fix cluster_switch)
+  // fix cluster_switch (cluster_switch.cu): per-molecule arrays are indexed by molecule id
   struct Cluster {
-    int mol_seed = 0, mol_offset = 0, max_mol = 0, n_switch = 0, n_contact_types = 0;
-    double cutoff = 0;
-    std::vector<int> type_on, type_off, contact_map;
-    std::vector<double> prob_on, prob_off;
-    ucg::Buf<int> d_label, d_label2, d_changed, d_typemap, d_contact, d_molflag;
-    ucg::Buf<double> d_prob;
     bool set = false;
+    int mol_seed = 0, mol_offset = 0, max_mol = -1, n_switch = 0, n_switch_per_mol = 0, nmol = 0, ntypes = 0, groupbit = 1;
+    int seed = 1, nedges = 0, rounds = 0;
+    unsigned long long ndrawn = 0;     // RanPark uniforms consumed so far (random_unequal, :915)
+    long long next_reneighbor = 0;     // :71, :480
+    double cutoff = 0, prob_on = 0, prob_off = 1;
+    double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<int> type_on, type_off;
+    ucg::Buf<int> d_state, d_restrict, d_label, d_accept, d_present, d_sum, d_draws, d_rank, d_gmask, d_scratch;
+    ucg::Buf<int2> d_edges;
+    ucg::Buf<unsigned char> d_contact;
   } cluster;
 
   // rleucg / bethe_density configuration (types are STATE types in these styles)

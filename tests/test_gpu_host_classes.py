@@ -171,3 +171,37 @@ def test_bethe_density_deck(pkg, fixtures, tmp_path):
     assert np.abs(b["ucgp"] - a["ucgp"]).max() <= 1e-9
     assert abs(gpu.eng_vdwl() - ref.eng_vdwl()) <= 1e-7 * abs(ref.eng_vdwl())
     assert rel_err(gpu.virial()[0], ref.virial()[0]) <= 1e-7
+
+
+def test_cluster_switch_deck(pkg, fixtures, tmp_path):
+    """config-4 style deck through the drop-in classes: table_rleucg_interface + nve/ucgld/wall/hard +
+    cluster_switch; same RanPark stream, so the switched atom types must agree exactly"""
+    import os
+    import test_gpu_cluster_switch as T
+    liq, half = T._system(6)
+    sims = []
+    for cls, sub in ((rb.RefSim, "ref"), (rb.HostSim, "gpu")):
+        d = tmp_path / sub
+        d.mkdir()
+        orig = rb.RefSim
+        try:
+            T.rb.RefSim = cls          # build the same deck with the other set of classes
+            s = T._ref(liq, half, d, fixtures, 1.08, 5, 15123, 0.3)
+        finally:
+            T.rb.RefSim = orig
+        cwd = os.getcwd()
+        os.chdir(d)
+        try:
+            s.setup(1)
+            s.run(17, 1)
+        finally:
+            os.chdir(cwd)
+        sims.append(s)
+    ref, gpu = sims
+    a, b = ref.get_atoms(), gpu.get_atoms()
+    assert np.array_equal(a["type"], b["type"]) and (a["type"] != liq.type).sum() > 0
+    assert [ref.fix_vector(2, k) for k in range(7)] == [gpu.fix_vector(2, k) for k in range(7)]
+    assert rel_err(b["x"], a["x"]) <= 1e-10
+    assert rel_err(b["f"], a["f"]) <= 1e-6
+    for name in ("cluster_assignment.log", "state_assignment.log"):
+        assert (tmp_path / "ref" / name).read_text() == (tmp_path / "gpu" / name).read_text()
