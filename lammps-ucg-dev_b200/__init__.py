@@ -248,6 +248,20 @@ class Context:
         self._ck(self._l.ucgb200_atoms_download(self._h, int(n), C.byref(st), C.c_uint(mask)))
         return arrs
 
+    def atoms_download_into(self, **arrays):
+        """same, into caller-owned C-contiguous arrays (pinned host memory makes the copies true DMA)"""
+        n = self.natoms()[0]
+        bits = dict(x=F_X, v=F_V, f=F_F, type=F_TYPE, mask=F_MASK, tag=F_TAG, molecule=F_MOLECULE,
+                    ucgstate=F_UCGSTATE, ucgl=F_UCGL, ucgvl=F_UCGVL, ucgml=F_UCGML, ucgp=F_UCGP,
+                    ucgforce=F_UCGFORCE, ucgsoftmaxscores=F_SCORES, num_ucgstates=F_NUMSTATES)
+        mask = 0
+        for k, v in arrays.items():
+            isint = k in ("type", "mask", "tag", "molecule", "ucgstate", "num_ucgstates")
+            assert v.flags.c_contiguous and v.dtype == (np.int32 if isint else np.float64) and v.shape[0] >= n, k
+            mask |= bits[k]
+        st = self._atoms_struct(arrays)
+        self._ck(self._l.ucgb200_atoms_download(self._h, int(n), C.byref(st), C.c_uint(mask)))
+
     def natoms(self):
         a, b = C.c_int(), C.c_int()
         self._ck(self._l.ucgb200_natoms(self._h, C.byref(a), C.byref(b)))

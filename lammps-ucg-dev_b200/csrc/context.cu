@@ -54,6 +54,7 @@ extern "C" int ucgb200_destroy(ucgb200_ctx *c) {
   c->gcell_count.release(); c->gcell_start.release(); c->order.release(); c->cell_of.release();
   c->scan_tmp.release(); c->ghost_cnt.release(); c->ghost_off.release();
   c->neigh.release(); c->numneigh.release(); c->statebits.release(); c->d_flags.release();
+  c->stage_d.release(); c->stage_i.release();
   c->d_partials.release(); c->d_ev.release(); c->d_err.release(); c->d_gfac.release();
   {
     auto &k = c->cluster;
@@ -433,29 +434,30 @@ extern "C" int ucgb200_atoms_upload(ucgb200_ctx *c, int nlocal, const ucgb200_at
     UCG_CHECK(c, cudaStreamSynchronize(st));
   }
   if (nlocal == 0) return 0;
-  // staging buffers (device): scan_tmp is reused for ints, d_partials for doubles
+  // device staging: every field gets its own slot, so the H2D copies queue back to back (true DMA
+  // when the host arrays are pinned) and each pack kernel only waits for its own copy
   size_t n = nlocal;
-  UCG_CHECK(c, c->d_partials.ensure(3 * n + 64));
-  UCG_CHECK(c, c->scan_tmp.ensure(n + 64));
-  double *sd = c->d_partials.p;
-  int *si = c->scan_tmp.p;
+  UCG_CHECK(c, c->stage_d.ensure(16 * n + 64));
+  UCG_CHECK(c, c->stage_i.ensure(5 * n + 64));
+  double *sd = c->stage_d.p;
+  int *si = c->stage_i.p;
   const int *orig = c->orig.p;
 #define UP_D(ptr, cnt) UCG_CHECK(c, cudaMemcpyAsync(sd, (ptr), (cnt) * sizeof(double), cudaMemcpyHostToDevice, st))
 #define UP_I(ptr, cnt) UCG_CHECK(c, cudaMemcpyAsync(si, (ptr), (cnt) * sizeof(int), cudaMemcpyHostToDevice, st))
-  if ((fields & UCGB200_F_X) && h->x) { UP_D(h->x, 3 * n); k_pack_vec3<<<GRID1(nlocal)>>>(c->pos.p, sd, orig, nlocal); UCG_LAUNCHED(c); c->list_valid = c->list_valid && !fresh; }
-  if ((fields & UCGB200_F_UCGL) && h->ucgl) { UP_D(h->ucgl, n); k_pack_w<<<GRID1(nlocal)>>>(c->pos.p, sd, orig, nlocal); UCG_LAUNCHED(c); }
-  if ((fields & UCGB200_F_V) && h->v) { UP_D(h->v, 3 * n); k_pack_vec3<<<GRID1(nlocal)>>>(c->vel.p, sd, orig, nlocal); UCG_LAUNCHED(c); }
-  if ((fields & UCGB200_F_UCGVL) && h->ucgvl) { UP_D(h->ucgvl, n); k_pack_w<<<GRID1(nlocal)>>>(c->vel.p, sd, orig, nlocal); UCG_LAUNCHED(c); }
-  if ((fields & UCGB200_F_F) && h->f) { UP_D(h->f, 3 * n); k_pack_vec3<<<GRID1(nlocal)>>>(c->frc.p, sd, orig, nlocal); UCG_LAUNCHED(c); }
-  if ((fields & UCGB200_F_UCGFORCE) && h->ucgforce) { UP_D(h->ucgforce, n); k_pack_w<<<GRID1(nlocal)>>>(c->frc.p, sd, orig, nlocal); UCG_LAUNCHED(c); }
-  if ((fields & UCGB200_F_SCORES) && h->ucgsoftmaxscores) { UP_D(h->ucgsoftmaxscores, 2 * n); k_pack_d2<<<GRID1(nlocal)>>>(c->scores.p, sd, orig, nlocal); UCG_LAUNCHED(c); }
-  if ((fields & UCGB200_F_UCGML) && h->ucgml) { UP_D(h->ucgml, n); k_pack_scalar_d<<<GRID1(nlocal)>>>(c->ucgml.p, sd, orig, nlocal); UCG_LAUNCHED(c); }
-  if ((fields & UCGB200_F_UCGP) && h->ucgp) { UP_D(h->ucgp, n); k_pack_scalar_d<<<GRID1(nlocal)>>>(c->ucgp.p, sd, orig, nlocal); UCG_LAUNCHED(c); }
-  if ((fields & UCGB200_F_TYPE) && h->type) { UP_I(h->type, n); k_pack_ts<<<GRID1(nlocal)>>>(c->ts.p, si, orig, nlocal, 0); UCG_LAUNCHED(c); }
-  if ((fields & UCGB200_F_UCGSTATE) && h->ucgstate) { UP_I(h->ucgstate, n); k_pack_ts<<<GRID1(nlocal)>>>(c->ts.p, si, orig, nlocal, 1); UCG_LAUNCHED(c); }
-  if ((fields & UCGB200_F_MASK) && h->mask) { UP_I(h->mask, n); k_pack_scalar_i<<<GRID1(nlocal)>>>(c->mask.p, si, orig, nlocal); UCG_LAUNCHED(c); }
-  if ((fields & UCGB200_F_TAG) && h->tag) { UP_I(h->tag, n); k_pack_scalar_i<<<GRID1(nlocal)>>>(c->tag.p, si, orig, nlocal); UCG_LAUNCHED(c); }
-  if ((fields & UCGB200_F_MOLECULE) && h->molecule) { UP_I(h->molecule, n); k_pack_scalar_i<<<GRID1(nlocal)>>>(c->mol.p, si, orig, nlocal); UCG_LAUNCHED(c); }
+  if ((fields & UCGB200_F_X) && h->x) { UP_D(h->x, 3 * n); k_pack_vec3<<<GRID1(nlocal)>>>(c->pos.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += 3 * n; c->list_valid = c->list_valid && !fresh; }
+  if ((fields & UCGB200_F_UCGL) && h->ucgl) { UP_D(h->ucgl, n); k_pack_w<<<GRID1(nlocal)>>>(c->pos.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += n; }
+  if ((fields & UCGB200_F_V) && h->v) { UP_D(h->v, 3 * n); k_pack_vec3<<<GRID1(nlocal)>>>(c->vel.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += 3 * n; }
+  if ((fields & UCGB200_F_UCGVL) && h->ucgvl) { UP_D(h->ucgvl, n); k_pack_w<<<GRID1(nlocal)>>>(c->vel.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += n; }
+  if ((fields & UCGB200_F_F) && h->f) { UP_D(h->f, 3 * n); k_pack_vec3<<<GRID1(nlocal)>>>(c->frc.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += 3 * n; }
+  if ((fields & UCGB200_F_UCGFORCE) && h->ucgforce) { UP_D(h->ucgforce, n); k_pack_w<<<GRID1(nlocal)>>>(c->frc.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += n; }
+  if ((fields & UCGB200_F_SCORES) && h->ucgsoftmaxscores) { UP_D(h->ucgsoftmaxscores, 2 * n); k_pack_d2<<<GRID1(nlocal)>>>(c->scores.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += 2 * n; }
+  if ((fields & UCGB200_F_UCGML) && h->ucgml) { UP_D(h->ucgml, n); k_pack_scalar_d<<<GRID1(nlocal)>>>(c->ucgml.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += n; }
+  if ((fields & UCGB200_F_UCGP) && h->ucgp) { UP_D(h->ucgp, n); k_pack_scalar_d<<<GRID1(nlocal)>>>(c->ucgp.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += n; }
+  if ((fields & UCGB200_F_TYPE) && h->type) { UP_I(h->type, n); k_pack_ts<<<GRID1(nlocal)>>>(c->ts.p, si, orig, nlocal, 0); UCG_LAUNCHED(c); si += n; }
+  if ((fields & UCGB200_F_UCGSTATE) && h->ucgstate) { UP_I(h->ucgstate, n); k_pack_ts<<<GRID1(nlocal)>>>(c->ts.p, si, orig, nlocal, 1); UCG_LAUNCHED(c); si += n; }
+  if ((fields & UCGB200_F_MASK) && h->mask) { UP_I(h->mask, n); k_pack_scalar_i<<<GRID1(nlocal)>>>(c->mask.p, si, orig, nlocal); UCG_LAUNCHED(c); si += n; }
+  if ((fields & UCGB200_F_TAG) && h->tag) { UP_I(h->tag, n); k_pack_scalar_i<<<GRID1(nlocal)>>>(c->tag.p, si, orig, nlocal); UCG_LAUNCHED(c); si += n; }
+  if ((fields & UCGB200_F_MOLECULE) && h->molecule) { UP_I(h->molecule, n); k_pack_scalar_i<<<GRID1(nlocal)>>>(c->mol.p, si, orig, nlocal); UCG_LAUNCHED(c); si += n; }
 #undef UP_D
 #undef UP_I
   return 0;
@@ -470,13 +472,17 @@ extern "C" int ucgb200_atoms_download(ucgb200_ctx *c, int cap, ucgb200_atoms *h,
   size_t n = nlocal;
   if (n == 0) return 0;
   if ((fields & UCGB200_F_NUMSTATES) && h->num_ucgstates) { int rc = rebuild_maps(c); if (rc) return rc; }
-  UCG_CHECK(c, c->d_partials.ensure(3 * n + 64));
-  UCG_CHECK(c, c->scan_tmp.ensure(n + 64));
-  double *sd = c->d_partials.p;
-  int *si = c->scan_tmp.p;
+  // every field is gathered into its own slot of a device staging area in host order, all D2H
+  // copies are queued behind the gathers, and the stream is synchronised once
+  UCG_CHECK(c, c->stage_d.ensure(16 * n + 64));
+  UCG_CHECK(c, c->stage_i.ensure(6 * n + 64));
+  double *sd = c->stage_d.p;
+  int *si = c->stage_i.p;
   const int *orig = c->orig.p;
-#define DN_D(ptr, cnt) UCG_CHECK(c, cudaMemcpyAsync((ptr), sd, (cnt) * sizeof(double), cudaMemcpyDeviceToHost, st)); UCG_CHECK(c, cudaStreamSynchronize(st))
-#define DN_I(ptr, cnt) UCG_CHECK(c, cudaMemcpyAsync((ptr), si, (cnt) * sizeof(int), cudaMemcpyDeviceToHost, st)); UCG_CHECK(c, cudaStreamSynchronize(st))
+  struct Copy { void *dst; const void *src; size_t bytes; };
+  std::vector<Copy> copies;
+#define DN_D(ptr, cnt) do { copies.push_back({(ptr), sd, (cnt) * sizeof(double)}); sd += (cnt); } while (0)
+#define DN_I(ptr, cnt) do { copies.push_back({(ptr), si, (cnt) * sizeof(int)}); si += (cnt); } while (0)
   if ((fields & UCGB200_F_X) && h->x) { k_unpack_vec3<<<GRID1(nlocal)>>>(sd, c->pos.p, orig, nlocal); UCG_LAUNCHED(c); DN_D(h->x, 3 * n); }
   if ((fields & UCGB200_F_UCGL) && h->ucgl) { k_unpack_w<<<GRID1(nlocal)>>>(sd, c->pos.p, orig, nlocal); UCG_LAUNCHED(c); DN_D(h->ucgl, n); }
   if ((fields & UCGB200_F_V) && h->v) { k_unpack_vec3<<<GRID1(nlocal)>>>(sd, c->vel.p, orig, nlocal); UCG_LAUNCHED(c); DN_D(h->v, 3 * n); }
@@ -492,6 +498,8 @@ extern "C" int ucgb200_atoms_download(ucgb200_ctx *c, int cap, ucgb200_atoms *h,
   if ((fields & UCGB200_F_MASK) && h->mask) { k_unpack_scalar_i<<<GRID1(nlocal)>>>(si, c->mask.p, orig, nlocal); UCG_LAUNCHED(c); DN_I(h->mask, n); }
   if ((fields & UCGB200_F_TAG) && h->tag) { k_unpack_scalar_i<<<GRID1(nlocal)>>>(si, c->tag.p, orig, nlocal); UCG_LAUNCHED(c); DN_I(h->tag, n); }
   if ((fields & UCGB200_F_MOLECULE) && h->molecule) { k_unpack_scalar_i<<<GRID1(nlocal)>>>(si, c->mol.p, orig, nlocal); UCG_LAUNCHED(c); DN_I(h->molecule, n); }
+  for (const Copy &cp : copies) UCG_CHECK(c, cudaMemcpyAsync(cp.dst, cp.src, cp.bytes, cudaMemcpyDeviceToHost, st));
+  if (!copies.empty()) UCG_CHECK(c, cudaStreamSynchronize(st));
 #undef DN_D
 #undef DN_I
   return 0;

@@ -142,6 +142,8 @@ struct ucgb200_ctx {
   ucg::Buf<double4> pos, pos_alt, vel, vel_alt, frc, frc_alt, xhold;
   ucg::Buf<double2> scores, scores_alt;
   ucg::Buf<double> ucgp, ucgp_alt, ucgml, ucgml_alt;
+  ucg::Buf<double> stage_d;   // host<->device staging of atoms_upload / atoms_download
+  ucg::Buf<int> stage_i;
   ucg::Buf<int> ts, ts_alt, mask, mask_alt, tag, tag_alt, mol, mol_alt, orig, orig_alt;
   // ghosts: sources = local periodic images + border records received from other bricks
   ucg::Buf<int> ghost_owner, ghost_code, ghost_src, slot_of_src;
