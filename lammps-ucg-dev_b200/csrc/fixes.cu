@@ -117,6 +117,116 @@ __global__ void k_langevin(const double4 *__restrict__ vel, double4 *__restrict_
   frc[i].w += gamma1 * vl + fran;
 }
 
+// ---- resident run loop: every per-site fix stage between two pair evaluations in ONE pass
+// post_force fixes in definition order (ucgld/langevin, ucgstate, wall bias) -> final_integrate of
+// this step -> [initial_integrate of the next step -> Neighbor::check_distance].  The arithmetic of
+// each stage is that of the single-stage kernels above, applied in the same order to the same
+// values, so trajectories are identical; the site record is read and written once (~270 B/site)
+// instead of five times.
+struct TailArgs {
+  double4 *pos, *vel, *frc;
+  const double4 *xhold;
+  int *ts;
+  const int *mask, *tag;
+  const double *ucgml, *gfac;
+  const double2 *scores;
+  double *ucgp;
+  const TypeInfo *tinfo;
+  int n, ntypes;
+  // langevin
+  int langevin, lgroupbit;
+  double tsqrt;
+  unsigned lseed;
+  // ucgstate
+  int ucgstate_mode;   // -1 absent, 0 deterministic, 1 ld, 2 mc
+  unsigned useed;
+  double urate;
+  // integrator
+  int groupbit, bias;
+  double barrier, dtv, dtf;
+  int fuse_next;       // also do the next step's initial_integrate + check_distance
+  double triggersq;
+  int *flags;
+  unsigned long long step;
+};
+
+template <bool WALL>
+__global__ void __launch_bounds__(256) k_step_tail(TailArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  int t = a.ts[i];
+  const int type = t & 0xffff;
+  const int m = a.mask[i];
+  double4 x = a.pos[i], v = a.vel[i], f = a.frc[i];
+  bool fdirty = false, xdirty = false;
+  if (a.langevin && (m & a.lgroupbit)) {                                  // k_langevin
+    const double gamma1 = a.gfac[type];
+    const double gamma2 = a.gfac[a.ntypes + 1 + type] * a.tsqrt;
+    const double fran = gamma2 * (philox_uniform(a.lseed, 0x4c414e47u, (unsigned)a.tag[i], a.step) - 0.5);
+    f.w += gamma1 * v.w + fran;
+    fdirty = true;
+  }
+  if (a.ucgstate_mode >= 0) {                                             // k_ucgstate
+    int state = (t >> 16) & 1;
+    double p;
+    if (a.tinfo[type].nstates == 1) {
+      if (a.ucgstate_mode != 1) state = 0;
+      p = 1.0;
+    } else {
+      const double2 s = a.scores[i];
+      const double e0 = exp(fmin(s.x, 700.0)), e1 = exp(fmin(s.y, 700.0));
+      p = fmin(1.0 - 1e-6, fmax(1e-6, e1 / (e0 + e1)));
+      if (a.ucgstate_mode == 2) {
+        double fac = state == 0 ? p / (1.0 - p) : (1.0 - p) / p;
+        fac = fmin(fac, 1.0) * a.urate;
+        const double r = philox_uniform(a.useed, 0x55434753u, (unsigned)a.tag[i], a.step);
+        state = (r < fac) ? 0 : 1;
+      } else if (a.ucgstate_mode == 0) {
+        state = (int)round(p);
+      }
+    }
+    a.ucgp[i] = p;
+    if (a.ucgstate_mode != 1) {
+      t = type | (state << 16);
+      x.w = p;
+      xdirty = true;
+    }
+  }
+  const bool ingroup = (m & a.groupbit) != 0;
+  if (WALL && a.bias && ingroup) {                                        // k_wall_bias
+    const double y = x.w - 0.5;
+    f.w += (-7980 * y * y * y * y * y * y * y * y * y + 2 * y) * 10 * a.barrier;
+    fdirty = true;
+  }
+  double dtfm = 0.0, dtflm = 0.0;
+  if (ingroup) {                                                          // k_nve_final
+    dtfm = a.dtf / a.tinfo[type].mass;
+    dtflm = a.dtf / a.ucgml[i];
+    v.x += dtfm * f.x; v.y += dtfm * f.y; v.z += dtfm * f.z;
+    v.w += dtflm * f.w;
+    if (WALL) {
+      if (x.w < 0.0) { x.w = -x.w; v.w = -v.w; xdirty = true; }
+      else if (x.w > 1.0) { x.w = 2.0 - x.w; v.w = -v.w; xdirty = true; }
+    }
+  }
+  if (a.fuse_next) {
+    if (ingroup) {                                                        // k_nve_initial of step + 1
+      v.x += dtfm * f.x; v.y += dtfm * f.y; v.z += dtfm * f.z;
+      x.x += a.dtv * v.x; x.y += a.dtv * v.y; x.z += a.dtv * v.z;
+      v.w += dtflm * f.w;
+      x.w += a.dtv * v.w;
+      xdirty = true;
+      if (WALL) t = type | ((x.w < 0.5 ? 0 : 1) << 16);
+    }
+    const double4 h = a.xhold[i];                                         // k_check_distance
+    if (rsq_exact(x.x - h.x, x.y - h.y, x.z - h.z) > a.triggersq) a.flags[0] = 1;
+  }
+  if (ingroup) a.vel[i] = v;
+  if (fdirty) a.frc[i] = f;
+  if (xdirty) a.pos[i] = x;
+  a.ts[i] = t;
+}
+
 // sums: [0] sum 0.5*ml*vl^2*mvv2e, [1] sum 0.5*m*|v|^2*mvv2e, [2] count in group
 template <int BS>
 __global__ void __launch_bounds__(BS) k_kinetic(const double4 *__restrict__ vel, const int *__restrict__ ts,
@@ -246,5 +356,41 @@ extern "C" int ucgb200_kinetic_energy(ucgb200_ctx *c, int groupbit, double *ke_s
   if (rc) return rc;
   if (ke_sum) *ke_sum = o[1];
   if (count) *count = (long long)(o[2] + 0.5);
+  return 0;
+}
+
+// Fused tail of a resident step (see k_step_tail).  gfac layout as uploaded by ucgb200_fix_langevin.
+int ucg_step_tail(ucgb200_ctx *c, const ucgb200_deck &d, double tsqrt, int fuse_next) {
+  cudaSetDevice(c->device);
+  int rc = rebuild_maps(c);
+  if (rc) return rc;
+  if (c->nlocal == 0) return 0;
+  if (d.langevin) {
+    const int nt = c->n_formal;
+    std::vector<double> g(2 * (nt + 1));
+    for (int t = 0; t <= nt; t++) { g[t] = c->lang_g1[t]; g[nt + 1 + t] = c->lang_g2[t]; }
+    if (g != c->gfactor1) {
+      UCG_CHECK(c, c->d_gfac.ensure(g.size()));
+      UCG_CHECK(c, cudaMemcpyAsync(c->d_gfac.p, g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      UCG_CHECK(c, cudaStreamSynchronize(c->stream));
+      c->gfactor1 = g;
+    }
+  }
+  TailArgs a{};
+  a.pos = c->pos.p; a.vel = c->vel.p; a.frc = c->frc.p; a.xhold = c->xhold.p; a.ts = c->ts.p;
+  a.mask = c->mask.p; a.tag = c->tag.p; a.ucgml = c->ucgml.p; a.gfac = c->d_gfac.p; a.scores = c->scores.p;
+  a.ucgp = c->ucgp.p; a.tinfo = c->d_typeinfo.p; a.n = c->nlocal; a.ntypes = c->n_formal;
+  a.langevin = d.langevin; a.lgroupbit = d.langevin_groupbit ? d.langevin_groupbit : 1; a.tsqrt = tsqrt;
+  a.lseed = (unsigned)d.langevin_seed;
+  a.ucgstate_mode = d.ucgstate == 0 ? -1 : (d.ucgstate == 1 ? 0 : (d.ucgstate == 2 ? 1 : 2));
+  a.useed = (unsigned)d.ucgstate_seed; a.urate = d.ucgstate_rate;
+  a.groupbit = d.nve_groupbit ? d.nve_groupbit : 1; a.bias = d.wall_bias; a.barrier = d.wall_barrier;
+  a.dtv = c->dt; a.dtf = 0.5 * c->dt * c->ftm2v;
+  a.fuse_next = fuse_next; a.triggersq = 0.25 * c->skin * c->skin; a.flags = c->d_flags.p;
+  a.step = (unsigned long long)c->ntimestep;
+  if (fuse_next) UCG_CHECK(c, cudaMemsetAsync(c->d_flags.p, 0, sizeof(int), c->stream));
+  if (d.nve == 2) k_step_tail<true><<<GRID1(c->nlocal)>>>(a);
+  else k_step_tail<false><<<GRID1(c->nlocal)>>>(a);
+  UCG_LAUNCHED(c);
   return 0;
 }

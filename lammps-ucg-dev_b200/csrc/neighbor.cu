@@ -513,6 +513,135 @@ k_build_rows(const double4 *__restrict__ pos, const int *__restrict__ ts, int nl
   }
 }
 
+// Cell-tiled variant of k_build_rows (same rows, same order): one CTA per owned cell.  The
+// candidates of the 27-cell stencil (18 contiguous ranges: 9 x-rows of 3 cells, owned then ghost)
+// are staged ONCE in shared memory — {x,y,z,.}, type and global index — and every site of the cell
+// scans them from there, so each candidate record is read from L2/HBM once per cell instead of once
+// per site (~18x less global traffic).  Cells whose stencil exceeds the staging capacity are
+// processed in chunks.  Row order (dz, dy, owned|ghost, index) and the inner/skin partition are
+// those of k_build_rows, so the lists are identical.
+constexpr int TILE_CAP = 768;     // candidates per chunk: 768 * 40 B = 30 KB
+constexpr int TILE_BS = 128;
+__global__ void __launch_bounds__(TILE_BS)
+k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, int nlocal, Grid g,
+                   const int *__restrict__ ostart, const int *__restrict__ gstart, const PairInfo *__restrict__ pinfo,
+                   int na, int *__restrict__ neigh, int stride, int *__restrict__ numneigh, int *__restrict__ flags,
+                   int cap) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  // structure of arrays: a 16-byte {x,y} and an 8-byte z per candidate keep the warp-wide reads free of
+  // bank conflicts (a 32-byte record read as two 16-byte halves is a 2-way conflict)
+  double2 *s_xy = reinterpret_cast<double2 *>(s_raw);
+  double *s_z = reinterpret_cast<double *>(s_xy + TILE_CAP);
+  int *s_ts = reinterpret_cast<int *>(s_z + TILE_CAP);
+  int *s_j = s_ts + TILE_CAP;
+  int *s_outer = s_j + TILE_CAP;                 // [warps][stride]
+  __shared__ int s_rb[18], s_re[18], s_roff[18], s_pre[19];
+  constexpr int NW = TILE_BS / 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // owned cell of this CTA
+  const int cell = blockIdx.x;
+  const int ix = cell % g.ninner[0] + 1, iy = (cell / g.ninner[0]) % g.ninner[1] + 1, iz = cell / (g.ninner[0] * g.ninner[1]) + 1;
+  const int c = (iz * g.nc[1] + iy) * g.nc[0] + ix;
+  const int sb = ostart[c], se = ostart[c + 1];
+  if (sb >= se) return;
+  if (threadIdx.x < 18) {
+    const int r = threadIdx.x, yz = r >> 1, pass = r & 1;
+    const int dz = yz / 3 - 1, dy = yz % 3 - 1;
+    const int c0 = ((iz + dz) * g.nc[1] + (iy + dy)) * g.nc[0] + (ix - 1);
+    s_rb[r] = pass == 0 ? ostart[c0] : gstart[c0];
+    s_re[r] = pass == 0 ? ostart[c0 + 3] : gstart[c0 + 3];
+    s_roff[r] = pass == 0 ? 0 : nlocal;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int r = 0; r < 18; r++) { s_pre[r] = acc; acc += s_re[r] - s_rb[r]; }
+    s_pre[18] = acc;
+  }
+  __syncthreads();
+  const int ncand = s_pre[18];
+  int *outer = s_outer + wid * stride;
+  const unsigned lt = (1u << lane) - 1;
+  // per-warp site cursor state lives in registers across chunks: one warp owns sites sb+wid, sb+wid+NW, ...
+  // (counts are kept per site in numneigh scratch when several chunks are needed)
+  const bool single = ncand <= cap;
+  for (int cbase = 0; cbase < ncand; cbase += cap) {
+    const int cn = min(cap, ncand - cbase);
+    __syncthreads();
+    for (int k = threadIdx.x; k < cn; k += TILE_BS) {
+      const int q = cbase + k;
+      int r = 0;
+#pragma unroll
+      for (int t = 1; t < 18; t++) r += (q >= s_pre[t]);
+      const int j = s_rb[r] + (q - s_pre[r]) + s_roff[r];
+      const double4 rj = pos[j];
+      s_xy[k] = make_double2(rj.x, rj.y);
+      s_z[k] = rj.z;
+      s_ts[k] = ts[j] & 0xffff;
+      s_j[k] = j;
+    }
+    __syncthreads();
+    for (int i = sb + wid; i < se; i += NW) {
+      const double4 ri = pos[i];
+      const PairInfo *prow = pinfo + (ts[i] & 0xffff) * na;
+      // one actual type (the benchmark liquids): the two cutoffs are loop invariants
+      const bool one_type = na == 2;
+      const double cn1 = prow[1].cutneighsq, cs1 = prow[1].cutsq;
+      int *row = neigh + (size_t)i * stride;
+      int cnt_in = 0, cnt_out = 0;
+      if (!single && cbase > 0) {   // resume: counts parked in the row tail / numneigh
+        cnt_in = numneigh[i] & 0xffff;
+        cnt_out = numneigh[i] >> 16;
+        for (int k = lane; k < min(cnt_out, stride); k += 32) outer[k] = row[stride - 1 - k];
+        __syncwarp();
+      }
+      for (int base = 0; base < cn; base += 32) {
+        const int k = base + lane;
+        bool hit = false, inner = false;
+        int j = -1;
+        if (k < cn) {
+          j = s_j[k];
+          const double2 rxy = s_xy[k];
+          const double rsq = rsq_exact(ri.x - rxy.x, ri.y - rxy.y, ri.z - s_z[k]);
+          double cn = cn1, cs = cs1;
+          if (!one_type) { const PairInfo pi = prow[s_ts[k]]; cn = pi.cutneighsq; cs = pi.cutsq; }
+          hit = (j != i) && (rsq <= cn);
+          inner = hit && (rsq < cs);
+        }
+        const unsigned m_in = __ballot_sync(0xffffffffu, inner);
+        const unsigned m_out = __ballot_sync(0xffffffffu, hit && !inner);
+        if (inner) {
+          const int p = cnt_in + __popc(m_in & lt);
+          if (p < stride) row[p] = j;
+        } else if (hit) {
+          const int p = cnt_out + __popc(m_out & lt);
+          if (p < stride) outer[p] = j;
+        }
+        cnt_in += __popc(m_in);
+        cnt_out += __popc(m_out);
+      }
+      __syncwarp();
+      const bool last = cbase + cap >= ncand;
+      const int total = cnt_in + cnt_out;
+      if (last) {
+        if (total <= stride)
+          for (int k = lane; k < cnt_out; k += 32) row[cnt_in + k] = outer[k];
+        if (lane == 0) {
+          numneigh[i] = min(total, stride);
+          if (total > stride) atomicMax(&flags[1], total);
+        }
+      } else {
+        // park the skin entries at the row's tail (reversed) until the next chunk; if the row is about
+        // to overflow the final count reports it and the build is redone with a larger stride
+        if (total <= stride)
+          for (int k = lane; k < cnt_out; k += 32) row[stride - 1 - k] = outer[k];
+        if (lane == 0) numneigh[i] = (min(cnt_in, 0xffff)) | (min(cnt_out, 0x7fff) << 16);
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // [stock] Neighbor::check_distance: any owned atom moved > skin/2 since the last build
 __global__ void k_check_distance(const double4 *__restrict__ pos, const double4 *__restrict__ xhold, int n,
                                  double triggersq, int *__restrict__ flags) {
@@ -611,10 +740,27 @@ static int build_rows(ucgb200_ctx *c) {
   while (true) {
     UCG_CHECK(c, c->neigh.ensure((size_t)nlocal * c->neigh_stride));
     UCG_CHECK(c, cudaMemsetAsync(c->d_flags.p + 1, 0, sizeof(int), c->stream));
-    long long nthreads = (long long)nlocal * 32;
-    k_build_rows<<<nblocks(nthreads, 256), 256, 8 * c->neigh_stride * sizeof(int), c->stream>>>(
-        c->pos.p, c->ts.p, nlocal, c->grid, c->cell_start.p, c->gcell_start.p, c->d_pairinfo.p, na,
-        c->neigh.p, c->neigh_stride, c->numneigh.p, c->d_flags.p);
+    const int tiled = getenv("UCGB200_BUILD_TILED") ? atoi(getenv("UCGB200_BUILD_TILED")) : 1;
+    int cap = getenv("UCGB200_TILE_CAP") ? atoi(getenv("UCGB200_TILE_CAP")) : TILE_CAP;   // small values exercise the chunked path
+    cap = std::min(std::max(cap, 32), TILE_CAP);
+    if (tiled) {
+      const int ncell_owned = c->grid.ninner[0] * c->grid.ninner[1] * c->grid.ninner[2];
+      const size_t smem = (size_t)TILE_CAP * (sizeof(double2) + sizeof(double) + 2 * sizeof(int)) + (TILE_BS / 32) * c->neigh_stride * sizeof(int);
+      static bool attr_set = false;
+      if (!attr_set) {
+        UCG_CHECK(c, cudaFuncSetAttribute(k_build_rows_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+      }
+      if (smem > 96 * 1024) return fail(c, "neighbor rows too long for the tiled build");
+      k_build_rows_tiled<<<ncell_owned, TILE_BS, smem, c->stream>>>(
+          c->pos.p, c->ts.p, nlocal, c->grid, c->cell_start.p, c->gcell_start.p, c->d_pairinfo.p, na,
+          c->neigh.p, c->neigh_stride, c->numneigh.p, c->d_flags.p, cap);
+    } else {
+      long long nthreads = (long long)nlocal * 32;
+      k_build_rows<<<nblocks(nthreads, 256), 256, 8 * c->neigh_stride * sizeof(int), c->stream>>>(
+          c->pos.p, c->ts.p, nlocal, c->grid, c->cell_start.p, c->gcell_start.p, c->d_pairinfo.p, na,
+          c->neigh.p, c->neigh_stride, c->numneigh.p, c->d_flags.p);
+    }
     UCG_LAUNCHED(c);
     int rc = read_flags(c);
     if (rc) return rc;
@@ -822,6 +968,17 @@ extern "C" int ucgb200_neigh_decide(ucgb200_ctx *c, int *rebuild) {
     k_check_distance<<<nblocks(c->nlocal, 256), 256, 0, c->stream>>>(c->pos.p, c->xhold.p, c->nlocal, triggersq, c->d_flags.p);
     UCG_LAUNCHED(c);
   }
+  UCG_CHECK(c, cudaMemcpyAsync(c->h_flags, c->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  UCG_CHECK(c, cudaStreamSynchronize(c->stream));
+  *rebuild = c->h_flags[0] ? 1 : 0;
+  return 0;
+}
+
+// Neighbor::decide when k_check_distance already ran inside the fused step tail (fixes.cu): only the
+// 4-byte flag travels
+int ucg_neigh_decide_prechecked(ucgb200_ctx *c, int *rebuild) {
+  cudaSetDevice(c->device);
+  if (!c->list_valid) { *rebuild = 1; return 0; }
   UCG_CHECK(c, cudaMemcpyAsync(c->h_flags, c->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   UCG_CHECK(c, cudaStreamSynchronize(c->stream));
   *rebuild = c->h_flags[0] ? 1 : 0;

@@ -71,6 +71,9 @@ static int pair_compute(ucgb200_ctx *c, int ev) {
   }
 }
 
+int ucg_step_tail(ucgb200_ctx *c, const ucgb200_deck &d, double tsqrt, int fuse_next);
+int ucg_neigh_decide_prechecked(ucgb200_ctx *c, int *rebuild);
+
 struct StageTimer {
   ucgb200_ctx *c;
   int slot;
@@ -141,10 +144,14 @@ extern "C" int ucgb200_run(ucgb200_ctx *c, int nsteps) {
   c->beginstep = c->ntimestep;
   c->endstep = c->ntimestep + nsteps;
   int rc;
+  // the per-site fix stages between two pair evaluations run as one fused kernel (fixes.cu,
+  // k_step_tail) unless UCGB200_FUSED_TAIL=0; it needs an integrator fix and a single brick loop
+  const bool fused = d.nve && !(getenv("UCGB200_FUSED_TAIL") && atoi(getenv("UCGB200_FUSED_TAIL")) == 0);
+  bool pre_integrated = false;   // initial_integrate + check_distance of this step already done by the last tail
   for (int n = 0; n < nsteps; n++) {
     c->ntimestep++;
     const int ev = d.thermo_every > 0 && (c->ntimestep % d.thermo_every == 0);
-    {
+    if (!pre_integrated) {
       StageTimer t(c, 3);
       if (d.nve) { if ((rc = ucgb200_fix_nve_initial(c, dtv, dtf, gb, d.nve == 2))) return rc; }
       t.stop();
@@ -152,7 +159,8 @@ extern "C" int ucgb200_run(ucgb200_ctx *c, int nsteps) {
     int flag = 0;
     {
       StageTimer t(c, 1);
-      if ((rc = ucgb200_neigh_decide(c, &flag))) return rc;
+      if (pre_integrated) { if ((rc = ucg_neigh_decide_prechecked(c, &flag))) return rc; }
+      else if ((rc = ucgb200_neigh_decide(c, &flag))) return rc;
       t.stop();
     }
     // fix cluster_switch: force_reneighbor at next_reneighbor; pre_exchange() rebuilds, labels the
@@ -179,8 +187,15 @@ extern "C" int ucgb200_run(ucgb200_ctx *c, int nsteps) {
     }
     {
       StageTimer t(c, 3);
-      if ((rc = post_force(c, false))) return rc;
-      if (d.nve) { if ((rc = ucgb200_fix_nve_final(c, dtf, gb, d.nve == 2))) return rc; }
+      if (fused) {
+        if (d.langevin && c->lang_g1.empty()) { if ((rc = langevin_factors(c, c->lang_g1, c->lang_g2))) return rc; }
+        const int fuse_next = (n + 1 < nsteps) ? 1 : 0;
+        if ((rc = ucg_step_tail(c, d, d.langevin ? std::sqrt(current_t_target(c)) : 0.0, fuse_next))) return rc;
+        pre_integrated = fuse_next != 0;
+      } else {
+        if ((rc = post_force(c, false))) return rc;
+        if (d.nve) { if ((rc = ucgb200_fix_nve_final(c, dtf, gb, d.nve == 2))) return rc; }
+      }
       t.stop();
     }
     if (ev) {

@@ -53,6 +53,23 @@ def test_neighbor_list_bit_exact(pkg, fixtures, ncell):
     assert np.array_equal(half_got, half_ref)
 
 
+@pytest.mark.parametrize("knobs", [dict(UCGB200_BUILD_TILED="0"), dict(UCGB200_TILE_CAP="64"), dict(UCGB200_TILE_CAP="200")])
+def test_neighbor_build_variants_give_identical_rows(pkg, fixtures, monkeypatch, knobs):
+    """the cell-tiled build (default), its chunked path (small staging capacity) and the
+    warp-per-site build must produce the same rows in the same order"""
+    liq = _liq((5, 6, 7))
+    ctx = decks.gpu_single_type(pkg, liq, fixtures)
+    ctx.neigh_build()
+    a = ctx.neigh_download()
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    ctx2 = decks.gpu_single_type(pkg, liq, fixtures)
+    ctx2.neigh_build()
+    b = ctx2.neigh_download()
+    for key in ("tag_i", "numneigh", "offsets", "neigh_tags", "neigh_shift"):
+        assert np.array_equal(a[key], b[key]), key
+
+
 def test_neighbor_rebuild_decision_matches(pkg, fixtures):
     liq = _liq(6)
     ctx = decks.gpu_single_type(pkg, liq, fixtures)
