@@ -313,6 +313,18 @@ int ucgb200_halo_unpack_forward(ucgb200_ctx *ctx, const void *d_recvbuf);
 /* device pointer of the rebuild flag (int32) so the host layer can all-reduce it (MAX) */
 int ucgb200_neigh_flag_ptr(ucgb200_ctx *ctx, void **d_flag);
 
+/* Resident multi-brick runs: with a communicator attached, ucgb200_setup / ucgb200_run drive the
+ * exchanges above themselves — NCCL send/recv groups on the context stream (one message per peer
+ * pair), the rebuild decision a 4-byte ncclAllReduce(MAX) — so a step needs no host-side
+ * orchestration and exactly one host synchronisation.  Rank 0 creates the id (128 bytes, the
+ * ncclUniqueId), the host layer broadcasts it by whatever means it has (MPI_Bcast inside LAMMPS,
+ * torch.distributed in the tests), every rank calls _comm_init after ucgb200_halo_configure.
+ * NCCL is loaded at run time (libnccl.so.2); _comm_unique_id returns -4 when it is absent. */
+int ucgb200_comm_unique_id(char *id, int len);
+int ucgb200_comm_init(ucgb200_ctx *ctx, const char *id, int len);
+int ucgb200_comm_destroy(ucgb200_ctx *ctx);
+int ucgb200_comm_stats(ucgb200_ctx *ctx, long long *bytes_forward, int *nrebuilds, int *send_records);
+
 #ifdef __cplusplus
 }
 #endif

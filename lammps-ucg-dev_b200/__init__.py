@@ -384,6 +384,24 @@ class Context:
         self._nranks = int(nranks)
 
     @staticmethod
+    def comm_unique_id() -> bytes:
+        """rank 0: the 128-byte ncclUniqueId to broadcast to every rank"""
+        buf = C.create_string_buffer(128)
+        n = lib().ucgb200_comm_unique_id(buf, 128)
+        if n < 0:
+            raise UCGError(n, "ucgb200_comm_unique_id: NCCL (libnccl.so.2) is not available")
+        return buf.raw[:128]
+
+    def comm_init(self, unique_id: bytes):
+        """attach an NCCL communicator: setup()/run() then drive the brick exchanges themselves"""
+        self._ck(self._l.ucgb200_comm_init(self._h, C.c_char_p(unique_id), len(unique_id)))
+
+    def comm_stats(self):
+        b, r, s_ = C.c_longlong(), C.c_int(), C.c_int()
+        self._ck(self._l.ucgb200_comm_stats(self._h, C.byref(b), C.byref(r), C.byref(s_)))
+        return dict(bytes_forward=b.value, rebuilds=r.value, send_records=s_.value)
+
+    @staticmethod
     def halo_record_bytes():
         a, b, c_ = C.c_int(), C.c_int(), C.c_int()
         lib().ucgb200_halo_record_bytes(C.byref(a), C.byref(b), C.byref(c_))

@@ -1,0 +1,233 @@
+// comm.cu — brick-to-brick exchange for the resident run loop: what stock Comm does over MPI for
+// the reference (exchange / borders / forward_comm with AtomVecUCG's payloads,
+// UCG/atom_vec_ucg.cpp:66-82), here NCCL point-to-point groups over NVLink/NVSwitch issued on the
+// context stream.  Every exchange is one grouped send/recv per peer pair (all peers addressed
+// directly: corners travel in one hop) between the device pack/unpack kernels of neighbor.cu;
+// the per-step rebuild decision is a 4-byte ncclAllReduce(MAX) on the device flag, so a step costs
+// exactly one host synchronisation (the flag read-back that Neighbor::decide needs).
+//
+// NCCL is resolved at run time (dlopen libnccl.so.2): single-GPU users of libucgb200.so need no
+// NCCL, and inside a PyTorch process the already loaded NCCL is the one that is used.
+#include "ucg_internal.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <numeric>
+
+using namespace ucg;
+
+namespace {
+
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+NcclApi &nccl() {
+  static NcclApi api;
+  if (api.lib) return api;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) return api;
+#define UCG_SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, name))
+  UCG_SYM(GetUniqueId, "ncclGetUniqueId"); UCG_SYM(CommInitRank, "ncclCommInitRank"); UCG_SYM(CommDestroy, "ncclCommDestroy");
+  UCG_SYM(Send, "ncclSend"); UCG_SYM(Recv, "ncclRecv"); UCG_SYM(GroupStart, "ncclGroupStart"); UCG_SYM(GroupEnd, "ncclGroupEnd");
+  UCG_SYM(AllReduce, "ncclAllReduce"); UCG_SYM(AllGather, "ncclAllGather"); UCG_SYM(GetErrorString, "ncclGetErrorString");
+#undef UCG_SYM
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.GroupStart && api.GroupEnd &&
+           api.AllReduce && api.AllGather && api.GetErrorString;
+  return api;
+}
+
+#define UCG_NCCL(ctx, expr)                                                                   \
+  do {                                                                                        \
+    ncclResult_t _r = (expr);                                                                 \
+    if (_r != ncclSuccess) {                                                                  \
+      (ctx)->err = std::string(#expr) + ": " + nccl().GetErrorString(_r);                     \
+      return -2;                                                                              \
+    }                                                                                         \
+  } while (0)
+
+struct CommState {
+  ncclComm_t comm = nullptr;
+  Buf<char> send, recv, fwd_send, fwd_recv;
+  Buf<int> d_counts;                 // [nranks] mine, then [nranks*nranks] gathered
+  std::vector<int> send_counts, recv_counts;   // border == forward counts of the current list
+  long long bytes_forward = 0;
+  int nrebuilds = 0;
+};
+
+CommState *state(ucgb200_ctx *c) { return static_cast<CommState *>(c->comm_state); }
+
+// counts[k] = records this rank sends to rank k  ->  recv[k] = records rank k sends to this rank
+int exchange_counts(ucgb200_ctx *c, const std::vector<int> &counts, std::vector<int> &recv) {
+  CommState *s = state(c);
+  const int nr = c->halo.nranks, me = c->halo.rank;
+  UCG_CHECK(c, s->d_counts.ensure((size_t)nr * (nr + 1)));
+  UCG_CHECK(c, cudaMemcpyAsync(s->d_counts.p, counts.data(), nr * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  UCG_NCCL(c, nccl().AllGather(s->d_counts.p, s->d_counts.p + nr, nr, ncclInt32, s->comm, c->stream));
+  std::vector<int> all((size_t)nr * nr);
+  UCG_CHECK(c, cudaMemcpyAsync(all.data(), s->d_counts.p + nr, all.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  UCG_CHECK(c, cudaStreamSynchronize(c->stream));
+  recv.resize(nr);
+  for (int k = 0; k < nr; k++) recv[k] = all[(size_t)k * nr + me];
+  return 0;
+}
+
+// send buffer grouped by destination, receive buffer grouped by source (the layouts of neighbor.cu)
+int all_to_all(ucgb200_ctx *c, const char *sendbuf, char *recvbuf, const std::vector<int> &scount, const std::vector<int> &rcount,
+               size_t rec) {
+  CommState *s = state(c);
+  const int nr = c->halo.nranks;
+  UCG_NCCL(c, nccl().GroupStart());
+  size_t so = 0, ro = 0;
+  for (int k = 0; k < nr; k++) {
+    const size_t sb = (size_t)scount[k] * rec, rb = (size_t)rcount[k] * rec;
+    if (sb) UCG_NCCL(c, nccl().Send(sendbuf + so, sb, ncclChar, k, s->comm, c->stream));
+    if (rb) UCG_NCCL(c, nccl().Recv(recvbuf + ro, rb, ncclChar, k, s->comm, c->stream));
+    so += sb; ro += rb;
+  }
+  UCG_NCCL(c, nccl().GroupEnd());
+  return 0;
+}
+
+int total(const std::vector<int> &v) { return std::accumulate(v.begin(), v.end(), 0); }
+
+}  // namespace
+
+extern "C" int ucgb200_comm_unique_id(char *id, int len) {
+  if (!id || len < (int)sizeof(ncclUniqueId)) return -1;
+  if (!nccl().ok) return -4;
+  ncclUniqueId u;
+  if (nccl().GetUniqueId(&u) != ncclSuccess) return -2;
+  memcpy(id, &u, sizeof(u));
+  return (int)sizeof(u);
+}
+
+extern "C" int ucgb200_comm_init(ucgb200_ctx *c, const char *id, int len) {
+  if (!c || !id || len < (int)sizeof(ncclUniqueId)) return -1;
+  if (c->halo.nranks < 2) return fail(c, "comm_init: configure the brick grid first (ucgb200_halo_configure)");
+  if (!nccl().ok) return fail(c, "comm_init: libnccl.so.2 could not be loaded");
+  cudaSetDevice(c->device);
+  if (c->comm_state) return fail(c, "comm_init: already initialised");
+  auto *s = new CommState();
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof(u));
+  ncclResult_t r = nccl().CommInitRank(&s->comm, c->halo.nranks, u, c->halo.rank);
+  if (r != ncclSuccess) {
+    c->err = std::string("ncclCommInitRank: ") + nccl().GetErrorString(r);
+    delete s;
+    return -2;
+  }
+  c->comm_state = s;
+  return 0;
+}
+
+extern "C" int ucgb200_comm_destroy(ucgb200_ctx *c) {
+  if (!c) return -1;
+  CommState *s = state(c);
+  if (!s) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (s->comm) nccl().CommDestroy(s->comm);
+  s->send.release(); s->recv.release(); s->fwd_send.release(); s->fwd_recv.release(); s->d_counts.release();
+  delete s;
+  c->comm_state = nullptr;
+  return 0;
+}
+
+// comm->exchange() + comm->borders() + neighbor->build(): the rebuild of a multi-brick run
+int ucg_mb_rebuild(ucgb200_ctx *c) {
+  CommState *s = state(c);
+  if (!s) return fail(c, "multi-brick run without ucgb200_comm_init");
+  const int nr = c->halo.nranks;
+  int rb = 0, rf = 0, rm = 0, rc;
+  ucgb200_halo_record_bytes(&rb, &rf, &rm);
+  // sites that left their brick
+  std::vector<int> sc(nr), rcv;
+  if ((rc = ucgb200_migrate_prepare(c, sc.data()))) return rc;
+  if ((rc = exchange_counts(c, sc, rcv))) return rc;
+  UCG_CHECK(c, s->send.ensure((size_t)total(sc) * rm + 64));
+  UCG_CHECK(c, s->recv.ensure((size_t)total(rcv) * rm + 64));
+  if ((rc = ucgb200_migrate_pack(c, s->send.p))) return rc;
+  if ((rc = all_to_all(c, s->send.p, s->recv.p, sc, rcv, rm))) return rc;
+  if ((rc = ucgb200_migrate_unpack(c, s->recv.p, total(rcv)))) return rc;
+  // ghost shells
+  if ((rc = ucgb200_neigh_build_local(c))) return rc;
+  if ((rc = ucgb200_halo_send_counts(c, sc.data()))) return rc;
+  if ((rc = exchange_counts(c, sc, rcv))) return rc;
+  UCG_CHECK(c, s->send.ensure((size_t)total(sc) * rb + 64));
+  UCG_CHECK(c, s->recv.ensure((size_t)total(rcv) * rb + 64));
+  if ((rc = ucgb200_halo_pack_border(c, s->send.p))) return rc;
+  if ((rc = all_to_all(c, s->send.p, s->recv.p, sc, rcv, rb))) return rc;
+  if ((rc = ucgb200_halo_unpack_border(c, s->recv.p, rcv.data()))) return rc;
+  if ((rc = ucgb200_neigh_build_finish(c))) return rc;
+  s->send_counts = sc;
+  s->recv_counts = rcv;
+  UCG_CHECK(c, s->fwd_send.ensure((size_t)total(sc) * rf + 64));
+  UCG_CHECK(c, s->fwd_recv.ensure((size_t)total(rcv) * rf + 64));
+  s->nrebuilds++;
+  return 0;
+}
+
+// comm->forward_comm(): refresh every ghost (records from other bricks + local periodic images)
+int ucg_mb_forward(ucgb200_ctx *c) {
+  CommState *s = state(c);
+  if (!s) return fail(c, "multi-brick run without ucgb200_comm_init");
+  int rf = 0, rc;
+  ucgb200_halo_record_bytes(nullptr, &rf, nullptr);
+  if ((rc = ucgb200_halo_pack_forward(c, s->fwd_send.p))) return rc;
+  if ((rc = ucgb200_ghosts_forward(c))) return rc;
+  if ((rc = all_to_all(c, s->fwd_send.p, s->fwd_recv.p, s->send_counts, s->recv_counts, rf))) return rc;
+  if ((rc = ucgb200_halo_unpack_forward(c, s->fwd_recv.p))) return rc;
+  s->bytes_forward += (long long)total(s->send_counts) * rf;
+  return 0;
+}
+
+// Neighbor::decide across bricks: MAX of the per-brick flags.  prechecked: k_check_distance already
+// ran (fused step tail) and d_flags[0] holds this brick's flag.
+int ucg_mb_decide(ucgb200_ctx *c, bool prechecked, int *rebuild) {
+  CommState *s = state(c);
+  if (!s) return fail(c, "multi-brick run without ucgb200_comm_init");
+  cudaSetDevice(c->device);
+  if (!prechecked) {
+    UCG_CHECK(c, cudaMemsetAsync(c->d_flags.p, 0, sizeof(int), c->stream));
+    if (!c->list_valid) {
+      const int one = 1;
+      UCG_CHECK(c, cudaMemcpyAsync(c->d_flags.p, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    } else if (c->nlocal > 0) {
+      int rc = ucg_check_distance_launch(c);
+      if (rc) return rc;
+    }
+  }
+  UCG_NCCL(c, nccl().AllReduce(c->d_flags.p, c->d_flags.p, 1, ncclInt32, ncclMax, s->comm, c->stream));
+  UCG_CHECK(c, cudaMemcpyAsync(c->h_flags, c->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  UCG_CHECK(c, cudaStreamSynchronize(c->stream));
+  *rebuild = c->h_flags[0] ? 1 : 0;
+  return 0;
+}
+
+extern "C" int ucgb200_comm_stats(ucgb200_ctx *c, long long *bytes_forward, int *nrebuilds, int *send_records) {
+  if (!c) return -1;
+  CommState *s = state(c);
+  if (!s) return fail(c, "comm not initialised");
+  if (bytes_forward) *bytes_forward = s->bytes_forward;
+  if (nrebuilds) *nrebuilds = s->nrebuilds;
+  if (send_records) *send_records = total(s->send_counts);
+  return 0;
+}

@@ -38,6 +38,7 @@ extern "C" int ucgb200_destroy(ucgb200_ctx *c) {
   if (!c) return -1;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  ucgb200_comm_destroy(c);
   for (void *p : c->table_allocs) cudaFree(p);
   // Buf<> members are released explicitly (no destructors: buffers may be swapped)
   c->d_tables.release(); c->d_pairinfo.release(); c->d_typeinfo.release(); c->d_fast_table.release();

@@ -974,6 +974,13 @@ extern "C" int ucgb200_neigh_decide(ucgb200_ctx *c, int *rebuild) {
   return 0;
 }
 
+int ucg::ucg_check_distance_launch(ucgb200_ctx *c) {
+  const double triggersq = 0.25 * c->skin * c->skin;
+  k_check_distance<<<nblocks(c->nlocal, 256), 256, 0, c->stream>>>(c->pos.p, c->xhold.p, c->nlocal, triggersq, c->d_flags.p);
+  UCG_LAUNCHED(c);
+  return 0;
+}
+
 // Neighbor::decide when k_check_distance already ran inside the fused step tail (fixes.cu): only the
 // 4-byte flag travels
 int ucg_neigh_decide_prechecked(ucgb200_ctx *c, int *rebuild) {

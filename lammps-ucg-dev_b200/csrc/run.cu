@@ -73,6 +73,17 @@ static int pair_compute(ucgb200_ctx *c, int ev) {
 
 int ucg_step_tail(ucgb200_ctx *c, const ucgb200_deck &d, double tsqrt, int fuse_next);
 int ucg_neigh_decide_prechecked(ucgb200_ctx *c, int *rebuild);
+// comm.cu: the same three operations across bricks (NCCL)
+int ucg_mb_rebuild(ucgb200_ctx *c);
+int ucg_mb_forward(ucgb200_ctx *c);
+int ucg_mb_decide(ucgb200_ctx *c, bool prechecked, int *rebuild);
+
+static int do_build(ucgb200_ctx *c) { return c->halo.nranks > 1 ? ucg_mb_rebuild(c) : ucgb200_neigh_build(c); }
+static int do_forward(ucgb200_ctx *c) { return c->halo.nranks > 1 ? ucg_mb_forward(c) : ucgb200_ghosts_forward(c); }
+static int do_decide(ucgb200_ctx *c, bool prechecked, int *flag) {
+  if (c->halo.nranks > 1) return ucg_mb_decide(c, prechecked, flag);
+  return prechecked ? ucg_neigh_decide_prechecked(c, flag) : ucgb200_neigh_decide(c, flag);
+}
 
 struct StageTimer {
   ucgb200_ctx *c;
@@ -125,7 +136,7 @@ extern "C" int ucgb200_setup(ucgb200_ctx *c) {
     c->kT = c->boltz * c->deck.t_start;
   }
   c->beginstep = c->endstep = c->ntimestep;
-  if ((rc = ucgb200_neigh_build(c))) return rc;
+  if ((rc = do_build(c))) return rc;
   c->nbuilds = 0;
   if ((rc = pair_compute(c, 1))) return rc;
   c->lang_g1.clear();
@@ -159,8 +170,7 @@ extern "C" int ucgb200_run(ucgb200_ctx *c, int nsteps) {
     int flag = 0;
     {
       StageTimer t(c, 1);
-      if (pre_integrated) { if ((rc = ucg_neigh_decide_prechecked(c, &flag))) return rc; }
-      else if ((rc = ucgb200_neigh_decide(c, &flag))) return rc;
+      if ((rc = do_decide(c, pre_integrated, &flag))) return rc;
       t.stop();
     }
     // fix cluster_switch: force_reneighbor at next_reneighbor; pre_exchange() rebuilds, labels the
@@ -174,10 +184,10 @@ extern "C" int ucgb200_run(ucgb200_ctx *c, int nsteps) {
       flag = 1;
       t.stop();
     }
-    if (flag) { if ((rc = ucgb200_neigh_build(c))) return rc; }
+    if (flag) { if ((rc = do_build(c))) return rc; }
     else {
       StageTimer t(c, 2);
-      if ((rc = ucgb200_ghosts_forward(c))) return rc;
+      if ((rc = do_forward(c))) return rc;
       t.stop();
     }
     {

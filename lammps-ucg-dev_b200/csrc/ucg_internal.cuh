@@ -230,6 +230,7 @@ struct ucgb200_ctx {
     ucg::Buf<char> d_bt;
     ucg::Buf<double> d_prob, d_partial, d_cvf;
   } bdens;
+  void *comm_state = nullptr;  // comm.cu: NCCL communicator + exchange buffers of a multi-brick run
   bool ev_two_parts = false;   // d_ev[16..22] holds a second virial part to be added (rleucg)
 };
 
@@ -314,5 +315,6 @@ __device__ __forceinline__ double philox_uniform(uint32_t seed, uint32_t purpose
 int rebuild_maps(ucgb200_ctx *c);
 int exclusive_scan(ucgb200_ctx *c, const int *in, int *out, int n, int *d_total);
 int reduce_partials(ucgb200_ctx *c, int nblocks, int nvals, int out_offset);
+int ucg_check_distance_launch(ucgb200_ctx *c);   // neighbor.cu: k_check_distance into d_flags[0]
 
 }  // namespace ucg

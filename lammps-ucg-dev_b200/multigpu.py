@@ -294,13 +294,36 @@ def bench(args, rank, world, local, dist):
                              box=(liq.box_lo, liq.box_hi))
     ctx.halo_configure(rank, world, grid)
     engine.upload_liquid(ctx, liq)
-    tr = DistTransport(dist, device)
-    cl = BrickCluster({rank: ctx}, tr, torch_alloc(device), pkg.Context.halo_record_bytes())
     L = B.LANGEVIN
-    ml = float(liq.ucgml[0])
-    g1 = np.array([0.0, -ml / L["t_period"], -ml / L["t_period"]])
-    g2 = np.array([0.0, 1.0, 1.0]) * np.sqrt(ml) * np.sqrt(24.0 / L["t_period"] / B.DT)
-    deck = dict(dt=B.DT, langevin=1, gfactor1=g1, gfactor2=g2, t_target=L["t_start"], langevin_seed=L["seed"], ucgstate=1)
+    resident = os.environ.get("UCGB200_MB_PYTHON", "0") != "1"
+    if resident:
+        # resident run: NCCL exchanges issued by libucgb200 itself on the context stream (csrc/comm.cu)
+        ids = [pkg.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        # no collective of torch's communicator may be in flight while ncclCommInitRank bootstraps
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        ctx.comm_init(ids[0])
+        ctx.deck_configure(pair_style=0, nve=1, langevin=1, t_start=L["t_start"], t_stop=L["t_stop"], t_period=L["t_period"],
+                           langevin_seed=L["seed"], ucgstate=2, thermo_every=0)
+
+        class _Resident:
+            def __init__(self):
+                self.rec = pkg.Context.halo_record_bytes()
+            def setup(self, deck=None): ctx.setup()
+            def run(self, n): ctx.run(n)
+            @property
+            def nrebuilds(self): return ctx.comm_stats()["rebuilds"]
+            @property
+            def send_counts(self): return {rank: np.array([ctx.comm_stats()["send_records"]])}
+        cl = _Resident()
+        deck = None
+    else:
+        tr = DistTransport(dist, device)
+        cl = BrickCluster({rank: ctx}, tr, torch_alloc(device), pkg.Context.halo_record_bytes())
+        ml = float(liq.ucgml[0])
+        g1 = np.array([0.0, -ml / L["t_period"], -ml / L["t_period"]])
+        g2 = np.array([0.0, 1.0, 1.0]) * np.sqrt(ml) * np.sqrt(24.0 / L["t_period"] / B.DT)
+        deck = dict(dt=B.DT, langevin=1, gfactor1=g1, gfactor2=g2, t_target=L["t_start"], langevin_seed=L["seed"], ucgstate=1)
     cl.setup(deck)
     cl.run(args.warmup)
     torch.cuda.synchronize()
@@ -349,39 +372,40 @@ def bench(args, rank, world, local, dist):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = bps * nloc / (pair_avg * 1e-3) / 1e9
 
-    # e2e: same step with this rank's HOST buffers in and out every step
+    # e2e: same step with this rank's HOST (pinned) buffers in and out every step.  A rebuild may migrate
+    # sites between bricks, so the host arrays carry slack and follow the brick's current population.
     n = nloc
-    cur = ctx.atoms_download(["x", "v", "ucgl", "ucgvl", "ucgstate"])
-    pinned = {k: torch.from_numpy(v.copy()).pin_memory() for k, v in cur.items()}
+    cap = n + n // 8 + 1024
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    H = dict(x=pin((cap, 3), torch.float64), v=pin((cap, 3), torch.float64), f=pin((cap, 3), torch.float64),
+             ucgl=pin((cap,), torch.float64), ucgvl=pin((cap,), torch.float64), ucgstate=pin((cap,), torch.int32),
+             ucgp=pin((cap,), torch.float64), ucgforce=pin((cap,), torch.float64))
+    up = ("x", "v", "ucgl", "ucgvl", "ucgstate")
+    ctx.atoms_download_into(**H)
     e2e_steps = max(3, min(args.steps, 10))
-
-    def e2e_step():
-        ctx.atoms_upload(n, **{k: v.numpy() for k, v in pinned.items()})
-        cl.run(1)
-        if ctx.natoms()[0] != n:      # a rebuild migrated sites: host arrays follow the new brick population
-            return False
-        got = ctx.atoms_download(["x", "v", "f", "ucgl", "ucgvl", "ucgstate", "ucgp", "ucgforce"])
-        for k in pinned:
-            pinned[k].numpy()[:] = got[k]
-        return True
+    h2d_total = d2h_total = 0
 
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
     done = 0
     for _ in range(e2e_steps):
-        ok = e2e_step()
+        n = ctx.natoms()[0]
+        ctx.atoms_upload(n, **{k: H[k][:n] for k in up})
+        cl.run(1)
+        ctx.atoms_download_into(**H)      # the (possibly migrated) population of this brick
+        h2d_total += sum(H[k][:n].nbytes for k in up)
+        d2h_total += sum(v[:ctx.natoms()[0]].nbytes for v in H.values())
         done += 1
-        if not ok:
-            n = ctx.natoms()[0]
-            cur = ctx.atoms_download(["x", "v", "ucgl", "ucgvl", "ucgstate"])
-            pinned = {k: torch.from_numpy(v.copy()).pin_memory() for k, v in cur.items()}
     torch.cuda.synchronize()
     dist.barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
+    tb = torch.tensor([h2d_total / done, d2h_total / done], dtype=torch.float64, device=device)
+    dist.all_reduce(tb)
+    h2d_step, d2h_step = int(tb[0].item()), int(tb[1].item())
 
     if rank == 0:
         cfg = B.workload_config(ncell, world)
@@ -395,12 +419,13 @@ def bench(args, rank, world, local, dist):
                              "traffic": None, "kernel": "k_pair_ucgld_fast", "kernel_ms": pair_avg, "bytes_per_site": bps,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
                 "cpu_baseline": None,
-                "e2e": {"value": nsites * done / e2e_s / 1e6, "unit": B.UNIT, "h2d_bytes_per_step": n * 68 * world,
-                        "d2h_bytes_per_step": n * 108 * world, "steps": done,
-                        "api": "per rank: ucgb200_atoms_upload + one step + ucgb200_atoms_download"},
+                "e2e": {"value": nsites * done / e2e_s / 1e6, "unit": B.UNIT, "h2d_bytes_per_step": h2d_step,
+                        "d2h_bytes_per_step": d2h_step, "steps": done,
+                        "api": "per rank: ucgb200_atoms_upload + ucgb200_run(1) + ucgb200_atoms_download, pinned host arrays"},
                 "gpu_launches": int(launches), "clocks": sampler.summary(),
                 "halo": {"forward_bytes_per_step_rank0": int(cl.send_counts[rank].sum()) * cl.rec["forward"],
-                         "rebuilds": cl.nrebuilds, "transport": "NCCL all_to_all_single over NVLink"}}
+                         "rebuilds": cl.nrebuilds, "transport": "NCCL send/recv groups issued by libucgb200 on the context stream (resident run)" if resident
+                         else "NCCL all_to_all_single driven from Python"}}
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()
