@@ -25,6 +25,8 @@
 // every visit — energies and forces are unaffected.
 #include "pair_common.cuh"
 
+#include <algorithm>
+
 using namespace ucg;
 
 namespace {
@@ -51,6 +53,7 @@ struct BetheArgs {
   double2 *scores;
   double *partials;
   ErrWord *err;
+  FastTable ft;   // shared-memory table path (W > 0)
 };
 
 // prior probability of substate 1 of site k
@@ -69,12 +72,19 @@ __device__ __forceinline__ double prior1(const BetheArgs &p, const TypeInfo &ty,
   return ucgl;
 }
 
-template <int LPA, bool EV, int BS>
+// W = 0: tables through L1 (any type system / table style); W = 3 / 4: interleaved LINEAR tables of the
+// single 2-state type in shared memory, persistent CTAs (one per SM)
+template <int LPA, bool EV, int BS, int W>
 __global__ void __launch_bounds__(BS) k_pair_bethe(BetheArgs p) {
-  const int gid = (blockIdx.x * BS + threadIdx.x) / LPA;
+  extern __shared__ double2 s_tab[];
+  if (W) fast_table_stage<W, BS>(s_tab, p.ft);
   const int sub = threadIdx.x % LPA;
+  constexpr int GROUPS = BS / LPA;
+  double evacc[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int base = blockIdx.x * GROUPS; base < p.nlocal; base += gridDim.x * GROUPS) {
+  const int gid = base + threadIdx.x / LPA;
   const bool active = gid < p.nlocal;
-  const int i = active ? gid : 0;
+  const int i = active ? gid : p.nlocal - 1;
   const double4 ri = p.pos[i];
   const int tsi = p.ts[i];
   const int ti = tsi & 0xffff;
@@ -103,11 +113,13 @@ __global__ void __launch_bounds__(BS) k_pair_bethe(BetheArgs p) {
       const int nj = pi.nj;
       double u[4] = {0, 0, 0, 0}, f[4] = {0, 0, 0, 0};
       int ec = 0;
-      for (int a = 0; a < ni; a++)
-        for (int b = 0; b < nj; b++) {
-          int e1 = table_eval(p.tables[pi.tab[a * 2 + b]], rsq, u[a * 2 + b], f[a * 2 + b]);
-          if (e1 && !ec) ec = e1;
-        }
+      if (W) ec = fast_table_eval<W>(s_tab, p.ft, rsq, u, f);
+      else
+        for (int a = 0; a < ni; a++)
+          for (int b = 0; b < nj; b++) {
+            int e1 = table_eval(p.tables[pi.tab[a * 2 + b]], rsq, u[a * 2 + b], f[a * 2 + b]);
+            if (e1 && !ec) ec = e1;
+          }
       if (ec) {
         report_error(p.err, ec, p.tag[i], p.tag[j], rsq);
         continue;
@@ -167,23 +179,23 @@ __global__ void __launch_bounds__(BS) k_pair_bethe(BetheArgs p) {
   fx = group_sum<LPA>(fx); fy = group_sum<LPA>(fy); fz = group_sum<LPA>(fz);
   eacc = group_sum<LPA>(eacc);
   S0 = group_sum<LPA>(S0); S1 = group_sum<LPA>(S1);
-  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
   if (active && sub == 0) {
     p.frc[i] = make_double4(fx, fy, fz, 0.0);   // the Bethe style leaves ucgforce at its cleared value
     if (ni == 2)  // :162-170 initialise with -mu/kT, then the pair tallies
       p.scores[i] = make_double2(-tyi.mu0 * p.inv_kT - S0 * p.inv_kT, -tyi.mu1 * p.inv_kT - S1 * p.inv_kT);
     else
       p.scores[i] = make_double2(-tyi.mu0 * p.inv_kT, 0.0);
-    if (EV) ev[0] = 0.5 * eacc;
+    if (EV) evacc[0] += 0.5 * eacc;
   }
   if (EV) {
 #pragma unroll
     for (int k = 0; k < 6; k++) {
       double v = group_sum<LPA>(vir[k]);
-      if (active && sub == 0) ev[1 + k] = 0.5 * v;
+      if (active && sub == 0) evacc[1 + k] += 0.5 * v;
     }
-    block_reduce_store<7, BS>(ev, p.partials);
   }
+  }   // persistent loop over site groups
+  if (EV) block_reduce_store<7, BS>(evacc, p.partials);
 }
 
 }  // namespace
@@ -210,12 +222,34 @@ extern "C" int ucgb200_pair_bethe(ucgb200_ctx *c, int eflag, int vflag, int meth
   a.kT = c->kT; a.inv_kT = 1.0 / c->kT;
   a.method = method; a.pseudo = pseudo; a.prior = prior; a.noise = noise_level; a.seed = (unsigned)seed;
   a.frc = c->frc.p; a.scores = c->scores.p; a.err = c->d_err.p;
-  const int nblk = nblocks((long long)c->nlocal * LPA, BS);
+  int nblk = nblocks((long long)c->nlocal * LPA, BS);
+  const size_t tab_bytes = (size_t)c->fast_len * c->fast_ntab * sizeof(double2);
+  const bool fast = c->fast_uniform && tab_bytes <= 220 * 1024 &&
+                    !(getenv("UCGB200_FORCE_GENERAL") && atoi(getenv("UCGB200_FORCE_GENERAL")));
+  constexpr int FLPA = 4, FBS = 512;
+  if (fast) {
+    const ucg::TableDev &t0 = c->tables[c->fast_tab[0]];
+    a.ft.table = c->d_fast_table.p; a.ft.tablen = c->fast_len; a.ft.W = c->fast_ntab;
+    a.ft.innersq = t0.innersq; a.ft.delta = t0.delta; a.ft.invdelta = t0.invdelta;
+    int dev_sms = 148;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c->device);
+    nblk = std::min(dev_sms, nblocks((long long)c->nlocal * FLPA, FBS));
+  }
   if (ev) UCG_CHECK(c, c->d_partials.ensure((size_t)nblk * 8 + 64));
   a.partials = c->d_partials.p;
   if (c->timers_on) cudaEventRecord(c->ev_pair0, c->stream);
-  if (ev) k_pair_bethe<LPA, true, BS><<<nblk, BS, 0, c->stream>>>(a);
-  else k_pair_bethe<LPA, false, BS><<<nblk, BS, 0, c->stream>>>(a);
+  if (fast) {
+#define UCG_BETHE_FAST(EVV, WW)                                                                              \
+    do {                                                                                                    \
+      auto kern = k_pair_bethe<FLPA, EVV, FBS, WW>;                                                         \
+      UCG_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes)); \
+      kern<<<nblk, FBS, tab_bytes, c->stream>>>(a);                                                         \
+    } while (0)
+    if (c->fast_ntab == 3) { if (ev) UCG_BETHE_FAST(true, 3); else UCG_BETHE_FAST(false, 3); }
+    else { if (ev) UCG_BETHE_FAST(true, 4); else UCG_BETHE_FAST(false, 4); }
+#undef UCG_BETHE_FAST
+  } else if (ev) k_pair_bethe<LPA, true, BS, 0><<<nblk, BS, 0, c->stream>>>(a);
+  else k_pair_bethe<LPA, false, BS, 0><<<nblk, BS, 0, c->stream>>>(a);
   UCG_LAUNCHED(c);
   if (c->timers_on) { cudaEventRecord(c->ev_pair1, c->stream); c->pair_timed = true; }
   if (ev) {

@@ -23,6 +23,7 @@
 // the virial (:622-625 with ev_tally newton off), i.e. each pair once in total.
 #include "pair_common.cuh"
 
+#include <algorithm>
 #include <cmath>
 
 using namespace ucg;
@@ -55,6 +56,7 @@ struct BdArgs {
   double *ucgp;
   double *partials;
   ErrWord *err;
+  FastTable ft;   // shared-memory table path (W > 0)
 };
 
 __device__ __forceinline__ double bd_prox(double r, double rth) {
@@ -108,12 +110,19 @@ __global__ void k_bd_ghost(double *__restrict__ a, int nlocal, int nlimg, const 
   a[nlocal + slot_of_src[k]] = a[owner[k]];
 }
 
-template <int LPA, int BS>
+// W = 0: tables through L1 (any type system, any table style); W = 3 / 4: the interleaved LINEAR tables
+// of the single 2-state type staged in shared memory, persistent CTAs (one per SM)
+template <int LPA, int BS, int W>
 __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
-  const int gid = (blockIdx.x * BS + threadIdx.x) / LPA;
+  extern __shared__ double2 s_tab[];
+  if (W) fast_table_stage<W, BS>(s_tab, p.ft);
   const int sub = threadIdx.x % LPA;
+  constexpr int GROUPS = BS / LPA;
+  double evacc[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int base = blockIdx.x * GROUPS; base < p.nlocal; base += gridDim.x * GROUPS) {
+  const int gid = base + threadIdx.x / LPA;
   const bool active = gid < p.nlocal;
-  const int i = active ? gid : 0;
+  const int i = active ? gid : p.nlocal - 1;
   const double4 ri = p.pos[i];
   const int ti = p.ts[i] & 0xffff;
   const TypeInfo tyi = p.tinfo[ti];
@@ -143,11 +152,13 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
       const bool jlocal = j < p.nlocal;
       double u[4] = {0, 0, 0, 0}, f[4] = {0, 0, 0, 0};
       int ec = 0;
-      for (int a = 0; a < ni; a++)
-        for (int b = 0; b < nj; b++) {
-          int e1 = table_eval(p.tables[pi.tab[a * 2 + b]], rsq, u[a * 2 + b], f[a * 2 + b]);
-          if (e1 && !ec) ec = e1;
-        }
+      if (W) ec = fast_table_eval<W>(s_tab, p.ft, rsq, u, f);
+      else
+        for (int a = 0; a < ni; a++)
+          for (int b = 0; b < nj; b++) {
+            int e1 = table_eval(p.tables[pi.tab[a * 2 + b]], rsq, u[a * 2 + b], f[a * 2 + b]);
+            if (e1 && !ec) ec = e1;
+          }
       if (ec) {
         report_error(p.err, ec, p.tag[i], p.tag[j], rsq);
         continue;
@@ -210,11 +221,10 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
   eacc = group_sum<LPA>(eacc);
   S0 = group_sum<LPA>(S0); S1 = group_sum<LPA>(S1);
   pf0 = group_sum<LPA>(pf0); pf1 = group_sum<LPA>(pf1);
-  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
   for (int k = 0; k < 6; k++) {
     const double v = group_sum<LPA>(vir[k]);
-    if (active && sub == 0) ev[1 + k] = v;
+    if (active && sub == 0) evacc[1 + k] += v;
   }
   if (active && sub == 0) {
     double s0 = -S0 * p.inv_kT, s1 = -S1 * p.inv_kT, cvf = 0.0;
@@ -236,9 +246,10 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
     // publishes only ucgp — atom->ucgsoftmaxscores stay at their cleared value
     p.ucgp[i] = ni > 1 ? exp(s1) / (exp(s0) + exp(s1)) : 1.0;
     p.scores[i] = make_double2(0.0, 0.0);
-    ev[0] = eacc;
+    evacc[0] += eacc;
   }
-  block_reduce_store<7, BS>(ev, p.partials);
+  }   // persistent loop over site groups
+  block_reduce_store<7, BS>(evacc, p.partials);
 }
 
 template <int LPA, int BS>
@@ -362,9 +373,33 @@ extern "C" int ucgb200_pair_bethe_density(ucgb200_ctx *c, int eflag, int vflag) 
     k_bd_ghost<<<nblocks(h.nlimg, 256), 256, 0, c->stream>>>(a.prob0, c->nlocal, h.nlimg, c->img_owner.p + h.nsend, c->slot_of_src.p);
     UCG_LAUNCHED(c);
   }
-  k_bd_pair<LPA, BS><<<nblk, BS, 0, c->stream>>>(a);
+  int nblk_pair = nblk;
+  const size_t tab_bytes = (size_t)c->fast_len * c->fast_ntab * sizeof(double2);
+  if (c->fast_uniform && tab_bytes <= 220 * 1024 && !(getenv("UCGB200_FORCE_GENERAL") && atoi(getenv("UCGB200_FORCE_GENERAL")))) {
+    // one 2-state type, LINEAR tables on one grid: interleaved rows in shared memory, persistent CTAs
+    constexpr int FLPA = 4, FBS = 512;
+    const ucg::TableDev &t0 = c->tables[c->fast_tab[0]];
+    a.ft.table = c->d_fast_table.p; a.ft.tablen = c->fast_len; a.ft.W = c->fast_ntab;
+    a.ft.innersq = t0.innersq; a.ft.delta = t0.delta; a.ft.invdelta = t0.invdelta;
+    int dev_sms = 148;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c->device);
+    nblk_pair = std::min(dev_sms, nblocks((long long)c->nlocal * FLPA, FBS));
+    UCG_CHECK(c, c->d_partials.ensure((size_t)std::max(nblk, nblk_pair) * 8 + 64));
+    a.partials = c->d_partials.p;
+    if (c->fast_ntab == 3) {
+      auto kern = k_bd_pair<FLPA, FBS, 3>;
+      UCG_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+      kern<<<nblk_pair, FBS, tab_bytes, c->stream>>>(a);
+    } else {
+      auto kern = k_bd_pair<FLPA, FBS, 4>;
+      UCG_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+      kern<<<nblk_pair, FBS, tab_bytes, c->stream>>>(a);
+    }
+  } else {
+    k_bd_pair<LPA, BS, 0><<<nblk, BS, 0, c->stream>>>(a);
+  }
   UCG_LAUNCHED(c);
-  if ((rc = reduce_partials(c, nblk, 7, 0))) return rc;
+  if ((rc = reduce_partials(c, nblk_pair, 7, 0))) return rc;
   k_bd_back<LPA, BS><<<nblk, BS, 0, c->stream>>>(a);
   UCG_LAUNCHED(c);
   if ((rc = reduce_partials(c, nblk, 7, 16))) return rc;   // second virial part -> d_ev[16..22]

@@ -57,6 +57,41 @@ __device__ __forceinline__ int table_eval(const TableDev &tb, double rsq, double
   return 0;
 }
 
+// ---- shared-memory table path (one 2-state actual type, LINEAR tables on one rsq grid; the layout
+// built by rebuild_maps for pair_ucgld.cu): row it = {e00,f00, e01,f01, [e10,f10,] e11,f11}.
+struct FastTable {
+  const double2 *table;   // [tablen][W]
+  int tablen, W;
+  double innersq, delta, invdelta;
+};
+template <int W, int BS>
+__device__ __forceinline__ void fast_table_stage(double2 *s_tab, const FastTable &ft) {
+  const int nwords = ft.tablen * W;
+  for (int k = threadIdx.x; k < nwords; k += BS) s_tab[k] = ft.table[k];
+  __syncthreads();
+}
+// the four potentials u[a*2+b], f[a*2+b] at rsq; same index / fraction arithmetic as table_eval
+template <int W>
+__device__ __forceinline__ int fast_table_eval(const double2 *s_tab, const FastTable &ft, double rsq, double (&u)[4],
+                                               double (&f)[4]) {
+  if (rsq < ft.innersq) return UCGB200_ERR_TABLE_INNER;
+  const int it = (int)__dmul_rn(__dadd_rn(rsq, -ft.innersq), ft.invdelta);
+  if (it >= ft.tablen - 1) return UCGB200_ERR_TABLE_OUTER;
+  const double rsq_it = __dadd_rn(ft.innersq, __dmul_rn((double)it, ft.delta));
+  const double frac = (rsq - rsq_it) * ft.invdelta;
+  const double2 *r0 = s_tab + it * W;
+  const double2 a00 = r0[0], a01 = r0[1], a11 = r0[W - 1];
+  const double2 b00 = r0[W], b01 = r0[W + 1], b11 = r0[2 * W - 1];
+  u[0] = a00.x + frac * (b00.x - a00.x); f[0] = a00.y + frac * (b00.y - a00.y);
+  u[1] = a01.x + frac * (b01.x - a01.x); f[1] = a01.y + frac * (b01.y - a01.y);
+  u[3] = a11.x + frac * (b11.x - a11.x); f[3] = a11.y + frac * (b11.y - a11.y);
+  if (W == 4) {
+    const double2 a10 = r0[2], b10 = r0[W + 2];
+    u[2] = a10.x + frac * (b10.x - a10.x); f[2] = a10.y + frac * (b10.y - a10.y);
+  } else { u[2] = u[1]; f[2] = f[1]; }
+  return 0;
+}
+
 // sum `v` over the LPA lanes of a sub-warp group (result valid in every lane)
 template <int LPA>
 __device__ __forceinline__ double group_sum(double v) {
