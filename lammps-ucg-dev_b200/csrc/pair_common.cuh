@@ -92,6 +92,22 @@ __device__ __forceinline__ int fast_table_eval(const double2 *s_tab, const FastT
   return 0;
 }
 
+// generic use of the same layout (any type system whose <= 4 uploaded tables are LINEAR on one grid;
+// slot k of a row = table k): index / fraction once per pair, then one slot per (state, state) table
+__device__ __forceinline__ int fast_table_index(const FastTable &ft, double rsq, int &it, double &frac) {
+  if (rsq < ft.innersq) return UCGB200_ERR_TABLE_INNER;
+  it = (int)__dmul_rn(__dadd_rn(rsq, -ft.innersq), ft.invdelta);
+  if (it >= ft.tablen - 1) return UCGB200_ERR_TABLE_OUTER;
+  const double rsq_it = __dadd_rn(ft.innersq, __dmul_rn((double)it, ft.delta));
+  frac = (rsq - rsq_it) * ft.invdelta;
+  return 0;
+}
+__device__ __forceinline__ void fast_table_slot(const double2 *s_tab, int W, int it, double frac, int slot, double &e, double &f) {
+  const double2 a = s_tab[it * W + slot], b = s_tab[(it + 1) * W + slot];
+  e = a.x + frac * (b.x - a.x);
+  f = a.y + frac * (b.y - a.y);
+}
+
 // sum `v` over the LPA lanes of a sub-warp group (result valid in every lane)
 template <int LPA>
 __device__ __forceinline__ double group_sum(double v) {

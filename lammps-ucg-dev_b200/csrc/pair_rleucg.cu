@@ -55,6 +55,7 @@ struct RleArgs {
   double4 *frc;
   double *partials;
   ErrWord *err;
+  FastTable ft;   // shared-memory table path (SM = true): slot k of a row = table k
 };
 
 __device__ __forceinline__ double prox(double r, double rth) {
@@ -99,12 +100,24 @@ __global__ void __launch_bounds__(BS) k_rle_density(RleArgs p) {
   }
 }
 
-template <int LPA, int BS>
+// SM = true: every uploaded table is LINEAR on one rsq grid and there are at most 4 of them — their rows
+// are interleaved in shared memory (slot = table index) and the CTAs are persistent; otherwise tables
+// come through L1.
+template <int LPA, int BS, bool SM>
 __global__ void __launch_bounds__(BS) k_rle_pair(RleArgs p) {
-  const int gid = (blockIdx.x * BS + threadIdx.x) / LPA;
+  extern __shared__ double2 s_tab[];
+  if (SM) {
+    const int nwords = p.ft.tablen * p.ft.W;
+    for (int k = threadIdx.x; k < nwords; k += BS) s_tab[k] = p.ft.table[k];
+    __syncthreads();
+  }
   const int sub = threadIdx.x % LPA;
+  constexpr int GROUPS = BS / LPA;
+  double evacc[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int base = blockIdx.x * GROUPS; base < p.nlocal; base += gridDim.x * GROUPS) {
+  const int gid = base + threadIdx.x / LPA;
   const bool active = gid < p.nlocal;
-  const int i = active ? gid : 0;
+  const int i = active ? gid : p.nlocal - 1;
   const double4 ri = p.pos[i];
   const int ti = p.ts[i] & 0xffff;
   const RleType rti = p.rt[ti];
@@ -129,13 +142,23 @@ __global__ void __launch_bounds__(BS) k_rle_pair(RleArgs p) {
       const bool jlocal = j < p.nlocal;
       double elj = 0.0, pfv = 0.0;
       bool bad = false;
+      int it = 0;
+      double frac = 0.0;
+      if (SM) {
+        const int ec = fast_table_index(p.ft, rsq, it, frac);
+        if (ec) { report_error(p.err, ec, p.tag[i], p.tag[j], rsq); bad = true; }
+      }
       for (int a = 0; a < ni && !bad; a++) {
         const double pa = ni > 1 ? (a == 0 ? pi0 : 1.0 - pi0) : 1.0;
         for (int b = 0; b < nj; b++) {
           const double pb = nj > 1 ? (b == 0 ? pj0 : 1.0 - pj0) : 1.0;
           double e, f;
-          const int ec = table_eval(p.tables[p.tabindex[(ti + a) * p.nt + (tj + b)]], rsq, e, f);
-          if (ec) { report_error(p.err, ec, p.tag[i], p.tag[j], rsq); bad = true; break; }
+          const int tix = p.tabindex[(ti + a) * p.nt + (tj + b)];
+          if (SM) fast_table_slot(s_tab, p.ft.W, it, frac, tix, e, f);
+          else {
+            const int ec = table_eval(p.tables[tix], rsq, e, f);
+            if (ec) { report_error(p.err, ec, p.tag[i], p.tag[j], rsq); bad = true; break; }
+          }
           e *= factor_lj;
           const double fp = factor_lj * f * pa * pb;
           fx += dx * fp; fy += dy * fp; fz += dz * fp;
@@ -155,11 +178,10 @@ __global__ void __launch_bounds__(BS) k_rle_pair(RleArgs p) {
   fx = group_sum<LPA>(fx); fy = group_sum<LPA>(fy); fz = group_sum<LPA>(fz);
   pf = group_sum<LPA>(pf);
   eacc = group_sum<LPA>(eacc);
-  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
   for (int k = 0; k < 6; k++) {
     const double v = group_sum<LPA>(vir[k]);
-    if (active && sub == 0) ev[1 + k] = v;
+    if (active && sub == 0) evacc[1 + k] += v;
   }
   if (active && sub == 0) {
     double cvf = 0.0;
@@ -172,9 +194,10 @@ __global__ void __launch_bounds__(BS) k_rle_pair(RleArgs p) {
     }
     p.cvf[i] = cvf;
     p.frc[i] = make_double4(fx, fy, fz, 0.0);
-    ev[0] = eacc;
+    evacc[0] += eacc;
   }
-  block_reduce_store<7, BS>(ev, p.partials);
+  }   // persistent loop over site groups
+  block_reduce_store<7, BS>(evacc, p.partials);
 }
 
 template <int LPA, int BS>
@@ -315,6 +338,28 @@ int ucg_rebuild_rle_maps(ucgb200_ctx *c) {
   UCG_CHECK(c, cudaMemcpy(d.d_tabindex.p, d.tabindex.data(), nt * nt * sizeof(int), cudaMemcpyHostToDevice));
   c->n_actual = d.n_types;   // the neighbor build indexes PairInfo by (state) type
   c->fast_uniform = false;
+  // shared-memory table path: all tables LINEAR on one grid, at most 4 of them
+  d.sm_tables = false;
+  if (ntab >= 1 && ntab <= 4) {
+    const TableDev &t0 = c->tables[0];
+    bool ok = t0.style == UCGB200_TAB_LINEAR && (size_t)t0.n * ntab * sizeof(double2) <= 220 * 1024;
+    for (int k = 1; k < ntab && ok; k++) {
+      const TableDev &t = c->tables[k];
+      ok = t.style == UCGB200_TAB_LINEAR && t.n == t0.n && t.innersq == t0.innersq && t.delta == t0.delta && t.invdelta == t0.invdelta;
+    }
+    if (ok) {
+      const int n = t0.n;
+      std::vector<double2> rows((size_t)n * ntab), tmp(n);
+      for (int k = 0; k < ntab; k++) {
+        UCG_CHECK(c, cudaMemcpy(tmp.data(), c->tables[k].ef, n * sizeof(double2), cudaMemcpyDeviceToHost));
+        for (int r = 0; r < n; r++) rows[(size_t)r * ntab + k] = tmp[r];
+      }
+      UCG_CHECK(c, c->d_fast_table.ensure(rows.size()));
+      UCG_CHECK(c, cudaMemcpy(c->d_fast_table.p, rows.data(), rows.size() * sizeof(double2), cudaMemcpyHostToDevice));
+      c->fast_ntab = ntab; c->fast_len = n;
+      d.sm_tables = true;
+    }
+  }
   c->maps_dirty = false;
   c->list_valid = false;
   return 0;
@@ -357,9 +402,26 @@ extern "C" int ucgb200_pair_rleucg(ucgb200_ctx *c, int eflag, int vflag) {
     k_ghost_scalar<<<nblocks(h.nlimg, 256), 256, 0, c->stream>>>(a.prob, a.partial, c->nlocal, h.nlimg, lown, c->slot_of_src.p);
     UCG_LAUNCHED(c);
   }
-  k_rle_pair<LPA, BS><<<nblk, BS, 0, c->stream>>>(a);
+  int nblk_pair = nblk;
+  if (d.sm_tables && !(getenv("UCGB200_FORCE_GENERAL") && atoi(getenv("UCGB200_FORCE_GENERAL")))) {
+    constexpr int FLPA = 4, FBS = 512;
+    const TableDev &t0 = c->tables[0];
+    a.ft.table = c->d_fast_table.p; a.ft.tablen = c->fast_len; a.ft.W = c->fast_ntab;
+    a.ft.innersq = t0.innersq; a.ft.delta = t0.delta; a.ft.invdelta = t0.invdelta;
+    const size_t tab_bytes = (size_t)c->fast_len * c->fast_ntab * sizeof(double2);
+    int dev_sms = 148;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c->device);
+    nblk_pair = std::min(dev_sms, nblocks((long long)c->nlocal * FLPA, FBS));
+    UCG_CHECK(c, c->d_partials.ensure((size_t)std::max(nblk, nblk_pair) * 8 + 64));
+    a.partials = c->d_partials.p;
+    auto kern = k_rle_pair<FLPA, FBS, true>;
+    UCG_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+    kern<<<nblk_pair, FBS, tab_bytes, c->stream>>>(a);
+  } else {
+    k_rle_pair<LPA, BS, false><<<nblk, BS, 0, c->stream>>>(a);
+  }
   UCG_LAUNCHED(c);
-  if ((rc = reduce_partials(c, nblk, 7, 0))) return rc;
+  if ((rc = reduce_partials(c, nblk_pair, 7, 0))) return rc;
   if (h.nlimg) {
     k_ghost_scalar<<<nblocks(h.nlimg, 256), 256, 0, c->stream>>>(a.cvf, nullptr, c->nlocal, h.nlimg, lown, c->slot_of_src.p);
     UCG_LAUNCHED(c);

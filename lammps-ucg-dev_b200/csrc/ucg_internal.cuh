@@ -211,7 +211,7 @@ struct ucgb200_ctx {
 
   // rleucg / bethe_density configuration (types are STATE types in these styles)
   struct Density {
-    bool set = false;
+    bool set = false, sm_tables = false;
     int n_types = 0, n_actual = 0;
     std::vector<int> actual_from_state, n_states_of_type, use_entropy, tabindex;
     std::vector<double> threshold_radius, density_threshold, chem_pot, cutsq, mass;

@@ -48,6 +48,7 @@ FixClusterSwitch::FixClusterSwitch(LAMMPS *lmp, int narg, char **arg)
   // the constructor scan over the atoms (maxmol, nSwitchPerMol, mol_state, mol_restrict) runs on the device
   dev = UCGDevice::get(lmp);
   dev->sync_globals(lmp);
+  dev->static_uploaded = false;   // types / molecule ids / masks as they are NOW (the scan below reads them)
   dev->upload(lmp, 0);
   int rc = ucgb200_cluster_configure(dev->ctx, mol_seed, mol_offset, cutoff, seed, probON, nSwitchTypes, atomtypesON.data(),
                                      atomtypesOFF.data(), (int) contactPairs.size() / 2, contactPairs.data(), atom->ntypes,

@@ -78,6 +78,8 @@ void PairTable_RLEUCG_INTERFACE::settings(int narg, char **arg) {
   allocated = 0;
   configured = false;
   dev = UCGDevice::get(lmp);
+  dev->static_uploaded = false;   // a new pair_style: every per-site array is sent again
+  dev->list_ready = false;
   dev->check(lmp, ucgb200_tables_clear(dev->ctx), "tables_clear");
 }
 

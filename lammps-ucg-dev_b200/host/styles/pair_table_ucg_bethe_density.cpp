@@ -116,6 +116,8 @@ void PairTable_UCG_Bethe_Density::settings(int narg, char **arg) {
   maps_applied = false;
   density_applied = false;
   dev = UCGDevice::get(lmp);
+  dev->static_uploaded = false;   // a new pair_style: every per-site array is sent again
+  dev->list_ready = false;
   dev->check(lmp, ucgb200_tables_clear(dev->ctx), "tables_clear");
 }
 

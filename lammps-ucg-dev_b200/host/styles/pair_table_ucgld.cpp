@@ -82,6 +82,8 @@ void PairTable_UCGLD::settings(int narg, char **arg) {
   allocated = 0;
   maps_applied = false;
   dev = UCGDevice::get(lmp);
+  dev->static_uploaded = false;   // a new pair_style: every per-site array is sent again
+  dev->list_ready = false;
   dev->check(lmp, ucgb200_tables_clear(dev->ctx), "tables_clear");
 }
 
