@@ -40,8 +40,9 @@ LANGEVIN = dict(t_start=1.0, t_stop=1.0, t_period=1.0, seed=48291)
 
 
 def workload_config(ncell, nranks):
-    return {"workload": "1M-site UCG-LD liquid, table_ucgld LINEAR 4096, fix nve/ucgld + ucgld/langevin + ucgstate ld",
-            "sites": int(4 * np.prod(ncell)) if not np.isscalar(ncell) else int(4 * ncell ** 3),
+    sites = int(4 * np.prod(ncell)) if not np.isscalar(ncell) else int(4 * ncell ** 3)
+    return {"workload": f"{sites / 1e6:.0f}M-site UCG-LD liquid, table_ucgld LINEAR 4096, fix nve/ucgld + ucgld/langevin + ucgstate ld",
+            "sites": sites,
             "ncell": list(ncell) if not np.isscalar(ncell) else [ncell] * 3,
             "tablength": TABLENGTH, "cut": CUT, "skin": SKIN, "dt": DT,
             "decomposition": "1 brick" if nranks == 1 else f"{nranks} bricks, halo over NCCL",
@@ -198,7 +199,10 @@ def run_gpu(args):
 
     td = tempfile.mkdtemp()
     tf, sf = make_fixtures(td)
-    liq = synth.fcc_liquid(NCELL_1GPU)
+    # UCGB200_NCELL_PER_GPU: non-default problem size (e.g. 100 -> 4M sites per GPU, the per-GPU share of
+    # BASELINE.json configs[4]); the default is the 1M-site configs[1]
+    ncell1 = int(os.environ.get("UCGB200_NCELL_PER_GPU", NCELL_1GPU))
+    liq = synth.fcc_liquid(ncell1)
     stream = torch.cuda.Stream()          # a real (non-default) stream: CUDA events on it bracket every kernel
     torch.cuda.set_stream(stream)
     ctx = pkg.Context(local, stream=stream.cuda_stream)
@@ -298,7 +302,7 @@ def run_gpu(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(NCELL_1GPU, 1),
+            "dtype": "f64", "data": "synthetic", "config": workload_config(ncell1, 1),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "thermo": {"lambda_temp": th[9], "rebuilds_total": int(th[11]), "nghost": int(th[13])}}

@@ -409,7 +409,6 @@ def bench(args, rank, world, local, dist):
 
     if rank == 0:
         cfg = B.workload_config(ncell, world)
-        cfg["workload"] = cfg["workload"].replace("1M-site", f"{nsites / 1e6:.0f}M-site")
         cfg["sites_per_gpu"] = nsites // world
         cfg["procgrid"] = list(grid)
         line = {"metric": B.METRIC, "value": nsites * args.steps / (ms * 1e-3) / 1e6, "unit": B.UNIT, "n_gpus": world,
