@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(BS) k_cs_edges(const double4 *__restrict__ pos
   const int jnum = numneigh[i];
   const int *row = neigh + (size_t)i * stride;
   for (int jj = sub; jj < jnum; jj += LPA) {
-    const int j = row[jj] & UCG_NEIGHMASK;
+    const int j = row[rowslot(jj)] & UCG_NEIGHMASK;
     const int mj = mol[j];
     if (mj == mi) continue;
     const int mk = j < nlocal ? mask[j] : gmask[j - nlocal];

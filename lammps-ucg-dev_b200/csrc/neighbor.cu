@@ -493,7 +493,7 @@ k_build_rows(const double4 *__restrict__ pos, const int *__restrict__ ts, int nl
           unsigned m_out = __ballot_sync(0xffffffffu, hit && !inner);
           if (inner) {
             int p = cnt_in + __popc(m_in & lt);
-            if (p < stride) row[p] = j;
+            if (p < stride) row[rowslot(p)] = j;
           } else if (hit) {
             int p = cnt_out + __popc(m_out & lt);
             if (p < stride) outer[p] = j;
@@ -506,7 +506,7 @@ k_build_rows(const double4 *__restrict__ pos, const int *__restrict__ ts, int nl
   __syncwarp();
   const int total = cnt_in + cnt_out;
   if (total <= stride)
-    for (int k = lane; k < cnt_out; k += 32) row[cnt_in + k] = outer[k];
+    for (int k = lane; k < cnt_out; k += 32) row[rowslot(cnt_in + k)] = outer[k];
   if (lane == 0) {
     numneigh[i] = min(total, stride);
     if (total > stride) atomicMax(&flags[1], total);
@@ -592,7 +592,7 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
       if (!single && cbase > 0) {   // resume: counts parked in the row tail / numneigh
         cnt_in = numneigh[i] & 0xffff;
         cnt_out = numneigh[i] >> 16;
-        for (int k = lane; k < min(cnt_out, stride); k += 32) outer[k] = row[stride - 1 - k];
+        for (int k = lane; k < min(cnt_out, stride); k += 32) outer[k] = row[rowslot(stride - 1 - k)];
         __syncwarp();
       }
       for (int base = 0; base < cn; base += 32) {
@@ -612,7 +612,7 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
         const unsigned m_out = __ballot_sync(0xffffffffu, hit && !inner);
         if (inner) {
           const int p = cnt_in + __popc(m_in & lt);
-          if (p < stride) row[p] = j;
+          if (p < stride) row[rowslot(p)] = j;
         } else if (hit) {
           const int p = cnt_out + __popc(m_out & lt);
           if (p < stride) outer[p] = j;
@@ -625,7 +625,7 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
       const int total = cnt_in + cnt_out;
       if (last) {
         if (total <= stride)
-          for (int k = lane; k < cnt_out; k += 32) row[cnt_in + k] = outer[k];
+          for (int k = lane; k < cnt_out; k += 32) row[rowslot(cnt_in + k)] = outer[k];
         if (lane == 0) {
           numneigh[i] = min(total, stride);
           if (total > stride) atomicMax(&flags[1], total);
@@ -634,7 +634,7 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
         // park the skin entries at the row's tail (reversed) until the next chunk; if the row is about
         // to overflow the final count reports it and the build is redone with a larger stride
         if (total <= stride)
-          for (int k = lane; k < cnt_out; k += 32) row[stride - 1 - k] = outer[k];
+          for (int k = lane; k < cnt_out; k += 32) row[rowslot(stride - 1 - k)] = outer[k];
         if (lane == 0) numneigh[i] = (min(cnt_in, 0xffff)) | (min(cnt_out, 0x7fff) << 16);
       }
       __syncwarp();
@@ -766,7 +766,7 @@ static int build_rows(ucgb200_ctx *c) {
     if (rc) return rc;
     if (c->h_flags[1] <= c->neigh_stride) break;
     // UCGB200_ERR_NEIGH_OVERFLOW handled internally: grow the row capacity and redo
-    c->neigh_stride = ((c->h_flags[1] + c->h_flags[1] / 8 + 7) / 8) * 8;
+    c->neigh_stride = ((c->h_flags[1] + c->h_flags[1] / 8 + 15) / 16) * 16;
   }
   return 0;
 }
@@ -934,7 +934,7 @@ extern "C" int ucgb200_neigh_build_finish(ucgb200_ctx *c) {
       for (int d = 0; d < 3; d++) vol *= (c->subhi[d] - c->sublo[d]);
       double est = 4.18879 * c->cutneighmax * c->cutneighmax * c->cutneighmax * nlocal / vol;
       int s = (int)(est * 1.35) + 24;
-      c->neigh_stride = ((s + 7) / 8) * 8;
+      c->neigh_stride = ((s + 15) / 16) * 16;
     }
     if ((rc = build_rows(c))) return rc;
     UCG_CHECK(c, c->xhold.ensure(nlocal));
@@ -1232,7 +1232,7 @@ extern "C" int ucgb200_neigh_download(ucgb200_ctx *c, int *nlocal_out, long long
     if (numneigh) numneigh[i] = nn[i];
     if (offsets) offsets[i] = off;
     for (int k = 0; k < nn[i]; k++) {
-      int j = rows[(size_t)i * c->neigh_stride + k] & UCG_NEIGHMASK;
+      int j = rows[(size_t)i * c->neigh_stride + rowslot(k)] & UCG_NEIGHMASK;
       neigh_tags[off + k] = tags[j];
       // image code of the neighbor: 0 = owned site, 1..26 local periodic image, 32+ = from another brick
       if (neigh_shift) neigh_shift[off + k] = j < nlocal ? 0 : gcode[j - nlocal];

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(BS) k_pair_bethe(BetheArgs p) {
   double vir[6] = {0, 0, 0, 0, 0, 0};
 
   for (int jj = sub; jj < jnum; jj += LPA) {
-    const int jraw = row[jj];
+    const int jraw = row[rowslot(jj)];
     const double factor_lj = p.special_lj[(jraw >> UCG_SBBITS) & 3];
     const int j = jraw & UCG_NEIGHMASK;
     const double4 rj = p.pos[j];

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(BS) k_bd_prior(BdArgs p) {
   const PairInfo *prow = p.pinfo + ti * p.na;
   double rho = 0.0;
   for (int jj = sub; jj < jnum; jj += LPA) {
-    const int j = row[jj] & UCG_NEIGHMASK;
+    const int j = row[rowslot(jj)] & UCG_NEIGHMASK;
     const double4 rj = p.pos[j];
     const int tj = p.ts[j] & 0xffff;
     const double rsq = rsq_exact(ri.x - rj.x, ri.y - rj.y, ri.z - rj.z);
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
   double vir[6] = {0, 0, 0, 0, 0, 0};
 
   for (int jj = sub; jj < jnum; jj += LPA) {
-    const int jraw = row[jj];
+    const int jraw = row[rowslot(jj)];
     const double factor_lj = p.special_lj[(jraw >> UCG_SBBITS) & 3];
     const int j = jraw & UCG_NEIGHMASK;
     const double4 rj = p.pos[j];
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(BS) k_bd_back(BdArgs p) {
   double fx = 0, fy = 0, fz = 0;
   double vir[6] = {0, 0, 0, 0, 0, 0};
   for (int jj = sub; jj < jnum; jj += LPA) {
-    const int j = row[jj] & UCG_NEIGHMASK;
+    const int j = row[rowslot(jj)] & UCG_NEIGHMASK;
     const double4 rj = p.pos[j];
     const int tj = p.ts[j] & 0xffff;
     const double dx = ri.x - rj.x, dy = ri.y - rj.y, dz = ri.z - rj.z;

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(BS) k_rle_density(RleArgs p) {
   const PairInfo *prow = p.pinfo + ti * p.nt;
   double rho = 0.0;
   for (int jj = sub; jj < jnum; jj += LPA) {
-    const int j = row[jj] & UCG_NEIGHMASK;
+    const int j = row[rowslot(jj)] & UCG_NEIGHMASK;
     const double4 rj = p.pos[j];
     const int tj = p.ts[j] & 0xffff;
     const double rsq = rsq_exact(ri.x - rj.x, ri.y - rj.y, ri.z - rj.z);
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(BS) k_rle_pair(RleArgs p) {
   double fx = 0, fy = 0, fz = 0, pf = 0, eacc = 0;
   double vir[6] = {0, 0, 0, 0, 0, 0};
   for (int jj = sub; jj < jnum; jj += LPA) {
-    const int jraw = row[jj];
+    const int jraw = row[rowslot(jj)];
     const double factor_lj = p.special_lj[(jraw >> UCG_SBBITS) & 3];
     const int j = jraw & UCG_NEIGHMASK;
     const double4 rj = p.pos[j];
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(BS) k_rle_back(RleArgs p) {
   double fx = 0, fy = 0, fz = 0;
   double vir[6] = {0, 0, 0, 0, 0, 0};
   for (int jj = sub; jj < jnum; jj += LPA) {
-    const int j = row[jj] & UCG_NEIGHMASK;
+    const int j = row[rowslot(jj)] & UCG_NEIGHMASK;
     const double4 rj = p.pos[j];
     const int tj = p.ts[j] & 0xffff;
     const double dx = ri.x - rj.x, dy = ri.y - rj.y, dz = ri.z - rj.z;

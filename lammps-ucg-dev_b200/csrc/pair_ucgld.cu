@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(BS) k_pair_ucgld(PairArgs p) {
   double vir[6] = {0, 0, 0, 0, 0, 0};
 
   for (int jj = sub; jj < jnum; jj += LPA) {
-    int jraw = row[jj];
+    int jraw = row[rowslot(jj)];
     const double factor_lj = p.special_lj[(jraw >> UCG_SBBITS) & 3];
     const int j = jraw & UCG_NEIGHMASK;
     const double4 rj = p.pos[j];
@@ -213,16 +213,41 @@ __global__ void __launch_bounds__(BS) k_pair_ucgld_fast(FastArgs p) {
     double fx = 0, fy = 0, fz = 0, accA = 0, accB = 0, S0 = 0, S1 = 0;
     double vir[6] = {0, 0, 0, 0, 0, 0};
 
+    // row entries: with LPA == 4 each lane fetches its next four (logical sub, 4+sub, 8+sub, 12+sub of a
+    // 16-entry block) with one 16-byte load from the transposed row storage (ucg_internal.cuh, rowslot);
+    // the block after the current one is already in flight
+    const int4 *rp = reinterpret_cast<const int4 *>(row) + sub;
+    int4 q = make_int4(0, 0, 0, 0), qn = q;
+    int qm = 0, qb = 0;
+    if (LPA == 4) {
+      if (sub < jnum) q = __ldg(rp);
+      if (16 + sub < jnum) qn = __ldg(rp + 4);
+    }
+    auto entry = [&](int jj_) -> int {
+      if (LPA == 4) return (qm == 0 ? q.x : (qm == 1 ? q.y : (qm == 2 ? q.z : q.w))) & UCG_NEIGHMASK;
+      return row[rowslot(jj_)] & UCG_NEIGHMASK;
+    };
+    auto advance = [&]() {
+      if (LPA == 4) {
+        qm = (qm + 1) & 3;
+        if (qm == 0) {
+          qb++;
+          q = qn;
+          if (16 * (qb + 1) + sub < jnum) qn = __ldg(rp + 4 * (qb + 1));
+        }
+      }
+    };
     int jj = sub;
     int j = -1, sj = 0;
     double4 rj = ri;
-    if (jj < jnum) { j = row[jj] & UCG_NEIGHMASK; rj = ld256(p.pos + j); sj = p.sbits[j >> 5] >> (j & 31); }
+    if (jj < jnum) { j = entry(jj); rj = ld256(p.pos + j); sj = p.sbits[j >> 5] >> (j & 31); }
     while (j >= 0) {
       int jn = -1, sn = 0;
       double4 rn = rj;
       jj += LPA;
+      advance();
       if (PF) {
-        if (jj < jnum) { jn = row[jj] & UCG_NEIGHMASK; rn = ld256(p.pos + jn); sn = p.sbits[jn >> 5] >> (jn & 31); }
+        if (jj < jnum) { jn = entry(jj); rn = ld256(p.pos + jn); sn = p.sbits[jn >> 5] >> (jn & 31); }
       }
       const double dx = ri.x - rj.x, dy = ri.y - rj.y, dz = ri.z - rj.z;
       const double rsq = rsq_exact(dx, dy, dz);
@@ -269,7 +294,7 @@ __global__ void __launch_bounds__(BS) k_pair_ucgld_fast(FastArgs p) {
         }
       }
       if (!PF) {
-        if (jj < jnum) { jn = row[jj] & UCG_NEIGHMASK; rn = ld256(p.pos + jn); sn = p.sbits[jn >> 5] >> (jn & 31); }
+        if (jj < jnum) { jn = entry(jj); rn = ld256(p.pos + jn); sn = p.sbits[jn >> 5] >> (jn & 31); }
       }
       j = jn; rj = rn; sj = sn;
     }

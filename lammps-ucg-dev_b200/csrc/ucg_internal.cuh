@@ -262,6 +262,12 @@ inline int fail(ucgb200_ctx *c, const char *msg) {
 }
 inline int nblocks(long long n, int bs) { return (int)((n + bs - 1) / bs); }
 
+// Neighbor rows are stored in blocks of 16 entries, transposed 4x4: memory slot 4*l + m of a block holds
+// logical entry 4*m + l.  The 4 lanes of a site in the table_ucgld kernel then fetch their next four
+// entries (logical l, 4+l, 8+l, 12+l) with ONE 16-byte load each; every other consumer goes through
+// rowslot().  Row capacities (neigh_stride) are multiples of 16.
+__host__ __device__ __forceinline__ int rowslot(int k) { return (k & ~15) | ((k & 3) << 2) | ((k >> 2) & 3); }
+
 // exact (non-contracted) squared distance, evaluated in the reference's order
 // delx*delx + dely*dely + delz*delz  (pair_table_ucgld.cpp:211, [stock] npair)
 __device__ __forceinline__ double rsq_exact(double dx, double dy, double dz) {
