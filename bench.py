@@ -257,7 +257,11 @@ def run_gpu(args):
     prof = os.path.join(ROOT, "profiles", "pair_traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            pj = json.load(open(prof))
+            roofline["traffic"] = pj.get("dram_bytes_per_launch")
+            # the ceilings that bind before HBM does (ncu, same capture): DESIGN.md §4
+            roofline["secondary"] = {"l1_data_pipe_pct_of_peak": pj.get("lsu_data_pipe_pct"), "fp64_pipe_pct_of_peak": pj.get("fp64_pipe_pct"),
+                                     "source": pj.get("source")}
         except Exception:
             pass
 
