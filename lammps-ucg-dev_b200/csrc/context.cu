@@ -39,6 +39,7 @@ extern "C" int ucgb200_destroy(ucgb200_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   ucgb200_comm_destroy(c);
+  for (auto *t : {&c->tex_pos[0], &c->tex_pos[1], &c->tex_sbits}) if (t->tex) cudaDestroyTextureObject(t->tex);
   for (void *p : c->table_allocs) cudaFree(p);
   // Buf<> members are released explicitly (no destructors: buffers may be swapped)
   c->d_tables.release(); c->d_pairinfo.release(); c->d_typeinfo.release(); c->d_fast_table.release();

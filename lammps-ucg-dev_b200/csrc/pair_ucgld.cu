@@ -184,12 +184,27 @@ struct FastArgs {
   double *partials;
   ErrWord *err;
   int smem_table;  // 1: stage table in shared memory, 0: read it through L1/L2
+  cudaTextureObject_t postex;   // {x,y,z,lambda} records as 2 int4 texels each (TEX = true)
+  cudaTextureObject_t sbtex;    // state bits as 32-bit texels (TEX = 3)
 };
 
 // PF = 1 software-pipelines the neighbor gathers: index and {x,y,z,lambda}/state of the
 // next neighbor are in flight while the current pair is evaluated.
 // SM = true: table rows come from shared memory (LDS.128, not generic loads).
-template <int LPA, bool EV, int W, int BS, int PF, bool SM>
+// gather of one site record through the texture pipe (two 16-byte texel fetches) instead of the LSU pipe
+__device__ __forceinline__ double4 ldtex(cudaTextureObject_t t, int j) {
+  const int4 a = tex1Dfetch<int4>(t, 2 * j), b = tex1Dfetch<int4>(t, 2 * j + 1);
+  return make_double4(__hiloint2double(a.y, a.x), __hiloint2double(a.w, a.z), __hiloint2double(b.y, b.x), __hiloint2double(b.w, b.z));
+}
+// split: {x,y} through the texture pipe, {z,lambda} through the LSU pipe
+__device__ __forceinline__ double4 ldtex_half(cudaTextureObject_t t, const double4 *pos, int j) {
+  const int4 a = tex1Dfetch<int4>(t, 2 * j);
+  double2 zl;
+  asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(zl.x), "=d"(zl.y) : "l"(reinterpret_cast<const double2 *>(pos + j) + 1));
+  return make_double4(__hiloint2double(a.y, a.x), __hiloint2double(a.w, a.z), zl.x, zl.y);
+}
+
+template <int LPA, bool EV, int W, int BS, int PF, bool SM, int TEX = 0>
 __global__ void __launch_bounds__(BS) k_pair_ucgld_fast(FastArgs p) {
   extern __shared__ double2 s_tab[];
   if (SM) {
@@ -240,14 +255,14 @@ __global__ void __launch_bounds__(BS) k_pair_ucgld_fast(FastArgs p) {
     int jj = sub;
     int j = -1, sj = 0;
     double4 rj = ri;
-    if (jj < jnum) { j = entry(jj); rj = ld256(p.pos + j); sj = p.sbits[j >> 5] >> (j & 31); }
+    if (jj < jnum) { j = entry(jj); rj = (TEX == 1 || TEX == 3) ? ldtex(p.postex, j) : (TEX == 2 ? ldtex_half(p.postex, p.pos, j) : ld256(p.pos + j)); sj = (TEX == 3 ? tex1Dfetch<unsigned>(p.sbtex, j >> 5) : p.sbits[j >> 5]) >> (j & 31); }
     while (j >= 0) {
       int jn = -1, sn = 0;
       double4 rn = rj;
       jj += LPA;
       advance();
       if (PF) {
-        if (jj < jnum) { jn = entry(jj); rn = ld256(p.pos + jn); sn = p.sbits[jn >> 5] >> (jn & 31); }
+        if (jj < jnum) { jn = entry(jj); rn = (TEX == 1 || TEX == 3) ? ldtex(p.postex, jn) : (TEX == 2 ? ldtex_half(p.postex, p.pos, jn) : ld256(p.pos + jn)); sn = (TEX == 3 ? tex1Dfetch<unsigned>(p.sbtex, jn >> 5) : p.sbits[jn >> 5]) >> (jn & 31); }
       }
       const double dx = ri.x - rj.x, dy = ri.y - rj.y, dz = ri.z - rj.z;
       const double rsq = rsq_exact(dx, dy, dz);
@@ -294,7 +309,7 @@ __global__ void __launch_bounds__(BS) k_pair_ucgld_fast(FastArgs p) {
         }
       }
       if (!PF) {
-        if (jj < jnum) { jn = entry(jj); rn = ld256(p.pos + jn); sn = p.sbits[jn >> 5] >> (jn & 31); }
+        if (jj < jnum) { jn = entry(jj); rn = (TEX == 1 || TEX == 3) ? ldtex(p.postex, jn) : (TEX == 2 ? ldtex_half(p.postex, p.pos, jn) : ld256(p.pos + jn)); sn = (TEX == 3 ? tex1Dfetch<unsigned>(p.sbtex, jn >> 5) : p.sbits[jn >> 5]) >> (jn & 31); }
       }
       j = jn; rj = rn; sj = sn;
     }
@@ -355,6 +370,9 @@ template <int LPA, bool EV, int W, int BS, int PF>
 static int launch_fast(ucgb200_ctx *c, FastArgs &a, int &nblk) {
   size_t smem = a.smem_table ? (size_t)a.tablen * W * sizeof(double2) : 0;
   auto kern = a.smem_table ? k_pair_ucgld_fast<LPA, EV, W, BS, PF, true> : k_pair_ucgld_fast<LPA, EV, W, BS, PF, false>;
+  if (a.postex && a.smem_table && LPA == 4 && !EV && PF == 1 && BS == 512)
+    kern = env_int("UCGB200_TEX", 3) == 2 ? k_pair_ucgld_fast<LPA, EV, W, BS, PF, true, 2>
+           : (env_int("UCGB200_TEX", 3) == 3 ? k_pair_ucgld_fast<LPA, EV, W, BS, PF, true, 3> : k_pair_ucgld_fast<LPA, EV, W, BS, PF, true, 1>);
   if (smem > 32 * 1024) UCG_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   if (!a.smem_table) per_sm = 2048 / BS > 3 ? 3 : 2048 / BS;
@@ -425,6 +443,35 @@ extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
     a.frc = c->frc.p; a.scores = c->scores.p; a.err = c->d_err.p;
     size_t smem = (size_t)c->fast_len * c->fast_ntab * sizeof(double2);
     a.smem_table = (smem_pref && smem <= 220 * 1024) ? 1 : 0;
+    a.postex = 0; a.sbtex = 0;
+    const int tex_mode = env_int("UCGB200_TEX", 3);   // 0: every gather through the LSU pipe
+    if (tex_mode) {
+      // texture objects over the position buffers (pos / pos_alt swap at every rebuild) and the state bits;
+      // (re)created only when a buffer moved or grew
+      auto bind = [&](ucgb200_ctx::TexSlot &slot, const void *ptr, size_t bytes, cudaChannelFormatDesc desc) -> int {
+        if (slot.tex && slot.ptr == ptr && slot.bytes == bytes) return 0;
+        if (slot.tex) cudaDestroyTextureObject(slot.tex);
+        slot.tex = 0;
+        cudaResourceDesc res{};
+        res.resType = cudaResourceTypeLinear;
+        res.res.linear.devPtr = const_cast<void *>(ptr);
+        res.res.linear.desc = desc;
+        res.res.linear.sizeInBytes = bytes;
+        cudaTextureDesc td{};
+        td.readMode = cudaReadModeElementType;
+        UCG_CHECK(c, cudaCreateTextureObject(&slot.tex, &res, &td, nullptr));
+        slot.ptr = ptr; slot.bytes = bytes;
+        return 0;
+      };
+      // slot already bound to this buffer, else the one NOT bound to the twin buffer (pos_alt)
+      int pick = c->tex_pos[0].ptr == c->pos.p ? 0 : (c->tex_pos[1].ptr == c->pos.p ? 1 : -1);
+      if (pick < 0) pick = (c->tex_pos[0].ptr == c->pos_alt.p && c->tex_pos[0].tex) ? 1 : 0;
+      ucgb200_ctx::TexSlot &slot = c->tex_pos[pick];
+      if ((rc = bind(slot, c->pos.p, c->pos.cap * sizeof(double4), cudaCreateChannelDesc<int4>()))) return rc;
+      if ((rc = bind(c->tex_sbits, c->statebits.p, c->statebits.cap * sizeof(unsigned), cudaCreateChannelDesc<unsigned>()))) return rc;
+      a.postex = slot.tex;
+      a.sbtex = c->tex_sbits.tex;
+    }
     const int bs = env_int("UCGB200_BS", 512), pf = env_int("UCGB200_PF", 1);
     if (c->fast_ntab == 3) {
       if (lpa_fast == 4) rc = dispatch_fast<4, 3>(c, a, nblk, ev, bs, pf);

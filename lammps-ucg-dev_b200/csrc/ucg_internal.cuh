@@ -230,6 +230,8 @@ struct ucgb200_ctx {
     ucg::Buf<char> d_bt;
     ucg::Buf<double> d_prob, d_partial, d_cvf;
   } bdens;
+  // texture objects for the gathers of the table_ucgld kernel (the TEX pipe works beside the LSU pipe)
+  struct TexSlot { const void *ptr = nullptr; size_t bytes = 0; cudaTextureObject_t tex = 0; } tex_pos[2], tex_sbits;
   void *comm_state = nullptr;  // comm.cu: NCCL communicator + exchange buffers of a multi-brick run
   bool ev_two_parts = false;   // d_ev[16..22] holds a second virial part to be added (rleucg)
 };
