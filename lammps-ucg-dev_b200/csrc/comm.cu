@@ -108,7 +108,53 @@ int all_to_all(ucgb200_ctx *c, const char *sendbuf, char *recvbuf, const std::ve
 
 int total(const std::vector<int> &v) { return std::accumulate(v.begin(), v.end(), 0); }
 
+// forward_comm(Pair*) payloads: up to 3 per-site doubles of the owners -> their ghosts on other bricks
+__global__ void k_pack_scalars(const double *a0, const double *a1, const double *a2, int na, const int *__restrict__ owner,
+                               int n, double *__restrict__ out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int o = owner[k];
+  out[(size_t)k * na] = a0[o];
+  if (na > 1) out[(size_t)k * na + 1] = a1[o];
+  if (na > 2) out[(size_t)k * na + 2] = a2[o];
+}
+__global__ void k_unpack_scalars(double *a0, double *a1, double *a2, int na, int nlocal, const int *__restrict__ slot_of_src,
+                                 int nlimg, int n, const double *__restrict__ in) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int s = nlocal + slot_of_src[nlimg + k];
+  a0[s] = in[(size_t)k * na];
+  if (na > 1) a1[s] = in[(size_t)k * na + 1];
+  if (na > 2) a2[s] = in[(size_t)k * na + 2];
+}
+
 }  // namespace
+
+// comm->forward_comm(this) of a pair style across bricks (pair_table_rleucg_interface.cpp:141-160, the repaired
+// forward comm of pair_table_ucg_bethe_density.cpp): arrays are indexed like pos (owned, then ghosts); the local
+// periodic images are refreshed by the caller.  Same send lists and receive order as the border exchange.
+int ucg_mb_forward_scalars(ucgb200_ctx *c, double *a0, double *a1, double *a2) {
+  if (c->halo.nranks < 2) return 0;
+  CommState *s = state(c);
+  if (!s) return fail(c, "multi-brick pair style without ucgb200_comm_init (the density styles need the resident NCCL driver)");
+  const int na = 1 + (a1 != nullptr) + (a2 != nullptr);
+  const int ns = total(s->send_counts), nr = total(s->recv_counts);
+  const size_t rec = (size_t)na * sizeof(double);
+  UCG_CHECK(c, s->send.ensure((size_t)ns * rec + 64));
+  UCG_CHECK(c, s->recv.ensure((size_t)nr * rec + 64));
+  if (ns) {
+    k_pack_scalars<<<nblocks(ns, 256), 256, 0, c->stream>>>(a0, a1, a2, na, c->img_owner.p, ns, reinterpret_cast<double *>(s->send.p));
+    UCG_LAUNCHED(c);
+  }
+  int rc = all_to_all(c, s->send.p, s->recv.p, s->send_counts, s->recv_counts, rec);
+  if (rc) return rc;
+  if (nr) {
+    k_unpack_scalars<<<nblocks(nr, 256), 256, 0, c->stream>>>(a0, a1, a2, na, c->nlocal, c->slot_of_src.p, c->halo.nlimg, nr,
+                                                              reinterpret_cast<const double *>(s->recv.p));
+    UCG_LAUNCHED(c);
+  }
+  return 0;
+}
 
 extern "C" int ucgb200_comm_unique_id(char *id, int len) {
   if (!id || len < (int)sizeof(ncclUniqueId)) return -1;

@@ -330,7 +330,6 @@ extern "C" int ucgb200_pair_bethe_density(ucgb200_ctx *c, int eflag, int vflag) 
   auto &b = c->bdens;
   if (!b.set) return fail(c, "pair_bethe_density: not configured");
   if (c->dens.set) return fail(c, "pair_bethe_density: context is configured for table_rleucg_interface");
-  if (c->halo.nranks > 1) return fail(c, "pair_bethe_density: the forward exchange of the priors across bricks is not built yet");
   cudaSetDevice(c->device);
   int rc = rebuild_maps(c);
   if (rc) return rc;
@@ -373,6 +372,7 @@ extern "C" int ucgb200_pair_bethe_density(ucgb200_ctx *c, int eflag, int vflag) 
     k_bd_ghost<<<nblocks(h.nlimg, 256), 256, 0, c->stream>>>(a.prob0, c->nlocal, h.nlimg, c->img_owner.p + h.nsend, c->slot_of_src.p);
     UCG_LAUNCHED(c);
   }
+  if ((rc = ucg_mb_forward_scalars(c, a.prob0, nullptr, nullptr))) return rc;   // ghosts owned by other bricks
   int nblk_pair = nblk;
   const size_t tab_bytes = (size_t)c->fast_len * c->fast_ntab * sizeof(double2);
   if (c->fast_uniform && tab_bytes <= 220 * 1024 && !(getenv("UCGB200_FORCE_GENERAL") && atoi(getenv("UCGB200_FORCE_GENERAL")))) {

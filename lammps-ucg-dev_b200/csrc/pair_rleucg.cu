@@ -368,7 +368,6 @@ int ucg_rebuild_rle_maps(ucgb200_ctx *c) {
 extern "C" int ucgb200_pair_rleucg(ucgb200_ctx *c, int eflag, int vflag) {
   if (!c) return -1;
   if (!c->dens.set) return fail(c, "pair_rleucg: not configured");
-  if (c->halo.nranks > 1) return fail(c, "pair_rleucg: the extra forward exchanges of (p, dp, cvf) across bricks are not built yet");
   cudaSetDevice(c->device);
   int rc = rebuild_maps(c);
   if (rc) return rc;
@@ -402,6 +401,7 @@ extern "C" int ucgb200_pair_rleucg(ucgb200_ctx *c, int eflag, int vflag) {
     k_ghost_scalar<<<nblocks(h.nlimg, 256), 256, 0, c->stream>>>(a.prob, a.partial, c->nlocal, h.nlimg, lown, c->slot_of_src.p);
     UCG_LAUNCHED(c);
   }
+  if ((rc = ucg_mb_forward_scalars(c, a.prob, a.partial, nullptr))) return rc;   // ghosts owned by other bricks
   int nblk_pair = nblk;
   if (d.sm_tables && !(getenv("UCGB200_FORCE_GENERAL") && atoi(getenv("UCGB200_FORCE_GENERAL")))) {
     constexpr int FLPA = 4, FBS = 512;
@@ -426,6 +426,7 @@ extern "C" int ucgb200_pair_rleucg(ucgb200_ctx *c, int eflag, int vflag) {
     k_ghost_scalar<<<nblocks(h.nlimg, 256), 256, 0, c->stream>>>(a.cvf, nullptr, c->nlocal, h.nlimg, lown, c->slot_of_src.p);
     UCG_LAUNCHED(c);
   }
+  if ((rc = ucg_mb_forward_scalars(c, a.cvf, nullptr, nullptr))) return rc;
   k_rle_back<LPA, BS><<<nblk, BS, 0, c->stream>>>(a);
   UCG_LAUNCHED(c);
   if ((rc = reduce_partials(c, nblk, 7, 16))) return rc;   // second virial part -> d_ev[16..22]

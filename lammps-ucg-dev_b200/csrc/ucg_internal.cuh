@@ -323,6 +323,9 @@ __device__ __forceinline__ double philox_uniform(uint32_t seed, uint32_t purpose
 int rebuild_maps(ucgb200_ctx *c);
 int exclusive_scan(ucgb200_ctx *c, const int *in, int *out, int n, int *d_total);
 int reduce_partials(ucgb200_ctx *c, int nblocks, int nvals, int out_offset);
-int ucg_check_distance_launch(ucgb200_ctx *c);   // neighbor.cu: k_check_distance into d_flags[0]
+int ucg_check_distance_launch(ucgb200_ctx *c);
+}  // namespace ucg
+int ucg_mb_forward_scalars(ucgb200_ctx *c, double *a0, double *a1, double *a2);   // comm.cu
+namespace ucg {   // neighbor.cu: k_check_distance into d_flags[0]
 
 }  // namespace ucg
