@@ -273,7 +273,8 @@ extern "C" int ucgb200_cluster_configure(ucgb200_ctx *c, int mol_seed, int mol_o
   if (n_switch_types < 1 || n_switch_types > CS_MAXSW) return fail(c, "Incorrect number of atom switching types (fix cluster_switch)");
   if (prob_on > 1.0) return fail(c, "Incorrect probability in rates.txt files (fix cluster_switch)");
   if (seed <= 0) return fail(c, "Invalid seed for Park random # generator");
-  if (c->halo.nranks > 1) return fail(c, "fix cluster_switch: the label all-reduce across bricks is not built yet");
+  if (c->halo.nranks > 1 && (groupbit ? groupbit : 1) != 1)
+    return fail(c, "fix cluster_switch across bricks supports group all only (ghost records carry no group mask)");
   if (c->nlocal <= 0) return fail(c, "fix cluster_switch: upload the atoms first (the constructor scans their molecule ids and types)");
   cudaSetDevice(c->device);
   auto &k = c->cluster;
@@ -298,6 +299,11 @@ extern "C" int ucgb200_cluster_configure(ucgb200_ctx *c, int mol_seed, int mol_o
   k_cs_scan_atoms<<<nblocks(c->nlocal, 256), 256, 0, c->stream>>>(c->ts.p, c->mask.p, c->mol.p, c->nlocal, k.groupbit, st,
                                                                   mol_seed, k.d_scratch.p);
   UCG_LAUNCHED(c);
+  {  // MPI_Allreduce of :109-111
+    int rc2;
+    if ((rc2 = ucg_mb_allreduce_int(c, k.d_scratch.p, 1, 1))) return rc2;
+    if ((rc2 = ucg_mb_allreduce_int(c, k.d_scratch.p + 1, 2, 0))) return rc2;
+  }
   UCG_CHECK(c, cudaMemcpyAsync(h3, k.d_scratch.p, sizeof(h3), cudaMemcpyDeviceToHost, c->stream));
   UCG_CHECK(c, cudaStreamSynchronize(c->stream));
   if (h3[0] < 0) return fail(c, "Selected group does not have any mols (fix cluster_switch)");
@@ -316,6 +322,7 @@ extern "C" int ucgb200_cluster_configure(ucgb200_ctx *c, int mol_seed, int mol_o
   k_cs_fill<<<nblocks(nm, 256), 256, 0, c->stream>>>(k.d_label.p, nm, -1); UCG_LAUNCHED(c);
   k_cs_init_state<<<nblocks(c->nlocal, 256), 256, 0, c->stream>>>(c->ts.p, c->mask.p, c->mol.p, c->nlocal, k.groupbit, st, k.d_state.p);
   UCG_LAUNCHED(c);
+  { int rc2; if ((rc2 = ucg_mb_allreduce_int(c, k.d_state.p, nm, 1))) return rc2; }   // :160-161
   k_cs_init_restrict<<<nblocks(nm, 256), 256, 0, c->stream>>>(k.d_state.p, k.d_restrict.p, nm, mol_seed, mol_offset);
   UCG_LAUNCHED(c);
   k.next_reneighbor = c->ntimestep + 1;   // :71
@@ -340,8 +347,10 @@ extern "C" int ucgb200_cluster_check(ucgb200_ctx *c, int *n_cluster) {
   k_cs_label_partner<<<nblocks(nlocal, 256), 256, 0, st>>>(c->mask.p, c->mol.p, nlocal, k.groupbit, k.d_state.p, k.mol_offset, nm,
                                                            k.d_label.p);
   UCG_LAUNCHED(c);
-  // group bits of the periodic images
+  { int rc2; if ((rc2 = ucg_mb_allreduce_int(c, k.d_label.p, nm, 1))) return rc2; }   // :586, MPI_MAX since labels start at -1
+  // group bits of the periodic images (ghosts owned by other bricks: group all, checked in _configure)
   UCG_CHECK(c, k.d_gmask.ensure(std::max(c->nghost, 1)));
+  if (c->halo.nranks > 1 && c->nghost > 0) { k_cs_fill<<<nblocks(c->nghost, 256), 256, 0, st>>>(k.d_gmask.p, c->nghost, 1); UCG_LAUNCHED(c); }
   if (c->halo.nlimg) {
     k_cs_ghost_mask<<<nblocks(c->halo.nlimg, 256), 256, 0, st>>>(c->mask.p, c->halo.nlimg, c->img_owner.p + c->halo.nsend,
                                                                  c->slot_of_src.p, k.d_gmask.p);
@@ -377,7 +386,11 @@ extern "C" int ucgb200_cluster_check(ucgb200_ctx *c, int *n_cluster) {
       if (nedges) { k_cs_hook<<<nblocks(nedges, 256), 256, 0, st>>>(k.d_edges.p, nedges, k.d_label.p, changed); UCG_LAUNCHED(c); }
       k_cs_jump<<<nblocks(nm, 256), 256, 0, st>>>(k.d_label.p, k.d_state.p, nm, k.mol_offset, changed); UCG_LAUNCHED(c);
       k.rounds++;
+      // :682-683: every brick's labels to the global minimum, "anychange" to the maximum
+      int rc2;
+      if ((rc2 = ucg_mb_allreduce_int(c, k.d_label.p, nm, 2))) return rc2;
     }
+    { int rc2; if ((rc2 = ucg_mb_allreduce_int(c, changed, 1, 1))) return rc2; }
     int h = 0;
     UCG_CHECK(c, cudaMemcpyAsync(&h, changed, sizeof(int), cudaMemcpyDeviceToHost, st));
     UCG_CHECK(c, cudaStreamSynchronize(st));
@@ -404,10 +417,16 @@ extern "C" int ucgb200_cluster_switch(ucgb200_ctx *c, int *n_attempts, int *n_su
   cudaStream_t st = c->stream;
   const int nm = k.max_mol + 1, nlocal = c->nlocal;
   const CsTypes ty = cs_types(c);
+  int rc0;
   UCG_CHECK(c, cudaMemsetAsync(k.d_present.p, 0, nm * sizeof(int), st));
   UCG_CHECK(c, cudaMemsetAsync(k.d_sum.p, 0, nm * sizeof(int), st));
   k_cs_tally<<<nblocks(nlocal, 256), 256, 0, st>>>(c->ts.p, c->mask.p, c->mol.p, nlocal, k.groupbit, ty, k.d_present.p, k.d_sum.p);
   UCG_LAUNCHED(c);
+  // every brick then holds the same per-molecule tallies and takes the same decisions from the same RanPark
+  // stream (the reference draws rank-local streams with identical seeds, Q22: there the outcome depends on
+  // the decomposition; here it does not)
+  if ((rc0 = ucg_mb_allreduce_int(c, k.d_present.p, nm, 1))) return rc0;
+  if ((rc0 = ucg_mb_allreduce_int(c, k.d_sum.p, nm, 0))) return rc0;
   const double decision_buffer = (double)k.n_switch_per_mol / 2.0 - 1.0 + 0.01;        // :848
   k_cs_draws<<<nblocks(nm, 256), 256, 0, st>>>(k.d_present.p, k.d_sum.p, k.d_restrict.p, nm, decision_buffer, k.d_draws.p);
   UCG_LAUNCHED(c);

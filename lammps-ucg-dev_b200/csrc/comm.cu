@@ -268,6 +268,17 @@ int ucg_mb_decide(ucgb200_ctx *c, bool prechecked, int *rebuild) {
   return 0;
 }
 
+// MPI_Allreduce of an int array in place (fix_cluster_switch.cpp:109-111,160-161,586,682-683,777);
+// op: 0 sum, 1 max, 2 min.  No-op on a single brick.
+int ucg_mb_allreduce_int(ucgb200_ctx *c, int *d_buf, int n, int op) {
+  if (c->halo.nranks < 2 || n <= 0) return 0;
+  CommState *s = state(c);
+  if (!s) return fail(c, "multi-brick fix cluster_switch without ucgb200_comm_init (it needs the resident NCCL driver)");
+  const ncclRedOp_t o = op == 0 ? ncclSum : (op == 1 ? ncclMax : ncclMin);
+  UCG_NCCL(c, nccl().AllReduce(d_buf, d_buf, (size_t)n, ncclInt32, o, s->comm, c->stream));
+  return 0;
+}
+
 extern "C" int ucgb200_comm_stats(ucgb200_ctx *c, long long *bytes_forward, int *nrebuilds, int *send_records) {
   if (!c) return -1;
   CommState *s = state(c);

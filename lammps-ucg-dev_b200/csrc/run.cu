@@ -177,7 +177,7 @@ extern "C" int ucgb200_run(ucgb200_ctx *c, int nsteps) {
     // clusters and switches types (fix_cluster_switch.cpp:464-481), then Verlet rebuilds again
     if (d.cluster_freq > 0 && c->cluster.set && c->cluster.next_reneighbor == c->ntimestep) {
       StageTimer t(c, 3);
-      if ((rc = ucgb200_neigh_build(c))) return rc;
+      if ((rc = do_build(c))) return rc;
       if ((rc = ucgb200_cluster_check(c, nullptr))) return rc;
       if ((rc = ucgb200_cluster_switch(c, nullptr, nullptr))) return rc;
       c->cluster.next_reneighbor = c->ntimestep + d.cluster_freq;

@@ -326,6 +326,7 @@ int reduce_partials(ucgb200_ctx *c, int nblocks, int nvals, int out_offset);
 int ucg_check_distance_launch(ucgb200_ctx *c);
 }  // namespace ucg
 int ucg_mb_forward_scalars(ucgb200_ctx *c, double *a0, double *a1, double *a2);   // comm.cu
+int ucg_mb_allreduce_int(ucgb200_ctx *c, int *d_buf, int n, int op);             // comm.cu: 0 sum, 1 max, 2 min
 namespace ucg {   // neighbor.cu: k_check_distance into d_flags[0]
 
 }  // namespace ucg
