@@ -392,7 +392,7 @@ template <int LPA, int W>
 static int dispatch_fast(ucgb200_ctx *c, FastArgs &a, int &nblk, bool ev, int bs, int pf) {
   // thermo steps are rare: one (BS, PF) variant is enough for EV
   if (ev) return launch_fast<LPA, true, W, 512, 1>(c, a, nblk);
-  if (bs == 1024) return pf ? launch_fast<LPA, false, W, 1024, 1>(c, a, nblk) : launch_fast<LPA, false, W, 1024, 0>(c, a, nblk);
+  (void)bs;   // 1024-thread CTAs were measured and dropped (the data pipe, not latency, is the limiter)
   return pf ? launch_fast<LPA, false, W, 512, 1>(c, a, nblk) : launch_fast<LPA, false, W, 512, 0>(c, a, nblk);
 }
 
@@ -476,12 +476,10 @@ extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
     if (c->fast_ntab == 3) {
       if (lpa_fast == 4) rc = dispatch_fast<4, 3>(c, a, nblk, ev, bs, pf);
       else if (lpa_fast == 16) rc = dispatch_fast<16, 3>(c, a, nblk, ev, bs, pf);
-      else if (lpa_fast == 32) rc = dispatch_fast<32, 3>(c, a, nblk, ev, bs, pf);
       else rc = dispatch_fast<8, 3>(c, a, nblk, ev, bs, pf);
     } else {
       if (lpa_fast == 4) rc = dispatch_fast<4, 4>(c, a, nblk, ev, bs, pf);
       else if (lpa_fast == 16) rc = dispatch_fast<16, 4>(c, a, nblk, ev, bs, pf);
-      else if (lpa_fast == 32) rc = dispatch_fast<32, 4>(c, a, nblk, ev, bs, pf);
       else rc = dispatch_fast<8, 4>(c, a, nblk, ev, bs, pf);
     }
   } else {

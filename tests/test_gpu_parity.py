@@ -102,7 +102,7 @@ def _check_pair(ctx, ref, o, tol_f=F_TOL):
 
 
 @pytest.mark.parametrize("variant", ["fast_smem", "fast_global", "general"])
-@pytest.mark.parametrize("lpa", [4, 8, 16, 32])
+@pytest.mark.parametrize("lpa", [4, 8, 16])
 def test_pair_ucgld_single_type(pkg, fixtures, variant, lpa, monkeypatch):
     if variant == "general" and lpa != 8:
         pytest.skip("general kernel has one schedule")
