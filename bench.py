@@ -69,7 +69,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([s.strip() for s in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
         if not self.samples:
@@ -143,7 +143,7 @@ def run_reference(args):
         return
     # bounded sample of the 1M-site workload: the same liquid at 32 000 sites (configs[0]'s size)
     ncell = 20
-    steps = max(args.steps, 1) * 2
+    steps = min(max(args.steps, 1) * 2, 300)   # bounded sample: <= ~10 s per core
     try:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
@@ -316,8 +316,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--serial", action="store_true", help="--impl reference: one core only")

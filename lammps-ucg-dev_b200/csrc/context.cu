@@ -39,7 +39,7 @@ extern "C" int ucgb200_destroy(ucgb200_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   ucgb200_comm_destroy(c);
-  for (auto *t : {&c->tex_pos[0], &c->tex_pos[1], &c->tex_sbits}) if (t->tex) cudaDestroyTextureObject(t->tex);
+  for (auto *t : {&c->tex_pos[0], &c->tex_pos[1], &c->tex_sbits, &c->tex_ts[0], &c->tex_ts[1]}) if (t->tex) cudaDestroyTextureObject(t->tex);
   for (void *p : c->table_allocs) cudaFree(p);
   // Buf<> members are released explicitly (no destructors: buffers may be swapped)
   c->d_tables.release(); c->d_pairinfo.release(); c->d_typeinfo.release(); c->d_fast_table.release();
@@ -155,6 +155,51 @@ extern "C" int ucgb200_set_kT(ucgb200_ctx *c, double kT) {
   if (!c) return -1;
   if (!(kT > 0)) return fail(c, "kT must be positive (no fix exports t_target? see SURVEY Q2)");
   c->kT = kT;
+  return 0;
+}
+
+// (re)create a linear texture object only when the buffer moved or grew
+int ucg_bind_texture(ucgb200_ctx *c, ucgb200_ctx::TexSlot &slot, const void *ptr, size_t bytes, cudaChannelFormatDesc desc) {
+  if (slot.tex && slot.ptr == ptr && slot.bytes == bytes) return 0;
+  if (slot.tex) cudaDestroyTextureObject(slot.tex);
+  slot.tex = 0;
+  cudaResourceDesc res{};
+  res.resType = cudaResourceTypeLinear;
+  res.res.linear.devPtr = const_cast<void *>(ptr);
+  res.res.linear.desc = desc;
+  res.res.linear.sizeInBytes = bytes;
+  cudaTextureDesc td{};
+  td.readMode = cudaReadModeElementType;
+  UCG_CHECK(c, cudaCreateTextureObject(&slot.tex, &res, &td, nullptr));
+  slot.ptr = ptr; slot.bytes = bytes;
+  return 0;
+}
+
+// pos / ts swap with their twins at every rebuild: two slots each, the one already bound to the live buffer
+// is reused, otherwise the slot that is not bound to the twin
+template <class B>
+static ucgb200_ctx::TexSlot &pick_slot(ucgb200_ctx::TexSlot (&slots)[2], const B &live, const B &twin) {
+  int pick = slots[0].ptr == live.p ? 0 : (slots[1].ptr == live.p ? 1 : -1);
+  if (pick < 0) pick = (slots[0].ptr == twin.p && slots[0].tex) ? 1 : 0;
+  return slots[pick];
+}
+
+int ucg_bind_gather_textures(ucgb200_ctx *c, cudaTextureObject_t *pos, cudaTextureObject_t *ts) {
+  if (pos) *pos = 0;
+  if (ts) *ts = 0;
+  const char *e = getenv("UCGB200_TEX");
+  if (e && atoi(e) == 0) return 0;
+  int rc;
+  if (pos) {
+    ucgb200_ctx::TexSlot &s = pick_slot(c->tex_pos, c->pos, c->pos_alt);
+    if ((rc = ucg_bind_texture(c, s, c->pos.p, c->pos.cap * sizeof(double4), cudaCreateChannelDesc<int4>()))) return rc;
+    *pos = s.tex;
+  }
+  if (ts) {
+    ucgb200_ctx::TexSlot &s = pick_slot(c->tex_ts, c->ts, c->ts_alt);
+    if ((rc = ucg_bind_texture(c, s, c->ts.p, c->ts.cap * sizeof(int), cudaCreateChannelDesc<int>()))) return rc;
+    *ts = s.tex;
+  }
   return 0;
 }
 

@@ -57,6 +57,7 @@ struct BdArgs {
   double *partials;
   ErrWord *err;
   FastTable ft;   // shared-memory table path (W > 0)
+  GatherTex gt;   // neighbor gathers through the texture pipe (0 = plain loads)
 };
 
 __device__ __forceinline__ double bd_prox(double r, double rth) {
@@ -137,12 +138,13 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
   double fx = 0, fy = 0, fz = 0, eacc = 0, S0 = 0, S1 = 0, pf0 = 0, pf1 = 0;
   double vir[6] = {0, 0, 0, 0, 0, 0};
 
-  for (int jj = sub; jj < jnum; jj += LPA) {
-    const int jraw = row[rowslot(jj)];
+  RowWalk<LPA> rw(row, sub, jnum);
+  for (int jj = sub; jj < jnum; jj += LPA, rw.advance()) {
+    const int jraw = rw.raw(jj);
     const double factor_lj = p.special_lj[(jraw >> UCG_SBBITS) & 3];
     const int j = jraw & UCG_NEIGHMASK;
-    const double4 rj = p.pos[j];
-    const int tsj = p.ts[j];
+    const double4 rj = gather_pos(p.gt, p.pos, j);
+    const int tsj = gather_ts(p.gt, p.ts, j);
     const int tj = tsj & 0xffff;
     const double dx = ri.x - rj.x, dy = ri.y - rj.y, dz = ri.z - rj.z;
     const double rsq = rsq_exact(dx, dy, dz);
@@ -378,6 +380,9 @@ extern "C" int ucgb200_pair_bethe_density(ucgb200_ctx *c, int eflag, int vflag) 
   if (c->fast_uniform && tab_bytes <= 220 * 1024 && !(getenv("UCGB200_FORCE_GENERAL") && atoi(getenv("UCGB200_FORCE_GENERAL")))) {
     // one 2-state type, LINEAR tables on one grid: interleaved rows in shared memory, persistent CTAs
     constexpr int FLPA = 4, FBS = 512;
+    // a.gt stays 0: texture-pipe gathers were measured here and gave nothing (these sweeps are bound by FP64
+    // transcendentals, not by the LSU data pipe); UCGB200_TEX_ALL=1 turns them on for experiments
+    if (getenv("UCGB200_TEX_ALL") && atoi(getenv("UCGB200_TEX_ALL")) && (rc = ucg_bind_gather_textures(c, &a.gt.pos, &a.gt.ts))) return rc;
     const ucg::TableDev &t0 = c->tables[c->fast_tab[0]];
     a.ft.table = c->d_fast_table.p; a.ft.tablen = c->fast_len; a.ft.W = c->fast_ntab;
     a.ft.innersq = t0.innersq; a.ft.delta = t0.delta; a.ft.invdelta = t0.invdelta;

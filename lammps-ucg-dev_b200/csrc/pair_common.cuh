@@ -108,6 +108,58 @@ __device__ __forceinline__ void fast_table_slot(const double2 *s_tab, int W, int
   f = a.y + frac * (b.y - a.y);
 }
 
+// ---- row walking and texture-pipe gathers shared by the shared-memory-table kernels
+// With LPA == 4 each lane fetches its next four row entries (logical sub, 4+sub, 8+sub, 12+sub of a 16-entry
+// block of the transposed row storage, ucg_internal.cuh rowslot) with one 16-byte load; the block after the
+// current one is already in flight.  Other LPA: plain rowslot() reads.
+template <int LPA>
+struct RowWalk {
+  const int *row;
+  const int4 *rp;
+  int4 q, qn;
+  int qm, qb, jnum, sub;
+  __device__ __forceinline__ RowWalk(const int *row_, int sub_, int jnum_) : row(row_), qm(0), qb(0), jnum(jnum_), sub(sub_) {
+    rp = reinterpret_cast<const int4 *>(row_) + sub_;
+    q = make_int4(0, 0, 0, 0);
+    qn = q;
+    if (LPA == 4) {
+      if (sub < jnum) q = __ldg(rp);
+      if (16 + sub < jnum) qn = __ldg(rp + 4);
+    }
+  }
+  __device__ __forceinline__ int raw(int jj) const {   // entry with its special-bond bits
+    if (LPA == 4) return qm == 0 ? q.x : (qm == 1 ? q.y : (qm == 2 ? q.z : q.w));
+    return row[rowslot(jj)];
+  }
+  __device__ __forceinline__ void advance() {
+    if (LPA == 4) {
+      qm = (qm + 1) & 3;
+      if (qm == 0) {
+        qb++;
+        q = qn;
+        if (16 * (qb + 1) + sub < jnum) qn = __ldg(rp + 4 * (qb + 1));
+      }
+    }
+  }
+};
+
+// per-site gathers through the texture pipe, which works beside the (saturated) LSU data pipe; a zero
+// texture object selects the plain load
+struct GatherTex {
+  cudaTextureObject_t pos;   // {x,y,z,lambda} records as two int4 texels
+  cudaTextureObject_t ts;    // type | state << 16, one int texel per site
+};
+__device__ __forceinline__ double4 gather_pos(const GatherTex &g, const double4 *pos, int j) {
+  if (g.pos) {
+    const int4 a = tex1Dfetch<int4>(g.pos, 2 * j), b = tex1Dfetch<int4>(g.pos, 2 * j + 1);
+    return make_double4(__hiloint2double(a.y, a.x), __hiloint2double(a.w, a.z), __hiloint2double(b.y, b.x), __hiloint2double(b.w, b.z));
+  }
+  return pos[j];
+}
+__device__ __forceinline__ int gather_ts(const GatherTex &g, const int *ts, int j) {
+  return g.ts ? tex1Dfetch<int>(g.ts, j) : ts[j];
+}
+
 // sum `v` over the LPA lanes of a sub-warp group (result valid in every lane)
 template <int LPA>
 __device__ __forceinline__ double group_sum(double v) {

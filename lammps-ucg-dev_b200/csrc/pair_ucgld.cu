@@ -446,30 +446,8 @@ extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
     a.postex = 0; a.sbtex = 0;
     const int tex_mode = env_int("UCGB200_TEX", 3);   // 0: every gather through the LSU pipe
     if (tex_mode) {
-      // texture objects over the position buffers (pos / pos_alt swap at every rebuild) and the state bits;
-      // (re)created only when a buffer moved or grew
-      auto bind = [&](ucgb200_ctx::TexSlot &slot, const void *ptr, size_t bytes, cudaChannelFormatDesc desc) -> int {
-        if (slot.tex && slot.ptr == ptr && slot.bytes == bytes) return 0;
-        if (slot.tex) cudaDestroyTextureObject(slot.tex);
-        slot.tex = 0;
-        cudaResourceDesc res{};
-        res.resType = cudaResourceTypeLinear;
-        res.res.linear.devPtr = const_cast<void *>(ptr);
-        res.res.linear.desc = desc;
-        res.res.linear.sizeInBytes = bytes;
-        cudaTextureDesc td{};
-        td.readMode = cudaReadModeElementType;
-        UCG_CHECK(c, cudaCreateTextureObject(&slot.tex, &res, &td, nullptr));
-        slot.ptr = ptr; slot.bytes = bytes;
-        return 0;
-      };
-      // slot already bound to this buffer, else the one NOT bound to the twin buffer (pos_alt)
-      int pick = c->tex_pos[0].ptr == c->pos.p ? 0 : (c->tex_pos[1].ptr == c->pos.p ? 1 : -1);
-      if (pick < 0) pick = (c->tex_pos[0].ptr == c->pos_alt.p && c->tex_pos[0].tex) ? 1 : 0;
-      ucgb200_ctx::TexSlot &slot = c->tex_pos[pick];
-      if ((rc = bind(slot, c->pos.p, c->pos.cap * sizeof(double4), cudaCreateChannelDesc<int4>()))) return rc;
-      if ((rc = bind(c->tex_sbits, c->statebits.p, c->statebits.cap * sizeof(unsigned), cudaCreateChannelDesc<unsigned>()))) return rc;
-      a.postex = slot.tex;
+      if ((rc = ucg_bind_gather_textures(c, &a.postex, nullptr))) return rc;
+      if ((rc = ucg_bind_texture(c, c->tex_sbits, c->statebits.p, c->statebits.cap * sizeof(unsigned), cudaCreateChannelDesc<unsigned>()))) return rc;
       a.sbtex = c->tex_sbits.tex;
     }
     const int bs = env_int("UCGB200_BS", 512), pf = env_int("UCGB200_PF", 1);

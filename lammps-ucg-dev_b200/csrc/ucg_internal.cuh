@@ -231,7 +231,7 @@ struct ucgb200_ctx {
     ucg::Buf<double> d_prob, d_partial, d_cvf;
   } bdens;
   // texture objects for the gathers of the table_ucgld kernel (the TEX pipe works beside the LSU pipe)
-  struct TexSlot { const void *ptr = nullptr; size_t bytes = 0; cudaTextureObject_t tex = 0; } tex_pos[2], tex_sbits;
+  struct TexSlot { const void *ptr = nullptr; size_t bytes = 0; cudaTextureObject_t tex = 0; } tex_pos[2], tex_sbits, tex_ts[2];
   void *comm_state = nullptr;  // comm.cu: NCCL communicator + exchange buffers of a multi-brick run
   bool ev_two_parts = false;   // d_ev[16..22] holds a second virial part to be added (rleucg)
 };
@@ -326,7 +326,10 @@ int reduce_partials(ucgb200_ctx *c, int nblocks, int nvals, int out_offset);
 int ucg_check_distance_launch(ucgb200_ctx *c);
 }  // namespace ucg
 int ucg_mb_forward_scalars(ucgb200_ctx *c, double *a0, double *a1, double *a2);   // comm.cu
-int ucg_mb_allreduce_int(ucgb200_ctx *c, int *d_buf, int n, int op);             // comm.cu: 0 sum, 1 max, 2 min
+int ucg_mb_allreduce_int(ucgb200_ctx *c, int *d_buf, int n, int op);
+// context.cu: texture objects over pos / ts of the current buffers (0 when UCGB200_TEX=0)
+int ucg_bind_gather_textures(ucgb200_ctx *c, cudaTextureObject_t *pos, cudaTextureObject_t *ts);
+int ucg_bind_texture(ucgb200_ctx *c, ucgb200_ctx::TexSlot &slot, const void *ptr, size_t bytes, cudaChannelFormatDesc desc);             // comm.cu: 0 sum, 1 max, 2 min
 namespace ucg {   // neighbor.cu: k_check_distance into d_flags[0]
 
 }  // namespace ucg
