@@ -213,7 +213,12 @@ extern "C" int ucgb200_pair_bethe(ucgb200_ctx *c, int eflag, int vflag, int meth
   if (!c->list_valid) return fail(c, "pair_bethe: neighbor list not built");
   c->ev_valid = false;
   c->ev_two_parts = false;
-  if (c->nlocal == 0) return 0;
+  if (c->nlocal == 0) {   // an empty brick still reports (zero) energy and virial
+    UCG_CHECK(c, cudaMemsetAsync(c->d_ev.p, 0, 32 * sizeof(double), c->stream));
+    c->ev_valid = true;
+    c->ev_two_parts = false;
+    return 0;
+  }
   const bool ev = eflag || vflag;
   constexpr int LPA = 8, BS = 256;
   BetheArgs a{};

@@ -338,7 +338,12 @@ extern "C" int ucgb200_pair_bethe_density(ucgb200_ctx *c, int eflag, int vflag) 
   if (b.n_actual != c->n_actual) return fail(c, "pair_bethe_density: configured for a different number of actual types");
   if (!c->list_valid) return fail(c, "pair_bethe_density: neighbor list not built");
   c->ev_valid = false;
-  if (c->nlocal == 0) return 0;
+  if (c->nlocal == 0) {   // an empty brick still reports (zero) energy and virial
+    UCG_CHECK(c, cudaMemsetAsync(c->d_ev.p, 0, 32 * sizeof(double), c->stream));
+    c->ev_valid = true;
+    c->ev_two_parts = false;
+    return 0;
+  }
   (void)eflag; (void)vflag;
   if (b.dirty) {
     std::vector<BdType> bt(b.n_actual + 1);

@@ -375,7 +375,12 @@ extern "C" int ucgb200_pair_rleucg(ucgb200_ctx *c, int eflag, int vflag) {
   if (rc) return rc;
   if (!c->list_valid) return fail(c, "pair_rleucg: neighbor list not built");
   c->ev_valid = false;
-  if (c->nlocal == 0) return 0;
+  if (c->nlocal == 0) {   // an empty brick still reports (zero) energy and virial
+    UCG_CHECK(c, cudaMemsetAsync(c->d_ev.p, 0, 32 * sizeof(double), c->stream));
+    c->ev_valid = true;
+    c->ev_two_parts = false;
+    return 0;
+  }
   (void)eflag; (void)vflag;
   auto &d = c->dens;
   const int nall = c->nlocal + c->nghost;

@@ -416,7 +416,12 @@ extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
   if (!c->list_valid) return fail(c, "pair_ucgld: neighbor list not built");
   c->ev_valid = false;
   c->ev_two_parts = false;
-  if (c->nlocal == 0) return 0;
+  if (c->nlocal == 0) {   // an empty brick still reports (zero) energy and virial
+    UCG_CHECK(c, cudaMemsetAsync(c->d_ev.p, 0, 32 * sizeof(double), c->stream));
+    c->ev_valid = true;
+    c->ev_two_parts = false;
+    return 0;
+  }
   const bool ev = eflag || vflag;
   int nblk = 0;
   const bool timed = c->timers_on;
