@@ -370,7 +370,7 @@ template <int LPA, bool EV, int W, int BS, int PF>
 static int launch_fast(ucgb200_ctx *c, FastArgs &a, int &nblk) {
   size_t smem = a.smem_table ? (size_t)a.tablen * W * sizeof(double2) : 0;
   auto kern = a.smem_table ? k_pair_ucgld_fast<LPA, EV, W, BS, PF, true> : k_pair_ucgld_fast<LPA, EV, W, BS, PF, false>;
-  if (a.postex && a.smem_table && LPA == 4 && !EV && PF == 1 && BS == 512)
+  if (a.postex && a.smem_table && LPA == 4 && !EV && PF == 1)
     kern = env_int("UCGB200_TEX", 3) == 2 ? k_pair_ucgld_fast<LPA, EV, W, BS, PF, true, 2>
            : (env_int("UCGB200_TEX", 3) == 3 ? k_pair_ucgld_fast<LPA, EV, W, BS, PF, true, 3> : k_pair_ucgld_fast<LPA, EV, W, BS, PF, true, 1>);
   if (smem > 32 * 1024) UCG_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -392,7 +392,10 @@ template <int LPA, int W>
 static int dispatch_fast(ucgb200_ctx *c, FastArgs &a, int &nblk, bool ev, int bs, int pf) {
   // thermo steps are rare: one (BS, PF) variant is enough for EV
   if (ev) return launch_fast<LPA, true, W, 512, 1>(c, a, nblk);
-  (void)bs;   // 1024-thread CTAs were measured and dropped (the data pipe, not latency, is the limiter)
+  // 24 warps per SM (768 threads, 80 registers): with the gathers on the texture pipe neither data pipe is
+  // saturated any more and the extra warps pay (0.64 -> 0.58 ms); 640 / 896 / 1024 threads were slower
+  // (0.65 / 0.69 / 0.89 ms: the last two spill)
+  if (LPA == 4 && pf && bs == 768) return launch_fast<LPA, false, W, 768, 1>(c, a, nblk);
   return pf ? launch_fast<LPA, false, W, 512, 1>(c, a, nblk) : launch_fast<LPA, false, W, 512, 0>(c, a, nblk);
 }
 
@@ -455,7 +458,7 @@ extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
       if ((rc = ucg_bind_texture(c, c->tex_sbits, c->statebits.p, c->statebits.cap * sizeof(unsigned), cudaCreateChannelDesc<unsigned>()))) return rc;
       a.sbtex = c->tex_sbits.tex;
     }
-    const int bs = env_int("UCGB200_BS", 512), pf = env_int("UCGB200_PF", 1);
+    const int bs = env_int("UCGB200_BS", 768), pf = env_int("UCGB200_PF", 1);
     if (c->fast_ntab == 3) {
       if (lpa_fast == 4) rc = dispatch_fast<4, 3>(c, a, nblk, ev, bs, pf);
       else if (lpa_fast == 16) rc = dispatch_fast<16, 3>(c, a, nblk, ev, bs, pf);
