@@ -260,7 +260,7 @@ def run_gpu(args):
             pj = json.load(open(prof))
             roofline["traffic"] = pj.get("dram_bytes_per_launch")
             # the ceilings that bind before HBM does (ncu, same capture): DESIGN.md §4
-            roofline["secondary"] = {"l1_data_pipe_pct_of_peak": pj.get("lsu_data_pipe_pct"), "fp64_pipe_pct_of_peak": pj.get("fp64_pipe_pct"),
+            roofline["secondary"] = {"l1_data_pipe_pct_of_peak": pj.get("lsu_data_pipe_pct"), "tex_data_pipe_pct_of_peak": pj.get("tex_data_pipe_pct"), "fp64_pipe_pct_of_peak": pj.get("fp64_pipe_pct"),
                                      "source": pj.get("source")}
         except Exception:
             pass
