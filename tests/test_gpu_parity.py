@@ -123,6 +123,27 @@ def test_pair_ucgld_single_type(pkg, fixtures, variant, lpa, monkeypatch):
         assert np.array_equal(again[k], got[k])
 
 
+@pytest.mark.parametrize("knobs", [dict(UCGB200_TEX="0", UCGB200_BS="512"), dict(UCGB200_TEX="1", UCGB200_BS="768"),
+                                   dict(UCGB200_TEX="3", UCGB200_BS="512"), dict(UCGB200_PF="0")])
+def test_pair_ucgld_schedule_knobs_do_not_change_results(pkg, fixtures, monkeypatch, knobs):
+    """texture-pipe gathers, CTA size and software pipelining are pure schedule choices: per-site results must
+    equal the default schedule's bit for bit (same arithmetic, same summation order per lane group)"""
+    liq = _liq(9)
+    ctx = decks.gpu_single_type(pkg, liq, fixtures)
+    ctx.neigh_build()
+    ctx.pair_ucgld(0, 0)
+    base = ctx.atoms_download(["f", "ucgforce", "ucgsoftmaxscores"])
+    o = decks.orc_single_type(liq, fixtures)
+    ref = decks.oracle_forces(o)
+    assert rel_err(base["f"], ref["f"]) <= F_TOL
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    ctx.pair_ucgld(0, 0)
+    again = ctx.atoms_download(["f", "ucgforce", "ucgsoftmaxscores"])
+    for k in again:
+        assert np.array_equal(again[k], base[k]), k
+
+
 def test_pair_ucgld_tablength_25000_uses_l2_path(pkg, fixtures, tmp_path):
     """the reference's own usage comment quotes `linear 25000` (pair_table_ucg_bethe.cpp:752):
     1.2 MB of tables cannot sit in shared memory"""
