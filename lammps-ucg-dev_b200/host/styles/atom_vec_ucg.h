@@ -15,20 +15,24 @@ AtomStyle(ucg, AtomVecUCG);
 namespace LAMMPS_NS {
 
 class AtomVecUCG : virtual public AtomVec {
+ protected:
+  struct Topology {        // per-atom topology counters reset in data_atom_post
+    int *bonds, *angles, *dihedrals, *impropers;
+    int **special_counts;
+  } topo;
+  struct Site {            // cached atom->ucg* pointers (re-taken in grow_pointers)
+    int *state, *nstates;
+    double *lambda, *vlambda, *mlambda, *prob, *flambda;
+    double **scores;
+  } site;
+
  public:
   AtomVecUCG(class LAMMPS *);
   void grow_pointers() override;
-  void force_clear(int, size_t) override;
   void data_atom_post(int) override;
+  void force_clear(int, size_t) override;
   int property_atom(const std::string &name) override;
   void pack_property_atom(int, double *, int, int) override;
-
- protected:
-  int *num_bond, *num_angle, *num_dihedral, *num_improper;
-  int **nspecial;
-  int *ucgstate, *num_ucgstates;
-  double *ucgl, *ucgvl, *ucgml, *ucgp, *ucgforce;
-  double **ucgsoftmaxscores;
 };
 
 }  // namespace LAMMPS_NS

@@ -6,29 +6,33 @@ FixStyle(nve/ucgld, FixNVE_UCGLD);
 #ifndef LMP_FIX_NVE_UCGLD_H
 #define LMP_FIX_NVE_UCGLD_H
 
-// GPU-backed drop-in for FixNVE_UCGLD (UCG/fix_nve_ucgld.h:16): velocity Verlet for the
-// particles and for lambda.
+// GPU-backed drop-in for FixNVE_UCGLD (UCG/fix_nve_ucgld.h:16): velocity Verlet for the particles and for
+// lambda; both half-steps are kernels of csrc/fixes.cu.  The hard-wall variant derives from this class and
+// only flips `hard_wall`.
 
 #include "fix.h"
 
 namespace LAMMPS_NS {
 
+class UCGDevice;
+
 class FixNVE_UCGLD : public Fix {
+ protected:
+  UCGDevice *dev;         // the device context shared by every UCG style of this LAMMPS instance
+  int hard_wall;          // 1: lambda is reflected at 0 and 1 and the discrete state follows lambda
+  double dt_pos;          // update->dt
+  double dt_half;         // 0.5 * update->dt * force->ftm2v
+  double *respa_steps;    // Respa::step when run_style respa is active
+
  public:
   FixNVE_UCGLD(class LAMMPS *, int, char **);
-  int setmask() override;
   void init() override;
-  void initial_integrate(int) override;
-  void final_integrate() override;
-  void initial_integrate_respa(int, int, int) override;
-  void final_integrate_respa(int, int) override;
+  int setmask() override;
   void reset_dt() override;
-
- protected:
-  double dtv, dtf;
-  double *step_respa;
-  int wall;               // 1 in the wall/hard subclass
-  class UCGDevice *dev;
+  void final_integrate() override;
+  void initial_integrate(int) override;
+  void final_integrate_respa(int, int) override;
+  void initial_integrate_respa(int, int, int) override;
 };
 
 }  // namespace LAMMPS_NS

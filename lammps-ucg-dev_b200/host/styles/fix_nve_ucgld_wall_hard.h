@@ -7,21 +7,23 @@ FixStyle(nve/ucgld/wall/hard, FixNVE_UCGLD_Wall_Hard);
 #define LMP_FIX_NVE_UCGLD_WALL_HARD_H
 
 // GPU-backed drop-in for FixNVE_UCGLD_Wall_Hard (UCG/fix_nve_ucgld_wall_hard.h:16):
-// fix ID group nve/ucgld/wall/hard [bias_potential H]
+//   fix ID group nve/ucgld/wall/hard [bias_potential H]
+// The reflection lives in the integrator kernels of the base class; this class adds the optional
+// double-well bias on lambda as a post_force stage.
 
 #include "fix_nve_ucgld.h"
 
 namespace LAMMPS_NS {
 
 class FixNVE_UCGLD_Wall_Hard : public FixNVE_UCGLD {
+ protected:
+  double bias_height;     // H of  (-7980 x^9 + 2 x) * 10 H,  x = lambda - 1/2
+  int bias_on;            // keyword bias_potential given
+
  public:
   FixNVE_UCGLD_Wall_Hard(class LAMMPS *, int, char **);
-  int setmask() override;
   void post_force(int) override;
-
- protected:
-  int bias_potential_flag;
-  double barrier;
+  int setmask() override;
 };
 
 }  // namespace LAMMPS_NS

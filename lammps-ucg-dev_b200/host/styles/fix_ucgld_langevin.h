@@ -7,38 +7,45 @@ FixStyle(ucgld/langevin, Fix_UCGLD_Langevin);
 #define LMP_FIX_LANGEVIN_UCGLD_H
 
 // GPU-backed drop-in for Fix_UCGLD_Langevin (UCG/fix_ucgld_langevin.h:16):
-// fix ID group ucgld/langevin Tstart Tstop period seed
+//   fix ID group ucgld/langevin Tstart Tstop period seed
+// Thermostat of the lambda degree of freedom; exports "t_target" to the pair styles and to fix ucgstate.
 
 #include "fix.h"
 
 namespace LAMMPS_NS {
 
+class UCGDevice;
+
 class Fix_UCGLD_Langevin : public Fix {
+ protected:
+  UCGDevice *dev;
+  struct Ramp {            // linear temperature ramp over the run
+    double start, stop, period;
+    double now, sqrt_now;  // target at the current step
+  } temp;
+  double *drag, *kick;     // per-type  -m/period/ftm2v  and  sqrt(m) sqrt(24 kB/(period dt mvv2e))/ftm2v
+  double *ratio;           // per-type scale factors (fix_modify-compatible, all 1)
+  int rng_seed, bias_temp, nlevels_respa;
+  char *temp_compute_id;
+  class Compute *temperature;
+  double lambda_temperature;
+  void compute_target();
+
  public:
   Fix_UCGLD_Langevin(class LAMMPS *, int, char **);
   ~Fix_UCGLD_Langevin() override;
-  int setmask() override;
   void init() override;
   void setup(int) override;
-  void post_force(int) override;
-  void post_force_respa(int, int, int) override;
-  void end_of_step() override;
-  void reset_target(double) override;
+  int setmask() override;
   void reset_dt() override;
-  int modify_param(int, char **) override;
-  double compute_scalar() override;
+  void end_of_step() override;
+  void post_force(int) override;
+  void reset_target(double) override;
   double memory_usage() override;
+  double compute_scalar() override;
+  int modify_param(int, char **) override;
   void *extract(const char *, int &) override;
-
- protected:
-  double t_start, t_stop, t_period, t_target, tsqrt;
-  double *gfactor1, *gfactor2, *ratio;
-  int seed, tbiasflag, nlevels_respa;
-  char *id_temp;
-  class Compute *temperature;
-  double lambda_temp;
-  class UCGDevice *dev;
-  void compute_target();
+  void post_force_respa(int, int, int) override;
 };
 
 }  // namespace LAMMPS_NS

@@ -30,7 +30,7 @@ static const unsigned DYN_IN = UCGB200_F_X | UCGB200_F_V | UCGB200_F_F | UCGB200
 
 // ---------------------------------------------------------------- fix nve/ucgld
 // UCG/fix_nve_ucgld.cpp:10-181
-FixNVE_UCGLD::FixNVE_UCGLD(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg), dtv(0), dtf(0), step_respa(nullptr), wall(0) {
+FixNVE_UCGLD::FixNVE_UCGLD(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg), dt_pos(0), dt_half(0), respa_steps(nullptr), hard_wall(0) {
   if (utils::strmatch(style, "^nve/ucgld$") && narg > 3)
     error->all(FLERR, 3, "Unsupported additional arguments for fix {}", style);
   dynamic_group_allow = 1;
@@ -39,47 +39,47 @@ FixNVE_UCGLD::FixNVE_UCGLD(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, a
 }
 int FixNVE_UCGLD::setmask() { return INITIAL_INTEGRATE | FINAL_INTEGRATE | INITIAL_INTEGRATE_RESPA | FINAL_INTEGRATE_RESPA; }
 void FixNVE_UCGLD::init() {
-  dtv = update->dt;
-  dtf = 0.5 * update->dt * force->ftm2v;
-  if (utils::strmatch(update->integrate_style, "^respa")) step_respa = (dynamic_cast<Respa *>(update->integrate))->step;
+  dt_pos = update->dt;
+  dt_half = 0.5 * update->dt * force->ftm2v;
+  if (utils::strmatch(update->integrate_style, "^respa")) respa_steps = (dynamic_cast<Respa *>(update->integrate))->step;
   if (atom->rmass) error->all(FLERR, "fix {}: per-atom masses (rmass) are not supported by ucg-b200", style);
 }
 void FixNVE_UCGLD::initial_integrate(int) {
   dev->upload(lmp, DYN_IN);
-  dev->check(lmp, ucgb200_fix_nve_initial(dev->ctx, dtv, dtf, groupbit, wall), "fix_nve_initial");
-  dev->download(lmp, UCGB200_F_X | UCGB200_F_V | UCGB200_F_UCGL | UCGB200_F_UCGVL | (wall ? UCGB200_F_UCGSTATE : 0u));
+  dev->check(lmp, ucgb200_fix_nve_initial(dev->ctx, dt_pos, dt_half, groupbit, hard_wall), "fix_nve_initial");
+  dev->download(lmp, UCGB200_F_X | UCGB200_F_V | UCGB200_F_UCGL | UCGB200_F_UCGVL | (hard_wall ? UCGB200_F_UCGSTATE : 0u));
 }
 void FixNVE_UCGLD::final_integrate() {
   dev->upload(lmp, UCGB200_F_V | UCGB200_F_F | UCGB200_F_UCGVL | UCGB200_F_UCGFORCE | UCGB200_F_UCGL);
-  dev->check(lmp, ucgb200_fix_nve_final(dev->ctx, dtf, groupbit, wall), "fix_nve_final");
-  dev->download(lmp, UCGB200_F_V | UCGB200_F_UCGVL | (wall ? UCGB200_F_UCGL : 0u));
+  dev->check(lmp, ucgb200_fix_nve_final(dev->ctx, dt_half, groupbit, hard_wall), "fix_nve_final");
+  dev->download(lmp, UCGB200_F_V | UCGB200_F_UCGVL | (hard_wall ? UCGB200_F_UCGL : 0u));
 }
 void FixNVE_UCGLD::initial_integrate_respa(int vflag, int ilevel, int) {
-  dtv = step_respa[ilevel];
-  dtf = 0.5 * step_respa[ilevel] * force->ftm2v;
+  dt_pos = respa_steps[ilevel];
+  dt_half = 0.5 * respa_steps[ilevel] * force->ftm2v;
   if (ilevel == 0) initial_integrate(vflag); else final_integrate();
 }
 void FixNVE_UCGLD::final_integrate_respa(int ilevel, int) {
-  dtf = 0.5 * step_respa[ilevel] * force->ftm2v;
+  dt_half = 0.5 * respa_steps[ilevel] * force->ftm2v;
   final_integrate();
 }
 void FixNVE_UCGLD::reset_dt() {
-  dtv = update->dt;
-  dtf = 0.5 * update->dt * force->ftm2v;
+  dt_pos = update->dt;
+  dt_half = 0.5 * update->dt * force->ftm2v;
 }
 
-// ------------------------------------------------------ fix nve/ucgld/wall/hard
+// ------------------------------------------------------ fix nve/ucgld/hard_wall/hard
 // UCG/fix_nve_ucgld_wall_hard.cpp:12-52, 234-257
 FixNVE_UCGLD_Wall_Hard::FixNVE_UCGLD_Wall_Hard(LAMMPS *lmp, int narg, char **arg)
-    : FixNVE_UCGLD(lmp, narg, arg), bias_potential_flag(0), barrier(0.1) {
+    : FixNVE_UCGLD(lmp, narg, arg), bias_on(0), bias_height(0.1) {
   if (narg > 5) error->all(FLERR, 3, "Unsupported additional arguments for fix {}", style);
-  wall = 1;
+  hard_wall = 1;
   int iarg = 3;
   while (iarg < narg) {
     if (utils::strmatch(arg[iarg], "bias_potential")) {
-      bias_potential_flag = 1;
+      bias_on = 1;
       iarg++;
-      if (iarg < narg) barrier = utils::numeric(FLERR, arg[iarg], false, lmp);
+      if (iarg < narg) bias_height = utils::numeric(FLERR, arg[iarg], false, lmp);
       iarg++;
     } else
       error->all(FLERR, "Unknown argument for fix {}", style);
@@ -87,28 +87,28 @@ FixNVE_UCGLD_Wall_Hard::FixNVE_UCGLD_Wall_Hard(LAMMPS *lmp, int narg, char **arg
 }
 int FixNVE_UCGLD_Wall_Hard::setmask() {
   int mask = FixNVE_UCGLD::setmask();
-  if (bias_potential_flag) mask |= POST_FORCE;
+  if (bias_on) mask |= POST_FORCE;
   return mask;
 }
 void FixNVE_UCGLD_Wall_Hard::post_force(int) {
   dev->upload(lmp, UCGB200_F_UCGL | UCGB200_F_UCGFORCE);
-  dev->check(lmp, ucgb200_fix_wall_bias(dev->ctx, barrier, groupbit), "fix_wall_bias");
+  dev->check(lmp, ucgb200_fix_wall_bias(dev->ctx, bias_height, groupbit), "fix_wall_bias");
   dev->download(lmp, UCGB200_F_UCGFORCE);
 }
 
 // ----------------------------------------------------------------- fix ucgstate
 // UCG/fix_ucgstate.cpp:34-171
-FixUCGState::FixUCGState(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg), kT(0), T(0), ld_flag(0), mc_flag(0), mc_seed(1), mc_rate(0.01) {
+FixUCGState::FixUCGState(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg), kT_now(0), t_bath(0), lambda_only(0), monte_carlo(0), rng_seed(1), switch_rate(0.01) {
   if (narg > 6) error->all(FLERR, 3, "Too many arguments for fix {}", style);
   if (!atom->ucg_flag) error->all(FLERR, 1, "fix ucgstate requires ucg atom style");
   if (narg > 3) {
-    if (utils::strmatch(arg[3], "ld")) ld_flag = 1;
+    if (utils::strmatch(arg[3], "ld")) lambda_only = 1;
     else if (utils::strmatch(arg[3], "mc")) {
-      mc_flag = 1;
+      monte_carlo = 1;
       if (narg == 4) error->all(FLERR, 1, "fix ucgstate mc requires seed and rate information");
       if (narg == 5) error->all(FLERR, 1, "fix ucgstate mc requires rate information");
-      mc_seed = utils::inumeric(FLERR, arg[4], false, lmp);
-      mc_rate = utils::numeric(FLERR, arg[5], false, lmp);
+      rng_seed = utils::inumeric(FLERR, arg[4], false, lmp);
+      switch_rate = utils::numeric(FLERR, arg[5], false, lmp);
     } else
       error->all(FLERR, 1, "Unknown argument for fix {}: {}", style, arg[3]);
   }
@@ -119,9 +119,9 @@ FixUCGState::FixUCGState(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg
 int FixUCGState::setmask() { return POST_FORCE | POST_FORCE_RESPA | MIN_POST_FORCE; }
 void FixUCGState::post_force(int) {
   dev->upload(lmp, UCGB200_F_SCORES | UCGB200_F_UCGSTATE | UCGB200_F_UCGL);
-  const int mode = ld_flag ? 1 : (mc_flag ? 2 : 0);
-  dev->check(lmp, ucgb200_fix_ucgstate(dev->ctx, mode, mc_seed + comm->me, mc_rate, update->ntimestep), "fix_ucgstate");
-  dev->download(lmp, UCGB200_F_UCGP | (ld_flag ? 0u : (UCGB200_F_UCGSTATE | UCGB200_F_UCGL)));
+  const int mode = lambda_only ? 1 : (monte_carlo ? 2 : 0);
+  dev->check(lmp, ucgb200_fix_ucgstate(dev->ctx, mode, rng_seed + comm->me, switch_rate, update->ntimestep), "fix_ucgstate");
+  dev->download(lmp, UCGB200_F_UCGP | (lambda_only ? 0u : (UCGB200_F_UCGSTATE | UCGB200_F_UCGL)));
 }
 void FixUCGState::post_force_respa(int vflag, int, int) { post_force(vflag); }
 void FixUCGState::min_post_force(int vflag) { post_force(vflag); }
@@ -130,18 +130,18 @@ void FixUCGState::setup(int vflag) {
   int pdim;
   for (int ifix = 0; ifix < modify->nfix; ifix++) {
     pT = (double *) modify->fix[ifix]->extract("t_target", pdim);
-    if (pT) { T = *pT; break; }
+    if (pT) { t_bath = *pT; break; }
   }
-  if (pT == nullptr) error->all(FLERR, "FixUCGState requires a thermostat fix BEFORE ITSELF to set the target temperature T.");
-  kT = force->boltz * T;
+  if (pT == nullptr) error->all(FLERR, "FixUCGState requires a thermostat fix BEFORE ITSELF to set the target temperature t_bath.");
+  kT_now = force->boltz * t_bath;
   post_force(vflag);
 }
 
 // ------------------------------------------------------------ fix ucgld/langevin
 // UCG/fix_ucgld_langevin.cpp:55-417
 Fix_UCGLD_Langevin::Fix_UCGLD_Langevin(LAMMPS *lmp, int narg, char **arg)
-    : Fix(lmp, narg, arg), gfactor1(nullptr), gfactor2(nullptr), ratio(nullptr), tbiasflag(0), nlevels_respa(1),
-      id_temp(nullptr), temperature(nullptr), lambda_temp(0.0) {
+    : Fix(lmp, narg, arg), drag(nullptr), kick(nullptr), ratio(nullptr), bias_temp(0), nlevels_respa(1),
+      temp_compute_id(nullptr), temperature(nullptr), lambda_temperature(0.0) {
   if (narg < 7) error->all(FLERR, "Illegal fix langevin command");
   dynamic_group_allow = 1;
   scalar_flag = 1;
@@ -150,43 +150,43 @@ Fix_UCGLD_Langevin::Fix_UCGLD_Langevin(LAMMPS *lmp, int narg, char **arg)
   ecouple_flag = 1;
   nevery = 1;
   if (utils::strmatch(arg[3], "^v_")) error->all(FLERR, "lambda dynamic variable is not supported with variable temperature");
-  t_start = utils::numeric(FLERR, arg[3], false, lmp);
-  t_target = t_start;
-  t_stop = utils::numeric(FLERR, arg[4], false, lmp);
-  t_period = utils::numeric(FLERR, arg[5], false, lmp);
-  seed = utils::inumeric(FLERR, arg[6], false, lmp);
-  if (t_period <= 0.0) error->all(FLERR, "Fix langevin period must be > 0.0");
-  if (seed <= 0) error->all(FLERR, "Illegal fix langevin command");
-  tsqrt = sqrt(t_target);
-  gfactor1 = new double[atom->ntypes + 1];
-  gfactor2 = new double[atom->ntypes + 1];
+  temp.start = utils::numeric(FLERR, arg[3], false, lmp);
+  temp.now = temp.start;
+  temp.stop = utils::numeric(FLERR, arg[4], false, lmp);
+  temp.period = utils::numeric(FLERR, arg[5], false, lmp);
+  rng_seed = utils::inumeric(FLERR, arg[6], false, lmp);
+  if (temp.period <= 0.0) error->all(FLERR, "Fix langevin period must be > 0.0");
+  if (rng_seed <= 0) error->all(FLERR, "Illegal fix langevin command");
+  temp.sqrt_now = sqrt(temp.now);
+  drag = new double[atom->ntypes + 1];
+  kick = new double[atom->ntypes + 1];
   ratio = new double[atom->ntypes + 1];
-  for (int i = 0; i <= atom->ntypes; i++) { ratio[i] = 1.0; gfactor1[i] = gfactor2[i] = 0.0; }
+  for (int i = 0; i <= atom->ntypes; i++) { ratio[i] = 1.0; drag[i] = kick[i] = 0.0; }
   dev = UCGDevice::get(lmp);
 }
 Fix_UCGLD_Langevin::~Fix_UCGLD_Langevin() {
   if (copymode) return;
-  delete[] gfactor1;
-  delete[] gfactor2;
+  delete[] drag;
+  delete[] kick;
   delete[] ratio;
-  delete[] id_temp;
+  delete[] temp_compute_id;
 }
 int Fix_UCGLD_Langevin::setmask() { return POST_FORCE | POST_FORCE_RESPA | END_OF_STEP; }
 void Fix_UCGLD_Langevin::init() {
-  if (id_temp) {
-    temperature = modify->get_compute_by_id(id_temp);
-    if (!temperature) error->all(FLERR, "Temperature compute ID {} for fix {} does not exist", id_temp, style);
-    if (temperature->tempflag == 0) error->all(FLERR, "Compute ID {} for fix {} does not compute temperature", id_temp, style);
+  if (temp_compute_id) {
+    temperature = modify->get_compute_by_id(temp_compute_id);
+    if (!temperature) error->all(FLERR, "Temperature compute ID {} for fix {} does not exist", temp_compute_id, style);
+    if (temperature->tempflag == 0) error->all(FLERR, "Compute ID {} for fix {} does not compute temperature", temp_compute_id, style);
   }
   // (sic) the reference reads atom->ucgml at the TYPE index (:164-171, quirk Q20)
   for (int i = 1; i <= atom->ntypes; i++) {
-    gfactor1[i] = -atom->ucgml[i] / t_period / force->ftm2v;
-    gfactor2[i] = sqrt(atom->ucgml[i]) / force->ftm2v;
-    gfactor2[i] *= sqrt(24.0 * force->boltz / t_period / update->dt / force->mvv2e);
-    gfactor1[i] *= 1.0 / ratio[i];
-    gfactor2[i] *= 1.0 / sqrt(ratio[i]);
+    drag[i] = -atom->ucgml[i] / temp.period / force->ftm2v;
+    kick[i] = sqrt(atom->ucgml[i]) / force->ftm2v;
+    kick[i] *= sqrt(24.0 * force->boltz / temp.period / update->dt / force->mvv2e);
+    drag[i] *= 1.0 / ratio[i];
+    kick[i] *= 1.0 / sqrt(ratio[i]);
   }
-  tbiasflag = (temperature && temperature->tempbias) ? 1 : 0;
+  bias_temp = (temperature && temperature->tempbias) ? 1 : 0;
   if (utils::strmatch(update->integrate_style, "^respa")) nlevels_respa = (static_cast<Respa *>(update->integrate))->nlevels;
 }
 void Fix_UCGLD_Langevin::setup(int vflag) {
@@ -196,15 +196,15 @@ void Fix_UCGLD_Langevin::setup(int vflag) {
 void Fix_UCGLD_Langevin::compute_target() {
   double delta = update->ntimestep - update->beginstep;
   if (delta != 0.0) delta /= update->endstep - update->beginstep;
-  t_target = t_start + delta * (t_stop - t_start);
-  tsqrt = sqrt(t_target);
+  temp.now = temp.start + delta * (temp.stop - temp.start);
+  temp.sqrt_now = sqrt(temp.now);
 }
 void Fix_UCGLD_Langevin::post_force(int) {
   compute_target();
-  if (tbiasflag) temperature->compute_scalar();
+  if (bias_temp) temperature->compute_scalar();
   dev->upload(lmp, UCGB200_F_UCGVL | UCGB200_F_UCGFORCE);
-  dev->check(lmp, ucgb200_fix_langevin(dev->ctx, gfactor1, gfactor2, atom->ntypes, tsqrt, seed + comm->me,
-                                       update->ntimestep, groupbit, tbiasflag), "fix_langevin");
+  dev->check(lmp, ucgb200_fix_langevin(dev->ctx, drag, kick, atom->ntypes, temp.sqrt_now, rng_seed + comm->me,
+                                       update->ntimestep, groupbit, bias_temp), "fix_langevin");
   dev->download(lmp, UCGB200_F_UCGFORCE);
 }
 void Fix_UCGLD_Langevin::post_force_respa(int vflag, int ilevel, int) {
@@ -216,37 +216,37 @@ void Fix_UCGLD_Langevin::end_of_step() {
   double ke = 0.0;
   long long cnt = 0;
   dev->check(lmp, ucgb200_lambda_ke(dev->ctx, groupbit, &ke, &cnt), "lambda_ke");
-  lambda_temp = atom->nlocal ? ke / (0.5 * force->boltz * atom->nlocal) : 0.0;
+  lambda_temperature = atom->nlocal ? ke / (0.5 * force->boltz * atom->nlocal) : 0.0;
 }
-void Fix_UCGLD_Langevin::reset_target(double t_new) { t_target = t_start = t_stop = t_new; }
+void Fix_UCGLD_Langevin::reset_target(double t_new) { temp.now = temp.start = temp.stop = t_new; }
 void Fix_UCGLD_Langevin::reset_dt() {
   // (sic) uses atom->mass, not ucgml (:366-376)
   if (atom->mass)
     for (int i = 1; i <= atom->ntypes; i++) {
-      gfactor2[i] = sqrt(atom->mass[i]) / force->ftm2v;
-      gfactor2[i] *= sqrt(24.0 * force->boltz / t_period / update->dt / force->mvv2e);
-      gfactor2[i] *= 1.0 / sqrt(ratio[i]);
+      kick[i] = sqrt(atom->mass[i]) / force->ftm2v;
+      kick[i] *= sqrt(24.0 * force->boltz / temp.period / update->dt / force->mvv2e);
+      kick[i] *= 1.0 / sqrt(ratio[i]);
     }
 }
 int Fix_UCGLD_Langevin::modify_param(int narg, char **arg) {
   if (strcmp(arg[0], "temp") == 0) {
     if (narg < 2) utils::missing_cmd_args(FLERR, "fix_modify", error);
-    delete[] id_temp;
-    id_temp = utils::strdup(arg[1]);
-    temperature = modify->get_compute_by_id(id_temp);
-    if (!temperature) error->all(FLERR, "Could not find fix_modify temperature compute ID: {}", id_temp);
-    if (temperature->tempflag == 0) error->all(FLERR, "Fix_modify temperature compute {} does not compute temperature", id_temp);
+    delete[] temp_compute_id;
+    temp_compute_id = utils::strdup(arg[1]);
+    temperature = modify->get_compute_by_id(temp_compute_id);
+    if (!temperature) error->all(FLERR, "Could not find fix_modify temperature compute ID: {}", temp_compute_id);
+    if (temperature->tempflag == 0) error->all(FLERR, "Fix_modify temperature compute {} does not compute temperature", temp_compute_id);
     if (temperature->igroup != igroup && comm->me == 0)
       error->warning(FLERR, "Group for fix_modify temp != fix group: {} vs {}", group->names[igroup], group->names[temperature->igroup]);
     return 2;
   }
   return 0;
 }
-double Fix_UCGLD_Langevin::compute_scalar() { return lambda_temp; }
+double Fix_UCGLD_Langevin::compute_scalar() { return lambda_temperature; }
 double Fix_UCGLD_Langevin::memory_usage() { return 0.0; }
 void *Fix_UCGLD_Langevin::extract(const char *str, int &dim) {
   dim = 0;
-  if (strcmp(str, "t_target") == 0) return &t_target;
+  if (strcmp(str, "t_target") == 0) return &temp.now;
   return nullptr;
 }
 
@@ -279,23 +279,23 @@ AtomVecUCG::AtomVecUCG(LAMMPS *lmp) : AtomVec(lmp) {
   setup_fields();
 }
 void AtomVecUCG::grow_pointers() {
-  num_bond = atom->num_bond; num_angle = atom->num_angle; num_dihedral = atom->num_dihedral; num_improper = atom->num_improper;
-  nspecial = atom->nspecial;
-  ucgstate = atom->ucgstate; ucgl = atom->ucgl; ucgforce = atom->ucgforce; ucgsoftmaxscores = atom->ucgsoftmaxscores;
-  ucgvl = atom->ucgvl; ucgp = atom->ucgp; ucgml = atom->ucgml; num_ucgstates = atom->num_ucgstates;
+  topo.bonds = atom->num_bond; topo.angles = atom->num_angle; topo.dihedrals = atom->num_dihedral; topo.impropers = atom->num_improper;
+  topo.special_counts = atom->nspecial;
+  site.state = atom->ucgstate; site.lambda = atom->ucgl; site.flambda = atom->ucgforce; site.scores = atom->ucgsoftmaxscores;
+  site.vlambda = atom->ucgvl; site.prob = atom->ucgp; site.mlambda = atom->ucgml; site.nstates = atom->num_ucgstates;
 }
 void AtomVecUCG::force_clear(int n, size_t nbytes) {
-  memset(&ucgforce[n], 0, nbytes);
-  memset(&ucgsoftmaxscores[n][0], 0, atom->max_ucgstates * nbytes);
+  memset(&site.flambda[n], 0, nbytes);
+  memset(&site.scores[n][0], 0, atom->max_ucgstates * nbytes);
 }
 void AtomVecUCG::data_atom_post(int ilocal) {
-  num_bond[ilocal] = num_angle[ilocal] = num_dihedral[ilocal] = num_improper[ilocal] = 0;
-  nspecial[ilocal][0] = nspecial[ilocal][1] = nspecial[ilocal][2] = 0;
-  if (ucgl[ilocal] < 0) ucgl[ilocal] = 0.;
-  else if (ucgl[ilocal] > 1) ucgl[ilocal] = 1.;
-  if (ucgstate[ilocal] < 0) ucgstate[ilocal] = 0;
-  else if (ucgstate[ilocal] > 1) ucgstate[ilocal] = 1;
-  ucgp[ilocal] = -1.0;   // "unassigned" until the first force evaluation
+  topo.bonds[ilocal] = topo.angles[ilocal] = topo.dihedrals[ilocal] = topo.impropers[ilocal] = 0;
+  topo.special_counts[ilocal][0] = topo.special_counts[ilocal][1] = topo.special_counts[ilocal][2] = 0;
+  if (site.lambda[ilocal] < 0) site.lambda[ilocal] = 0.;
+  else if (site.lambda[ilocal] > 1) site.lambda[ilocal] = 1.;
+  if (site.state[ilocal] < 0) site.state[ilocal] = 0;
+  else if (site.state[ilocal] > 1) site.state[ilocal] = 1;
+  site.prob[ilocal] = -1.0;   // "unassigned" until the first force evaluation
 }
 int AtomVecUCG::property_atom(const std::string &name) {
   static const char *names[] = {"ucgstate", "ucgl", "ucgforce", "ucgvl", "ucgp", "ucgml"};
@@ -306,10 +306,10 @@ void AtomVecUCG::pack_property_atom(int index, double *buf, int nvalues, int gro
   if (index < 0 || index > 5) error->all(FLERR, "Unknown property_atom index in AtomVecUCG::pack_property_atom");
   const int *mask = atom->mask;
   const int nlocal = atom->nlocal;
-  const double *src[6] = {nullptr, ucgl, ucgforce, ucgvl, ucgp, ucgml};
+  const double *src[6] = {nullptr, site.lambda, site.flambda, site.vlambda, site.prob, site.mlambda};
   int n = 0;
   for (int j = 0; j < nlocal; j++, n += nvalues) {
     if (!(mask[j] & groupbit)) buf[n] = 0.0;
-    else buf[n] = index == 0 ? (double) ucgstate[j] : src[index][j];
+    else buf[n] = index == 0 ? (double) site.state[j] : src[index][j];
   }
 }
