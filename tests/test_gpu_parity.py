@@ -330,7 +330,7 @@ def test_full_size_properties_1M(pkg, fixtures):
     total, maxrow, _ = ctx.neigh_stats()
     assert 70 * liq.n < total < 85 * liq.n
     res = {}
-    for lpa, smem in ((8, 1), (32, 1), (8, 0)):
+    for lpa, smem in ((8, 1), (16, 1), (4, 1), (8, 0)):
         os.environ["UCGB200_LPA"] = str(lpa); os.environ["UCGB200_SMEM_TABLE"] = str(smem)
         ctx.pair_ucgld(1, 1)
         res[lpa, smem] = (ctx.pair_energy_virial(), ctx.atoms_download(["f", "ucgforce"]))
@@ -338,12 +338,64 @@ def test_full_size_properties_1M(pkg, fixtures):
     (e0, v0), a0 = res[8, 1]
     fscale = np.abs(a0["f"]).max()
     assert np.abs(a0["f"].sum(0)).max() < 1e-9 * fscale * np.sqrt(liq.n)
-    for key in ((32, 1), (8, 0)):
+    for key in ((16, 1), (4, 1), (8, 0)):
         (e, v), a = res[key]
         assert abs(e - e0) <= 1e-11 * abs(e0)
         assert rel_err(v, v0) <= 1e-10
         assert rel_err(a["f"], a0["f"]) <= 1e-11
     assert ctx.status()[0] == 0
+
+
+def test_full_size_density_styles_1M(pkg, fixtures, monkeypatch):
+    """the other pair styles at 1 M sites: the shared-memory-table kernels (persistent CTAs, transposed 16-byte row
+    fetches) and the general kernels (tables through L1, one table_eval per (state, state) table) are independent
+    code paths over the same rows and must agree to rounding"""
+    from lammps_ucg_dev_b200 import engine
+    liq = _liq(63)
+    ctx = decks.gpu_single_type(pkg, liq, fixtures)
+    ctx.pair_bethe_density_configure([0, 1], [0, 1], [0.0, 12.0], [0.0, 1.5])
+    ctx.neigh_build()
+
+    def both(fn, fields):
+        out = []
+        for general in ("0", "1"):
+            monkeypatch.setenv("UCGB200_FORCE_GENERAL", general)
+            fn()
+            out.append((ctx.pair_energy_virial(), ctx.atoms_download(fields)))
+        monkeypatch.setenv("UCGB200_FORCE_GENERAL", "0")
+        return out
+    for fn, fields in ((lambda: ctx.pair_bethe(1, 1, 1, 0, 2), ["f", "ucgsoftmaxscores"]),
+                       (lambda: ctx.pair_bethe_density(1, 1), ["f", "ucgp"])):
+        ((e0, v0), a0), ((e1, v1), a1) = both(fn, fields)
+        assert abs(e0 - e1) <= 1e-11 * abs(e0)
+        assert rel_err(v0, v1) <= 1e-10
+        for k in fields:
+            assert rel_err(a0[k], a1[k]) <= 1e-11, k
+        assert np.isfinite(a0["f"]).all()
+    assert ctx.status()[0] == 0
+    # rleucg (state types) on its own context
+    t = fixtures["table4096"]
+    c2 = pkg.Context(0)
+    c2.set_units(1.0, 1.0, 1.0)
+    c2.set_box(liq.box_lo, liq.box_hi)
+    idx = [engine.HostTable.from_file(t, k, 2.5, 1, 4096).upload(c2) for k in ("UCG_00", "UCG_01", "UCG_11")]
+    tabindex = np.zeros((3, 3), np.int32)
+    tabindex[1, 1], tabindex[1, 2], tabindex[2, 1], tabindex[2, 2] = idx[0], idx[1], idx[1], idx[2]
+    cutsq = np.zeros((3, 3)); cutsq[1:, 1:] = 2.5 ** 2
+    c2.pair_rleucg_configure(2, [0, 1, 1], 1, [0, 2], [0, 1], [0.0, 12.0], [0.0, 1.5], [0.0, 0.3, 0.0], tabindex, cutsq,
+                             [0.0, 1.0, 1.0], 1.0)
+    c2.neigh_configure(0.3)
+    engine.upload_liquid(c2, liq)
+    c2.neigh_build()
+    res = []
+    for general in ("0", "1"):
+        monkeypatch.setenv("UCGB200_FORCE_GENERAL", general)
+        c2.pair_rleucg(1, 1)
+        res.append((c2.pair_energy_virial(), c2.atoms_download(["f"])))
+    ((e0, v0), a0), ((e1, v1), a1) = res
+    assert abs(e0 - e1) <= 1e-11 * abs(e0) and rel_err(v0, v1) <= 1e-10 and rel_err(a0["f"], a1["f"]) <= 1e-11
+    # the pair part is symmetric, so the total force vanishes up to the CV back-force asymmetry of the style (Q17)
+    assert c2.status()[0] == 0
 
 
 # ---------------------------------------------------------------- pair bethe
