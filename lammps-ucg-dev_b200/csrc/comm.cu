@@ -253,6 +253,7 @@ int ucg_mb_decide(ucgb200_ctx *c, bool prechecked, int *rebuild) {
   cudaSetDevice(c->device);
   if (!prechecked) {
     UCG_CHECK(c, cudaMemsetAsync(c->d_flags.p, 0, sizeof(int), c->stream));
+    UCG_CHECK(c, cudaMemsetAsync(c->d_maxdisp.p, 0, sizeof(unsigned long long), c->stream));
     if (!c->list_valid) {
       const int one = 1;
       UCG_CHECK(c, cudaMemcpyAsync(c->d_flags.p, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -261,7 +262,13 @@ int ucg_mb_decide(ucgb200_ctx *c, bool prechecked, int *rebuild) {
       if (rc) return rc;
     }
   }
+  // one fused launch: the rebuild flag and the largest squared displacement of any site of any brick (the
+  // bound that lets the pair kernel skip skin entries must hold for ghosts owned by other bricks too)
+  UCG_NCCL(c, nccl().GroupStart());
   UCG_NCCL(c, nccl().AllReduce(c->d_flags.p, c->d_flags.p, 1, ncclInt32, ncclMax, s->comm, c->stream));
+  UCG_NCCL(c, nccl().AllReduce(c->d_maxdisp.p, c->d_maxdisp.p, 1, ncclUint64, ncclMax, s->comm, c->stream));
+  UCG_NCCL(c, nccl().GroupEnd());
+  c->maxdisp_valid = true;
   UCG_CHECK(c, cudaMemcpyAsync(c->h_flags, c->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   UCG_CHECK(c, cudaStreamSynchronize(c->stream));
   *rebuild = c->h_flags[0] ? 1 : 0;

@@ -29,6 +29,8 @@ extern "C" int ucgb200_create(int device, ucgb200_ctx **out) {
   c->d_err.ensure(1);
   cudaMemset(c->d_err.p, 0, sizeof(ErrWord));
   c->d_ev.ensure(32);
+  c->d_maxdisp.ensure(4);
+  cudaMemset(c->d_maxdisp.p, 0, 4 * sizeof(unsigned long long));
   cudaMemset(c->d_ev.p, 0, 32 * sizeof(double));
   *out = c;
   return 0;
@@ -56,7 +58,7 @@ extern "C" int ucgb200_destroy(ucgb200_ctx *c) {
   c->gcell_count.release(); c->gcell_start.release(); c->order.release(); c->cell_of.release();
   c->scan_tmp.release(); c->ghost_cnt.release(); c->ghost_off.release();
   c->neigh.release(); c->numneigh.release(); c->statebits.release(); c->d_flags.release();
-  c->stage_d.release(); c->stage_i.release();
+  c->stage_d.release(); c->stage_i.release(); c->levcnt.release(); c->d_maxdisp.release();
   c->d_partials.release(); c->d_ev.release(); c->d_err.release(); c->d_gfac.release();
   {
     auto &k = c->cluster;
@@ -461,7 +463,7 @@ extern "C" int ucgb200_atoms_upload(ucgb200_ctx *c, int nlocal, const ucgb200_at
   bool fresh = (nlocal != c->nlocal);
   if (fresh) {
     // a new atom count resets the device ordering; every array must come along
-    c->nlocal = nlocal; c->nghost = 0; c->list_valid = false;
+    c->nlocal = nlocal; c->nghost = 0; c->list_valid = false; c->maxdisp_valid = false;
     int rc = ensure_atom_capacity(c, (size_t)nlocal + nlocal / 4 + 1024, nlocal);
     if (rc) return rc;
     k_iota<<<GRID1(nlocal)>>>(c->orig.p, nlocal); UCG_LAUNCHED(c);
@@ -491,7 +493,7 @@ extern "C" int ucgb200_atoms_upload(ucgb200_ctx *c, int nlocal, const ucgb200_at
   const int *orig = c->orig.p;
 #define UP_D(ptr, cnt) UCG_CHECK(c, cudaMemcpyAsync(sd, (ptr), (cnt) * sizeof(double), cudaMemcpyHostToDevice, st))
 #define UP_I(ptr, cnt) UCG_CHECK(c, cudaMemcpyAsync(si, (ptr), (cnt) * sizeof(int), cudaMemcpyHostToDevice, st))
-  if ((fields & UCGB200_F_X) && h->x) { UP_D(h->x, 3 * n); k_pack_vec3<<<GRID1(nlocal)>>>(c->pos.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += 3 * n; c->list_valid = c->list_valid && !fresh; }
+  if ((fields & UCGB200_F_X) && h->x) { c->maxdisp_valid = false; UP_D(h->x, 3 * n); k_pack_vec3<<<GRID1(nlocal)>>>(c->pos.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += 3 * n; c->list_valid = c->list_valid && !fresh; }
   if ((fields & UCGB200_F_UCGL) && h->ucgl) { UP_D(h->ucgl, n); k_pack_w<<<GRID1(nlocal)>>>(c->pos.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += n; }
   if ((fields & UCGB200_F_V) && h->v) { UP_D(h->v, 3 * n); k_pack_vec3<<<GRID1(nlocal)>>>(c->vel.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += 3 * n; }
   if ((fields & UCGB200_F_UCGVL) && h->ucgvl) { UP_D(h->ucgvl, n); k_pack_w<<<GRID1(nlocal)>>>(c->vel.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += n; }

@@ -147,6 +147,7 @@ struct TailArgs {
   int fuse_next;       // also do the next step's initial_integrate + check_distance
   double triggersq;
   int *flags;
+  unsigned long long *maxdisp;
   unsigned long long step;
 };
 
@@ -219,7 +220,10 @@ __global__ void __launch_bounds__(256) k_step_tail(TailArgs a) {
       if (WALL) t = type | ((x.w < 0.5 ? 0 : 1) << 16);
     }
     const double4 h = a.xhold[i];                                         // k_check_distance
-    if (rsq_exact(x.x - h.x, x.y - h.y, x.z - h.z) > a.triggersq) a.flags[0] = 1;
+    const double moved = rsq_exact(x.x - h.x, x.y - h.y, x.z - h.z);
+    if (moved > a.triggersq) a.flags[0] = 1;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(moved);
+    if (bits > *a.maxdisp) atomicMax(a.maxdisp, bits);
   }
   if (ingroup) a.vel[i] = v;
   if (fdirty) a.frc[i] = f;
@@ -252,6 +256,7 @@ __global__ void __launch_bounds__(BS) k_kinetic(const double4 *__restrict__ vel,
 extern "C" int ucgb200_fix_nve_initial(ucgb200_ctx *c, double dtv, double dtf, int groupbit, int wall) {
   if (!c) return -1;
   cudaSetDevice(c->device);
+  c->maxdisp_valid = false;   // sites move: the displacement bound is stale until the next check_distance
   int rc = rebuild_maps(c);
   if (rc) return rc;
   if (c->nlocal == 0) return 0;
@@ -386,9 +391,13 @@ int ucg_step_tail(ucgb200_ctx *c, const ucgb200_deck &d, double tsqrt, int fuse_
   a.useed = (unsigned)d.ucgstate_seed; a.urate = d.ucgstate_rate;
   a.groupbit = d.nve_groupbit ? d.nve_groupbit : 1; a.bias = d.wall_bias; a.barrier = d.wall_barrier;
   a.dtv = c->dt; a.dtf = 0.5 * c->dt * c->ftm2v;
-  a.fuse_next = fuse_next; a.triggersq = 0.25 * c->skin * c->skin; a.flags = c->d_flags.p;
+  a.fuse_next = fuse_next; a.triggersq = 0.25 * c->skin * c->skin; a.flags = c->d_flags.p; a.maxdisp = c->d_maxdisp.p;
   a.step = (unsigned long long)c->ntimestep;
-  if (fuse_next) UCG_CHECK(c, cudaMemsetAsync(c->d_flags.p, 0, sizeof(int), c->stream));
+  if (fuse_next) {
+    UCG_CHECK(c, cudaMemsetAsync(c->d_flags.p, 0, sizeof(int), c->stream));
+    UCG_CHECK(c, cudaMemsetAsync(c->d_maxdisp.p, 0, sizeof(unsigned long long), c->stream));
+  }
+  c->maxdisp_valid = false;   // sites move (or not): valid again after the decide that follows
   if (d.nve == 2) k_step_tail<true><<<GRID1(c->nlocal)>>>(a);
   else k_step_tail<false><<<GRID1(c->nlocal)>>>(a);
   UCG_LAUNCHED(c);

