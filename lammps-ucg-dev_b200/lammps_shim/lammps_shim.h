@@ -36,7 +36,7 @@ typedef int MPI_Op;
 #define MPI_SUM 1
 #define MPI_MAX 2
 #define MPI_MIN 3
-static inline size_t shim_mpi_size(MPI_Datatype t) { return t == MPI_DOUBLE ? sizeof(double) : (t == MPI_INT ? sizeof(int) : 1); }
+static inline size_t shim_mpi_size(MPI_Datatype t) { return (t == MPI_DOUBLE || t == 4 /* MPI_LMP_BIGINT */) ? 8 : (t == MPI_INT ? sizeof(int) : 1); }
 static inline int MPI_Comm_rank(MPI_Comm, int *r) { *r = 0; return 0; }
 static inline int MPI_Comm_size(MPI_Comm, int *n) { *n = 1; return 0; }
 static inline int MPI_Bcast(void *, int, MPI_Datatype, int, MPI_Comm) { return 0; }
@@ -61,6 +61,10 @@ typedef int smallint;
 #define MIN(A, B) ((A) < (B) ? (A) : (B))
 #endif
 #define SBBITS 30
+#define IMGMASK 1023
+#define IMGMAX 512
+#define IMGBITS 10
+#define IMG2BITS 20
 #define NEIGHMASK 0x1FFFFFFF
 #define BIG_SHIM 1.0e20
 
@@ -104,6 +108,19 @@ template <class T>
 inline void one(std::ostringstream &os, const T &v) { os << v; }
 inline void one(std::ostringstream &os, const char *v) { os << (v ? v : "(null)"); }
 inline void one(std::ostringstream &os, char *v) { os << (v ? v : "(null)"); }
+// "{:>1.16e}" / "{:.16}" on a double: the fmt spec [align][width][.precision][type] as its printf twin
+// (no type letter = general format); anything else falls back to the stream form
+template <class T>
+inline void one_spec(std::ostringstream &os, const std::string &, const T &v) { one(os, v); }
+inline void one_spec(std::ostringstream &os, const std::string &spec, const double &v) {
+  std::string p = spec;
+  if (!p.empty() && (p[0] == '>' || p[0] == '<')) p = p.substr(1);
+  char type = 'g';
+  if (!p.empty() && isalpha((unsigned char)p.back())) { type = p.back(); p.pop_back(); }
+  char buf[128];
+  snprintf(buf, sizeof buf, ("%" + p + type).c_str(), v);
+  os << buf;
+}
 inline std::string format(const std::string &f) { return f; }
 template <class T, class... R>
 inline std::string format(const std::string &f, const T &v, const R &...rest) {
@@ -115,7 +132,7 @@ inline std::string format(const std::string &f, const T &v, const R &...rest) {
     size_t e = f.find('}', q);
     std::ostringstream os;
     os << f.substr(0, q);
-    one(os, v);
+    one_spec(os, f.substr(q + 2, e - q - 2), v);
     return os.str() + format(f.substr(e + 1), rest...);
   }
   std::ostringstream os;
@@ -172,6 +189,8 @@ class Memory {
     return realloc(p, (size_t)n);
   }
   void sfree(void *p) { free(p); }
+  template <class T>
+  double usage(T *, int n1, int n2 = 1, int n3 = 1) { return (double)sizeof(T) * n1 * n2 * n3; }
 
   template <class T>
   T *create(T *&a, int n, const char *name) {
@@ -550,6 +569,28 @@ class Atom : protected Pointers {
 
   int map_style = 0;
   int nextsort = 0, sortfreq = 0;
+
+  // members only the reference's patched I/O files touch (dump_custom.cpp, read_dump.cpp); never allocated here
+  enum { MAP_NONE = 0, MAP_ARRAY = 1, MAP_HASH = 2, MAP_YES = 3 };
+  int mu_flag = 0, radius_flag = 0, omega_flag = 0, angmom_flag = 0, torque_flag = 0, heatflow_flag = 0, temperature_flag = 0;
+  double **mu = nullptr, **omega = nullptr, **angmom = nullptr, **torque = nullptr;
+  double *radius = nullptr, *heatflow = nullptr, *temperature = nullptr;
+  int **ivector = nullptr, ***iarray = nullptr, *icols = nullptr, *dcols = nullptr;
+  double **dvector = nullptr, ***darray = nullptr;
+  class LabelMap *lmap = nullptr;
+  double **msucgl = nullptr, **msucgp = nullptr;
+  void data_fix_compute_variable(int, int) {}
+  int find_custom(const char *, int &, int &) { return -1; }
+  // global id -> local index map, [stock] Atom::map_* (serial: a hash over the owned atoms)
+  tagint map_tag_max = -1;
+  std::map<tagint, int> idmap;
+  void map_init(int = 1) { idmap.clear(); map_tag_max = -1; for (int i = 0; i < nlocal; i++) map_tag_max = MAX(map_tag_max, tag[i]); }
+  void map_clear() { idmap.clear(); }
+  void map_set() { for (int i = nlocal - 1; i >= 0; i--) idmap[tag[i]] = i; }
+  void map_delete() { idmap.clear(); }
+  int map(tagint id) { auto it = idmap.find(id); return it == idmap.end() ? -1 : it->second; }
+  void tag_check() {}
+  void tag_extend() {}
 };
 
 // --------------------------------------------------------------------------------- AtomVec
@@ -567,6 +608,11 @@ class AtomVec : protected Pointers {
   virtual void grow_pointers() {}
   virtual void force_clear(int, size_t) {}
   virtual void data_atom_post(int) {}
+  // implemented by the serial driver (it owns the per-atom storage)
+  void (*copy_hook)(void *, int, int) = nullptr;
+  void *hook_arg = nullptr;
+  void copy(int i, int j, int = 0) { if (copy_hook) copy_hook(hook_arg, i, j); }
+  virtual void create_atom(int, double *) {}
   virtual int property_atom(const std::string &) { return -1; }
   virtual void pack_property_atom(int, double *, int, int) {}
   void setup_fields() {
@@ -627,6 +673,7 @@ class Update : protected Pointers {
   char *integrate_style = (char *)"verlet";
   Integrate *integrate = nullptr;
   char *unit_style = (char *)"lj";
+  void reset_timestep(bigint n, bool = true) { ntimestep = n; }
 };
 
 class Compute : protected Pointers {
@@ -635,6 +682,11 @@ class Compute : protected Pointers {
   char *id = nullptr, *style = nullptr;
   int igroup = 0, groupbit = 1, tempflag = 0, tempbias = 0;
   double scalar = 0.0;
+  enum { INVOKED_NONE = 0, INVOKED_SCALAR = 1 << 0, INVOKED_VECTOR = 1 << 1, INVOKED_ARRAY = 1 << 2, INVOKED_PERATOM = 1 << 3 };
+  int peratom_flag = 0, size_peratom_cols = 0, invoked_flag = 0, initialized_flag = 1;
+  double *vector_atom = nullptr, **array_atom = nullptr;
+  bool is_initialized() const { return initialized_flag == 1; }
+  virtual void compute_peratom() {}
   virtual double compute_scalar() { return scalar; }
   virtual void remove_bias(int, double *) {}
   virtual void restore_bias(int, double *) {}
@@ -654,6 +706,8 @@ class Input : protected Pointers {
   explicit Input(LAMMPS *l) : Pointers(l), variable(new Variable(l)) {}
   ~Input() override { delete variable; }
   Variable *variable;
+  char **arg = nullptr;
+  int narg = 0;
 };
 class Output : protected Pointers {
  public:
@@ -697,6 +751,64 @@ class Domain : protected Pointers {
   void (*pbc_hook)(void *) = nullptr;
   void *hook_arg = nullptr;
   void pbc() { if (pbc_hook) pbc_hook(hook_arg); }
+
+  // what the reference's patched I/O files read: orthogonal boxes only, the triclinic members stay zero
+  int triclinic_general = 0, box_exist = 1;
+  void print_box(const std::string &) {}
+  int boundary[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+  double xy = 0, xz = 0, yz = 0;
+  double h[6] = {1, 1, 1, 0, 0, 0}, h_inv[6] = {1, 1, 1, 0, 0, 0};
+  double boxlo_lamda[3] = {0, 0, 0}, boxhi_lamda[3] = {1, 1, 1}, boxlo_bound[3] = {0, 0, 0}, boxhi_bound[3] = {1, 1, 1};
+  double avec[3] = {1, 0, 0}, bvec[3] = {0, 1, 0}, cvec[3] = {0, 0, 1};
+  void restricted_to_general_vector(double *) {}
+  void restricted_to_general_vector(double *, double *) {}
+  void restricted_to_general_coords(double *) {}
+  void restricted_to_general_coords(double *, double *) {}
+  class Region *get_region_by_id(const std::string &) { return nullptr; }
+  void boundary_string(char *str) {   // [stock] Domain::boundary_string: "pp pp pp" from boundary[][]
+    int m = 0;
+    for (int d = 0; d < 3; d++) {
+      for (int s = 0; s < 2; s++) str[m++] = "pfsm"[boundary[d][s]];
+      str[m++] = ' ';
+    }
+    str[8] = '\0';
+  }
+  // [stock] Domain::set_initial_box / set_global_box / set_local_box for an orthogonal box on one process
+  void set_initial_box(int = 1) {}
+  void set_global_box() {
+    for (int d = 0; d < 3; d++) prd[d] = boxhi[d] - boxlo[d];
+    xprd = prd[0]; yprd = prd[1]; zprd = prd[2];
+    h[0] = xprd; h[1] = yprd; h[2] = zprd;
+    h_inv[0] = 1.0 / h[0]; h_inv[1] = 1.0 / h[1]; h_inv[2] = 1.0 / h[2];
+  }
+  void set_local_box() { for (int d = 0; d < 3; d++) { sublo[d] = boxlo[d]; subhi[d] = boxhi[d]; } }
+  void reset_box() {}
+  void x2lamda(int) {}
+  void lamda2x(int) {}
+  // [stock] Domain::remap(x, image): wrap into the periodic box, counting the crossings in the image flags
+  void remap(double *x, imageint &image) {
+    const int per[3] = {xperiodic, yperiodic, zperiodic};
+    const int shift[3] = {0, IMGBITS, IMG2BITS};
+    for (int d = 0; d < 3; d++) {
+      if (!per[d]) continue;
+      imageint idim, otherdims;
+      while (x[d] < boxlo[d]) {
+        x[d] += prd[d];
+        idim = (image >> shift[d]) & IMGMASK;
+        otherdims = image ^ (idim << shift[d]);
+        idim--; idim &= IMGMASK;
+        image = otherdims | (idim << shift[d]);
+      }
+      while (x[d] >= boxhi[d]) {
+        x[d] -= prd[d];
+        idim = (image >> shift[d]) & IMGMASK;
+        otherdims = image ^ (idim << shift[d]);
+        idim++; idim &= IMGMASK;
+        image = otherdims | (idim << shift[d]);
+      }
+      x[d] = MAX(x[d], boxlo[d]);
+    }
+  }
 };
 
 // -------------------------------------------------------------------------------- Neighbor
@@ -774,6 +886,7 @@ class Comm : protected Pointers {
   void exchange() { if (hooks.exchange) hooks.exchange(hooks.arg); }
   void borders() { if (hooks.borders) hooks.borders(hooks.arg); }
   void setup() {}
+  void set_proc_grid(int = 1) {}
 };
 
 // ------------------------------------------------------------------------------------- Fix
@@ -887,6 +1000,12 @@ class Modify : protected Pointers {
     for (auto c : computes) if (c->id && id == c->id) return c;
     return nullptr;
   }
+  Fix *get_fix_by_id(const std::string &id) {
+    for (auto f : fixes) if (f->id && id == f->id) return f;
+    return nullptr;
+  }
+  Fix *add_fix(const std::string &, int = 1) { return nullptr; }
+  void delete_fix(const std::string &) {}
   void clearstep_compute() {}
   void addstep_compute(bigint) {}
   void pre_neighbor() { for (int i = 0; i < nfix; i++) if (fmask[i] & FixConst::PRE_NEIGHBOR) fix[i]->pre_neighbor(); }

@@ -13,8 +13,11 @@
 #include <memory>
 
 #include "lammps_shim.h"
+#include "lammps_shim_io.h"
 
 #include "atom_vec_ucg.h"
+#include "dump_custom.h"
+#include "read_dump.h"
 #include "fix_cluster_switch.h"
 #include "fix_nve_ucgld.h"
 #include "fix_nve_ucgld_wall_hard.h"
@@ -30,6 +33,45 @@ using namespace LAMMPS_NS;
 int Pair::instance_total = 0;
 
 namespace {
+
+// [stock] compute property/atom restricted to the names AtomVec::property_atom knows (the UCG taps,
+// atom_vec_ucg.cpp:172-234): compute_peratom() fills vector_atom / array_atom through the
+// reference's own AtomVecUCG::pack_property_atom
+class ComputePropertyAtomStub : public Compute {
+  std::vector<int> index;
+  int nvalues, nmax = 0;
+
+ public:
+  ComputePropertyAtomStub(LAMMPS *l, int narg, char **arg) : Compute(l) {
+    if (narg < 4) error->all(FLERR, "Illegal compute property/atom command");
+    id = utils::strdup(arg[0]);
+    igroup = l->group->find(arg[1]);
+    if (igroup == -1) error->all(FLERR, "Could not find compute group ID {}", arg[1]);
+    groupbit = l->group->bitmask[igroup];
+    style = utils::strdup(arg[2]);
+    nvalues = narg - 3;
+    for (int k = 3; k < narg; k++) {
+      int ix = atom->avec->property_atom(arg[k]);
+      if (ix < 0) error->all(FLERR, "Invalid keyword {} for atom style in compute property/atom command", arg[k]);
+      index.push_back(ix);
+    }
+    peratom_flag = 1;
+    size_peratom_cols = nvalues == 1 ? 0 : nvalues;
+  }
+  ~ComputePropertyAtomStub() override {
+    delete[] id; delete[] style;
+    memory->destroy(vector_atom); memory->destroy(array_atom);
+  }
+  void compute_peratom() override {
+    if (atom->nmax > nmax) {
+      nmax = atom->nmax;
+      if (nvalues == 1) { memory->destroy(vector_atom); memory->create(vector_atom, nmax, "property/atom:vector"); }
+      else { memory->destroy(array_atom); memory->create(array_atom, nmax, nvalues, "property/atom:array"); }
+    }
+    double *buf = nvalues == 1 ? vector_atom : (nmax > 0 ? &array_atom[0][0] : nullptr);
+    for (int n = 0; n < nvalues; n++) atom->avec->pack_property_atom(index[n], &buf[n], nvalues, groupbit);
+  }
+};
 
 // deterministic thermostat stand-in: exports t_target and nothing else
 class FixTTargetStub : public Fix {
@@ -60,6 +102,8 @@ struct Sim {
   int nbuilds = 0;
   double timers[4] = {0, 0, 0, 0};
   std::vector<Fix *> owned_fixes;
+  std::map<std::string, Dump *> dumps;
+  std::vector<Compute *> owned_computes;
   bool initialized = false;
   int eflag_last = 0;
 
@@ -95,8 +139,12 @@ struct Sim {
     h.forward_fix = [](void *a, Fix *f) { ((Sim *)a)->forward_comm_fix(f); };
     h.exchange = [](void *) {};
     h.borders = [](void *a) { ((Sim *)a)->borders(); };
+    lmp.atom->avec->hook_arg = this;
+    lmp.atom->avec->copy_hook = [](void *a, int i, int j) { ((Sim *)a)->copy_atom(i, j); };
   }
   ~Sim() {
+    for (auto &d : dumps) delete d.second;
+    for (auto c : owned_computes) delete c;
     for (auto f : owned_fixes) delete f;
     delete lmp.force->pair;
     delete lmp.atom->avec;
@@ -115,7 +163,7 @@ struct Sim {
     m->destroy(a->ucgstate); m->destroy(a->num_ucgstates); m->destroy(a->ucgl); m->destroy(a->ucgvl);
     m->destroy(a->ucgml); m->destroy(a->ucgp); m->destroy(a->ucgforce); m->destroy(a->ucgsoftmaxscores);
     m->destroy(a->num_bond); m->destroy(a->num_angle); m->destroy(a->num_dihedral); m->destroy(a->num_improper);
-    m->destroy(a->nspecial);
+    m->destroy(a->nspecial); m->destroy(a->image);
     delete[] a->mass; a->mass = nullptr;
   }
   void grow(int nmax) {
@@ -132,13 +180,28 @@ struct Sim {
     m->grow(a->ucgsoftmaxscores, nmax, a->max_ucgstates, "scores");
     m->grow(a->num_bond, nmax, "nb"); m->grow(a->num_angle, nmax, "na"); m->grow(a->num_dihedral, nmax, "nd");
     m->grow(a->num_improper, nmax, "ni"); m->grow(a->nspecial, nmax, 3, "nspecial");
+    m->grow(a->image, nmax, "image");
     for (int i = a->nmax; i < nmax; i++) {
+      a->image[i] = ((imageint)IMGMAX << IMG2BITS) | ((imageint)IMGMAX << IMGBITS) | IMGMAX;
       a->ucgforce[i] = 0; a->ucgsoftmaxscores[i][0] = a->ucgsoftmaxscores[i][1] = 0; a->num_ucgstates[i] = 0;
       a->ucgp[i] = 0; a->ucgvl[i] = 0; a->ucgml[i] = 1; a->q[i] = 0;
       for (int d = 0; d < 3; d++) a->f[i][d] = a->v[i][d] = 0;
     }
     a->nmax = nmax;
     a->avec->grow_pointers();
+  }
+
+  // [stock] AtomVec::copy(i, j): every per-atom field of fields_copy (+ the defaults x v tag type mask image)
+  void copy_atom(int i, int j) {
+    Atom *a = lmp.atom;
+    for (int k = 0; k < 3; k++) { a->x[j][k] = a->x[i][k]; a->v[j][k] = a->v[i][k]; a->f[j][k] = a->f[i][k]; a->nspecial[j][k] = a->nspecial[i][k]; }
+    a->tag[j] = a->tag[i]; a->type[j] = a->type[i]; a->mask[j] = a->mask[i]; a->image[j] = a->image[i];
+    a->molecule[j] = a->molecule[i]; a->q[j] = a->q[i];
+    a->ucgstate[j] = a->ucgstate[i]; a->num_ucgstates[j] = a->num_ucgstates[i]; a->ucgl[j] = a->ucgl[i];
+    a->ucgvl[j] = a->ucgvl[i]; a->ucgml[j] = a->ucgml[i]; a->ucgp[j] = a->ucgp[i]; a->ucgforce[j] = a->ucgforce[i];
+    a->ucgsoftmaxscores[j][0] = a->ucgsoftmaxscores[i][0]; a->ucgsoftmaxscores[j][1] = a->ucgsoftmaxscores[i][1];
+    a->num_bond[j] = a->num_bond[i]; a->num_angle[j] = a->num_angle[i]; a->num_dihedral[j] = a->num_dihedral[i];
+    a->num_improper[j] = a->num_improper[i];
   }
 
   // ---------------------------------------------------------------- domain / comm
@@ -504,6 +567,43 @@ struct Sim {
       // is whatever the allocator left; this presets it (quirk Q24)
       const int v = utils::inumeric(FLERR, w.at(1), false, &lmp);
       for (int i = 0; i < lmp.atom->nlocal + lmp.atom->nghost; i++) lmp.atom->num_ucgstates[i] = v;
+    } else if (cmd == "group") {
+      // harness-only: "group NAME" registers the next free group bit; masks come in through ref_atoms
+      if (lmp.group->find(w.at(1)) < 0) lmp.group->names[lmp.group->ngroup++] = utils::strdup(w.at(1));
+    } else if (cmd == "compute") {
+      if (w.at(3) != "property/atom") lmp.error->all(FLERR, "Unrecognized compute style '{}'", w.at(3));
+      Compute *c = new ComputePropertyAtomStub(&lmp, narg, arg.data());
+      owned_computes.push_back(c);
+      lmp.modify->computes.push_back(c);
+    } else if (cmd == "dump") {
+      // dump ID group custom N file args   ([stock] Output::add_dump); the reference's patched DumpCustom
+      if (w.at(3) != "custom") lmp.error->all(FLERR, "Unrecognized dump style '{}'", w.at(3));
+      if (dumps.count(w.at(1))) lmp.error->all(FLERR, "Reuse of dump ID: {}", w.at(1));
+      lmp.input->arg = arg.data(); lmp.input->narg = narg;
+      dumps[w.at(1)] = new DumpCustom(&lmp, narg, arg.data());
+    } else if (cmd == "dump_modify") {
+      auto it = dumps.find(w.at(1));
+      if (it == dumps.end()) lmp.error->all(FLERR, "Could not find dump_modify ID: {}", w.at(1));
+      it->second->modify_params(narg - 1, arg.data() + 1);
+    } else if (cmd == "dump_write") {
+      // harness-only: what [stock] Output::write does on a dump step (computes are cleared, init, write)
+      auto it = dumps.find(w.at(1));
+      if (it == dumps.end()) lmp.error->all(FLERR, "Could not find dump ID: {}", w.at(1));
+      for (auto c : lmp.modify->computes) c->invoked_flag = 0;
+      it->second->init();
+      it->second->write();
+    } else if (cmd == "undump") {
+      auto it = dumps.find(w.at(1));
+      if (it == dumps.end()) lmp.error->all(FLERR, "Could not find undump ID: {}", w.at(1));
+      delete it->second;
+      dumps.erase(it);
+    } else if (cmd == "read_dump") {
+      lmp.atom->map_style = Atom::MAP_YES;   // molecular atom styles keep an id map
+      lmp.atom->map_init(); lmp.atom->map_set();
+      ReadDump rd(&lmp);
+      rd.command(narg, arg.data());
+      lmp.atom->nghost = 0;
+      initialized = false;
     } else if (cmd == "mass") {
       int t = utils::inumeric(FLERR, w.at(1), false, &lmp);
       if (t < 1 || t > lmp.atom->ntypes) lmp.error->all(FLERR, "Invalid type for mass set");
@@ -542,6 +642,7 @@ int ref_box(void *h, const double *lo, const double *hi, int ntypes) {
       d->boxlo[k] = d->sublo[k] = lo[k]; d->boxhi[k] = d->subhi[k] = hi[k]; d->prd[k] = hi[k] - lo[k];
     }
     d->xprd = d->prd[0]; d->yprd = d->prd[1]; d->zprd = d->prd[2];
+    d->set_global_box();
     s->lmp.atom->ntypes = ntypes;
     delete[] s->lmp.atom->mass;
     s->lmp.atom->mass = new double[ntypes + 1];
@@ -596,6 +697,23 @@ int ref_command(void *h, const char *line) {
   Sim *s = (Sim *)h;
   return guarded(s, [&] { s->command(line); });
 }
+// image flags (ix, iy, iz) and the current box, for the read_dump / dump checks
+int ref_get_image(void *h, int *ix, int *iy, int *iz, int *mask, int *molecule) {
+  Atom *a = ((Sim *)h)->lmp.atom;
+  for (int i = 0; i < a->nlocal; i++) {
+    if (ix) ix[i] = (a->image[i] & IMGMASK) - IMGMAX;
+    if (iy) iy[i] = (a->image[i] >> IMGBITS & IMGMASK) - IMGMAX;
+    if (iz) iz[i] = (a->image[i] >> IMG2BITS) - IMGMAX;
+    if (mask) mask[i] = a->mask[i];
+    if (molecule) molecule[i] = a->molecule[i];
+  }
+  return 0;
+}
+void ref_get_box(void *h, double *lo, double *hi) {
+  Domain *d = ((Sim *)h)->lmp.domain;
+  for (int k = 0; k < 3; k++) { lo[k] = d->boxlo[k]; hi[k] = d->boxhi[k]; }
+}
+void ref_set_ntimestep(void *h, long long n) { ((Sim *)h)->lmp.update->ntimestep = n; }
 int ref_nlocal(void *h) { return ((Sim *)h)->lmp.atom->nlocal; }
 int ref_nghost(void *h) { return ((Sim *)h)->lmp.atom->nghost; }
 int ref_get_atoms(void *h, double *x, double *v, double *f, int *type, int *tag, int *ucgstate, double *ucgl,
