@@ -92,6 +92,7 @@ long long ucgb200_launch_count(const ucgb200_ctx *ctx);
 int ucgb200_set_units(ucgb200_ctx *ctx, double boltz, double ftm2v, double mvv2e);
 /* domain->boxlo/boxhi/periodicity [stock Domain]; orthogonal boxes only */
 int ucgb200_set_box(ucgb200_ctx *ctx, const double lo[3], const double hi[3], const int periodic[3]);
+int ucgb200_get_box(const ucgb200_ctx *ctx, double lo[3], double hi[3], int periodic[3]);
 /* sub-domain owned by this context (multi-GPU brick); defaults to the box */
 int ucgb200_set_subdomain(ucgb200_ctx *ctx, const double sublo[3], const double subhi[3]);
 /* update->dt */
@@ -324,6 +325,89 @@ int ucgb200_comm_unique_id(char *id, int len);
 int ucgb200_comm_init(ucgb200_ctx *ctx, const char *id, int len);
 int ucgb200_comm_destroy(ucgb200_ctx *ctx);
 int ucgb200_comm_stats(ucgb200_ctx *ctx, long long *bytes_forward, int *nrebuilds, int *send_records);
+
+/* ------------------------------------------------------ dump / read_dump taps */
+/* Column codes: the `dump custom` keywords the reference's patched dump_custom.cpp adds
+ * (ucgstate ucgl ucgp, dump_custom.cpp:1672-1687, 3552-3577), the stock per-atom keywords around
+ * them, and the `compute property/atom` names of AtomVecUCG::property_atom
+ * (UCG/atom_vec_ucg.cpp:172-181; those columns are zero outside the COMPUTE's group, :184-231).
+ * The same codes name the fields of a read_dump snapshot (reader.h:24-26, read_dump.cpp:1326-1352). */
+#define UCGB200_COL_ID 0
+#define UCGB200_COL_MOL 1
+#define UCGB200_COL_TYPE 2
+#define UCGB200_COL_MASS 3
+#define UCGB200_COL_X 4
+#define UCGB200_COL_Y 5
+#define UCGB200_COL_Z 6
+#define UCGB200_COL_XS 7
+#define UCGB200_COL_YS 8
+#define UCGB200_COL_ZS 9
+#define UCGB200_COL_VX 10
+#define UCGB200_COL_VY 11
+#define UCGB200_COL_VZ 12
+#define UCGB200_COL_FX 13
+#define UCGB200_COL_FY 14
+#define UCGB200_COL_FZ 15
+#define UCGB200_COL_UCGSTATE 16
+#define UCGB200_COL_UCGL 17
+#define UCGB200_COL_UCGP 18
+#define UCGB200_COL_PROC 19
+#define UCGB200_COL_Q 20            /* atom_style ucg carries q but no UCG style reads it: always 0 */
+#define UCGB200_COL_P_UCGSTATE 21   /* compute property/atom ... (index 0..5 of property_atom) */
+#define UCGB200_COL_P_UCGL 22
+#define UCGB200_COL_P_UCGFORCE 23
+#define UCGB200_COL_P_UCGVL 24
+#define UCGB200_COL_P_UCGP 25
+#define UCGB200_COL_P_UCGML 26
+#define UCGB200_COL_COUNT 27
+#define UCGB200_DUMP_MAXCOL 32
+#define UCGB200_DUMP_MAXTHRESH 8
+/* dump_modify thresh operators, enum{LT,LE,GT,GE,EQ,NEQ,XOR} dump_custom.cpp:50 */
+#define UCGB200_THRESH_LT 0
+#define UCGB200_THRESH_LE 1
+#define UCGB200_THRESH_GT 2
+#define UCGB200_THRESH_GE 3
+#define UCGB200_THRESH_EQ 4
+#define UCGB200_THRESH_NEQ 5
+#define UCGB200_THRESH_XOR 6
+/* row order: the host index order an unsorted serial dump has, or `dump_modify sort id` */
+#define UCGB200_DUMP_ORDER_INDEX 0
+#define UCGB200_DUMP_ORDER_ID 1
+
+typedef struct ucgb200_dump_spec {
+  int ncols;
+  const int *cols;          /* [ncols] UCGB200_COL_* */
+  const int *col_groupbit;  /* [ncols] group bit of the compute behind a P_* column (NULL = all) */
+  int groupbit;             /* the dump's group */
+  int nthresh;              /* dump_modify thresh: attribute (a non-P column code), operator, value */
+  const int *thresh_col;
+  const int *thresh_op;
+  const double *thresh_value;
+  int order;                /* UCGB200_DUMP_ORDER_* */
+} ucgb200_dump_spec;
+
+/* DumpCustom::count(): number of owned atoms in the group that pass every threshold (dump_custom.cpp:721-1368) */
+int ucgb200_dump_count(ucgb200_ctx *ctx, const ucgb200_dump_spec *spec, long long *nrows);
+/* DumpCustom::count() + pack() (+ Dump::sort): selection, ordering and the column gather run on the
+ * device; buf[row * ncols + col] receives what DumpCustom::buf holds (ints as exactly converted doubles) */
+int ucgb200_dump_pack(ucgb200_ctx *ctx, const ucgb200_dump_spec *spec, double *buf, long long capacity_rows,
+                      long long *nrows);
+/* The same rows as TEXT, formatted on the device exactly as DumpCustom::convert_string / write_lines
+ * do with the default formats (dump_custom.cpp:1388-1468: "%d" for id mol type proc ucgstate, "%g" for the
+ * rest, one blank between columns, none before the newline).  Only nbytes characters cross PCIe. */
+int ucgb200_dump_text(ucgb200_ctx *ctx, const ucgb200_dump_spec *spec, char *text, long long capacity_bytes,
+                      long long *nrows, long long *nbytes);
+/* text == NULL above formats on the device and reports the size; this fetches the characters */
+int ucgb200_dump_text_copy(ucgb200_ctx *ctx, char *text, long long capacity_bytes);
+/* ReadDump::process_atoms in replace mode + the remap of migrate_atoms_by_coords (read_dump.cpp:797-935,
+ * 1150-1163): fields[i * nfield + j] is the snapshot as Reader::read_atoms leaves it, fieldtype[0] must be
+ * UCGB200_COL_ID; rows whose id matches an owned atom overwrite x y z (unscaled with the SNAPSHOT box when
+ * `scaled`), vx vy vz, fx fy fz, ucgstate, ucgl, ucgp of that atom; positions are then wrapped into the
+ * CURRENT box (ucgb200_set_box first for `box yes`).  updated[nlocal] (host index order, may be NULL)
+ * receives the updateflag array `trim` works from; *nreplace counts the matches. */
+int ucgb200_atoms_update_by_tag(ucgb200_ctx *ctx, int nnew, int nfield, const int *fieldtype, const double *fields,
+                                int scaled, const double snap_lo[3], const double snap_hi[3], int *updated,
+                                long long *nreplace);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,43 @@ int ucgb200_host_statemap_get(const ucgb200_statemap *m, int *n_states, int *for
 /* set_types + set_pair_maps on a context; mass[1..n_formal] = atom->mass */
 int ucgb200_host_statemap_apply(ucgb200_ctx *ctx, const ucgb200_statemap *m, const double *mass);
 
+/* ------------------------------------------------- dump custom / read_dump / read_data
+ * Host halves of the taps around the resident step, with the reference's grammar and file formats
+ * (dump_custom.cpp, read_dump.cpp, reader_native.cpp — the patched stock files of the reference tree — and the
+ * data-file columns of UCG/atom_vec_ucg.cpp:85-90).  The rows themselves are selected, ordered, gathered
+ * and — with the default formats — turned into text on the device (ucgb200_dump_pack / _dump_text). */
+typedef struct ucgb200_dump ucgb200_dump;
+typedef struct ucgb200_data ucgb200_data;
+
+/* `dump ID group custom N file col ...`: arg[0..narg) are the words after "dump"; groupbit is the bit of `group`.
+ * Columns: id mol type mass x y z xs ys zs vx vy vz fx fy fz q proc ucgstate ucgl ucgp, c_ID / c_ID[k]. */
+int ucgb200_host_dump_create(int narg, const char *const *arg, int groupbit, ucgb200_dump **out, char *errbuf, int errlen);
+void ucgb200_host_dump_free(ucgb200_dump *d);
+/* `compute ID group property/atom name ...` (names of AtomVecUCG::property_atom, atom_vec_ucg.cpp:172-181):
+ * resolves the dump's c_ID / c_ID[k] columns, as DumpCustom::init_style does by compute ID */
+int ucgb200_host_dump_bind_compute(ucgb200_dump *d, const char *id, int groupbit, int nvalues, const char *const *names,
+                                   char *errbuf, int errlen);
+/* `dump_modify ID keyword value ...` (words after the ID): append buffer every flush header pad time units,
+ * sort off|id, format line|int|float|M|none, thresh attribute op value | none */
+int ucgb200_host_dump_modify(ucgb200_dump *d, int narg, const char *const *arg, char *errbuf, int errlen);
+/* Dump::write() of one snapshot of the context's resident atoms */
+int ucgb200_host_dump_write(ucgb200_dump *d, ucgb200_ctx *ctx, long long ntimestep, double time, const char *unit_style,
+                            char *errbuf, int errlen);
+int ucgb200_host_dump_stats(const ucgb200_dump *d, long long *rows, long long *bytes, int *nevery);
+
+/* `read_dump file Nstep field ... keyword value ...` on the resident atoms (native text dump files):
+ * fields x y z vx vy vz fx fy fz q ucgstate ucgl ucgp; keywords box timestep replace trim label scaled wrapped
+ * format native (purge / add are not supported).  stats[7] = atoms before, in snapshot, purged, replaced,
+ * trimmed, added, after — the lines the reference logs (read_dump.cpp:143-151). */
+int ucgb200_host_read_dump(ucgb200_ctx *ctx, int narg, const char *const *arg, long long stats[7], char *errbuf, int errlen);
+
+/* A data file of atom_style ucg (header, Masses, Atoms, Velocities) -> arrays, data_atom_post applied */
+int ucgb200_host_data_read(const char *file, ucgb200_data **out, char *errbuf, int errlen);
+void ucgb200_host_data_free(ucgb200_data *d);
+int ucgb200_host_data_info(const ucgb200_data *d, long long *natoms, int *ntypes, double lo[3], double hi[3]);
+int ucgb200_host_data_view(ucgb200_data *d, ucgb200_atoms *view, const double **q, const int **image, const double **mass);
+int ucgb200_host_data_upload(ucgb200_ctx *ctx, ucgb200_data *d, const int periodic[3]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,7 @@ extern "C" int ucgb200_destroy(ucgb200_ctx *c) {
   c->gcell_count.release(); c->gcell_start.release(); c->order.release(); c->cell_of.release();
   c->scan_tmp.release(); c->ghost_cnt.release(); c->ghost_off.release();
   c->neigh.release(); c->numneigh.release(); c->statebits.release(); c->d_flags.release();
+  c->dump_keys.release(); c->dump_sites.release(); c->dump_tmp.release(); c->dump_text.release(); c->dump_buf.release(); c->dump_off.release(); c->dump_slots.release();
   c->stage_d.release(); c->stage_i.release(); c->levcnt.release(); c->d_maxdisp.release();
   c->d_partials.release(); c->d_ev.release(); c->d_err.release(); c->d_gfac.release();
   {
@@ -109,6 +110,15 @@ extern "C" int ucgb200_set_box(ucgb200_ctx *c, const double lo[3], const double 
     if (!c->sub_set) { c->sublo[d] = lo[d]; c->subhi[d] = hi[d]; }
   }
   c->list_valid = false;
+  return 0;
+}
+extern "C" int ucgb200_get_box(const ucgb200_ctx *c, double lo[3], double hi[3], int periodic[3]) {
+  if (!c) return -1;
+  for (int d = 0; d < 3; d++) {
+    if (lo) lo[d] = c->boxlo[d];
+    if (hi) hi[d] = c->boxhi[d];
+    if (periodic) periodic[d] = c->periodic[d];
+  }
   return 0;
 }
 extern "C" int ucgb200_set_subdomain(ucgb200_ctx *c, const double sublo[3], const double subhi[3]) {

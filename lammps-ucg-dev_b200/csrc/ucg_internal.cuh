@@ -143,6 +143,14 @@ struct ucgb200_ctx {
   ucg::Buf<double2> scores, scores_alt;
   ucg::Buf<double> ucgp, ucgp_alt, ucgml, ucgml_alt;
   ucg::Buf<double> stage_d;   // host<->device staging of atoms_upload / atoms_download
+  // dump.cu: sort keys / chosen sites / radix-sort scratch / packed rows (and formatted text) of a dump
+  ucg::Buf<unsigned> dump_keys;
+  ucg::Buf<int> dump_sites;
+  ucg::Buf<char> dump_tmp, dump_text;
+  ucg::Buf<double> dump_buf;
+  ucg::Buf<long long> dump_off;
+  ucg::Buf<uint4> dump_slots;
+  long long dump_text_bytes = 0;
   ucg::Buf<int> stage_i;
   ucg::Buf<int> ts, ts_alt, mask, mask_alt, tag, tag_alt, mol, mol_alt, orig, orig_alt;
   // ghosts: sources = local periodic images + border records received from other bricks
@@ -331,6 +339,7 @@ int exclusive_scan(ucgb200_ctx *c, const int *in, int *out, int n, int *d_total)
 int reduce_partials(ucgb200_ctx *c, int nblocks, int nvals, int out_offset);
 int ucg_check_distance_launch(ucgb200_ctx *c);
 }  // namespace ucg
+int ucg_dump_pack_device(ucgb200_ctx *c, const ucgb200_dump_spec *sp, long long *nrows);   // dump.cu
 int ucg_mb_forward_scalars(ucgb200_ctx *c, double *a0, double *a1, double *a2);   // comm.cu
 int ucg_mb_allreduce_int(ucgb200_ctx *c, int *d_buf, int n, int op);
 // context.cu: texture objects over pos / ts of the current buffers (0 when UCGB200_TEX=0)

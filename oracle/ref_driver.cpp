@@ -514,10 +514,23 @@ struct Sim {
   // ---------------------------------------------------------------- input lines
   void command(const std::string &line) {
     std::vector<std::string> w;
-    {
-      std::istringstream is(line);
-      std::string t;
-      while (is >> t) w.push_back(t);
+    {   // blank-separated words; a double-quoted string is one word ([stock] Input::parse)
+      size_t p = 0;
+      while (p < line.size()) {
+        while (p < line.size() && isspace((unsigned char)line[p])) p++;
+        if (p >= line.size()) break;
+        if (line[p] == '"') {
+          size_t e = line.find('"', p + 1);
+          if (e == std::string::npos) lmp.error->all(FLERR, "Unbalanced quotes in input line");
+          w.push_back(line.substr(p + 1, e - p - 1));
+          p = e + 1;
+        } else {
+          size_t e = p;
+          while (e < line.size() && !isspace((unsigned char)line[e])) e++;
+          w.push_back(line.substr(p, e - p));
+          p = e;
+        }
+      }
     }
     if (w.empty()) return;
     std::vector<char *> arg;
