@@ -408,6 +408,9 @@ int ucgb200_dump_text_copy(ucgb200_ctx *ctx, char *text, long long capacity_byte
 int ucgb200_atoms_update_by_tag(ucgb200_ctx *ctx, int nnew, int nfield, const int *fieldtype, const double *fields,
                                 int scaled, const double snap_lo[3], const double snap_hi[3], int *updated,
                                 long long *nreplace);
+/* Domain::remap of every owned atom into the current periodic box, any number of periods
+ * (ReadDump::migrate_atoms_by_coords, read_dump.cpp:1150-1163); invalidates the neighbor list */
+int ucgb200_atoms_remap(ucgb200_ctx *ctx);
 
 #ifdef __cplusplus
 }

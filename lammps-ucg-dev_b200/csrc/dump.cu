@@ -386,6 +386,23 @@ __global__ void k_update_by_tag(UpdateArgs a, const double *__restrict__ fields,
   a.pos[s] = r; a.vel[s] = v; a.frc[s] = f;
 }
 
+// ReadDump::migrate_atoms_by_coords (read_dump.cpp:1150-1163): Domain::remap of EVERY owned atom into the current box
+__global__ void k_remap_all(double4 *__restrict__ pos, int n, UpdateArgs a) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  double4 r = pos[s];
+  double x[3] = {r.x, r.y, r.z};
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    if (!a.periodic[d]) continue;
+    while (x[d] < a.boxlo[d]) x[d] += a.prd[d];
+    while (x[d] >= a.boxhi[d]) x[d] -= a.prd[d];
+    x[d] = fmax(x[d], a.boxlo[d]);
+  }
+  r.x = x[0]; r.y = x[1]; r.z = x[2];
+  pos[s] = r;
+}
+
 __global__ void k_tag_keys(const int *__restrict__ tag, int n, unsigned *__restrict__ keys, int *__restrict__ vals) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < n) { keys[s] = (unsigned)tag[s]; vals[s] = s; }
@@ -447,5 +464,19 @@ extern "C" int ucgb200_atoms_update_by_tag(ucgb200_ctx *c, int nnew, int nfield,
   UCG_CHECK(c, cudaStreamSynchronize(st));
   if (nreplace) *nreplace = cnt;
   if (moves) { c->list_valid = false; c->maxdisp_valid = false; }
+  return 0;
+}
+
+extern "C" int ucgb200_atoms_remap(ucgb200_ctx *c) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  if (c->nlocal == 0) return 0;
+  UpdateArgs a;
+  memset(&a, 0, sizeof a);
+  for (int d = 0; d < 3; d++) { a.boxlo[d] = c->boxlo[d]; a.boxhi[d] = c->boxhi[d]; a.prd[d] = c->prd[d]; a.periodic[d] = c->periodic[d]; }
+  k_remap_all<<<nblocks(c->nlocal, 256), 256, 0, c->stream>>>(c->pos.p, c->nlocal, a);
+  UCG_LAUNCHED(c);
+  c->list_valid = false;
+  c->maxdisp_valid = false;
   return 0;
 }

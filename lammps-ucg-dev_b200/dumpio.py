@@ -8,6 +8,7 @@ UCG/atom_vec_ucg.cpp:85-90, 145-234.
 from __future__ import annotations
 
 import ctypes as C
+import shlex
 from typing import Optional, Sequence
 
 import numpy as np
@@ -96,7 +97,7 @@ class DumpCustom:
 
     def __init__(self, ctx: Context, line: str, groupbit: int = 1):
         self.ctx, self._l = ctx, lib()
-        words = line.split()
+        words = shlex.split(line)
         if words and words[0] == "dump":
             words = words[1:]
         self._h = C.c_void_p()
@@ -122,7 +123,7 @@ class DumpCustom:
 
     def bind_compute(self, line: str, groupbit: int = 1):
         """`compute ID group property/atom name ...`"""
-        w = line.split()
+        w = shlex.split(line)
         if w and w[0] == "compute":
             w = w[1:]
         if len(w) < 4 or w[2] != "property/atom":
@@ -131,7 +132,7 @@ class DumpCustom:
         self._call(self._l.ucgb200_host_dump_bind_compute, w[0].encode(), int(groupbit), len(names), _argv(names))
 
     def modify(self, line: str):
-        w = line.split()
+        w = shlex.split(line)   # a quoted format line is one word, as in a LAMMPS deck
         if w and w[0] == "dump_modify":
             w = w[2:]
         self._call(self._l.ucgb200_host_dump_modify, len(w), _argv(w))
@@ -147,7 +148,7 @@ class DumpCustom:
 
 def read_dump(ctx: Context, line: str) -> dict:
     """`read_dump file Nstep field ... keyword value ...` applied to the resident atoms"""
-    w = line.split()
+    w = shlex.split(line)
     if w and w[0] == "read_dump":
         w = w[1:]
     stats = (C.c_longlong * 7)()

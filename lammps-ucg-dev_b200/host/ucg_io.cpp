@@ -639,6 +639,8 @@ extern "C" int ucgb200_host_read_dump(ucgb200_ctx *ctx, int narg, const char *co
         throw IoError("read_dump: " + ctx_error(ctx));
       if (!replaceflag) nreplace = 0;
     }
+    // migrate_atoms_by_coords: every atom, replaced or not, is wrapped into the (possibly new) box
+    if (ucgb200_atoms_remap(ctx)) throw IoError("read_dump: " + ctx_error(ctx));
     int nafter = nbefore;
     if (trimflag) {
       // ReadDump::process_atoms :919-935: `avec->copy(nlocal-1,i)` into every hole, same resulting order
