@@ -25,6 +25,7 @@
  */
 #ifndef UCGB200_H
 #define UCGB200_H
+#include <stddef.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -92,6 +93,9 @@ long long ucgb200_launch_count(const ucgb200_ctx *ctx);
 int ucgb200_set_units(ucgb200_ctx *ctx, double boltz, double ftm2v, double mvv2e);
 /* domain->boxlo/boxhi/periodicity [stock Domain]; orthogonal boxes only */
 int ucgb200_set_box(ucgb200_ctx *ctx, const double lo[3], const double hi[3], const int periodic[3]);
+/* page-locked host memory for callers that stage large downloads (dump rows / text) */
+int ucgb200_pinned_alloc(size_t bytes, void **out);
+int ucgb200_pinned_free(void *p);
 int ucgb200_get_box(const ucgb200_ctx *ctx, double lo[3], double hi[3], int periodic[3]);
 /* sub-domain owned by this context (multi-GPU brick); defaults to the box */
 int ucgb200_set_subdomain(ucgb200_ctx *ctx, const double sublo[3], const double subhi[3]);

@@ -112,6 +112,16 @@ extern "C" int ucgb200_set_box(ucgb200_ctx *c, const double lo[3], const double 
   c->list_valid = false;
   return 0;
 }
+// page-locked host staging for the host layer above the C-ABI (dump text / packed rows): D2H copies into it run as DMA
+extern "C" int ucgb200_pinned_alloc(size_t bytes, void **out) {
+  if (!out) return -1;
+  *out = nullptr;
+  return cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? 0 : -2;
+}
+extern "C" int ucgb200_pinned_free(void *p) {
+  if (p) cudaFreeHost(p);
+  return 0;
+}
 extern "C" int ucgb200_get_box(const ucgb200_ctx *c, double lo[3], double hi[3], int periodic[3]) {
   if (!c) return -1;
   for (int d = 0; d < 3; d++) {

@@ -139,7 +139,7 @@ int fill_args(ucgb200_ctx *c, const ucgb200_dump_spec *sp, DumpArgs &a) {
   }
   a.nthresh = sp->nthresh;
   for (int t = 0; t < sp->nthresh; t++) {
-    if (sp->thresh_col[t] < 0 || sp->thresh_col[t] >= UCGB200_COL_P_UCGSTATE) return fail(c, "dump: threshold on an unknown attribute");
+    if (sp->thresh_col[t] < 0 || sp->thresh_col[t] >= UCGB200_COL_COUNT) return fail(c, "dump: threshold on an unknown attribute");
     if (sp->thresh_op[t] < 0 || sp->thresh_op[t] > UCGB200_THRESH_XOR) return fail(c, "dump: unknown threshold operation");
     a.tcol[t] = sp->thresh_col[t]; a.top[t] = sp->thresh_op[t]; a.tval[t] = sp->thresh_value[t];
   }

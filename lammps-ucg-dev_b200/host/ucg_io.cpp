@@ -23,6 +23,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ucgb200_host.h"
@@ -68,6 +69,55 @@ int logical(const std::string &s) {
   throw IoError("Expected boolean parameter instead of '" + s + "' in input script or data file");
 }
 
+// page-locked staging that grows geometrically (falls back to pageable memory if pinning fails)
+struct Staging {
+  char *p = nullptr;
+  size_t cap = 0;
+  bool pinned = false;
+  ~Staging() { release(); }
+  void release() {
+    if (p) { if (pinned) ucgb200_pinned_free(p); else free(p); }
+    p = nullptr; cap = 0;
+  }
+  char *ensure(size_t n) {
+    if (n <= cap) return p;
+    release();
+    size_t want = n + n / 4 + 4096;
+    void *q = nullptr;
+    if (ucgb200_pinned_alloc(want, &q) == 0 && q) { p = (char *)q; pinned = true; }
+    else { p = (char *)malloc(want); pinned = false; if (!p) throw IoError("out of host memory"); }
+    cap = want;
+    return p;
+  }
+};
+
+// [0, n) split into contiguous chunks over the host cores (UCGB200_IO_THREADS overrides the count)
+template <class F>
+void parallel_chunks(long long n, long long min_chunk, F &&fn) {
+  int nt = (int)std::thread::hardware_concurrency();
+  if (const char *e = getenv("UCGB200_IO_THREADS")) nt = atoi(e);
+  if (nt < 1) nt = 1;
+  if (nt > 64) nt = 64;
+  if ((long long)nt * min_chunk > n) nt = (int)std::max<long long>(1, n / std::max<long long>(1, min_chunk));
+  if (nt <= 1) { fn(0, 0LL, n); return; }
+  std::vector<std::thread> th;
+  std::vector<std::string> errs(nt);
+  for (int t = 0; t < nt; t++) {
+    const long long b = n * t / nt, e = n * (t + 1) / nt;
+    th.emplace_back([&, t, b, e] { try { fn(t, b, e); } catch (const std::exception &x) { errs[t] = x.what(); } });
+  }
+  for (auto &x : th) x.join();
+  for (auto &m : errs) if (!m.empty()) throw IoError(m);
+}
+int chunk_count(long long n, long long min_chunk) {
+  int nt = (int)std::thread::hardware_concurrency();
+  if (const char *e = getenv("UCGB200_IO_THREADS")) nt = atoi(e);
+  if (nt < 1) nt = 1;
+  if (nt > 64) nt = 64;
+  if ((long long)nt * min_chunk > n) nt = (int)std::max<long long>(1, n / std::max<long long>(1, min_chunk));
+  return nt;
+}
+
 // ------------------------------------------------------------------------------------ columns
 struct Keyword { const char *name; int code; };
 const Keyword DUMP_KEYWORDS[] = {
@@ -75,7 +125,9 @@ const Keyword DUMP_KEYWORDS[] = {
     {"x", UCGB200_COL_X}, {"y", UCGB200_COL_Y}, {"z", UCGB200_COL_Z}, {"xs", UCGB200_COL_XS}, {"ys", UCGB200_COL_YS},
     {"zs", UCGB200_COL_ZS}, {"vx", UCGB200_COL_VX}, {"vy", UCGB200_COL_VY}, {"vz", UCGB200_COL_VZ},
     {"fx", UCGB200_COL_FX}, {"fy", UCGB200_COL_FY}, {"fz", UCGB200_COL_FZ}, {"q", UCGB200_COL_Q},
-    {"proc", UCGB200_COL_PROC}, {"ucgstate", UCGB200_COL_UCGSTATE}, {"ucgl", UCGB200_COL_UCGL}, {"ucgp", UCGB200_COL_UCGP}};
+    {"proc", UCGB200_COL_PROC}, {"ucgstate", UCGB200_COL_UCGSTATE}, {"ucgl", UCGB200_COL_UCGL}, {"ucgp", UCGB200_COL_UCGP},
+    // not dump keywords of the reference (there they need `compute property/atom`): the remaining UCG per-site arrays, directly
+    {"ucgforce", UCGB200_COL_P_UCGFORCE}, {"ucgvl", UCGB200_COL_P_UCGVL}, {"ucgml", UCGB200_COL_P_UCGML}};
 // AtomVecUCG::property_atom (atom_vec_ucg.cpp:172-181)
 const Keyword PROPERTY_NAMES[] = {{"ucgstate", UCGB200_COL_P_UCGSTATE}, {"ucgl", UCGB200_COL_P_UCGL},
                                   {"ucgforce", UCGB200_COL_P_UCGFORCE}, {"ucgvl", UCGB200_COL_P_UCGVL},
@@ -113,8 +165,7 @@ struct ucgb200_dump {
   bool opened = false;
   long long last_rows = 0, last_bytes = 0;
   int device_format = 1;   // rows formatted on the device whenever every format is the default one
-  std::vector<double> buf;
-  std::vector<char> text;
+  Staging rows, text;   // page-locked: the D2H copies of the packed rows / the formatted text land here
 
   ~ucgb200_dump() { if (fp) fclose(fp); }
 
@@ -349,33 +400,42 @@ extern "C" int ucgb200_host_dump_write(ucgb200_dump *d, ucgb200_ctx *ctx, long l
     dump_open(d, ntimestep);
     long long nrows = 0, nbytes = 0;
     const bool on_device = d->device_format && d->default_formats();
+    const char *body = nullptr;
+    std::vector<std::string> parts;
     if (on_device) {
       if (ucgb200_dump_text(ctx, &sp, nullptr, 0, &nrows, &nbytes)) throw IoError("dump: " + ctx_error(ctx));
       if (d->header_flag) dump_header(d, ctx, ntimestep, time, unit_style, nrows);
-      if ((long long)d->text.size() < nbytes + 1) d->text.resize((size_t)nbytes + 1);
-      if (nbytes && ucgb200_dump_text_copy(ctx, d->text.data(), (long long)d->text.size())) throw IoError("dump: " + ctx_error(ctx));
+      char *text = d->text.ensure((size_t)nbytes + 1);
+      if (nbytes && ucgb200_dump_text_copy(ctx, text, (long long)d->text.cap)) throw IoError("dump: " + ctx_error(ctx));
+      body = text;
     } else {
       int nl = 0;
       ucgb200_natoms(ctx, &nl, nullptr);
-      if (d->buf.size() < (size_t)nl * sp.ncols + 1) d->buf.resize((size_t)nl * sp.ncols + 1);
-      if (ucgb200_dump_pack(ctx, &sp, d->buf.data(), nl, &nrows)) throw IoError("dump: " + ctx_error(ctx));
+      const double *buf = (const double *)d->rows.ensure(((size_t)nl * sp.ncols + 1) * sizeof(double));
+      if (ucgb200_dump_pack(ctx, &sp, (double *)d->rows.p, nl, &nrows)) throw IoError("dump: " + ctx_error(ctx));
       if (d->header_flag) dump_header(d, ctx, ntimestep, time, unit_style, nrows);
       const std::vector<std::string> vf = d->vformats();
-      // convert_string(): snprintf per field, "\n" per row
-      size_t cap = (size_t)nrows * sp.ncols * 32 + 64, off = 0;
-      if (d->text.size() < cap) d->text.resize(cap);
-      size_t m = 0;
-      for (long long r = 0; r < nrows; r++) {
-        if (off + (size_t)sp.ncols * 256 + 2 > d->text.size()) d->text.resize(d->text.size() * 2 + (size_t)sp.ncols * 256);
-        for (int c = 0; c < sp.ncols; c++, m++) {
-          if (code_is_int(d->cols[c])) off += snprintf(&d->text[off], d->text.size() - off, vf[c].c_str(), static_cast<int>(d->buf[m]));
-          else off += snprintf(&d->text[off], d->text.size() - off, vf[c].c_str(), d->buf[m]);
+      // convert_string(): snprintf per field, "\n" per row — rows are independent, so chunks of them go to the host cores
+      const int nc = sp.ncols;
+      parts.assign(chunk_count(nrows, 4096), std::string());
+      parallel_chunks(nrows, 4096, [&](int t, long long b, long long e) {
+        std::string &out = parts[t];
+        out.reserve((size_t)(e - b) * nc * 12 + 64);
+        char field[512];
+        for (long long r = b; r < e; r++) {
+          const double *row = buf + (size_t)r * nc;
+          for (int c = 0; c < nc; c++) {
+            int len = code_is_int(d->cols[c]) ? snprintf(field, sizeof field, vf[c].c_str(), static_cast<int>(row[c]))
+                                              : snprintf(field, sizeof field, vf[c].c_str(), row[c]);
+            out.append(field, (size_t)std::min<int>(len, (int)sizeof field - 1));
+          }
+          out.push_back('\n');
         }
-        d->text[off++] = '\n';
-      }
-      nbytes = (long long)off;
+      });
+      for (const std::string &p : parts) nbytes += (long long)p.size();
     }
-    if (nbytes) fwrite(d->text.data(), 1, (size_t)nbytes, d->fp);
+    if (body && nbytes) fwrite(body, 1, (size_t)nbytes, d->fp);
+    for (const std::string &p : parts) if (!p.empty()) fwrite(p.data(), 1, p.size(), d->fp);
     if (d->flush_flag) fflush(d->fp);
     if (d->multifile) { fclose(d->fp); d->fp = nullptr; }
     d->last_rows = nrows;
@@ -594,23 +654,42 @@ extern "C" int ucgb200_host_read_dump(ucgb200_ctx *ctx, int narg, const char *co
       if (xyzflag[d] != UNSET && xyzflag[d] != value) throw IoError("Read_dump xyz fields do not have consistent scaling/wrapping");
     const int scaled = (value == SCALE_NOWRAP || value == SCALE_WRAP) ? 1 : 0;
 
-    // ReaderNative::read_atoms
+    // ReaderNative::read_atoms: the snapshot body is read in one block, lines are located, and chunks of lines are
+    // tokenised and converted (strtod == std::stod) on the host cores
     const int nfield = (int)fieldtype.size();
     std::vector<double> fields((size_t)snap.natoms * nfield);
-    std::string line;
-    std::vector<const char *> starts;
-    for (long long i = 0; i < snap.natoms; i++) {
-      need_line(fp, line);
-      starts.clear();
-      const char *p = line.c_str();
-      while (*p) {
-        while (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n' || *p == '\f') p++;
-        if (!*p) break;
-        starts.push_back(p);
-        while (*p && !(*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n' || *p == '\f')) p++;
+    {
+      const long body0 = ftell(fp);
+      fseek(fp, 0, SEEK_END);
+      const long fend = ftell(fp);
+      fseek(fp, body0, SEEK_SET);
+      std::vector<char> text((size_t)(fend - body0) + 1);
+      const size_t got = fread(text.data(), 1, (size_t)(fend - body0), fp);
+      text[got] = '\0';
+      std::vector<size_t> start((size_t)snap.natoms + 1);
+      size_t pos = 0;
+      for (long long i = 0; i < snap.natoms; i++) {
+        if (pos >= got) throw IoError("Unexpected end of dump file");
+        start[i] = pos;
+        const char *nl = (const char *)memchr(text.data() + pos, '\n', got - pos);
+        pos = nl ? (size_t)(nl - text.data()) + 1 : got;
       }
-      if ((int)starts.size() < nwords) throw IoError("Insufficient columns in dump file");
-      for (int m = 0; m < nfield; m++) fields[(size_t)i * nfield + m] = strtod(starts[fieldindex[m]], nullptr);   // std::stod
+      start[snap.natoms] = pos;
+      parallel_chunks(snap.natoms, 2048, [&](int, long long b, long long e) {
+        std::vector<const char *> tok;
+        for (long long i = b; i < e; i++) {
+          tok.clear();
+          const char *p = text.data() + start[i], *end = text.data() + start[i + 1];
+          while (p < end) {
+            while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n' || *p == '\f')) p++;
+            if (p >= end) break;
+            tok.push_back(p);
+            while (p < end && !(*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n' || *p == '\f')) p++;
+          }
+          if ((int)tok.size() < nwords) throw IoError("Insufficient columns in dump file");
+          for (int m = 0; m < nfield; m++) fields[(size_t)i * nfield + m] = strtod(tok[fieldindex[m]], nullptr);
+        }
+      });
     }
     fclose(fp);
     fp = nullptr;

@@ -16,8 +16,17 @@
 #include "lammps_shim_io.h"
 
 #include "atom_vec_ucg.h"
+#ifdef UCG_PRODUCT_STYLES   // oracle/Makefile.hostdrv: the product's GPU-backed classes under the same deck words
+#include "dump_custom_ucg_b200.h"
+#include "read_dump_ucg_b200.h"
+namespace LAMMPS_NS {
+typedef DumpCustomUCGB200 DumpCustom;
+typedef ReadDumpUCGB200 ReadDump;
+}
+#else
 #include "dump_custom.h"
 #include "read_dump.h"
+#endif
 #include "fix_cluster_switch.h"
 #include "fix_nve_ucgld.h"
 #include "fix_nve_ucgld_wall_hard.h"

@@ -205,3 +205,52 @@ def test_cluster_switch_deck(pkg, fixtures, tmp_path):
     assert rel_err(b["f"], a["f"]) <= 1e-6
     for name in ("cluster_assignment.log", "state_assignment.log"):
         assert (tmp_path / "ref" / name).read_text() == (tmp_path / "gpu" / name).read_text()
+
+
+def _dump_table(path):
+    """(header bytes, column names, rows) of a one-snapshot dump file"""
+    raw = open(path, "rb").read()
+    head, body = raw.split(b"ITEM: ATOMS", 1)
+    lines = body.decode().split("\n")
+    return head, lines[0].split(), np.array([[float(w) for w in l.split()] for l in lines[1:] if l])
+
+
+def test_dump_and_read_dump_decks(pkg, fixtures, tmp_path):
+    """`dump ... custom` + `dump_modify` + `read_dump` lines through the reference's patched dump_custom.cpp / read_dump.cpp
+    and through the product's DumpCustomUCGB200 / ReadDumpUCGB200 classes (device selection, packing, formatting, scatter)"""
+    liq = _liq(5, mol_size=4)
+    fixes = ["fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld", "fix 2 all ucgstate"]
+    ref, gpu = _both(liq, fixtures, fixes)
+    cols = "id mol type mass x y z xs vx fx ucgstate ucgl ucgp"
+    files = []
+    for tag, s in (("ref", ref), ("gpu", gpu)):
+        s.setup(1)
+        s.run(5, 0)
+        p = str(tmp_path / (tag + ".dump"))
+        s.command("dump d all custom 5 %s %s" % (p, cols))
+        s.command("dump_modify d sort id thresh ucgl >= 0.2 time yes")
+        s.command("dump_write d")
+        s.command("undump d")
+        files.append(p)
+    (h0, c0, t0), (h1, c1, t1) = _dump_table(files[0]), _dump_table(files[1])
+    assert h0 == h1 and c0 == c1 and t0.shape == t1.shape       # same header, same atoms selected
+    ints = [c0.index(k) for k in ("id", "mol", "type", "ucgstate")]
+    assert np.array_equal(t0[:, ints], t1[:, ints])
+    assert np.allclose(t0, t1, rtol=3e-6, atol=1e-9)            # 6 printed digits of a 1e-10-close trajectory
+    # read the reference's file back into both, after scrambling the state
+    states = []
+    for s in (ref, gpu):
+        n = s.nlocal()
+        s.set_state(x=liq.x[::-1].copy(), ucgl=np.zeros(n), ucgstate=np.zeros(n, np.int32), v=np.zeros((n, 3)))
+        s.command("read_dump %s 5 x y z vx ucgstate ucgl ucgp box yes" % files[0])
+        assert s.ntimestep() == 5
+        states.append(s.get_atoms())
+    a, b = states
+    for k in ("x", "v", "ucgl", "ucgp", "ucgstate", "tag", "type"):
+        assert np.array_equal(a[k], b[k]), k
+    # and the run continues from the restored state
+    for s in (ref, gpu):
+        s.setup(0)
+        s.run(3, 0)
+    a, b = ref.get_atoms(), gpu.get_atoms()
+    assert rel_err(b["x"], a["x"]) <= 1e-10 and rel_err(b["ucgp"], a["ucgp"]) <= 1e-8
