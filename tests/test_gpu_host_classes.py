@@ -232,6 +232,9 @@ def test_dump_and_read_dump_decks(pkg, fixtures, tmp_path):
         s.command("dump_write d")
         s.command("undump d")
         files.append(p)
+        s.command("dump full all custom 5 %s id type x y z vx ucgstate ucgl ucgp" % (p + ".full"))
+        s.command("dump_write full")
+        s.command("undump full")
     (h0, c0, t0), (h1, c1, t1) = _dump_table(files[0]), _dump_table(files[1])
     assert h0 == h1 and c0 == c1 and t0.shape == t1.shape       # same header, same atoms selected
     ints = [c0.index(k) for k in ("id", "mol", "type", "ucgstate")]
@@ -242,7 +245,7 @@ def test_dump_and_read_dump_decks(pkg, fixtures, tmp_path):
     for s in (ref, gpu):
         n = s.nlocal()
         s.set_state(x=liq.x[::-1].copy(), ucgl=np.zeros(n), ucgstate=np.zeros(n, np.int32), v=np.zeros((n, 3)))
-        s.command("read_dump %s 5 x y z vx ucgstate ucgl ucgp box yes" % files[0])
+        s.command("read_dump %s 5 x y z vx ucgstate ucgl ucgp box yes" % (files[0] + ".full"))
         assert s.ntimestep() == 5
         states.append(s.get_atoms())
     a, b = states
