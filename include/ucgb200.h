@@ -407,11 +407,23 @@ int ucgb200_dump_text_copy(ucgb200_ctx *ctx, char *text, long long capacity_byte
  * 1150-1163): fields[i * nfield + j] is the snapshot as Reader::read_atoms leaves it, fieldtype[0] must be
  * UCGB200_COL_ID; rows whose id matches an owned atom overwrite x y z (unscaled with the SNAPSHOT box when
  * `scaled`), vx vy vz, fx fy fz, ucgstate, ucgl, ucgp of that atom; positions are then wrapped into the
- * CURRENT box (ucgb200_set_box first for `box yes`).  updated[nlocal] (host index order, may be NULL)
+ * CURRENT box (ucgb200_set_box first for `box yes`).  fields == NULL takes the block ucgb200_snapshot_parse left on
+ * the device.  updated[nlocal] (host index order, may be NULL)
  * receives the updateflag array `trim` works from; *nreplace counts the matches. */
 int ucgb200_atoms_update_by_tag(ucgb200_ctx *ctx, int nnew, int nfield, const int *fieldtype, const double *fields,
                                 int scaled, const double snap_lo[3], const double snap_hi[3], int *updated,
                                 long long *nreplace);
+/* ReaderNative::read_atoms (reader_native.cpp:486-500) on the device: `text` holds the nrows atom lines of one
+ * snapshot (nwords columns each); column fieldindex[m] of every line becomes fields[row][m] of a block that stays
+ * on the device for ucgb200_atoms_update_by_tag(..., fields = NULL, ...).  Decimal tokens that convert exactly in one
+ * IEEE operation (<= 2^53 mantissa, |power of ten| <= 22: everything "%g" prints up to e+-22) are converted
+ * there; rows holding any other token are reported (row index, byte offset of the line) so that the caller
+ * converts them with strtod and sends them back with ucgb200_snapshot_patch.  Returns UCGB200_PARSE_ON_HOST when the
+ * block should be converted by the caller instead (>= 2 GiB of text, > 64 columns, more than slow_cap such rows). */
+#define UCGB200_PARSE_ON_HOST 7
+int ucgb200_snapshot_parse(ucgb200_ctx *ctx, const char *text, long long nbytes, long long nrows, int nwords, int nfield,
+                           const int *fieldindex, int slow_cap, int *slow_rows, int *slow_offsets, long long *nslow);
+int ucgb200_snapshot_patch(ucgb200_ctx *ctx, int n, const int *rows, const double *values /* [n][nfield] */);
 /* Domain::remap of every owned atom into the current periodic box, any number of periods
  * (ReadDump::migrate_atoms_by_coords, read_dump.cpp:1150-1163); invalidates the neighbor list */
 int ucgb200_atoms_remap(ucgb200_ctx *ctx);

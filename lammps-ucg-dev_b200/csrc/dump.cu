@@ -13,6 +13,8 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 #include "dump_format.cuh"
 #include "ucg_internal.cuh"
@@ -421,7 +423,8 @@ extern "C" int ucgb200_atoms_update_by_tag(ucgb200_ctx *c, int nnew, int nfield,
   if (nreplace) *nreplace = 0;
   if (updated) for (int i = 0; i < n; i++) updated[i] = 0;
   if (n == 0 || nnew == 0) return 0;
-  if (!fields) return -1;
+  if (!fields && (c->parsed_rows != nnew || c->parsed_fields != nfield))
+    return fail(c, "atoms_update_by_tag: no host block given and no matching block parsed on the device");
   UpdateArgs a;
   a.pos = c->pos.p; a.vel = c->vel.p; a.frc = c->frc.p; a.ucgp = c->ucgp.p; a.ts = c->ts.p; a.orig = c->orig.p;
   a.nfield = nfield;
@@ -451,9 +454,12 @@ extern "C" int ucgb200_atoms_update_by_tag(ucgb200_ctx *c, int nnew, int nfield,
   c->launches += 7;
   // snapshot rows and the per-host-index update flags
   const size_t nval = (size_t)nnew * nfield;
-  UCG_CHECK(c, c->dump_buf.ensure(nval + 8));
   UCG_CHECK(c, c->stage_i.ensure((size_t)n + 8));
-  UCG_CHECK(c, cudaMemcpyAsync(c->dump_buf.p, fields, nval * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (fields) {
+    UCG_CHECK(c, c->dump_buf.ensure(nval + 8));
+    UCG_CHECK(c, cudaMemcpyAsync(c->dump_buf.p, fields, nval * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  c->parsed_rows = -1;
   UCG_CHECK(c, cudaMemsetAsync(c->stage_i.p, 0, ((size_t)n + 1) * sizeof(int), st));
   int *d_flag = c->stage_i.p, *d_cnt = c->stage_i.p + n;
   k_update_by_tag<<<nblocks(nnew, 256), 256, 0, st>>>(a, c->dump_buf.p, nnew, k_out, v_out, n, d_flag, d_cnt);
@@ -478,5 +484,191 @@ extern "C" int ucgb200_atoms_remap(ucgb200_ctx *c) {
   UCG_LAUNCHED(c);
   c->list_valid = false;
   c->maxdisp_valid = false;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ snapshot text -> fields
+// ReaderNative::read_atoms (reader_native.cpp:486-500) on the device: the snapshot body is uploaded as text, line starts
+// are compacted, and one thread per line tokenises it and converts the requested columns.  A decimal token converts
+// exactly when its digits fit 2^53 and its power of ten is at most 10^22 in magnitude (one correctly rounded IEEE
+// multiplication or division of two exact doubles — every number a "%g" dump holds, unless its exponent is beyond e+-22);
+// any other token (longer mantissas, large exponents, inf/nan, malformed text) marks the row, and the host converts
+// those rows with strtod, as std::stod does in the reference.
+namespace {
+
+struct IsLineStart {
+  const char *text;
+  __device__ bool operator()(const int &i) const { return i == 0 || text[i - 1] == '\n'; }
+};
+
+constexpr int MAXWORDS = 64;
+struct ParseArgs {
+  int nwords, nfield, maxcol;
+  int fieldindex[MAXCOL];
+};
+
+__device__ __forceinline__ bool is_blank(char ch) { return ch == ' ' || ch == '\t' || ch == '\r' || ch == '\n' || ch == '\f'; }
+
+// returns false when the token needs strtod
+__device__ bool parse_token(const char *p, const char *end, double *out) {
+  const double P10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17,
+                          1e18, 1e19, 1e20, 1e21, 1e22};
+  bool neg = false;
+  if (p < end && (*p == '-' || *p == '+')) { neg = *p == '-'; p++; }
+  unsigned long long mant = 0;
+  int e10 = 0;
+  bool digits = false;
+  while (p < end && *p >= '0' && *p <= '9') {
+    if (mant >= 900000000000000000ull) return false;
+    mant = mant * 10ull + (unsigned)(*p - '0');
+    digits = true;
+    p++;
+  }
+  if (p < end && *p == '.') {
+    p++;
+    while (p < end && *p >= '0' && *p <= '9') {
+      if (mant >= 900000000000000000ull) return false;
+      mant = mant * 10ull + (unsigned)(*p - '0');
+      e10--;
+      digits = true;
+      p++;
+    }
+  }
+  if (!digits) return false;
+  if (p < end && (*p == 'e' || *p == 'E')) {
+    p++;
+    bool eneg = false;
+    if (p < end && (*p == '-' || *p == '+')) { eneg = *p == '-'; p++; }
+    if (!(p < end && *p >= '0' && *p <= '9')) return false;
+    int ex = 0;
+    while (p < end && *p >= '0' && *p <= '9') {
+      if (ex > 10000) return false;
+      ex = ex * 10 + (*p - '0');
+      p++;
+    }
+    e10 += eneg ? -ex : ex;
+  }
+  if (p < end && !is_blank(*p)) return false;   // trailing characters: let strtod decide
+  if (mant == 0) { *out = neg ? -0.0 : 0.0; return true; }
+  while (e10 > 22 && mant < 900719925474099ull) { mant *= 10ull; e10--; }
+  while (e10 < -22 && mant % 10ull == 0) { mant /= 10ull; e10++; }
+  if (mant > 9007199254740992ull || e10 > 22 || e10 < -22) return false;
+  const double m = (double)mant;
+  const double v = e10 >= 0 ? __dmul_rn(m, P10[e10]) : __ddiv_rn(m, P10[-e10]);
+  *out = neg ? -v : v;
+  return true;
+}
+
+__global__ void k_parse_rows(const char *__restrict__ text, int nbytes, const int *__restrict__ start, int nrows, ParseArgs a,
+                             double *__restrict__ fields, int *__restrict__ counters, int *__restrict__ slow_rows,
+                             int *__restrict__ slow_off, int cap) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  const char *p = text + start[r];
+  const char *end = text + (r + 1 < nrows ? start[r + 1] : nbytes);
+  int tok[MAXWORDS];
+  int nt = 0;
+  const char *q = p;
+  while (q < end && nt <= a.maxcol) {
+    while (q < end && is_blank(*q)) q++;
+    if (q >= end) break;
+    tok[nt++] = (int)(q - p);
+    while (q < end && !is_blank(*q)) q++;
+  }
+  bool slow = false;
+  if (nt <= a.maxcol) {
+    // fewer words than the columns needed: is the line short of nwords as a whole ("Insufficient columns")?
+    atomicAdd(&counters[1], 1);
+    return;
+  }
+  for (int m = 0; m < a.nfield; m++) {
+    double v = 0.0;
+    if (!parse_token(p + tok[a.fieldindex[m]], end, &v)) slow = true;
+    fields[(size_t)r * a.nfield + m] = v;
+  }
+  if (slow) {
+    int k = atomicAdd(&counters[0], 1);
+    if (k < cap) { slow_rows[k] = r; slow_off[k] = start[r]; }
+  }
+}
+
+__global__ void k_patch_rows(double *__restrict__ fields, int nfield, const int *__restrict__ rows, const double *__restrict__ vals, int n) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * nfield) return;
+  fields[(size_t)rows[e / nfield] * nfield + e % nfield] = vals[e];
+}
+
+}  // namespace
+
+extern "C" int ucgb200_snapshot_parse(ucgb200_ctx *c, const char *text, long long nbytes, long long nrows, int nwords, int nfield,
+                                      const int *fieldindex, int slow_cap, int *slow_rows, int *slow_offsets, long long *nslow) {
+  if (!c || !text || !fieldindex || !nslow || nfield < 1 || nfield > MAXCOL) return -1;
+  *nslow = 0;
+  c->parsed_rows = -1;
+  if (nbytes >= 0x7fffffffLL || nrows >= 0x7fffffffLL || nwords > MAXWORDS) return UCGB200_PARSE_ON_HOST;
+  cudaSetDevice(c->device);
+  cudaStream_t st = c->stream;
+  if (nrows == 0) { c->parsed_rows = 0; c->parsed_fields = nfield; return 0; }
+  ParseArgs a;
+  a.nwords = nwords; a.nfield = nfield; a.maxcol = 0;
+  for (int m = 0; m < nfield; m++) {
+    if (fieldindex[m] < 0 || fieldindex[m] >= nwords) return fail(c, "snapshot_parse: column index outside the line");
+    a.fieldindex[m] = fieldindex[m];
+    a.maxcol = fieldindex[m] > a.maxcol ? fieldindex[m] : a.maxcol;
+  }
+  const int nb = (int)nbytes, nr = (int)nrows;
+  UCG_CHECK(c, c->dump_text.ensure((size_t)nb + 16));
+  UCG_CHECK(c, cudaMemcpyAsync(c->dump_text.p, text, (size_t)nb, cudaMemcpyHostToDevice, st));
+  // line starts: offsets i with i == 0 or text[i-1] == '\n'
+  UCG_CHECK(c, c->dump_sites.ensure((size_t)nb / 2 + (size_t)nr + 2 * (size_t)slow_cap + 64));
+  int *starts = c->dump_sites.p;
+  int *d_cnt = c->d_flags.p + 4;   // [4] lines found / slow rows, [5] short lines
+  cub::CountingInputIterator<int> idx(0);
+  IsLineStart pred{c->dump_text.p};
+  // a line is at least 2 bytes ("0\n"), so nb/2+1 offsets always fit
+  size_t tmp = 0;
+  UCG_CHECK(c, cub::DeviceSelect::If(nullptr, tmp, idx, starts, d_cnt, nb, pred, st));
+  UCG_CHECK(c, c->dump_tmp.ensure(tmp + 16));
+  UCG_CHECK(c, cub::DeviceSelect::If(c->dump_tmp.p, tmp, idx, starts, d_cnt, nb, pred, st));
+  c->launches += 2;
+  int nlines = 0;
+  UCG_CHECK(c, cudaMemcpyAsync(&nlines, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+  UCG_CHECK(c, cudaStreamSynchronize(st));
+  if (nlines < nr) return fail(c, "Unexpected end of dump file");
+  UCG_CHECK(c, c->dump_buf.ensure((size_t)nr * nfield + 8));
+  int *d_slow_rows = c->dump_sites.p + (size_t)nb / 2 + nr + 8, *d_slow_off = d_slow_rows + slow_cap;
+  UCG_CHECK(c, cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), st));
+  k_parse_rows<<<nblocks(nr, 128), 128, 0, st>>>(c->dump_text.p, nb, starts, nr, a, c->dump_buf.p, d_cnt, d_slow_rows, d_slow_off, slow_cap);
+  UCG_LAUNCHED(c);
+  int cnt[2] = {0, 0};
+  UCG_CHECK(c, cudaMemcpyAsync(cnt, d_cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  UCG_CHECK(c, cudaStreamSynchronize(st));
+  if (cnt[1]) return fail(c, "Insufficient columns in dump file");
+  if (cnt[0] > slow_cap) return UCGB200_PARSE_ON_HOST;   // mostly non-trivial numbers: the host cores convert the whole block
+  if (cnt[0]) {
+    UCG_CHECK(c, cudaMemcpyAsync(slow_rows, d_slow_rows, cnt[0] * sizeof(int), cudaMemcpyDeviceToHost, st));
+    UCG_CHECK(c, cudaMemcpyAsync(slow_offsets, d_slow_off, cnt[0] * sizeof(int), cudaMemcpyDeviceToHost, st));
+    UCG_CHECK(c, cudaStreamSynchronize(st));
+  }
+  *nslow = cnt[0];
+  c->parsed_rows = nr;
+  c->parsed_fields = nfield;
+  return 0;
+}
+
+extern "C" int ucgb200_snapshot_patch(ucgb200_ctx *c, int n, const int *rows, const double *values) {
+  if (!c || n < 0) return -1;
+  if (n == 0) return 0;
+  if (c->parsed_rows < 0 || !rows || !values) return fail(c, "snapshot_patch: nothing parsed");
+  cudaSetDevice(c->device);
+  cudaStream_t st = c->stream;
+  const int nf = c->parsed_fields;
+  UCG_CHECK(c, c->stage_i.ensure((size_t)n + 8));
+  UCG_CHECK(c, c->stage_d.ensure((size_t)n * nf + 8));
+  UCG_CHECK(c, cudaMemcpyAsync(c->stage_i.p, rows, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  UCG_CHECK(c, cudaMemcpyAsync(c->stage_d.p, values, (size_t)n * nf * sizeof(double), cudaMemcpyHostToDevice, st));
+  k_patch_rows<<<nblocks((long long)n * nf, 256), 256, 0, st>>>(c->dump_buf.p, nf, c->stage_i.p, c->stage_d.p, n);
+  UCG_LAUNCHED(c);
+  UCG_CHECK(c, cudaStreamSynchronize(st));
   return 0;
 }

@@ -151,6 +151,7 @@ struct ucgb200_ctx {
   ucg::Buf<long long> dump_off;
   ucg::Buf<uint4> dump_slots;
   long long dump_text_bytes = 0;
+  int parsed_rows = -1, parsed_fields = 0;   // block left in dump_buf by ucgb200_snapshot_parse
   ucg::Buf<int> stage_i;
   ucg::Buf<int> ts, ts_alt, mask, mask_alt, tag, tag_alt, mol, mol_alt, orig, orig_alt;
   // ghosts: sources = local periodic images + border records received from other bricks

@@ -656,40 +656,79 @@ extern "C" int ucgb200_host_read_dump(ucgb200_ctx *ctx, int narg, const char *co
 
     // ReaderNative::read_atoms: the snapshot body is read in one block, lines are located, and chunks of lines are
     // tokenised and converted (strtod == std::stod) on the host cores
+    // The snapshot body is read in one block (page-locked, so the upload is a DMA) and converted on the device
+    // (ucgb200_snapshot_parse); rows holding a token the device does not convert exactly, or the whole block when the
+    // device declines, are tokenised and converted (strtod == std::stod) on the host cores.
     const int nfield = (int)fieldtype.size();
-    std::vector<double> fields((size_t)snap.natoms * nfield);
+    std::vector<double> fields;
+    bool fields_on_device = false;
     {
       const long body0 = ftell(fp);
       fseek(fp, 0, SEEK_END);
       const long fend = ftell(fp);
       fseek(fp, body0, SEEK_SET);
-      std::vector<char> text((size_t)(fend - body0) + 1);
-      const size_t got = fread(text.data(), 1, (size_t)(fend - body0), fp);
+      Staging textbuf;
+      char *text = textbuf.ensure((size_t)(fend - body0) + 1);
+      const size_t got = fread(text, 1, (size_t)(fend - body0), fp);
       text[got] = '\0';
-      std::vector<size_t> start((size_t)snap.natoms + 1);
-      size_t pos = 0;
-      for (long long i = 0; i < snap.natoms; i++) {
-        if (pos >= got) throw IoError("Unexpected end of dump file");
-        start[i] = pos;
-        const char *nl = (const char *)memchr(text.data() + pos, '\n', got - pos);
-        pos = nl ? (size_t)(nl - text.data()) + 1 : got;
-      }
-      start[snap.natoms] = pos;
-      parallel_chunks(snap.natoms, 2048, [&](int, long long b, long long e) {
-        std::vector<const char *> tok;
-        for (long long i = b; i < e; i++) {
-          tok.clear();
-          const char *p = text.data() + start[i], *end = text.data() + start[i + 1];
-          while (p < end) {
-            while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n' || *p == '\f')) p++;
-            if (p >= end) break;
-            tok.push_back(p);
-            while (p < end && !(*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n' || *p == '\f')) p++;
-          }
-          if ((int)tok.size() < nwords) throw IoError("Insufficient columns in dump file");
-          for (int m = 0; m < nfield; m++) fields[(size_t)i * nfield + m] = strtod(tok[fieldindex[m]], nullptr);
+      auto parse_line = [&](const char *p, const char *end, double *out, std::vector<const char *> &tok) {
+        tok.clear();
+        while (p < end) {
+          while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n' || *p == '\f')) p++;
+          if (p >= end) break;
+          tok.push_back(p);
+          while (p < end && !(*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n' || *p == '\f')) p++;
         }
-      });
+        if ((int)tok.size() < nwords) throw IoError("Insufficient columns in dump file");
+        for (int m = 0; m < nfield; m++) out[m] = strtod(tok[fieldindex[m]], nullptr);
+      };
+      const char *env = getenv("UCGB200_READ_DUMP_DEVICE_PARSE");
+      int rc = UCGB200_PARSE_ON_HOST;
+      // only the lines of THIS snapshot: later snapshots may follow in the file
+      size_t body_len = got;
+      if (!(env && atoi(env) == 0)) {
+        size_t pos = 0;
+        for (long long i = 0; i < snap.natoms && pos < got; i++) {
+          const char *nl = (const char *)memchr(text + pos, '\n', got - pos);
+          pos = nl ? (size_t)(nl - text) + 1 : got;
+          if (i + 1 == snap.natoms) body_len = pos;
+        }
+        const int cap = 1 << 16;
+        std::vector<int> srow(cap), soff(cap);
+        long long nslow = 0;
+        rc = ucgb200_snapshot_parse(ctx, text, (long long)body_len, snap.natoms, nwords, nfield, fieldindex.data(), cap, srow.data(),
+                                    soff.data(), &nslow);
+        if (rc < 0) throw IoError(ctx_error(ctx));
+        if (rc == 0) {
+          if (nslow) {
+            std::vector<double> vals((size_t)nslow * nfield);
+            std::vector<const char *> tok;
+            for (long long k = 0; k < nslow; k++) {
+              const char *p = text + soff[k];
+              const char *nl = (const char *)memchr(p, '\n', body_len - soff[k]);
+              parse_line(p, nl ? nl + 1 : text + body_len, &vals[(size_t)k * nfield], tok);
+            }
+            if (ucgb200_snapshot_patch(ctx, (int)nslow, srow.data(), vals.data())) throw IoError(ctx_error(ctx));
+          }
+          fields_on_device = true;
+        }
+      }
+      if (!fields_on_device) {
+        fields.resize((size_t)snap.natoms * nfield);
+        std::vector<size_t> start((size_t)snap.natoms + 1);
+        size_t pos = 0;
+        for (long long i = 0; i < snap.natoms; i++) {
+          if (pos >= got) throw IoError("Unexpected end of dump file");
+          start[i] = pos;
+          const char *nl = (const char *)memchr(text + pos, '\n', got - pos);
+          pos = nl ? (size_t)(nl - text) + 1 : got;
+        }
+        start[snap.natoms] = pos;
+        parallel_chunks(snap.natoms, 2048, [&](int, long long b, long long e) {
+          std::vector<const char *> tok;
+          for (long long i = b; i < e; i++) parse_line(text + start[i], text + start[i + 1], &fields[(size_t)i * nfield], tok);
+        });
+      }
     }
     fclose(fp);
     fp = nullptr;
@@ -706,15 +745,11 @@ extern "C" int ucgb200_host_read_dump(ucgb200_ctx *ctx, int narg, const char *co
     std::vector<int> updated((size_t)nbefore + 1, 0);
     if (replaceflag || trimflag) {
       // without `replace` only the update flags are needed: an id-only pass changes nothing
-      const int nf = replaceflag ? nfield : 1;
-      std::vector<double> ids;
-      const double *src = fields.data();
-      if (!replaceflag) {
-        ids.resize((size_t)snap.natoms);
-        for (long long i = 0; i < snap.natoms; i++) ids[i] = fields[(size_t)i * nfield];
-        src = ids.data();
-      }
-      if (ucgb200_atoms_update_by_tag(ctx, (int)snap.natoms, nf, fieldtype.data(), src, scaled, snap.lo, snap.hi, updated.data(), &nreplace))
+      // `replace no`: the same pass with every field but the id masked out marks the matches and changes nothing
+      std::vector<int> ftype = fieldtype;
+      if (!replaceflag) for (int j = 1; j < nfield; j++) ftype[j] = UCGB200_COL_Q;
+      if (ucgb200_atoms_update_by_tag(ctx, (int)snap.natoms, nfield, ftype.data(), fields_on_device ? nullptr : fields.data(), scaled,
+                                      snap.lo, snap.hi, updated.data(), &nreplace))
         throw IoError("read_dump: " + ctx_error(ctx));
       if (!replaceflag) nreplace = 0;
     }

@@ -112,9 +112,11 @@ def test_device_g_format_on_extreme_values(pkg, fixtures):
     assert dumpio.dump_text(ctx, cols) == IO.lines(buf, cols)
 
 
+@pytest.mark.parametrize("device_parse", [1, 0])
 @pytest.mark.parametrize("name", sorted(IC.READ_CASES))
-def test_read_dump_equals_the_reference(pkg, fixtures, name):
+def test_read_dump_equals_the_reference(pkg, fixtures, monkeypatch, name, device_parse):
     from lammps_ucg_dev_b200 import dumpio, synth
+    monkeypatch.setenv("UCGB200_READ_DUMP_DEVICE_PARSE", str(device_parse))
     liq2, dyn2 = IC.second_state(synth)
     ctx = make_ctx(pkg, fixtures, liq2, dyn2)
     gold = np.load(os.path.join(IC.GOLDEN, "read_dump_results.npz"))
@@ -135,6 +137,45 @@ def test_read_dump_equals_the_reference(pkg, fixtures, name):
     # the context is usable afterwards: the list is rebuilt for the new positions / box
     ctx.neigh_build()
     assert ctx.natoms()[0] == stats["after"]
+
+
+def test_device_snapshot_parse_equals_strtod(pkg, fixtures, tmp_path, monkeypatch):
+    """every number spelling through read_dump's device converter: "%g", "%.17g" (longer than 2^53: converted by the
+    host for that row), fixed, exponents beyond e+-22, signs, leading '+', '.5', '5.', inf — the state must equal
+    float(token) bit for bit, and equal the host-only path"""
+    from lammps_ucg_dev_b200 import dumpio, synth
+    liq, dyn = IC.make_state(synth, ncell=8)
+    n = liq.n
+    rng = np.random.default_rng(17)
+    spell = ["%g", "%.17g", "%.3f", "%.10e", "%+.6g", "%.15g", "%25.16e"]
+    vals = rng.normal(size=(n, 4)) * 10.0 ** rng.integers(-30, 31, size=(n, 4))
+    vals[:, 3] = rng.uniform(0, 1, n)
+    special = ["0", "-0", ".5", "5.", "+1.5e+3", "1E5", "123456789012345678", "0.000000000000000000000001", "1e-320", "inf",
+               "9007199254740993", "1e22", "1e23", "8.5e-23", "00012.50", "4.9406564584124654e-324"]
+    rows, want = [], np.zeros((n, 4))
+    for i in range(n):
+        toks = []
+        for j in range(4):
+            t = (special[(i * 4 + j) % len(special)] if (i + j) % 7 == 0 and j < 3 else spell[(i + j) % len(spell)] % vals[i, j]).strip()
+            toks.append(t)
+            want[i, j] = float(t)
+        rows.append("%d %s junk\n" % (liq.tag[i], " ".join(toks)))
+    p = str(tmp_path / "hand.dump")
+    with open(p, "w") as f:
+        f.write("ITEM: TIMESTEP\n3\nITEM: NUMBER OF ATOMS\n%d\nITEM: BOX BOUNDS pp pp pp\n" % n)
+        for d in range(3):
+            f.write("%.17g %.17g\n" % (liq.box_lo[d], liq.box_hi[d]))
+        f.write("ITEM: ATOMS id vx vy vz ucgl extra\n" + "".join(rows))
+    got = []
+    for mode in (1, 0):
+        monkeypatch.setenv("UCGB200_READ_DUMP_DEVICE_PARSE", str(mode))
+        ctx = make_ctx(pkg, fixtures, liq, dyn)
+        st = dumpio.read_dump(ctx, "read_dump %s 3 vx vy vz ucgl box no" % p)
+        assert st["replaced"] == n
+        a = ctx.atoms_download(["v", "ucgl"])
+        got.append(np.concatenate([a["v"], a["ucgl"][:, None]], axis=1))
+    assert np.array_equal(got[0], got[1], equal_nan=True)
+    assert np.array_equal(got[0].view(np.uint64), want.view(np.uint64))
 
 
 def test_error_texts(pkg, fixtures, tmp_path):
