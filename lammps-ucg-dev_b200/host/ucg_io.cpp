@@ -667,7 +667,7 @@ extern "C" int ucgb200_host_read_dump(ucgb200_ctx *ctx, int narg, const char *co
       fseek(fp, 0, SEEK_END);
       const long fend = ftell(fp);
       fseek(fp, body0, SEEK_SET);
-      Staging textbuf;
+      static thread_local Staging textbuf;   // page-locking 74 MB costs more than copying them: kept across calls
       char *text = textbuf.ensure((size_t)(fend - body0) + 1);
       const size_t got = fread(text, 1, (size_t)(fend - body0), fp);
       text[got] = '\0';
