@@ -297,6 +297,7 @@ int ucgb200_last_pair_ms(ucgb200_ctx *ctx, double *ms);
  * DEVICE buffers so that any transport can carry them (NCCL all-to-all driven by the host
  * layer, or peer-mapped stores).  The device list is full, so there is no reverse halo. */
 int ucgb200_halo_configure(ucgb200_ctx *ctx, int rank, int nranks, const int procgrid[3]);
+int ucgb200_halo_info(const ucgb200_ctx *ctx, int *rank, int *nranks);
 /* record sizes in bytes: border (rebuild), forward (every step), migrate (rebuild) */
 int ucgb200_halo_record_bytes(int *border, int *forward, int *migrate);
 /* comm->exchange(): wrap, count the sites that left this brick per destination rank ... */

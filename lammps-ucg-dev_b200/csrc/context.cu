@@ -122,6 +122,12 @@ extern "C" int ucgb200_pinned_free(void *p) {
   if (p) cudaFreeHost(p);
   return 0;
 }
+extern "C" int ucgb200_halo_info(const ucgb200_ctx *c, int *rank, int *nranks) {
+  if (!c) return -1;
+  if (rank) *rank = c->halo.rank;
+  if (nranks) *nranks = c->halo.nranks;
+  return 0;
+}
 extern "C" int ucgb200_get_box(const ucgb200_ctx *c, double lo[3], double hi[3], int periodic[3]) {
   if (!c) return -1;
   for (int d = 0; d < 3; d++) {

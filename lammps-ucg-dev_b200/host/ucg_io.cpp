@@ -147,7 +147,7 @@ bool code_is_int(int code) {   // vtype Dump::INT in parse_fields
 struct ucgb200_dump {
   std::string id, filename;
   int groupbit = 1, nevery = 1;
-  bool multifile = false;
+  bool multifile = false, multiproc = false;
   // columns
   std::vector<std::string> colnames;         // as typed (ITEM: ATOMS line)
   std::vector<int> cols, colbit;             // device codes; -1 while a c_ID[k] column is unbound
@@ -207,7 +207,7 @@ extern "C" int ucgb200_host_dump_create(int narg, const char *const *arg, int gr
     d->nevery = (int)inumeric(arg[3]);
     if (d->nevery <= 0) throw IoError("Illegal dump custom command: output frequency must be > 0");
     d->filename = arg[4];
-    if (d->filename.find('%') != std::string::npos) throw IoError("Dump custom: one file per processor ('%') is not supported by the device writer");
+    d->multiproc = d->filename.find('%') != std::string::npos;   // one file per brick, as `dump ... file.%` gives one per processor
     if (d->filename.size() > 4 && d->filename.compare(d->filename.size() - 4, 4, ".bin") == 0)
       throw IoError("Dump custom: binary files are not supported by the device writer");
     d->multifile = d->filename.find('*') != std::string::npos;
@@ -344,9 +344,13 @@ extern "C" int ucgb200_host_dump_modify(ucgb200_dump *d, int narg, const char *c
 
 namespace {
 
-void dump_open(ucgb200_dump *d, long long ntimestep) {
+void dump_open(ucgb200_dump *d, ucgb200_ctx *ctx, long long ntimestep) {
   if (d->opened && !d->multifile) return;
   std::string name = d->filename;
+  int rank = 0, nranks = 1;
+  ucgb200_halo_info(ctx, &rank, &nranks);
+  if (d->multiproc) name.replace(name.find('%'), 1, std::to_string(rank));
+  else if (nranks > 1) throw IoError("Dump custom: a multi-brick run writes one file per brick (use '%' in the file name)");
   if (d->multifile) {   // utils::star_subst with dump_modify pad
     size_t star = name.find('*');
     char num[64];
@@ -397,7 +401,7 @@ extern "C" int ucgb200_host_dump_write(ucgb200_dump *d, ucgb200_ctx *ctx, long l
     sp.nthresh = (int)d->tcol.size();
     sp.thresh_col = d->tcol.data(); sp.thresh_op = d->top.data(); sp.thresh_value = d->tval.data();
     sp.order = d->sort_flag ? UCGB200_DUMP_ORDER_ID : UCGB200_DUMP_ORDER_INDEX;
-    dump_open(d, ntimestep);
+    dump_open(d, ctx, ntimestep);
     long long nrows = 0, nbytes = 0;
     const bool on_device = d->device_format && d->default_formats();
     const char *body = nullptr;

@@ -95,3 +95,56 @@ def test_single_brick_cluster_equals_resident_run(pkg, fixtures):
     o = np.argsort(b["tag"])
     for k in ("x", "f", "ucgp"):
         assert np.array_equal(a[k], b[k][o]), k
+
+
+def test_per_brick_dump_files_cover_the_single_domain_dump(pkg, fixtures, tmp_path):
+    """`dump ... file.%`: every brick writes its own rows (selection, sort and text on its device); together they are
+    the single-domain dump, the `proc` column names the brick"""
+    from lammps_ucg_dev_b200 import dumpio, multigpu, synth
+    ncell, nranks = (8, 8, 8), 4
+    grid = multigpu.procgrid_for(nranks)
+    whole = synth.fcc_liquid_brick(ncell, (1, 1, 1), 0)
+    parts = [synth.fcc_liquid_brick(ncell, grid, r) for r in range(nranks)]
+    box = (whole.box_lo, whole.box_hi)
+    ref = _cluster(pkg, fixtures, [whole], (1, 1, 1), box)
+    cl = _cluster(pkg, fixtures, parts, grid, box)
+    for c in (ref, cl):
+        c.setup(dict(dt=0.002, ucgstate=0))
+        c.run(25)
+    cols = "id type proc x y z vx ucgstate ucgl ucgp"
+
+    def table(path):
+        raw = open(path).read().split("ITEM: ATOMS", 1)
+        head = raw[0].split("\n")
+        rows = np.array([[float(w) for w in l.split()] for l in raw[1].split("\n")[1:] if l]).reshape(-1, 10)
+        return int(head[3]), rows
+
+    d = dumpio.DumpCustom(ref.bricks[0], "dump d all custom 25 %s %s" % (tmp_path / "one.dump", cols))
+    d.modify("dump_modify d sort id thresh ucgl > 0.3")
+    d.write(25)
+    d.close()
+    n1, t1 = table(tmp_path / "one.dump")
+    with pytest.raises(pkg.UCGError, match="one file per brick"):
+        dumpio.DumpCustom(cl.bricks[0], "dump d all custom 25 %s %s" % (tmp_path / "x.dump", cols)).write(25)
+    parts_t = []
+    for r, b in cl.bricks.items():
+        d = dumpio.DumpCustom(b, "dump d all custom 25 %s %s" % (tmp_path / "brick.%.dump", cols))
+        d.modify("dump_modify d sort id thresh ucgl > 0.3")
+        d.write(25)
+        d.close()
+        nr, tr = table(tmp_path / ("brick.%d.dump" % r))
+        assert nr == len(tr) and np.all(tr[:, 2] == r) and np.all(np.diff(tr[:, 0]) > 0)
+        parts_t.append(tr)
+    tall = np.concatenate(parts_t)
+    tall = tall[np.argsort(tall[:, 0])]
+    # a site within 1e-10 of the threshold may differ between decompositions; everything else is the same set
+    assert abs(len(tall) - n1) <= 2
+    common = np.intersect1d(tall[:, 0], t1[:, 0])
+    assert len(common) >= n1 - 2
+    a = t1[np.isin(t1[:, 0], common)]
+    b = tall[np.isin(tall[:, 0], common)]
+    assert np.array_equal(a[:, [0, 1, 7]], b[:, [0, 1, 7]])
+    L = whole.box_hi - whole.box_lo
+    dx = np.abs(a[:, 3:6] - b[:, 3:6])
+    assert np.all(np.minimum(dx, np.abs(dx - L)) <= 2e-5 * np.maximum(1.0, np.abs(a[:, 3:6])))
+    assert np.allclose(a[:, [6, 8, 9]], b[:, [6, 8, 9]], rtol=3e-6, atol=1e-9)
