@@ -275,6 +275,9 @@ int ucgb200_setup(ucgb200_ctx *ctx);
 /* Verlet::run(n) [stock] with every stage on the device; ntimestep continues from
  * the last call; beginstep/endstep of the run are (current, current+n). */
 int ucgb200_run(ucgb200_ctx *ctx, int nsteps);
+/* `run N start S stop E`: nsteps steps of a run spanning beginstep..endstep (the span only matters to ramps such
+ * as the target temperature of fix ucgld/langevin): a run cut into pieces at dump steps stays bit-identical */
+int ucgb200_run_between(ucgb200_ctx *ctx, int nsteps, long long beginstep, long long endstep);
 /* thermo scalars of the last thermo step: out[0]=eng_vdwl, out[1..6]=virial,
  * out[7]=particle KE sum, out[8]=lambda KE sum, out[9]=lambda temperature,
  * out[10]=ntimestep, out[11]=rebuild count, out[12]=nlocal, out[13]=nghost */

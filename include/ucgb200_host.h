@@ -87,6 +87,11 @@ int ucgb200_host_dump_modify(ucgb200_dump *d, int narg, const char *const *arg, 
 /* Dump::write() of one snapshot of the context's resident atoms */
 int ucgb200_host_dump_write(ucgb200_dump *d, ucgb200_ctx *ctx, long long ntimestep, double time, const char *unit_style,
                             char *errbuf, int errlen);
+/* `run N` of a resident deck (ucgb200_deck_configure + ucgb200_setup done) with dumps, as [stock] Output schedules
+ * them: every dump writes at the start of the run if the current step is a multiple of its N, then on every multiple;
+ * between dump steps the steps run on the device without touching the host (ucgb200_run_between) */
+int ucgb200_host_run(ucgb200_ctx *ctx, long long nsteps, int ndump, ucgb200_dump *const *dumps, double dt, const char *unit_style,
+                     char *errbuf, int errlen);
 int ucgb200_host_dump_stats(const ucgb200_dump *d, long long *rows, long long *bytes, int *nevery);
 
 /* `read_dump file Nstep field ... keyword value ...` on the resident atoms (native text dump files):

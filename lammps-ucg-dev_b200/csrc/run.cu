@@ -147,13 +147,22 @@ extern "C" int ucgb200_setup(ucgb200_ctx *c) {
 
 extern "C" int ucgb200_run(ucgb200_ctx *c, int nsteps) {
   if (!c || nsteps < 0) return -1;
+  return ucgb200_run_between(c, nsteps, c->ntimestep, c->ntimestep + nsteps);
+}
+
+// `run N start S stop E` [stock Run::command]: N steps of a run whose ramps (fix ucgld/langevin's target
+// temperature, fix_ucgld_langevin.cpp:318-353) span S..E — lets a caller cut a run into pieces (dump steps) without
+// changing a single bit of it
+extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginstep, long long endstep) {
+  if (!c || nsteps < 0) return -1;
   if (!c->deck_set) return fail(c, "deck not configured");
+  if (beginstep > c->ntimestep || endstep < c->ntimestep + nsteps) return fail(c, "run_between: the steps lie outside start..stop");
   cudaSetDevice(c->device);
   const ucgb200_deck &d = c->deck;
   const int gb = d.nve_groupbit ? d.nve_groupbit : 1;
   const double dtv = c->dt, dtf = 0.5 * c->dt * c->ftm2v;  // FixNVE_UCGLD::init (fix_nve_ucgld.cpp:35-41)
-  c->beginstep = c->ntimestep;
-  c->endstep = c->ntimestep + nsteps;
+  c->beginstep = beginstep;
+  c->endstep = endstep;
   int rc;
   // the per-site fix stages between two pair evaluations run as one fused kernel (fixes.cu,
   // k_step_tail) unless UCGB200_FUSED_TAIL=0; it needs an integrator fix and a single brick loop

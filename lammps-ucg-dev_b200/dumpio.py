@@ -146,6 +146,14 @@ class DumpCustom:
         return dict(rows=r.value, bytes=b.value, nevery=e.value)
 
 
+def run(ctx: Context, nsteps: int, dumps: Sequence[DumpCustom] = (), dt: float = 0.005, units: str = "lj"):
+    """`run N` of a configured resident deck with its dumps ([stock] Output scheduling)"""
+    arr = (C.c_void_p * max(len(dumps), 1))(*[d._h for d in dumps])
+    err = C.create_string_buffer(512)
+    if lib().ucgb200_host_run(ctx._h, C.c_longlong(int(nsteps)), len(dumps), arr, C.c_double(dt), units.encode(), err, 512):
+        raise UCGError(-1, err.value.decode())
+
+
 def read_dump(ctx: Context, line: str) -> dict:
     """`read_dump file Nstep field ... keyword value ...` applied to the resident atoms"""
     w = shlex.split(line)

@@ -163,7 +163,7 @@ struct ucgb200_dump {
   // run state
   FILE *fp = nullptr;
   bool opened = false;
-  long long last_rows = 0, last_bytes = 0;
+  long long last_rows = 0, last_bytes = 0, last_step = -1;
   int device_format = 1;   // rows formatted on the device whenever every format is the default one
   Staging rows, text;   // page-locked: the D2H copies of the packed rows / the formatted text land here
 
@@ -444,6 +444,38 @@ extern "C" int ucgb200_host_dump_write(ucgb200_dump *d, ucgb200_ctx *ctx, long l
     if (d->multifile) { fclose(d->fp); d->fp = nullptr; }
     d->last_rows = nrows;
     d->last_bytes = nbytes;
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(errbuf, errlen, e.what());
+  }
+}
+
+extern "C" int ucgb200_host_run(ucgb200_ctx *ctx, long long nsteps, int ndump, ucgb200_dump *const *dumps, double dt,
+                                const char *unit_style, char *errbuf, int errlen) {
+  if (!ctx || nsteps < 0 || ndump < 0 || (ndump && !dumps)) return -1;
+  try {
+    double th[16];
+    if (ucgb200_thermo(ctx, th)) throw IoError("run: " + ctx_error(ctx));
+    long long step = (long long)th[10];
+    const long long begin = step, end = step + nsteps;
+    auto write_due = [&]() {
+      for (int k = 0; k < ndump; k++) {
+        if (step % dumps[k]->nevery) continue;
+        if (dumps[k]->last_step == step && dumps[k]->opened) continue;   // already written at the end of the previous run
+        if (ucgb200_host_dump_write(dumps[k], ctx, step, (double)step * dt, unit_style, errbuf, errlen)) throw IoError(errbuf);
+        dumps[k]->last_step = step;
+      }
+    };
+    write_due();
+    while (step < end) {
+      long long next = end;
+      for (int k = 0; k < ndump; k++) next = std::min(next, (step / dumps[k]->nevery + 1) * dumps[k]->nevery);
+      const int n = (int)(next - step);
+      const int rc = ucgb200_run_between(ctx, n, begin, end);
+      if (rc) throw IoError("run: " + ctx_error(ctx) + " (rc " + std::to_string(rc) + ")");
+      step = next;
+      write_due();
+    }
     return 0;
   } catch (const std::exception &e) {
     return fail(errbuf, errlen, e.what());

@@ -250,3 +250,42 @@ def test_full_size_round_trip_1M(pkg, fixtures, tmp_path):
     assert np.allclose(a["ucgl"][o], liq.ucgl, rtol=1e-5, atol=1e-6)
     d = np.abs(a["x"][o] - liq.x)
     assert np.all(np.minimum(d, np.abs(d - L)) < 1e-3)
+
+
+def test_resident_run_with_dumps_is_the_same_run(pkg, fixtures, tmp_path):
+    """`run 45` with a dump every 10 and one every 15 steps ([stock] Output scheduling through ucgb200_host_run): the
+    pieces between dump steps run with `start/stop` semantics, so the trajectory — including the Langevin temperature
+    ramp — equals the uncut ucgb200_run bit for bit; each file holds the snapshots of its own steps, the last one
+    formats the final state"""
+    from lammps_ucg_dev_b200 import dumpio, synth
+    liq = synth.fcc_liquid(8)
+    deck = dict(pair_style=0, nve=1, langevin=1, t_start=1.0, t_stop=0.4, t_period=0.5, langevin_seed=4711, ucgstate=2)
+    finals = []
+    for cut in (False, True):
+        ctx = decks.gpu_single_type(pkg, liq, fixtures)
+        ctx.deck_configure(**deck)
+        ctx.setup()
+        if cut:
+            d10 = dumpio.DumpCustom(ctx, "dump a all custom 10 %s id x y z ucgl ucgstate" % (tmp_path / "a.dump"))
+            d15 = dumpio.DumpCustom(ctx, "dump b all custom 15 %s id ucgp" % (tmp_path / "b.*.dump"))
+            d10.modify("dump_modify a sort id")
+            d15.modify("dump_modify b pad 4")
+            dumpio.run(ctx, 45, [d10, d15], dt=0.002)
+            dumpio.run(ctx, 5, [d10, d15], dt=0.002)      # a second `run`: step 45 is not written twice
+            d10.close()
+            d15.close()
+        else:
+            ctx.run(45)
+            ctx.run(5)
+        finals.append(ctx.atoms_download(["x", "v", "ucgl", "ucgvl", "ucgp", "ucgstate", "tag"]))
+    for k in finals[0]:
+        assert np.array_equal(finals[0][k], finals[1][k]), k
+    text = open(tmp_path / "a.dump").read()
+    steps = [int(b.split("\n")[1]) for b in text.split("ITEM: TIMESTEP")[1:]]
+    assert steps == [0, 10, 20, 30, 40, 50]
+    assert sorted(p.name for p in tmp_path.glob("b.*.dump")) == ["b.0000.dump", "b.0015.dump", "b.0030.dump", "b.0045.dump"]
+    a = finals[1]
+    o = np.argsort(a["tag"])
+    buf = np.stack([a["tag"][o], a["x"][o, 0], a["x"][o, 1], a["x"][o, 2], a["ucgl"][o], a["ucgstate"][o]], axis=1)
+    last = text.split("ITEM: ATOMS id x y z ucgl ucgstate\n")[-1]
+    assert last.encode() == IO.lines(buf, ["id", "x", "y", "z", "ucgl", "ucgstate"])
