@@ -275,6 +275,8 @@ int ucgb200_setup(ucgb200_ctx *ctx);
 /* Verlet::run(n) [stock] with every stage on the device; ntimestep continues from
  * the last call; beginstep/endstep of the run are (current, current+n). */
 int ucgb200_run(ucgb200_ctx *ctx, int nsteps);
+/* update->ntimestep at the start of a run (reset_timestep, read_dump, a host driver taking over) */
+int ucgb200_set_ntimestep(ucgb200_ctx *ctx, long long ntimestep);
 /* `run N start S stop E`: nsteps steps of a run spanning beginstep..endstep (the span only matters to ramps such
  * as the target temperature of fix ucgld/langevin): a run cut into pieces at dump steps stays bit-identical */
 int ucgb200_run_between(ucgb200_ctx *ctx, int nsteps, long long beginstep, long long endstep);

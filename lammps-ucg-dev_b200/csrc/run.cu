@@ -227,6 +227,12 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
   return 0;
 }
 
+extern "C" int ucgb200_set_ntimestep(ucgb200_ctx *c, long long ntimestep) {
+  if (!c || ntimestep < 0) return -1;
+  c->ntimestep = ntimestep;
+  return 0;
+}
+
 extern "C" int ucgb200_thermo(ucgb200_ctx *c, double out[16]) {
   if (!c || !out) return -1;
   cudaSetDevice(c->device);

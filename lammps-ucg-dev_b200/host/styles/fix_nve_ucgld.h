@@ -11,12 +11,12 @@ FixStyle(nve/ucgld, FixNVE_UCGLD);
 // only flips `hard_wall`.
 
 #include "fix.h"
+#include "ucg_device.h"
 
 namespace LAMMPS_NS {
 
-class UCGDevice;
 
-class FixNVE_UCGLD : public Fix {
+class FixNVE_UCGLD : public Fix, public UCGDeckPart {
  protected:
   UCGDevice *dev;         // the device context shared by every UCG style of this LAMMPS instance
   int hard_wall;          // 1: lambda is reflected at 0 and 1 and the discrete state follows lambda
@@ -33,6 +33,7 @@ class FixNVE_UCGLD : public Fix {
   void initial_integrate(int) override;
   void final_integrate_respa(int, int) override;
   void initial_integrate_respa(int, int, int) override;
+  void ucg_deck(ucgb200_deck &deck) const override;
 };
 
 }  // namespace LAMMPS_NS

@@ -11,12 +11,12 @@ FixStyle(ucgld/langevin, Fix_UCGLD_Langevin);
 // Thermostat of the lambda degree of freedom; exports "t_target" to the pair styles and to fix ucgstate.
 
 #include "fix.h"
+#include "ucg_device.h"
 
 namespace LAMMPS_NS {
 
-class UCGDevice;
 
-class Fix_UCGLD_Langevin : public Fix {
+class Fix_UCGLD_Langevin : public Fix, public UCGDeckPart {
  protected:
   UCGDevice *dev;
   struct Ramp {            // linear temperature ramp over the run
@@ -46,6 +46,7 @@ class Fix_UCGLD_Langevin : public Fix {
   int modify_param(int, char **) override;
   void *extract(const char *, int &) override;
   void post_force_respa(int, int, int) override;
+  void ucg_deck(ucgb200_deck &deck) const override;
 };
 
 }  // namespace LAMMPS_NS

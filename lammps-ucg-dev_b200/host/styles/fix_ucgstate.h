@@ -11,12 +11,12 @@ FixStyle(ucgstate, FixUCGState);
 // with a counter-based RNG keyed by site tag and time step) and ucgl = ucgp.
 
 #include "fix.h"
+#include "ucg_device.h"
 
 namespace LAMMPS_NS {
 
-class UCGDevice;
 
-class FixUCGState : public Fix {
+class FixUCGState : public Fix, public UCGDeckPart {
   UCGDevice *dev;
   int lambda_only;        // `ld`: probabilities only, lambda dynamics owns the state
   int monte_carlo;        // `mc seed rate`
@@ -31,6 +31,7 @@ class FixUCGState : public Fix {
   void post_force(int) override;
   void min_post_force(int) override;
   void post_force_respa(int, int, int) override;
+  void ucg_deck(ucgb200_deck &deck) const override;
 };
 
 }  // namespace LAMMPS_NS

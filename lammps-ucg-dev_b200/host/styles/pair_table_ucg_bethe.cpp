@@ -47,6 +47,14 @@ void PairTable_UCG_Bethe::settings(int narg, char **arg) {
   PairTable_UCGLD::settings((int) rest.size(), rest.data());
 }
 
+bool PairTable_UCG_Bethe::ucg_deck(ucgb200_deck &deck) const {
+  deck.pair_style = 1;
+  deck.bethe_method = method_flag;
+  deck.bethe_pseudo = pseudo_flag;
+  deck.bethe_prior = prior_flag;
+  return prior_flag != CHEMICAL_POTENTIAL_NOISE;   // the noise prior keeps its own RNG stream: offload mode only
+}
+
 void PairTable_UCG_Bethe::device_compute(int eflag, int vflag) {
   dev->check(lmp, ucgb200_pair_bethe(dev->ctx, eflag, vflag, method_flag, pseudo_flag, prior_flag, noise_level, seed), "pair_bethe");
 }

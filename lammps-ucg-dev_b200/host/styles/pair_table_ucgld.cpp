@@ -249,6 +249,11 @@ double PairTable_UCGLD::single(int, int, int itype, int jtype, double rsq, doubl
   return phi;
 }
 
+bool PairTable_UCGLD::ucg_deck(ucgb200_deck &deck) const {
+  deck.pair_style = 0;
+  return true;
+}
+
 void *PairTable_UCGLD::extract(const char *str, int &dim) {
   if (strcmp(str, "cut_coul") != 0) return nullptr;
   if (tables.empty()) error->all(FLERR, Error::NOLASTLINE, "All pair coeffs are not set");

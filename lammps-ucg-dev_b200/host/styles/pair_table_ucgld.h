@@ -32,6 +32,8 @@ class PairTable_UCGLD : public Pair {
   void read_restart_settings(FILE *) override;
   double single(int, int, int, int, double, double, double, double &) override;
   void *extract(const char *, int &) override;
+  // this style's part of the resident deck (run_style ucg/b200); false when the resident loop cannot run it
+  virtual bool ucg_deck(ucgb200_deck &deck) const;
   enum { LOOKUP, LINEAR, SPLINE, BITMAP };
 
  protected:

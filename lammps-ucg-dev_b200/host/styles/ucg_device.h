@@ -21,6 +21,14 @@
 
 namespace LAMMPS_NS {
 
+// what a UCG style contributes to the resident integrator (run_style ucg/b200): each class writes its own
+// part of the ucgb200_deck the device runs (include/ucgb200.h "resident run")
+class UCGDeckPart {
+ public:
+  virtual ~UCGDeckPart() = default;
+  virtual void ucg_deck(ucgb200_deck &deck) const = 0;
+};
+
 class UCGDevice {
  public:
   ucgb200_ctx *ctx = nullptr;

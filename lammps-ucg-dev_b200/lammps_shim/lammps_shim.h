@@ -649,7 +649,15 @@ class Force : protected Pointers {
 class Integrate : protected Pointers {
  public:
   explicit Integrate(LAMMPS *l) : Pointers(l) {}
+  Integrate(LAMMPS *l, int, char **) : Pointers(l) {}
   virtual ~Integrate() = default;
+  virtual void init() {}
+  virtual void setup(int) {}
+  virtual void setup_minimal(int) {}
+  virtual void run(int) {}
+  virtual void force_clear() {}
+  virtual void cleanup() {}
+  virtual void reset_dt() {}
 };
 class Respa : public Integrate {
  public:
@@ -712,6 +720,13 @@ class Input : protected Pointers {
 class Output : protected Pointers {
  public:
   explicit Output(LAMMPS *l) : Pointers(l) {}
+  bigint next = MAXBIGINT;   // next step any output (thermo, dump, restart) is due
+  int thermo_every = 0;
+  // implemented by the serial driver
+  void (*write_hook)(void *, bigint) = nullptr;
+  void *hook_arg = nullptr;
+  void setup(int = 1) {}
+  void write(bigint step) { if (write_hook) write_hook(hook_arg, step); }
 };
 
 class Group : protected Pointers {

@@ -19,6 +19,7 @@
 #ifdef UCG_PRODUCT_STYLES   // oracle/Makefile.hostdrv: the product's GPU-backed classes under the same deck words
 #include "dump_custom_ucg_b200.h"
 #include "read_dump_ucg_b200.h"
+#include "verlet_ucg_b200.h"
 namespace LAMMPS_NS {
 typedef DumpCustomUCGB200 DumpCustom;
 typedef ReadDumpUCGB200 ReadDump;
@@ -462,11 +463,17 @@ struct Sim {
     lmp.force->pair->compute(eflag, vflag);
     if (lmp.force->newton) reverse_comm();
   }
+  bool resident = false;   // run_style ucg/b200 (product build only): the integrator class owns setup and run
   void setup(int ev) {
     lmp.update->whichflag = 1;
     init();
     lmp.update->beginstep = lmp.update->firststep = lmp.update->ntimestep;
     lmp.update->endstep = lmp.update->laststep = lmp.update->ntimestep;
+    if (resident) {
+      lmp.update->integrate->init();
+      lmp.update->integrate->setup(1);
+      return;
+    }
     for (int i = 0; i < lmp.modify->nfix; i++) if (lmp.modify->fmask[i] & FixConst::PRE_EXCHANGE) lmp.modify->fix[i]->setup_pre_exchange();
     pbc();
     borders();
@@ -481,6 +488,16 @@ struct Sim {
     u->beginstep = u->firststep = u->ntimestep;
     u->endstep = u->laststep = u->ntimestep + nsteps;
     for (int k = 0; k < 4; k++) timers[k] = 0;
+    if (resident) {   // [stock] Run::command: Output knows the next thermo step, Integrate::run does the rest
+      Output *o = lmp.output;
+      o->thermo_every = thermo_every;
+      o->next = thermo_every > 0 ? (u->ntimestep / thermo_every + 1) * (bigint)thermo_every : MAXBIGINT;
+      o->hook_arg = this;
+      o->write_hook = [](void *a, bigint) { Output *oo = ((Sim *)a)->lmp.output; oo->next += oo->thermo_every; };
+      u->integrate->run(nsteps);
+      u->integrate->cleanup();
+      return;
+    }
     for (int n = 0; n < nsteps; n++) {
       u->ntimestep++;
       int ev = thermo_every > 0 && (u->ntimestep % thermo_every == 0);
@@ -589,6 +606,16 @@ struct Sim {
       // is whatever the allocator left; this presets it (quirk Q24)
       const int v = utils::inumeric(FLERR, w.at(1), false, &lmp);
       for (int i = 0; i < lmp.atom->nlocal + lmp.atom->nghost; i++) lmp.atom->num_ucgstates[i] = v;
+    } else if (cmd == "run_style") {
+#ifdef UCG_PRODUCT_STYLES
+      if (w.at(1) == "ucg/b200") {
+        delete lmp.update->integrate;
+        lmp.update->integrate = new VerletUCGB200(&lmp, narg, arg.data());
+        lmp.update->integrate_style = (char *)"ucg/b200";
+        resident = true;
+      } else
+#endif
+      if (w.at(1) != "verlet") lmp.error->all(FLERR, "Unrecognized integrate style '{}'", w.at(1));
     } else if (cmd == "group") {
       // harness-only: "group NAME" registers the next free group bit; masks come in through ref_atoms
       if (lmp.group->find(w.at(1)) < 0) lmp.group->names[lmp.group->ngroup++] = utils::strdup(w.at(1));

@@ -258,3 +258,59 @@ def test_dump_and_read_dump_decks(pkg, fixtures, tmp_path):
         s.run(3, 0)
     a, b = ref.get_atoms(), gpu.get_atoms()
     assert rel_err(b["x"], a["x"]) <= 1e-10 and rel_err(b["ucgp"], a["ucgp"]) <= 1e-8
+
+
+@pytest.mark.parametrize("fixes,tols", [
+    (["fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld", "fix 2 all ucgstate"], "deterministic"),
+    (["fix 1 all nve/ucgld/wall/hard bias_potential 0.2", "fix 2 all ucgld/langevin 1.0 0.6 0.5 4711", "fix 3 all ucgstate ld"], "langevin"),
+])
+def test_run_style_ucg_b200_is_the_offload_run_kept_on_the_device(pkg, fixtures, fixes, tols):
+    """`run_style ucg/b200` (VerletUCGB200: deck handed to ucgb200_setup / ucgb200_run_between, host arrays refreshed on
+    thermo steps and at the end) against the same classes driven call by call by the stock Verlet order (offload mode):
+    the trajectory is identical; and, for the deterministic deck, equal to the reference's within the usual tolerances"""
+    liq = _liq(6)
+    sims = {}
+    for tag, cls, resident in (("ref", rb.RefSim, False), ("offload", rb.HostSim, False), ("resident", rb.HostSim, True)):
+        s = cls.single_type(liq, fixtures["table4096"], fixtures["state"])
+        for f in fixes:
+            s.command(f)
+        if resident:
+            s.command("run_style ucg/b200")
+        s.setup(1)
+        e0 = s.eng_vdwl()
+        s.run(12, 6)
+        s.run(13, 0)      # a second run continues from the device state pulled at the end of the first
+        sims[tag] = (s, e0)
+    a, b = sims["offload"][0].get_atoms(), sims["resident"][0].get_atoms()
+    for k in ("x", "v", "f", "ucgl", "ucgvl", "ucgp", "ucgforce", "ucgsoftmaxscores", "ucgstate", "num_ucgstates"):
+        assert np.array_equal(a[k], b[k]), k
+    assert sims["offload"][1] == sims["resident"][1]                      # setup energy
+    assert sims["resident"][0].ntimestep() == 25
+    if tols == "deterministic":
+        r = sims["ref"][0].get_atoms()
+        assert rel_err(b["x"], r["x"]) <= 1e-10 and rel_err(b["f"], r["f"]) <= 1e-6 and rel_err(b["ucgp"], r["ucgp"]) <= 1e-8
+        assert abs(sims["resident"][1] - sims["ref"][1]) <= 1e-8 * abs(sims["ref"][1])
+
+
+def test_run_style_ucg_b200_rejects_what_it_cannot_run(pkg, fixtures):
+    liq = _liq(4)
+    s = rb.HostSim.single_type(liq, fixtures["table4096"], fixtures["state"], pair="table_ucg_bethe",
+                               extra="prior chemical_potential noise 0.1 77")
+    s.command("fix 0 all ttarget/stub 1.0")
+    s.command("fix 1 all nve/ucgld")
+    s.command("run_style ucg/b200")
+    with pytest.raises(RuntimeError, match="without the noise prior"):
+        s.setup(1)
+    # the same deck without the noise prior runs, and equals the offload run
+    out = []
+    for resident in (False, True):
+        s = rb.HostSim.single_type(liq, fixtures["table4096"], fixtures["state"], pair="table_ucg_bethe", extra="method bethe prior ucgl")
+        for f in ("fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld", "fix 2 all ucgstate"):
+            s.command(f)
+        if resident:
+            s.command("run_style ucg/b200")
+        s.setup(1)
+        s.run(10, 0)
+        out.append(s.get_atoms())
+    for k in ("x", "f", "ucgp", "ucgstate"):
+        assert np.array_equal(out[0][k], out[1][k]), k
