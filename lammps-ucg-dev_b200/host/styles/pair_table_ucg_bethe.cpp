@@ -47,7 +47,8 @@ void PairTable_UCG_Bethe::settings(int narg, char **arg) {
   PairTable_UCGLD::settings((int) rest.size(), rest.data());
 }
 
-bool PairTable_UCG_Bethe::ucg_deck(ucgb200_deck &deck) const {
+bool PairTable_UCG_Bethe::ucg_deck(ucgb200_deck &deck) {
+  PairTable_UCGLD::ucg_deck(deck);
   deck.pair_style = 1;
   deck.bethe_method = method_flag;
   deck.bethe_pseudo = pseudo_flag;

@@ -18,7 +18,7 @@ class PairTable_UCG_Bethe : public PairTable_UCGLD {
  public:
   PairTable_UCG_Bethe(class LAMMPS *);
   void settings(int, char **) override;
-  bool ucg_deck(ucgb200_deck &deck) const override;
+  bool ucg_deck(ucgb200_deck &deck) override;
   enum { MF, BETHE };
   enum { CHEMICAL_POTENTIAL, CHEMICAL_POTENTIAL_NOISE, UCGL };
 

@@ -249,7 +249,8 @@ double PairTable_UCGLD::single(int, int, int itype, int jtype, double rsq, doubl
   return phi;
 }
 
-bool PairTable_UCGLD::ucg_deck(ucgb200_deck &deck) const {
+bool PairTable_UCGLD::ucg_deck(ucgb200_deck &deck) {
+  if (!maps_applied) apply_maps();   // types, tables -> type maps, kT, skin: what the first compute() would send
   deck.pair_style = 0;
   return true;
 }

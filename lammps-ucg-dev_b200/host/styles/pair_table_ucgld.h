@@ -33,7 +33,7 @@ class PairTable_UCGLD : public Pair {
   double single(int, int, int, int, double, double, double, double &) override;
   void *extract(const char *, int &) override;
   // this style's part of the resident deck (run_style ucg/b200); false when the resident loop cannot run it
-  virtual bool ucg_deck(ucgb200_deck &deck) const;
+  virtual bool ucg_deck(ucgb200_deck &deck);
   enum { LOOKUP, LINEAR, SPLINE, BITMAP };
 
  protected:
