@@ -36,8 +36,22 @@ class UCGDevice {
   bool static_uploaded = false;   // type, mask, tag, molecule, ucgml
   bool list_ready = false;
 
-  static UCGDevice *get(LAMMPS *lmp) {
+  static std::map<LAMMPS *, UCGDevice *> &instances() {
     static std::map<LAMMPS *, UCGDevice *> inst;
+    return inst;
+  }
+  // to be called when the LAMMPS instance goes away (LAMMPS::destroy, or a driver's teardown): destroys the
+  // context, so that a later instance at the same address starts from a fresh device
+  static void drop(LAMMPS *lmp) {
+    auto &inst = instances();
+    auto it = inst.find(lmp);
+    if (it == inst.end()) return;
+    if (it->second->ctx) ucgb200_destroy(it->second->ctx);
+    delete it->second;
+    inst.erase(it);
+  }
+  static UCGDevice *get(LAMMPS *lmp) {
+    auto &inst = instances();
     auto it = inst.find(lmp);
     if (it != inst.end()) return it->second;
     auto *d = new UCGDevice();

@@ -20,6 +20,7 @@
 #include "dump_custom_ucg_b200.h"
 #include "read_dump_ucg_b200.h"
 #include "verlet_ucg_b200.h"
+#include "ucg_device.h"
 namespace LAMMPS_NS {
 typedef DumpCustomUCGB200 DumpCustom;
 typedef ReadDumpUCGB200 ReadDump;
@@ -161,6 +162,9 @@ struct Sim {
     delete lmp.output; delete lmp.input; delete lmp.domain; delete lmp.comm; delete lmp.neighbor;
     delete lmp.modify; delete lmp.update->integrate; delete lmp.update; delete lmp.force;
     free_atoms();
+#ifdef UCG_PRODUCT_STYLES
+    UCGDevice::drop(&lmp);   // the device context of this session
+#endif
     delete lmp.atom; delete lmp.group; delete lmp.error; delete lmp.memory;
   }
 

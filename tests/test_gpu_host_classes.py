@@ -282,8 +282,16 @@ def test_run_style_ucg_b200_is_the_offload_run_kept_on_the_device(pkg, fixtures,
         s.run(13, 0)      # a second run continues from the device state pulled at the end of the first
         sims[tag] = (s, e0)
     a, b = sims["offload"][0].get_atoms(), sims["resident"][0].get_atoms()
-    for k in ("x", "v", "f", "ucgl", "ucgvl", "ucgp", "ucgforce", "ucgsoftmaxscores", "ucgstate", "num_ucgstates"):
-        assert np.array_equal(a[k], b[k]), k
+    # the deterministic deck is bit-identical; with the Langevin / wall stages the fused per-site pass of the resident loop
+    # contracts a few multiply-adds differently from the single-stage kernels: last-bit differences
+    exact = tols == "deterministic"
+    for k in ("x", "v", "f", "ucgl", "ucgvl", "ucgp", "ucgforce", "ucgsoftmaxscores"):
+        if exact:
+            assert np.array_equal(a[k], b[k]), (k, float(np.abs(a[k] - b[k]).max()), int((a[k] != b[k]).sum()))
+        else:
+            assert rel_err(b[k], a[k]) <= 1e-11, (k, rel_err(b[k], a[k]))
+    away = np.abs(a["ucgl"] - 0.5) > 1e-9
+    assert np.array_equal(a["ucgstate"][away], b["ucgstate"][away]) and np.array_equal(a["num_ucgstates"], b["num_ucgstates"])
     assert sims["offload"][1] == sims["resident"][1]                      # setup energy
     assert sims["resident"][0].ntimestep() == 25
     if tols == "deterministic":
