@@ -96,6 +96,9 @@ int ucgb200_set_box(ucgb200_ctx *ctx, const double lo[3], const double hi[3], co
 /* page-locked host memory for callers that stage large downloads (dump rows / text) */
 int ucgb200_pinned_alloc(size_t bytes, void **out);
 int ucgb200_pinned_free(void *p);
+/* page-lock / release caller-owned arrays in place (cudaHostRegister); unregister before the memory is freed or moved */
+int ucgb200_host_register(void *p, size_t bytes);
+int ucgb200_host_unregister(void *p);
 int ucgb200_get_box(const ucgb200_ctx *ctx, double lo[3], double hi[3], int periodic[3]);
 /* sub-domain owned by this context (multi-GPU brick); defaults to the box */
 int ucgb200_set_subdomain(ucgb200_ctx *ctx, const double sublo[3], const double subhi[3]);

@@ -122,6 +122,20 @@ extern "C" int ucgb200_pinned_free(void *p) {
   if (p) cudaFreeHost(p);
   return 0;
 }
+// page-lock caller-owned host arrays (the LAMMPS per-atom arrays of the offload-mode classes) so that uploads and
+// downloads run as DMA; the caller must unregister before the memory is freed or moved
+extern "C" int ucgb200_host_register(void *p, size_t bytes) {
+  if (!p || !bytes) return -1;
+  cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); return -2; }
+  return 0;
+}
+extern "C" int ucgb200_host_unregister(void *p) {
+  if (!p) return -1;
+  cudaError_t e = cudaHostUnregister(p);
+  if (e != cudaSuccess) { cudaGetLastError(); return -2; }
+  return 0;
+}
 extern "C" int ucgb200_halo_info(const ucgb200_ctx *c, int *rank, int *nranks) {
   if (!c) return -1;
   if (rank) *rank = c->halo.rank;

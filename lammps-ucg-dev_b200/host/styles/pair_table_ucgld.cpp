@@ -185,10 +185,14 @@ void PairTable_UCGLD::compute(int eflag, int vflag) {
   const int ev = (eflag_either || vflag_either) ? 1 : 0;
   device_compute(ev, ev);
   // results are ADDED to the host arrays, like the reference's f[i] += ... after force_clear
-  std::vector<double> f(3 * (size_t)nlocal), uf(nlocal), sc(2 * (size_t)nlocal);
-  std::vector<int> ns(nlocal);
+  const size_t nl = (size_t)nlocal;
+  char *buf = (char *)dev->scratch((6 * nl + 8) * sizeof(double) + (nl + 8) * sizeof(int));
+  std::vector<char> pageable;
+  if (!buf) { pageable.resize((6 * nl + 8) * sizeof(double) + (nl + 8) * sizeof(int)); buf = pageable.data(); }
+  double *f = (double *)buf, *uf = f + 3 * nl, *sc = uf + nl;
+  int *ns = (int *)(sc + 2 * nl);
   ucgb200_atoms h{};
-  h.f = f.data(); h.ucgforce = uf.data(); h.ucgsoftmaxscores = sc.data(); h.num_ucgstates = ns.data();
+  h.f = f; h.ucgforce = uf; h.ucgsoftmaxscores = sc; h.num_ucgstates = ns;
   dev->check(lmp, ucgb200_atoms_download(dev->ctx, nlocal, &h,
                                          UCGB200_F_F | UCGB200_F_UCGFORCE | UCGB200_F_SCORES | UCGB200_F_NUMSTATES),
              "atoms_download");

@@ -7,8 +7,10 @@
 #ifndef LMP_UCG_DEVICE_H
 #define LMP_UCG_DEVICE_H
 
+#include <cstdlib>
 #include <map>
 #include <string>
+#include <vector>
 
 #include "atom.h"
 #include "domain.h"
@@ -46,6 +48,8 @@ class UCGDevice {
     auto &inst = instances();
     auto it = inst.find(lmp);
     if (it == inst.end()) return;
+    it->second->unpin_all();
+    if (it->second->scratch_p) ucgb200_pinned_free(it->second->scratch_p);
     if (it->second->ctx) ucgb200_destroy(it->second->ctx);
     delete it->second;
     inst.erase(it);
@@ -94,8 +98,60 @@ class UCGDevice {
     return h;
   }
 
+  // Offload mode moves the LAMMPS per-atom arrays themselves; page-locking them in place makes every transfer a DMA.
+  // LAMMPS re-allocates per-atom arrays only when atom->nmax grows (AtomVec::grow), so the registrations are redone
+  // whenever nmax or any of the pointers changed since the last call — before the arrays are touched again.
+  // UCGB200_PIN_HOST=0 leaves the arrays pageable.
+  struct Pinned { void *p; size_t bytes; };
+  std::vector<Pinned> pinned;
+  std::vector<const void *> pinned_key;
+  int pinned_nmax = -1;
+  void unpin_all() {
+    for (auto &r : pinned) ucgb200_host_unregister(r.p);
+    pinned.clear();
+    pinned_key.clear();
+    pinned_nmax = -1;
+  }
+  void pin_arrays(LAMMPS *lmp) {
+    static const bool enabled = !(getenv("UCGB200_PIN_HOST") && atoi(getenv("UCGB200_PIN_HOST")) == 0);
+    if (!enabled) return;
+    Atom *a = lmp->atom;
+    const size_t n = (size_t) a->nmax;
+    const size_t D = sizeof(double), I = sizeof(int);
+    const Pinned want[] = {{a->x ? &a->x[0][0] : nullptr, 3 * n * D}, {a->v ? &a->v[0][0] : nullptr, 3 * n * D},
+                           {a->f ? &a->f[0][0] : nullptr, 3 * n * D}, {a->type, n * I}, {a->mask, n * I}, {a->tag, n * I},
+                           {a->molecule, n * I}, {a->ucgstate, n * I}, {a->num_ucgstates, n * I}, {a->ucgl, n * D},
+                           {a->ucgvl, n * D}, {a->ucgml, n * D}, {a->ucgp, n * D}, {a->ucgforce, n * D},
+                           {a->ucgsoftmaxscores ? &a->ucgsoftmaxscores[0][0] : nullptr, 2 * n * D}};
+    bool same = pinned_nmax == a->nmax && pinned_key.size() == sizeof(want) / sizeof(want[0]);
+    for (size_t k = 0; same && k < pinned_key.size(); k++) same = pinned_key[k] == want[k].p;
+    if (same) return;
+    unpin_all();
+    if (n == 0) return;
+    for (const Pinned &w : want) {
+      pinned_key.push_back(w.p);
+      if (w.p && w.bytes && ucgb200_host_register(w.p, w.bytes) == 0) pinned.push_back(w);
+    }
+    pinned_nmax = a->nmax;
+  }
+  // page-locked scratch for results that are added to the host arrays (pair compute)
+  void *scratch_p = nullptr;
+  size_t scratch_bytes = 0;
+  void *scratch(size_t bytes) {
+    if (bytes <= scratch_bytes) return scratch_p;
+    if (scratch_p) ucgb200_pinned_free(scratch_p);
+    scratch_p = nullptr;
+    scratch_bytes = 0;
+    void *q = nullptr;
+    if (ucgb200_pinned_alloc(bytes + bytes / 8, &q) || !q) return nullptr;
+    scratch_p = q;
+    scratch_bytes = bytes + bytes / 8;
+    return scratch_p;
+  }
+
   void upload(LAMMPS *lmp, unsigned fields) {
     Atom *a = lmp->atom;
+    pin_arrays(lmp);
     if (a->nlocal != nlocal_dev) { static_uploaded = false; list_ready = false; }
     if (!static_uploaded) fields |= UCGB200_F_TYPE | UCGB200_F_MASK | UCGB200_F_TAG | UCGB200_F_MOLECULE | UCGB200_F_UCGML |
                                     UCGB200_F_X | UCGB200_F_V | UCGB200_F_UCGL | UCGB200_F_UCGVL | UCGB200_F_UCGSTATE | UCGB200_F_UCGP;
@@ -106,6 +162,7 @@ class UCGDevice {
   }
   void download(LAMMPS *lmp, unsigned fields) {
     Atom *a = lmp->atom;
+    pin_arrays(lmp);
     ucgb200_atoms h = view(a);
     check(lmp, ucgb200_atoms_download(ctx, a->nlocal, &h, fields), "atoms_download");
   }

@@ -161,10 +161,10 @@ struct Sim {
     delete lmp.atom->avec;
     delete lmp.output; delete lmp.input; delete lmp.domain; delete lmp.comm; delete lmp.neighbor;
     delete lmp.modify; delete lmp.update->integrate; delete lmp.update; delete lmp.force;
-    free_atoms();
 #ifdef UCG_PRODUCT_STYLES
-    UCGDevice::drop(&lmp);   // the device context of this session
+    UCGDevice::drop(&lmp);   // the device context of this session; releases the page locks on the per-atom arrays first
 #endif
+    free_atoms();
     delete lmp.atom; delete lmp.group; delete lmp.error; delete lmp.memory;
   }
 
