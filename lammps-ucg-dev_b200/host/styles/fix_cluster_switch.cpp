@@ -129,7 +129,7 @@ int FixClusterSwitch::setmask() { return PRE_EXCHANGE; }
 
 void FixClusterSwitch::init() {
   // the reference asks for its own full list (:395); the device keeps one full list for every style
-  neighbor->add_request(this, NeighConst::REQ_FULL);
+  // (no host-side list either: the labelling runs on the device list)
 }
 
 void FixClusterSwitch::init_list(int, NeighList *ptr) { list = ptr; }

@@ -134,7 +134,8 @@ void PairTable_UCGLD::coeff(int narg, char **arg) {
 }
 
 void PairTable_UCGLD::init_style() {
-  neighbor->add_request(this);
+  // no neighbor->add_request(): the device builds and owns the (full) list, following the same skin rule; LAMMPS
+  // keeps its ghost exchange (cutghost = cutforce + skin) but spends nothing on a host-side pair list
   double *pT = nullptr;
   int pdim;
   kT_found = false;
