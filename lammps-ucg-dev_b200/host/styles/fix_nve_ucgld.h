@@ -33,7 +33,7 @@ class FixNVE_UCGLD : public Fix, public UCGDeckPart {
   void initial_integrate(int) override;
   void final_integrate_respa(int, int) override;
   void initial_integrate_respa(int, int, int) override;
-  void ucg_deck(ucgb200_deck &deck) const override;
+  bool ucg_deck(ucgb200_deck &deck) override;
 };
 
 }  // namespace LAMMPS_NS

@@ -24,7 +24,7 @@ class FixNVE_UCGLD_Wall_Hard : public FixNVE_UCGLD {
   FixNVE_UCGLD_Wall_Hard(class LAMMPS *, int, char **);
   void post_force(int) override;
   int setmask() override;
-  void ucg_deck(ucgb200_deck &deck) const override;
+  bool ucg_deck(ucgb200_deck &deck) override;
 };
 
 }  // namespace LAMMPS_NS

@@ -46,7 +46,7 @@ class Fix_UCGLD_Langevin : public Fix, public UCGDeckPart {
   int modify_param(int, char **) override;
   void *extract(const char *, int &) override;
   void post_force_respa(int, int, int) override;
-  void ucg_deck(ucgb200_deck &deck) const override;
+  bool ucg_deck(ucgb200_deck &deck) override;
 };
 
 }  // namespace LAMMPS_NS

@@ -31,7 +31,7 @@ class FixUCGState : public Fix, public UCGDeckPart {
   void post_force(int) override;
   void min_post_force(int) override;
   void post_force_respa(int, int, int) override;
-  void ucg_deck(ucgb200_deck &deck) const override;
+  bool ucg_deck(ucgb200_deck &deck) override;
 };
 
 }  // namespace LAMMPS_NS

@@ -201,6 +201,12 @@ void PairTable_RLEUCG_INTERFACE::configure_device() {
   configured = true;
 }
 
+bool PairTable_RLEUCG_INTERFACE::ucg_deck(ucgb200_deck &deck) {
+  if (!configured) configure_device();
+  deck.pair_style = 2;
+  return true;
+}
+
 void PairTable_RLEUCG_INTERFACE::compute(int eflag, int vflag) {
   ev_init(eflag, vflag);
   if (!configured) configure_device();

@@ -18,16 +18,18 @@ PairStyle(table_rleucg_interface, PairTable_RLEUCG_INTERFACE)
 
 #include "pair.h"
 #include "ucgb200_host.h"
+#include "ucg_device.h"
 
 #include <vector>
 
 namespace LAMMPS_NS {
 
-class PairTable_RLEUCG_INTERFACE : public Pair {
+class PairTable_RLEUCG_INTERFACE : public Pair, public UCGDeckPart {
  public:
   PairTable_RLEUCG_INTERFACE(class LAMMPS *);
   ~PairTable_RLEUCG_INTERFACE() override;
   void compute(int, int) override;
+  bool ucg_deck(ucgb200_deck &deck) override;
   void settings(int, char **) override;
   void coeff(int, char **) override;
   void init_style() override;

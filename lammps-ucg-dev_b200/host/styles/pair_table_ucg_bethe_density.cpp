@@ -139,8 +139,7 @@ void PairTable_UCG_Bethe_Density::init_style() {
   density_applied = false;
 }
 
-void PairTable_UCG_Bethe_Density::compute(int eflag, int vflag) {
-  ev_init(eflag, vflag);
+void PairTable_UCG_Bethe_Density::configure_device() {
   if (!maps_applied) apply_maps();
   if (!density_applied) {
     dev->check(lmp, ucgb200_pair_bethe_density_configure(dev->ctx, n_actual, use_density.data(), use_state_entropy.data(),
@@ -148,6 +147,17 @@ void PairTable_UCG_Bethe_Density::compute(int eflag, int vflag) {
                "pair_bethe_density_configure");
     density_applied = true;
   }
+}
+
+bool PairTable_UCG_Bethe_Density::ucg_deck(ucgb200_deck &deck) {
+  configure_device();
+  deck.pair_style = 3;
+  return true;
+}
+
+void PairTable_UCG_Bethe_Density::compute(int eflag, int vflag) {
+  ev_init(eflag, vflag);
+  configure_device();
   const int nlocal = atom->nlocal;
   dev->upload(lmp, UCGB200_F_X | UCGB200_F_UCGL | UCGB200_F_UCGSTATE | UCGB200_F_UCGP);
   dev->ensure_list(lmp);

@@ -26,6 +26,8 @@ class PairTable_UCG_Bethe_Density : public PairTable_UCGLD {
  public:
   PairTable_UCG_Bethe_Density(class LAMMPS *);
   void compute(int, int) override;
+  bool ucg_deck(ucgb200_deck &deck) override;
+  void configure_device();
   void settings(int, char **) override;
   void init_style() override;
 

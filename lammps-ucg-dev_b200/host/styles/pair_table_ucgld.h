@@ -12,12 +12,13 @@ PairStyle(table_ucgld, PairTable_UCGLD)
 
 #include "pair.h"
 #include "ucgb200_host.h"
+#include "ucg_device.h"
 
 #include <vector>
 
 namespace LAMMPS_NS {
 
-class PairTable_UCGLD : public Pair {
+class PairTable_UCGLD : public Pair, public UCGDeckPart {
  public:
   PairTable_UCGLD(class LAMMPS *);
   ~PairTable_UCGLD() override;
@@ -32,8 +33,7 @@ class PairTable_UCGLD : public Pair {
   void read_restart_settings(FILE *) override;
   double single(int, int, int, int, double, double, double, double &) override;
   void *extract(const char *, int &) override;
-  // this style's part of the resident deck (run_style ucg/b200); false when the resident loop cannot run it
-  virtual bool ucg_deck(ucgb200_deck &deck);
+  bool ucg_deck(ucgb200_deck &deck) override;   // this style's part of the resident deck (run_style ucg/b200)
   enum { LOOKUP, LINEAR, SPLINE, BITMAP };
 
  protected:

@@ -28,7 +28,8 @@ namespace LAMMPS_NS {
 class UCGDeckPart {
  public:
   virtual ~UCGDeckPart() = default;
-  virtual void ucg_deck(ucgb200_deck &deck) const = 0;
+  // false: this style (or this set of its options) cannot run inside the device loop
+  virtual bool ucg_deck(ucgb200_deck &deck) = 0;
 };
 
 class UCGDevice {

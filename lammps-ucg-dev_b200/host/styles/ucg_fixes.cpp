@@ -63,9 +63,10 @@ void FixNVE_UCGLD::final_integrate_respa(int ilevel, int) {
   dt_half = 0.5 * respa_steps[ilevel] * force->ftm2v;
   final_integrate();
 }
-void FixNVE_UCGLD::ucg_deck(ucgb200_deck &deck) const {
+bool FixNVE_UCGLD::ucg_deck(ucgb200_deck &deck) {
   deck.nve = 1;
   deck.nve_groupbit = groupbit;
+  return true;
 }
 void FixNVE_UCGLD::reset_dt() {
   dt_pos = update->dt;
@@ -94,11 +95,12 @@ int FixNVE_UCGLD_Wall_Hard::setmask() {
   if (bias_on) mask |= POST_FORCE;
   return mask;
 }
-void FixNVE_UCGLD_Wall_Hard::ucg_deck(ucgb200_deck &deck) const {
+bool FixNVE_UCGLD_Wall_Hard::ucg_deck(ucgb200_deck &deck) {
   deck.nve = 2;
   deck.nve_groupbit = groupbit;
   deck.wall_bias = bias_on;
   deck.wall_barrier = bias_height;
+  return true;
 }
 void FixNVE_UCGLD_Wall_Hard::post_force(int) {
   dev->upload(lmp, UCGB200_F_UCGL | UCGB200_F_UCGFORCE);
@@ -133,10 +135,11 @@ void FixUCGState::post_force(int) {
   dev->check(lmp, ucgb200_fix_ucgstate(dev->ctx, mode, rng_seed + comm->me, switch_rate, update->ntimestep), "fix_ucgstate");
   dev->download(lmp, UCGB200_F_UCGP | (lambda_only ? 0u : (UCGB200_F_UCGSTATE | UCGB200_F_UCGL)));
 }
-void FixUCGState::ucg_deck(ucgb200_deck &deck) const {
+bool FixUCGState::ucg_deck(ucgb200_deck &deck) {
   deck.ucgstate = lambda_only ? 2 : (monte_carlo ? 3 : 1);
   deck.ucgstate_seed = rng_seed + comm->me;
   deck.ucgstate_rate = switch_rate;
+  return true;
 }
 void FixUCGState::post_force_respa(int vflag, int, int) { post_force(vflag); }
 void FixUCGState::min_post_force(int vflag) { post_force(vflag); }
@@ -222,13 +225,14 @@ void Fix_UCGLD_Langevin::post_force(int) {
                                        update->ntimestep, groupbit, bias_temp), "fix_langevin");
   dev->download(lmp, UCGB200_F_UCGFORCE);
 }
-void Fix_UCGLD_Langevin::ucg_deck(ucgb200_deck &deck) const {
+bool Fix_UCGLD_Langevin::ucg_deck(ucgb200_deck &deck) {
   deck.langevin = 1;
   deck.t_start = temp.start;
   deck.t_stop = temp.stop;
   deck.t_period = temp.period;
   deck.langevin_seed = rng_seed + comm->me;
   deck.langevin_groupbit = groupbit;
+  return !bias_temp;   // a bias temperature compute lives on the host
 }
 void Fix_UCGLD_Langevin::post_force_respa(int vflag, int ilevel, int) {
   if (ilevel == nlevels_respa - 1) post_force(vflag);

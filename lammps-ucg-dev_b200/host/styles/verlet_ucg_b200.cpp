@@ -15,7 +15,6 @@
 #include "pair.h"
 #include "update.h"
 
-#include "pair_table_ucgld.h"
 #include "ucg_device.h"
 
 using namespace LAMMPS_NS;
@@ -26,13 +25,14 @@ VerletUCGB200::VerletUCGB200(LAMMPS *lmp, int narg, char **arg) : Integrate(lmp,
 
 void VerletUCGB200::collect_deck() {
   memset(&deck, 0, sizeof deck);
-  auto *pair = dynamic_cast<PairTable_UCGLD *>(force->pair);
+  auto *pair = dynamic_cast<UCGDeckPart *>(force->pair);
   if (!pair || !pair->ucg_deck(deck))
-    error->all(FLERR, "run_style ucg/b200 needs pair_style table_ucgld or table_ucg_bethe (without the noise prior); use run_style verlet");
+    error->all(FLERR, "run_style ucg/b200 needs one of the UCG pair styles (table_ucg_bethe without the noise prior); use run_style verlet");
   for (int i = 0; i < modify->nfix; i++) {
     Fix *f = modify->fix[i];
-    if (auto *part = dynamic_cast<UCGDeckPart *>(f)) part->ucg_deck(deck);
-    else if (modify->fmask[i])
+    auto *part = dynamic_cast<UCGDeckPart *>(f);
+    if (part && part->ucg_deck(deck)) continue;
+    if (part || modify->fmask[i])
       error->all(FLERR, "run_style ucg/b200: fix {} (style {}) has no part in the device loop; use run_style verlet", f->id, f->style);
   }
   if (comm->nprocs > 1) error->all(FLERR, "run_style ucg/b200 drives one context per process; multi-brick runs use the resident NCCL driver");

@@ -322,3 +322,33 @@ def test_run_style_ucg_b200_rejects_what_it_cannot_run(pkg, fixtures):
         out.append(s.get_atoms())
     for k in ("x", "f", "ucgp", "ucgstate"):
         assert np.array_equal(out[0][k], out[1][k]), k
+
+
+@pytest.mark.parametrize("style", ["rleucg", "bethe_density"])
+def test_run_style_ucg_b200_density_styles(pkg, fixtures, tmp_path, style):
+    """the three-sweep density styles under `run_style ucg/b200`: the resident run equals the offload run of the same
+    classes (and so, by the deck tests above, the reference's)"""
+    liq = _liq(6)
+    t = fixtures["table4096"]
+    if style == "rleucg":
+        sf = tmp_path / "rle.conf"
+        sf.write_text("1 2\n2 density use_entropy\n12.0 1.5\n0.3\n")
+        lines = ["newton off", "neighbor 0.3 bin", "timestep 0.002", f"pair_style table_rleucg_interface linear 4096 {sf}",
+                 f"pair_coeff 1 1 {t} UCG_00 2.5", f"pair_coeff 1 2 {t} UCG_01 2.5", f"pair_coeff 2 2 {t} UCG_11 2.5",
+                 "fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld/wall/hard"]
+    else:
+        sf = tmp_path / "bd.conf"
+        sf.write_text("1 2 2\n1 2\n1 2 density entropy \n12.0 1.5\n0.0 0.5\n")
+        lines = ["newton off", "neighbor 0.3 bin", "timestep 0.002", f"pair_style table_ucg_bethe_density linear 4096 {sf}",
+                 f"pair_coeff 1 1 2 2 {t} UCG_00 2.5 {t} UCG_01 2.5 {t} UCG_01 2.5 {t} UCG_11 2.5",
+                 "fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld", "fix 2 all ucgstate"]
+    out = []
+    for resident in (False, True):
+        s = _deck(rb.HostSim, liq, lines + (["run_style ucg/b200"] if resident else []))
+        s.setup(1)
+        s.run(20, 10)
+        out.append((s.get_atoms(), s.eng_vdwl()))
+    (a, ea), (b, eb) = out
+    for k in ("x", "v", "f", "ucgl", "ucgp"):
+        assert rel_err(b[k], a[k]) <= 1e-11, (k, rel_err(b[k], a[k]))
+    assert abs(ea - eb) <= 1e-11 * abs(ea)
