@@ -134,3 +134,56 @@ def test_data_file_errors(pkg, tmp_path):
         dumpio.DataFile(str(p))
     with pytest.raises(pkg.UCGError, match="Cannot open file"):
         dumpio.DataFile(str(tmp_path / "missing.data"))
+
+
+def test_dump_command_grammar_without_a_device(pkg, tmp_path):
+    """`dump` / `dump_modify` / `compute property/atom` words are parsed on the host: the reference's messages
+    (dump_custom.cpp:67, 1843, 2005, 2293; [stock] Dump::modify_params), no GPU involved"""
+    import ctypes as C
+    from lammps_ucg_dev_b200 import dumpio
+    l = pkg.lib()
+
+    def create(line):
+        w = line.split()
+        h, err = C.c_void_p(), C.create_string_buffer(512)
+        rc = l.ucgb200_host_dump_create(len(w), dumpio._argv(w), 1, C.byref(h), err, 512)
+        return rc, h, err.value.decode()
+
+    def modify(h, line):
+        import shlex
+        w = shlex.split(line)
+        err = C.create_string_buffer(512)
+        return l.ucgb200_host_dump_modify(h, len(w), dumpio._argv(w), err, 512), err.value.decode()
+
+    f = tmp_path / "x.dump"
+    for line, msg in ((f"d all custom 10 {f}", "No dump custom arguments specified"),
+                      (f"d all custom 0 {f} id", "output frequency must be > 0"),
+                      (f"d all atom 10 {f} id", "Unrecognized dump style 'atom'"),
+                      (f"d all custom 10 {f} id radius", "Invalid attribute radius in dump custom command"),
+                      (f"d all custom 10 {f} id c_p[0]", "Invalid attribute c_p[0] in dump custom command"),
+                      (f"d all custom 10 {tmp_path}/x.bin id", "binary files are not supported")):
+        rc, h, err = create(line)
+        assert rc != 0 and msg in err, (line, err)
+    rc, h, err = create(f"d all custom 10 {f} id type x ucgstate ucgl ucgp c_p[2] ucgforce")
+    assert rc == 0, err
+    for line, msg in (("thresh x ~ 1.0", "Invalid dump_modify thresh operator"), ("thresh radius > 1.0", "Invalid dump_modify thresh attribute: radius"),
+                      ("thresh x > LAST", "thresh LAST is not supported"), ("format 9 %g", "Unknown dump_modify format ID keyword: 9"),
+                      ("format int %f", "Dump_modify int format does not contain d character"), ("sort 3", "sort by column is not supported"),
+                      ("colour red", "Unknown dump_modify keyword: colour"), ("append", "missing argument"), ("every 0", "Illegal dump_modify command")):
+        rc, err = modify(h, line)
+        assert rc != 0 and msg in err, (line, err)
+    for line in ("sort id thresh ucgl >= 0.5 thresh ucgstate == 1", 'format line "%d %d %g %d %g %g %g %g"', "format float %12.6e format 3 %8.3f",
+                 "format none thresh none", "append yes header no time yes units yes pad 6 flush no buffer yes every 50"):
+        rc, err = modify(h, line)
+        assert rc == 0, (line, err)
+    names = ["ucgl", "radius"]
+    err = C.create_string_buffer(512)
+    assert l.ucgb200_host_dump_bind_compute(h, b"p", 1, 2, dumpio._argv(names), err, 512) != 0
+    assert "Invalid keyword radius for atom style in compute property/atom command" in err.value.decode()
+    assert l.ucgb200_host_dump_bind_compute(h, b"p", 1, 1, dumpio._argv(["ucgl"]), err, 512) != 0
+    assert "does not calculate per-atom array" in err.value.decode()
+    assert l.ucgb200_host_dump_bind_compute(h, b"p", 1, 3, dumpio._argv(["ucgforce", "ucgvl", "ucgml"]), err, 512) == 0
+    n = C.c_int(0)
+    l.ucgb200_host_dump_stats(h, None, None, C.byref(n))
+    assert n.value == 50
+    l.ucgb200_host_dump_free(h)
