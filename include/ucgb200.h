@@ -247,6 +247,8 @@ int ucgb200_cluster_switch(ucgb200_ctx *ctx, int *n_attempts, int *n_success);
 /* compute_vector (:923-933): out[0..6] = nAttemptsTotal, nSuccessTotal, nAttemptsON, nAttemptsOFF,
  * nSuccessON, nSuccessOFF, nCluster; out[7] = labelling rounds of the last check */
 int ucgb200_cluster_stats(ucgb200_ctx *ctx, double out[8]);
+/* Fix::next_reneighbor of fix cluster_switch for the resident loop (fix_cluster_switch.cpp:71, 480) */
+int ucgb200_cluster_next_reneighbor(ucgb200_ctx *ctx, long long step);
 /* per-molecule arrays [0..maxmol] (cluster_assignment.log / state_assignment.log, :711-727) */
 int ucgb200_cluster_get(ucgb200_ctx *ctx, int cap, int *mol_cluster, int *mol_state, int *mol_restrict,
                         int *mol_accept, int *max_mol);

@@ -456,6 +456,12 @@ extern "C" int ucgb200_cluster_switch(ucgb200_ctx *c, int *n_attempts, int *n_su
 }
 
 // FixClusterSwitch::compute_vector (:923-933) and the per-molecule arrays (logs :711-727, tests)
+extern "C" int ucgb200_cluster_next_reneighbor(ucgb200_ctx *c, long long step) {
+  if (!c || !c->cluster.set) return -1;
+  c->cluster.next_reneighbor = step;
+  return 0;
+}
+
 extern "C" int ucgb200_cluster_stats(ucgb200_ctx *c, double out[8]) {
   if (!c || !out) return -1;
   for (int i = 0; i < 7; i++) out[i] = c->cluster.stats[i];

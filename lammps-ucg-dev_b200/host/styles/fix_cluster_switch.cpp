@@ -144,25 +144,46 @@ void FixClusterSwitch::pre_exchange() {
   dev->list_ready = true;
   int ncl = 0, natt = 0, nsuc = 0;
   dev->check(lmp, ucgb200_cluster_check(dev->ctx, &ncl), "cluster_check");
-  if (comm->me == 0) {   // cluster_assignment.log / state_assignment.log (:711-727), written before the switch
-    std::vector<int> cl(maxmol + 1), st(maxmol + 1);
-    dev->check(lmp, ucgb200_cluster_get(dev->ctx, maxmol + 1, cl.data(), st.data(), nullptr, nullptr, nullptr), "cluster_get");
-    const int cid = cl[mol_seed], now = (int) update->ntimestep;
-    fprintf(fp1, "%d ", now);
-    fprintf(fp2, "%d ", now);
-    for (int i = 0; i <= maxmol; i++) {
-      fprintf(fp1, "%d ", cl[i] == cid ? 1 : 0);
-      fprintf(fp2, "%d ", st[i]);
-    }
-    fprintf(fp1, "\n");
-    fprintf(fp2, "\n");
-    fflush(fp1);
-    fflush(fp2);
-  }
+  if (comm->me == 0) write_logs((int) update->ntimestep, false);   // written before the switch
   dev->check(lmp, ucgb200_cluster_switch(dev->ctx, &natt, &nsuc), "cluster_switch");
   dev->download(lmp, UCGB200_F_TYPE);
   comm->forward_comm(this);   // changed types to the ghosts (:825)
   next_reneighbor = update->ntimestep + switchFreq;
+}
+
+// cluster_assignment.log / state_assignment.log (:711-727): the labelling and the molecule states as they were BEFORE
+// the switch of that step; after_switch undoes the accepted flips (state 0 <-> 1 where mol_accept == 1)
+void FixClusterSwitch::write_logs(int now, bool after_switch) {
+  std::vector<int> cl(maxmol + 1), st(maxmol + 1), acc(maxmol + 1, 0);
+  dev->check(lmp, ucgb200_cluster_get(dev->ctx, maxmol + 1, cl.data(), st.data(), nullptr, after_switch ? acc.data() : nullptr, nullptr),
+             "cluster_get");
+  const int cid = cl[mol_seed];
+  fprintf(fp1, "%d ", now);
+  fprintf(fp2, "%d ", now);
+  for (int i = 0; i <= maxmol; i++) {
+    int state = st[i];
+    if (after_switch && acc[i] == 1 && (state == 0 || state == 1)) state = 1 - state;
+    fprintf(fp1, "%d ", cl[i] == cid ? 1 : 0);
+    fprintf(fp2, "%d ", state);
+  }
+  fprintf(fp1, "\n");
+  fprintf(fp2, "\n");
+  fflush(fp1);
+  fflush(fp2);
+}
+
+// run_style ucg/b200: the device loop rebuilds, labels and switches at next_reneighbor itself (csrc/run.cu); it returns
+// right after that step so that the two log lines are written
+bool FixClusterSwitch::ucg_deck(ucgb200_deck &deck) {
+  deck.cluster_freq = switchFreq;
+  if (switchFreq > 0) dev->check(lmp, ucgb200_cluster_next_reneighbor(dev->ctx, next_reneighbor), "cluster_next_reneighbor");
+  return true;
+}
+long long FixClusterSwitch::ucg_next_stop() const { return switchFreq > 0 ? (long long) next_reneighbor : -1; }
+void FixClusterSwitch::ucg_after_step(long long step) {
+  if (switchFreq == 0 || step != next_reneighbor) return;
+  if (comm->me == 0) write_logs((int) step, true);
+  next_reneighbor = step + switchFreq;
 }
 
 int FixClusterSwitch::pack_forward_comm(int n, int *lst, double *buf, int, int *) {

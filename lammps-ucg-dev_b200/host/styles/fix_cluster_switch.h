@@ -12,13 +12,14 @@ FixStyle(cluster_switch, FixClusterSwitch);
 // the fix-line grammar, the two input-file formats, the log files and compute_vector.
 
 #include "fix.h"
+#include "ucg_device.h"
 
 #include <cstdio>
 #include <vector>
 
 namespace LAMMPS_NS {
 
-class FixClusterSwitch : public Fix {
+class FixClusterSwitch : public Fix, public UCGDeckPart {
  public:
   FixClusterSwitch(class LAMMPS *, int, char **);
   ~FixClusterSwitch() override;
@@ -30,8 +31,12 @@ class FixClusterSwitch : public Fix {
   double memory_usage() override;
   int pack_forward_comm(int, int *, double *, int, int *) override;
   void unpack_forward_comm(int, int, double *) override;
+  bool ucg_deck(ucgb200_deck &deck) override;
+  long long ucg_next_stop() const override;
+  void ucg_after_step(long long) override;
 
  private:
+  void write_logs(int now, bool after_switch);
   int mol_seed, mol_offset, seed, switchFreq;
   double cutoff, probON, probOFF;
   int nSwitchTypes, nContactTypes, nAtomsPerContact, maxmol;

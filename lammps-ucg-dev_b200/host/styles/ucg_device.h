@@ -30,6 +30,9 @@ class UCGDeckPart {
   virtual ~UCGDeckPart() = default;
   // false: this style (or this set of its options) cannot run inside the device loop
   virtual bool ucg_deck(ucgb200_deck &deck) = 0;
+  // the next step after which the device loop must hand control back to this style, and what it does then
+  virtual long long ucg_next_stop() const { return -1; }
+  virtual void ucg_after_step(long long) {}
 };
 
 class UCGDevice {

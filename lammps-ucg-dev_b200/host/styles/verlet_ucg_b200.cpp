@@ -25,13 +25,14 @@ VerletUCGB200::VerletUCGB200(LAMMPS *lmp, int narg, char **arg) : Integrate(lmp,
 
 void VerletUCGB200::collect_deck() {
   memset(&deck, 0, sizeof deck);
+  parts.clear();
   auto *pair = dynamic_cast<UCGDeckPart *>(force->pair);
   if (!pair || !pair->ucg_deck(deck))
     error->all(FLERR, "run_style ucg/b200 needs one of the UCG pair styles (table_ucg_bethe without the noise prior); use run_style verlet");
   for (int i = 0; i < modify->nfix; i++) {
     Fix *f = modify->fix[i];
     auto *part = dynamic_cast<UCGDeckPart *>(f);
-    if (part && part->ucg_deck(deck)) continue;
+    if (part && part->ucg_deck(deck)) { parts.push_back(part); continue; }
     if (part || modify->fmask[i])
       error->all(FLERR, "run_style ucg/b200: fix {} (style {}) has no part in the device loop; use run_style verlet", f->id, f->style);
   }
@@ -56,7 +57,7 @@ void VerletUCGB200::push() {
 
 void VerletUCGB200::pull(bool thermo) {
   dev->download(lmp, UCGB200_F_X | UCGB200_F_V | UCGB200_F_F | UCGB200_F_UCGL | UCGB200_F_UCGVL | UCGB200_F_UCGSTATE | UCGB200_F_UCGP |
-                         UCGB200_F_UCGFORCE | UCGB200_F_SCORES | UCGB200_F_NUMSTATES);
+                         UCGB200_F_UCGFORCE | UCGB200_F_SCORES | UCGB200_F_NUMSTATES | UCGB200_F_TYPE);
   dev->list_ready = false;   // the offload-mode classes rebuild their list if they are used again
   if (thermo) {
     double th[16];
@@ -83,9 +84,14 @@ void VerletUCGB200::run(int n) {
   while (update->ntimestep < last) {
     bigint next = last;
     if (output && output->next > update->ntimestep && output->next < next) next = output->next;
+    for (UCGDeckPart *p : parts) {
+      const long long stop = p->ucg_next_stop();
+      if (stop > update->ntimestep && stop < next) next = stop;
+    }
     const int rc = ucgb200_run_between(dev->ctx, (int) (next - update->ntimestep), update->beginstep, update->endstep);
     dev->check(lmp, rc, "run");
     update->ntimestep = next;
+    for (UCGDeckPart *p : parts) if (p->ucg_next_stop() == next) p->ucg_after_step(next);
     if (output && output->next == next) {
       pull(true);
       output->write(next);

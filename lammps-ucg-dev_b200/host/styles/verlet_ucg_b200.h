@@ -12,6 +12,8 @@ IntegrateStyle(ucg/b200, VerletUCGB200);
 // ucgb200_run_between once, and the host arrays are refreshed on output steps and at the end of the run only.
 // Same kernels, same order, same random streams: the trajectory is the offload-mode one bit for bit.
 
+#include <vector>
+
 #include "integrate.h"
 #include "ucgb200.h"
 
@@ -29,6 +31,7 @@ class VerletUCGB200 : public Integrate {
  protected:
   class UCGDevice *dev;
   ucgb200_deck deck;
+  std::vector<class UCGDeckPart *> parts;   // the fixes that take part in the device loop
   void collect_deck();
   void push();            // host arrays -> device (everything the run starts from)
   void pull(bool thermo); // device -> host arrays, pair energy / virial on thermo steps

@@ -352,3 +352,44 @@ def test_run_style_ucg_b200_density_styles(pkg, fixtures, tmp_path, style):
     for k in ("x", "v", "f", "ucgl", "ucgp"):
         assert rel_err(b[k], a[k]) <= 1e-11, (k, rel_err(b[k], a[k]))
     assert abs(ea - eb) <= 1e-11 * abs(ea)
+
+
+def test_run_style_ucg_b200_config4_deck(pkg, fixtures, tmp_path):
+    """BASELINE config-4 style deck (table_rleucg_interface + nve/ucgld/wall/hard + cluster_switch) under
+    `run_style ucg/b200`: the device loop rebuilds, labels and switches by itself and hands control back after every
+    switch step for the two log lines — types, statistics and log files equal the offload run's (and the reference's)"""
+    import os
+    import test_gpu_cluster_switch as T
+    liq, half = T._system(6)
+    sims = {}
+    for cls, sub, resident in ((rb.RefSim, "ref", False), (rb.HostSim, "gpu", False), (rb.HostSim, "res", True)):
+        d = tmp_path / sub
+        d.mkdir()
+        orig = rb.RefSim
+        try:
+            T.rb.RefSim = cls
+            s = T._ref(liq, half, d, fixtures, 1.08, 5, 15123, 0.3)
+        finally:
+            T.rb.RefSim = orig
+        if resident:
+            s.command("run_style ucg/b200")
+        cwd = os.getcwd()
+        os.chdir(d)
+        try:
+            s.setup(1)
+            s.run(17, 0)
+            s.run(9, 0)
+        finally:
+            os.chdir(cwd)
+        sims[sub] = s
+    a, b, r = sims["gpu"].get_atoms(), sims["res"].get_atoms(), sims["ref"].get_atoms()
+    assert np.array_equal(a["type"], b["type"]) and np.array_equal(r["type"], b["type"]) and (b["type"] != liq.type).sum() > 0
+    assert [sims["gpu"].fix_vector(2, k) for k in range(7)] == [sims["res"].fix_vector(2, k) for k in range(7)]
+    assert [sims["ref"].fix_vector(2, k) for k in range(7)] == [sims["res"].fix_vector(2, k) for k in range(7)]
+    for k in ("x", "v", "f", "ucgl"):
+        assert rel_err(b[k], a[k]) <= 1e-11, (k, rel_err(b[k], a[k]))
+    assert rel_err(b["x"], r["x"]) <= 1e-10
+    for name in ("cluster_assignment.log", "state_assignment.log"):
+        text = (tmp_path / "res" / name).read_text()
+        assert text == (tmp_path / "gpu" / name).read_text() == (tmp_path / "ref" / name).read_text()
+        assert len(text.strip().split("\n")) == 6     # steps 1 6 11 16 21 26
