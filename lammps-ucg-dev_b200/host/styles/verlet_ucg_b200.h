@@ -8,7 +8,7 @@ IntegrateStyle(ucg/b200, VerletUCGB200);
 
 // run_style ucg/b200: the [stock] Verlet loop of a UCG deck kept on the device.  With the default run_style the
 // UCG classes work in offload mode (every style call moves the arrays it touches); with this one the deck — any of the
-// four UCG pair styles, fix nve/ucgld(/wall/hard), ucgld/langevin, ucgstate — is handed to ucgb200_setup /
+// four UCG pair styles, fix nve/ucgld(/wall/hard), ucgld/langevin, ucgstate, cluster_switch — is handed to ucgb200_setup /
 // ucgb200_run_between once, and the host arrays are refreshed on output steps and at the end of the run only.
 // Same kernels, same order, same random streams: the trajectory is the offload-mode one bit for bit.
 
