@@ -296,6 +296,32 @@ def run_gpu(args):
            "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
            "api": "ucgb200_atoms_upload + ucgb200_run(1) + ucgb200_atoms_download, pinned host arrays"}
 
+    # ---- the taps either side of the path, after the timed regions: one `dump custom` snapshot of the
+    # resident state written to a file (rows selected, sorted, packed and formatted on the device) and read back
+    taps = None
+    try:
+        from lammps_ucg_dev_b200 import dumpio
+        path = os.path.join(td, "bench.dump")
+        cols = "id type x y z vx vy vz ucgstate ucgl ucgp"
+        d = dumpio.DumpCustom(ctx, f"dump b all custom 1000 {path} {cols}")
+        d.modify("dump_modify b sort id")
+        ts = []
+        for rep in range(2):
+            ctx.sync(); t0 = time.perf_counter(); d.write(int(th[10])); ctx.sync(); ts.append(time.perf_counter() - t0)
+        st = d.stats()
+        d.close()
+        d = dumpio.DumpCustom(ctx, f"dump c all custom 1000 {path}.one {cols}")
+        d.modify("dump_modify c sort id")
+        d.write(int(th[10]))
+        d.close()
+        ctx.sync(); t0 = time.perf_counter()
+        rd = dumpio.read_dump(ctx, f"read_dump {path}.one {int(th[10])} x y z vx vy vz ucgstate ucgl ucgp")
+        ctx.sync(); t_read = time.perf_counter() - t0
+        taps = {"dump_custom_ms": 1e3 * min(ts), "dump_rows": st["rows"], "dump_bytes": st["bytes"], "columns": len(cols.split()),
+                "read_dump_ms": 1e3 * t_read, "read_dump_replaced": rd["replaced"]}
+    except Exception as e:   # never fail the bench line because of the taps
+        taps = {"error": str(e)[:200]}
+
     # ---- CPU baseline beside it (bounded sample, rank 0 only)
     cpu = None
     if not args.no_cpu:
@@ -309,7 +335,7 @@ def run_gpu(args):
             "dtype": "f64", "data": "synthetic", "config": workload_config(ncell1, 1),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "thermo": {"lambda_temp": th[9], "rebuilds_total": int(th[11]), "nghost": int(th[13])}}
+            "thermo": {"lambda_temp": th[9], "rebuilds_total": int(th[11]), "nghost": int(th[13])}, "taps": taps}
     print(json.dumps(line))
 
 
