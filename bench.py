@@ -314,9 +314,12 @@ def run_gpu(args):
         d.modify("dump_modify c sort id")
         d.write(int(th[10]))
         d.close()
-        ctx.sync(); t0 = time.perf_counter()
-        rd = dumpio.read_dump(ctx, f"read_dump {path}.one {int(th[10])} x y z vx vy vz ucgstate ucgl ucgp")
-        ctx.sync(); t_read = time.perf_counter() - t0
+        tr = []
+        for rep in range(2):   # the first call also page-locks its text staging
+            ctx.sync(); t0 = time.perf_counter()
+            rd = dumpio.read_dump(ctx, f"read_dump {path}.one {int(th[10])} x y z vx vy vz ucgstate ucgl ucgp")
+            ctx.sync(); tr.append(time.perf_counter() - t0)
+        t_read = min(tr)
         taps = {"dump_custom_ms": 1e3 * min(ts), "dump_rows": st["rows"], "dump_bytes": st["bytes"], "columns": len(cols.split()),
                 "read_dump_ms": 1e3 * t_read, "read_dump_replaced": rd["replaced"]}
     except Exception as e:   # never fail the bench line because of the taps
