@@ -73,6 +73,7 @@ extern "C" int ucgb200_destroy(ucgb200_ctx *c) {
   if (c->h_flags) cudaFreeHost(c->h_flags);
   cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b);
   cudaEventDestroy(c->ev_pair0); cudaEventDestroy(c->ev_pair1);
+  if (c->ev_flag) cudaEventDestroy(c->ev_flag);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;

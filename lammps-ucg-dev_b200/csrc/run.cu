@@ -168,6 +168,9 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
   // k_step_tail) unless UCGB200_FUSED_TAIL=0; it needs an integrator fix and a single brick loop
   const bool fused = d.nve && !(getenv("UCGB200_FUSED_TAIL") && atoi(getenv("UCGB200_FUSED_TAIL")) == 0);
   bool pre_integrated = false;   // initial_integrate + check_distance of this step already done by the last tail
+  // speculative launch of the next pair evaluation (single brick, fused tail); UCGB200_SPECULATE=0 turns it off
+  const bool speculative = fused && c->halo.nranks == 1 && !(getenv("UCGB200_SPECULATE") && atoi(getenv("UCGB200_SPECULATE")) == 0);
+  c->last_maxdisp = -1.0;
   for (int n = 0; n < nsteps; n++) {
     c->ntimestep++;
     const int ev = d.thermo_every > 0 && (c->ntimestep % d.thermo_every == 0);
@@ -177,14 +180,40 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
       t.stop();
     }
     int flag = 0;
-    {
+    bool pair_in_flight = false;
+    const bool cluster_due = d.cluster_freq > 0 && c->cluster.set && c->cluster.next_reneighbor == c->ntimestep;
+    if (speculative && pre_integrated && c->list_valid && !cluster_due && !c->timers_on) {
+      // Neighbor::decide without a pipeline bubble: the flag (and the largest squared displacement since the build) of
+      // this step were computed by the previous step's fused tail.  Their read-back is queued, and — when the last known
+      // displacement says a rebuild is still some steps away — so are the ghost refresh and the pair kernel of this
+      // step, BEFORE the host waits for the flag: the device never idles while the host decides.  If the flag says
+      // rebuild after all, the speculative results are simply overwritten by the rebuild + pair that follow.
+      if (!c->ev_flag) UCG_CHECK(c, cudaEventCreateWithFlags(&c->ev_flag, cudaEventDisableTiming));
+      UCG_CHECK(c, cudaMemcpyAsync(c->h_flags, c->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      UCG_CHECK(c, cudaMemcpyAsync(c->h_flags + 6, c->d_maxdisp.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+      UCG_CHECK(c, cudaEventRecord(c->ev_flag, c->stream));
+      c->maxdisp_valid = true;
+      const double quiet = 0.8 * 0.5 * c->skin;
+      if (c->last_maxdisp >= 0.0 && c->last_maxdisp < quiet * quiet) {
+        if ((rc = do_forward(c))) return rc;
+        if ((rc = pair_compute(c, ev))) return rc;
+        pair_in_flight = true;
+      }
+      UCG_CHECK(c, cudaEventSynchronize(c->ev_flag));
+      flag = c->h_flags[0] ? 1 : 0;
+      unsigned long long bits;
+      memcpy(&bits, c->h_flags + 6, sizeof bits);
+      memcpy(&c->last_maxdisp, &bits, sizeof bits);
+      if (flag) pair_in_flight = false;   // discarded
+    } else {
       StageTimer t(c, 1);
       if ((rc = do_decide(c, pre_integrated, &flag))) return rc;
       t.stop();
+      c->last_maxdisp = -1.0;   // unknown until a fused tail has reported it
     }
     // fix cluster_switch: force_reneighbor at next_reneighbor; pre_exchange() rebuilds, labels the
     // clusters and switches types (fix_cluster_switch.cpp:464-481), then Verlet rebuilds again
-    if (d.cluster_freq > 0 && c->cluster.set && c->cluster.next_reneighbor == c->ntimestep) {
+    if (cluster_due) {
       StageTimer t(c, 3);
       if ((rc = do_build(c))) return rc;
       if ((rc = ucgb200_cluster_check(c, nullptr))) return rc;
@@ -193,13 +222,13 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
       flag = 1;
       t.stop();
     }
-    if (flag) { if ((rc = do_build(c))) return rc; }
-    else {
+    if (flag) { if ((rc = do_build(c))) return rc; c->last_maxdisp = 0.0; }
+    else if (!pair_in_flight) {
       StageTimer t(c, 2);
       if ((rc = do_forward(c))) return rc;
       t.stop();
     }
-    {
+    if (!pair_in_flight) {
       StageTimer t(c, 0);
       if ((rc = pair_compute(c, ev))) return rc;
       t.stop();

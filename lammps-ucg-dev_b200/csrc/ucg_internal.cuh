@@ -205,6 +205,8 @@ struct ucgb200_ctx {
   // timers
   bool timers_on = false;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_pair0 = nullptr, ev_pair1 = nullptr;
+  cudaEvent_t ev_flag = nullptr;   // run.cu: marks the read-back of the rebuild flag inside the step stream
+  double last_maxdisp = -1.0;      // largest squared displacement since the build, as last read back (< 0: unknown)
   double t_ms[4] = {0, 0, 0, 0};
   long long t_launch[4] = {0, 0, 0, 0};
   bool pair_timed = false;

@@ -484,3 +484,28 @@ def test_pair_bethe_mixed_types(pkg, fixtures):
     assert rel_err(got["f"], ref["f"]) <= F_TOL
     assert abs(e - o.eng_vdwl()) <= E_TOL * abs(o.eng_vdwl())
     assert rel_err(got["ucgsoftmaxscores"], ref["ucgsoftmaxscores"]) <= F_TOL
+
+
+def test_speculative_pair_launch_changes_nothing(pkg, fixtures, monkeypatch):
+    """the resident loop queues the next pair evaluation before the host has read the rebuild flag whenever the last
+    displacement read-back says a rebuild is some steps away (csrc/run.cu); with and without it, over several rebuilds
+    and thermo steps, every per-site array, the energy and the rebuild count are bit-identical"""
+    from lammps_ucg_dev_b200 import synth
+    liq = synth.fcc_liquid(10)
+    out = []
+    for spec in ("1", "0"):
+        monkeypatch.setenv("UCGB200_SPECULATE", spec)
+        ctx = decks.gpu_single_type(pkg, liq, fixtures)
+        ctx.deck_configure(pair_style=0, nve=2, wall_bias=1, wall_barrier=0.2, langevin=1, t_start=1.5, t_stop=1.0, t_period=0.5,
+                           langevin_seed=99, ucgstate=2, thermo_every=7)
+        ctx.setup()
+        ctx.run(40)
+        ctx.run(37)
+        th = ctx.thermo()
+        a = ctx.atoms_download(["x", "v", "f", "ucgl", "ucgvl", "ucgp", "ucgforce", "ucgsoftmaxscores", "ucgstate"])
+        out.append((a, th))
+    (a, ta), (b, tb) = out
+    assert ta[11] >= 3 and ta[11] == tb[11]          # rebuilds happened, on the same steps
+    assert ta[0] == tb[0] and np.array_equal(ta[1:7], tb[1:7])
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
