@@ -538,7 +538,8 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
   int *s_ts = reinterpret_cast<int *>(s_z + TILE_CAP);
   int *s_j = s_ts + TILE_CAP;
   int *s_outer = s_j + TILE_CAP;                 // [warps][stride] skin entries of the row being built ...
-  unsigned *s_okey = reinterpret_cast<unsigned *>(s_outer + (TILE_BS / 32) * stride);   // ... and their sort keys
+  unsigned *s_okey = reinterpret_cast<unsigned *>(s_outer + (TILE_BS / 32) * stride);   // ... their sort keys (first: the type of j) ...
+  double *s_orsq = reinterpret_cast<double *>(s_okey + (TILE_BS / 32) * stride);         // ... and their squared distances
   __shared__ int s_rb[18], s_re[18], s_roff[18], s_pre[19];
   constexpr int NW = TILE_BS / 32;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -566,6 +567,7 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
   const int ncand = s_pre[18];
   int *outer = s_outer + wid * stride;
   unsigned *okey = s_okey + wid * stride;
+  double *orsq = s_orsq + wid * stride;
   const unsigned lt = (1u << lane) - 1;
   const double inv_skin = skin > 0.0 ? 1.0 / skin : 0.0;
   // per-warp site cursor state lives in registers across chunks: one warp owns sites sb+wid, sb+wid+NW, ...
@@ -623,12 +625,11 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
         } else if (hit) {
           const int p = cnt_out + __popc(m_out & lt);
           if (p < stride) {
+            // only a few lanes take this branch in every pass over the candidates: the two square roots of the sort
+            // key are taken later, once per row, with all lanes busy
             outer[p] = j;
-            // key = how far beyond the cutoff the pair sits, in units of skin / 2^27, rounded DOWN with a
-            // safety margin: key >> 24 is the displacement level (eighths of the skin) below which the
-            // pair cannot have entered the cutoff yet
-            const double beyond = (sqrt(rsq_k) - sqrt(cs_k)) * (1.0 - 1e-9) * inv_skin;
-            okey[p] = (unsigned)fmin(fmax(beyond, 0.0) * 134217728.0, 134217727.0);
+            orsq[p] = rsq_k;
+            okey[p] = (unsigned)s_ts[k];
           }
         }
         cnt_in += __popc(m_in);
@@ -641,6 +642,15 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
         unsigned lc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // entries to visit at displacement level 0..7
         if (total <= stride) {
           if (single) {
+            // key = how far beyond the cutoff the pair sits, in units of skin / 2^27, rounded DOWN with a
+            // safety margin: key >> 24 is the displacement level (eighths of the skin) below which the
+            // pair cannot have entered the cutoff yet
+            for (int k = lane; k < cnt_out; k += 32) {
+              const double cs_k = one_type ? cs1 : prow[okey[k]].cutsq;
+              const double beyond = (sqrt(orsq[k]) - sqrt(cs_k)) * (1.0 - 1e-9) * inv_skin;
+              okey[k] = (unsigned)fmin(fmax(beyond, 0.0) * 134217728.0, 134217727.0);
+            }
+            __syncwarp();
             // skin entries in ascending distance (rank sort inside the warp), and the level counts
             for (int k = lane; k < ((cnt_out + 31) & ~31); k += 32) {
               const bool have = k < cnt_out;
@@ -788,7 +798,8 @@ static int build_rows(ucgb200_ctx *c) {
     cap = std::min(std::max(cap, 32), TILE_CAP);
     if (tiled) {
       const int ncell_owned = c->grid.ninner[0] * c->grid.ninner[1] * c->grid.ninner[2];
-      const size_t smem = (size_t)TILE_CAP * (sizeof(double2) + sizeof(double) + 2 * sizeof(int)) + 2 * (TILE_BS / 32) * c->neigh_stride * sizeof(int);
+      const size_t smem = (size_t)TILE_CAP * (sizeof(double2) + sizeof(double) + 2 * sizeof(int)) +
+                          (TILE_BS / 32) * (size_t)c->neigh_stride * (2 * sizeof(int) + sizeof(double));
       static bool attr_set = false;
       if (!attr_set) {
         UCG_CHECK(c, cudaFuncSetAttribute(k_build_rows_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
