@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(TILE_BS)
 k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, int nlocal, Grid g,
                    const int *__restrict__ ostart, const int *__restrict__ gstart, const PairInfo *__restrict__ pinfo,
                    int na, int *__restrict__ neigh, int stride, int *__restrict__ numneigh, int *__restrict__ flags,
-                   int cap, uint4 *__restrict__ levcnt, double skin) {
+                   int cap, uint4 *__restrict__ levcnt, double skin, int defer_keys) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   // structure of arrays: a 16-byte {x,y} and an 8-byte z per candidate keep the warp-wide reads free of
   // bank conflicts (a 32-byte record read as two 16-byte halves is a 2-way conflict)
@@ -628,8 +628,11 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
             // only a few lanes take this branch in every pass over the candidates: the two square roots of the sort
             // key are taken later, once per row, with all lanes busy
             outer[p] = j;
-            orsq[p] = rsq_k;
-            okey[p] = (unsigned)s_ts[k];
+            if (defer_keys) { orsq[p] = rsq_k; okey[p] = (unsigned)s_ts[k]; }
+            else {
+              const double beyond = (sqrt(rsq_k) - sqrt(cs_k)) * (1.0 - 1e-9) * inv_skin;
+              okey[p] = (unsigned)fmin(fmax(beyond, 0.0) * 134217728.0, 134217727.0);
+            }
           }
         }
         cnt_in += __popc(m_in);
@@ -645,7 +648,7 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
             // key = how far beyond the cutoff the pair sits, in units of skin / 2^27, rounded DOWN with a
             // safety margin: key >> 24 is the displacement level (eighths of the skin) below which the
             // pair cannot have entered the cutoff yet
-            for (int k = lane; k < cnt_out; k += 32) {
+            for (int k = lane; defer_keys && k < cnt_out; k += 32) {
               const double cs_k = one_type ? cs1 : prow[okey[k]].cutsq;
               const double beyond = (sqrt(orsq[k]) - sqrt(cs_k)) * (1.0 - 1e-9) * inv_skin;
               okey[k] = (unsigned)fmin(fmax(beyond, 0.0) * 134217728.0, 134217727.0);
@@ -808,7 +811,8 @@ static int build_rows(ucgb200_ctx *c) {
       if (smem > 96 * 1024) return fail(c, "neighbor rows too long for the tiled build");
       k_build_rows_tiled<<<ncell_owned, TILE_BS, smem, c->stream>>>(
           c->pos.p, c->ts.p, nlocal, c->grid, c->cell_start.p, c->gcell_start.p, c->d_pairinfo.p, na,
-          c->neigh.p, c->neigh_stride, c->numneigh.p, c->d_flags.p, cap, c->levcnt.p, c->skin);
+          c->neigh.p, c->neigh_stride, c->numneigh.p, c->d_flags.p, cap, c->levcnt.p, c->skin,
+          getenv("UCGB200_BUILD_DEFER_KEYS") ? atoi(getenv("UCGB200_BUILD_DEFER_KEYS")) : 1);
     } else {
       long long nthreads = (long long)nlocal * 32;
       k_build_rows<<<nblocks(nthreads, 256), 256, 8 * c->neigh_stride * sizeof(int), c->stream>>>(
