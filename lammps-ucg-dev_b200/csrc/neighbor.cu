@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(TILE_BS)
 k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, int nlocal, Grid g,
                    const int *__restrict__ ostart, const int *__restrict__ gstart, const PairInfo *__restrict__ pinfo,
                    int na, int *__restrict__ neigh, int stride, int *__restrict__ numneigh, int *__restrict__ flags,
-                   int cap, uint4 *__restrict__ levcnt, double skin, int defer_keys, int prefilter) {
+                   int cap, uint4 *__restrict__ levcnt, double skin, int defer_keys) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   // structure of arrays: a 16-byte {x,y} and an 8-byte z per candidate keep the warp-wide reads free of
   // bank conflicts (a 32-byte record read as two 16-byte halves is a 2-way conflict)
@@ -540,9 +540,6 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
   int *s_outer = s_j + TILE_CAP;                 // [warps][stride] skin entries of the row being built ...
   unsigned *s_okey = reinterpret_cast<unsigned *>(s_outer + (TILE_BS / 32) * stride);   // ... their sort keys (first: the type of j) ...
   double *s_orsq = reinterpret_cast<double *>(s_okey + (TILE_BS / 32) * stride);         // ... and their squared distances
-  // FP32 prefilter: candidate positions relative to the first site of the cell, and a 64-entry survivor queue per warp
-  float4 *s_f4 = reinterpret_cast<float4 *>(s_orsq + (TILE_BS / 32) * stride);
-  unsigned short *s_queue = reinterpret_cast<unsigned short *>(s_f4 + TILE_CAP);
   __shared__ int s_rb[18], s_re[18], s_roff[18], s_pre[19];
   constexpr int NW = TILE_BS / 32;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -576,8 +573,6 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
   // per-warp site cursor state lives in registers across chunks: one warp owns sites sb+wid, sb+wid+NW, ...
   // (counts are kept per site in numneigh scratch when several chunks are needed)
   const bool single = ncand <= cap;
-  const double4 org = pos[sb];   // every candidate of the stencil lies within two cells of it
-  unsigned short *queue = s_queue + wid * 64;
   for (int cbase = 0; cbase < ncand; cbase += cap) {
     const int cn = min(cap, ncand - cbase);
     __syncthreads();
@@ -592,7 +587,6 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
       s_z[k] = rj.z;
       s_ts[k] = ts[j] & 0xffff;
       s_j[k] = j;
-      s_f4[k] = make_float4((float)(rj.x - org.x), (float)(rj.y - org.y), (float)(rj.z - org.z), 0.0f);
     }
     __syncthreads();
     for (int i = sb + wid; i < se; i += NW) {
@@ -609,12 +603,12 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
         for (int k = lane; k < min(cnt_out, stride); k += 32) outer[k] = row[rowslot(stride - 1 - k)];
         __syncwarp();
       }
-      // exact test + row append of up to 32 staged candidates (k, valid per lane), in lane order
-      auto visit = [&](const int k, const bool valid) {
+      for (int base = 0; base < cn; base += 32) {
+        const int k = base + lane;
         bool hit = false, inner = false;
         int j = -1;
         double rsq_k = 0.0, cs_k = cs1;
-        if (valid) {
+        if (k < cn) {
           j = s_j[k];
           const double2 rxy = s_xy[k];
           rsq_k = rsq_exact(ri.x - rxy.x, ri.y - rxy.y, ri.z - s_z[k]);
@@ -643,43 +637,6 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
         }
         cnt_in += __popc(m_in);
         cnt_out += __popc(m_out);
-      };
-      if (!prefilter) {
-        for (int base = 0; base < cn; base += 32) visit(base + lane, base + lane < cn);
-      } else {
-        // Six of seven staged candidates are not neighbors.  A single-precision distance (coordinates relative to the
-        // cell, error < 4e-6 of the squared cutoff, tested against the largest cutoff of the row with a 2e-4 margin)
-        // throws them out for a fifth of the instructions; the survivors are queued in candidate order and go through
-        // the exact double-precision test 32 at a time, all lanes busy.  Rows are the same, entry for entry.
-        const float fxi = (float)(ri.x - org.x), fyi = (float)(ri.y - org.y), fzi = (float)(ri.z - org.z);
-        double cnmax = cn1;
-        if (!one_type) for (int t = 1; t < na; t++) cnmax = fmax(cnmax, prow[t].cutneighsq);
-        const float lim = (float)(cnmax * 1.0002);
-        int qn = 0;
-        for (int base = 0; base < cn; base += 32) {
-          const int k = base + lane;
-          bool cand = false;
-          if (k < cn) {
-            const float4 f = s_f4[k];
-            const float dx = fxi - f.x, dy = fyi - f.y, dz = fzi - f.z;
-            cand = dx * dx + dy * dy + dz * dz <= lim;
-          }
-          const unsigned m = __ballot_sync(0xffffffffu, cand);
-          if (cand) queue[qn + __popc(m & lt)] = (unsigned short)k;
-          qn += __popc(m);
-          __syncwarp();
-          if (qn >= 32) {
-            visit(queue[lane], true);
-            __syncwarp();
-            const int rem = qn - 32;
-            const unsigned short v = lane < rem ? queue[32 + lane] : (unsigned short)0;
-            __syncwarp();
-            if (lane < rem) queue[lane] = v;
-            qn = rem;
-            __syncwarp();
-          }
-        }
-        if (qn > 0) visit(lane < qn ? queue[lane] : 0, lane < qn);
       }
       __syncwarp();
       const bool last = cbase + cap >= ncand;
@@ -845,8 +802,7 @@ static int build_rows(ucgb200_ctx *c) {
     if (tiled) {
       const int ncell_owned = c->grid.ninner[0] * c->grid.ninner[1] * c->grid.ninner[2];
       const size_t smem = (size_t)TILE_CAP * (sizeof(double2) + sizeof(double) + 2 * sizeof(int)) +
-                          (TILE_BS / 32) * (size_t)c->neigh_stride * (2 * sizeof(int) + sizeof(double)) +
-                          (size_t)TILE_CAP * sizeof(float4) + (TILE_BS / 32) * 64 * sizeof(unsigned short);
+                          (TILE_BS / 32) * (size_t)c->neigh_stride * (2 * sizeof(int) + sizeof(double));
       static bool attr_set = false;
       if (!attr_set) {
         UCG_CHECK(c, cudaFuncSetAttribute(k_build_rows_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -856,8 +812,7 @@ static int build_rows(ucgb200_ctx *c) {
       k_build_rows_tiled<<<ncell_owned, TILE_BS, smem, c->stream>>>(
           c->pos.p, c->ts.p, nlocal, c->grid, c->cell_start.p, c->gcell_start.p, c->d_pairinfo.p, na,
           c->neigh.p, c->neigh_stride, c->numneigh.p, c->d_flags.p, cap, c->levcnt.p, c->skin,
-          getenv("UCGB200_BUILD_DEFER_KEYS") ? atoi(getenv("UCGB200_BUILD_DEFER_KEYS")) : 1,
-          getenv("UCGB200_BUILD_PREFILTER") ? atoi(getenv("UCGB200_BUILD_PREFILTER")) : 1);
+          getenv("UCGB200_BUILD_DEFER_KEYS") ? atoi(getenv("UCGB200_BUILD_DEFER_KEYS")) : 1);
     } else {
       long long nthreads = (long long)nlocal * 32;
       k_build_rows<<<nblocks(nthreads, 256), 256, 8 * c->neigh_stride * sizeof(int), c->stream>>>(

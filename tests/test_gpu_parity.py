@@ -54,11 +54,10 @@ def test_neighbor_list_bit_exact(pkg, fixtures, ncell):
 
 
 @pytest.mark.parametrize("knobs", [dict(UCGB200_BUILD_TILED="0"), dict(UCGB200_TILE_CAP="64"), dict(UCGB200_TILE_CAP="200"),
-                                   dict(UCGB200_BUILD_PREFILTER="0"), dict(UCGB200_BUILD_DEFER_KEYS="0"),
-                                   dict(UCGB200_BUILD_PREFILTER="0", UCGB200_BUILD_DEFER_KEYS="0", UCGB200_TILE_CAP="96")])
+                                   dict(UCGB200_BUILD_DEFER_KEYS="0"), dict(UCGB200_BUILD_DEFER_KEYS="0", UCGB200_TILE_CAP="96")])
 def test_neighbor_build_variants_give_identical_rows(pkg, fixtures, monkeypatch, knobs):
-    """the cell-tiled build (default: single-precision prefilter + survivor queue, sort keys taken in a dense pass), the same
-    without either, its chunked path (small staging capacity) and the warp-per-site build must produce the same rows in
+    """the cell-tiled build (default: sort keys of the skin entries taken in a dense pass per row), the same with the keys
+    taken inline, its chunked path (small staging capacity) and the warp-per-site build must produce the same rows in
     the same order"""
     liq = _liq((5, 6, 7))
     ctx = decks.gpu_single_type(pkg, liq, fixtures)
