@@ -852,6 +852,24 @@ static int permute_all(ucgb200_ctx *c, int n) {
   return 0;
 }
 
+// UCGB200_BUILD_TRACE=1: wall-clock marks (with a stream synchronisation each) through a rebuild, to stderr
+struct BuildTrace {
+  ucgb200_ctx *c;
+  bool on;
+  double t0;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+  explicit BuildTrace(ucgb200_ctx *ctx) : c(ctx), on(getenv("UCGB200_BUILD_TRACE") && atoi(getenv("UCGB200_BUILD_TRACE"))), t0(0) {
+    if (on) { cudaStreamSynchronize(c->stream); t0 = now(); }
+  }
+  void mark(const char *what) {
+    if (!on) return;
+    cudaStreamSynchronize(c->stream);
+    const double t = now();
+    fprintf(stderr, "[build] %-28s %8.3f ms\n", what, t - t0);
+    t0 = t;
+  }
+};
+
 struct BuildTimer {
   ucgb200_ctx *c;
   long long l0;
@@ -901,9 +919,11 @@ extern "C" int ucgb200_neigh_build_local(ucgb200_ctx *c) {
   if (nlocal == 0) { timer.stop(); return 0; }
 
   // 1. pbc wrap + owned-cell histogram
+  BuildTrace trace(c);
   k_wrap_count<<<nblocks(nlocal, 256), 256, 0, st>>>(c->pos.p, nlocal, box, c->grid, c->cell_of.p,
                                                      c->cell_count.p, c->d_flags.p);
   UCG_LAUNCHED(c);
+  trace.mark("wrap_count");
   // 2. cell offsets (ncells+4 entries so that start[c0+3] is always readable)
   if ((rc = exclusive_scan(c, c->cell_count.p, c->cell_start.p, ncells + 4, nullptr))) return rc;
   // 3. counting sort into cells, deterministic inside each cell
@@ -912,7 +932,9 @@ extern "C" int ucgb200_neigh_build_local(ucgb200_ctx *c) {
   k_sort_cells<int><<<nblocks(ncells, 128), 128, 0, st>>>(c->order.p, c->cell_start.p, ncells);
   UCG_LAUNCHED(c);
   // 4. move every per-site array into cell order
+  trace.mark("scan+order+sort");
   if ((rc = permute_all(c, nlocal))) return rc;
+  trace.mark("permute");
 
   // 5. image lists: counters [0..nranks) = border records per destination rank, [nranks] = local
   const int nr = h.nranks;
@@ -925,6 +947,7 @@ extern "C" int ucgb200_neigh_build_local(ucgb200_ctx *c) {
   std::vector<int> hc(nr + 1), ho(nr + 2, 0);
   UCG_CHECK(c, cudaMemcpyAsync(hc.data(), counters, (nr + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
   if ((rc = read_flags(c))) return rc;
+  trace.mark("images count + readback");
   if (c->h_flags[3]) { c->err = "atoms lost: position outside the periodic box by more than one period"; return UCGB200_ERR_LOST_ATOMS; }
   for (int k = 0; k <= nr; k++) ho[k + 1] = ho[k] + hc[k];
   const int ntotal = ho[nr + 1];
@@ -941,6 +964,7 @@ extern "C" int ucgb200_neigh_build_local(ucgb200_ctx *c) {
                                                          c->img_code.p);
     UCG_LAUNCHED(c);
   }
+  trace.mark("images fill");
   timer.stop();
   return 0;
 }
@@ -966,7 +990,9 @@ extern "C" int ucgb200_neigh_build_finish(ucgb200_ctx *c) {
                                                               c->gcell_count.p, nullptr, nullptr, nullptr, nullptr);
     UCG_LAUNCHED(c);
   }
+  BuildTrace trace(c);
   if ((rc = exclusive_scan(c, c->gcell_count.p, c->gcell_start.p, ncells + 4, nullptr))) return rc;
+  trace.mark("ghost cell scan");
   c->nghost = nsrc;
   if ((rc = ucg_ensure_atom_capacity(c, (size_t)nlocal + nsrc, nlocal))) return rc;
   if (nsrc > 0) {
@@ -994,7 +1020,9 @@ extern "C" int ucgb200_neigh_build_finish(ucgb200_ctx *c) {
       int s = (int)(est * 1.35) + 24;
       c->neigh_stride = ((s + 15) / 16) * 16;
     }
+    trace.mark("ghost bin+sort+fill");
     if ((rc = build_rows(c))) return rc;
+    trace.mark("build_rows (+ overflow check)");
     UCG_CHECK(c, c->xhold.ensure(nlocal));
     UCG_CHECK(c, cudaMemcpyAsync(c->xhold.p, c->pos.p, (size_t)nlocal * sizeof(double4), cudaMemcpyDeviceToDevice, st));
   }
