@@ -272,7 +272,12 @@ typedef struct ucgb200_deck {
   int bethe_method, bethe_pseudo, bethe_prior;
   int thermo_every;      /* eflag/vflag on steps that are multiples of this (0 = never) */
   int cluster_freq;      /* fix cluster_switch rateFreq (0 = absent); configure it with ucgb200_cluster_configure */
-  int reserved[7];
+  /* order in which the post_force stages act = the deck's fix definition order ([stock] Modify::post_force): decimal
+   * digits, first stage in the highest place, 1 = ucgld/langevin, 2 = ucgstate, 3 = wall bias of nve/ucgld/wall/hard;
+   * 0 = 123.  Matters when the wall fix (with bias_potential) is defined before a non-ld fix ucgstate, which
+   * overwrites the ucgl the bias reads (fix_nve_ucgld_wall_hard.cpp:234-239, fix_ucgstate.cpp:130). */
+  int post_force_order;
+  int reserved[6];
 } ucgb200_deck;
 int ucgb200_deck_configure(ucgb200_ctx *ctx, const ucgb200_deck *deck);
 /* Verlet::setup [stock]: pbc, build, force_clear, pair->compute, fix setup() calls */
@@ -291,6 +296,9 @@ int ucgb200_run_between(ucgb200_ctx *ctx, int nsteps, long long beginstep, long 
 int ucgb200_thermo(ucgb200_ctx *ctx, double out[16]);
 /* sticky device error word: code (UCGB200_ERR_*), tags of the pair, rsq */
 int ucgb200_status(ucgb200_ctx *ctx, int *code, int *tag_i, int *tag_j, double *rsq);
+/* the same word WITHOUT clearing it (ucgb200_status clears a non-zero word once it has been read): lets a caller test
+ * the code first and fetch the pair's tags and distance with ucgb200_status afterwards */
+int ucgb200_status_peek(ucgb200_ctx *ctx, int *code, int *tag_i, int *tag_j, double *rsq);
 /* per-kernel-class CUDA-event timers (ms since last reset): pair, neigh, comm, modify */
 int ucgb200_timers(ucgb200_ctx *ctx, int enable, double out_ms[4], long long out_launches[4]);
 /* duration of the last pair kernel launch in ms (events on the context stream) */

@@ -60,7 +60,7 @@ class Deck(C.Structure):
         ("langevin_seed", C.c_int), ("langevin_groupbit", C.c_int),
         ("ucgstate", C.c_int), ("ucgstate_seed", C.c_int), ("ucgstate_rate", C.c_double),
         ("bethe_method", C.c_int), ("bethe_pseudo", C.c_int), ("bethe_prior", C.c_int),
-        ("thermo_every", C.c_int), ("cluster_freq", C.c_int), ("reserved", C.c_int * 7),
+        ("thermo_every", C.c_int), ("cluster_freq", C.c_int), ("post_force_order", C.c_int), ("reserved", C.c_int * 6),
     ]
 
 
@@ -498,6 +498,12 @@ class Context:
     def status(self):
         code, ti, tj, rsq = C.c_int(), C.c_int(), C.c_int(), C.c_double()
         self._l.ucgb200_status(self._h, C.byref(code), C.byref(ti), C.byref(tj), C.byref(rsq))
+        return code.value, ti.value, tj.value, rsq.value
+
+    def status_peek(self):
+        """the sticky error word without clearing it"""
+        code, ti, tj, rsq = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+        self._l.ucgb200_status_peek(self._h, C.byref(code), C.byref(ti), C.byref(tj), C.byref(rsq))
         return code.value, ti.value, tj.value, rsq.value
 
     def timers(self, enable: int = -1):

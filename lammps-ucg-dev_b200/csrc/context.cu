@@ -25,7 +25,8 @@ extern "C" int ucgb200_create(int device, ucgb200_ctx **out) {
   cudaEventCreate(&c->ev_pair1);
   c->d_flags.ensure(8);
   cudaMemset(c->d_flags.p, 0, 8 * sizeof(int));
-  cudaHostAlloc((void **)&c->h_flags, 8 * sizeof(int), cudaHostAllocDefault);
+  cudaHostAlloc((void **)&c->h_flags, 16 * sizeof(int), cudaHostAllocDefault);
+  if (c->h_flags) memset(c->h_flags, 0, 16 * sizeof(int));
   c->d_err.ensure(1);
   cudaMemset(c->d_err.p, 0, sizeof(ErrWord));
   c->d_ev.ensure(32);
@@ -206,6 +207,15 @@ int ucg_bind_texture(ucgb200_ctx *c, ucgb200_ctx::TexSlot &slot, const void *ptr
   if (slot.tex && slot.ptr == ptr && slot.bytes == bytes) return 0;
   if (slot.tex) cudaDestroyTextureObject(slot.tex);
   slot.tex = 0;
+  slot.ptr = nullptr;
+  {
+    // 1-D linear textures address at most cudaDevAttrMaxTexture1DLinearWidth texels (2^27..2^28): beyond that the
+    // caller gets a zero object and takes its LSU-pipe gather path instead of failing
+    int maxw = 0;
+    cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxTexture1DLinearWidth, c->device);
+    const size_t texel = (size_t)(desc.x + desc.y + desc.z + desc.w) / 8;
+    if (maxw > 0 && texel > 0 && bytes / texel > (size_t)maxw) return 0;
+  }
   cudaResourceDesc res{};
   res.resType = cudaResourceTypeLinear;
   res.res.linear.devPtr = const_cast<void *>(ptr);
@@ -611,7 +621,7 @@ extern "C" int ucgb200_force_clear(ucgb200_ctx *c) {
   return 0;
 }
 
-extern "C" int ucgb200_status(ucgb200_ctx *c, int *code, int *tag_i, int *tag_j, double *rsq) {
+static int read_status(ucgb200_ctx *c, int *code, int *tag_i, int *tag_j, double *rsq, bool clear) {
   if (!c) return -1;
   cudaSetDevice(c->device);
   ErrWord w;
@@ -621,9 +631,15 @@ extern "C" int ucgb200_status(ucgb200_ctx *c, int *code, int *tag_i, int *tag_j,
   if (tag_i) *tag_i = w.tag_i;
   if (tag_j) *tag_j = w.tag_j;
   if (rsq) *rsq = w.rsq;
-  if (w.code) {
+  if (w.code && clear) {
     // sticky until read: clear so that a corrected run can continue
     UCG_CHECK(c, cudaMemsetAsync(c->d_err.p, 0, sizeof(ErrWord), c->stream));
   }
   return w.code;
+}
+extern "C" int ucgb200_status(ucgb200_ctx *c, int *code, int *tag_i, int *tag_j, double *rsq) {
+  return read_status(c, code, tag_i, tag_j, rsq, true);
+}
+extern "C" int ucgb200_status_peek(ucgb200_ctx *c, int *code, int *tag_i, int *tag_j, double *rsq) {
+  return read_status(c, code, tag_i, tag_j, rsq, false);
 }

@@ -118,7 +118,7 @@ __global__ void k_langevin(const double4 *__restrict__ vel, double4 *__restrict_
 }
 
 // ---- resident run loop: every per-site fix stage between two pair evaluations in ONE pass
-// post_force fixes in definition order (ucgld/langevin, ucgstate, wall bias) -> final_integrate of
+// post_force fixes in the deck's definition order (default ucgld/langevin, ucgstate, wall bias) -> final_integrate of
 // this step -> [initial_integrate of the next step -> Neighbor::check_distance].  The arithmetic of
 // each stage is that of the single-stage kernels above, applied in the same order to the same
 // values, so trajectories are identical; the site record is read and written once (~270 B/site)
@@ -144,6 +144,7 @@ struct TailArgs {
   // integrator
   int groupbit, bias;
   double barrier, dtv, dtf;
+  int order;           // post_force stages, one per byte, first stage in the lowest byte: 1 langevin, 2 ucgstate, 3 wall bias
   int fuse_next;       // also do the next step's initial_integrate + check_distance
   double triggersq;
   int *flags;
@@ -160,44 +161,53 @@ __global__ void __launch_bounds__(256) k_step_tail(TailArgs a) {
   const int m = a.mask[i];
   double4 x = a.pos[i], v = a.vel[i], f = a.frc[i];
   bool fdirty = false, xdirty = false;
-  if (a.langevin && (m & a.lgroupbit)) {                                  // k_langevin
-    const double gamma1 = a.gfac[type];
-    const double gamma2 = a.gfac[a.ntypes + 1 + type] * a.tsqrt;
-    const double fran = gamma2 * (philox_uniform(a.lseed, 0x4c414e47u, (unsigned)a.tag[i], a.step) - 0.5);
-    f.w += gamma1 * v.w + fran;
-    fdirty = true;
-  }
-  if (a.ucgstate_mode >= 0) {                                             // k_ucgstate
-    int state = (t >> 16) & 1;
-    double p;
-    if (a.tinfo[type].nstates == 1) {
-      if (a.ucgstate_mode != 1) state = 0;
-      p = 1.0;
+  const bool ingroup = (m & a.groupbit) != 0;
+  // post_force stages in the deck's fix definition order (TailArgs::order, [stock] Modify::post_force)
+#pragma unroll
+  for (int stage = 0; stage < 3; stage++) {
+    const int which = (a.order >> (8 * stage)) & 0xff;
+    if (which == 1) {
+      if (a.langevin && (m & a.lgroupbit)) {                              // k_langevin
+        const double gamma1 = a.gfac[type];
+        const double gamma2 = a.gfac[a.ntypes + 1 + type] * a.tsqrt;
+        const double fran = gamma2 * (philox_uniform(a.lseed, 0x4c414e47u, (unsigned)a.tag[i], a.step) - 0.5);
+        f.w += gamma1 * v.w + fran;
+        fdirty = true;
+      }
+    } else if (which == 2) {
+      if (a.ucgstate_mode >= 0) {                                         // k_ucgstate
+        int state = (t >> 16) & 1;
+        double p;
+        if (a.tinfo[type].nstates == 1) {
+          if (a.ucgstate_mode != 1) state = 0;
+          p = 1.0;
+        } else {
+          const double2 s = a.scores[i];
+          const double e0 = exp(fmin(s.x, 700.0)), e1 = exp(fmin(s.y, 700.0));
+          p = fmin(1.0 - 1e-6, fmax(1e-6, e1 / (e0 + e1)));
+          if (a.ucgstate_mode == 2) {
+            double fac = state == 0 ? p / (1.0 - p) : (1.0 - p) / p;
+            fac = fmin(fac, 1.0) * a.urate;
+            const double r = philox_uniform(a.useed, 0x55434753u, (unsigned)a.tag[i], a.step);
+            state = (r < fac) ? 0 : 1;
+          } else if (a.ucgstate_mode == 0) {
+            state = (int)round(p);
+          }
+        }
+        a.ucgp[i] = p;
+        if (a.ucgstate_mode != 1) {
+          t = type | (state << 16);
+          x.w = p;
+          xdirty = true;
+        }
+      }
     } else {
-      const double2 s = a.scores[i];
-      const double e0 = exp(fmin(s.x, 700.0)), e1 = exp(fmin(s.y, 700.0));
-      p = fmin(1.0 - 1e-6, fmax(1e-6, e1 / (e0 + e1)));
-      if (a.ucgstate_mode == 2) {
-        double fac = state == 0 ? p / (1.0 - p) : (1.0 - p) / p;
-        fac = fmin(fac, 1.0) * a.urate;
-        const double r = philox_uniform(a.useed, 0x55434753u, (unsigned)a.tag[i], a.step);
-        state = (r < fac) ? 0 : 1;
-      } else if (a.ucgstate_mode == 0) {
-        state = (int)round(p);
+      if (WALL && a.bias && ingroup) {                                    // k_wall_bias
+        const double y = x.w - 0.5;
+        f.w += (-7980 * y * y * y * y * y * y * y * y * y + 2 * y) * 10 * a.barrier;
+        fdirty = true;
       }
     }
-    a.ucgp[i] = p;
-    if (a.ucgstate_mode != 1) {
-      t = type | (state << 16);
-      x.w = p;
-      xdirty = true;
-    }
-  }
-  const bool ingroup = (m & a.groupbit) != 0;
-  if (WALL && a.bias && ingroup) {                                        // k_wall_bias
-    const double y = x.w - 0.5;
-    f.w += (-7980 * y * y * y * y * y * y * y * y * y + 2 * y) * 10 * a.barrier;
-    fdirty = true;
   }
   double dtfm = 0.0, dtflm = 0.0;
   if (ingroup) {                                                          // k_nve_final
@@ -364,6 +374,7 @@ extern "C" int ucgb200_kinetic_energy(ucgb200_ctx *c, int groupbit, double *ke_s
   return 0;
 }
 
+int ucg_post_force_order(const ucgb200_deck &d, int order[3]);   // run.cu
 // Fused tail of a resident step (see k_step_tail).  gfac layout as uploaded by ucgb200_fix_langevin.
 int ucg_step_tail(ucgb200_ctx *c, const ucgb200_deck &d, double tsqrt, int fuse_next) {
   cudaSetDevice(c->device);
@@ -393,6 +404,11 @@ int ucg_step_tail(ucgb200_ctx *c, const ucgb200_deck &d, double tsqrt, int fuse_
   a.dtv = c->dt; a.dtf = 0.5 * c->dt * c->ftm2v;
   a.fuse_next = fuse_next; a.triggersq = 0.25 * c->skin * c->skin; a.flags = c->d_flags.p; a.maxdisp = c->d_maxdisp.p;
   a.step = (unsigned long long)c->ntimestep;
+  {
+    int ord[3];
+    if (ucg_post_force_order(d, ord)) return fail(c, "deck: post_force_order must be a permutation of the digits 1 2 3");
+    a.order = ord[0] | (ord[1] << 8) | (ord[2] << 16);
+  }
   if (fuse_next) {
     UCG_CHECK(c, cudaMemsetAsync(c->d_flags.p, 0, sizeof(int), c->stream));
     UCG_CHECK(c, cudaMemsetAsync(c->d_maxdisp.p, 0, sizeof(unsigned long long), c->stream));

@@ -803,11 +803,8 @@ static int build_rows(ucgb200_ctx *c) {
       const int ncell_owned = c->grid.ninner[0] * c->grid.ninner[1] * c->grid.ninner[2];
       const size_t smem = (size_t)TILE_CAP * (sizeof(double2) + sizeof(double) + 2 * sizeof(int)) +
                           (TILE_BS / 32) * (size_t)c->neigh_stride * (2 * sizeof(int) + sizeof(double));
-      static bool attr_set = false;
-      if (!attr_set) {
-        UCG_CHECK(c, cudaFuncSetAttribute(k_build_rows_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
-      }
+      // the attribute is per device: set it on every call (a process may hold contexts on several GPUs)
+      UCG_CHECK(c, cudaFuncSetAttribute(k_build_rows_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       if (smem > 96 * 1024) return fail(c, "neighbor rows too long for the tiled build");
       k_build_rows_tiled<<<ncell_owned, TILE_BS, smem, c->stream>>>(
           c->pos.p, c->ts.p, nlocal, c->grid, c->cell_start.p, c->gcell_start.p, c->d_pairinfo.p, na,

@@ -103,27 +103,61 @@ struct StageTimer {
   }
 };
 
+// the three post_force stages in the deck's fix definition order (ucgb200_deck::post_force_order; 0 = 123)
+int ucg_post_force_order(const ucgb200_deck &d, int order[3]) {
+  int code = d.post_force_order ? d.post_force_order : 123;
+  bool seen[4] = {false, false, false, false};
+  for (int k = 2; k >= 0; k--) {
+    const int s = code % 10;
+    code /= 10;
+    if (s < 1 || s > 3 || seen[s]) return -1;
+    seen[s] = true;
+    order[k] = s;
+  }
+  return code == 0 ? 0 : -1;
+}
+
 static int post_force(ucgb200_ctx *c, bool at_setup) {
   const ucgb200_deck &d = c->deck;
-  int rc;
-  // fixes act in definition order: langevin (thermostat) must precede ucgstate
-  // (fix_ucgstate.cpp:143-156); the wall bias belongs to the integrator fix.
-  if (d.langevin) {
-    double tt = current_t_target(c);
-    if (c->lang_g1.empty()) { if ((rc = langevin_factors(c, c->lang_g1, c->lang_g2))) return rc; }
-    if ((rc = ucgb200_fix_langevin(c, c->lang_g1.data(), c->lang_g2.data(), c->n_formal, std::sqrt(tt),
-                                   d.langevin_seed, c->ntimestep, d.langevin_groupbit ? d.langevin_groupbit : 1, 0)))
-      return rc;
-  }
-  if (d.ucgstate) {
-    int mode = d.ucgstate == 1 ? 0 : (d.ucgstate == 2 ? 1 : 2);
-    if ((rc = ucgb200_fix_ucgstate(c, mode, d.ucgstate_seed, d.ucgstate_rate, c->ntimestep))) return rc;
-  }
-  // [stock] Fix::setup() is a no-op for the wall fix, so no bias at step 0
-  if (!at_setup && d.nve == 2 && d.wall_bias) {
-    if ((rc = ucgb200_fix_wall_bias(c, d.wall_barrier, d.nve_groupbit ? d.nve_groupbit : 1))) return rc;
+  int rc, order[3];
+  if (ucg_post_force_order(d, order)) return fail(c, "deck: post_force_order must be a permutation of the digits 1 2 3");
+  // fixes act in definition order ([stock] Modify::post_force): 1 ucgld/langevin, 2 ucgstate, 3 the wall bias of the
+  // integrator fix.  The thermostat must precede ucgstate (fix_ucgstate.cpp:143-156) for t_target, not for post_force.
+  for (int k = 0; k < 3; k++) {
+    if (order[k] == 1 && d.langevin) {
+      double tt = current_t_target(c);
+      if (c->lang_g1.empty()) { if ((rc = langevin_factors(c, c->lang_g1, c->lang_g2))) return rc; }
+      if ((rc = ucgb200_fix_langevin(c, c->lang_g1.data(), c->lang_g2.data(), c->n_formal, std::sqrt(tt),
+                                     d.langevin_seed, c->ntimestep, d.langevin_groupbit ? d.langevin_groupbit : 1, 0)))
+        return rc;
+    }
+    if (order[k] == 2 && d.ucgstate) {
+      int mode = d.ucgstate == 1 ? 0 : (d.ucgstate == 2 ? 1 : 2);
+      if ((rc = ucgb200_fix_ucgstate(c, mode, d.ucgstate_seed, d.ucgstate_rate, c->ntimestep))) return rc;
+    }
+    // [stock] Fix::setup() is a no-op for the wall fix, so no bias at step 0
+    if (order[k] == 3 && !at_setup && d.nve == 2 && d.wall_bias) {
+      if ((rc = ucgb200_fix_wall_bias(c, d.wall_barrier, d.nve_groupbit ? d.nve_groupbit : 1))) return rc;
+    }
   }
   return 0;
+}
+
+// The pair kernels report "Pair distance < table inner cutoff" & co. (error->one in the reference,
+// pair_table_ucgld.cpp:223-230) through the sticky device word and go on.  The resident loop reads the code with the
+// rebuild flag that crosses to the host every step anyway (same pinned read-back, no extra synchronisation) and stops
+// the run with the UCGB200_ERR_* code; ucgb200_status then yields the pair.
+static int queue_error_readback(ucgb200_ctx *c) {
+  UCG_CHECK(c, cudaMemcpyAsync(c->h_flags + 8, &c->d_err.p->code, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+static int device_error(ucgb200_ctx *c) {
+  const int code = c->h_flags[8];
+  if (!code) return 0;
+  c->err = code == UCGB200_ERR_TABLE_INNER ? "Pair distance < table inner cutoff"
+           : code == UCGB200_ERR_TABLE_OUTER ? "Pair distance > table outer cutoff"
+           : code == UCGB200_ERR_DENSITY_TYPE ? "Declared type in RLEUCG does not exist." : "device error word set";
+  return code;
 }
 
 extern "C" int ucgb200_setup(ucgb200_ctx *c) {
@@ -142,7 +176,9 @@ extern "C" int ucgb200_setup(ucgb200_ctx *c) {
   c->lang_g1.clear();
   c->lang_g2.clear();
   if ((rc = post_force(c, true))) return rc;
-  return 0;
+  if ((rc = queue_error_readback(c))) return rc;
+  UCG_CHECK(c, cudaStreamSynchronize(c->stream));
+  return device_error(c);
 }
 
 extern "C" int ucgb200_run(ucgb200_ctx *c, int nsteps) {
@@ -191,6 +227,7 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
       if (!c->ev_flag) UCG_CHECK(c, cudaEventCreateWithFlags(&c->ev_flag, cudaEventDisableTiming));
       UCG_CHECK(c, cudaMemcpyAsync(c->h_flags, c->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       UCG_CHECK(c, cudaMemcpyAsync(c->h_flags + 6, c->d_maxdisp.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+      if ((rc = queue_error_readback(c))) return rc;
       UCG_CHECK(c, cudaEventRecord(c->ev_flag, c->stream));
       c->maxdisp_valid = true;
       const double quiet = 0.8 * 0.5 * c->skin;
@@ -207,10 +244,12 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
       if (flag) pair_in_flight = false;   // discarded
     } else {
       StageTimer t(c, 1);
+      if ((rc = queue_error_readback(c))) return rc;     // rides on the synchronisation of the decision below
       if ((rc = do_decide(c, pre_integrated, &flag))) return rc;
       t.stop();
       c->last_maxdisp = -1.0;   // unknown until a fused tail has reported it
     }
+    if ((rc = device_error(c))) return rc;   // set by a pair evaluation of an earlier step (or of setup)
     // fix cluster_switch: force_reneighbor at next_reneighbor; pre_exchange() rebuilds, labels the
     // clusters and switches types (fix_cluster_switch.cpp:464-481), then Verlet rebuilds again
     if (cluster_due) {
@@ -252,6 +291,12 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
       c->thermo[0] = e;
       for (int k = 0; k < 6; k++) c->thermo[1 + k] = v[k];
     }
+  }
+  // the last pair evaluation(s) of this piece: one read-back per run_between call
+  if (nsteps > 0) {
+    if ((rc = queue_error_readback(c))) return rc;
+    UCG_CHECK(c, cudaStreamSynchronize(c->stream));
+    if ((rc = device_error(c))) return rc;
   }
   return 0;
 }

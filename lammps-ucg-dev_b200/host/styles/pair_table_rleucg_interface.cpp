@@ -221,7 +221,7 @@ void PairTable_RLEUCG_INTERFACE::compute(int eflag, int vflag) {
   h.f = f.data();
   dev->check(lmp, ucgb200_atoms_download(dev->ctx, nlocal, &h, UCGB200_F_F), "atoms_download");
   int code;
-  if ((code = ucgb200_status(dev->ctx, nullptr, nullptr, nullptr, nullptr))) {
+  if ((code = ucgb200_status_peek(dev->ctx, nullptr, nullptr, nullptr, nullptr))) {
     if (code == UCGB200_ERR_DENSITY_TYPE) error->one(FLERR, "Declared type in RLEUCG does not exist.");
     dev->check(lmp, code, "pair_rleucg");
   }

@@ -167,7 +167,7 @@ void PairTable_UCG_Bethe_Density::compute(int eflag, int vflag) {
   h.f = f.data(); h.ucgp = atom->ucgp;   // the style publishes its posterior in atom->ucgp (:689)
   dev->check(lmp, ucgb200_atoms_download(dev->ctx, nlocal, &h, UCGB200_F_F | UCGB200_F_UCGP), "atoms_download");
   int code;
-  if ((code = ucgb200_status(dev->ctx, nullptr, nullptr, nullptr, nullptr))) dev->check(lmp, code, "pair_bethe_density");
+  if ((code = ucgb200_status_peek(dev->ctx, nullptr, nullptr, nullptr, nullptr))) dev->check(lmp, code, "pair_bethe_density");
   double **fh = atom->f;
   for (int i = 0; i < nlocal; i++) { fh[i][0] += f[3 * i]; fh[i][1] += f[3 * i + 1]; fh[i][2] += f[3 * i + 2]; }
   double e, v[6];

@@ -198,7 +198,7 @@ void PairTable_UCGLD::compute(int eflag, int vflag) {
                                          UCGB200_F_F | UCGB200_F_UCGFORCE | UCGB200_F_SCORES | UCGB200_F_NUMSTATES),
              "atoms_download");
   int code;
-  if ((code = ucgb200_status(dev->ctx, nullptr, nullptr, nullptr, nullptr))) dev->check(lmp, code, "pair_ucgld");
+  if ((code = ucgb200_status_peek(dev->ctx, nullptr, nullptr, nullptr, nullptr))) dev->check(lmp, code, "pair_ucgld");
   double **fh = atom->f, **sh = atom->ucgsoftmaxscores;
   for (int i = 0; i < nlocal; i++) {
     fh[i][0] += f[3 * i]; fh[i][1] += f[3 * i + 1]; fh[i][2] += f[3 * i + 2];

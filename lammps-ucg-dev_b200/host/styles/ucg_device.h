@@ -72,9 +72,9 @@ class UCGDevice {
   // error->one / error->all with the reference's message texts
   void check(LAMMPS *lmp, int rc, const char *where) {
     if (rc == 0) return;
+    int code = 0, ti = 0, tj = 0; double rsq = 0.0;
+    if (rc > 0) ucgb200_status(ctx, &code, &ti, &tj, &rsq);   // one read fetches the pair and clears the sticky word
     if (rc == UCGB200_ERR_TABLE_INNER || rc == UCGB200_ERR_TABLE_OUTER) {
-      int code, ti, tj; double rsq;
-      ucgb200_status(ctx, &code, &ti, &tj, &rsq);
       lmp->error->one(FLERR, rc == UCGB200_ERR_TABLE_INNER ? "Pair distance < table inner cutoff: atoms {} {} dist {}"
                                                             : "Pair distance > table outer cutoff: atoms {} {} dist {}",
                       ti, tj, sqrt(rsq));

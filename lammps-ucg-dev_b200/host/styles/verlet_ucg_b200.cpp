@@ -29,14 +29,26 @@ void VerletUCGB200::collect_deck() {
   auto *pair = dynamic_cast<UCGDeckPart *>(force->pair);
   if (!pair || !pair->ucg_deck(deck))
     error->all(FLERR, "run_style ucg/b200 needs one of the UCG pair styles (table_ucg_bethe without the noise prior); use run_style verlet");
+  // the post_force stages act in fix definition order ([stock] Modify::post_force); the device loop is told which
+  int order = 0, nstage = 0;
+  bool have[4] = {false, false, false, false};
   for (int i = 0; i < modify->nfix; i++) {
     Fix *f = modify->fix[i];
     auto *part = dynamic_cast<UCGDeckPart *>(f);
-    if (part && part->ucg_deck(deck)) { parts.push_back(part); continue; }
+    const ucgb200_deck before = deck;
+    if (part && part->ucg_deck(deck)) {
+      parts.push_back(part);
+      const int stage = deck.langevin != before.langevin ? 1 : (deck.ucgstate != before.ucgstate ? 2 : (deck.nve == 2 && before.nve != 2 ? 3 : 0));
+      if (stage && !have[stage]) { have[stage] = true; order = order * 10 + stage; nstage++; }
+      continue;
+    }
     if (part || modify->fmask[i])
       error->all(FLERR, "run_style ucg/b200: fix {} (style {}) has no part in the device loop; use run_style verlet", f->id, f->style);
   }
   if (comm->nprocs > 1) error->all(FLERR, "run_style ucg/b200 drives one context per process; multi-brick runs use the resident NCCL driver");
+  for (int stage = 1; stage <= 3; stage++)
+    if (!have[stage]) order = order * 10 + stage;   // absent stages do nothing, any place will do
+  deck.post_force_order = order;
   deck.thermo_every = output ? output->thermo_every : 0;
 }
 

@@ -478,12 +478,15 @@ struct Sim {
       lmp.update->integrate->setup(1);
       return;
     }
+    if (respa) respa_steps();
     for (int i = 0; i < lmp.modify->nfix; i++) if (lmp.modify->fmask[i] & FixConst::PRE_EXCHANGE) lmp.modify->fix[i]->setup_pre_exchange();
     pbc();
     borders();
     build_all();
     nbuilds = 0;
     compute_forces(ev);
+    if (respa) for (int l = 0; l < respa->nlevels; l++) { respa->flevel[l].assign(3 * (size_t)(lmp.atom->nlocal + lmp.atom->nghost), 0.0); }
+    if (respa) respa_copy(respa->nlevels - 1, false);
     for (int i = 0; i < lmp.modify->nfix; i++) lmp.modify->fix[i]->setup(ev ? 1 : 0);
   }
   void run(int nsteps, int thermo_every) {
@@ -502,6 +505,7 @@ struct Sim {
       u->integrate->cleanup();
       return;
     }
+    if (respa) { run_respa(nsteps, thermo_every); return; }
     for (int n = 0; n < nsteps; n++) {
       u->ntimestep++;
       int ev = thermo_every > 0 && (u->ntimestep % thermo_every == 0);
@@ -539,6 +543,84 @@ struct Sim {
       for (int i = 0; i < m->nfix; i++) if (m->fmask[i] & FixConst::END_OF_STEP) m->fix[i]->end_of_step();
       timers[3] += now() - t6;
     }
+  }
+
+  // ---------------------------------------------------------------- rRESPA ([stock] Respa::setup/run/recurse)
+  // Restricted to what the UCG fixes can see: the pair style sits at the outermost level (the stock default), no
+  // bonded or k-space levels, f_level[] kept for atom->f only (stock fix RESPA stores f and torque, nothing else).
+  // Both class sets (the reference's and the product's) are driven by this same loop, so the test compares their
+  // *_respa entry points under an identical call sequence (UCG/fix_nve_ucgld.cpp:155-173,
+  // fix_nve_ucgld_wall_hard.cpp:206-224, fix_ucgstate.cpp:134-136, fix_ucgld_langevin.cpp:217-220).
+  struct DriverRespa : Respa {
+    explicit DriverRespa(LAMMPS *l) : Respa(l) {}
+    std::vector<int> loop;
+    std::vector<double> steps;
+    std::vector<std::vector<double>> flevel;
+  };
+  DriverRespa *respa = nullptr;
+  void respa_steps() {
+    respa->steps.assign(respa->nlevels, 0.0);
+    respa->steps[respa->nlevels - 1] = lmp.update->dt;
+    for (int l = respa->nlevels - 2; l >= 0; l--) respa->steps[l] = respa->steps[l + 1] / respa->loop[l];
+    respa->step = respa->steps.data();
+  }
+  void respa_copy(int ilevel, bool to_f) {
+    Atom *a = lmp.atom;
+    std::vector<double> &fl = respa->flevel[ilevel];
+    fl.resize(3 * (size_t)(a->nlocal + a->nghost), 0.0);
+    const size_t n = 3 * (size_t)a->nlocal;
+    if (!n) return;
+    if (to_f) memcpy(&a->f[0][0], fl.data(), n * sizeof(double));
+    else memcpy(fl.data(), &a->f[0][0], n * sizeof(double));
+  }
+  void respa_recurse(int ilevel, int ev) {
+    Modify *m = lmp.modify;
+    respa_copy(ilevel, true);
+    for (int iloop = 0; iloop < respa->loop[ilevel]; iloop++) {
+      for (int i = 0; i < m->nfix; i++)
+        if (m->fmask[i] & FixConst::INITIAL_INTEGRATE_RESPA) m->fix[i]->initial_integrate_respa(ev, ilevel, iloop);
+      if (ilevel == respa->nlevels - 1) {
+        if (decide()) {
+          for (int i = 0; i < m->nfix; i++) if (m->fmask[i] & FixConst::PRE_EXCHANGE) m->fix[i]->pre_exchange();
+          pbc();
+          borders();
+          build_all();
+        } else if (ilevel == 0) forward_comm();
+      } else if (ilevel == 0) forward_comm();
+      if (ilevel) respa_recurse(ilevel - 1, ev);
+      force_clear();
+      if (ilevel == respa->nlevels - 1) {
+        int eflag, vflag;
+        ev_flags(ev, eflag, vflag);
+        lmp.force->pair->compute(eflag, vflag);
+      }
+      if (lmp.force->newton) reverse_comm();
+      for (int i = 0; i < m->nfix; i++)
+        if (m->fmask[i] & FixConst::POST_FORCE_RESPA) m->fix[i]->post_force_respa(ev, ilevel, iloop);
+      for (int i = 0; i < m->nfix; i++)
+        if (m->fmask[i] & FixConst::FINAL_INTEGRATE_RESPA) m->fix[i]->final_integrate_respa(ilevel, iloop);
+    }
+    respa_copy(ilevel, false);
+  }
+  void run_respa(int nsteps, int thermo_every) {
+    Update *u = lmp.update;
+    Modify *m = lmp.modify;
+    for (int n = 0; n < nsteps; n++) {
+      u->ntimestep++;
+      const int ev = thermo_every > 0 && (u->ntimestep % thermo_every == 0);
+      respa_recurse(respa->nlevels - 1, ev);
+      for (int i = 0; i < m->nfix; i++) if (m->fmask[i] & FixConst::END_OF_STEP) m->fix[i]->end_of_step();
+    }
+  }
+  // ---------------------------------------------------------------- minimiser hook ([stock] Min::energy_force)
+  // One force evaluation the way the minimisers do it: pbc/borders/rebuild when the skin rule fires, force_clear,
+  // pair->compute, reverse_comm, then every fix's min_post_force (UCG/fix_ucgstate.cpp:138-140).
+  void min_energy_force(int ev) {
+    Modify *m = lmp.modify;
+    lmp.update->whichflag = 2;
+    if (decide()) { pbc(); borders(); build_all(); } else forward_comm();
+    compute_forces(ev);
+    for (int i = 0; i < m->nfix; i++) if (m->fmask[i] & FixConst::MIN_POST_FORCE) m->fix[i]->min_post_force(ev);
   }
 
   // ---------------------------------------------------------------- input lines
@@ -619,7 +701,24 @@ struct Sim {
         resident = true;
       } else
 #endif
-      if (w.at(1) != "verlet") lmp.error->all(FLERR, "Unrecognized integrate style '{}'", w.at(1));
+      if (w.at(1) == "respa") {
+        // run_style respa N n1 ... n(N-1)   ([stock] Respa::Respa: loop factors between adjacent levels)
+        const int nl = utils::inumeric(FLERR, w.at(2), false, &lmp);
+        if (nl < 1 || (int)w.size() < 3 + nl - 1) lmp.error->all(FLERR, "Illegal run_style respa command");
+        delete lmp.update->integrate;
+        respa = new DriverRespa(&lmp);
+        respa->nlevels = nl;
+        respa->loop.assign(nl, 1);
+        for (int l = 0; l < nl - 1; l++) {
+          respa->loop[l] = utils::inumeric(FLERR, w.at(3 + l), false, &lmp);
+          if (respa->loop[l] <= 0) lmp.error->all(FLERR, "Illegal run_style respa command");
+        }
+        respa->flevel.resize(nl);
+        respa->level_outer = nl - 1;
+        lmp.update->integrate = respa;
+        lmp.update->integrate_style = (char *)"respa";
+        respa_steps();
+      } else if (w.at(1) != "verlet") lmp.error->all(FLERR, "Unrecognized integrate style '{}'", w.at(1));
     } else if (cmd == "group") {
       // harness-only: "group NAME" registers the next free group bit; masks come in through ref_atoms
       if (lmp.group->find(w.at(1)) < 0) lmp.group->names[lmp.group->ngroup++] = utils::strdup(w.at(1));
@@ -818,7 +917,14 @@ int ref_fix_call(void *h, int ifix, int what) {
     else if (what == 3) f->end_of_step();
     else if (what == 4) f->setup(0);
     else if (what == 5) f->pre_exchange();
+    else if (what == 6) f->min_post_force(0);
+    else if (what == 7) f->post_force_respa(0, 0, 0);
+    else if (what == 8) f->post_force_respa(0, s->respa ? s->respa->nlevels - 1 : 0, 0);
   });
+}
+int ref_min_energy_force(void *h, int ev) {
+  Sim *s = (Sim *)h;
+  return guarded(s, [&] { s->init(); s->min_energy_force(ev); });
 }
 double ref_fix_scalar(void *h, int ifix) { return ((Sim *)h)->lmp.modify->fix[ifix]->compute_scalar(); }
 double ref_fix_vector(void *h, int ifix, int k) { return ((Sim *)h)->lmp.modify->fix[ifix]->compute_vector(k); }

@@ -125,8 +125,13 @@ class RefSim:
         self._ck(self.l.ref_run(self.h, int(nsteps), int(thermo_every)))
 
     def fix_call(self, ifix, what):
-        names = dict(initial_integrate=0, post_force=1, final_integrate=2, end_of_step=3, setup=4, pre_exchange=5)
+        names = dict(initial_integrate=0, post_force=1, final_integrate=2, end_of_step=3, setup=4, pre_exchange=5,
+                     min_post_force=6, post_force_respa_inner=7, post_force_respa_outer=8)
         self._ck(self.l.ref_fix_call(self.h, int(ifix), names[what]))
+
+    def min_energy_force(self, ev=0):
+        """one force evaluation the way [stock] Min::energy_force does it: ... pair->compute, then every fix's min_post_force"""
+        self._ck(self.l.ref_min_energy_force(self.h, int(ev)))
 
     def fix_scalar(self, ifix):
         return self.l.ref_fix_scalar(self.h, int(ifix))

@@ -394,3 +394,99 @@ def test_run_style_ucg_b200_config4_deck(pkg, fixtures, tmp_path):
         text = (tmp_path / "res" / name).read_text()
         assert text == (tmp_path / "gpu" / name).read_text() == (tmp_path / "ref" / name).read_text()
         assert len(text.strip().split("\n")) == 6     # steps 1 6 11 16 21 26
+
+
+# ------------------------------------------------------------------ rRESPA and minimiser entry points
+def _cmp_state(a, b, tol_x=1e-10, tol_v=1e-8):
+    assert rel_err(b["x"], a["x"]) <= tol_x
+    assert rel_err(b["v"], a["v"]) <= tol_v
+    assert rel_err(b["ucgl"], a["ucgl"]) <= 1e-9
+    assert rel_err(b["ucgvl"], a["ucgvl"]) <= tol_v
+    assert rel_err(b["f"], a["f"]) <= 1e-6
+    assert rel_err(b["ucgp"], a["ucgp"]) <= 1e-8
+
+
+@pytest.mark.parametrize("fixes", [
+    ["fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld", "fix 2 all ucgstate"],
+    ["fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld/wall/hard", "fix 2 all ucgstate ld"],
+])
+@pytest.mark.parametrize("levels", ["respa 2 4", "respa 3 2 3", "respa 1"])
+def test_respa_entry_points(pkg, fixtures, fixes, levels):
+    """initial_integrate_respa / final_integrate_respa / post_force_respa of the drop-in classes against the
+    reference's (UCG/fix_nve_ucgld.cpp:155-173, fix_nve_ucgld_wall_hard.cpp:206-224, fix_ucgstate.cpp:134-136): the
+    same restricted rRESPA loop (pair style at the outermost level) drives both class sets for 12 steps; per-level
+    step sizes come from Respa::step, the innermost level moves x and lambda, the others only kick"""
+    liq = _liq(6)
+    sims = []
+    for cls in (rb.RefSim, rb.HostSim):
+        s = cls.single_type(liq, fixtures["table4096"], fixtures["state"])
+        s.command("run_style " + levels)
+        for f in fixes:
+            s.command(f)
+        s.setup(1)
+        s.run(12, 12)
+        sims.append(s)
+    ref, gpu = sims
+    a, b = ref.get_atoms(), gpu.get_atoms()
+    _cmp_state(a, b)
+    away = np.abs(a["ucgp"] - 0.5) > 1e-7 if "ld" not in fixes[2] else np.abs(a["ucgl"] - 0.5) > 1e-9
+    assert np.array_equal(a["ucgstate"][away], b["ucgstate"][away])
+    assert abs(gpu.eng_vdwl() - ref.eng_vdwl()) <= 1e-8 * abs(ref.eng_vdwl())
+    if levels == "respa 1":
+        # one level with loop 1 is velocity Verlet: must equal the verlet run of the same deck (both class sets)
+        v = rb.HostSim.single_type(liq, fixtures["table4096"], fixtures["state"])
+        for f in fixes:
+            v.command(f)
+        v.setup(1)
+        v.run(12, 12)
+        c = v.get_atoms()
+        assert rel_err(b["x"], c["x"]) <= 1e-12 and rel_err(b["ucgl"], c["ucgl"]) <= 1e-12
+
+
+def test_respa_langevin_acts_on_the_outermost_level_only(pkg, fixtures):
+    """Fix_UCGLD_Langevin::post_force_respa (fix_ucgld_langevin.cpp:217-220): a call at an inner level must not touch
+    ucgforce, a call at the outermost level is post_force.  Checked on both class sets through the drag term: with
+    gamma2 = 0 impossible (T > 0), so compare ucgforce before/after the inner-level call exactly and the
+    outer-level call against drag + bounded noise"""
+    liq = _liq(5)
+    for cls in (rb.RefSim, rb.HostSim):
+        s = cls.single_type(liq, fixtures["table4096"], fixtures["state"])
+        s.command("run_style respa 2 4")
+        s.command("fix 1 all nve/ucgld")
+        s.command("fix 2 all ucgld/langevin 1.0 1.0 0.5 4711")
+        s.command("fix 3 all ucgstate ld")
+        s.setup(0)
+        before = s.get_atoms()["ucgforce"].copy()
+        s.fix_call(1, "post_force_respa_inner")
+        assert np.array_equal(s.get_atoms()["ucgforce"], before), cls.__name__
+        s.fix_call(1, "post_force_respa_outer")
+        after = s.get_atoms()
+        g1 = -10.0 / 0.5
+        g2 = np.sqrt(10.0) * np.sqrt(24.0 / 0.5 / 0.002)
+        noise = (after["ucgforce"] - before - g1 * after["ucgvl"]) / g2
+        assert noise.min() >= -0.5 - 1e-9 and noise.max() <= 0.5 + 1e-9, cls.__name__
+        assert abs(noise.mean()) < 6 * np.sqrt(1 / 12 / liq.n)
+
+
+def test_min_post_force(pkg, fixtures):
+    """FixUCGState::min_post_force (fix_ucgstate.cpp:138-140) through the force evaluation of a minimiser: displace
+    the sites between two evaluations so that the second one sees new scores"""
+    liq = _liq(6)
+    out = []
+    for cls in (rb.RefSim, rb.HostSim):
+        s = cls.single_type(liq, fixtures["table4096"], fixtures["state"])
+        s.command("fix 0 all ttarget/stub 1.0")
+        s.command("fix 2 all ucgstate")
+        s.setup(1)
+        x = liq.x + 0.02 * np.sin(np.arange(liq.n * 3).reshape(liq.n, 3))      # a line-search move
+        s.set_state(x=x)
+        s.min_energy_force(1)
+        out.append((s.get_atoms(), s.eng_vdwl()))
+    (a, ea), (b, eb) = out
+    assert rel_err(b["f"], a["f"]) <= 1e-6
+    assert rel_err(b["ucgsoftmaxscores"], a["ucgsoftmaxscores"]) <= 1e-6
+    assert rel_err(b["ucgp"], a["ucgp"]) <= 1e-10
+    assert rel_err(b["ucgl"], a["ucgl"]) <= 1e-10          # deterministic mode copies ucgp into ucgl
+    away = np.abs(a["ucgp"] - 0.5) > 1e-9
+    assert np.array_equal(a["ucgstate"][away], b["ucgstate"][away])
+    assert abs(eb - ea) <= 1e-8 * abs(ea)

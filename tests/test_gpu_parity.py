@@ -511,3 +511,68 @@ def test_speculative_pair_launch_changes_nothing(pkg, fixtures, monkeypatch):
     assert ta[0] == tb[0] and np.array_equal(ta[1:7], tb[1:7])
     for k in a:
         assert np.array_equal(a[k], b[k]), k
+
+
+# ------------------------------------------------------- resident loop: error word and post_force order
+def test_resident_run_stops_on_table_inner_cutoff(pkg, fixtures):
+    """'Pair distance < table inner cutoff' is error->one in the reference (pair_table_ucgld.cpp:223): the resident
+    loop must not run on with that pair's force missing.  The code comes back from ucgb200_setup /
+    ucgb200_run, the word stays readable (peek) and one ucgb200_status call yields the pair and clears it."""
+    from lammps_ucg_dev_b200 import UCGError
+    liq = _liq(5)
+    ctx = decks.gpu_single_type(pkg, liq, fixtures)
+    ctx.deck_configure(pair_style=0, nve=1, ucgstate=1, thermo_every=0)
+    ctx.setup()
+    ctx.run(3)                               # a healthy run first
+    assert ctx.status_peek()[0] == 0
+    x = ctx.atoms_download(["x"])["x"]
+    x[1] = x[0] + np.array([0.3, 0.0, 0.0])  # r = 0.3 < table inner cutoff 0.5
+    ctx.atoms_upload(liq.n, x=x)
+    with pytest.raises(UCGError) as ei:
+        ctx.run(5)
+    assert ei.value.rc == 1
+    code, ti, tj, rsq = ctx.status_peek()
+    assert code == 1 and {ti, tj} == {1, 2}
+    assert ctx.status() == (code, ti, tj, rsq)
+    assert ctx.status()[0] == 0              # cleared by the read
+    # the same at setup
+    liq.x[1] = liq.x[0] + np.array([0.3, 0.0, 0.0])
+    ctx2 = decks.gpu_single_type(pkg, liq, fixtures)
+    ctx2.deck_configure(pair_style=0, nve=1, ucgstate=1, thermo_every=0)
+    with pytest.raises(UCGError) as ei:
+        ctx2.setup()
+    assert ei.value.rc == 1
+
+
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_post_force_order_follows_the_deck(pkg, fixtures, monkeypatch, fused):
+    """[stock] Modify::post_force runs the fixes in definition order.  With fix nve/ucgld/wall/hard bias_potential
+    defined BEFORE a non-ld fix ucgstate the bias reads the ucgl of the integrator, not the ucgp the state fix is
+    about to write: the oracle registers the fixes in that order, the device loop is told through
+    ucgb200_deck::post_force_order (VerletUCGB200::collect_deck records it from the deck)"""
+    monkeypatch.setenv("UCGB200_FUSED_TAIL", fused)
+    liq = _liq(6)
+    nsteps = 12
+    res = {}
+    for order in (321, 123):          # wall bias first / last
+        ctx = decks.gpu_single_type(pkg, liq, fixtures)
+        o = decks.orc_single_type(liq, fixtures)
+        o.fix_ttarget(1.0)
+        if order == 321:
+            o.fix_nve_wall(1, 1, 0.3); o.fix_ucgstate(mode=0)
+        else:
+            o.fix_ucgstate(mode=0); o.fix_nve_wall(1, 1, 0.3)
+        ctx.deck_configure(pair_style=0, nve=2, wall_bias=1, wall_barrier=0.3, ucgstate=1, thermo_every=0,
+                           post_force_order=order)
+        ctx.setup(); o.setup()
+        ctx.run(nsteps); o.run(nsteps)
+        got = ctx.atoms_download(["x", "ucgl", "ucgvl", "ucgp", "ucgforce"])
+        ref = o.get_atoms()
+        for k, tol in (("ucgvl", 1e-9), ("ucgl", 1e-9), ("ucgp", 1e-9), ("ucgforce", F_TOL)):
+            assert rel_err(got[k], ref[k]) <= tol, (order, k)
+        res[order] = got
+    # the two orders really differ (otherwise the test proves nothing)
+    assert np.abs(res[321]["ucgvl"] - res[123]["ucgvl"]).max() > 1e-6
+    with pytest.raises(Exception):
+        ctx.deck_configure(pair_style=0, nve=2, wall_bias=1, ucgstate=1, post_force_order=122)
+        ctx.setup(); ctx.run(1)
