@@ -353,6 +353,141 @@ __global__ void __launch_bounds__(BS) k_pair_ucgld_fast(FastArgs p) {
   if (EV) block_reduce_store<7, BS>(ev, p.partials);
 }
 
+// ------------------------------------------------------------- Newton's-third-law variant (experiment, UCGB200_N3L=1)
+// Every owned-owned pair is evaluated ONCE, by the site with the smaller index: the i side accumulates in registers
+// as in the fast kernel, the j side (f[3], ucgforce, 2 scores: pair_table_ucgld.cpp:500-502, :516, :527-529) is
+// scattered with one red.global.add.f64 per component.  Pairs with a ghost partner are evaluated from the owned side
+// only (no reverse halo), exactly as in the full-list kernel.  The kernel walks the same full rows and skips the
+// entries its partner owns, so rows, skin levels and ghosts need no second list.  Results are no longer bit-
+// reproducible (atomic order), but stay inside the north-star tolerances; frc / scores must be zero on entry and every
+// site adds its own sums atomically as well.  Measured against the full-list kernel in profiles/r02_pair_n3l.json.
+__device__ __forceinline__ void red_add(double *p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+
+template <bool EV, int W, int BS>
+__global__ void __launch_bounds__(BS) k_pair_ucgld_n3l(FastArgs p) {
+  constexpr int LPA = 4;
+  extern __shared__ double2 s_tab[];
+  {
+    const int nwords = p.tablen * W;
+    for (int k = threadIdx.x; k < nwords; k += BS) s_tab[k] = p.table[k];
+    __syncthreads();
+  }
+  const int sub = threadIdx.x % LPA;
+  const int groups_per_block = BS / LPA;
+  const int tlm1 = p.tablen - 1;
+  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+  int level = 7;
+  if (p.levcnt) {
+    const double md = sqrt(__longlong_as_double((long long)*p.maxdisp)) * (1.0 + 1e-12);
+    level = min(7, (int)floor(2.0 * md * p.inv_w));
+  }
+  double *frc = reinterpret_cast<double *>(p.frc), *sco = reinterpret_cast<double *>(p.scores);
+  for (int base = blockIdx.x * groups_per_block; base < p.nlocal; base += gridDim.x * groups_per_block) {
+    const int gid = base + threadIdx.x / LPA;
+    const bool active = gid < p.nlocal;
+    const int i = active ? gid : p.nlocal - 1;
+    const double4 ri = p.pos[i];
+    const double li = ri.w, ai = 1.0 - li;
+    const bool si1 = (p.sbits[i >> 5] >> (i & 31)) & 1;
+    int jnum = active ? p.numneigh[i] : 0;
+    if (p.levcnt && level < 7 && active) {
+      const uint4 lc = p.levcnt[i];
+      const unsigned w = level < 2 ? lc.x : (level < 4 ? lc.y : (level < 6 ? lc.z : lc.w));
+      jnum = min(jnum, (int)((level & 1) ? (w >> 16) : (w & 0xffffu)));
+    }
+    const int *row = p.neigh + (size_t)i * p.stride;
+    double fx = 0, fy = 0, fz = 0, accA = 0, accB = 0, S0 = 0, S1 = 0;
+    double vir[6] = {0, 0, 0, 0, 0, 0};
+    RowWalk<LPA> rw(row, sub, jnum);
+    // next entry this lane has to evaluate: entries owned by the partner (j owned, j < i) are skipped before any gather
+    auto next_entry = [&](int &jj) -> int {
+      while (jj < jnum) {
+        const int j = rw.raw(jj) & UCG_NEIGHMASK;
+        if (j > i) return j;     // ghosts have j >= nlocal > i
+        jj += LPA;
+        rw.advance();
+      }
+      return -1;
+    };
+    int jj = sub;
+    int j = next_entry(jj), sj = 0;
+    double4 rj = ri;
+    if (j >= 0) { rj = ldtex(p.postex, j); sj = tex1Dfetch<unsigned>(p.sbtex, j >> 5) >> (j & 31); }
+    while (j >= 0) {
+      jj += LPA;
+      rw.advance();
+      const int jn = next_entry(jj);
+      int sn = 0;
+      double4 rn = rj;
+      if (jn >= 0) { rn = ldtex(p.postex, jn); sn = tex1Dfetch<unsigned>(p.sbtex, jn >> 5) >> (jn & 31); }
+      const double dx = ri.x - rj.x, dy = ri.y - rj.y, dz = ri.z - rj.z;
+      const double rsq = rsq_exact(dx, dy, dz);
+      if (rsq < p.cutsq) {
+        const int it = (int)__dmul_rn(__dadd_rn(rsq, -p.innersq), p.invdelta);
+        if (rsq < p.innersq || it >= tlm1) {
+          report_error(p.err, rsq < p.innersq ? UCGB200_ERR_TABLE_INNER : UCGB200_ERR_TABLE_OUTER, p.tag[i], p.tag[j], rsq);
+        } else {
+          const double rsq_it = __dadd_rn(p.innersq, __dmul_rn((double)it, p.delta));
+          const double frac = (rsq - rsq_it) * p.invdelta;
+          const double2 *r0 = s_tab + it * W;
+          const double2 a00 = r0[0], a01 = r0[1], a11 = r0[W - 1];
+          const double2 b00 = r0[W], b01 = r0[W + 1], b11 = r0[2 * W - 1];
+          const double u00 = a00.x + frac * (b00.x - a00.x), f00 = a00.y + frac * (b00.y - a00.y);
+          const double u01 = a01.x + frac * (b01.x - a01.x), f01 = a01.y + frac * (b01.y - a01.y);
+          const double u11 = a11.x + frac * (b11.x - a11.x), f11 = a11.y + frac * (b11.y - a11.y);
+          double u10, f10;
+          if (W == 4) {
+            const double2 a10 = r0[2], b10 = r0[W + 2];
+            u10 = a10.x + frac * (b10.x - a10.x);
+            f10 = a10.y + frac * (b10.y - a10.y);
+          } else { u10 = u01; f10 = f01; }
+          const double lj = rj.w, bj = 1.0 - lj;
+          const double A = bj * u00 + lj * u01, B = bj * u10 + lj * u11;
+          const double FA = bj * f00 + lj * f01, FB = bj * f10 + lj * f11;
+          accA += A; accB += B;
+          const double fpair = ai * FA + li * FB;
+          const bool s1 = sj & 1;
+          S0 += s1 ? u01 : u00;
+          S1 += s1 ? u11 : u10;
+          const double px = dx * fpair, py = dy * fpair, pz = dz * fpair;
+          fx += px; fy += py; fz += pz;
+          const bool owned = j < p.nlocal;
+          if (owned) {
+            // the partner's side of the same pair (:500-502, :516, :527-529)
+            red_add(frc + 4 * (size_t)j, -px); red_add(frc + 4 * (size_t)j + 1, -py); red_add(frc + 4 * (size_t)j + 2, -pz);
+            red_add(frc + 4 * (size_t)j + 3, -(li * (u11 - u10) + ai * (u01 - u00)));
+            red_add(sco + 2 * (size_t)j, -(si1 ? u10 : u00) * p.inv_kT);
+            red_add(sco + 2 * (size_t)j + 1, -(si1 ? u11 : u01) * p.inv_kT);
+          }
+          if (EV) {
+            // a pair with a ghost partner is seen again from the image's owner: half of it belongs here
+            const double wgt = owned ? 1.0 : 0.5;
+            const double e = (ai * A + li * B) * wgt, fw = fpair * wgt;
+            ev[0] += e;
+            vir[0] += dx * dx * fw; vir[1] += dy * dy * fw; vir[2] += dz * dz * fw;
+            vir[3] += dx * dy * fw; vir[4] += dx * dz * fw; vir[5] += dy * dz * fw;
+          }
+        }
+      }
+      j = jn; rj = rn; sj = sn;
+    }
+    fx = group_sum<LPA>(fx); fy = group_sum<LPA>(fy); fz = group_sum<LPA>(fz);
+    accA = group_sum<LPA>(accA); accB = group_sum<LPA>(accB);
+    S0 = group_sum<LPA>(S0); S1 = group_sum<LPA>(S1);
+    if (active && sub == 0) {
+      red_add(frc + 4 * (size_t)i, fx); red_add(frc + 4 * (size_t)i + 1, fy); red_add(frc + 4 * (size_t)i + 2, fz);
+      red_add(frc + 4 * (size_t)i + 3, -p.dmu - (accB - accA));
+      red_add(sco + 2 * (size_t)i, -S0 * p.inv_kT);
+      red_add(sco + 2 * (size_t)i + 1, -p.dmu * p.inv_kT - S1 * p.inv_kT);
+    }
+    if (EV) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) ev[1 + k] += vir[k];
+    }
+  }
+  if (EV) block_reduce_store<7, BS>(ev, p.partials);
+}
+
 __global__ void k_reduce_partials(const double *__restrict__ partials, int nblocks, int nvals, double *__restrict__ out) {
   // one warp per value, fixed order => deterministic
   int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -401,6 +536,24 @@ static int launch_fast(ucgb200_ctx *c, FastArgs &a, int &nblk) {
   if (nblk > need) nblk = need;
   if (EV) UCG_CHECK(c, c->d_partials.ensure((size_t)nblk * 8 + 64));
   a.partials = c->d_partials.p;
+  kern<<<nblk, BS, smem, c->stream>>>(a);
+  UCG_LAUNCHED(c);
+  return 0;
+}
+
+template <bool EV, int W>
+static int launch_n3l(ucgb200_ctx *c, FastArgs &a, int &nblk) {
+  constexpr int BS = EV ? 512 : 768;   // the energy/virial variant spills at 768 threads (80 registers)
+  const size_t smem = (size_t)a.tablen * W * sizeof(double2);
+  auto kern = k_pair_ucgld_n3l<EV, W, BS>;
+  UCG_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nblk = sm_count(c->device);
+  const int groups = BS / 4, need = (a.nlocal + groups - 1) / groups;
+  if (nblk > need) nblk = need;
+  if (EV) UCG_CHECK(c, c->d_partials.ensure((size_t)nblk * 8 + 64));
+  a.partials = c->d_partials.p;
+  UCG_CHECK(c, cudaMemsetAsync(c->frc.p, 0, (size_t)a.nlocal * sizeof(double4), c->stream));
+  UCG_CHECK(c, cudaMemsetAsync(c->scores.p, 0, (size_t)a.nlocal * sizeof(double2), c->stream));
   kern<<<nblk, BS, smem, c->stream>>>(a);
   UCG_LAUNCHED(c);
   return 0;
@@ -479,7 +632,10 @@ extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
       a.sbtex = c->tex_sbits.tex;
     }
     const int bs = env_int("UCGB200_BS", 768), pf = env_int("UCGB200_PF", 1);
-    if (c->fast_ntab == 3) {
+    if (env_int("UCGB200_N3L", 0) && a.postex && a.sbtex && a.smem_table) {
+      if (c->fast_ntab == 3) rc = ev ? launch_n3l<true, 3>(c, a, nblk) : launch_n3l<false, 3>(c, a, nblk);
+      else rc = ev ? launch_n3l<true, 4>(c, a, nblk) : launch_n3l<false, 4>(c, a, nblk);
+    } else if (c->fast_ntab == 3) {
       if (lpa_fast == 4) rc = dispatch_fast<4, 3>(c, a, nblk, ev, bs, pf);
       else if (lpa_fast == 16) rc = dispatch_fast<16, 3>(c, a, nblk, ev, bs, pf);
       else rc = dispatch_fast<8, 3>(c, a, nblk, ev, bs, pf);

@@ -576,3 +576,32 @@ def test_post_force_order_follows_the_deck(pkg, fixtures, monkeypatch, fused):
     with pytest.raises(Exception):
         ctx.deck_configure(pair_style=0, nve=2, wall_bias=1, ucgstate=1, post_force_order=122)
         ctx.setup(); ctx.run(1)
+
+
+@pytest.mark.parametrize("ncell", [8, (5, 6, 7)])
+def test_pair_ucgld_newton_third_law_variant(pkg, fixtures, monkeypatch, ncell):
+    """UCGB200_N3L=1: every owned-owned pair evaluated once, the partner's side scattered with red.global.add.f64
+    (pair_table_ucgld.cpp:500-502, :516, :527-529 — what the reference's half list does).  Atomic order makes the
+    sums non-reproducible in the last bits, so the comparison is to the north-star tolerances, against the oracle
+    and against the default full-list kernel."""
+    liq = _liq(ncell)
+    ctx = decks.gpu_single_type(pkg, liq, fixtures)
+    ctx.neigh_build()
+    ctx.pair_ucgld(1, 1)
+    base = ctx.atoms_download(["f", "ucgforce", "ucgsoftmaxscores"])
+    e0, v0 = ctx.pair_energy_virial()
+    monkeypatch.setenv("UCGB200_N3L", "1")
+    o = decks.orc_single_type(liq, fixtures)
+    ref = decks.oracle_forces(o)
+    for ev in (1, 0):
+        ctx.pair_ucgld(ev, ev)
+        got = ctx.atoms_download(["f", "ucgforce", "ucgsoftmaxscores"])
+        for k in got:
+            assert rel_err(got[k], ref[k]) <= F_TOL, (ev, k)
+            assert rel_err(got[k], base[k]) <= 1e-11, (ev, k)
+    ctx.pair_ucgld(1, 1)
+    e, vir = ctx.pair_energy_virial()
+    assert abs(e - o.eng_vdwl()) <= E_TOL * abs(o.eng_vdwl())
+    assert rel_err(vir, o.virial()) <= E_TOL
+    assert abs(e - e0) <= 1e-11 * abs(e0) and rel_err(vir, v0) <= 1e-10
+    assert ctx.status()[0] == 0
