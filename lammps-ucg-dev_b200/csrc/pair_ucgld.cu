@@ -488,6 +488,157 @@ __global__ void __launch_bounds__(BS) k_pair_ucgld_n3l(FastArgs p) {
   if (EV) block_reduce_store<7, BS>(ev, p.partials);
 }
 
+// ---------------------------------------------- Newton's third law with TMA bulk reductions (UCGB200_N3L=2)
+// Same pair ownership as k_pair_ucgld_n3l, but the partner's six sums {fx, fy, fz, ucgforce, s0, s1} leave the SM as
+// ONE 48-byte cp.reduce.async.bulk.global.shared::cta.add.f64 (SASS UBLKRED) from a per-lane staging slot in shared
+// memory instead of six red.global.add.f64: the reduction is carried out by the L2 slices, the SM only issues the
+// descriptor.  Measured in isolation (csrc/microbench.cu, profiles/r02_pair_floors.json) 27.5 M such operations take
+// 0.35 ms against 0.87 ms for the six REDs.  Accumulator layout: acc[j] = 6 contiguous doubles (48-byte records, zero on
+// entry); k_merge_acc turns them into the frc / scores records.  The staging slots sit behind the 192 KB table:
+// 48 B x 704 threads is what fits into 227 KB.
+__device__ __forceinline__ void bulk_red_48(double *gdst, const double *slot) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(slot);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 48;" ::"l"(gdst), "r"(sa) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+template <bool EV, int W, int BS>
+__global__ void __launch_bounds__(BS) k_pair_ucgld_n3l_bulk(FastArgs p, double *__restrict__ acc) {
+  constexpr int LPA = 4;
+  extern __shared__ double2 s_tab[];
+  double *slot = reinterpret_cast<double *>(s_tab + (size_t)p.tablen * W) + threadIdx.x * 6;
+  {
+    const int nwords = p.tablen * W;
+    for (int k = threadIdx.x; k < nwords; k += BS) s_tab[k] = p.table[k];
+    __syncthreads();
+  }
+  const int sub = threadIdx.x % LPA;
+  const int groups_per_block = BS / LPA;
+  const int tlm1 = p.tablen - 1;
+  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+  int level = 7;
+  if (p.levcnt) {
+    const double md = sqrt(__longlong_as_double((long long)*p.maxdisp)) * (1.0 + 1e-12);
+    level = min(7, (int)floor(2.0 * md * p.inv_w));
+  }
+  for (int base = blockIdx.x * groups_per_block; base < p.nlocal; base += gridDim.x * groups_per_block) {
+    const int gid = base + threadIdx.x / LPA;
+    const bool active = gid < p.nlocal;
+    const int i = active ? gid : p.nlocal - 1;
+    const double4 ri = p.pos[i];
+    const double li = ri.w, ai = 1.0 - li;
+    const bool si1 = (p.sbits[i >> 5] >> (i & 31)) & 1;
+    int jnum = active ? p.numneigh[i] : 0;
+    if (p.levcnt && level < 7 && active) {
+      const uint4 lc = p.levcnt[i];
+      const unsigned w = level < 2 ? lc.x : (level < 4 ? lc.y : (level < 6 ? lc.z : lc.w));
+      jnum = min(jnum, (int)((level & 1) ? (w >> 16) : (w & 0xffffu)));
+    }
+    const int *row = p.neigh + (size_t)i * p.stride;
+    double fx = 0, fy = 0, fz = 0, accA = 0, accB = 0, S0 = 0, S1 = 0;
+    double vir[6] = {0, 0, 0, 0, 0, 0};
+    RowWalk<LPA> rw(row, sub, jnum);
+    auto next_entry = [&](int &jj) -> int {
+      while (jj < jnum) {
+        const int j = rw.raw(jj) & UCG_NEIGHMASK;
+        if (j > i) return j;
+        jj += LPA;
+        rw.advance();
+      }
+      return -1;
+    };
+    int jj = sub;
+    int j = next_entry(jj), sj = 0;
+    double4 rj = ri;
+    if (j >= 0) { rj = ldtex(p.postex, j); sj = tex1Dfetch<unsigned>(p.sbtex, j >> 5) >> (j & 31); }
+    while (j >= 0) {
+      jj += LPA;
+      rw.advance();
+      const int jn = next_entry(jj);
+      int sn = 0;
+      double4 rn = rj;
+      if (jn >= 0) { rn = ldtex(p.postex, jn); sn = tex1Dfetch<unsigned>(p.sbtex, jn >> 5) >> (jn & 31); }
+      const double dx = ri.x - rj.x, dy = ri.y - rj.y, dz = ri.z - rj.z;
+      const double rsq = rsq_exact(dx, dy, dz);
+      if (rsq < p.cutsq) {
+        const int it = (int)__dmul_rn(__dadd_rn(rsq, -p.innersq), p.invdelta);
+        if (rsq < p.innersq || it >= tlm1) {
+          report_error(p.err, rsq < p.innersq ? UCGB200_ERR_TABLE_INNER : UCGB200_ERR_TABLE_OUTER, p.tag[i], p.tag[j], rsq);
+        } else {
+          const double rsq_it = __dadd_rn(p.innersq, __dmul_rn((double)it, p.delta));
+          const double frac = (rsq - rsq_it) * p.invdelta;
+          const double2 *r0 = s_tab + it * W;
+          const double2 a00 = r0[0], a01 = r0[1], a11 = r0[W - 1];
+          const double2 b00 = r0[W], b01 = r0[W + 1], b11 = r0[2 * W - 1];
+          const double u00 = a00.x + frac * (b00.x - a00.x), f00 = a00.y + frac * (b00.y - a00.y);
+          const double u01 = a01.x + frac * (b01.x - a01.x), f01 = a01.y + frac * (b01.y - a01.y);
+          const double u11 = a11.x + frac * (b11.x - a11.x), f11 = a11.y + frac * (b11.y - a11.y);
+          double u10, f10;
+          if (W == 4) {
+            const double2 a10 = r0[2], b10 = r0[W + 2];
+            u10 = a10.x + frac * (b10.x - a10.x);
+            f10 = a10.y + frac * (b10.y - a10.y);
+          } else { u10 = u01; f10 = f01; }
+          const double lj = rj.w, bj = 1.0 - lj;
+          const double A = bj * u00 + lj * u01, B = bj * u10 + lj * u11;
+          const double FA = bj * f00 + lj * f01, FB = bj * f10 + lj * f11;
+          accA += A; accB += B;
+          const double fpair = ai * FA + li * FB;
+          const bool s1 = sj & 1;
+          S0 += s1 ? u01 : u00;
+          S1 += s1 ? u11 : u10;
+          const double px = dx * fpair, py = dy * fpair, pz = dz * fpair;
+          fx += px; fy += py; fz += pz;
+          const bool owned = j < p.nlocal;
+          if (owned) {
+            // the staging slot is free again once the previous reduction has READ it
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            slot[0] = -px; slot[1] = -py; slot[2] = -pz;
+            slot[3] = -(li * (u11 - u10) + ai * (u01 - u00));
+            slot[4] = -(si1 ? u10 : u00) * p.inv_kT;
+            slot[5] = -(si1 ? u11 : u01) * p.inv_kT;
+            bulk_red_48(acc + 6 * (size_t)j, slot);
+          }
+          if (EV) {
+            const double wgt = owned ? 1.0 : 0.5;
+            const double e = (ai * A + li * B) * wgt, fw = fpair * wgt;
+            ev[0] += e;
+            vir[0] += dx * dx * fw; vir[1] += dy * dy * fw; vir[2] += dz * dz * fw;
+            vir[3] += dx * dy * fw; vir[4] += dx * dz * fw; vir[5] += dy * dz * fw;
+          }
+        }
+      }
+      j = jn; rj = rn; sj = sn;
+    }
+    fx = group_sum<LPA>(fx); fy = group_sum<LPA>(fy); fz = group_sum<LPA>(fz);
+    accA = group_sum<LPA>(accA); accB = group_sum<LPA>(accB);
+    S0 = group_sum<LPA>(S0); S1 = group_sum<LPA>(S1);
+    if (active && sub == 0) {
+      double *a = acc + 6 * (size_t)i;
+      red_add(a, fx); red_add(a + 1, fy); red_add(a + 2, fz);
+      red_add(a + 3, -p.dmu - (accB - accA));
+      red_add(a + 4, -S0 * p.inv_kT);
+      red_add(a + 5, -p.dmu * p.inv_kT - S1 * p.inv_kT);
+    }
+    if (EV) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) ev[1 + k] += vir[k];
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (EV) block_reduce_store<7, BS>(ev, p.partials);
+}
+
+__global__ void k_merge_acc(const double *__restrict__ acc, int n, double4 *__restrict__ frc, double2 *__restrict__ scores) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double2 a = reinterpret_cast<const double2 *>(acc)[3 * (size_t)i], b = reinterpret_cast<const double2 *>(acc)[3 * (size_t)i + 1],
+                c = reinterpret_cast<const double2 *>(acc)[3 * (size_t)i + 2];
+  frc[i] = make_double4(a.x, a.y, b.x, b.y);
+  scores[i] = c;
+}
+
 __global__ void k_reduce_partials(const double *__restrict__ partials, int nblocks, int nvals, double *__restrict__ out) {
   // one warp per value, fixed order => deterministic
   int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -555,6 +706,27 @@ static int launch_n3l(ucgb200_ctx *c, FastArgs &a, int &nblk) {
   UCG_CHECK(c, cudaMemsetAsync(c->frc.p, 0, (size_t)a.nlocal * sizeof(double4), c->stream));
   UCG_CHECK(c, cudaMemsetAsync(c->scores.p, 0, (size_t)a.nlocal * sizeof(double2), c->stream));
   kern<<<nblk, BS, smem, c->stream>>>(a);
+  UCG_LAUNCHED(c);
+  return 0;
+}
+
+template <bool EV, int W>
+static int launch_n3l_bulk(ucgb200_ctx *c, FastArgs &a, int &nblk) {
+  constexpr int BS = EV ? 512 : 704;   // 48-byte staging slot per thread behind the table: 196608 + 48 * 704 <= 227 KB
+  const size_t smem = (size_t)a.tablen * W * sizeof(double2) + (size_t)BS * 48;
+  if (smem > 227 * 1024) return fail(c, "N3L bulk variant: table + staging slots exceed shared memory");
+  auto kern = k_pair_ucgld_n3l_bulk<EV, W, BS>;
+  UCG_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nblk = sm_count(c->device);
+  const int groups = BS / 4, need = (a.nlocal + groups - 1) / groups;
+  if (nblk > need) nblk = need;
+  if (EV) UCG_CHECK(c, c->d_partials.ensure((size_t)nblk * 8 + 64));
+  a.partials = c->d_partials.p;
+  UCG_CHECK(c, c->pair_acc.ensure((size_t)a.nlocal * 6 + 8));
+  UCG_CHECK(c, cudaMemsetAsync(c->pair_acc.p, 0, (size_t)a.nlocal * 6 * sizeof(double), c->stream));
+  kern<<<nblk, BS, smem, c->stream>>>(a, c->pair_acc.p);
+  UCG_LAUNCHED(c);
+  k_merge_acc<<<nblocks(a.nlocal, 256), 256, 0, c->stream>>>(c->pair_acc.p, a.nlocal, c->frc.p, c->scores.p);
   UCG_LAUNCHED(c);
   return 0;
 }
@@ -632,7 +804,10 @@ extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
       a.sbtex = c->tex_sbits.tex;
     }
     const int bs = env_int("UCGB200_BS", 768), pf = env_int("UCGB200_PF", 1);
-    if (env_int("UCGB200_N3L", 0) && a.postex && a.sbtex && a.smem_table) {
+    const int n3l = env_int("UCGB200_N3L", 0);
+    if (n3l == 2 && a.postex && a.sbtex && a.smem_table && c->fast_ntab == 3) {
+      rc = ev ? launch_n3l_bulk<true, 3>(c, a, nblk) : launch_n3l_bulk<false, 3>(c, a, nblk);
+    } else if (n3l && a.postex && a.sbtex && a.smem_table) {
       if (c->fast_ntab == 3) rc = ev ? launch_n3l<true, 3>(c, a, nblk) : launch_n3l<false, 3>(c, a, nblk);
       else rc = ev ? launch_n3l<true, 4>(c, a, nblk) : launch_n3l<false, 4>(c, a, nblk);
     } else if (c->fast_ntab == 3) {

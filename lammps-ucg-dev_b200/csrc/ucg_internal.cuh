@@ -180,6 +180,7 @@ struct ucgb200_ctx {
   ucg::Buf<unsigned long long> d_maxdisp;
   bool maxdisp_valid = false;
   ucg::Buf<unsigned> statebits;
+  ucg::Buf<double> pair_acc;   // pair_ucgld.cu, N3L bulk variant: 6 doubles per owned site
   int neigh_stride = 0;
   bool list_valid = false;
   int nbuilds = 0;

@@ -922,6 +922,18 @@ int ref_fix_call(void *h, int ifix, int what) {
     else if (what == 8) f->post_force_respa(0, s->respa ? s->respa->nlevels - 1 : 0, 0);
   });
 }
+// the rRESPA entry points one by one (teacher forcing): what = 0 initial_integrate_respa(0, ilevel, iloop),
+// 1 final_integrate_respa(ilevel, iloop), 2 post_force_respa(0, ilevel, iloop)
+int ref_fix_call_respa(void *h, int ifix, int what, int ilevel, int iloop) {
+  Sim *s = (Sim *)h;
+  return guarded(s, [&] {
+    s->init();
+    Fix *f = s->lmp.modify->fix[ifix];
+    if (what == 0) f->initial_integrate_respa(0, ilevel, iloop);
+    else if (what == 1) f->final_integrate_respa(ilevel, iloop);
+    else if (what == 2) f->post_force_respa(0, ilevel, iloop);
+  });
+}
 int ref_min_energy_force(void *h, int ev) {
   Sim *s = (Sim *)h;
   return guarded(s, [&] { s->init(); s->min_energy_force(ev); });

@@ -129,6 +129,10 @@ class RefSim:
                      min_post_force=6, post_force_respa_inner=7, post_force_respa_outer=8)
         self._ck(self.l.ref_fix_call(self.h, int(ifix), names[what]))
 
+    def fix_call_respa(self, ifix, what, ilevel, iloop=0):
+        names = dict(initial_integrate_respa=0, final_integrate_respa=1, post_force_respa=2)
+        self._ck(self.l.ref_fix_call_respa(self.h, int(ifix), names[what], int(ilevel), int(iloop)))
+
     def min_energy_force(self, ev=0):
         """one force evaluation the way [stock] Min::energy_force does it: ... pair->compute, then every fix's min_post_force"""
         self._ck(self.l.ref_min_energy_force(self.h, int(ev)))

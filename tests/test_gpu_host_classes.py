@@ -406,17 +406,19 @@ def _cmp_state(a, b, tol_x=1e-10, tol_v=1e-8):
     assert rel_err(b["ucgp"], a["ucgp"]) <= 1e-8
 
 
-@pytest.mark.parametrize("fixes", [
-    ["fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld", "fix 2 all ucgstate"],
-    ["fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld/wall/hard", "fix 2 all ucgstate ld"],
-])
 @pytest.mark.parametrize("levels", ["respa 2 4", "respa 3 2 3", "respa 1"])
-def test_respa_entry_points(pkg, fixtures, fixes, levels):
+def test_respa_loop(pkg, fixtures, levels):
     """initial_integrate_respa / final_integrate_respa / post_force_respa of the drop-in classes against the
-    reference's (UCG/fix_nve_ucgld.cpp:155-173, fix_nve_ucgld_wall_hard.cpp:206-224, fix_ucgstate.cpp:134-136): the
-    same restricted rRESPA loop (pair style at the outermost level) drives both class sets for 12 steps; per-level
-    step sizes come from Respa::step, the innermost level moves x and lambda, the others only kick"""
+    reference's (UCG/fix_nve_ucgld.cpp:155-173, fix_ucgstate.cpp:134-136): the same restricted rRESPA loop (pair style
+    at the outermost level) drives both class sets for 12 steps; per-level step sizes come from Respa::step, the
+    innermost level moves x and lambda, the others only kick.
+    Deck: nve/ucgld + ucgstate ld, in which no fix writes ucgl / ucgstate after the innermost level's forward_comm.
+    (With a fix that does — deterministic ucgstate, the wall's reflection — the reference's ghosts keep the value
+    from before that write while the owners have the new one, [stock] Respa communicates at level 0 only; a drop-in
+    whose ghosts are always images of their owners cannot and should not reproduce that.  Those fixes are covered
+    call by call below.)"""
     liq = _liq(6)
+    fixes = ["fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld", "fix 2 all ucgstate ld"]
     sims = []
     for cls in (rb.RefSim, rb.HostSim):
         s = cls.single_type(liq, fixtures["table4096"], fixtures["state"])
@@ -429,11 +431,10 @@ def test_respa_entry_points(pkg, fixtures, fixes, levels):
     ref, gpu = sims
     a, b = ref.get_atoms(), gpu.get_atoms()
     _cmp_state(a, b)
-    away = np.abs(a["ucgp"] - 0.5) > 1e-7 if "ld" not in fixes[2] else np.abs(a["ucgl"] - 0.5) > 1e-9
-    assert np.array_equal(a["ucgstate"][away], b["ucgstate"][away])
+    assert np.array_equal(a["ucgstate"], b["ucgstate"])
     assert abs(gpu.eng_vdwl() - ref.eng_vdwl()) <= 1e-8 * abs(ref.eng_vdwl())
     if levels == "respa 1":
-        # one level with loop 1 is velocity Verlet: must equal the verlet run of the same deck (both class sets)
+        # one level with loop 1 is velocity Verlet: must equal the verlet run of the same deck
         v = rb.HostSim.single_type(liq, fixtures["table4096"], fixtures["state"])
         for f in fixes:
             v.command(f)
@@ -441,6 +442,49 @@ def test_respa_entry_points(pkg, fixtures, fixes, levels):
         v.run(12, 12)
         c = v.get_atoms()
         assert rel_err(b["x"], c["x"]) <= 1e-12 and rel_err(b["ucgl"], c["ucgl"]) <= 1e-12
+
+
+@pytest.mark.parametrize("fixes", [
+    ["fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld", "fix 2 all ucgstate"],
+    ["fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld/wall/hard bias_potential 0.2", "fix 2 all ucgstate ld"],
+    ["fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld/wall/hard", "fix 2 all ucgstate mc 77 0.5"],
+])
+def test_respa_entry_points_call_by_call(pkg, fixtures, fixes):
+    """every *_respa entry point called on both class sets from the same state, arrays compared after each call
+    (UCG/fix_nve_ucgld.cpp:155-173, fix_nve_ucgld_wall_hard.cpp:206-224, fix_ucgstate.cpp:134-136): level 0 of
+    initial_integrate_respa integrates positions and lambda with Respa::step[0], every other level is a kick with that
+    level's step; final_integrate_respa kicks (and reflects at the wall); fix ucgstate acts at every level"""
+    liq = _liq(5)
+    liq.ucgvl = np.random.default_rng(5).normal(0, 40.0, liq.n)      # many sites cross the wall
+    sims = []
+    for cls in (rb.RefSim, rb.HostSim):
+        s = cls.single_type(liq, fixtures["table4096"], fixtures["state"])
+        s.command("run_style respa 3 2 3")
+        for f in fixes:
+            s.command(f)
+        s.setup(0)
+        sims.append(s)
+    ref, gpu = sims
+    mc = "mc" in fixes[2]
+    calls = [(1, "initial_integrate_respa", 2), (1, "initial_integrate_respa", 1), (1, "initial_integrate_respa", 0),
+             (1, "final_integrate_respa", 0), (2, "post_force_respa", 0), (1, "initial_integrate_respa", 0),
+             (1, "final_integrate_respa", 1), (2, "post_force_respa", 2), (1, "final_integrate_respa", 2)]
+    for ifix, what, lev in calls:
+        a0 = ref.get_atoms()
+        # same input state on both sides before every call (teacher forcing)
+        gpu.set_state(x=a0["x"], v=a0["v"], ucgstate=a0["ucgstate"], ucgl=a0["ucgl"], ucgvl=a0["ucgvl"], ucgp=a0["ucgp"],
+                      f=a0["f"], ucgforce=a0["ucgforce"], scores=a0["ucgsoftmaxscores"])
+        ref.fix_call_respa(ifix, what, lev)
+        gpu.fix_call_respa(ifix, what, lev)
+        a, b = ref.get_atoms(), gpu.get_atoms()
+        for k in ("x", "v", "ucgl", "ucgvl", "ucgforce", "ucgp"):
+            if mc and what == "post_force_respa" and k == "ucgl":
+                continue
+            assert rel_err(b[k], a[k]) <= 1e-13, (what, lev, k)
+        if not (mc and what == "post_force_respa"):       # mc draws from different generators by design
+            away = (np.abs(a["ucgp"] - 0.5) > 1e-9) & (np.abs(a["ucgl"] - 0.5) > 1e-12)
+            assert np.array_equal(a["ucgstate"][away], b["ucgstate"][away]), (what, lev)
+    assert np.abs(ref.get_atoms()["x"] - liq.x).max() > 1e-4        # the sequence did move the sites
 
 
 def test_respa_langevin_acts_on_the_outermost_level_only(pkg, fixtures):

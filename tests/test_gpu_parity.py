@@ -578,10 +578,12 @@ def test_post_force_order_follows_the_deck(pkg, fixtures, monkeypatch, fused):
         ctx.setup(); ctx.run(1)
 
 
+@pytest.mark.parametrize("mode", ["1", "2"])
 @pytest.mark.parametrize("ncell", [8, (5, 6, 7)])
-def test_pair_ucgld_newton_third_law_variant(pkg, fixtures, monkeypatch, ncell):
+def test_pair_ucgld_newton_third_law_variant(pkg, fixtures, monkeypatch, ncell, mode):
     """UCGB200_N3L=1: every owned-owned pair evaluated once, the partner's side scattered with red.global.add.f64
-    (pair_table_ucgld.cpp:500-502, :516, :527-529 — what the reference's half list does).  Atomic order makes the
+    (pair_table_ucgld.cpp:500-502, :516, :527-529 — what the reference's half list does); UCGB200_N3L=2: the same
+    with one 48-byte TMA bulk reduction (cp.reduce.async.bulk.add.f64) per pair.  Atomic order makes the
     sums non-reproducible in the last bits, so the comparison is to the north-star tolerances, against the oracle
     and against the default full-list kernel."""
     liq = _liq(ncell)
@@ -590,7 +592,7 @@ def test_pair_ucgld_newton_third_law_variant(pkg, fixtures, monkeypatch, ncell):
     ctx.pair_ucgld(1, 1)
     base = ctx.atoms_download(["f", "ucgforce", "ucgsoftmaxscores"])
     e0, v0 = ctx.pair_energy_virial()
-    monkeypatch.setenv("UCGB200_N3L", "1")
+    monkeypatch.setenv("UCGB200_N3L", mode)
     o = decks.orc_single_type(liq, fixtures)
     ref = decks.oracle_forces(o)
     for ev in (1, 0):
