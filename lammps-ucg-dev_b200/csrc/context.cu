@@ -363,6 +363,7 @@ int ucg::rebuild_maps(ucgb200_ctx *c) {
   UCG_CHECK(c, cudaMemcpy(c->d_typeinfo.p, ti.data(), na * sizeof(TypeInfo), cudaMemcpyHostToDevice));
   UCG_CHECK(c, c->d_pairinfo.ensure(na * na));
   UCG_CHECK(c, cudaMemcpy(c->d_pairinfo.p, pi.data(), na * na * sizeof(PairInfo), cudaMemcpyHostToDevice));
+  c->h_pairinfo = pi;
   UCG_CHECK(c, c->d_tables.ensure(std::max(ntab, 1)));
   if (ntab) UCG_CHECK(c, cudaMemcpy(c->d_tables.p, c->tables.data(), ntab * sizeof(TableDev), cudaMemcpyHostToDevice));
 

@@ -234,28 +234,47 @@ __device__ __forceinline__ int face_options(double x, double lo, double hi, doub
 template <bool FILL>
 __global__ void k_images(const double4 *__restrict__ pos, int n, BoxDev box, ImageMap im, int *__restrict__ counters,
                          const int *__restrict__ offsets, int *__restrict__ list_owner, int *__restrict__ list_code) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double4 r = pos[i];
-  int ox[3], oy[3], oz[3];
-  int nx = face_options(r.x, box.sublo[0], box.subhi[0], box.cutghost, im.allow_lo[0], im.allow_hi[0], ox);
-  int ny = face_options(r.y, box.sublo[1], box.subhi[1], box.cutghost, im.allow_lo[1], im.allow_hi[1], oy);
-  int nz = face_options(r.z, box.sublo[2], box.subhi[2], box.cutghost, im.allow_lo[2], im.allow_hi[2], oz);
-  if (nx * ny * nz == 1) return;
-  for (int c = 0; c < nz; c++)
-    for (int b = 0; b < ny; b++)
-      for (int a = 0; a < nx; a++) {
-        int code = ox[a] + 3 * oy[b] + 9 * oz[c];
-        if (code == 0) continue;
-        int d = im.dest[code];
-        int idx = (d == im.self) ? im.nranks : d;
-        int k = atomicAdd(&counters[idx], 1);
-        if (FILL) {
-          int slot = offsets[idx] + k;
-          list_owner[slot] = i;
-          list_code[slot] = code;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  // 7 images for a site in a corner of the sub-domain, up to 26 when the box is barely wider than the ghost cutoff
+  // (a site then lies within reach of both faces of a dimension): 5 bits per code, 26 codes in two 64-bit words + one
+  unsigned long long packed[3] = {0ull, 0ull, 0ull};
+  int ncode = 0;
+  if (i < n) {
+    const double4 r = pos[i];
+    int ox[3], oy[3], oz[3];
+    const int nx = face_options(r.x, box.sublo[0], box.subhi[0], box.cutghost, im.allow_lo[0], im.allow_hi[0], ox);
+    const int ny = face_options(r.y, box.sublo[1], box.subhi[1], box.cutghost, im.allow_lo[1], im.allow_hi[1], oy);
+    const int nz = face_options(r.z, box.sublo[2], box.subhi[2], box.cutghost, im.allow_lo[2], im.allow_hi[2], oz);
+    for (int c = 0; c < nz; c++)
+      for (int b = 0; b < ny; b++)
+        for (int a = 0; a < nx; a++) {
+          const int code = ox[a] + 3 * oy[b] + 9 * oz[c];
+          if (code) { packed[ncode / 12] |= (unsigned long long)code << (5 * (ncode % 12)); ncode++; }
         }
-      }
+  }
+  // one atomicAdd per (warp, destination) instead of one per image: the counters are a handful of addresses that
+  // ~18 % of all sites hit (the unaggregated kernel spent 0.15 ms per pass at 1 M sites in L2 atomic serialisation).
+  // Slots inside a destination's list are handed out in lane order; the lists are sorted by (tag, image) later anyway.
+  const int most = __reduce_max_sync(0xffffffffu, ncode);
+  for (int t = 0; t < most; t++) {
+    const bool has = t < ncode;
+    const int code = has ? (int)((packed[t / 12] >> (5 * (t % 12))) & 31) : 0;
+    const int d = has ? im.dest[code] : -1;
+    const int idx = has ? ((d == im.self) ? im.nranks : d) : -1;
+    const unsigned active = __ballot_sync(0xffffffffu, has);
+    if (!has) continue;
+    const unsigned peers = __match_any_sync(active, idx);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&counters[idx], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    if (FILL) {
+      const int slot = offsets[idx] + base + __popc(peers & ((1u << lane) - 1));
+      list_owner[slot] = i;
+      list_code[slot] = code;
+    }
+  }
 }
 
 struct BorderRec {  // 64 B: fields_border of AtomVecUCG (atom_vec_ucg.cpp:66-67) + tag/type
@@ -524,6 +543,7 @@ k_build_rows(const double4 *__restrict__ pos, const int *__restrict__ ts, int nl
 // processed in chunks.  Row order (dz, dy, owned|ghost, index) and the inner/skin partition are
 // those of k_build_rows, so the lists are identical.
 constexpr int TILE_CAP = 768;     // candidates per chunk: 768 * 40 B = 30 KB
+constexpr int TILE_CAP_F32 = 1024;   // k_build_rows_tiled_f32: 1024 * 16 B = 16 KB
 constexpr int TILE_BS = 128;
 __global__ void __launch_bounds__(TILE_BS)
 k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, int nlocal, Grid g,
@@ -694,6 +714,195 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
   }
 }
 
+// Single-precision prefilter variant of k_build_rows_tiled for one actual type (one cutoff pair): the SAME rows in the
+// SAME order, decided exactly.  Candidates are staged as float4 {x - ox, y - oy, z - oz, index} relative to the centre
+// of the CTA's cell (16 bytes instead of 40, one LDS.128 per test), the squared distance is formed in FP32 and decides
+// the test whenever it lies further than `band` from both thresholds (cutneighsq, cutsq); `band` bounds the FP32 error
+// for every candidate within reach (host: 4 x [6 sqrt(3) E r_c + 4 r_c^2] 2^-24, E = largest |relative coordinate|,
+// r_c = cut + skin).  The ~1e-5 of the candidates inside the band are re-tested with the reference's FP64 arithmetic on
+// the records in global memory, so classification — and with it every row — is bit-identical to the FP64 kernel
+// (tests/test_gpu_parity.py::test_neighbor_build_variants_give_identical_rows).  Exact squared distances are needed
+// again only for the sort keys of the skin entries (~23 per row): they are recomputed in the dense per-row pass.
+// ~30 instead of ~75 instructions per 32 candidates.
+__global__ void __launch_bounds__(TILE_BS)
+k_build_rows_tiled_f32(const double4 *__restrict__ pos, int nlocal, Grid g, const int *__restrict__ ostart,
+                       const int *__restrict__ gstart, double cutneighsq, double cutsq, float band,
+                       int *__restrict__ neigh, int stride, int *__restrict__ numneigh, int *__restrict__ flags,
+                       int cap, uint4 *__restrict__ levcnt, double skin, int cull) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  float4 *s_c = reinterpret_cast<float4 *>(s_raw);                       // [TILE_CAP_F32] staged candidates
+  int *s_inner = reinterpret_cast<int *>(s_c + TILE_CAP_F32);            // [warps][stride] inner entries found in this chunk
+  int *s_outer = s_inner + (TILE_BS / 32) * stride;                      // [warps][stride] skin entries of the row being built
+  unsigned *s_okey = reinterpret_cast<unsigned *>(s_outer + (TILE_BS / 32) * stride);
+  __shared__ int s_rb[18], s_re[18], s_roff[18], s_pre[19];
+  constexpr int NW = TILE_BS / 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int cell = blockIdx.x;
+  const int ix = cell % g.ninner[0] + 1, iy = (cell / g.ninner[0]) % g.ninner[1] + 1, iz = cell / (g.ninner[0] * g.ninner[1]) + 1;
+  const int c = (iz * g.nc[1] + iy) * g.nc[0] + ix;
+  const int sb = ostart[c], se = ostart[c + 1];
+  if (sb >= se) return;
+  if (threadIdx.x < 18) {
+    const int r = threadIdx.x, yz = r >> 1, pass = r & 1;
+    const int dz = yz / 3 - 1, dy = yz % 3 - 1;
+    const int c0 = ((iz + dz) * g.nc[1] + (iy + dy)) * g.nc[0] + (ix - 1);
+    s_rb[r] = pass == 0 ? ostart[c0] : gstart[c0];
+    s_re[r] = pass == 0 ? ostart[c0 + 3] : gstart[c0 + 3];
+    s_roff[r] = pass == 0 ? 0 : nlocal;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int r = 0; r < 18; r++) { s_pre[r] = acc; acc += s_re[r] - s_rb[r]; }
+    s_pre[18] = acc;
+  }
+  __syncthreads();
+  const int ncand = s_pre[18];
+  // centre of this cell: relative coordinates of everything in the 27-cell stencil stay below 1.5 cell edges
+  const double ox = g.lo[0] + ((double)ix - 0.5) / g.inv[0], oy = g.lo[1] + ((double)iy - 0.5) / g.inv[1],
+               oz = g.lo[2] + ((double)iz - 0.5) / g.inv[2];
+  const float cnf = (float)cutneighsq, csf = (float)cutsq;
+  // half edges of the cell, padded by the rounding of the owned sites' cell assignment at the faces
+  // (cull == 0: a non-periodic dimension, where sites beyond the box face are binned into the edge cells — no culling)
+  const float hx = cull ? (float)(0.5 / g.inv[0]) * 1.0001f : 1e30f, hy = cull ? (float)(0.5 / g.inv[1]) * 1.0001f : 1e30f,
+              hz = cull ? (float)(0.5 / g.inv[2]) * 1.0001f : 1e30f;
+  __shared__ int s_wcnt[TILE_BS / 32];
+  int *inner_buf = s_inner + wid * stride;
+  int *outer = s_outer + wid * stride;
+  unsigned *okey = s_okey + wid * stride;
+  const unsigned lt = (1u << lane) - 1;
+  const double inv_skin = skin > 0.0 ? 1.0 / skin : 0.0;
+  const double rcut = sqrt(cutsq);
+  const bool single = ncand <= cap;
+  for (int cbase = 0; cbase < ncand; cbase += cap) {
+    const int cn_all = min(cap, ncand - cbase);
+    __syncthreads();
+    // Stage this chunk, dropping every candidate that lies further than cut + skin from the CELL (its box in
+    // relative coordinates is [-h, h]^3): such a candidate is a neighbor of none of the cell's sites.  About a quarter
+    // of the 27-cell stencil goes this way.  The compaction is stable, so rows keep their order.
+    int cn = 0;
+    for (int kb = 0; kb < cn_all; kb += TILE_BS) {
+      const int k = kb + threadIdx.x;
+      bool keep = false;
+      float4 rec;
+      if (k < cn_all) {
+        const int q = cbase + k;
+        int r = 0;
+#pragma unroll
+        for (int t = 1; t < 18; t++) r += (q >= s_pre[t]);
+        const int j = s_rb[r] + (q - s_pre[r]) + s_roff[r];
+        const double4 rj = pos[j];
+        rec = make_float4((float)(rj.x - ox), (float)(rj.y - oy), (float)(rj.z - oz), __int_as_float(j));
+        const float ex = fmaxf(fabsf(rec.x) - hx, 0.f), ey = fmaxf(fabsf(rec.y) - hy, 0.f), ez = fmaxf(fabsf(rec.z) - hz, 0.f);
+        keep = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) <= cnf + band;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) s_wcnt[wid] = __popc(m);
+      __syncthreads();
+      int off = cn;
+      for (int w = 0; w < wid; w++) off += s_wcnt[w];
+      if (keep) s_c[off + __popc(m & lt)] = rec;
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < NW; w++) tot += s_wcnt[w];
+      cn += tot;
+      __syncthreads();
+    }
+    const int cn32 = (cn + 31) & ~31;       // cap is a multiple of 32: the padded tail stays inside the staging array
+    for (int k = cn + threadIdx.x; k < cn32; k += TILE_BS)
+      s_c[k] = make_float4(1e18f, 1e18f, 1e18f, __int_as_float(-1));   // never a hit, never inside the band
+    __syncthreads();
+    for (int i = sb + wid; i < se; i += NW) {
+      const double4 ri = pos[i];
+      const float xf = (float)(ri.x - ox), yf = (float)(ri.y - oy), zf = (float)(ri.z - oz);
+      int *row = neigh + (size_t)i * stride;
+      int cnt_in = 0, cnt_out = 0;
+      if (!single && cbase > 0) {   // resume: counts parked in numneigh, skin entries at the row's tail
+        cnt_in = numneigh[i] & 0xffff;
+        cnt_out = numneigh[i] >> 16;
+        for (int k = lane; k < min(cnt_out, stride); k += 32) outer[k] = row[rowslot(stride - 1 - k)];
+        __syncwarp();
+      }
+      const int cnt_in0 = cnt_in;
+      for (int base = 0; base < cn32; base += 32) {
+        const float4 cj = s_c[base + lane];
+        const int j = __float_as_int(cj.w);
+        const float dx = xf - cj.x, dy = yf - cj.y, dz = zf - cj.z;
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        bool hit = r2 <= cnf, inner = r2 < csf;
+        if (fabsf(r2 - cnf) <= band || fabsf(r2 - csf) <= band) {
+          // too close to a threshold for FP32: the reference's arithmetic on the FP64 records
+          const double4 rj = pos[j];
+          const double rsq = rsq_exact(ri.x - rj.x, ri.y - rj.y, ri.z - rj.z);
+          hit = rsq <= cutneighsq;
+          inner = rsq < cutsq;
+        }
+        hit = hit && (j != i);
+        inner = inner && hit;
+        const unsigned m_in = __ballot_sync(0xffffffffu, inner);
+        const unsigned m_out = __ballot_sync(0xffffffffu, hit && !inner);
+        if (hit) {
+          // both kinds go to shared memory; the row is written in one dense pass below
+          const int p = inner ? cnt_in + __popc(m_in & lt) : cnt_out + __popc(m_out & lt);
+          if (p < stride) (inner ? inner_buf - cnt_in0 : outer)[p] = j;
+        }
+        cnt_in += __popc(m_in);
+        cnt_out += __popc(m_out);
+      }
+      __syncwarp();
+      const bool last = cbase + cap >= ncand;
+      const int total = cnt_in + cnt_out;
+      if (total <= stride)
+        for (int k = cnt_in0 + lane; k < cnt_in; k += 32) row[rowslot(k)] = inner_buf[k - cnt_in0];
+      if (last) {
+        unsigned lc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (total <= stride) {
+          if (single) {
+            // sort keys of the skin entries from their exact distances (same formula as k_build_rows_tiled)
+            for (int k = lane; k < cnt_out; k += 32) {
+              const double4 rj = pos[outer[k]];
+              const double rsq = rsq_exact(ri.x - rj.x, ri.y - rj.y, ri.z - rj.z);
+              const double beyond = (sqrt(rsq) - rcut) * (1.0 - 1e-9) * inv_skin;
+              okey[k] = (unsigned)fmin(fmax(beyond, 0.0) * 134217728.0, 134217727.0);
+            }
+            __syncwarp();
+            for (int k = lane; k < ((cnt_out + 31) & ~31); k += 32) {
+              const bool have = k < cnt_out;
+              const unsigned key = have ? okey[k] : 0xffffffffu;
+              int rank = 0;
+              if (have)
+                for (int m = 0; m < cnt_out; m++) {
+                  const unsigned km = okey[m];
+                  rank += (km < key) || (km == key && m < k);
+                }
+              if (have) row[rowslot(cnt_in + rank)] = outer[k];
+              const unsigned lev = have ? min(key >> 24, 7u) : 8u;
+#pragma unroll
+              for (int L = 0; L < 8; L++) lc[L] += __popc(__ballot_sync(0xffffffffu, lev <= (unsigned)L));
+            }
+#pragma unroll
+            for (int L = 0; L < 8; L++) lc[L] += cnt_in;
+          } else {
+            for (int k = lane; k < cnt_out; k += 32) row[rowslot(cnt_in + k)] = outer[k];
+#pragma unroll
+            for (int L = 0; L < 8; L++) lc[L] = total;
+          }
+        }
+        if (lane == 0) {
+          numneigh[i] = min(total, stride);
+          if (total > stride) atomicMax(&flags[1], total);
+          levcnt[i] = make_uint4(lc[0] | (lc[1] << 16), lc[2] | (lc[3] << 16), lc[4] | (lc[5] << 16), lc[6] | (lc[7] << 16));
+        }
+      } else {
+        if (total <= stride)
+          for (int k = lane; k < cnt_out; k += 32) row[rowslot(stride - 1 - k)] = outer[k];
+        if (lane == 0) numneigh[i] = (min(cnt_in, 0xffff)) | (min(cnt_out, 0x7fff) << 16);
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // [stock] Neighbor::check_distance: any owned atom moved > skin/2 since the last build
 __global__ void k_check_distance(const double4 *__restrict__ pos, const double4 *__restrict__ xhold, int n,
                                  double triggersq, int *__restrict__ flags, unsigned long long *__restrict__ maxdisp) {
@@ -799,7 +1008,26 @@ static int build_rows(ucgb200_ctx *c) {
     const int tiled = getenv("UCGB200_BUILD_TILED") ? atoi(getenv("UCGB200_BUILD_TILED")) : 1;
     int cap = getenv("UCGB200_TILE_CAP") ? atoi(getenv("UCGB200_TILE_CAP")) : TILE_CAP;   // small values exercise the chunked path
     cap = std::min(std::max(cap, 32), TILE_CAP);
-    if (tiled) {
+    const int f32 = getenv("UCGB200_BUILD_F32") ? atoi(getenv("UCGB200_BUILD_F32")) : 1;
+    if (tiled && f32 && na == 2 && c->h_pairinfo.size() == 4) {
+      // one actual type: single-precision prefilter, exact re-test inside the error band (k_build_rows_tiled_f32)
+      const int ncell_owned = c->grid.ninner[0] * c->grid.ninner[1] * c->grid.ninner[2];
+      const size_t smem = (size_t)TILE_CAP_F32 * sizeof(float4) + (TILE_BS / 32) * (size_t)c->neigh_stride * (3 * sizeof(int));
+      UCG_CHECK(c, cudaFuncSetAttribute(k_build_rows_tiled_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      if (smem > 96 * 1024) return fail(c, "neighbor rows too long for the tiled build");
+      const double cs = c->h_pairinfo[3].cutsq, cn = c->h_pairinfo[3].cutneighsq;   // the thresholds the FP64 kernels read
+      const double rc = std::sqrt(cn);
+      double edge = 0.0;
+      for (int d = 0; d < 3; d++) edge = std::max(edge, 1.0 / c->grid.inv[d]);
+      const double E = 1.5 * edge + 1e-6 * edge;
+      const float band = (float)(4.0 * (6.0 * 1.7320508 * E * rc + 4.0 * rc * rc) * 5.9604644775390625e-08);
+      int cap32 = getenv("UCGB200_TILE_CAP") ? atoi(getenv("UCGB200_TILE_CAP")) : TILE_CAP_F32;
+      cap32 = (std::min(std::max(cap32, 32), TILE_CAP_F32) / 32) * 32;   // whole passes of 32 candidates
+      k_build_rows_tiled_f32<<<ncell_owned, TILE_BS, smem, c->stream>>>(
+          c->pos.p, nlocal, c->grid, c->cell_start.p, c->gcell_start.p, cn, cs, band, c->neigh.p, c->neigh_stride,
+          c->numneigh.p, c->d_flags.p, cap32, c->levcnt.p, c->skin,
+          (c->periodic[0] && c->periodic[1] && c->periodic[2] && !(getenv("UCGB200_BUILD_CULL") && atoi(getenv("UCGB200_BUILD_CULL")) == 0)) ? 1 : 0);
+    } else if (tiled) {
       const int ncell_owned = c->grid.ninner[0] * c->grid.ninner[1] * c->grid.ninner[2];
       const size_t smem = (size_t)TILE_CAP * (sizeof(double2) + sizeof(double) + 2 * sizeof(int)) +
                           (TILE_BS / 32) * (size_t)c->neigh_stride * (2 * sizeof(int) + sizeof(double));

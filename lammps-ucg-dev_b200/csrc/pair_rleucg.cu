@@ -332,6 +332,7 @@ int ucg_rebuild_rle_maps(ucgb200_ctx *c) {
   UCG_CHECK(c, cudaMemcpy(c->d_typeinfo.p, ti.data(), nt * sizeof(TypeInfo), cudaMemcpyHostToDevice));
   UCG_CHECK(c, c->d_pairinfo.ensure(nt * nt));
   UCG_CHECK(c, cudaMemcpy(c->d_pairinfo.p, pi.data(), nt * nt * sizeof(PairInfo), cudaMemcpyHostToDevice));
+  c->h_pairinfo = pi;
   UCG_CHECK(c, c->d_tables.ensure(std::max(ntab, 1)));
   if (ntab) UCG_CHECK(c, cudaMemcpy(c->d_tables.p, c->tables.data(), ntab * sizeof(TableDev), cudaMemcpyHostToDevice));
   UCG_CHECK(c, d.d_rt.ensure(nt * sizeof(RleType)));

@@ -130,6 +130,7 @@ struct ucgb200_ctx {
   std::vector<void *> table_allocs;
   ucg::Buf<ucg::TableDev> d_tables;
   ucg::Buf<ucg::PairInfo> d_pairinfo;
+  std::vector<ucg::PairInfo> h_pairinfo;   // host copy of what d_pairinfo holds (the F32 neighbor build takes its two thresholds from it)
   ucg::Buf<ucg::TypeInfo> d_typeinfo;
   bool fast_uniform = false;   // one 2-state actual type, LINEAR tables on one rsq grid
   int fast_tab[4] = {0, 0, 0, 0};

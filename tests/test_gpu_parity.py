@@ -53,13 +53,28 @@ def test_neighbor_list_bit_exact(pkg, fixtures, ncell):
     assert np.array_equal(half_got, half_ref)
 
 
+def _canonical_rows(nl):
+    """rows with their entries ordered by (tag, image code): what every build variant must agree on.  The ORDER inside
+    a row is a schedule choice: inner entries come in stencil order in every variant, the skin entries are sorted by
+    distance when the whole stencil fits the staging capacity of the variant and stay in stencil order when it is
+    processed in chunks (then every displacement level visits the whole row)."""
+    rows = np.repeat(np.arange(len(nl["tag_i"])), nl["numneigh"])
+    key = nl["neigh_tags"].astype(np.int64) * 64 + nl["neigh_shift"]
+    o = np.lexsort((key, rows))
+    return key[o]
+
+
 @pytest.mark.parametrize("knobs", [dict(UCGB200_BUILD_TILED="0"), dict(UCGB200_TILE_CAP="64"), dict(UCGB200_TILE_CAP="200"),
-                                   dict(UCGB200_BUILD_DEFER_KEYS="0"), dict(UCGB200_BUILD_DEFER_KEYS="0", UCGB200_TILE_CAP="96")])
-def test_neighbor_build_variants_give_identical_rows(pkg, fixtures, monkeypatch, knobs):
-    """the cell-tiled build (default: sort keys of the skin entries taken in a dense pass per row), the same with the keys
-    taken inline, its chunked path (small staging capacity) and the warp-per-site build must produce the same rows in
-    the same order"""
-    liq = _liq((5, 6, 7))
+                                   dict(UCGB200_BUILD_F32="0"), dict(UCGB200_BUILD_CULL="0"), dict(UCGB200_BUILD_F32="0", UCGB200_TILE_CAP="64"),
+                                   dict(UCGB200_BUILD_F32="0", UCGB200_BUILD_DEFER_KEYS="0"),
+                                   dict(UCGB200_BUILD_F32="0", UCGB200_BUILD_DEFER_KEYS="0", UCGB200_TILE_CAP="96")])
+@pytest.mark.parametrize("ncell", [(5, 6, 7), 12])
+def test_neighbor_build_variants_give_identical_rows(pkg, fixtures, monkeypatch, knobs, ncell):
+    """the default build of a one-type system (cell-tiled, single-precision prefilter with an exact FP64 re-test inside
+    the FP32 error band), its chunked path (small staging capacity), the all-FP64 cell-tiled build (sort keys of the
+    skin entries taken in a dense pass per row, or inline; chunked) and the warp-per-site build must produce the same
+    rows; variants that sort the skin entries by distance (un-chunked cell-tiled builds) must agree entry for entry"""
+    liq = _liq(ncell)
     ctx = decks.gpu_single_type(pkg, liq, fixtures)
     ctx.neigh_build()
     a = ctx.neigh_download()
@@ -68,8 +83,23 @@ def test_neighbor_build_variants_give_identical_rows(pkg, fixtures, monkeypatch,
     ctx2 = decks.gpu_single_type(pkg, liq, fixtures)
     ctx2.neigh_build()
     b = ctx2.neigh_download()
-    for key in ("tag_i", "numneigh", "offsets", "neigh_tags", "neigh_shift"):
+    for key in ("tag_i", "numneigh", "offsets"):
         assert np.array_equal(a[key], b[key]), key
+    assert np.array_equal(_canonical_rows(a), _canonical_rows(b))
+    # the inner partition (entries inside the cutoff at build time) comes first and in the same order everywhere
+    pos = np.zeros((liq.n + 1, 3)); pos[liq.tag] = liq.x
+    box = liq.box_hi - liq.box_lo
+    ti = np.repeat(a["tag_i"], a["numneigh"])
+    for nl in (a, b):
+        d = pos[ti] - pos[nl["neigh_tags"]]
+        d -= box * np.round(d / box)
+        nl["inner"] = (d * d).sum(1) < 2.5 ** 2
+    assert np.array_equal(a["inner"], b["inner"])
+    assert np.array_equal(a["neigh_tags"][a["inner"]], b["neigh_tags"][b["inner"]])
+    if ncell == 12 and knobs.get("UCGB200_BUILD_TILED") != "0" and "UCGB200_TILE_CAP" not in knobs:
+        # 20 sites per cell: both variants hold the whole stencil at once and sort the skin entries
+        for key in ("neigh_tags", "neigh_shift"):
+            assert np.array_equal(a[key], b[key]), key
 
 
 def test_neighbor_rebuild_decision_matches(pkg, fixtures):
@@ -607,3 +637,36 @@ def test_pair_ucgld_newton_third_law_variant(pkg, fixtures, monkeypatch, ncell, 
     assert rel_err(vir, o.virial()) <= E_TOL
     assert abs(e - e0) <= 1e-11 * abs(e0) and rel_err(vir, v0) <= 1e-10
     assert ctx.status()[0] == 0
+
+
+def test_neighbor_f32_prefilter_is_exact_at_the_thresholds(pkg, fixtures, monkeypatch):
+    """pairs placed within 1e-9 .. 1e-5 of the two thresholds (cut+skin, cut), where the single-precision squared
+    distance of the default build cannot decide: the FP64 re-test must give the rows of the all-FP64 build and of the
+    oracle, entry for entry"""
+    liq = _liq(7)
+    rng = np.random.default_rng(17)
+    n = liq.n
+    x = liq.x.copy()
+    box = liq.box_hi - liq.box_lo
+    donors = rng.choice(n, 120, replace=False)
+    for k, j in enumerate(donors):
+        i = (j + 1 + k) % n
+        u = rng.normal(size=3); u /= np.linalg.norm(u)
+        target = (2.8, 2.5)[k % 2]
+        eps = (1e-9, -1e-9, 3e-7, -3e-7, 1e-5, -1e-5, 0.0)[k % 7]
+        x[j] = x[i] + (target + eps) * u
+        x[j] = liq.box_lo + np.mod(x[j] - liq.box_lo, box)
+    liq.x = x
+    rows = {}
+    for f32 in ("1", "0"):
+        monkeypatch.setenv("UCGB200_BUILD_F32", f32)
+        ctx = decks.gpu_single_type(pkg, liq, fixtures)
+        ctx.neigh_build()
+        rows[f32] = ctx.neigh_download()
+    for key in ("tag_i", "numneigh", "offsets", "neigh_tags", "neigh_shift"):
+        assert np.array_equal(rows["1"][key], rows["0"][key]), key
+    of = decks.orc_single_type(liq, fixtures, full=1)
+    of.neigh_build_all()
+    fi, fj = of.neigh_pairs()
+    nl = rows["1"]
+    assert np.array_equal(_pair_sets(nl, n), np.sort(fi.astype(np.int64) * (n + 1) + fj))
