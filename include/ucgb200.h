@@ -41,6 +41,7 @@ typedef struct ucgb200_ctx ucgb200_ctx;
 #define UCGB200_ERR_DENSITY_TYPE 4 /* rleucg/bethe_density: density CV defined for actual type 1 only (Q15) */
 #define UCGB200_ERR_LOST_ATOMS 5   /* an atom left the box by more than one period */
 #define UCGB200_ERR_BOX_TOO_SMALL 6 /* periodic box shorter than cut+skin */
+#define UCGB200_ERR_PEER_TIMEOUT 7  /* multi-brick run: a peer brick's halo did not arrive within 2 s (peer-mapped forward exchange) */
 
 /* table styles: enum{LOOKUP, LINEAR, SPLINE, BITMAP} pair_table_ucgld.h */
 #define UCGB200_TAB_LOOKUP 0
@@ -338,9 +339,10 @@ int ucgb200_halo_unpack_forward(ucgb200_ctx *ctx, const void *d_recvbuf);
 int ucgb200_neigh_flag_ptr(ucgb200_ctx *ctx, void **d_flag);
 
 /* Resident multi-brick runs: with a communicator attached, ucgb200_setup / ucgb200_run drive the
- * exchanges above themselves — NCCL send/recv groups on the context stream (one message per peer
- * pair), the rebuild decision a 4-byte ncclAllReduce(MAX) — so a step needs no host-side
- * orchestration and exactly one host synchronisation.  Rank 0 creates the id (128 bytes, the
+ * exchanges above themselves — on the context stream: the per-step ghost refresh as direct stores into the peers'
+ * mapped memory (fallback: NCCL send/recv groups plus a 4-byte ncclAllReduce(MAX) for the rebuild decision), the
+ * rebuild (migration, borders) as NCCL send/recv groups — so a step needs no host-side orchestration and exactly one
+ * host synchronisation.  Rank 0 creates the id (128 bytes, the
  * ncclUniqueId), the host layer broadcasts it by whatever means it has (MPI_Bcast inside LAMMPS,
  * torch.distributed in the tests), every rank calls _comm_init after ucgb200_halo_configure.
  * NCCL is loaded at run time (libnccl.so.2); _comm_unique_id returns -4 when it is absent. */
@@ -348,6 +350,11 @@ int ucgb200_comm_unique_id(char *id, int len);
 int ucgb200_comm_init(ucgb200_ctx *ctx, const char *id, int len);
 int ucgb200_comm_destroy(ucgb200_ctx *ctx);
 int ucgb200_comm_stats(ucgb200_ctx *ctx, long long *bytes_forward, int *nrebuilds, int *send_records);
+/* how the forward halo of the current lists travels: *peer_mapped = 1 when every brick stores its records straight
+ * into its peers' ghost staging through CUDA-IPC-mapped memory over NVLink (the default on one NVSwitch node; the flag
+ * and displacement reductions of Neighbor::decide ride in the same push), 0 for NCCL send/recv groups (UCGB200_P2P=0,
+ * or the mapping could not be established).  *pushes counts the peer-mapped exchanges so far. */
+int ucgb200_comm_transport(ucgb200_ctx *ctx, int *peer_mapped, long long *pushes);
 
 /* ------------------------------------------------------ dump / read_dump taps */
 /* Column codes: the `dump custom` keywords the reference's patched dump_custom.cpp adds

@@ -399,7 +399,14 @@ class Context:
     def comm_stats(self):
         b, r, s_ = C.c_longlong(), C.c_int(), C.c_int()
         self._ck(self._l.ucgb200_comm_stats(self._h, C.byref(b), C.byref(r), C.byref(s_)))
-        return dict(bytes_forward=b.value, rebuilds=r.value, send_records=s_.value)
+        pm, pu = C.c_int(), C.c_longlong()
+        self._ck(self._l.ucgb200_comm_transport(self._h, C.byref(pm), C.byref(pu)))
+        return dict(bytes_forward=b.value, rebuilds=r.value, send_records=s_.value, pushes=pu.value,
+                    transport="peer-mapped stores over NVLink (CUDA IPC), flags in the same push" if pm.value
+                    else "NCCL send/recv groups + all-reduce of the rebuild flag")
+
+    def comm_destroy(self):
+        self._ck(self._l.ucgb200_comm_destroy(self._h))
 
     @staticmethod
     def halo_record_bytes():

@@ -68,9 +68,23 @@ struct CommState {
   Buf<char> send, recv, fwd_send, fwd_recv;
   Buf<int> d_counts;                 // [nranks] mine, then [nranks*nranks] gathered
   std::vector<int> send_counts, recv_counts;   // border == forward counts of the current list
+  std::vector<int> count_matrix;     // [src * nranks + dst] of the last exchange_counts
   long long bytes_forward = 0;
   int nrebuilds = 0;
+  // forward halo through peer-mapped memory (UCGB200_P2P=0 keeps the NCCL send/recv path)
+  struct P2P {
+    bool tried = false, mapped = false, active = false;   // active: the current send lists fit the mapped regions
+    char *mine = nullptr;                                 // control block + two receive regions
+    char *peer[UCG_P2P_MAX_RANKS] = {nullptr};
+    size_t region_records = 0;                            // capacity of ONE receive region
+    unsigned *done = nullptr;
+    int seq = 0;
+    int remote_off[UCG_P2P_MAX_RANKS] = {0};              // my block's first record inside rank r's receive region
+    long long pushes = 0;
+  } p2p;
 };
+constexpr size_t P2P_CTL_BYTES = 2 * UCG_P2P_MAX_RANKS * sizeof(UcgP2PCtl);   // [parity][source rank]
+constexpr size_t P2P_REC = 48;                                                // sizeof(ForwardRec)
 
 CommState *state(ucgb200_ctx *c) { return static_cast<CommState *>(c->comm_state); }
 
@@ -86,6 +100,118 @@ int exchange_counts(ucgb200_ctx *c, const std::vector<int> &counts, std::vector<
   UCG_CHECK(c, cudaStreamSynchronize(c->stream));
   recv.resize(nr);
   for (int k = 0; k < nr; k++) recv[k] = all[(size_t)k * nr + me];
+  s->count_matrix = all;
+  return 0;
+}
+
+// ---------------------------------------------------------------- peer-mapped forward halo
+// One buffer per brick, mapped by every peer through CUDA IPC (the bricks are processes on one NVSwitch node).  Set up
+// once, at the first rebuild, when the size of the ghost shell is known; the handles travel through an ncclAllGather.
+// Every brick must reach the same verdict (mapped or not), hence the final MIN all-reduce.
+int p2p_setup(ucgb200_ctx *c) {
+  CommState *s = state(c);
+  CommState::P2P &p = s->p2p;
+  if (p.tried) return 0;
+  p.tried = true;
+  const int nr = c->halo.nranks, me = c->halo.rank;
+  const char *env = getenv("UCGB200_P2P");
+  int ok = (!env || atoi(env) != 0) && nr <= UCG_P2P_MAX_RANKS ? 1 : 0;
+  // region capacity: twice the largest ghost shell of any brick at this first rebuild (the liquid's density fluctuates
+  // by a few per cent; a list that ever outgrows it falls back to the NCCL path for that list)
+  size_t largest = 0;
+  for (int dst = 0; dst < nr; dst++) {
+    size_t col = 0;
+    for (int src = 0; src < nr; src++) col += (size_t)s->count_matrix[(size_t)src * nr + dst];
+    largest = std::max(largest, col);
+  }
+  p.region_records = 2 * largest + 4096;
+  const size_t bytes = P2P_CTL_BYTES + 2 * p.region_records * P2P_REC;
+  cudaIpcMemHandle_t mine{};
+  if (ok) {
+    if (cudaMalloc((void **)&p.mine, bytes) != cudaSuccess || cudaMalloc((void **)&p.done, sizeof(unsigned)) != cudaSuccess) ok = 0;
+    if (ok) {
+      cudaMemsetAsync(p.mine, 0xff, P2P_CTL_BYTES, c->stream);     // sequence numbers start at -1
+      cudaMemsetAsync(p.done, 0, sizeof(unsigned), c->stream);
+      if (cudaIpcGetMemHandle(&mine, p.mine) != cudaSuccess) ok = 0;
+    }
+    cudaGetLastError();
+  }
+  // all-gather the handles (64 bytes each) through device memory
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  Buf<char> hb;
+  UCG_CHECK(c, hb.ensure((size_t)(nr + 1) * 64));
+  UCG_CHECK(c, cudaMemcpyAsync(hb.p, &mine, 64, cudaMemcpyHostToDevice, c->stream));
+  UCG_NCCL(c, nccl().AllGather(hb.p, hb.p + 64, 64, ncclChar, s->comm, c->stream));
+  std::vector<cudaIpcMemHandle_t> all(nr);
+  UCG_CHECK(c, cudaMemcpyAsync(all.data(), hb.p + 64, (size_t)nr * 64, cudaMemcpyDeviceToHost, c->stream));
+  UCG_CHECK(c, cudaStreamSynchronize(c->stream));
+  hb.release();
+  // every brick must have produced a handle before anyone opens one
+  UCG_CHECK(c, s->d_counts.ensure((size_t)nr * (nr + 1)));
+  UCG_CHECK(c, cudaMemcpyAsync(s->d_counts.p, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  UCG_NCCL(c, nccl().AllReduce(s->d_counts.p, s->d_counts.p, 1, ncclInt32, ncclMin, s->comm, c->stream));
+  UCG_CHECK(c, cudaMemcpyAsync(&ok, s->d_counts.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  UCG_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (ok) {
+    for (int r = 0; r < nr && ok; r++) {
+      if (r == me) { p.peer[r] = p.mine; continue; }
+      void *q = nullptr;
+      if (cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+      p.peer[r] = (char *)q;
+    }
+  }
+  UCG_CHECK(c, cudaMemcpyAsync(s->d_counts.p, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  UCG_NCCL(c, nccl().AllReduce(s->d_counts.p, s->d_counts.p, 1, ncclInt32, ncclMin, s->comm, c->stream));
+  UCG_CHECK(c, cudaMemcpyAsync(&ok, s->d_counts.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  UCG_CHECK(c, cudaStreamSynchronize(c->stream));
+  p.mapped = ok != 0;
+  if (getenv("UCGB200_COMM_TRACE")) fprintf(stderr, "[ucgb200 rank %d] peer-mapped forward halo: %s (%zu records per region)\n", me, p.mapped ? "on" : "off (NCCL send/recv)", p.region_records);
+  return 0;
+}
+
+// after every rebuild: where my block starts inside each destination's receive region, and whether every brick's ghost
+// shell still fits its region (the same matrix on every brick, hence the same verdict)
+void p2p_plan(ucgb200_ctx *c) {
+  CommState *s = state(c);
+  CommState::P2P &p = s->p2p;
+  p.active = false;
+  if (!p.mapped) return;
+  const int nr = c->halo.nranks, me = c->halo.rank;
+  bool fits = true;
+  for (int dst = 0; dst < nr; dst++) {
+    size_t col = 0, before_me = 0;
+    for (int src = 0; src < nr; src++) {
+      if (src == me) before_me = col;
+      col += (size_t)s->count_matrix[(size_t)src * nr + dst];
+    }
+    if (col > p.region_records) fits = false;
+    p.remote_off[dst] = (int)before_me;
+  }
+  p.active = fits;
+}
+
+int p2p_forward(ucgb200_ctx *c) {
+  CommState *s = state(c);
+  CommState::P2P &p = s->p2p;
+  const int nr = c->halo.nranks, me = c->halo.rank;
+  const int seq = ++p.seq, parity = seq & 1;
+  UcgPushTargets t{};
+  t.nranks = nr; t.self = me; t.seq = seq;
+  for (int r = 0; r <= nr; r++) t.send_off[r] = c->halo.send_offsets[r];
+  for (int r = 0; r < nr; r++) {
+    char *base = p.peer[r];
+    t.rec[r] = base + P2P_CTL_BYTES + ((size_t)parity * p.region_records + (size_t)p.remote_off[r]) * P2P_REC;
+    t.ctl[r] = reinterpret_cast<UcgP2PCtl *>(base) + parity * UCG_P2P_MAX_RANKS + me;
+  }
+  t.local_flag = c->d_flags.p;
+  t.local_maxdisp = c->d_maxdisp.p;
+  t.done = p.done;
+  int rc;
+  if ((rc = ucg_halo_push_forward(c, t))) return rc;
+  if ((rc = ucgb200_ghosts_forward(c))) return rc;      // local periodic images meanwhile
+  if ((rc = ucg_halo_wait_reduce(c, reinterpret_cast<const UcgP2PCtl *>(p.mine) + parity * UCG_P2P_MAX_RANKS, nr, me, seq))) return rc;
+  if ((rc = ucgb200_halo_unpack_forward(c, p.mine + P2P_CTL_BYTES + (size_t)parity * p.region_records * P2P_REC))) return rc;
+  p.pushes++;
   return 0;
 }
 
@@ -190,6 +316,10 @@ extern "C" int ucgb200_comm_destroy(ucgb200_ctx *c) {
   if (!s) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  for (int r = 0; r < UCG_P2P_MAX_RANKS; r++)
+    if (s->p2p.peer[r] && s->p2p.peer[r] != s->p2p.mine) cudaIpcCloseMemHandle(s->p2p.peer[r]);
+  if (s->p2p.mine) cudaFree(s->p2p.mine);
+  if (s->p2p.done) cudaFree(s->p2p.done);
   if (s->comm) nccl().CommDestroy(s->comm);
   s->send.release(); s->recv.release(); s->fwd_send.release(); s->fwd_recv.release(); s->d_counts.release();
   delete s;
@@ -225,6 +355,8 @@ int ucg_mb_rebuild(ucgb200_ctx *c) {
   if ((rc = ucgb200_neigh_build_finish(c))) return rc;
   s->send_counts = sc;
   s->recv_counts = rcv;
+  if ((rc = p2p_setup(c))) return rc;     // first rebuild only
+  p2p_plan(c);
   UCG_CHECK(c, s->fwd_send.ensure((size_t)total(sc) * rf + 64));
   UCG_CHECK(c, s->fwd_recv.ensure((size_t)total(rcv) * rf + 64));
   s->nrebuilds++;
@@ -232,9 +364,27 @@ int ucg_mb_rebuild(ucgb200_ctx *c) {
 }
 
 // comm->forward_comm(): refresh every ghost (records from other bricks + local periodic images)
+int ucg_mb_forward(ucgb200_ctx *c);
+// with_decide: the rebuild flag and displacement bound of every brick are reduced along the way (MAX), into d_flags[0]
+// and d_maxdisp of every brick: the peer-mapped push carries them in its control words, the NCCL path adds the two
+// small all-reduces of ucg_mb_decide.  Neither synchronises with the host.
+int ucg_mb_forward_reduce(ucgb200_ctx *c, bool with_decide) {
+  CommState *s = state(c);
+  if (!s) return fail(c, "multi-brick run without ucgb200_comm_init");
+  if (s->p2p.active) { s->bytes_forward += (long long)total(s->send_counts) * (long long)P2P_REC; return p2p_forward(c); }
+  int rc = ucg_mb_forward(c);
+  if (rc || !with_decide) return rc;
+  UCG_NCCL(c, nccl().GroupStart());
+  UCG_NCCL(c, nccl().AllReduce(c->d_flags.p, c->d_flags.p, 1, ncclInt32, ncclMax, s->comm, c->stream));
+  UCG_NCCL(c, nccl().AllReduce(c->d_maxdisp.p, c->d_maxdisp.p, 1, ncclUint64, ncclMax, s->comm, c->stream));
+  UCG_NCCL(c, nccl().GroupEnd());
+  return 0;
+}
+
 int ucg_mb_forward(ucgb200_ctx *c) {
   CommState *s = state(c);
   if (!s) return fail(c, "multi-brick run without ucgb200_comm_init");
+  if (s->p2p.active) return ucg_mb_forward_reduce(c, false);
   int rf = 0, rc;
   ucgb200_halo_record_bytes(nullptr, &rf, nullptr);
   if ((rc = ucgb200_halo_pack_forward(c, s->fwd_send.p))) return rc;
@@ -283,6 +433,20 @@ int ucg_mb_allreduce_int(ucgb200_ctx *c, int *d_buf, int n, int op) {
   if (!s) return fail(c, "multi-brick fix cluster_switch without ucgb200_comm_init (it needs the resident NCCL driver)");
   const ncclRedOp_t o = op == 0 ? ncclSum : (op == 1 ? ncclMax : ncclMin);
   UCG_NCCL(c, nccl().AllReduce(d_buf, d_buf, (size_t)n, ncclInt32, o, s->comm, c->stream));
+  return 0;
+}
+
+int ucg_mb_p2p_active(ucgb200_ctx *c) {
+  CommState *s = state(c);
+  return s && s->p2p.active ? 1 : 0;
+}
+
+extern "C" int ucgb200_comm_transport(ucgb200_ctx *c, int *peer_mapped, long long *pushes) {
+  if (!c) return -1;
+  CommState *s = state(c);
+  if (!s) return fail(c, "comm not initialised");
+  if (peer_mapped) *peer_mapped = s->p2p.active ? 1 : 0;
+  if (pushes) *pushes = s->p2p.pushes;
   return 0;
 }
 

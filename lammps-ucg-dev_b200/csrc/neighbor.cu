@@ -330,6 +330,87 @@ __global__ void k_unpack_forward(double4 *__restrict__ pos, int *__restrict__ ts
   pos[s] = f.pos; ts[s] = f.ts; ucgp[s] = f.ucgp;
 }
 
+// Forward halo as direct stores into the peers' receive regions (NVLink / NVSwitch peer mapping): one kernel packs every
+// record of the send list and stores it where the destination brick will read it; no send buffer, no NCCL kernel, no
+// receive-side copy.  The last CTA to finish publishes this brick's rebuild flag and displacement bound and then the
+// sequence number in every peer's control block, behind a system-scope fence.  comm->forward_comm() of the reference:
+// the payload is AtomVecUCG's fields_comm (UCG/atom_vec_ucg.cpp:71).
+__global__ void k_push_forward(const double4 *__restrict__ pos, const int *__restrict__ ts, const double *__restrict__ ucgp,
+                               const int *__restrict__ owner, const int *__restrict__ code, int n, ImageMap im,
+                               UcgPushTargets t) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) {
+    int r = 0;
+#pragma unroll 1
+    while (r + 1 < t.nranks && k >= t.send_off[r + 1]) r++;
+    const int o = owner[k], cd = code[k];
+    double4 p = pos[o];
+    if (im.shift[cd][0] != 0.0) p.x = p.x + im.shift[cd][0];
+    if (im.shift[cd][1] != 0.0) p.y = p.y + im.shift[cd][1];
+    if (im.shift[cd][2] != 0.0) p.z = p.z + im.shift[cd][2];
+    ForwardRec f;
+    f.pos = p; f.ts = ts[o]; f.pad = 0; f.ucgp = ucgp[o];
+    reinterpret_cast<ForwardRec *>(t.rec[r])[k - t.send_off[r]] = f;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(t.done, 1u);
+    if (prev == gridDim.x - 1) {
+      *t.done = 0u;
+      const int flag = *t.local_flag;
+      const unsigned long long md = *t.local_maxdisp;
+      for (int r = 0; r < t.nranks; r++)
+        if (r != t.self) {
+          volatile UcgP2PCtl *w = t.ctl[r];
+          w->maxdisp = md;
+          w->flag = flag;
+        }
+      __threadfence_system();
+      for (int r = 0; r < t.nranks; r++)
+        if (r != t.self) {
+          volatile UcgP2PCtl *w = t.ctl[r];
+          w->seq = t.seq;
+        }
+      __threadfence_system();
+    }
+  }
+}
+
+// One thread per peer waits until that peer's push of this sequence number has landed (bounded: ~2 s of
+// %globaltimer, then the error word is set and the run stops), then the rebuild flags and displacement bounds of all
+// bricks are folded into this brick's d_flags[0] / d_maxdisp: Neighbor::decide's MPI_Allreduce without a collective.
+__global__ void k_wait_reduce(const UcgP2PCtl *ctl, int nranks, int self, int seq, int *flag, unsigned long long *maxdisp,
+                              ErrWord *err) {
+  const int r = threadIdx.x;
+  int f = 0;
+  unsigned long long md = 0ull;
+  if (r < nranks && r != self) {
+    const volatile UcgP2PCtl *w = ctl + r;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    bool ok = true;
+    while (w->seq != seq) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ull) { ok = false; break; }
+      __nanosleep(64);
+    }
+    __threadfence_system();
+    if (ok) { f = w->flag; md = w->maxdisp; }
+    else if (atomicCAS(&err->code, 0, UCGB200_ERR_PEER_TIMEOUT) == 0) { err->tag_i = r; err->tag_j = seq; err->rsq = 0.0; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    f = max(f, __shfl_xor_sync(0xffffffffu, f, o));
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, md, o);
+    md = other > md ? other : md;
+  }
+  if (threadIdx.x == 0) {
+    if (f > *flag) *flag = f;
+    if (md > *maxdisp) *maxdisp = md;
+  }
+}
+
 // ghost sources = local images [0,nlimg) followed by received border records.
 __device__ __forceinline__ double4 source_pos(int k, int nlimg, const double4 *pos, const int *lo, const int *lc,
                                               const ImageMap &im, const BorderRec *recv) {
@@ -1491,6 +1572,22 @@ extern "C" int ucgb200_halo_pack_forward(ucgb200_ctx *c, void *d_sendbuf) {
   ImageMap im = make_image_map(c);
   k_pack_forward<<<nblocks(h.nsend, 256), 256, 0, c->stream>>>(c->pos.p, c->ts.p, c->ucgp.p, c->img_owner.p, c->img_code.p,
                                                               h.nsend, im, (ForwardRec *)d_sendbuf);
+  UCG_LAUNCHED(c);
+  return 0;
+}
+
+int ucg_halo_push_forward(ucgb200_ctx *c, const UcgPushTargets &t) {
+  cudaSetDevice(c->device);
+  auto &h = c->halo;
+  ImageMap im = make_image_map(c);
+  const int nb = std::max(1, nblocks(h.nsend, 256));     // at least one CTA: the control words go out even with an empty list
+  k_push_forward<<<nb, 256, 0, c->stream>>>(c->pos.p, c->ts.p, c->ucgp.p, c->img_owner.p, c->img_code.p, h.nsend, im, t);
+  UCG_LAUNCHED(c);
+  return 0;
+}
+int ucg_halo_wait_reduce(ucgb200_ctx *c, const UcgP2PCtl *ctl_mine, int nranks, int self, int seq) {
+  cudaSetDevice(c->device);
+  k_wait_reduce<<<1, 32, 0, c->stream>>>(ctl_mine, nranks, self, seq, c->d_flags.p, c->d_maxdisp.p, c->d_err.p);
   UCG_LAUNCHED(c);
   return 0;
 }

@@ -77,6 +77,7 @@ int ucg_neigh_decide_prechecked(ucgb200_ctx *c, int *rebuild);
 int ucg_mb_rebuild(ucgb200_ctx *c);
 int ucg_mb_forward(ucgb200_ctx *c);
 int ucg_mb_decide(ucgb200_ctx *c, bool prechecked, int *rebuild);
+int ucg_mb_forward_reduce(ucgb200_ctx *c, bool with_decide);   // forward halo + MAX of the bricks' rebuild flags / displacement bounds
 
 static int do_build(ucgb200_ctx *c) { return c->halo.nranks > 1 ? ucg_mb_rebuild(c) : ucgb200_neigh_build(c); }
 static int do_forward(ucgb200_ctx *c) { return c->halo.nranks > 1 ? ucg_mb_forward(c) : ucgb200_ghosts_forward(c); }
@@ -204,8 +205,11 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
   // k_step_tail) unless UCGB200_FUSED_TAIL=0; it needs an integrator fix and a single brick loop
   const bool fused = d.nve && !(getenv("UCGB200_FUSED_TAIL") && atoi(getenv("UCGB200_FUSED_TAIL")) == 0);
   bool pre_integrated = false;   // initial_integrate + check_distance of this step already done by the last tail
-  // speculative launch of the next pair evaluation (single brick, fused tail); UCGB200_SPECULATE=0 turns it off
-  const bool speculative = fused && c->halo.nranks == 1 && !(getenv("UCGB200_SPECULATE") && atoi(getenv("UCGB200_SPECULATE")) == 0);
+  // speculative launch of the next pair evaluation (fused tail); UCGB200_SPECULATE=0 turns it off.  Across bricks the
+  // decision rests on the all-reduced displacement bound, which is the same number on every brick, so all bricks
+  // speculate (or not) together.
+  const bool speculative = fused && !(getenv("UCGB200_SPECULATE") && atoi(getenv("UCGB200_SPECULATE")) == 0);
+  const bool bricks = c->halo.nranks > 1;
   c->last_maxdisp = -1.0;
   for (int n = 0; n < nsteps; n++) {
     c->ntimestep++;
@@ -216,7 +220,7 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
       t.stop();
     }
     int flag = 0;
-    bool pair_in_flight = false;
+    bool pair_in_flight = false, forward_done = false;
     const bool cluster_due = d.cluster_freq > 0 && c->cluster.set && c->cluster.next_reneighbor == c->ntimestep;
     if (speculative && pre_integrated && c->list_valid && !cluster_due && !c->timers_on) {
       // Neighbor::decide without a pipeline bubble: the flag (and the largest squared displacement since the build) of
@@ -225,6 +229,13 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
       // step, BEFORE the host waits for the flag: the device never idles while the host decides.  If the flag says
       // rebuild after all, the speculative results are simply overwritten by the rebuild + pair that follow.
       if (!c->ev_flag) UCG_CHECK(c, cudaEventCreateWithFlags(&c->ev_flag, cudaEventDisableTiming));
+      if (bricks) {
+        // the ghost refresh of this step carries every brick's flag and displacement bound with it (control words of
+        // the peer-mapped push, or two small all-reduces behind the NCCL send/recv group): after it d_flags[0] and
+        // d_maxdisp hold the MAX over all bricks.  A refresh that turns out to precede a rebuild is simply redone.
+        if ((rc = ucg_mb_forward_reduce(c, true))) return rc;
+        forward_done = true;
+      }
       UCG_CHECK(c, cudaMemcpyAsync(c->h_flags, c->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       UCG_CHECK(c, cudaMemcpyAsync(c->h_flags + 6, c->d_maxdisp.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
       if ((rc = queue_error_readback(c))) return rc;
@@ -232,7 +243,7 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
       c->maxdisp_valid = true;
       const double quiet = 0.8 * 0.5 * c->skin;
       if (c->last_maxdisp >= 0.0 && c->last_maxdisp < quiet * quiet) {
-        if ((rc = do_forward(c))) return rc;
+        if (!forward_done && (rc = do_forward(c))) return rc;
         if ((rc = pair_compute(c, ev))) return rc;
         pair_in_flight = true;
       }
@@ -262,7 +273,7 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
       t.stop();
     }
     if (flag) { if ((rc = do_build(c))) return rc; c->last_maxdisp = 0.0; }
-    else if (!pair_in_flight) {
+    else if (!pair_in_flight && !forward_done) {
       StageTimer t(c, 2);
       if ((rc = do_forward(c))) return rc;
       t.stop();

@@ -344,6 +344,27 @@ int exclusive_scan(ucgb200_ctx *c, const int *in, int *out, int n, int *d_total)
 int reduce_partials(ucgb200_ctx *c, int nblocks, int nvals, int out_offset);
 int ucg_check_distance_launch(ucgb200_ctx *c);
 }  // namespace ucg
+// Forward halo over peer-mapped memory (comm.cu drives it, the kernels live in neighbor.cu next to the record types).
+// Every brick owns one buffer that all its peers have mapped: a control block (one 16-byte word per (parity, source
+// rank): rebuild flag, largest squared displacement, sequence number) followed by two receive regions (parity = sequence
+// number & 1) of forward records grouped by source rank.
+#define UCG_P2P_MAX_RANKS 16
+struct UcgP2PCtl {                 // written by the source rank, read by the owner of the buffer
+  unsigned long long maxdisp;      // bits of a double >= 0
+  int flag;                        // Neighbor::decide flag of the source rank
+  int seq;                         // written LAST (after a system-scope fence): the records and the two words above are visible
+};
+struct UcgPushTargets {
+  int nranks, self, seq;
+  int send_off[UCG_P2P_MAX_RANKS + 1];   // send list of this brick, grouped by destination rank
+  char *rec[UCG_P2P_MAX_RANKS];          // where this brick's block starts inside the destination's receive region (this parity)
+  UcgP2PCtl *ctl[UCG_P2P_MAX_RANKS];     // this brick's control word in the destination's buffer (this parity)
+  const int *local_flag;                 // d_flags[0]
+  const unsigned long long *local_maxdisp;
+  unsigned *done;                        // block counter of the push kernel (zero between launches)
+};
+int ucg_halo_push_forward(ucgb200_ctx *c, const UcgPushTargets &t);   // neighbor.cu
+int ucg_halo_wait_reduce(ucgb200_ctx *c, const UcgP2PCtl *ctl_mine, int nranks, int self, int seq);   // neighbor.cu
 int ucg_dump_pack_device(ucgb200_ctx *c, const ucgb200_dump_spec *sp, long long *nrows);   // dump.cu
 int ucg_mb_forward_scalars(ucgb200_ctx *c, double *a0, double *a1, double *a2);   // comm.cu
 int ucg_mb_allreduce_int(ucgb200_ctx *c, int *d_buf, int n, int op);

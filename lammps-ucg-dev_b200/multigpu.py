@@ -265,6 +265,93 @@ def torch_alloc(device):
     return alloc
 
 
+# ------------------------------------------------------------------------------ parity of the resident multi-brick path
+def resident_parity(pkg, dist, rank, world, local, stream, tf, sf, per=12, nsteps=30):
+    """A small liquid run for `nsteps` steps (a) across all ranks through the resident driver (csrc/comm.cu: the code
+    bench.py --gpus N times) and (b) as ONE brick on rank 0; returns on rank 0 the comparison that goes into the bench
+    line as "parity": neighbor pairs of the final list as (tag, tag) multisets, states, forces, positions.
+    Deck: nve/ucgld/wall/hard + ucgld/langevin + ucgstate ld at T* = 2 (several rebuilds with migrations in 30 steps);
+    the thermostat draws are keyed by (seed, tag, step), hence independent of the decomposition."""
+    import torch
+
+    import bench as B
+    from lammps_ucg_dev_b200 import engine, synth
+
+    grid = procgrid_for(world)
+    ncell = (per * grid[0], per * grid[1], per * grid[2])
+    liq = synth.fcc_liquid_brick(ncell, grid, rank, T=2.0)
+    L = B.LANGEVIN
+    deck = dict(pair_style=0, nve=2, wall_bias=1, wall_barrier=0.1, langevin=1, t_start=2.0, t_stop=2.0,
+                t_period=L["t_period"], langevin_seed=L["seed"], ucgstate=2, thermo_every=0)
+
+    def setup(ctx):
+        engine.setup_single_type(ctx, tf, sf, tablength=B.TABLENGTH, cut=B.CUT, skin=B.SKIN, dt=B.DT, kT=2.0,
+                                 box=(liq.box_lo, liq.box_hi))
+
+    ctx = make_gpu_brick(pkg, local, stream=stream)
+    setup(ctx)
+    ctx.halo_configure(rank, world, grid)
+    engine.upload_liquid(ctx, liq)
+    ids = [pkg.Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    ctx.comm_init(ids[0])
+    ctx.deck_configure(**deck)
+    ctx.setup()
+    ctx.run(nsteps)
+    torch.cuda.synchronize()
+    got = ctx.atoms_download(["x", "f", "ucgl", "ucgstate", "ucgforce", "tag"])
+    nl = ctx.neigh_download()
+    n_glob = 4 * int(np.prod(ncell))
+    keys = np.repeat(nl["tag_i"], nl["numneigh"]).astype(np.int64) * (n_glob + 1) + nl["neigh_tags"]
+    stats = ctx.comm_stats()
+    parts = [None] * world
+    dist.all_gather_object(parts, dict(x=liq.x, v=liq.v, type=liq.type, mask=liq.mask, tag=liq.tag, molecule=liq.molecule,
+                                       ucgstate=liq.ucgstate, ucgl=liq.ucgl, ucgvl=liq.ucgvl, ucgml=liq.ucgml))
+    res = [None] * world
+    dist.gather_object(dict(got=got, keys=keys), res if rank == 0 else None, dst=0)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    ctx.comm_destroy()
+    ctx.close()
+    out = None
+    if rank == 0:
+        cat = {k: np.concatenate([p_[k] for p_ in parts]) for k in parts[0]}
+        t = pkg.Context(local, stream=stream)
+        setup(t)
+        t.atoms_upload(len(cat["tag"]), ucgp=np.full(len(cat["tag"]), -1.0), **cat)
+        t.deck_configure(**deck)
+        t.setup()
+        t.run(nsteps)
+        ref = t.atoms_download(["x", "f", "ucgl", "ucgstate", "ucgforce", "tag"])
+        rnl = t.neigh_download()
+        rkeys = np.sort(np.repeat(rnl["tag_i"], rnl["numneigh"]).astype(np.int64) * (n_glob + 1) + rnl["neigh_tags"])
+        rebuilds_one = int(t.thermo()[11])
+        t.close()
+        o = np.argsort(ref["tag"])
+        ref = {k: v[o] for k, v in ref.items()}
+        g = {k: np.concatenate([r_["got"][k] for r_ in res]) for k in res[0]["got"]}
+        o = np.argsort(g["tag"])
+        g = {k: v[o] for k, v in g.items()}
+        gkeys = np.sort(np.concatenate([r_["keys"] for r_ in res]))
+        box = liq.box_hi - liq.box_lo
+        dx = g["x"] - ref["x"]
+        dx -= box * np.round(dx / box)
+        away = np.abs(ref["ucgl"] - 0.5) > 1e-9
+        out = {"sites": int(len(ref["tag"])), "steps": nsteps, "bricks": world,
+               "deck": "table_ucgld + nve/ucgld/wall/hard bias + ucgld/langevin + ucgstate ld, T*=2",
+               "rebuilds": int(stats["rebuilds"]) - 1, "rebuilds_one_brick": rebuilds_one,      # not counting the build of setup
+               "owners_equal": bool(np.array_equal(g["tag"], ref["tag"])),
+               "pairs_equal": bool(gkeys.size == rkeys.size and np.array_equal(gkeys, rkeys)),
+               "states_equal": bool(np.array_equal(g["ucgstate"][away], ref["ucgstate"][away])),
+               "max_rel_f": float(np.abs(g["f"] - ref["f"]).max() / np.abs(ref["f"]).max()),
+               "max_rel_ucgforce": float(np.abs(g["ucgforce"] - ref["ucgforce"]).max() / np.abs(ref["ucgforce"]).max()),
+               "max_abs_x": float(np.abs(dx).max()), "max_abs_ucgl": float(np.abs(g["ucgl"] - ref["ucgl"]).max()),
+               "transport": stats.get("transport", "nccl")}
+        out["ok"] = bool(out["owners_equal"] and out["pairs_equal"] and out["states_equal"] and out["max_rel_f"] <= 1e-6 and
+                         out["max_abs_x"] <= 1e-9 and out["rebuilds"] == rebuilds_one and rebuilds_one >= 1)
+    return out
+
+
 # ------------------------------------------------------------------------------ bench leg
 def bench(args, rank, world, local, dist):
     """bench.py --gpus N (N > 1): weak scaling, one brick of NCELL_1GPU^3 fcc cells per GPU."""
@@ -287,6 +374,10 @@ def bench(args, rank, world, local, dist):
     torch.cuda.set_stream(stream)
     td = tempfile.mkdtemp()
     tf, sf = B.make_fixtures(td)
+    # proof for the code this leg times: the resident multi-brick path against one brick, before the timed region
+    parity = None
+    if os.environ.get("UCGB200_BENCH_PARITY", "1") != "0":
+        parity = resident_parity(pkg, dist, rank, world, local, stream.cuda_stream, tf, sf)
     # every rank generates only its own brick of the lattice (same global jitter seed per cell)
     liq = synth.fcc_liquid_brick(ncell, grid, rank)
     ctx = make_gpu_brick(pkg, local, stream=stream.cuda_stream)
@@ -407,6 +498,51 @@ def bench(args, rank, world, local, dist):
     dist.all_reduce(tb)
     h2d_step, d2h_step = int(tb[0].item()), int(tb[1].item())
 
+    halo_info = {"forward_bytes_per_step_rank0": int(cl.send_counts[rank].sum()) * cl.rec["forward"], "rebuilds": cl.nrebuilds,
+                 "transport": (ctx.comm_stats()["transport"] + ", issued by libucgb200 on the context stream (resident run)") if resident
+                 else "NCCL all_to_all_single driven from Python"}
+    # ---- BASELINE configs[4]'s own size next to the headline: 4 M sites per GPU (32 M on 8), same deck, same code
+    weak4m = None
+    per4 = int(os.environ.get("UCGB200_WEAK4M_NCELL", "100"))
+    if resident and per4 > 0 and per4 != per:
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        ctx.comm_destroy()
+        ctx.close()
+        del H
+        ncell4 = (per4 * grid[0], per4 * grid[1], per4 * grid[2])
+        liq4 = synth.fcc_liquid_brick(ncell4, grid, rank)
+        c4 = make_gpu_brick(pkg, local, stream=stream.cuda_stream)
+        engine.setup_single_type(c4, tf, sf, tablength=B.TABLENGTH, cut=B.CUT, skin=B.SKIN, dt=B.DT, kT=1.0,
+                                 box=(liq4.box_lo, liq4.box_hi))
+        c4.halo_configure(rank, world, grid)
+        engine.upload_liquid(c4, liq4)
+        ids = [pkg.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        c4.comm_init(ids[0])
+        c4.deck_configure(pair_style=0, nve=1, langevin=1, t_start=L["t_start"], t_stop=L["t_stop"], t_period=L["t_period"],
+                          langevin_seed=L["seed"], ucgstate=2, thermo_every=0)
+        c4.setup()
+        c4.run(max(3, min(args.warmup, 5)))
+        k4 = max(5, min(args.steps, 20))
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        c4.run(k4)
+        e1.record(stream)
+        torch.cuda.synchronize(); dist.barrier()
+        t4 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+        n4 = torch.tensor([c4.natoms()[0]], dtype=torch.int64, device=device)
+        dist.all_reduce(n4)
+        st4 = c4.comm_stats()
+        weak4m = {"sites": int(n4.item()), "sites_per_gpu": int(n4.item()) // world, "steps": k4, "ms_per_step": float(t4.item()) / k4,
+                  "value": int(n4.item()) * k4 / (float(t4.item()) * 1e-3) / 1e6, "unit": B.UNIT, "rebuilds": st4["rebuilds"],
+                  "transport": st4["transport"]}
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        c4.comm_destroy()
+        c4.close()
+
     if rank == 0:
         cfg = B.workload_config(ncell, world)
         cfg["sites_per_gpu"] = nsites // world
@@ -422,9 +558,7 @@ def bench(args, rank, world, local, dist):
                         "d2h_bytes_per_step": d2h_step, "steps": done,
                         "api": "per rank: ucgb200_atoms_upload + ucgb200_run(1) + ucgb200_atoms_download, pinned host arrays"},
                 "gpu_launches": int(launches), "clocks": sampler.summary(),
-                "halo": {"forward_bytes_per_step_rank0": int(cl.send_counts[rank].sum()) * cl.rec["forward"],
-                         "rebuilds": cl.nrebuilds, "transport": "NCCL send/recv groups issued by libucgb200 on the context stream (resident run)" if resident
-                         else "NCCL all_to_all_single driven from Python"}}
+                "halo": halo_info, "parity": parity, "weak_4M_per_gpu": weak4m}
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()
