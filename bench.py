@@ -134,16 +134,17 @@ def _replica(job):
 
 
 def run_reference(args):
-    """The reference's own CPU code (oracle/_ref) on the host cores.  The UCG package is serial per
-    MPI rank and this box has no MPI, so "all the host threads it can use" is realised as one
-    independent replica of the bounded sample per core, all running at once; the aggregate is an
-    UPPER bound for an MPI run of the same size (no halo exchange, no load imbalance)."""
+    """The reference's own CPU code (oracle/_ref) on the host cores, on THIS arm's workload: the 1 000 188-site liquid
+    of configs[1].  The UCG package is serial per MPI rank and this box has no MPI, so "all the host threads it can
+    use" is realised as one independent serial run of the whole liquid per core, all at once; the aggregate is an
+    UPPER bound for an MPI run of one liquid over the same cores (no halo exchange, no load imbalance).  A bounded
+    sample: `steps` capped so that the run ends within a few minutes (~1.2 s per step per core)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample of the 1M-site workload: the same liquid at 32 000 sites (configs[0]'s size)
-    ncell = 20
-    steps = min(max(args.steps, 1) * 2, 300)   # bounded sample: <= ~10 s per core
+    ncell = int(os.environ.get("UCGB200_NCELL_PER_GPU", NCELL_1GPU))
+    steps = max(1, min(args.steps, 40))
+    warm = min(args.warmup, 2)
     try:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
@@ -153,25 +154,32 @@ def run_reference(args):
         cores = 1
     import multiprocessing as mp
     t0 = time.perf_counter()
+    # the truly serial figure first (one core, nothing else running): cpu_baseline.serial_1M
+    serial = _replica((ncell, max(5, min(steps, 8)), 1))
     if cores == 1:
-        rs = [_replica((ncell, steps, min(args.warmup, 2)))]
+        rs = [serial]
     else:
         with mp.get_context("spawn").Pool(cores) as pool:
-            rs = pool.map(_replica, [(ncell, steps, min(args.warmup, 2))] * cores)
+            rs = pool.map(_replica, [(ncell, steps, warm)] * cores)
     wall = time.perf_counter() - t0
     value = sum(r["value"] for r in rs)
     slowest = max(r["seconds"] for r in rs)
     r0 = rs[0]
-    cfg = workload_config(NCELL_1GPU, 1)
+    cfg = workload_config(ncell, 1)
+    cfg["reference_arm"] = (f"{cores} concurrent serial runs of the whole {r0['sites']}-site liquid (one per host core), "
+                            f"{r0['steps']} timed steps each after setup and {warm} warm-up steps")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * slowest / r0["steps"],
+            "steps": r0["steps"], "steps_requested": args.steps, "warmup": warm, "ms_per_step": 1e3 * slowest / r0["steps"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": r0["kind"],
-                             "sample": f"{cores} concurrent serial replicas of {r0['sites']} sites x {r0['steps']} steps of the same deck "
+                             "sample": f"{cores} concurrent serial runs of the same {r0['sites']}-site liquid x {r0['steps']} steps "
                                        "(one per core; no MPI on this box, so this is an upper bound for an MPI run)",
                              "per_core": [r["value"] for r in rs][:8], "wall_s": wall,
-                             "breakdown_s": r0["breakdown"]},
+                             "breakdown_s": r0["breakdown"],
+                             "serial_1M": {"value": serial["value"], "unit": UNIT, "cores": 1, "sites": serial["sites"],
+                                           "steps": serial["steps"], "seconds": serial["seconds"],
+                                           "breakdown_s": serial["breakdown"]}},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -253,7 +261,9 @@ def run_gpu(args):
                 "traffic": None, "kernel": "k_pair_ucgld_fast", "kernel_ms": pair_avg,
                 "bytes_per_site": bytes_per_site, "half_neighbors_per_site": m_half,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
-                "stage_ms_per_step": {k: v / len(pair_ms) for k, v in tms.items()}}
+                "stage_ms_per_step": {k: v / len(pair_ms) for k, v in tms.items()},
+                "stage_ms_note": "from a separate instrumented loop (one event synchronisation per stage, one step per call, "
+                                 "no speculative launch): the stages do not add up to ms_per_step of the timed loop"}
     prof = os.path.join(ROOT, "profiles", "pair_traffic.json")
     if os.path.exists(prof):
         try:
@@ -279,10 +289,16 @@ def run_gpu(args):
     d2h = sum(v.nbytes for v in H.values())
     e2e_steps = max(3, min(args.steps, 20))
 
+    pipelined = os.environ.get("UCGB200_E2E_PIPELINE", "1") != "0"
+    inp = {k: H[k] for k in up}
+
     def e2e_step():
-        ctx.atoms_upload(n, **{k: H[k] for k in up})
-        ctx.run(1)
-        ctx.atoms_download_into(**H)
+        if pipelined:
+            ctx.step_host(inp, H)          # ucgb200_step_host: D2H of x under the pair kernel, of f under the fix stages
+        else:
+            ctx.atoms_upload(n, **inp)
+            ctx.run(1)
+            ctx.atoms_download_into(**H)
 
     for _ in range(2):
         e2e_step()
@@ -294,7 +310,8 @@ def run_gpu(args):
     e2e_s = time.perf_counter() - t0
     e2e = {"value": n * e2e_steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-           "api": "ucgb200_atoms_upload + ucgb200_run(1) + ucgb200_atoms_download, pinned host arrays"}
+           "api": ("ucgb200_step_host (upload, one step, download; device->host copies overlap the kernels), pinned host arrays"
+                   if pipelined else "ucgb200_atoms_upload + ucgb200_run(1) + ucgb200_atoms_download, pinned host arrays")}
 
     # ---- the taps either side of the path, after the timed regions: one `dump custom` snapshot of the
     # resident state written to a file (rows selected, sorted, packed and formatted on the device) and read back
@@ -328,10 +345,11 @@ def run_gpu(args):
     # ---- CPU baseline beside it (bounded sample, rank 0 only)
     cpu = None
     if not args.no_cpu:
-        r = cpu_reference(20, 150, 2, td)
+        r = cpu_reference(ncell1, 8, 1, td)
         cpu = {"value": r["value"], "unit": UNIT, "cores": 1, "kind": r["kind"],
-               "sample": f"{r['sites']} sites x {r['steps']} steps of the same deck, serial (no MPI on this box)",
-               "breakdown_s": r["breakdown"]}
+               "sample": f"the same {r['sites']}-site liquid and deck, {r['steps']} steps after setup and 1 warm-up step, serial "
+                         "(one core; the UCG package is single-threaded per MPI rank and this box has no MPI)",
+               "seconds": r["seconds"], "breakdown_s": r["breakdown"]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -142,6 +142,13 @@ int ucgb200_atoms_upload(ucgb200_ctx *ctx, int nlocal, const ucgb200_atoms *host
  * re-sorts atoms by cell at every neighbor rebuild; tags travel with them). */
 int ucgb200_atoms_download(ucgb200_ctx *ctx, int nlocal_capacity, ucgb200_atoms *host, unsigned fields);
 int ucgb200_natoms(const ucgb200_ctx *ctx, int *nlocal, int *nghost);
+/* ONE timestep of the configured deck (ucgb200_deck_configure + ucgb200_setup) driven from HOST arrays: `in` (fields
+ * in_fields, nlocal sites in host order) goes to the device, the step runs, `out` (fields out_fields) comes back —
+ * what ucgb200_atoms_upload + ucgb200_run(ctx, 1) + ucgb200_atoms_download do, but with the device->host copies on a
+ * second stream so that they overlap the kernels: x (and ucgl / ucgstate when no later stage of the deck writes them)
+ * leave while the pair kernel runs, f while the fix stages run, the rest after them.  Page-lock the host arrays
+ * (ucgb200_host_register / cudaHostRegister) or the copies serialise.  Returns when `out` is complete. */
+int ucgb200_step_host(ucgb200_ctx *ctx, const ucgb200_atoms *in, unsigned in_fields, ucgb200_atoms *out, unsigned out_fields);
 /* AtomVecUCG::force_clear (atom_vec_ucg.cpp:131-135) + stock f memset.  The pair
  * kernels overwrite f/ucgforce/scores, so this is only needed when no pair style runs. */
 int ucgb200_force_clear(ucgb200_ctx *ctx);

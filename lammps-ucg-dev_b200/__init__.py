@@ -262,6 +262,25 @@ class Context:
         st = self._atoms_struct(arrays)
         self._ck(self._l.ucgb200_atoms_download(self._h, int(n), C.byref(st), C.c_uint(mask)))
 
+    _BITS = dict(x=F_X, v=F_V, f=F_F, type=F_TYPE, mask=F_MASK, tag=F_TAG, molecule=F_MOLECULE, ucgstate=F_UCGSTATE,
+                 ucgl=F_UCGL, ucgvl=F_UCGVL, ucgml=F_UCGML, ucgp=F_UCGP, ucgforce=F_UCGFORCE, ucgsoftmaxscores=F_SCORES)
+
+    def step_host(self, inputs: dict, outputs: dict):
+        """ucgb200_step_host: one timestep with host arrays in (`inputs`) and out (`outputs`, caller-owned C-contiguous
+        arrays, ideally pinned); the device->host copies overlap the kernels of the step."""
+        n = self.natoms()[0]
+        im = om = 0
+        for k, v in inputs.items():
+            isint = k in ("type", "mask", "tag", "molecule", "ucgstate")
+            assert v.flags.c_contiguous and v.dtype == (np.int32 if isint else np.float64) and v.shape[0] >= n, k
+            im |= self._BITS[k]
+        for k, v in outputs.items():
+            isint = k in ("ucgstate",)
+            assert v.flags.c_contiguous and v.dtype == (np.int32 if isint else np.float64) and v.shape[0] >= n, k
+            om |= self._BITS[k]
+        si, so = self._atoms_struct(inputs), self._atoms_struct(outputs)
+        self._ck(self._l.ucgb200_step_host(self._h, C.byref(si), C.c_uint(im), C.byref(so), C.c_uint(om)))
+
     def natoms(self):
         a, b = C.c_int(), C.c_int()
         self._ck(self._l.ucgb200_natoms(self._h, C.byref(a), C.byref(b)))

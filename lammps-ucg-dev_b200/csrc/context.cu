@@ -42,6 +42,8 @@ extern "C" int ucgb200_destroy(ucgb200_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   ucgb200_comm_destroy(c);
+  if (c->stream_dl) cudaStreamDestroy(c->stream_dl);
+  if (c->ev_dl) cudaEventDestroy(c->ev_dl);
   for (auto *t : {&c->tex_pos[0], &c->tex_pos[1], &c->tex_sbits, &c->tex_ts[0], &c->tex_ts[1]}) if (t->tex) cudaDestroyTextureObject(t->tex);
   for (void *p : c->table_allocs) cudaFree(p);
   // Buf<> members are released explicitly (no destructors: buffers may be swapped)
@@ -604,6 +606,68 @@ extern "C" int ucgb200_atoms_download(ucgb200_ctx *c, int cap, ucgb200_atoms *h,
 #undef DN_D
 #undef DN_I
   return 0;
+}
+
+// ucgb200_step_host: the fields of `mask` that the caller asked for and that have not left yet are gathered into
+// host order on the context stream (fixed staging slot per field) and copied out on the download stream behind an event,
+// so the kernels that follow on the context stream run while the copy engine works.
+int ucg_host_out_queue(ucgb200_ctx *c, unsigned mask) {
+  ucgb200_atoms *h = c->host_out;
+  if (!h) return 0;
+  const unsigned fields = c->host_out_fields & mask & ~c->host_out_done;
+  if (!fields || c->nlocal == 0) return 0;
+  cudaSetDevice(c->device);
+  const int nlocal = c->nlocal;
+  const size_t n = nlocal;
+  if (!c->stream_dl) UCG_CHECK(c, cudaStreamCreateWithFlags(&c->stream_dl, cudaStreamNonBlocking));
+  if (!c->ev_dl) UCG_CHECK(c, cudaEventCreateWithFlags(&c->ev_dl, cudaEventDisableTiming));
+  if (c->stage_d.cap < 16 * n + 64 || c->stage_i.cap < 6 * n + 64) return fail(c, "step_host: staging not sized (upload first)");
+  double *sd = c->stage_d.p;
+  int *si = c->stage_i.p;
+  const int *orig = c->orig.p;
+  struct Copy { void *dst; const void *src; size_t bytes; };
+  std::vector<Copy> copies;
+  // slots: x 0, ucgl 3n, v 4n, ucgvl 7n, f 8n, ucgforce 11n, ucgp 12n, scores 13n (doubles); ucgstate 0 (ints)
+  if ((fields & UCGB200_F_X) && h->x) { k_unpack_vec3<<<GRID1(nlocal)>>>(sd, c->pos.p, orig, nlocal); UCG_LAUNCHED(c); copies.push_back({h->x, sd, 3 * n * sizeof(double)}); }
+  if ((fields & UCGB200_F_UCGL) && h->ucgl) { k_unpack_w<<<GRID1(nlocal)>>>(sd + 3 * n, c->pos.p, orig, nlocal); UCG_LAUNCHED(c); copies.push_back({h->ucgl, sd + 3 * n, n * sizeof(double)}); }
+  if ((fields & UCGB200_F_V) && h->v) { k_unpack_vec3<<<GRID1(nlocal)>>>(sd + 4 * n, c->vel.p, orig, nlocal); UCG_LAUNCHED(c); copies.push_back({h->v, sd + 4 * n, 3 * n * sizeof(double)}); }
+  if ((fields & UCGB200_F_UCGVL) && h->ucgvl) { k_unpack_w<<<GRID1(nlocal)>>>(sd + 7 * n, c->vel.p, orig, nlocal); UCG_LAUNCHED(c); copies.push_back({h->ucgvl, sd + 7 * n, n * sizeof(double)}); }
+  if ((fields & UCGB200_F_F) && h->f) { k_unpack_vec3<<<GRID1(nlocal)>>>(sd + 8 * n, c->frc.p, orig, nlocal); UCG_LAUNCHED(c); copies.push_back({h->f, sd + 8 * n, 3 * n * sizeof(double)}); }
+  if ((fields & UCGB200_F_UCGFORCE) && h->ucgforce) { k_unpack_w<<<GRID1(nlocal)>>>(sd + 11 * n, c->frc.p, orig, nlocal); UCG_LAUNCHED(c); copies.push_back({h->ucgforce, sd + 11 * n, n * sizeof(double)}); }
+  if ((fields & UCGB200_F_UCGP) && h->ucgp) { k_unpack_scalar_d<<<GRID1(nlocal)>>>(sd + 12 * n, c->ucgp.p, orig, nlocal); UCG_LAUNCHED(c); copies.push_back({h->ucgp, sd + 12 * n, n * sizeof(double)}); }
+  if ((fields & UCGB200_F_SCORES) && h->ucgsoftmaxscores) { k_unpack_d2<<<GRID1(nlocal)>>>(sd + 13 * n, c->scores.p, orig, nlocal); UCG_LAUNCHED(c); copies.push_back({h->ucgsoftmaxscores, sd + 13 * n, 2 * n * sizeof(double)}); }
+  if ((fields & UCGB200_F_UCGSTATE) && h->ucgstate) { k_unpack_ts<<<GRID1(nlocal)>>>(si, c->ts.p, orig, nlocal, 1, nullptr); UCG_LAUNCHED(c); copies.push_back({h->ucgstate, si, n * sizeof(int)}); }
+  UCG_CHECK(c, cudaEventRecord(c->ev_dl, c->stream));
+  UCG_CHECK(c, cudaStreamWaitEvent(c->stream_dl, c->ev_dl, 0));
+  for (const Copy &cp : copies) UCG_CHECK(c, cudaMemcpyAsync(cp.dst, cp.src, cp.bytes, cudaMemcpyDeviceToHost, c->stream_dl));
+  c->host_out_done |= fields;
+  return 0;
+}
+
+extern "C" int ucgb200_step_host(ucgb200_ctx *c, const ucgb200_atoms *in, unsigned in_fields, ucgb200_atoms *out, unsigned out_fields) {
+  if (!c || !in || !out) return -1;
+  if (!c->deck_set) return fail(c, "step_host: deck not configured");
+  if (!c->list_valid && c->nlocal == 0) return fail(c, "step_host: no atoms (upload them and call ucgb200_setup first)");
+  const unsigned supported = UCGB200_F_X | UCGB200_F_V | UCGB200_F_F | UCGB200_F_UCGSTATE | UCGB200_F_UCGL | UCGB200_F_UCGVL |
+                             UCGB200_F_UCGP | UCGB200_F_UCGFORCE | UCGB200_F_SCORES;
+  if (out_fields & ~supported) return fail(c, "step_host: out_fields holds a field that a step does not produce");
+  cudaSetDevice(c->device);
+  int rc = ucgb200_atoms_upload(c, c->nlocal, in, in_fields);
+  if (rc) return rc;
+  // the staging slots of the results lie behind those of the inputs' pack kernels in stream order
+  c->host_out = out;
+  c->host_out_fields = out_fields;
+  c->host_out_done = 0;
+  rc = ucgb200_run(c, 1);
+  if (!rc) rc = ucg_host_out_queue(c, ~0u);     // everything that could not leave earlier
+  c->host_out = nullptr;
+  if (c->stream_dl) {
+    cudaError_t e = cudaStreamSynchronize(c->stream_dl);
+    if (!rc && e != cudaSuccess) { c->err = std::string("step_host download: ") + cudaGetErrorString(e); rc = -2; }
+  }
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (!rc && e != cudaSuccess) { c->err = std::string("step_host: ") + cudaGetErrorString(e); rc = -2; }
+  return rc;
 }
 
 extern "C" int ucgb200_natoms(const ucgb200_ctx *c, int *nlocal, int *nghost) {

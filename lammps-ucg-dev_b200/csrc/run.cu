@@ -278,11 +278,19 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
       if ((rc = do_forward(c))) return rc;
       t.stop();
     }
+    if (c->host_out && !pair_in_flight) {
+      // ucgb200_step_host: positions are final for this step once the list is valid; lambda and the state too unless a
+      // later stage writes them (the wall's reflection, a non-ld fix ucgstate): their copy runs under the pair kernel
+      unsigned early = UCGB200_F_X;
+      if (d.nve != 2 && (d.ucgstate == 0 || d.ucgstate == 2)) early |= UCGB200_F_UCGL | UCGB200_F_UCGSTATE;
+      if ((rc = ucg_host_out_queue(c, early))) return rc;
+    }
     if (!pair_in_flight) {
       StageTimer t(c, 0);
       if ((rc = pair_compute(c, ev))) return rc;
       t.stop();
     }
+    if (c->host_out && (rc = ucg_host_out_queue(c, UCGB200_F_F))) return rc;   // f is final after the pair kernel
     {
       StageTimer t(c, 3);
       if (fused) {

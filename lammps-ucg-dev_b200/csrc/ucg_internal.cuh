@@ -251,6 +251,11 @@ struct ucgb200_ctx {
   } bdens;
   // texture objects for the gathers of the table_ucgld kernel (the TEX pipe works beside the LSU pipe)
   struct TexSlot { const void *ptr = nullptr; size_t bytes = 0; cudaTextureObject_t tex = 0; } tex_pos[2], tex_sbits, tex_ts[2];
+  // ucgb200_step_host: results leave on a second stream while the step is still running
+  ucgb200_atoms *host_out = nullptr;
+  unsigned host_out_fields = 0, host_out_done = 0;
+  cudaStream_t stream_dl = nullptr;
+  cudaEvent_t ev_dl = nullptr;
   void *comm_state = nullptr;  // comm.cu: NCCL communicator + exchange buffers of a multi-brick run
   bool ev_two_parts = false;   // d_ev[16..22] holds a second virial part to be added (rleucg)
 };
@@ -365,6 +370,7 @@ struct UcgPushTargets {
 };
 int ucg_halo_push_forward(ucgb200_ctx *c, const UcgPushTargets &t);   // neighbor.cu
 int ucg_halo_wait_reduce(ucgb200_ctx *c, const UcgP2PCtl *ctl_mine, int nranks, int self, int seq);   // neighbor.cu
+int ucg_host_out_queue(ucgb200_ctx *c, unsigned mask);   // context.cu: gather + D2H of the not yet delivered fields in mask
 int ucg_dump_pack_device(ucgb200_ctx *c, const ucgb200_dump_spec *sp, long long *nrows);   // dump.cu
 int ucg_mb_forward_scalars(ucgb200_ctx *c, double *a0, double *a1, double *a2);   // comm.cu
 int ucg_mb_allreduce_int(ucgb200_ctx *c, int *d_buf, int n, int op);

@@ -670,3 +670,35 @@ def test_neighbor_f32_prefilter_is_exact_at_the_thresholds(pkg, fixtures, monkey
     fi, fj = of.neigh_pairs()
     nl = rows["1"]
     assert np.array_equal(_pair_sets(nl, n), np.sort(fi.astype(np.int64) * (n + 1) + fj))
+
+
+@pytest.mark.parametrize("deck", [dict(nve=1, langevin=1, t_start=1.0, t_stop=1.0, t_period=1.0, langevin_seed=5, ucgstate=2),
+                                  dict(nve=2, wall_bias=1, wall_barrier=0.1, ucgstate=1),
+                                  dict(nve=1, ucgstate=1)])
+def test_step_host_equals_upload_run_download(pkg, fixtures, deck):
+    """ucgb200_step_host (results leave on a second stream while the step still runs: x under the pair kernel, f under
+    the fix stages) must deliver bit for bit what upload + run(1) + download deliver, over steps that include rebuilds,
+    for decks whose later stages do and do not rewrite lambda / the state"""
+    liq = _liq(9, T=2.0)
+    n = liq.n
+    ins = ("x", "v", "ucgl", "ucgvl", "ucgstate")
+    outs = ("x", "v", "f", "ucgl", "ucgvl", "ucgstate", "ucgp", "ucgforce", "ucgsoftmaxscores")
+    res = []
+    for pipelined in (True, False):
+        ctx = decks.gpu_single_type(pkg, liq, fixtures)
+        ctx.deck_configure(pair_style=0, thermo_every=0, **deck)
+        ctx.setup()
+        H = ctx.atoms_download(list(outs))
+        for step in range(25):
+            inp = {k: H[k] for k in ins}
+            if pipelined:
+                ctx.step_host(inp, H)
+            else:
+                ctx.atoms_upload(n, **inp)
+                ctx.run(1)
+                ctx.atoms_download_into(**H)
+        res.append(({k: v.copy() for k, v in H.items()}, ctx.thermo()[11]))
+    (a, ra), (b, rb) = res
+    assert ra == rb and ra >= 1
+    for k in outs:
+        assert np.array_equal(a[k], b[k]), k
