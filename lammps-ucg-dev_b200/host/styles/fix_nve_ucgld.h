@@ -34,6 +34,13 @@ class FixNVE_UCGLD : public Fix, public UCGDeckPart {
   void final_integrate_respa(int, int) override;
   void initial_integrate_respa(int, int, int) override;
   bool ucg_deck(ucgb200_deck &deck) override;
+  bool ucg_tracked_ok() const override { return true; }
+  // tracked offload mode (ucg_device.h): the integrator fix opens the window in which per-atom arrays stay on the
+  // device, and hands them back where stock LAMMPS reads or reorders them
+  void setup(int) override;
+  void pre_exchange() override;
+  void end_of_step() override;
+  void post_run() override;
 };
 
 }  // namespace LAMMPS_NS

@@ -47,6 +47,7 @@ class Fix_UCGLD_Langevin : public Fix, public UCGDeckPart {
   void *extract(const char *, int &) override;
   void post_force_respa(int, int, int) override;
   bool ucg_deck(ucgb200_deck &deck) override;
+  bool ucg_tracked_ok() const override { return true; }
 };
 
 }  // namespace LAMMPS_NS

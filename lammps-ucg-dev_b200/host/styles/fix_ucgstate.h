@@ -32,6 +32,7 @@ class FixUCGState : public Fix, public UCGDeckPart {
   void min_post_force(int) override;
   void post_force_respa(int, int, int) override;
   bool ucg_deck(ucgb200_deck &deck) override;
+  bool ucg_tracked_ok() const override { return true; }
 };
 
 }  // namespace LAMMPS_NS

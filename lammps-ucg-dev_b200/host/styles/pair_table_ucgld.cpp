@@ -185,6 +185,25 @@ void PairTable_UCGLD::compute(int eflag, int vflag) {
   dev->ensure_list(lmp);
   const int ev = (eflag_either || vflag_either) ? 1 : 0;
   device_compute(ev, ev);
+  if (dev->tracked) {
+    // tracked offload mode: nobody on the host reads f / ucgforce / scores before the next flush, and after stock
+    // Verlet's force_clear "added to zero" is "assigned": the results stay on the device
+    dev->download(lmp, UCGB200_F_F | UCGB200_F_UCGFORCE | UCGB200_F_SCORES | UCGB200_F_NUMSTATES);
+    int code;
+    if ((code = ucgb200_status_peek(dev->ctx, nullptr, nullptr, nullptr, nullptr))) dev->check(lmp, code, "pair_ucgld");
+    if (ev) {
+      double e, v[6];
+      dev->check(lmp, ucgb200_pair_energy_virial(dev->ctx, &e, v), "pair_energy_virial");
+      if (eflag_global) eng_vdwl += e;
+      for (int k = 0; k < 6; k++) {
+#ifdef LAMMPS_UCG_SHIM
+        virial_tally[k] = v[k];
+#endif
+        if (vflag_global) virial[k] += v[k];
+      }
+    }
+    return;
+  }
   // results are ADDED to the host arrays, like the reference's f[i] += ... after force_clear
   const size_t nl = (size_t)nlocal;
   char *buf = (char *)dev->scratch((6 * nl + 8) * sizeof(double) + (nl + 8) * sizeof(int));

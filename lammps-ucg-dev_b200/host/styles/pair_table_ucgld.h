@@ -34,6 +34,7 @@ class PairTable_UCGLD : public Pair, public UCGDeckPart {
   double single(int, int, int, int, double, double, double, double &) override;
   void *extract(const char *, int &) override;
   bool ucg_deck(ucgb200_deck &deck) override;   // this style's part of the resident deck (run_style ucg/b200)
+  bool ucg_tracked_ok() const override { return true; }
   enum { LOOKUP, LINEAR, SPLINE, BITMAP };
 
  protected:

@@ -1,9 +1,15 @@
 // ucg_device.h — glue between the LAMMPS-facing style classes and the C-ABI (ucgb200_*).
-// One device context per LAMMPS instance.  In this "offload" mode every style call uploads
-// the AtomVecUCG arrays it reads and downloads the ones it writes, so an unmodified stock
-// Verlet loop (which touches atom->x / atom->f directly) stays correct; the device keeps its
-// own cell-sorted copy, ghosts and FULL neighbor list between calls.  The resident mode
-// (ucgb200_deck_configure + ucgb200_run) avoids these transfers altogether.
+// One device context per LAMMPS instance.  In this "offload" mode an unmodified stock Verlet loop drives the styles;
+// the device keeps its own cell-sorted copy of the AtomVecUCG arrays, ghosts and FULL neighbor list between calls.
+// Which arrays cross PCIe is decided per field:
+//  * eager (any deck): every style call uploads the arrays it reads and downloads the ones it writes — always right,
+//    ~25 transfers per step;
+//  * tracked (decks whose every force and fix style is a UCG style, inside `run`): a field is uploaded only when the
+//    host copy is newer than the device's, and a field the device has written stays there until something on the host
+//    needs it — positions after initial_integrate (stock Verlet's Neighbor::decide and Comm::forward_comm read them
+//    every step), everything before an exchange (Fix::pre_exchange), on output steps (Fix::end_of_step) and when the
+//    run ends (Fix::post_run).  An all-UCG deck then moves x out once per step and nothing in.
+// The resident mode (run_style ucg/b200: ucgb200_deck_configure + ucgb200_run) avoids even that.
 #ifndef LMP_UCG_DEVICE_H
 #define LMP_UCG_DEVICE_H
 
@@ -31,6 +37,9 @@ class UCGDeckPart {
   // false: this style (or this set of its options) cannot run inside the device loop
   virtual bool ucg_deck(ucgb200_deck &deck) = 0;
   // the next step after which the device loop must hand control back to this style, and what it does then
+  // true: inside a stock Verlet run this style reads and writes the per-atom arrays through UCGDevice::upload /
+  // download only, so the tracked offload mode may leave them on the device between its calls
+  virtual bool ucg_tracked_ok() const { return false; }
   virtual long long ucg_next_stop() const { return -1; }
   virtual void ucg_after_step(long long) {}
 };
@@ -153,22 +162,70 @@ class UCGDevice {
     return scratch_p;
   }
 
-  void upload(LAMMPS *lmp, unsigned fields) {
-    Atom *a = lmp->atom;
-    pin_arrays(lmp);
-    if (a->nlocal != nlocal_dev) { static_uploaded = false; list_ready = false; }
-    if (!static_uploaded) fields |= UCGB200_F_TYPE | UCGB200_F_MASK | UCGB200_F_TAG | UCGB200_F_MOLECULE | UCGB200_F_UCGML |
-                                    UCGB200_F_X | UCGB200_F_V | UCGB200_F_UCGL | UCGB200_F_UCGVL | UCGB200_F_UCGSTATE | UCGB200_F_UCGP;
-    ucgb200_atoms h = view(a);
-    check(lmp, ucgb200_atoms_upload(ctx, a->nlocal, &h, fields), "atoms_upload");
-    nlocal_dev = a->nlocal;
-    static_uploaded = true;
+  // ---- tracked mode (see the header of this file)
+  bool tracked = false;
+  unsigned dev_valid = 0;    // fields whose device copy is what the host holds or newer: no upload needed
+  unsigned dev_newer = 0;    // fields the device has written and the host has not seen yet
+  long long bytes_up = 0, bytes_down = 0;   // per-site payload moved so far (diagnostics: ucg_traffic())
+  static constexpr unsigned EAGER_OUT = UCGB200_F_X;   // what stock Verlet reads on the host every step
+  static unsigned bytes_per_site(unsigned fields) {
+    unsigned b = 0;
+    if (fields & UCGB200_F_X) b += 24; if (fields & UCGB200_F_V) b += 24; if (fields & UCGB200_F_F) b += 24;
+    if (fields & UCGB200_F_SCORES) b += 16;
+    for (unsigned f : {UCGB200_F_UCGL, UCGB200_F_UCGVL, UCGB200_F_UCGML, UCGB200_F_UCGP, UCGB200_F_UCGFORCE}) if (fields & f) b += 8;
+    for (unsigned f : {UCGB200_F_TYPE, UCGB200_F_MASK, UCGB200_F_TAG, UCGB200_F_MOLECULE, UCGB200_F_UCGSTATE, UCGB200_F_NUMSTATES}) if (fields & f) b += 4;
+    return b;
   }
-  void download(LAMMPS *lmp, unsigned fields) {
+  // every force and fix style of the deck is a UCG style, one process, velocity Verlet: nothing else reads or writes
+  // the per-atom arrays between two of our calls except stock Verlet itself (force_clear, decide, forward_comm)
+  bool tracking_allowed(LAMMPS *lmp);
+  void tracking_begin(LAMMPS *lmp) {
+    tracked = tracking_allowed(lmp);
+    dev_valid = dev_newer = 0;       // the host is the truth at the start of a run
+  }
+  void flush(LAMMPS *lmp) {          // the host is about to read (or reorder) the arrays
+    if (!tracked || !dev_newer) return;
+    const unsigned f = dev_newer;
+    dev_newer = 0;
+    raw_download(lmp, f);
+  }
+  void host_changed() { dev_valid = 0; static_uploaded = false; list_ready = false; }   // after a flush: host reordered / rewrote
+  void tracking_end(LAMMPS *lmp) { flush(lmp); tracked = false; dev_valid = dev_newer = 0; }
+
+  void raw_download(LAMMPS *lmp, unsigned fields) {
     Atom *a = lmp->atom;
     pin_arrays(lmp);
     ucgb200_atoms h = view(a);
     check(lmp, ucgb200_atoms_download(ctx, a->nlocal, &h, fields), "atoms_download");
+    bytes_down += (long long) bytes_per_site(fields) * a->nlocal;
+  }
+  // a style is about to READ `fields` on the device
+  void upload(LAMMPS *lmp, unsigned fields) {
+    Atom *a = lmp->atom;
+    pin_arrays(lmp);
+    if (a->nlocal != nlocal_dev) { static_uploaded = false; list_ready = false; dev_valid = 0; dev_newer = 0; }
+    if (tracked) fields &= ~dev_valid;
+    if (!static_uploaded) fields |= (UCGB200_F_TYPE | UCGB200_F_MASK | UCGB200_F_TAG | UCGB200_F_MOLECULE | UCGB200_F_UCGML |
+                                     UCGB200_F_X | UCGB200_F_V | UCGB200_F_UCGL | UCGB200_F_UCGVL | UCGB200_F_UCGSTATE | UCGB200_F_UCGP) &
+                                    ~(tracked ? dev_newer : 0u);
+    if (fields) {
+      ucgb200_atoms h = view(a);
+      check(lmp, ucgb200_atoms_upload(ctx, a->nlocal, &h, fields), "atoms_upload");
+      bytes_up += (long long) bytes_per_site(fields) * a->nlocal;
+    }
+    nlocal_dev = a->nlocal;
+    static_uploaded = true;
+    if (tracked) dev_valid |= fields;
+  }
+  // a style has WRITTEN `fields` on the device
+  void download(LAMMPS *lmp, unsigned fields) {
+    if (tracked) {
+      dev_valid |= fields;
+      dev_newer |= fields & ~EAGER_OUT;
+      fields &= EAGER_OUT;
+      if (!fields) return;
+    }
+    raw_download(lmp, fields);
   }
   // the device list follows the same skin rule as Neighbor::decide
   void ensure_list(LAMMPS *lmp) {

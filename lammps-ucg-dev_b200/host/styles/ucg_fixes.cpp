@@ -15,6 +15,7 @@
 #include "group.h"
 #include "memory.h"
 #include "modify.h"
+#include "output.h"
 #include "respa.h"
 #include "ucg_device.h"
 #include "update.h"
@@ -37,7 +38,41 @@ FixNVE_UCGLD::FixNVE_UCGLD(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, a
   time_integrate = 1;
   dev = UCGDevice::get(lmp);
 }
-int FixNVE_UCGLD::setmask() { return INITIAL_INTEGRATE | FINAL_INTEGRATE | INITIAL_INTEGRATE_RESPA | FINAL_INTEGRATE_RESPA; }
+int FixNVE_UCGLD::setmask() {
+  return INITIAL_INTEGRATE | FINAL_INTEGRATE | INITIAL_INTEGRATE_RESPA | FINAL_INTEGRATE_RESPA | PRE_EXCHANGE | END_OF_STEP | POST_RUN;
+}
+// [stock] Verlet::setup calls Fix::setup after the first force evaluation: from here to post_run the arrays may stay on
+// the device if the deck allows it
+void FixNVE_UCGLD::setup(int) { dev->tracking_begin(lmp); }
+// rebuild steps: Domain::pbc, Comm::exchange / borders and Atom::sort are about to rewrite and reorder the host arrays
+void FixNVE_UCGLD::pre_exchange() {
+  if (!dev->tracked) return;
+  dev->flush(lmp);
+  dev->host_changed();
+}
+// output steps: thermo computes and dumps read the host arrays right after end_of_step
+void FixNVE_UCGLD::end_of_step() {
+  if (dev->tracked && output && output->next == update->ntimestep) dev->flush(lmp);
+}
+void FixNVE_UCGLD::post_run() { dev->tracking_end(lmp); }
+
+bool UCGDevice::tracking_allowed(LAMMPS *lmp) {
+  if (getenv("UCGB200_OFFLOAD_TRACKED") && atoi(getenv("UCGB200_OFFLOAD_TRACKED")) == 0) return false;
+  if (lmp->comm->nprocs > 1) return false;
+  if (!utils::strmatch(lmp->update->integrate_style, "^verlet")) return false;
+  Force *f = lmp->force;
+  auto *pp = f->pair ? dynamic_cast<UCGDeckPart *>(f->pair) : nullptr;
+  if (!pp || !pp->ucg_tracked_ok()) return false;
+  if (f->bond || f->angle || f->dihedral || f->improper || f->kspace) return false;
+  Modify *m = lmp->modify;
+  for (int i = 0; i < m->nfix; i++) {
+    Fix *fx = m->fix[i];
+    if (!m->fmask[i]) continue;                                     // does nothing inside the step
+    auto *part = dynamic_cast<UCGDeckPart *>(fx);
+    if (!part || !part->ucg_tracked_ok()) return false;              // somebody else's fix may read anything
+  }
+  return true;
+}
 void FixNVE_UCGLD::init() {
   dt_pos = update->dt;
   dt_half = 0.5 * update->dt * force->ftm2v;

@@ -543,6 +543,11 @@ struct Sim {
       for (int i = 0; i < m->nfix; i++) if (m->fmask[i] & FixConst::END_OF_STEP) m->fix[i]->end_of_step();
       timers[3] += now() - t6;
     }
+    post_run();
+  }
+  void post_run() {   // [stock] Verlet::cleanup -> Modify::post_run
+    Modify *m = lmp.modify;
+    for (int i = 0; i < m->nfix; i++) if (m->fmask[i] & FixConst::POST_RUN) m->fix[i]->post_run();
   }
 
   // ---------------------------------------------------------------- rRESPA ([stock] Respa::setup/run/recurse)
@@ -611,6 +616,7 @@ struct Sim {
       respa_recurse(respa->nlevels - 1, ev);
       for (int i = 0; i < m->nfix; i++) if (m->fmask[i] & FixConst::END_OF_STEP) m->fix[i]->end_of_step();
     }
+    post_run();
   }
   // ---------------------------------------------------------------- minimiser hook ([stock] Min::energy_force)
   // One force evaluation the way the minimisers do it: pbc/borders/rebuild when the skin rule fires, force_clear,

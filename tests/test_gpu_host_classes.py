@@ -534,3 +534,29 @@ def test_min_post_force(pkg, fixtures):
     away = np.abs(a["ucgp"] - 0.5) > 1e-9
     assert np.array_equal(a["ucgstate"][away], b["ucgstate"][away])
     assert abs(eb - ea) <= 1e-8 * abs(ea)
+
+
+# ------------------------------------------------------------------ offload mode: tracked transfers
+@pytest.mark.parametrize("fixes", [
+    ["fix 1 all nve/ucgld", "fix 2 all ucgld/langevin 1.5 1.5 0.5 4711", "fix 3 all ucgstate ld"],
+    ["fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld/wall/hard bias_potential 0.2", "fix 2 all ucgstate"],
+])
+def test_offload_tracked_transfers_change_nothing(pkg, fixtures, monkeypatch, fixes):
+    """stock Verlet over an all-UCG deck: with per-field tracking (a field goes up only when the host copy is newer,
+    comes down only where stock LAMMPS reads it: x every step, everything before an exchange, on output steps and at
+    the end of the run) every array after the run equals the eager mode's bit for bit, over several rebuilds"""
+    liq = _liq(8, T=2.0)
+    res = []
+    for tracked in ("1", "0"):
+        monkeypatch.setenv("UCGB200_OFFLOAD_TRACKED", tracked)
+        s = rb.HostSim.single_type(liq, fixtures["table4096"], fixtures["state"])
+        for f in fixes:
+            s.command(f)
+        s.setup(1)
+        s.run(45, 15)
+        res.append((s.get_atoms(), s.eng_vdwl(), s.nbuilds()))
+    (a, ea, na), (b, eb, nb) = res
+    assert na == nb and na >= 2
+    assert ea == eb
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
