@@ -212,6 +212,13 @@ int ucgb200_pair_bethe_density(ucgb200_ctx *ctx, int eflag, int vflag);
 int ucgb200_pair_bethe_density_priors(ucgb200_ctx *ctx, int cap, double *prob0, double *cvforce);
 /* eng_vdwl, virial[6] (xx,yy,zz,xy,xz,yz) of the last pair call with eflag/vflag */
 int ucgb200_pair_energy_virial(ucgb200_ctx *ctx, double *eng_vdwl, double virial[6]);
+/* Per-atom energy and virial of the last pair call that asked for them: LAMMPS' flag bits are honoured, eflag & 2 =
+ * ENERGY_ATOM, vflag & 4 = VIRIAL_ATOM (what compute pe/atom and compute stress/atom set through Pair::ev_setup).
+ * eatom[i] = sum_j E_ij / 2, vatom[i][0..5] = sum_j (d x d) fpair / 2 in LAMMPS' xx yy zz xy xz yz order — each site's
+ * own half of every pair it is in, which is what [stock] Pair::ev_tally (pair_table_ucgld.cpp:531-533) leaves on the
+ * owners after the reverse communication of the compute.  Host order; either pointer may be NULL.
+ * Implemented for table_ucgld (every table style and type system). */
+int ucgb200_pair_peratom(ucgb200_ctx *ctx, int nlocal_capacity, double *eatom /*[n]*/, double *vatom /*[6n]*/);
 
 /* --------------------------------------------------------------------- fixes */
 /* FixNVE_UCGLD::initial_integrate (fix_nve_ucgld.cpp:44-101); wall != 0 adds the

@@ -363,6 +363,14 @@ class Context:
         self._ck(self._l.ucgb200_pair_bethe_density_priors(self._h, int(n), _pd(p), _pd(f)))
         return p, f
 
+    def pair_peratom(self, eatom=True, vatom=True):
+        """per-atom energy [n] / virial [n,6] of the last pair_ucgld(eflag | 2, vflag | 4) call, host order"""
+        n = self.natoms()[0]
+        e = np.zeros(n) if eatom else None
+        v = np.zeros((n, 6)) if vatom else None
+        self._ck(self._l.ucgb200_pair_peratom(self._h, int(n), _pd(e), _pd(v)))
+        return e, v
+
     def pair_energy_virial(self):
         e, v = C.c_double(), np.zeros(6)
         self._ck(self._l.ucgb200_pair_energy_virial(self._h, C.byref(e), _pd(v)))

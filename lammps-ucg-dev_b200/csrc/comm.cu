@@ -190,7 +190,8 @@ void p2p_plan(ucgb200_ctx *c) {
   p.active = fits;
 }
 
-int p2p_forward(ucgb200_ctx *c) {
+// first half: this brick's records and control words go out, the local periodic images are refreshed
+int p2p_forward_begin(ucgb200_ctx *c) {
   CommState *s = state(c);
   CommState::P2P &p = s->p2p;
   const int nr = c->halo.nranks, me = c->halo.rank;
@@ -209,10 +210,24 @@ int p2p_forward(ucgb200_ctx *c) {
   int rc;
   if ((rc = ucg_halo_push_forward(c, t))) return rc;
   if ((rc = ucgb200_ghosts_forward(c))) return rc;      // local periodic images meanwhile
+  return 0;
+}
+// second half: wait for every peer's push of this sequence number (it has usually landed long ago when interior work
+// ran in between), fold the bricks' flags, move the records into the ghost slots
+int p2p_forward_end(ucgb200_ctx *c) {
+  CommState *s = state(c);
+  CommState::P2P &p = s->p2p;
+  const int nr = c->halo.nranks, me = c->halo.rank;
+  const int seq = p.seq, parity = seq & 1;
+  int rc;
   if ((rc = ucg_halo_wait_reduce(c, reinterpret_cast<const UcgP2PCtl *>(p.mine) + parity * UCG_P2P_MAX_RANKS, nr, me, seq))) return rc;
   if ((rc = ucgb200_halo_unpack_forward(c, p.mine + P2P_CTL_BYTES + (size_t)parity * p.region_records * P2P_REC))) return rc;
   p.pushes++;
   return 0;
+}
+int p2p_forward(ucgb200_ctx *c) {
+  int rc = p2p_forward_begin(c);
+  return rc ? rc : p2p_forward_end(c);
 }
 
 // send buffer grouped by destination, receive buffer grouped by source (the layouts of neighbor.cu)
@@ -328,35 +343,65 @@ extern "C" int ucgb200_comm_destroy(ucgb200_ctx *c) {
 }
 
 // comm->exchange() + comm->borders() + neighbor->build(): the rebuild of a multi-brick run
+// UCGB200_COMM_TRACE=2: wall-clock marks (with a stream synchronisation each) through a multi-brick rebuild, rank 0, stderr
+struct CommTrace {
+  ucgb200_ctx *c;
+  bool on;
+  double t0;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+  explicit CommTrace(ucgb200_ctx *ctx) : c(ctx), on(ctx->halo.rank == 0 && getenv("UCGB200_COMM_TRACE") && atoi(getenv("UCGB200_COMM_TRACE")) == 2), t0(0) {
+    if (on) { cudaStreamSynchronize(c->stream); t0 = now(); }
+  }
+  void mark(const char *what) {
+    if (!on) return;
+    cudaStreamSynchronize(c->stream);
+    const double t = now();
+    fprintf(stderr, "[mb_rebuild] %-30s %8.3f ms\n", what, t - t0);
+    t0 = t;
+  }
+};
+
 int ucg_mb_rebuild(ucgb200_ctx *c) {
   CommState *s = state(c);
   if (!s) return fail(c, "multi-brick run without ucgb200_comm_init");
   const int nr = c->halo.nranks;
   int rb = 0, rf = 0, rm = 0, rc;
   ucgb200_halo_record_bytes(&rb, &rf, &rm);
+  CommTrace tr(c);
   // sites that left their brick
   std::vector<int> sc(nr), rcv;
   if ((rc = ucgb200_migrate_prepare(c, sc.data()))) return rc;
+  tr.mark("migrate_prepare");
   if ((rc = exchange_counts(c, sc, rcv))) return rc;
+  tr.mark("exchange_counts (migrate)");
   UCG_CHECK(c, s->send.ensure((size_t)total(sc) * rm + 64));
   UCG_CHECK(c, s->recv.ensure((size_t)total(rcv) * rm + 64));
   if ((rc = ucgb200_migrate_pack(c, s->send.p))) return rc;
   if ((rc = all_to_all(c, s->send.p, s->recv.p, sc, rcv, rm))) return rc;
   if ((rc = ucgb200_migrate_unpack(c, s->recv.p, total(rcv)))) return rc;
+  tr.mark("migrate pack+a2a+unpack");
   // ghost shells
   if ((rc = ucgb200_neigh_build_local(c))) return rc;
+  tr.mark("build_local");
   if ((rc = ucgb200_halo_send_counts(c, sc.data()))) return rc;
   if ((rc = exchange_counts(c, sc, rcv))) return rc;
+  tr.mark("exchange_counts (borders)");
   UCG_CHECK(c, s->send.ensure((size_t)total(sc) * rb + 64));
   UCG_CHECK(c, s->recv.ensure((size_t)total(rcv) * rb + 64));
   if ((rc = ucgb200_halo_pack_border(c, s->send.p))) return rc;
   if ((rc = all_to_all(c, s->send.p, s->recv.p, sc, rcv, rb))) return rc;
   if ((rc = ucgb200_halo_unpack_border(c, s->recv.p, rcv.data()))) return rc;
+  tr.mark("border pack+a2a+unpack");
   if ((rc = ucgb200_neigh_build_finish(c))) return rc;
+  tr.mark("build_finish");
   s->send_counts = sc;
   s->recv_counts = rcv;
   if ((rc = p2p_setup(c))) return rc;     // first rebuild only
   p2p_plan(c);
+  // UCGB200_OVERLAP=1: interior / boundary split of the pair evaluation around the halo (run.cu).  Off by default:
+  // measured on 8 GPUs it LOSES 0.015 ms per step (two persistent launches stage the table twice and end in two
+  // partial waves, against ~0.02 ms of exchange latency that the push already keeps off the critical path).
+  if (s->p2p.active && getenv("UCGB200_OVERLAP") && atoi(getenv("UCGB200_OVERLAP")) == 1 && (rc = ucg_classify_rows(c))) return rc;
   UCG_CHECK(c, s->fwd_send.ensure((size_t)total(sc) * rf + 64));
   UCG_CHECK(c, s->fwd_recv.ensure((size_t)total(rcv) * rf + 64));
   s->nrebuilds++;
@@ -435,6 +480,15 @@ int ucg_mb_allreduce_int(ucgb200_ctx *c, int *d_buf, int n, int op) {
   UCG_NCCL(c, nccl().AllReduce(d_buf, d_buf, (size_t)n, ncclInt32, o, s->comm, c->stream));
   return 0;
 }
+
+// split form of ucg_mb_forward_reduce for the peer-mapped transport (run.cu puts the interior pair work in between)
+int ucg_mb_forward_begin(ucgb200_ctx *c) {
+  CommState *s = state(c);
+  if (!s || !s->p2p.active) return fail(c, "forward_begin: peer-mapped transport not active");
+  s->bytes_forward += (long long)total(s->send_counts) * (long long)P2P_REC;
+  return p2p_forward_begin(c);
+}
+int ucg_mb_forward_end(ucgb200_ctx *c) { return p2p_forward_end(c); }
 
 int ucg_mb_p2p_active(ucgb200_ctx *c) {
   CommState *s = state(c);

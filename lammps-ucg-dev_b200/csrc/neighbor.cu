@@ -1208,6 +1208,7 @@ extern "C" int ucgb200_neigh_build_local(ucgb200_ctx *c) {
   auto &h = c->halo;
   BuildTimer timer(c);
   c->list_valid = false;
+  c->parts_valid = false;
 
   UCG_CHECK(c, c->cell_count.ensure(ncells + 4));
   UCG_CHECK(c, c->cell_start.ensure(ncells + 4));
@@ -1573,6 +1574,57 @@ extern "C" int ucgb200_halo_pack_forward(ucgb200_ctx *c, void *d_sendbuf) {
   k_pack_forward<<<nblocks(h.nsend, 256), 256, 0, c->stream>>>(c->pos.p, c->ts.p, c->ucgp.p, c->img_owner.p, c->img_code.p,
                                                               h.nsend, im, (ForwardRec *)d_sendbuf);
   UCG_LAUNCHED(c);
+  return 0;
+}
+
+// ---- interior / boundary rows of a multi-brick list
+// 8 lanes per row: does the row hold a ghost that came from another brick (source index >= nlimg)?
+__global__ void k_row_has_remote(const int *__restrict__ neigh, int stride, const int *__restrict__ numneigh, int nlocal,
+                                 const int *__restrict__ ghost_src, int nlimg, int *__restrict__ flag) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = t >> 3, sub = t & 7;
+  bool hit = false;
+  if (i < nlocal) {
+    const int *row = neigh + (size_t)i * stride;
+    const int n = numneigh[i];
+    for (int k = sub; k < n; k += 8) {      // any order: storage slots 0..n-1 hold the row's n entries (rowslot permutes inside 16-blocks)
+      const int j = row[rowslot(k)] & UCG_NEIGHMASK;
+      if (j >= nlocal && ghost_src[j - nlocal] >= nlimg) hit = true;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, hit);
+  if (i < nlocal && sub == 0) flag[i] = ((m >> ((threadIdx.x & 31) & ~7)) & 0xffu) ? 1 : 0;
+}
+__global__ void k_fill_site_list(const int *__restrict__ flag, const int *__restrict__ scan, int nlocal, const int *__restrict__ nboundary,
+                                 int *__restrict__ list, int *__restrict__ part) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) part[0] = nlocal - *nboundary;
+  if (i >= nlocal) return;
+  const int ninterior = nlocal - *nboundary;
+  if (flag[i]) list[ninterior + scan[i]] = i;          // scan = boundary sites before i
+  else list[i - scan[i]] = i;
+}
+int ucg_classify_rows(ucgb200_ctx *c) {
+  cudaSetDevice(c->device);
+  c->parts_valid = false;
+  const int nlocal = c->nlocal;
+  if (!c->list_valid || nlocal == 0) return 0;
+  UCG_CHECK(c, c->row_flag.ensure(nlocal + 1));
+  UCG_CHECK(c, c->row_scan.ensure(nlocal + 1));
+  UCG_CHECK(c, c->site_list.ensure(nlocal + 1));
+  UCG_CHECK(c, c->d_part.ensure(4));
+  if (c->nghost == 0) {
+    UCG_CHECK(c, cudaMemsetAsync(c->row_flag.p, 0, nlocal * sizeof(int), c->stream));
+  } else {
+    k_row_has_remote<<<nblocks((long long)nlocal * 8, 256), 256, 0, c->stream>>>(c->neigh.p, c->neigh_stride, c->numneigh.p, nlocal,
+                                                                                  c->ghost_src.p, c->halo.nlimg, c->row_flag.p);
+    UCG_LAUNCHED(c);
+  }
+  int rc = exclusive_scan(c, c->row_flag.p, c->row_scan.p, nlocal, c->d_part.p + 1);
+  if (rc) return rc;
+  k_fill_site_list<<<nblocks(nlocal, 256), 256, 0, c->stream>>>(c->row_flag.p, c->row_scan.p, nlocal, c->d_part.p + 1, c->site_list.p, c->d_part.p);
+  UCG_LAUNCHED(c);
+  c->parts_valid = true;
   return 0;
 }
 

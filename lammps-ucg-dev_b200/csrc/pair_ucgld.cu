@@ -41,6 +41,7 @@ struct PairArgs {
   double2 *scores;
   double *partials;
   ErrWord *err;
+  double *eatom, *vatom;   // per-atom tallies (EV launches only), nullptr: not asked for
 };
 
 // ---------------------------------------------------------------- general kernel
@@ -133,12 +134,13 @@ __global__ void __launch_bounds__(BS) k_pair_ucgld(PairArgs p) {
     p.frc[i] = fo;
     p.scores[i] = so;
     if (EV) ev[0] = 0.5 * e_i;
+    if (EV && p.eatom) p.eatom[i] = 0.5 * e_i;          // this site's half of every pair it is in (ev_tally, eflag_atom)
   }
   if (EV) {
 #pragma unroll
     for (int k = 0; k < 6; k++) {
       double v = group_sum<LPA>(vir[k]);
-      if (active && sub == 0) ev[1 + k] = 0.5 * v;
+      if (active && sub == 0) { ev[1 + k] = 0.5 * v; if (p.vatom) p.vatom[6 * (size_t)i + k] = 0.5 * v; }
     }
     block_reduce_store<7, BS>(ev, p.partials);
   }
@@ -191,6 +193,12 @@ struct FastArgs {
   double inv_w;
   cudaTextureObject_t postex;   // {x,y,z,lambda} records as 2 int4 texels each (TEX = true)
   cudaTextureObject_t sbtex;    // state bits as 32-bit texels (TEX = 3)
+  // multi-brick runs: walk only one part of the owned sites (site_list = interior sites, then boundary sites;
+  // part_count[0] = number of interior sites); nullptr: every site
+  const int *site_list;
+  const int *part_count;
+  int part;
+  double *eatom, *vatom;        // per-atom tallies (EV launches only), nullptr: not asked for
 };
 
 // PF = 1 software-pipelines the neighbor gathers: index and {x,y,z,lambda}/state of the
@@ -230,10 +238,17 @@ __global__ void __launch_bounds__(BS) k_pair_ucgld_fast(FastArgs p) {
     level = min(7, (int)floor(2.0 * md * p.inv_w));
   }
 
-  for (int base = blockIdx.x * groups_per_block; base < p.nlocal; base += gridDim.x * groups_per_block) {
+  int first = 0, count = p.nlocal;
+  if (p.site_list) {
+    const int ninterior = p.part_count[0];
+    first = p.part == 0 ? 0 : ninterior;
+    count = p.part == 0 ? ninterior : p.nlocal - ninterior;
+  }
+  for (int base = blockIdx.x * groups_per_block; base < count; base += gridDim.x * groups_per_block) {
     const int gid = base + threadIdx.x / LPA;
-    const bool active = gid < p.nlocal;
-    const int i = active ? gid : p.nlocal - 1;
+    const bool active = gid < count;
+    const int idx = active ? gid : count - 1;
+    const int i = p.site_list ? p.site_list[first + idx] : idx;
     const double4 ri = p.pos[i];
     const double li = ri.w, ai = 1.0 - li;
     int jnum = active ? p.numneigh[i] : 0;
@@ -341,12 +356,13 @@ __global__ void __launch_bounds__(BS) k_pair_ucgld_fast(FastArgs p) {
       p.frc[i] = fo;
       p.scores[i] = make_double2(-S0 * p.inv_kT, -p.dmu * p.inv_kT - S1 * p.inv_kT);
       if (EV) ev[0] += 0.5 * (ai * accA + li * accB);
+      if (EV && p.eatom) p.eatom[i] = 0.5 * (ai * accA + li * accB);
     }
     if (EV) {
 #pragma unroll
       for (int k = 0; k < 6; k++) {
         double v = group_sum<LPA>(vir[k]);
-        if (active && sub == 0) ev[1 + k] += 0.5 * v;
+        if (active && sub == 0) { ev[1 + k] += 0.5 * v; if (p.vatom) p.vatom[6 * (size_t)i + k] = 0.5 * v; }
       }
     }
   }
@@ -754,6 +770,13 @@ static int launch_general(ucgb200_ctx *c, PairArgs &a, int &nblk) {
   return 0;
 }
 
+// run.cu: may the next non-thermo evaluation be split into its interior and boundary parts (pair_part 0 / 1)?
+int ucg_pair_can_split(ucgb200_ctx *c) {
+  return c->fast_uniform && c->parts_valid && c->list_valid && !env_int("UCGB200_FORCE_GENERAL", 0) && !env_int("UCGB200_N3L", 0) &&
+         env_int("UCGB200_LPA", 4) == 4 && env_int("UCGB200_TEX", 3) && env_int("UCGB200_SMEM_TABLE", 1) &&
+         (size_t)c->fast_len * c->fast_ntab * sizeof(double2) <= 220 * 1024;
+}
+
 extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
   if (!c) return -1;
   cudaSetDevice(c->device);
@@ -769,6 +792,12 @@ extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
     return 0;
   }
   const bool ev = eflag || vflag;
+  // LAMMPS flag bits: eflag & 2 = ENERGY_ATOM, vflag & 4 = VIRIAL_ATOM
+  const bool want_eatom = (eflag & 2) != 0, want_vatom = (vflag & 4) != 0;
+  c->eatom_valid = c->vatom_valid = false;
+  double *d_eatom = nullptr, *d_vatom = nullptr;
+  if (want_eatom) { UCG_CHECK(c, c->d_eatom.ensure((size_t)c->nlocal + 8)); d_eatom = c->d_eatom.p; }
+  if (want_vatom) { UCG_CHECK(c, c->d_vatom.ensure(6 * (size_t)c->nlocal + 8)); d_vatom = c->d_vatom.p; }
   int nblk = 0;
   const bool timed = c->timers_on;
   if (timed) cudaEventRecord(c->ev_pair0, c->stream);
@@ -797,6 +826,12 @@ extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
     a.levcnt = nullptr; a.maxdisp = c->d_maxdisp.p; a.inv_w = c->skin > 0.0 ? 8.0 / c->skin : 0.0;
     if (c->maxdisp_valid && c->skin > 0.0 && env_int("UCGB200_SKIN_LEVELS", 1)) a.levcnt = c->levcnt.p;
     a.postex = 0; a.sbtex = 0;
+    a.site_list = nullptr; a.part_count = nullptr; a.part = -1;
+    a.eatom = d_eatom; a.vatom = d_vatom;
+    if (c->pair_part >= 0 && c->parts_valid && !ev && !env_int("UCGB200_N3L", 0)) {
+      a.site_list = c->site_list.p; a.part_count = c->d_part.p; a.part = c->pair_part;
+    }
+    c->pair_part = -1;
     const int tex_mode = env_int("UCGB200_TEX", 3);   // 0: every gather through the LSU pipe
     if (tex_mode) {
       if ((rc = ucg_bind_gather_textures(c, &a.postex, nullptr))) return rc;
@@ -804,7 +839,7 @@ extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
       a.sbtex = c->tex_sbits.tex;
     }
     const int bs = env_int("UCGB200_BS", 768), pf = env_int("UCGB200_PF", 1);
-    const int n3l = env_int("UCGB200_N3L", 0);
+    const int n3l = (want_eatom || want_vatom) ? 0 : env_int("UCGB200_N3L", 0);   // the experiments carry no per-atom tallies
     if (n3l == 2 && a.postex && a.sbtex && a.smem_table && c->fast_ntab == 3) {
       rc = ev ? launch_n3l_bulk<true, 3>(c, a, nblk) : launch_n3l_bulk<false, 3>(c, a, nblk);
     } else if (n3l && a.postex && a.sbtex && a.smem_table) {
@@ -827,6 +862,7 @@ extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
     for (int k = 0; k < 4; k++) a.special_lj[k] = c->special_lj[k];
     a.inv_kT = 1.0 / c->kT;
     a.frc = c->frc.p; a.scores = c->scores.p; a.err = c->d_err.p;
+    a.eatom = d_eatom; a.vatom = d_vatom;
     if (ev) rc = launch_general<8, true>(c, a, nblk); else rc = launch_general<8, false>(c, a, nblk);
   }
   if (rc) return rc;
@@ -834,7 +870,42 @@ extern "C" int ucgb200_pair_ucgld(ucgb200_ctx *c, int eflag, int vflag) {
   if (ev) {
     if ((rc = reduce_partials(c, nblk, 7, 0))) return rc;
     c->ev_valid = true;
+    c->eatom_valid = want_eatom;
+    c->vatom_valid = want_vatom;
   }
+  return 0;
+}
+
+namespace {
+__global__ void k_peratom_to_host_order(const double *__restrict__ src, const int *__restrict__ orig, int n, int width, double *__restrict__ dst) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * width) return;
+  const int i = t / width, k = t - i * width;
+  dst[(size_t)orig[i] * width + k] = src[(size_t)i * width + k];
+}
+}  // namespace
+
+extern "C" int ucgb200_pair_peratom(ucgb200_ctx *c, int cap, double *eatom, double *vatom) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  const int n = c->nlocal;
+  if (cap < n) return fail(c, "pair_peratom: host capacity smaller than nlocal");
+  if ((eatom && !c->eatom_valid) || (vatom && !c->vatom_valid))
+    return fail(c, "pair_peratom: the last pair call did not tally per-atom values (eflag & 2 / vflag & 4), or the style does not support them");
+  if (n == 0) return 0;
+  UCG_CHECK(c, c->stage_d.ensure(16 * (size_t)n + 64));
+  double *sd = c->stage_d.p;
+  if (eatom) {
+    k_peratom_to_host_order<<<nblocks(n, 256), 256, 0, c->stream>>>(c->d_eatom.p, c->orig.p, n, 1, sd);
+    UCG_LAUNCHED(c);
+    UCG_CHECK(c, cudaMemcpyAsync(eatom, sd, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (vatom) {
+    k_peratom_to_host_order<<<nblocks((long long)n * 6, 256), 256, 0, c->stream>>>(c->d_vatom.p, c->orig.p, n, 6, sd + n);
+    UCG_LAUNCHED(c);
+    UCG_CHECK(c, cudaMemcpyAsync(vatom, sd + n, 6 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  UCG_CHECK(c, cudaStreamSynchronize(c->stream));
   return 0;
 }
 

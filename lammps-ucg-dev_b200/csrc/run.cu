@@ -78,6 +78,10 @@ int ucg_mb_rebuild(ucgb200_ctx *c);
 int ucg_mb_forward(ucgb200_ctx *c);
 int ucg_mb_decide(ucgb200_ctx *c, bool prechecked, int *rebuild);
 int ucg_mb_forward_reduce(ucgb200_ctx *c, bool with_decide);   // forward halo + MAX of the bricks' rebuild flags / displacement bounds
+int ucg_mb_forward_begin(ucgb200_ctx *c);   // peer-mapped transport: push + local images ...
+int ucg_mb_forward_end(ucgb200_ctx *c);     // ... wait + flag reduction + unpack
+int ucg_mb_p2p_active(ucgb200_ctx *c);
+int ucg_pair_can_split(ucgb200_ctx *c);     // pair_ucgld.cu
 
 static int do_build(ucgb200_ctx *c) { return c->halo.nranks > 1 ? ucg_mb_rebuild(c) : ucgb200_neigh_build(c); }
 static int do_forward(ucgb200_ctx *c) { return c->halo.nranks > 1 ? ucg_mb_forward(c) : ucgb200_ghosts_forward(c); }
@@ -229,7 +233,21 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
       // step, BEFORE the host waits for the flag: the device never idles while the host decides.  If the flag says
       // rebuild after all, the speculative results are simply overwritten by the rebuild + pair that follow.
       if (!c->ev_flag) UCG_CHECK(c, cudaEventCreateWithFlags(&c->ev_flag, cudaEventDisableTiming));
-      if (bricks) {
+      const double quiet = 0.8 * 0.5 * c->skin;
+      const bool calm = c->last_maxdisp >= 0.0 && c->last_maxdisp < quiet * quiet;
+      // halo / compute overlap: the interior sites (no neighbor from another brick) are evaluated between the push of
+      // this brick's records and the wait for the peers', the boundary sites after the unpack
+      const bool split = bricks && calm && !ev && d.pair_style == 0 && ucg_mb_p2p_active(c) && ucg_pair_can_split(c);
+      if (split) {
+        if ((rc = ucg_mb_forward_begin(c))) return rc;
+        // interior rows only meet sites of this brick (and their local periodic images): the displacement bound of
+        // THIS brick, left by the fused tail, is enough for the exact skin skipping of this part
+        c->maxdisp_valid = true;
+        c->pair_part = 0;
+        if ((rc = pair_compute(c, 0))) return rc;
+        if ((rc = ucg_mb_forward_end(c))) return rc;
+        forward_done = true;
+      } else if (bricks) {
         // the ghost refresh of this step carries every brick's flag and displacement bound with it (control words of
         // the peer-mapped push, or two small all-reduces behind the NCCL send/recv group): after it d_flags[0] and
         // d_maxdisp hold the MAX over all bricks.  A refresh that turns out to precede a rebuild is simply redone.
@@ -241,9 +259,9 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
       if ((rc = queue_error_readback(c))) return rc;
       UCG_CHECK(c, cudaEventRecord(c->ev_flag, c->stream));
       c->maxdisp_valid = true;
-      const double quiet = 0.8 * 0.5 * c->skin;
-      if (c->last_maxdisp >= 0.0 && c->last_maxdisp < quiet * quiet) {
+      if (calm) {
         if (!forward_done && (rc = do_forward(c))) return rc;
+        if (split) c->pair_part = 1;
         if ((rc = pair_compute(c, ev))) return rc;
         pair_in_flight = true;
       }

@@ -182,6 +182,11 @@ struct ucgb200_ctx {
   bool maxdisp_valid = false;
   ucg::Buf<unsigned> statebits;
   ucg::Buf<double> pair_acc;   // pair_ucgld.cu, N3L bulk variant: 6 doubles per owned site
+  // multi-brick runs: owned sites whose row holds no ghost received from another brick ("interior", first in
+  // site_list) and the rest ("boundary"): the interior part of a pair evaluation runs while the halo is in flight
+  ucg::Buf<int> row_flag, row_scan, site_list, d_part;   // d_part[0] = number of interior sites
+  bool parts_valid = false;
+  int pair_part = -1;          // next ucgb200_pair_ucgld call: -1 all sites, 0 interior, 1 boundary (reset by the call)
   int neigh_stride = 0;
   bool list_valid = false;
   int nbuilds = 0;
@@ -193,6 +198,8 @@ struct ucgb200_ctx {
   ucg::Buf<ucg::ErrWord> d_err;
   double h_ev[16] = {0};
   bool ev_valid = false;
+  ucg::Buf<double> d_eatom, d_vatom;   // per-atom energy [n] / virial [6n] of the last pair call that asked for them
+  bool eatom_valid = false, vatom_valid = false;
 
   // deck / run state
   ucgb200_deck deck{};
@@ -368,6 +375,7 @@ struct UcgPushTargets {
   const unsigned long long *local_maxdisp;
   unsigned *done;                        // block counter of the push kernel (zero between launches)
 };
+int ucg_classify_rows(ucgb200_ctx *c);                                // neighbor.cu: fills site_list / d_part of the current list
 int ucg_halo_push_forward(ucgb200_ctx *c, const UcgPushTargets &t);   // neighbor.cu
 int ucg_halo_wait_reduce(ucgb200_ctx *c, const UcgP2PCtl *ctl_mine, int nranks, int self, int seq);   // neighbor.cu
 int ucg_host_out_queue(ucgb200_ctx *c, unsigned mask);   // context.cu: gather + D2H of the not yet delivered fields in mask

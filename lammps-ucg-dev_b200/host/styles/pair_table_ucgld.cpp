@@ -184,7 +184,17 @@ void PairTable_UCGLD::compute(int eflag, int vflag) {
   dev->upload(lmp, UCGB200_F_X | UCGB200_F_UCGL | UCGB200_F_UCGSTATE | UCGB200_F_UCGP);
   dev->ensure_list(lmp);
   const int ev = (eflag_either || vflag_either) ? 1 : 0;
-  device_compute(ev, ev);
+  // per-atom tallies (compute pe/atom, stress/atom): LAMMPS' own flag bits go down to the device
+  const bool want_peratom = eflag_atom || vflag_atom;
+  if (want_peratom && !peratom_supported())
+    error->all(FLERR, "ucg-b200: per-atom energy / virial is implemented for pair_style table_ucgld only");
+  device_compute(ev | (eflag_atom ? 2 : 0), ev | (vflag_atom ? 4 : 0));
+  if (want_peratom) {
+    std::vector<double> ea(eflag_atom ? (size_t)nlocal : 0), va(vflag_atom ? 6 * (size_t)nlocal : 0);
+    dev->check(lmp, ucgb200_pair_peratom(dev->ctx, nlocal, eflag_atom ? ea.data() : nullptr, vflag_atom ? va.data() : nullptr), "pair_peratom");
+    if (eflag_atom) for (int i = 0; i < nlocal; i++) eatom[i] += ea[i];
+    if (vflag_atom) for (int i = 0; i < nlocal; i++) for (int k = 0; k < 6; k++) vatom[i][k] += va[6 * (size_t)i + k];
+  }
   if (dev->tracked) {
     // tracked offload mode: nobody on the host reads f / ucgforce / scores before the next flush, and after stock
     // Verlet's force_clear "added to zero" is "assigned": the results stay on the device

@@ -35,6 +35,7 @@ class PairTable_UCGLD : public Pair, public UCGDeckPart {
   void *extract(const char *, int &) override;
   bool ucg_deck(ucgb200_deck &deck) override;   // this style's part of the resident deck (run_style ucg/b200)
   bool ucg_tracked_ok() const override { return true; }
+  virtual bool peratom_supported() const { return true; }   // eflag_atom / vflag_atom tallies on the device
   enum { LOOKUP, LINEAR, SPLINE, BITMAP };
 
  protected:

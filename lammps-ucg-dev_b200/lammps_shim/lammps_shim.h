@@ -1089,8 +1089,10 @@ class Pair : protected Pointers {
   }
   void ev_setup(int eflag, int vflag, int = 1) {
     evflag = 1;
-    eflag_either = eflag; eflag_global = eflag & 1; eflag_atom = 0;
-    vflag_either = vflag; vflag_global = vflag & 3; vflag_atom = 0; cvflag_atom = 0;
+    // [stock] ENERGY_GLOBAL = 1, ENERGY_ATOM = 2; VIRIAL_PAIR = 1, VIRIAL_FDOTR = 2, VIRIAL_ATOM = 4
+    eflag_either = eflag; eflag_global = eflag & 1; eflag_atom = eflag & 2;
+    vflag_either = vflag; vflag_global = vflag & 3; vflag_atom = vflag & 4; cvflag_atom = 0;
+    if (eflag_atom || vflag_atom) shim_peratom_alloc();
     // with newton_pair on and no_virial_fdotr unset, the global virial is left to
     // virial_fdotr_compute() and ev_tally skips it
     vflag_fdotr = 0;
@@ -1108,6 +1110,11 @@ class Pair : protected Pointers {
         if (j < nlocal) { eng_vdwl += 0.5 * evdwl; eng_coul += 0.5 * ecoul; }
       }
     }
+    if (eflag_either && eflag_atom) {
+      const double epairhalf = 0.5 * (evdwl + ecoul);
+      if (newton_pair || i < nlocal) eatom[i] += epairhalf;
+      if (newton_pair || j < nlocal) eatom[j] += epairhalf;
+    }
     if (vflag_either || vflag_fdotr) {
       double v[6] = {delx * delx * fpair, dely * dely * fpair, delz * delz * fpair,
                      delx * dely * fpair, delx * delz * fpair, dely * delz * fpair};
@@ -1116,8 +1123,15 @@ class Pair : protected Pointers {
         virial_tally[k] += w * v[k];
         if (vflag_global) virial[k] += w * v[k];
       }
+      if (vflag_atom) {
+        if (newton_pair || i < nlocal) for (int k = 0; k < 6; k++) vatom[i][k] += 0.5 * v[k];
+        if (newton_pair || j < nlocal) for (int k = 0; k < 6; k++) vatom[j][k] += 0.5 * v[k];
+      }
     }
   }
+  std::vector<double> shim_eatom, shim_vatom;
+  std::vector<double *> shim_vrows;
+  void shim_peratom_alloc();   // eatom / vatom over nlocal + nghost, zeroed ([stock] ev_setup)
   void virial_fdotr_compute();
   void init_bitmap(double inner, double outer, int ntablebits, int &masklo, int &maskhi, int &nmask, int &nshiftbits);
   inline int sbmask(int j) const { return j >> SBBITS & 3; }
@@ -1167,6 +1181,15 @@ inline NeighRequest *Neighbor::add_request(Fix *f, int flags) {
   return r;
 }
 inline int Pair::shim_newton_pair() { return force->newton_pair; }
+inline void Pair::shim_peratom_alloc() {
+  const size_t n = (size_t)atom->nlocal + atom->nghost + 1;
+  shim_eatom.assign(n, 0.0);
+  shim_vatom.assign(6 * n, 0.0);
+  shim_vrows.resize(n);
+  for (size_t i = 0; i < n; i++) shim_vrows[i] = shim_vatom.data() + 6 * i;
+  eatom = shim_eatom.data();
+  vatom = shim_vrows.data();
+}
 inline bigint Group::count(int igroup) {
   bigint n = 0;
   for (int i = 0; i < atom->nlocal; i++) if (atom->mask[i] & bitmask[igroup]) n++;

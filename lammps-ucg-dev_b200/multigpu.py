@@ -443,6 +443,19 @@ def bench(args, rank, world, local, dist):
         sampler.stop_flag.set()
         sampler.join()
 
+    # where a step's time goes on this brick: instrumented loop (one step per call, event synchronisation per stage,
+    # no speculative launch), every rank takes part in the exchanges
+    stage = None
+    if resident and os.environ.get("UCGB200_BENCH_STAGES", "1") != "0":
+        nst = 20
+        r0 = ctx.comm_stats()["rebuilds"]
+        ctx.timers(2)
+        for _ in range(nst):
+            cl.run(1)
+        tms, _ = ctx.timers(0)
+        stage = {k: v / nst for k, v in tms.items()}
+        stage["rebuilds_in_window"] = ctx.comm_stats()["rebuilds"] - r0
+        stage["note"] = "separate instrumented loop; neigh = decide + rebuild (migration, borders, rows), comm = forward halo"
     # pair-kernel roofline on rank 0's brick
     total_full, _, _ = ctx.neigh_stats()
     nloc = ctx.natoms()[0]
@@ -552,6 +565,7 @@ def bench(args, rank, world, local, dist):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "kernel": "k_pair_ucgld_fast", "kernel_ms": pair_avg, "bytes_per_site": bps,
+                             "stage_ms_per_step": stage,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
                 "cpu_baseline": None,
                 "e2e": {"value": nsites * done / e2e_s / 1e6, "unit": B.UNIT, "h2d_bytes_per_step": h2d_step,

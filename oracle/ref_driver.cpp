@@ -458,6 +458,7 @@ struct Sim {
   void ev_flags(int ev, int &eflag, int &vflag) {
     eflag = ev ? 1 : 0;
     vflag = ev ? (lmp.force->newton_pair ? 2 : 1) : 0;  // VIRIAL_FDOTR : VIRIAL_PAIR
+    if (ev == 3) { eflag |= 2; vflag |= 4; }            // + ENERGY_ATOM, VIRIAL_ATOM (compute pe/atom, stress/atom)
     eflag_last = eflag;
   }
   void compute_forces(int ev) {
@@ -938,6 +939,25 @@ int ref_fix_call_respa(void *h, int ifix, int what, int ilevel, int iloop) {
     if (what == 0) f->initial_integrate_respa(0, ilevel, iloop);
     else if (what == 1) f->final_integrate_respa(ilevel, iloop);
     else if (what == 2) f->post_force_respa(0, ilevel, iloop);
+  });
+}
+// per-atom energy / virial of the last compute(eflag|ENERGY_ATOM, vflag|VIRIAL_ATOM): what compute pe/atom and
+// compute stress/atom read, with the ghost tallies folded onto their owners ([stock] Compute...::compute_peratom
+// calls comm->reverse_comm(this) when newton is on)
+int ref_pair_peratom(void *h, double *eatom, double *vatom) {
+  Sim *s = (Sim *)h;
+  return guarded(s, [&] {
+    Pair *p = s->lmp.force->pair;
+    Atom *a = s->lmp.atom;
+    if (!p->eatom || !p->vatom) s->lmp.error->all(FLERR, "no per-atom tallies: compute with ev = 3 first");
+    const int nl = a->nlocal;
+    for (int i = 0; i < nl; i++) { eatom[i] = p->eatom[i]; for (int k = 0; k < 6; k++) vatom[6 * i + k] = p->vatom[i][k]; }
+    if (s->lmp.force->newton_pair)
+      for (int g = 0; g < a->nghost; g++) {
+        const int o = s->ghost_owner[g];
+        eatom[o] += p->eatom[nl + g];
+        for (int k = 0; k < 6; k++) vatom[6 * o + k] += p->vatom[nl + g][k];
+      }
   });
 }
 int ref_min_energy_force(void *h, int ev) {

@@ -129,6 +129,13 @@ class RefSim:
                      min_post_force=6, post_force_respa_inner=7, post_force_respa_outer=8)
         self._ck(self.l.ref_fix_call(self.h, int(ifix), names[what]))
 
+    def pair_peratom(self):
+        """(eatom[n], vatom[n,6]) of the last compute_once(3), ghost tallies folded onto the owners"""
+        n = self.nlocal()
+        e, v = np.zeros(n), np.zeros((n, 6))
+        self._ck(self.l.ref_pair_peratom(self.h, _pd(e), _pd(v)))
+        return e, v
+
     def fix_call_respa(self, ifix, what, ilevel, iloop=0):
         names = dict(initial_integrate_respa=0, final_integrate_respa=1, post_force_respa=2)
         self._ck(self.l.ref_fix_call_respa(self.h, int(ifix), names[what], int(ilevel), int(iloop)))

@@ -560,3 +560,34 @@ def test_offload_tracked_transfers_change_nothing(pkg, fixtures, monkeypatch, fi
     assert ea == eb
     for k in a:
         assert np.array_equal(a[k], b[k]), k
+
+
+# ------------------------------------------------------------------ per-atom energy / virial (eflag_atom, vflag_atom)
+@pytest.mark.parametrize("tabstyle,tablength", [("linear", 4096), ("spline", 1500)])
+def test_per_atom_energy_and_virial(pkg, fixtures, tabstyle, tablength):
+    """compute pe/atom / stress/atom ask the pair style for per-atom tallies through Pair::ev_setup (ENERGY_ATOM = 2,
+    VIRIAL_ATOM = 4); the reference delivers them through [stock] Pair::ev_tally (pair_table_ucgld.cpp:531-533): half
+    of every pair's energy and virial to each partner, ghost tallies reverse-communicated to the owners.  The drop-in
+    class fills Pair::eatom / Pair::vatom from the device (ucgb200_pair_peratom); they must sum to the global values"""
+    liq = _liq(7)
+    out = []
+    for cls in (rb.RefSim, rb.HostSim):
+        s = cls.single_type(liq, fixtures["table4096"], fixtures["state"], tabstyle=tabstyle, tablength=tablength)
+        s.command("fix 0 all ttarget/stub 1.0")
+        s.compute_once(3)
+        e, v = s.pair_peratom()
+        out.append((e, v, s.eng_vdwl(), s.virial()))
+    (ea, va, Ea, Wa), (eb, vb, Eb, Wb) = out
+    assert rel_err(eb, ea) <= 1e-8
+    assert rel_err(vb, va) <= 1e-8
+    worst = np.abs(eb - ea).max() / np.abs(ea).max()
+    assert abs(eb.sum() - Eb) <= 1e-10 * abs(Eb) and abs(ea.sum() - Ea) <= 1e-10 * abs(Ea)
+    assert rel_err(vb.sum(0), Wb[0]) <= 1e-10          # the drop-in's global virial is the per-pair tally (Q3)
+    assert rel_err(va.sum(0), Wa[1]) <= 1e-10
+    assert abs(Eb - Ea) <= 1e-8 * abs(Ea)
+    # the bethe style does not carry per-atom tallies: asked for, it must say so instead of returning zeros
+    s = rb.HostSim.single_type(liq, fixtures["table4096"], fixtures["state"], pair="table_ucg_bethe",
+                               extra="method bethe pseudo yes prior ucgl")
+    s.command("fix 0 all ttarget/stub 1.0")
+    with pytest.raises(RuntimeError, match="per-atom energy / virial is implemented for pair_style table_ucgld only"):
+        s.compute_once(3)
