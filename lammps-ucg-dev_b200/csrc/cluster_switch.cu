@@ -273,8 +273,6 @@ extern "C" int ucgb200_cluster_configure(ucgb200_ctx *c, int mol_seed, int mol_o
   if (n_switch_types < 1 || n_switch_types > CS_MAXSW) return fail(c, "Incorrect number of atom switching types (fix cluster_switch)");
   if (prob_on > 1.0) return fail(c, "Incorrect probability in rates.txt files (fix cluster_switch)");
   if (seed <= 0) return fail(c, "Invalid seed for Park random # generator");
-  if (c->halo.nranks > 1 && (groupbit ? groupbit : 1) != 1)
-    return fail(c, "fix cluster_switch across bricks supports group all only (ghost records carry no group mask)");
   if (c->nlocal <= 0) return fail(c, "fix cluster_switch: upload the atoms first (the constructor scans their molecule ids and types)");
   cudaSetDevice(c->device);
   auto &k = c->cluster;
@@ -348,9 +346,13 @@ extern "C" int ucgb200_cluster_check(ucgb200_ctx *c, int *n_cluster) {
                                                            k.d_label.p);
   UCG_LAUNCHED(c);
   { int rc2; if ((rc2 = ucg_mb_allreduce_int(c, k.d_label.p, nm, 1))) return rc2; }   // :586, MPI_MAX since labels start at -1
-  // group bits of the periodic images (ghosts owned by other bricks: group all, checked in _configure)
+  // group bits of the ghosts: local periodic images from their owners, ghosts owned by other bricks from the border
+  // records of the last rebuild (neighbor.cu, BorderRec::mask)
   UCG_CHECK(c, k.d_gmask.ensure(std::max(c->nghost, 1)));
-  if (c->halo.nranks > 1 && c->nghost > 0) { k_cs_fill<<<nblocks(c->nghost, 256), 256, 0, st>>>(k.d_gmask.p, c->nghost, 1); UCG_LAUNCHED(c); }
+  if (c->halo.nranks > 1 && c->nghost > 0) {
+    if (c->ghost_mask.cap < (size_t)c->nghost) return fail(c, "cluster_check: ghost group bits missing (no rebuild since configure)");
+    UCG_CHECK(c, cudaMemcpyAsync(k.d_gmask.p, c->ghost_mask.p, (size_t)c->nghost * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  }
   if (c->halo.nlimg) {
     k_cs_ghost_mask<<<nblocks(c->halo.nlimg, 256), 256, 0, st>>>(c->mask.p, c->halo.nlimg, c->img_owner.p + c->halo.nsend,
                                                                  c->slot_of_src.p, k.d_gmask.p);

@@ -280,7 +280,8 @@ __global__ void k_images(const double4 *__restrict__ pos, int n, BoxDev box, Ima
 struct BorderRec {  // 64 B: fields_border of AtomVecUCG (atom_vec_ucg.cpp:66-67) + tag/type
   double4 pos;      // x,y,z (shifted), ucgl
   int ts, tag, mol, code;
-  double ucgp, pad;
+  double ucgp;
+  int mask, pad;    // group bits travel with the border record (fix cluster_switch masks by groupbit, fix_cluster_switch.cpp:102,138,569,578)
 };
 struct ForwardRec {  // 48 B: x + fields_comm {ucgstate, ucgl, ucgp} (atom_vec_ucg.cpp:71)
   double4 pos;
@@ -294,8 +295,9 @@ struct MigrateRec {  // 96 B: the UCG part of fields_exchange (atom_vec_ucg.cpp:
 };
 
 __global__ void k_pack_border(const double4 *__restrict__ pos, const int *__restrict__ ts, const int *__restrict__ tag,
-                              const int *__restrict__ mol, const double *__restrict__ ucgp, const int *__restrict__ owner,
-                              const int *__restrict__ code, int n, ImageMap im, BorderRec *__restrict__ out) {
+                              const int *__restrict__ mol, const double *__restrict__ ucgp, const int *__restrict__ mask,
+                              const int *__restrict__ owner, const int *__restrict__ code, int n, ImageMap im,
+                              BorderRec *__restrict__ out) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   int o = owner[k], cd = code[k];
@@ -304,7 +306,7 @@ __global__ void k_pack_border(const double4 *__restrict__ pos, const int *__rest
   if (im.shift[cd][1] != 0.0) r.y = r.y + im.shift[cd][1];
   if (im.shift[cd][2] != 0.0) r.z = r.z + im.shift[cd][2];
   BorderRec b;
-  b.pos = r; b.ts = ts[o]; b.tag = tag[o]; b.mol = mol[o]; b.code = cd; b.ucgp = ucgp[o]; b.pad = 0.0;
+  b.pos = r; b.ts = ts[o]; b.tag = tag[o]; b.mol = mol[o]; b.code = cd; b.ucgp = ucgp[o]; b.mask = mask[o]; b.pad = 0;
   out[k] = b;
 }
 __global__ void k_pack_forward(const double4 *__restrict__ pos, const int *__restrict__ ts, const double *__restrict__ ucgp,
@@ -462,7 +464,7 @@ __global__ void k_ghost_fill(double4 *__restrict__ pos, int *__restrict__ ts, do
                              int *__restrict__ tag, int *__restrict__ mol, int nlocal, int n, int nlimg,
                              const int *__restrict__ gsrc, int *__restrict__ slot_of_src, const int *__restrict__ lo,
                              const int *__restrict__ lc, ImageMap im, const BorderRec *__restrict__ recv,
-                             int *__restrict__ gcode) {
+                             int *__restrict__ gcode, const int *__restrict__ mask = nullptr, int *__restrict__ gmask = nullptr) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   int k, slot;
@@ -474,10 +476,11 @@ __global__ void k_ghost_fill(double4 *__restrict__ pos, int *__restrict__ ts, do
     pos[s] = source_pos(k, nlimg, pos, lo, lc, im, recv);
     ts[s] = ts[o];
     ucgp[s] = ucgp[o];
-    if (FULL) { tag[s] = tag[o]; mol[s] = mol[o]; gcode[slot] = lc[k]; }
+    if (FULL) { tag[s] = tag[o]; mol[s] = mol[o]; gcode[slot] = lc[k]; if (gmask) gmask[slot] = mask[o]; }
   } else if (FULL) {
     BorderRec b = recv[k - nlimg];
     pos[s] = b.pos; ts[s] = b.ts; ucgp[s] = b.ucgp; tag[s] = b.tag; mol[s] = b.mol; gcode[slot] = 32 + b.code;
+    if (gmask) gmask[slot] = b.mask;
   }
 }
 
@@ -1314,9 +1317,10 @@ extern "C" int ucgb200_neigh_build_finish(ucgb200_ctx *c) {
     UCG_LAUNCHED(c);
     k_sort_cells_kv<<<nblocks(ncells, 128), 128, 0, st>>>(c->ghost_key.p, c->ghost_src.p, c->gcell_start.p, ncells);
     UCG_LAUNCHED(c);
+    UCG_CHECK(c, c->ghost_mask.ensure(nsrc));
     k_ghost_fill<true><<<nblocks(nsrc, 256), 256, 0, st>>>(c->pos.p, c->ts.p, c->ucgp.p, c->tag.p, c->mol.p, nlocal, nsrc,
                                                            nlimg, c->ghost_src.p, c->slot_of_src.p, lo, lc, im, recv,
-                                                           c->ghost_code.p);
+                                                           c->ghost_code.p, c->mask.p, c->ghost_mask.p);
     UCG_LAUNCHED(c);
   }
   if (nlocal > 0) {
@@ -1541,7 +1545,7 @@ extern "C" int ucgb200_halo_pack_border(ucgb200_ctx *c, void *d_sendbuf) {
   if (h.nsend == 0) return 0;
   if (!d_sendbuf) return fail(c, "halo_pack_border: null buffer");
   ImageMap im = make_image_map(c);
-  k_pack_border<<<nblocks(h.nsend, 256), 256, 0, c->stream>>>(c->pos.p, c->ts.p, c->tag.p, c->mol.p, c->ucgp.p,
+  k_pack_border<<<nblocks(h.nsend, 256), 256, 0, c->stream>>>(c->pos.p, c->ts.p, c->tag.p, c->mol.p, c->ucgp.p, c->mask.p,
                                                              c->img_owner.p, c->img_code.p, h.nsend, im,
                                                              (BorderRec *)d_sendbuf);
   UCG_LAUNCHED(c);

@@ -156,7 +156,7 @@ struct ucgb200_ctx {
   ucg::Buf<int> stage_i;
   ucg::Buf<int> ts, ts_alt, mask, mask_alt, tag, tag_alt, mol, mol_alt, orig, orig_alt;
   // ghosts: sources = local periodic images + border records received from other bricks
-  ucg::Buf<int> ghost_owner, ghost_code, ghost_src, slot_of_src;
+  ucg::Buf<int> ghost_owner, ghost_code, ghost_src, slot_of_src, ghost_mask;   // ghost_mask: group bits of every ghost slot
   ucg::Buf<long long> ghost_key;
   ucg::Buf<int> img_counters, img_owner, img_code;   // [send lists by dest rank | local images]
   ucg::Buf<char> recv_border;

@@ -84,5 +84,8 @@ def oracle_forces(o, eflag=1, vflag=1, pair="ucgld"):
 
 
 def rel_err(a, b):
-    """max |a-b| / max |b|: the 'relative' of the north-star tolerances"""
+    """max |a-b| / max |b| over the WHOLE array: how the north star's "within 1e-6 relative" is read throughout the
+    suite (an error is measured against the largest force in the system, not against each site's own, which may be
+    arbitrarily close to zero).  tests/test_gpu_config_sizes.py additionally asserts the worst PER-SITE ratio over the
+    sites whose reference magnitude exceeds 1e-3 of the largest (per_site_rel)."""
     return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))

@@ -133,3 +133,69 @@ def test_resident_steps_against_oracle_at_config_size(pkg, fixtures, ncell, nste
     assert np.array_equal(got["ucgstate"][away], ref["ucgstate"][away])
     assert abs(th[0] - o.eng_vdwl()) <= (E_TOL if nsteps <= 4 else 1e-7) * abs(o.eng_vdwl())
     assert ctx.status()[0] == 0
+
+
+# ------------------------------------------------------------------ the other pair styles at 1 M sites
+def test_bethe_at_1M_against_oracle(pkg, fixtures):
+    """PairTable_UCG_Bethe::compute, one evaluation of the 1 000 188-site liquid against the oracle"""
+    liq = _liq(63)
+    ctx = decks.gpu_single_type(pkg, liq, fixtures)
+    ctx.neigh_build()
+    ctx.pair_bethe(1, 1, method=1, pseudo=0, prior=2)
+    o = decks.orc_single_type(liq, fixtures)
+    o.pair_bethe_config(1, 0, 2)
+    ref = decks.oracle_forces(o, pair="bethe")
+    got = ctx.atoms_download(["f", "ucgsoftmaxscores"])
+    e, vir = ctx.pair_energy_virial()
+    assert rel_err(got["f"], ref["f"]) <= F_TOL and per_site_rel(got["f"], ref["f"])[0] <= F_TOL
+    assert rel_err(got["ucgsoftmaxscores"], ref["ucgsoftmaxscores"]) <= F_TOL      # same option set as test_pair_bethe_single_evaluation
+    assert abs(e - o.eng_vdwl()) <= E_TOL * abs(o.eng_vdwl())
+    assert rel_err(vir, o.virial()) <= E_TOL
+    assert ctx.status()[0] == 0
+
+
+def _ref_available():
+    import ref_binding as rb
+    return rb.available()
+
+
+@pytest.mark.skipif(not _ref_available(), reason="oracle/_ref not built")
+def test_bethe_density_at_1M_against_reference(pkg, fixtures, tmp_path):
+    """BASELINE configs[2]'s pair style: pair_style table_ucg_bethe_density (three neighbor sweeps) on the 1 000 188-site
+    liquid against the reference's own (repaired, oracle/repair_bethe_density.py) source: forces, the posterior published
+    through atom->ucgp, energy and virial of one evaluation"""
+    import test_gpu_bethe_density as TB
+    liq = _liq(63)
+    ref, ctx = TB._setup(pkg, fixtures, tmp_path, liq)
+    ref.compute_once(1)
+    a = ref.get_atoms()
+    ctx.neigh_build()
+    ctx.pair_bethe_density(1, 1)
+    b = ctx.atoms_download(["f", "ucgp"])
+    e, vir = ctx.pair_energy_virial()
+    p0, _ = ctx.pair_bethe_density_priors()
+    assert 0.02 < p0.mean() < 0.98
+    assert rel_err(b["f"], a["f"]) <= F_TOL and per_site_rel(b["f"], a["f"])[0] <= F_TOL
+    assert np.abs(b["ucgp"] - a["ucgp"]).max() <= 1e-9
+    assert abs(e - ref.eng_vdwl()) <= E_TOL * abs(ref.eng_vdwl())
+    assert rel_err(vir, ref.virial()[0]) <= E_TOL
+    assert ctx.status()[0] == 0
+
+
+@pytest.mark.skipif(not _ref_available(), reason="oracle/_ref not built")
+def test_rleucg_at_1M_against_reference(pkg, fixtures, tmp_path):
+    """BASELINE configs[3]'s pair style: pair_style table_rleucg_interface on the 1 000 188-site liquid against the
+    reference's own source (eflag on, quirk Q16)"""
+    import test_gpu_rleucg as TR
+    liq = _liq(63)
+    ref, ctx = TR._setup(pkg, fixtures, tmp_path, liq)
+    ref.compute_once(1)
+    a = ref.get_atoms()
+    ctx.neigh_build()
+    ctx.pair_rleucg(1, 1)
+    b = ctx.atoms_download(["f"])
+    e, vir = ctx.pair_energy_virial()
+    assert rel_err(b["f"], a["f"]) <= F_TOL and per_site_rel(b["f"], a["f"])[0] <= F_TOL
+    assert abs(e - ref.eng_vdwl()) <= E_TOL * abs(ref.eng_vdwl())
+    assert rel_err(vir, ref.virial()[0]) <= E_TOL
+    assert ctx.status()[0] == 0
