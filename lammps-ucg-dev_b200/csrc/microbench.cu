@@ -66,6 +66,49 @@ __global__ void __launch_bounds__(BS) k_lds(const double2 *__restrict__ table, c
   out[t] = a0 + a1 + a2 + a3;
 }
 
+// Conflict-free schedule of the same reads ("rejected on paper"; measured here).  In
+// instruction k the l-th lane of a quarter-warp reads the slot of its 96-byte window (slots w .. w+5, w = 3*it) that
+// lies in bank group (k + l) mod 8: eight instructions instead of six, two of them idle per lane, every wavefront
+// conflict-free.  The loaded values arrive rotated by r = (w - l) mod 8 and are routed back to window order with a
+// three-stage barrel rotation of the eight double2 registers (96 32-bit selects per visit).
+__global__ void __launch_bounds__(BS) k_lds_rotated(const double2 *__restrict__ table, const unsigned short *__restrict__ its,
+                                                    int per_thread, double *__restrict__ out) {
+  extern __shared__ double2 s_tab[];
+  for (int k = threadIdx.x; k < TABLEN * W; k += BS) s_tab[k] = table[k];
+  __syncthreads();
+  const size_t t = (size_t)blockIdx.x * BS + threadIdx.x;
+  const size_t nthreads = (size_t)gridDim.x * BS;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  const int l = threadIdx.x & 7;
+  for (int n = 0; n < per_thread; n++) {
+    const int it = its[(size_t)n * nthreads + t];
+    const int w = it * W;
+    double2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int o = (k + l - w) & 7;                 // window offset whose bank group is (k + l) mod 8
+      v[k] = o < 6 ? s_tab[w + o] : make_double2(0.0, 0.0);
+    }
+    // v[k] holds window offset (k - r) mod 8, r = (w - l) mod 8: rotate left by r so that x[o] = window offset o
+    const int r = (w - l) & 7;
+#pragma unroll
+    for (int stage = 0; stage < 3; stage++) {
+      const int sh = 1 << stage;
+      const bool take = (r & sh) != 0;          // selects, not a divergent branch
+      double2 u[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        u[k].x = take ? v[(k + sh) & 7].x : v[k].x;
+        u[k].y = take ? v[(k + sh) & 7].y : v[k].y;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) v[k] = u[k];
+    }
+    a0 += v[0].x + v[3].y; a1 += v[1].x + v[4].y; a2 += v[2].x + v[5].y; a3 += v[0].y + v[1].y + v[2].y + v[3].x + v[4].x + v[5].x;
+  }
+  out[t] = a0 + a1 + a2 + a3;
+}
+
 // ------------------------------------------------------------------ FP64 arithmetic of one launch
 // per in-cutoff visit: dx,dy,dz (3 DADD), rsq (3 DMUL 2 DADD), index (1 DADD 1 DMUL, cvt), rsq_it (I2F, DMUL, DADD),
 // frac (DADD DMUL), 6 x (DADD + DFMA), bj (DADD), A B FA FB (4 x (DMUL + DFMA)), accA accB (2 DADD),
@@ -236,6 +279,9 @@ int main(int argc, char **argv) {
   printf(fmt, "lds_ordered", ms, visits, "in-cutoff visits", grid, BS, "same reads, lanes on consecutive rows: no bank-group conflicts");
   ms = time_ms([&] { k_lds<2><<<grid, BS, TABLE_BYTES>>>(d_tab, d_its, per_visit, d_out); });
   printf(fmt, "lds_broadcast", ms, visits, "in-cutoff visits", grid, BS, "same reads, one row per warp");
+  CK(cudaFuncSetAttribute(k_lds_rotated, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TABLE_BYTES));
+  ms = time_ms([&] { k_lds_rotated<<<grid, BS, TABLE_BYTES>>>(d_tab, d_its, per_visit, d_out); });
+  printf(fmt, "lds_rotated", ms, visits, "in-cutoff visits", grid, BS, "conflict-free rotated schedule: 8 x LDS.128 + 3-stage register rotation (96 selects) per visit");
   ms = time_ms([&] { k_fp64<<<grid, BS>>>(per_visit, innersq, invdelta, delta, d_out); });
   printf(fmt, "fp64", ms, visits, "in-cutoff visits", grid, BS, "FP64 arithmetic of a visit on register operands");
   ms = time_ms([&] { k_fp64<<<grid, BS>>>(per_pair, innersq, invdelta, delta, d_out); });
