@@ -798,6 +798,16 @@ k_build_rows_tiled(const double4 *__restrict__ pos, const int *__restrict__ ts, 
   }
 }
 
+// displacement level of a skin entry from its squared distance: the number of thresholds ((cut + k skin / 8)^2, rounded
+// up) it has reached, k = 1..7
+struct LevelThresholds { float t[7]; };
+__device__ __forceinline__ int level_of(float r2, const LevelThresholds &lv) {
+  int n = 0;
+#pragma unroll
+  for (int k = 0; k < 7; k++) n += (r2 >= lv.t[k]);
+  return n;
+}
+
 // Single-precision prefilter variant of k_build_rows_tiled for one actual type (one cutoff pair): the SAME rows in the
 // SAME order, decided exactly.  Candidates are staged as float4 {x - ox, y - oy, z - oz, index} relative to the centre
 // of the CTA's cell (16 bytes instead of 40, one LDS.128 per test), the squared distance is formed in FP32 and decides
@@ -812,7 +822,7 @@ __global__ void __launch_bounds__(TILE_BS)
 k_build_rows_tiled_f32(const double4 *__restrict__ pos, int nlocal, Grid g, const int *__restrict__ ostart,
                        const int *__restrict__ gstart, double cutneighsq, double cutsq, float band,
                        int *__restrict__ neigh, int stride, int *__restrict__ numneigh, int *__restrict__ flags,
-                       int cap, uint4 *__restrict__ levcnt, double skin, int cull) {
+                       int cap, uint4 *__restrict__ levcnt, double skin, int cull, LevelThresholds lvl) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   float4 *s_c = reinterpret_cast<float4 *>(s_raw);                       // [TILE_CAP_F32] staged candidates
   int *s_inner = reinterpret_cast<int *>(s_c + TILE_CAP_F32);            // [warps][stride] inner entries found in this chunk
@@ -928,7 +938,10 @@ k_build_rows_tiled_f32(const double4 *__restrict__ pos, int nlocal, Grid g, cons
         if (hit) {
           // both kinds go to shared memory; the row is written in one dense pass below
           const int p = inner ? cnt_in + __popc(m_in & lt) : cnt_out + __popc(m_out & lt);
-          if (p < stride) (inner ? inner_buf - cnt_in0 : outer)[p] = j;
+          if (p < stride) {
+            (inner ? inner_buf - cnt_in0 : outer)[p] = j;
+            if (!inner) okey[p] = __float_as_uint(r2);     // for the displacement level of this skin entry
+          }
         }
         cnt_in += __popc(m_in);
         cnt_out += __popc(m_out);
@@ -942,30 +955,30 @@ k_build_rows_tiled_f32(const double4 *__restrict__ pos, int nlocal, Grid g, cons
         unsigned lc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (total <= stride) {
           if (single) {
-            // sort keys of the skin entries from their exact distances (same formula as k_build_rows_tiled)
-            for (int k = lane; k < cnt_out; k += 32) {
-              const double4 rj = pos[outer[k]];
-              const double rsq = rsq_exact(ri.x - rj.x, ri.y - rj.y, ri.z - rj.z);
-              const double beyond = (sqrt(rsq) - rcut) * (1.0 - 1e-9) * inv_skin;
-              okey[k] = (unsigned)fmin(fmax(beyond, 0.0) * 134217728.0, 134217727.0);
-            }
-            __syncwarp();
-            for (int k = lane; k < ((cnt_out + 31) & ~31); k += 32) {
-              const bool have = k < cnt_out;
-              const unsigned key = have ? okey[k] : 0xffffffffu;
-              int rank = 0;
-              if (have)
-                for (int m = 0; m < cnt_out; m++) {
-                  const unsigned km = okey[m];
-                  rank += (km < key) || (km == key && m < k);
-                }
-              if (have) row[rowslot(cnt_in + rank)] = outer[k];
-              const unsigned lev = have ? min(key >> 24, 7u) : 8u;
+            // The pair kernels only need the skin entries grouped by displacement level (the eighth of the skin the
+            // pair sat in at build time), not sorted by distance: a counting sort over 8 levels, stable in candidate
+            // order.  The level comes from the FP32 squared distance kept with the hit, pushed DOWN by the error band
+            // (a lower level is visited earlier: always safe).  No FP64 gather, no square root, no rank sort.
+            int cntL[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int kb = 0; kb < cnt_out; kb += 32) {
+              const int k = kb + lane;
+              const int lev = k < cnt_out ? level_of(__uint_as_float(okey[k]) - band, lvl) : 8;
 #pragma unroll
-              for (int L = 0; L < 8; L++) lc[L] += __popc(__ballot_sync(0xffffffffu, lev <= (unsigned)L));
+              for (int L = 0; L < 8; L++) cntL[L] += __popc(__ballot_sync(0xffffffffu, lev == L));
             }
+            int off[8], running = cnt_in;
 #pragma unroll
-            for (int L = 0; L < 8; L++) lc[L] += cnt_in;
+            for (int L = 0; L < 8; L++) { off[L] = running; running += cntL[L]; lc[L] = running; }
+            for (int kb = 0; kb < cnt_out; kb += 32) {
+              const int k = kb + lane;
+              const int lev = k < cnt_out ? level_of(__uint_as_float(okey[k]) - band, lvl) : 8;
+#pragma unroll
+              for (int L = 0; L < 8; L++) {
+                const unsigned m = __ballot_sync(0xffffffffu, lev == L);
+                if (lev == L) row[rowslot(off[L] + __popc(m & lt))] = outer[k];
+                off[L] += __popc(m);
+              }
+            }
           } else {
             for (int k = lane; k < cnt_out; k += 32) row[rowslot(cnt_in + k)] = outer[k];
 #pragma unroll
@@ -1105,12 +1118,23 @@ static int build_rows(ucgb200_ctx *c) {
       for (int d = 0; d < 3; d++) edge = std::max(edge, 1.0 / c->grid.inv[d]);
       const double E = 1.5 * edge + 1e-6 * edge;
       const float band = (float)(4.0 * (6.0 * 1.7320508 * E * rc + 4.0 * rc * rc) * 5.9604644775390625e-08);
+      // level k starts where the pair sits k eighths of the skin beyond the cutoff (the pair kernels visit an entry of
+      // level l once 2 sqrt(maxdisp) has reached l eighths): thresholds rounded UP, so a level is never overstated
+      LevelThresholds lvl;
+      {
+        const double rcut = std::sqrt(cs);
+        for (int k = 1; k <= 7; k++) {
+          const double r = rcut + k * c->skin / 8.0;
+          lvl.t[k - 1] = std::nextafter((float)(r * r * (1.0 + 1e-6)), 1e30f);
+        }
+      }
       int cap32 = getenv("UCGB200_TILE_CAP") ? atoi(getenv("UCGB200_TILE_CAP")) : TILE_CAP_F32;
       cap32 = (std::min(std::max(cap32, 32), TILE_CAP_F32) / 32) * 32;   // whole passes of 32 candidates
       k_build_rows_tiled_f32<<<ncell_owned, TILE_BS, smem, c->stream>>>(
           c->pos.p, nlocal, c->grid, c->cell_start.p, c->gcell_start.p, cn, cs, band, c->neigh.p, c->neigh_stride,
           c->numneigh.p, c->d_flags.p, cap32, c->levcnt.p, c->skin,
-          (c->periodic[0] && c->periodic[1] && c->periodic[2] && !(getenv("UCGB200_BUILD_CULL") && atoi(getenv("UCGB200_BUILD_CULL")) == 0)) ? 1 : 0);
+          (c->periodic[0] && c->periodic[1] && c->periodic[2] && !(getenv("UCGB200_BUILD_CULL") && atoi(getenv("UCGB200_BUILD_CULL")) == 0)) ? 1 : 0,
+          lvl);
     } else if (tiled) {
       const int ncell_owned = c->grid.ninner[0] * c->grid.ninner[1] * c->grid.ninner[2];
       const size_t smem = (size_t)TILE_CAP * (sizeof(double2) + sizeof(double) + 2 * sizeof(int)) +
