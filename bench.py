@@ -155,10 +155,11 @@ def run_reference(args):
     import multiprocessing as mp
     t0 = time.perf_counter()
     # the truly serial figure first (one core, nothing else running): cpu_baseline.serial_1M
-    serial = _replica((ncell, max(5, min(steps, 8)), 1))
     if cores == 1:
+        serial = _replica((ncell, steps, warm))
         rs = [serial]
     else:
+        serial = _replica((ncell, max(5, min(steps, 8)), 1))
         with mp.get_context("spawn").Pool(cores) as pool:
             rs = pool.map(_replica, [(ncell, steps, warm)] * cores)
     wall = time.perf_counter() - t0

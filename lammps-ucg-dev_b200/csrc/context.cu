@@ -621,7 +621,9 @@ int ucg_host_out_queue(ucgb200_ctx *c, unsigned mask) {
   const size_t n = nlocal;
   if (!c->stream_dl) UCG_CHECK(c, cudaStreamCreateWithFlags(&c->stream_dl, cudaStreamNonBlocking));
   if (!c->ev_dl) UCG_CHECK(c, cudaEventCreateWithFlags(&c->ev_dl, cudaEventDisableTiming));
-  if (c->stage_d.cap < 16 * n + 64 || c->stage_i.cap < 6 * n + 64) return fail(c, "step_host: staging not sized (upload first)");
+  // the brick's population may have grown during the step (migration): cudaFree inside ensure() waits for copies in flight
+  UCG_CHECK(c, c->stage_d.ensure(16 * n + 64));
+  UCG_CHECK(c, c->stage_i.ensure(6 * n + 64));
   double *sd = c->stage_d.p;
   int *si = c->stage_i.p;
   const int *orig = c->orig.p;
