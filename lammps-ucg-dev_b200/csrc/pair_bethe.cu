@@ -53,6 +53,7 @@ struct BetheArgs {
   double2 *scores;
   double *partials;
   ErrWord *err;
+  double *eatom, *vatom;   // per-atom tallies (EV launches only), nullptr: not asked for
   FastTable ft;   // shared-memory table path (W > 0)
   GatherTex gt;   // neighbor gathers through the texture pipe (0 = plain loads)
 };
@@ -188,12 +189,13 @@ __global__ void __launch_bounds__(BS) k_pair_bethe(BetheArgs p) {
     else
       p.scores[i] = make_double2(-tyi.mu0 * p.inv_kT, 0.0);
     if (EV) evacc[0] += 0.5 * eacc;
+    if (EV && p.eatom) p.eatom[i] = 0.5 * eacc;          // this site's half of every pair it is in (ev_tally, eflag_atom)
   }
   if (EV) {
 #pragma unroll
     for (int k = 0; k < 6; k++) {
       double v = group_sum<LPA>(vir[k]);
-      if (active && sub == 0) evacc[1 + k] += 0.5 * v;
+      if (active && sub == 0) { evacc[1 + k] += 0.5 * v; if (p.vatom) p.vatom[6 * (size_t)i + k] = 0.5 * v; }
     }
   }
   }   // persistent loop over site groups
@@ -220,8 +222,13 @@ extern "C" int ucgb200_pair_bethe(ucgb200_ctx *c, int eflag, int vflag, int meth
     return 0;
   }
   const bool ev = eflag || vflag;
+  // LAMMPS flag bits: eflag & 2 = ENERGY_ATOM, vflag & 4 = VIRIAL_ATOM (ucgb200_pair_peratom fetches them)
+  const bool want_eatom = (eflag & 2) != 0, want_vatom = (vflag & 4) != 0;
+  c->eatom_valid = c->vatom_valid = false;
   constexpr int LPA = 8, BS = 256;
   BetheArgs a{};
+  if (want_eatom) { UCG_CHECK(c, c->d_eatom.ensure((size_t)c->nlocal + 8)); a.eatom = c->d_eatom.p; }
+  if (want_vatom) { UCG_CHECK(c, c->d_vatom.ensure(6 * (size_t)c->nlocal + 8)); a.vatom = c->d_vatom.p; }
   a.pos = c->pos.p; a.ts = c->ts.p; a.tag = c->tag.p; a.ucgp = c->ucgp.p; a.nlocal = c->nlocal;
   a.neigh = c->neigh.p; a.stride = c->neigh_stride; a.numneigh = c->numneigh.p;
   a.pinfo = c->d_pairinfo.p; a.tinfo = c->d_typeinfo.p; a.na = c->n_actual + 1; a.tables = c->d_tables.p;
@@ -265,6 +272,8 @@ extern "C" int ucgb200_pair_bethe(ucgb200_ctx *c, int eflag, int vflag, int meth
   if (ev) {
     if ((rc = reduce_partials(c, nblk, 7, 0))) return rc;
     c->ev_valid = true;
+    c->eatom_valid = want_eatom;
+    c->vatom_valid = want_vatom;
   }
   return 0;
 }

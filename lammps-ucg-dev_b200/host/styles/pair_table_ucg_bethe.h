@@ -19,7 +19,6 @@ class PairTable_UCG_Bethe : public PairTable_UCGLD {
   PairTable_UCG_Bethe(class LAMMPS *);
   void settings(int, char **) override;
   bool ucg_deck(ucgb200_deck &deck) override;
-  bool peratom_supported() const override { return false; }
   enum { MF, BETHE };
   enum { CHEMICAL_POTENTIAL, CHEMICAL_POTENTIAL_NOISE, UCGL };
 

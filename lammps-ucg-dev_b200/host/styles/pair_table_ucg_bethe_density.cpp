@@ -157,6 +157,8 @@ bool PairTable_UCG_Bethe_Density::ucg_deck(ucgb200_deck &deck) {
 
 void PairTable_UCG_Bethe_Density::compute(int eflag, int vflag) {
   ev_init(eflag, vflag);
+  if (eflag_atom || vflag_atom)   // asked for, say so instead of leaving zeros in eatom / vatom
+    error->all(FLERR, "ucg-b200: per-atom energy / virial is implemented for pair_style table_ucgld and table_ucg_bethe only");
   configure_device();
   const int nlocal = atom->nlocal;
   dev->upload(lmp, UCGB200_F_X | UCGB200_F_UCGL | UCGB200_F_UCGSTATE | UCGB200_F_UCGP);

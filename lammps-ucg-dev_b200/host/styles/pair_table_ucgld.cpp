@@ -187,7 +187,7 @@ void PairTable_UCGLD::compute(int eflag, int vflag) {
   // per-atom tallies (compute pe/atom, stress/atom): LAMMPS' own flag bits go down to the device
   const bool want_peratom = eflag_atom || vflag_atom;
   if (want_peratom && !peratom_supported())
-    error->all(FLERR, "ucg-b200: per-atom energy / virial is implemented for pair_style table_ucgld only");
+    error->all(FLERR, "ucg-b200: per-atom energy / virial is implemented for pair_style table_ucgld and table_ucg_bethe only");
   device_compute(ev | (eflag_atom ? 2 : 0), ev | (vflag_atom ? 4 : 0));
   if (want_peratom) {
     std::vector<double> ea(eflag_atom ? (size_t)nlocal : 0), va(vflag_atom ? 6 * (size_t)nlocal : 0);

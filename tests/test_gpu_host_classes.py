@@ -585,9 +585,29 @@ def test_per_atom_energy_and_virial(pkg, fixtures, tabstyle, tablength):
     assert rel_err(vb.sum(0), Wb[0]) <= 1e-10          # the drop-in's global virial is the per-pair tally (Q3)
     assert rel_err(va.sum(0), Wa[1]) <= 1e-10
     assert abs(Eb - Ea) <= 1e-8 * abs(Ea)
-    # the bethe style does not carry per-atom tallies: asked for, it must say so instead of returning zeros
-    s = rb.HostSim.single_type(liq, fixtures["table4096"], fixtures["state"], pair="table_ucg_bethe",
-                               extra="method bethe pseudo yes prior ucgl")
-    s.command("fix 0 all ttarget/stub 1.0")
-    with pytest.raises(RuntimeError, match="per-atom energy / virial is implemented for pair_style table_ucgld only"):
+    # the same through pair_style table_ucg_bethe
+    out = []
+    for cls in (rb.RefSim, rb.HostSim):
+        s = cls.single_type(liq, fixtures["table4096"], fixtures["state"], pair="table_ucg_bethe",
+                            extra="method bethe pseudo yes prior ucgl")
+        s.command("fix 0 all ttarget/stub 1.0")
+        s.compute_once(3)
+        out.append(s.pair_peratom() + (s.eng_vdwl(),))
+    (ea, va, Ea), (eb, vb, Eb) = out
+    assert rel_err(eb, ea) <= 1e-8 and rel_err(vb, va) <= 1e-8
+    assert abs(eb.sum() - Eb) <= 1e-10 * abs(Eb) and abs(Eb - Ea) <= 1e-8 * abs(Ea)
+
+
+def test_per_atom_tallies_refused_by_the_density_styles(pkg, fixtures, tmp_path):
+    """table_rleucg_interface / table_ucg_bethe_density carry no per-atom tallies on the device: asked for them, the
+    drop-in classes say so instead of leaving zeros in Pair::eatom / Pair::vatom"""
+    liq = _liq(5)
+    sf = tmp_path / "rle.conf"
+    sf.write_text("1 2\n2 density use_entropy\n12.0 1.5\n0.3\n")
+    t = fixtures["table4096"]
+    lines = ["newton off", "neighbor 0.3 bin", "timestep 0.002", f"pair_style table_rleucg_interface linear 4096 {sf}",
+             f"pair_coeff 1 1 {t} UCG_00 2.5", f"pair_coeff 1 2 {t} UCG_01 2.5", f"pair_coeff 2 2 {t} UCG_11 2.5",
+             "fix 0 all ttarget/stub 1.0"]
+    s = _deck(rb.HostSim, liq, lines)
+    with pytest.raises(RuntimeError, match="per-atom energy / virial is implemented for pair_style table_ucgld and table_ucg_bethe only"):
         s.compute_once(3)
