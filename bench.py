@@ -169,6 +169,9 @@ def run_reference(args):
     cfg = workload_config(ncell, 1)
     cfg["reference_arm"] = (f"{cores} concurrent serial runs of the whole {r0['sites']}-site liquid (one per host core), "
                             f"{r0['steps']} timed steps each after setup and {warm} warm-up steps")
+    if args.gpus > 1:
+        cfg["reference_arm"] += (f"; launched beside the {args.gpus}-GPU arm ({args.gpus} x {r0['sites']} sites, weak scaling): the host has the "
+                                 "same cores whatever N is, so this is the same CPU figure as at N = 1 (one brick's liquid per core)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": r0["steps"], "steps_requested": args.steps, "warmup": warm, "ms_per_step": 1e3 * slowest / r0["steps"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
