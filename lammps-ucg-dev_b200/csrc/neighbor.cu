@@ -959,6 +959,19 @@ k_build_rows_tiled_f32(const double4 *__restrict__ pos, int nlocal, Grid g, cons
             // pair sat in at build time), not sorted by distance: a counting sort over 8 levels, stable in candidate
             // order.  The level comes from the FP32 squared distance kept with the hit, pushed DOWN by the error band
             // (a lower level is visited earlier: always safe).  No FP64 gather, no square root, no rank sort.
+            if (cnt_out <= 32) {
+              // the usual case (~23 skin entries): one entry per lane, every ballot taken once
+              const int lev = lane < cnt_out ? level_of(__uint_as_float(okey[lane]) - band, lvl) : 8;
+              int running = cnt_in, mypos = 0;
+#pragma unroll
+              for (int L = 0; L < 8; L++) {
+                const unsigned m = __ballot_sync(0xffffffffu, lev == L);
+                if (lev == L) mypos = running + __popc(m & lt);
+                running += __popc(m);
+                lc[L] = running;
+              }
+              if (lev < 8) row[rowslot(mypos)] = outer[lane];
+            } else {
             int cntL[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             for (int kb = 0; kb < cnt_out; kb += 32) {
               const int k = kb + lane;
@@ -978,6 +991,7 @@ k_build_rows_tiled_f32(const double4 *__restrict__ pos, int nlocal, Grid g, cons
                 if (lev == L) row[rowslot(off[L] + __popc(m & lt))] = outer[k];
                 off[L] += __popc(m);
               }
+            }
             }
           } else {
             for (int k = lane; k < cnt_out; k += 32) row[rowslot(cnt_in + k)] = outer[k];
