@@ -918,13 +918,15 @@ k_build_rows_tiled_f32(const double4 *__restrict__ pos, int nlocal, Grid g, cons
         __syncwarp();
       }
       const int cnt_in0 = cnt_in;
+      const unsigned sa_inner = (unsigned)__cvta_generic_to_shared(inner_buf) - 4u * (unsigned)cnt_in0;
+      const unsigned sa_outer = (unsigned)__cvta_generic_to_shared(outer), sa_okey = (unsigned)__cvta_generic_to_shared(okey);
       for (int base = 0; base < cn32; base += 32) {
         const float4 cj = s_c[base + lane];
         const int j = __float_as_int(cj.w);
         const float dx = xf - cj.x, dy = yf - cj.y, dz = zf - cj.z;
         const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
         bool hit = r2 <= cnf, inner = r2 < csf;
-        if (fabsf(r2 - cnf) <= band || fabsf(r2 - csf) <= band) {
+        if ((fabsf(r2 - cnf) <= band) | (fabsf(r2 - csf) <= band)) {     // one branch (no short-circuit)
           // too close to a threshold for FP32: the reference's arithmetic on the FP64 records
           const double4 rj = pos[j];
           const double rsq = rsq_exact(ri.x - rj.x, ri.y - rj.y, ri.z - rj.z);
@@ -939,8 +941,11 @@ k_build_rows_tiled_f32(const double4 *__restrict__ pos, int nlocal, Grid g, cons
           // both kinds go to shared memory; the row is written in one dense pass below
           const int p = inner ? cnt_in + __popc(m_in & lt) : cnt_out + __popc(m_out & lt);
           if (p < stride) {
-            (inner ? inner_buf - cnt_in0 : outer)[p] = j;
-            if (!inner) okey[p] = __float_as_uint(r2);     // for the displacement level of this skin entry
+            // 32-bit shared-window addresses taken once per site: the generic-pointer form makes the compiler rebuild
+            // the window base (S2UR SR_CgaCtaId, ULEA ...) inside this branch on every pass
+            const unsigned a = (inner ? sa_inner : sa_outer) + 4u * (unsigned)p;
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(j) : "memory");
+            if (!inner) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa_okey + 4u * (unsigned)p), "r"(__float_as_uint(r2)) : "memory");   // for the displacement level of this skin entry
           }
         }
         cnt_in += __popc(m_in);
