@@ -315,7 +315,11 @@ int ucgb200_status(ucgb200_ctx *ctx, int *code, int *tag_i, int *tag_j, double *
 /* the same word WITHOUT clearing it (ucgb200_status clears a non-zero word once it has been read): lets a caller test
  * the code first and fetch the pair's tags and distance with ucgb200_status afterwards */
 int ucgb200_status_peek(ucgb200_ctx *ctx, int *code, int *tag_i, int *tag_j, double *rsq);
-/* per-kernel-class CUDA-event timers (ms since last reset): pair, neigh, comm, modify */
+/* per-stage CUDA-event timers of the resident loop (ms since the last reset): pair, neigh (decide + rebuild), comm
+ * (ghost refresh / halo), modify (fix stages).  enable: -1 read only; 0 off; 1 on, blocking (one event synchronisation
+ * per stage: the loop loses its speculative pair launch while it is being timed); 2 = 1 + reset; 3 on + reset,
+ * NON-blocking: event pairs from a ring, resolved when the totals are read, so the loop keeps the schedule it has when
+ * it is not being timed.  ucgb200_last_pair_ms (pair kernel alone) needs any of the "on" modes. */
 int ucgb200_timers(ucgb200_ctx *ctx, int enable, double out_ms[4], long long out_launches[4]);
 /* duration of the last pair kernel launch in ms (events on the context stream) */
 int ucgb200_last_pair_ms(ucgb200_ctx *ctx, double *ms);

@@ -42,6 +42,7 @@ extern "C" int ucgb200_destroy(ucgb200_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   ucgb200_comm_destroy(c);
+  for (auto &e : c->stage_ring) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
   if (c->stream_dl) cudaStreamDestroy(c->stream_dl);
   if (c->ev_dl) cudaEventDestroy(c->ev_dl);
   for (auto *t : {&c->tex_pos[0], &c->tex_pos[1], &c->tex_sbits, &c->tex_ts[0], &c->tex_ts[1]}) if (t->tex) cudaDestroyTextureObject(t->tex);

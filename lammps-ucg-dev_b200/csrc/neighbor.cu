@@ -1222,20 +1222,14 @@ struct BuildTrace {
   }
 };
 
-struct BuildTimer {
+struct BuildTimer {     // neighbor stage (slot 1) of ucgb200_timers: blocking or from the asynchronous event ring
+  ucg::StageTimer t;
   ucgb200_ctx *c;
   long long l0;
-  explicit BuildTimer(ucgb200_ctx *ctx) : c(ctx), l0(ctx->launches) {
-    if (c->timers_on) cudaEventRecord(c->ev_a, c->stream);
-  }
+  explicit BuildTimer(ucgb200_ctx *ctx) : t(ctx, 1), c(ctx), l0(ctx->launches) {}
   void stop() {
-    if (!c->timers_on) return;
-    cudaEventRecord(c->ev_b, c->stream);
-    cudaEventSynchronize(c->ev_b);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
-    c->t_ms[1] += ms;
-    c->t_launch[1] += c->launches - l0;
+    if (c->timers_on) c->t_launch[1] += c->launches - l0;
+    t.stop();
   }
 };
 

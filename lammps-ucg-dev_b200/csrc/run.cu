@@ -90,24 +90,6 @@ static int do_decide(ucgb200_ctx *c, bool prechecked, int *flag) {
   return prechecked ? ucg_neigh_decide_prechecked(c, flag) : ucgb200_neigh_decide(c, flag);
 }
 
-struct StageTimer {
-  ucgb200_ctx *c;
-  int slot;
-  long long l0;
-  StageTimer(ucgb200_ctx *ctx, int s) : c(ctx), slot(s), l0(ctx->launches) {
-    if (c->timers_on) cudaEventRecord(c->ev_a, c->stream);
-  }
-  void stop() {
-    if (!c->timers_on) return;
-    cudaEventRecord(c->ev_b, c->stream);
-    cudaEventSynchronize(c->ev_b);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
-    c->t_ms[slot] += ms;
-    if (slot != 1) c->t_launch[slot] += c->launches - l0;
-  }
-};
-
 // the three post_force stages in the deck's fix definition order (ucgb200_deck::post_force_order; 0 = 123)
 int ucg_post_force_order(const ucgb200_deck &d, int order[3]) {
   int code = d.post_force_order ? d.post_force_order : 123;
@@ -226,7 +208,7 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
     int flag = 0;
     bool pair_in_flight = false, forward_done = false;
     const bool cluster_due = d.cluster_freq > 0 && c->cluster.set && c->cluster.next_reneighbor == c->ntimestep;
-    if (speculative && pre_integrated && c->list_valid && !cluster_due && !c->timers_on) {
+    if (speculative && pre_integrated && c->list_valid && !cluster_due && (!c->timers_on || c->timers_async)) {
       // Neighbor::decide without a pipeline bubble: the flag (and the largest squared displacement since the build) of
       // this step were computed by the previous step's fused tail.  Their read-back is queued, and — when the last known
       // displacement says a rebuild is still some steps away — so are the ghost refresh and the pair kernel of this
@@ -238,6 +220,7 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
       // halo / compute overlap: the interior sites (no neighbor from another brick) are evaluated between the push of
       // this brick's records and the wait for the peers', the boundary sites after the unpack
       const bool split = bricks && calm && !ev && d.pair_style == 0 && ucg_mb_p2p_active(c) && ucg_pair_can_split(c);
+      StageTimer tf(c, 2);
       if (split) {
         if ((rc = ucg_mb_forward_begin(c))) return rc;
         // interior rows only meet sites of this brick (and their local periodic images): the displacement bound of
@@ -254,15 +237,22 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
         if ((rc = ucg_mb_forward_reduce(c, true))) return rc;
         forward_done = true;
       }
+      tf.stop();
       UCG_CHECK(c, cudaMemcpyAsync(c->h_flags, c->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       UCG_CHECK(c, cudaMemcpyAsync(c->h_flags + 6, c->d_maxdisp.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
       if ((rc = queue_error_readback(c))) return rc;
       UCG_CHECK(c, cudaEventRecord(c->ev_flag, c->stream));
       c->maxdisp_valid = true;
       if (calm) {
-        if (!forward_done && (rc = do_forward(c))) return rc;
+        if (!forward_done) {
+          StageTimer t2(c, 2);
+          if ((rc = do_forward(c))) return rc;
+          t2.stop();
+        }
         if (split) c->pair_part = 1;
+        StageTimer t0(c, 0);
         if ((rc = pair_compute(c, ev))) return rc;
+        t0.stop();
         pair_in_flight = true;
       }
       UCG_CHECK(c, cudaEventSynchronize(c->ev_flag));
@@ -376,13 +366,15 @@ extern "C" int ucgb200_thermo(ucgb200_ctx *c, double out[16]) {
 
 extern "C" int ucgb200_timers(ucgb200_ctx *c, int enable, double out_ms[4], long long out_launches[4]) {
   if (!c) return -1;
+  stage_resolve_all(c);
   if (out_ms) for (int k = 0; k < 4; k++) out_ms[k] = c->t_ms[k];
   if (out_launches) for (int k = 0; k < 4; k++) out_launches[k] = c->t_launch[k];
   if (enable >= 0) {
-    if (enable != (int)c->timers_on || enable == 2) {
+    if (enable != (int)c->timers_on || enable >= 2) {
       for (int k = 0; k < 4; k++) { c->t_ms[k] = 0; c->t_launch[k] = 0; }
     }
     c->timers_on = enable != 0;
+    c->timers_async = enable == 3;
   }
   return 0;
 }

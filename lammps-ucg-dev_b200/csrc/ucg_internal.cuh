@@ -218,6 +218,12 @@ struct ucgb200_ctx {
   double last_maxdisp = -1.0;      // largest squared displacement since the build, as last read back (< 0: unknown)
   double t_ms[4] = {0, 0, 0, 0};
   long long t_launch[4] = {0, 0, 0, 0};
+  // non-blocking stage timing (ucgb200_timers(ctx, 3, ...)): event pairs from a ring, resolved when the ring wraps or
+  // when the totals are read, so that the loop being timed keeps its asynchronous (speculative) schedule
+  bool timers_async = false;
+  struct StageEv { cudaEvent_t a = nullptr, b = nullptr; int slot = -1; };
+  std::vector<StageEv> stage_ring;
+  size_t stage_next = 0;
   bool pair_timed = false;
 
   // fix cluster_switch (cluster_switch.cu): per-molecule arrays are indexed by molecule id
@@ -288,6 +294,51 @@ namespace ucg {
       return -2;                                                                          \
     }                                                                                     \
   } while (0)
+
+// Stage timer shared by run.cu and neighbor.cu.  Blocking mode (timers_on, !timers_async): one event synchronisation
+// per stage.  Async mode: the pair of events is taken from a ring and its elapsed time added later.
+inline void stage_resolve(ucgb200_ctx *c, ucgb200_ctx::StageEv &e) {
+  if (e.slot < 0) return;
+  cudaEventSynchronize(e.b);
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) c->t_ms[e.slot] += ms;
+  e.slot = -1;
+}
+inline void stage_resolve_all(ucgb200_ctx *c) {
+  for (auto &e : c->stage_ring) stage_resolve(c, e);
+}
+struct StageTimer {
+  ucgb200_ctx *c;
+  int slot;
+  long long l0;
+  ucgb200_ctx::StageEv *ev = nullptr;
+  StageTimer(ucgb200_ctx *ctx, int s) : c(ctx), slot(s), l0(ctx->launches) {
+    if (!c->timers_on) return;
+    if (c->timers_async) {
+      if (c->stage_ring.empty()) c->stage_ring.resize(256);
+      ev = &c->stage_ring[c->stage_next++ % c->stage_ring.size()];
+      stage_resolve(c, *ev);
+      if (!ev->a) { cudaEventCreate(&ev->a); cudaEventCreate(&ev->b); }
+      cudaEventRecord(ev->a, c->stream);
+    } else {
+      cudaEventRecord(c->ev_a, c->stream);
+    }
+  }
+  void stop() {
+    if (!c->timers_on) return;
+    if (slot != 1) c->t_launch[slot] += c->launches - l0;
+    if (c->timers_async) {
+      cudaEventRecord(ev->b, c->stream);
+      ev->slot = slot;
+      return;
+    }
+    cudaEventRecord(c->ev_b, c->stream);
+    cudaEventSynchronize(c->ev_b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
+    c->t_ms[slot] += ms;
+  }
+};
 
 inline int fail(ucgb200_ctx *c, const char *msg) {
   c->err = msg;
