@@ -293,7 +293,15 @@ typedef struct ucgb200_deck {
    * 0 = 123.  Matters when the wall fix (with bias_potential) is defined before a non-ld fix ucgstate, which
    * overwrites the ucgl the bias reads (fix_nve_ucgld_wall_hard.cpp:234-239, fix_ucgstate.cpp:130). */
   int post_force_order;
-  int reserved[6];
+  /* table_ucg_bethe `prior chemical_potential noise <level> <seed>` (bethe_prior = 1, pair_table_ucg_bethe.cpp:189-194):
+   * acts on the first evaluation only (sites whose ucgp is still -1); one Philox draw per site, keyed by (seed, tag) */
+  double bethe_noise_level;
+  int bethe_seed;
+  /* fix ucgld/langevin with a bias temperature compute (fix_ucgld_langevin.cpp:174-177): the reference's Tp_BIAS
+   * branch differs from the plain one in a single rule, no random force on a site whose lambda velocity is exactly
+   * zero (:285; remove_bias / restore_bias are commented out there) */
+  int langevin_bias;
+  int reserved[2];
 } ucgb200_deck;
 int ucgb200_deck_configure(ucgb200_ctx *ctx, const ucgb200_deck *deck);
 /* Verlet::setup [stock]: pbc, build, force_clear, pair->compute, fix setup() calls */

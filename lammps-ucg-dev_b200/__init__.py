@@ -60,7 +60,8 @@ class Deck(C.Structure):
         ("langevin_seed", C.c_int), ("langevin_groupbit", C.c_int),
         ("ucgstate", C.c_int), ("ucgstate_seed", C.c_int), ("ucgstate_rate", C.c_double),
         ("bethe_method", C.c_int), ("bethe_pseudo", C.c_int), ("bethe_prior", C.c_int),
-        ("thermo_every", C.c_int), ("cluster_freq", C.c_int), ("post_force_order", C.c_int), ("reserved", C.c_int * 6),
+        ("thermo_every", C.c_int), ("cluster_freq", C.c_int), ("post_force_order", C.c_int),
+        ("bethe_noise_level", C.c_double), ("bethe_seed", C.c_int), ("langevin_bias", C.c_int), ("reserved", C.c_int * 2),
     ]
 
 

@@ -134,7 +134,7 @@ struct TailArgs {
   const TypeInfo *tinfo;
   int n, ntypes;
   // langevin
-  int langevin, lgroupbit;
+  int langevin, lgroupbit, lbias;
   double tsqrt;
   unsigned lseed;
   // ucgstate
@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(256) k_step_tail(TailArgs a) {
       if (a.langevin && (m & a.lgroupbit)) {                              // k_langevin
         const double gamma1 = a.gfac[type];
         const double gamma2 = a.gfac[a.ntypes + 1 + type] * a.tsqrt;
-        const double fran = gamma2 * (philox_uniform(a.lseed, 0x4c414e47u, (unsigned)a.tag[i], a.step) - 0.5);
+        double fran = gamma2 * (philox_uniform(a.lseed, 0x4c414e47u, (unsigned)a.tag[i], a.step) - 0.5);
+        if (a.lbias && v.w == 0.0) fran = 0.0;                            // Tp_BIAS branch (:285)
         f.w += gamma1 * v.w + fran;
         fdirty = true;
       }
@@ -396,7 +397,7 @@ int ucg_step_tail(ucgb200_ctx *c, const ucgb200_deck &d, double tsqrt, int fuse_
   a.pos = c->pos.p; a.vel = c->vel.p; a.frc = c->frc.p; a.xhold = c->xhold.p; a.ts = c->ts.p;
   a.mask = c->mask.p; a.tag = c->tag.p; a.ucgml = c->ucgml.p; a.gfac = c->d_gfac.p; a.scores = c->scores.p;
   a.ucgp = c->ucgp.p; a.tinfo = c->d_typeinfo.p; a.n = c->nlocal; a.ntypes = c->n_formal;
-  a.langevin = d.langevin; a.lgroupbit = d.langevin_groupbit ? d.langevin_groupbit : 1; a.tsqrt = tsqrt;
+  a.langevin = d.langevin; a.lgroupbit = d.langevin_groupbit ? d.langevin_groupbit : 1; a.tsqrt = tsqrt; a.lbias = d.langevin_bias;
   a.lseed = (unsigned)d.langevin_seed;
   a.ucgstate_mode = d.ucgstate == 0 ? -1 : (d.ucgstate == 1 ? 0 : (d.ucgstate == 2 ? 1 : 2));
   a.useed = (unsigned)d.ucgstate_seed; a.urate = d.ucgstate_rate;

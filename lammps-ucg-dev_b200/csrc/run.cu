@@ -8,6 +8,7 @@
 
 using namespace ucg;
 
+static_assert(sizeof(ucgb200_deck) == 128, "ucgb200_deck is part of the C-ABI: new fields come out of reserved[]");
 extern "C" int ucgb200_deck_configure(ucgb200_ctx *c, const ucgb200_deck *deck) {
   if (!c || !deck) return -1;
   if (deck->pair_style < 0 || deck->pair_style > 3) return fail(c, "unknown pair style");
@@ -65,7 +66,7 @@ static int pair_compute(ucgb200_ctx *c, int ev) {
   const ucgb200_deck &d = c->deck;
   switch (d.pair_style) {
     case 0: return ucgb200_pair_ucgld(c, ev, ev);
-    case 1: return ucgb200_pair_bethe(c, ev, ev, d.bethe_method, d.bethe_pseudo, d.bethe_prior, 0.0, 1);
+    case 1: return ucgb200_pair_bethe(c, ev, ev, d.bethe_method, d.bethe_pseudo, d.bethe_prior, d.bethe_noise_level, d.bethe_seed ? d.bethe_seed : 1);
     case 2: return ucgb200_pair_rleucg(c, ev, ev);
     default: return ucgb200_pair_bethe_density(c, ev, ev);
   }
@@ -115,7 +116,7 @@ static int post_force(ucgb200_ctx *c, bool at_setup) {
       double tt = current_t_target(c);
       if (c->lang_g1.empty()) { if ((rc = langevin_factors(c, c->lang_g1, c->lang_g2))) return rc; }
       if ((rc = ucgb200_fix_langevin(c, c->lang_g1.data(), c->lang_g2.data(), c->n_formal, std::sqrt(tt),
-                                     d.langevin_seed, c->ntimestep, d.langevin_groupbit ? d.langevin_groupbit : 1, 0)))
+                                     d.langevin_seed, c->ntimestep, d.langevin_groupbit ? d.langevin_groupbit : 1, d.langevin_bias)))
         return rc;
     }
     if (order[k] == 2 && d.ucgstate) {

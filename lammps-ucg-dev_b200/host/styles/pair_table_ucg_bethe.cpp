@@ -53,7 +53,9 @@ bool PairTable_UCG_Bethe::ucg_deck(ucgb200_deck &deck) {
   deck.bethe_method = method_flag;
   deck.bethe_pseudo = pseudo_flag;
   deck.bethe_prior = prior_flag;
-  return prior_flag != CHEMICAL_POTENTIAL_NOISE;   // the noise prior keeps its own RNG stream: offload mode only
+  deck.bethe_noise_level = noise_level;   // acts on the first evaluation only (ucgp still -1): the same draws as in offload mode
+  deck.bethe_seed = seed;
+  return true;
 }
 
 void PairTable_UCG_Bethe::device_compute(int eflag, int vflag) {

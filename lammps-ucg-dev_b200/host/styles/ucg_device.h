@@ -163,7 +163,7 @@ class UCGDevice {
   }
 
   // ---- tracked mode (see the header of this file)
-  bool tracked = false;
+  bool tracked = false, tracking_pending = false;
   unsigned dev_valid = 0;    // fields whose device copy is what the host holds or newer: no upload needed
   unsigned dev_newer = 0;    // fields the device has written and the host has not seen yet
   long long bytes_up = 0, bytes_down = 0;   // per-site payload moved so far (diagnostics: ucg_traffic())

@@ -41,9 +41,10 @@ FixNVE_UCGLD::FixNVE_UCGLD(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, a
 int FixNVE_UCGLD::setmask() {
   return INITIAL_INTEGRATE | FINAL_INTEGRATE | INITIAL_INTEGRATE_RESPA | FINAL_INTEGRATE_RESPA | PRE_EXCHANGE | END_OF_STEP | POST_RUN;
 }
-// [stock] Verlet::setup calls Fix::setup after the first force evaluation: from here to post_run the arrays may stay on
-// the device if the deck allows it
-void FixNVE_UCGLD::setup(int) { dev->tracking_begin(lmp); }
+// [stock] Verlet::setup: force evaluation, every Fix::setup (fix ucgstate and fix ucgld/langevin act there), then the
+// step-0 thermo line and dumps read the host arrays: set-up stays eager.  From the first initial_integrate to post_run
+// the arrays may stay on the device if the deck allows it
+void FixNVE_UCGLD::setup(int) { dev->tracked = false; dev->tracking_pending = true; }
 // rebuild steps: Domain::pbc, Comm::exchange / borders and Atom::sort are about to rewrite and reorder the host arrays
 void FixNVE_UCGLD::pre_exchange() {
   if (!dev->tracked) return;
@@ -54,7 +55,7 @@ void FixNVE_UCGLD::pre_exchange() {
 void FixNVE_UCGLD::end_of_step() {
   if (dev->tracked && output && output->next == update->ntimestep) dev->flush(lmp);
 }
-void FixNVE_UCGLD::post_run() { dev->tracking_end(lmp); }
+void FixNVE_UCGLD::post_run() { dev->tracking_end(lmp); dev->tracking_pending = false; }
 
 bool UCGDevice::tracking_allowed(LAMMPS *lmp) {
   if (getenv("UCGB200_OFFLOAD_TRACKED") && atoi(getenv("UCGB200_OFFLOAD_TRACKED")) == 0) return false;
@@ -80,6 +81,7 @@ void FixNVE_UCGLD::init() {
   if (atom->rmass) error->all(FLERR, "fix {}: per-atom masses (rmass) are not supported by ucg-b200", style);
 }
 void FixNVE_UCGLD::initial_integrate(int) {
+  if (dev->tracking_pending) { dev->tracking_pending = false; dev->tracking_begin(lmp); }
   dev->upload(lmp, DYN_IN);
   dev->check(lmp, ucgb200_fix_nve_initial(dev->ctx, dt_pos, dt_half, groupbit, hard_wall), "fix_nve_initial");
   dev->download(lmp, UCGB200_F_X | UCGB200_F_V | UCGB200_F_UCGL | UCGB200_F_UCGVL | (hard_wall ? UCGB200_F_UCGSTATE : 0u));
@@ -267,7 +269,10 @@ bool Fix_UCGLD_Langevin::ucg_deck(ucgb200_deck &deck) {
   deck.t_period = temp.period;
   deck.langevin_seed = rng_seed + comm->me;
   deck.langevin_groupbit = groupbit;
-  return !bias_temp;   // a bias temperature compute lives on the host
+  // a bias temperature compute changes one rule of the fix (no random force at zero lambda velocity, :285); its
+  // compute_scalar() has no effect on the forces (remove_bias / restore_bias are commented out in the reference)
+  deck.langevin_bias = bias_temp;
+  return true;
 }
 void Fix_UCGLD_Langevin::post_force_respa(int vflag, int ilevel, int) {
   if (ilevel == nlevels_respa - 1) post_force(vflag);

@@ -28,7 +28,7 @@ void VerletUCGB200::collect_deck() {
   parts.clear();
   auto *pair = dynamic_cast<UCGDeckPart *>(force->pair);
   if (!pair || !pair->ucg_deck(deck))
-    error->all(FLERR, "run_style ucg/b200 needs one of the UCG pair styles (table_ucg_bethe without the noise prior); use run_style verlet");
+    error->all(FLERR, "run_style ucg/b200 needs one of the UCG pair styles; use run_style verlet");
   // the post_force stages act in fix definition order ([stock] Modify::post_force); the device loop is told which
   int order = 0, nstage = 0;
   bool have[4] = {false, false, false, false};

@@ -45,6 +45,37 @@ int Pair::instance_total = 0;
 
 namespace {
 
+// harness-only stand-in for a [stock] temperature compute WITH a velocity bias (temp/com, temp/profile, ...): what
+// Fix_UCGLD_Langevin looks at is tempflag, tempbias and a compute_scalar() call per post_force
+// (fix_ucgld_langevin.cpp:174-177, 271); the value is the plain kinetic temperature of the group
+class ComputeTempBiasStub : public Compute {
+ public:
+  int ncalls = 0;
+  ComputeTempBiasStub(LAMMPS *l, int narg, char **arg) : Compute(l) {
+    if (narg < 3) error->all(FLERR, "Illegal compute temp/bias_stub command");
+    id = utils::strdup(arg[0]);
+    igroup = l->group->find(arg[1]);
+    if (igroup == -1) error->all(FLERR, "Could not find compute group ID {}", arg[1]);
+    groupbit = l->group->bitmask[igroup];
+    style = utils::strdup(arg[2]);
+    tempflag = tempbias = 1;
+  }
+  ~ComputeTempBiasStub() override { delete[] id; delete[] style; }
+  double compute_scalar() override {
+    ncalls++;
+    double ke = 0.0;
+    int n = 0;
+    for (int i = 0; i < atom->nlocal; i++)
+      if (atom->mask[i] & groupbit) {
+        const double *v = atom->v[i];
+        ke += atom->mass[atom->type[i]] * (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        n++;
+      }
+    scalar = n > 1 ? ke * force->mvv2e / (3.0 * (n - 1) * force->boltz) : 0.0;
+    return scalar;
+  }
+};
+
 // [stock] compute property/atom restricted to the names AtomVec::property_atom knows (the UCG taps,
 // atom_vec_ucg.cpp:172-234): compute_peratom() fills vector_atom / array_atom through the
 // reference's own AtomVecUCG::pack_property_atom
@@ -730,10 +761,22 @@ struct Sim {
       // harness-only: "group NAME" registers the next free group bit; masks come in through ref_atoms
       if (lmp.group->find(w.at(1)) < 0) lmp.group->names[lmp.group->ngroup++] = utils::strdup(w.at(1));
     } else if (cmd == "compute") {
-      if (w.at(3) != "property/atom") lmp.error->all(FLERR, "Unrecognized compute style '{}'", w.at(3));
-      Compute *c = new ComputePropertyAtomStub(&lmp, narg, arg.data());
+      Compute *c = nullptr;
+      if (w.at(3) == "property/atom") c = new ComputePropertyAtomStub(&lmp, narg, arg.data());
+      else if (w.at(3) == "temp/bias_stub") c = new ComputeTempBiasStub(&lmp, narg, arg.data());
+      else lmp.error->all(FLERR, "Unrecognized compute style '{}'", w.at(3));
       owned_computes.push_back(c);
       lmp.modify->computes.push_back(c);
+    } else if (cmd == "fix_modify") {
+      // [stock] Modify::modify_fix -> Fix::modify_params: style-specific keywords go to Fix::modify_param
+      Fix *f = lmp.modify->get_fix_by_id(w.at(1));
+      if (!f) lmp.error->all(FLERR, "Could not find fix_modify ID {}", w.at(1));
+      for (int k = 1; k < narg;) {
+        const int used = f->modify_param(narg - k, arg.data() + k);
+        if (used == 0) lmp.error->all(FLERR, "Illegal fix_modify command: {}", arg[k]);
+        k += used;
+      }
+      initialized = false;
     } else if (cmd == "dump") {
       // dump ID group custom N file args   ([stock] Output::add_dump); the reference's patched DumpCustom
       if (w.at(3) != "custom") lmp.error->all(FLERR, "Unrecognized dump style '{}'", w.at(3));

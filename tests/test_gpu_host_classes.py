@@ -300,28 +300,82 @@ def test_run_style_ucg_b200_is_the_offload_run_kept_on_the_device(pkg, fixtures,
         assert abs(sims["resident"][1] - sims["ref"][1]) <= 1e-8 * abs(sims["ref"][1])
 
 
-def test_run_style_ucg_b200_rejects_what_it_cannot_run(pkg, fixtures):
-    liq = _liq(4)
-    s = rb.HostSim.single_type(liq, fixtures["table4096"], fixtures["state"], pair="table_ucg_bethe",
-                               extra="prior chemical_potential noise 0.1 77")
-    s.command("fix 0 all ttarget/stub 1.0")
-    s.command("fix 1 all nve/ucgld")
-    s.command("run_style ucg/b200")
-    with pytest.raises(RuntimeError, match="without the noise prior"):
-        s.setup(1)
-    # the same deck without the noise prior runs, and equals the offload run
-    out = []
-    for resident in (False, True):
-        s = rb.HostSim.single_type(liq, fixtures["table4096"], fixtures["state"], pair="table_ucg_bethe", extra="method bethe prior ucgl")
-        for f in ("fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld", "fix 2 all ucgstate"):
+def test_bethe_noise_prior_offload_resident_and_reference(pkg, fixtures):
+    """`prior chemical_potential noise L S` (pair_table_ucg_bethe.cpp:189-194, 228-233): acts on the first evaluation only
+    (ucgp still -1).  The device draws one Philox number per site keyed by (seed, tag), so the resident loop and the
+    offload classes give the same run bit for bit; against the reference (a sequential RanMars draw per site and per
+    visit) the comparison is statistical: the spread the noise adds to the first posterior"""
+    liq = _liq(6)
+    fixes = ("fix 0 all ttarget/stub 1.0", "fix 1 all nve/ucgld", "fix 2 all ucgstate")
+    first = {}
+    # the priors only enter the SCE scores (`pseudo no`); with pseudo-likelihood scores no prior changes anything
+    noise, plain = "pseudo no prior chemical_potential noise 0.1 77", "pseudo no prior chemical_potential"
+    for tag, cls, resident, extra in (("ref", rb.RefSim, False, noise), ("ref0", rb.RefSim, False, plain),
+                                      ("offload", rb.HostSim, False, noise), ("resident", rb.HostSim, True, noise),
+                                      ("gpu0", rb.HostSim, True, plain)):
+        s = cls.single_type(liq, fixtures["table4096"], fixtures["state"], pair="table_ucg_bethe", extra=extra)
+        for f in fixes:
             s.command(f)
         if resident:
             s.command("run_style ucg/b200")
         s.setup(1)
+        a = s.get_atoms()
         s.run(10, 0)
-        out.append(s.get_atoms())
-    for k in ("x", "f", "ucgp", "ucgstate"):
-        assert np.array_equal(out[0][k], out[1][k]), k
+        first[tag] = (a, s.get_atoms())
+    for k in ("x", "f", "ucgp", "ucgstate", "ucgsoftmaxscores"):
+        assert np.array_equal(first["offload"][0][k], first["resident"][0][k]), k
+        assert np.array_equal(first["offload"][1][k], first["resident"][1][k]), k
+    # what the noise did to the first posterior, reference and device
+    def logit_shift(a, b):
+        sa, sb = first[a][0]["ucgsoftmaxscores"], first[b][0]["ucgsoftmaxscores"]
+        return (sa[:, 1] - sa[:, 0]) - (sb[:, 1] - sb[:, 0])
+    d_ref, d_gpu = logit_shift("ref", "ref0"), logit_shift("resident", "gpu0")
+    print("noise prior: logit shift mean/std  reference %.4g %.4g   device %.4g %.4g" % (d_ref.mean(), d_ref.std(), d_gpu.mean(), d_gpu.std()))
+    assert d_ref.std() > 1e-3 and d_gpu.std() > 1e-3                 # the prior is on
+    n = liq.n
+    assert abs(d_ref.mean() - d_gpu.mean()) < 6 * (d_ref.std() + d_gpu.std()) / np.sqrt(n)
+    # same order only: the reference's SCE j-side formulas are not the mirror image of its i-side ones
+    # (pair_table_ucg_bethe.cpp:583-601, DESIGN.md §8), so half of its visits respond differently to a prior
+    # (measured: device 0.65, reference 0.41)
+    assert 0.5 < d_gpu.std() / d_ref.std() < 2.0, (d_gpu.std(), d_ref.std())
+    # after the first evaluation the prior is ucgl for every site: no further draws, the run stays finite and bounded
+    assert np.all(np.isfinite(first["resident"][1]["x"]))
+
+
+def test_langevin_bias_compute_in_the_resident_loop(pkg, fixtures):
+    """fix ucgld/langevin with a bias temperature compute (fix_modify temp, fix_ucgld_langevin.cpp:174-177): the Tp_BIAS
+    branch gives no random force to a site whose lambda velocity is exactly zero (:285).  With ucgvl = 0 on half of the
+    sites the setup post_force is deterministic there: equal to the reference's; resident and offload agree everywhere"""
+    liq = _liq(6)
+    n = liq.n
+    vl = np.where(np.arange(n) % 2 == 0, 0.0, 0.05 * np.cos(np.arange(n)))
+    res = {}
+    for tag, cls, resident, bias in (("ref", rb.RefSim, False, True), ("offload", rb.HostSim, False, True),
+                                     ("resident", rb.HostSim, True, True), ("nobias", rb.HostSim, True, False)):
+        s = cls.single_type(liq, fixtures["table4096"], fixtures["state"])
+        s.set_state(ucgvl=vl)
+        s.command("fix 1 all nve/ucgld")
+        s.command("fix 2 all ucgld/langevin 1.0 1.0 0.5 4711")
+        s.command("fix 3 all ucgstate ld")
+        if bias:
+            s.command("compute tb all temp/bias_stub")
+            s.command("fix_modify 2 temp tb")
+        if resident:
+            s.command("run_style ucg/b200")
+        s.setup(1)
+        a = s.get_atoms()
+        s.run(8, 0)
+        res[tag] = (a, s.get_atoms())
+    order = {k: np.argsort(v[0]["tag"]) for k, v in res.items()}
+    uf = {k: v[0]["ucgforce"][order[k]] for k, v in res.items()}
+    still = vl == 0.0
+    scale = np.abs(uf["ref"]).max()
+    for k in ("offload", "resident"):
+        assert np.abs(uf[k][still] - uf["ref"][still]).max() <= 1e-6 * scale, k        # no noise, no drag: the pair term alone
+    assert np.abs(uf["nobias"][still] - uf["ref"][still]).max() > 1e-3 * scale          # without the bias compute they are kicked
+    assert np.abs(uf["resident"][~still] - uf["ref"][~still]).max() > 1e-3 * scale     # moving sites are kicked either way
+    for k in ("x", "v", "ucgl", "ucgvl", "ucgforce"):
+        assert rel_err(res["resident"][1][k], res["offload"][1][k]) <= 1e-11, k
 
 
 @pytest.mark.parametrize("style", ["rleucg", "bethe_density"])
