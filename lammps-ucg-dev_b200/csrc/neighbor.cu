@@ -1019,6 +1019,176 @@ k_build_rows_tiled_f32(const double4 *__restrict__ pos, int nlocal, Grid g, cons
   }
 }
 
+// Lane-per-site variant of k_build_rows_tiled_f32 (experiment, UCGB200_BUILD_LANES=1): the SAME rows in the SAME order.
+// One warp owns one cell.  The candidates of the 27-cell stencil are staged and culled exactly as above; then every
+// LANE takes one of the cell's sites and walks the staged candidates one by one (the float4 is a shared-memory
+// broadcast: one wavefront, no conflict), so a distance test costs ~11 warp instructions per 32 (site, candidate)
+// pairs instead of ~57 per 32 with a warp per site (profiles/r02_build_rows_lines.json: ballots, ranks and the band
+// test ran once per candidate AND per site there).  Pass A keeps the tile index of everything within
+// cutneighsq + band in a 16-bit list per lane; pass B1 classifies only those ~80 entries per site (exact re-test
+// inside the band, self exclusion, inner / displacement level) with every lane busy, pass B2 places them: inner
+// entries first, skin entries grouped by level, both in candidate order.  Level counters live in one 64-bit word
+// (8 x 8 bits; a multiply by 0x0101..01 gives the prefix sums).
+constexpr int LANE_CAP = 512;                      // staged candidates per cell (after the cull); more: flags[2], generic kernel
+__global__ void __launch_bounds__(32)
+k_build_rows_lanes_f32(const double4 *__restrict__ pos, int nlocal, Grid g, const int *__restrict__ ostart,
+                       const int *__restrict__ gstart, double cutneighsq, double cutsq, float band,
+                       int *__restrict__ neigh, int stride, int *__restrict__ numneigh, int *__restrict__ flags,
+                       uint4 *__restrict__ levcnt, int cull, LevelThresholds lvl) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  float4 *s_c = reinterpret_cast<float4 *>(s_raw);                                   // [LANE_CAP] staged candidates
+  unsigned short *s_hit = reinterpret_cast<unsigned short *>(s_c + LANE_CAP);        // [32][HS] tile indices (+ class) per lane
+  const int HS = stride + 2;                       // HS / 2 odd: the 32 lists start in 32 different banks
+  const int lane = threadIdx.x;
+  const unsigned lt = (1u << lane) - 1;
+  const int cell = blockIdx.x;
+  const int ix = cell % g.ninner[0] + 1, iy = (cell / g.ninner[0]) % g.ninner[1] + 1, iz = cell / (g.ninner[0] * g.ninner[1]) + 1;
+  const int c = (iz * g.nc[1] + iy) * g.nc[0] + ix;
+  const int sb = ostart[c], se = ostart[c + 1];
+  if (sb >= se) return;
+  // the 18 runs of the stencil (9 rows of three cells, owned sites then ghosts): lane r keeps run r
+  int rb = 0, re = 0, roff = 0;
+  if (lane < 18) {
+    const int yz = lane >> 1, pass = lane & 1;
+    const int dz = yz / 3 - 1, dy = yz % 3 - 1;
+    const int c0 = ((iz + dz) * g.nc[1] + (iy + dy)) * g.nc[0] + (ix - 1);
+    rb = pass == 0 ? ostart[c0] : gstart[c0];
+    re = pass == 0 ? ostart[c0 + 3] : gstart[c0 + 3];
+    roff = pass == 0 ? 0 : nlocal;
+  }
+  const double ox = g.lo[0] + ((double)ix - 0.5) / g.inv[0], oy = g.lo[1] + ((double)iy - 0.5) / g.inv[1],
+               oz = g.lo[2] + ((double)iz - 0.5) / g.inv[2];
+  const float cnf = (float)cutneighsq, csf = (float)cutsq, cnb = cnf + band;
+  const float hx = cull ? (float)(0.5 / g.inv[0]) * 1.0001f : 1e30f, hy = cull ? (float)(0.5 / g.inv[1]) * 1.0001f : 1e30f,
+              hz = cull ? (float)(0.5 / g.inv[2]) * 1.0001f : 1e30f;
+  // stage + cull (stable): identical to k_build_rows_tiled_f32, run by run
+  int cn = 0;
+  for (int r = 0; r < 18; r++) {
+    const int b = __shfl_sync(0xffffffffu, rb, r), e = __shfl_sync(0xffffffffu, re, r), off = __shfl_sync(0xffffffffu, roff, r);
+    for (int k0 = b; k0 < e; k0 += 32) {
+      const int k = k0 + lane;
+      bool keep = false;
+      float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < e) {
+        const int j = k + off;
+        const double4 rj = pos[j];
+        rec = make_float4((float)(rj.x - ox), (float)(rj.y - oy), (float)(rj.z - oz), __int_as_float(j));
+        const float ex = fmaxf(fabsf(rec.x) - hx, 0.f), ey = fmaxf(fabsf(rec.y) - hy, 0.f), ez = fmaxf(fabsf(rec.z) - hz, 0.f);
+        keep = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) <= cnb;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      const int at = cn + __popc(m & lt);
+      if (keep && at < LANE_CAP) s_c[at] = rec;
+      cn += __popc(m);
+    }
+  }
+  if (cn > LANE_CAP) {                                  // a cell this crowded goes to the generic kernel (host re-launch)
+    if (lane == 0) atomicMax(&flags[2], cn);
+    return;
+  }
+  const int cn4 = (cn + 3) & ~3;                      // LANE_CAP is a multiple of 4: the padded tail stays inside the array
+  if (lane < cn4 - cn) s_c[cn + lane] = make_float4(1e18f, 1e18f, 1e18f, __int_as_float(-1));   // never a hit
+  __syncwarp();
+  const unsigned sa_hit = (unsigned)__cvta_generic_to_shared(s_hit) + 2u * (unsigned)(lane * HS);
+  for (int s0 = sb; s0 < se; s0 += 32) {
+    const int i = s0 + lane;
+    const bool have = i < se;
+    double4 ri = make_double4(0, 0, 0, 0);
+    float xf = 1e18f, yf = 1e18f, zf = 1e18f;        // an idle lane hits nothing
+    if (have) {
+      ri = pos[i];
+      xf = (float)(ri.x - ox); yf = (float)(ri.y - oy); zf = (float)(ri.z - oz);
+    }
+    // ---- pass A: every staged candidate against every lane's site
+    unsigned a = sa_hit;
+    const unsigned a_end = sa_hit + 2u * (unsigned)HS;
+    int nhit = 0;                                     // may run past HS: reported as an overflow
+    for (int k0 = 0; k0 < cn4; k0 += 4) {              // four broadcast loads in flight, then the four tests
+      float4 cj[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) cj[u] = s_c[k0 + u];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const float dx = xf - cj[u].x, dy = yf - cj[u].y, dz = zf - cj[u].z;
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        const bool h = r2 <= cnb;
+        if (h && a < a_end) asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)(k0 + u)) : "memory");
+        a += h ? 2u : 0u;
+        nhit += h ? 1 : 0;
+      }
+    }
+    const int nkeep = min(nhit, HS);
+    // ---- pass B1: classify the kept entries: 0 inner, 1 + level for a skin entry, 15 not a neighbor
+    int cnt_in = 0;
+    unsigned long long lev64 = 0;
+    const int nmax = __reduce_max_sync(0xffffffffu, nkeep);
+    for (int e = 0; e < nmax; e++) {
+      if (e < nkeep) {
+        unsigned short kk;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(kk) : "r"(sa_hit + 2u * (unsigned)e));
+        const float4 cj = s_c[kk];
+        const int j = __float_as_int(cj.w);
+        const float dx = xf - cj.x, dy = yf - cj.y, dz = zf - cj.z;
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        bool hit = r2 <= cnf, inner = r2 < csf;
+        if ((fabsf(r2 - cnf) <= band) | (fabsf(r2 - csf) <= band)) {
+          const double4 rj = pos[j];
+          const double rsq = rsq_exact(ri.x - rj.x, ri.y - rj.y, ri.z - rj.z);
+          hit = rsq <= cutneighsq;
+          inner = rsq < cutsq;
+        }
+        hit = hit && (j != i);
+        int cls = 15;
+        if (hit) {
+          if (inner) { cls = 0; cnt_in++; }
+          else {
+            const int lev = level_of(r2 - band, lvl);
+            cls = 1 + lev;
+            lev64 += 1ull << (8 * lev);
+          }
+        }
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(sa_hit + 2u * (unsigned)e), "h"((unsigned short)(kk | (cls << 12))) : "memory");
+      }
+    }
+    // ---- pass B2: place
+    const unsigned long long incl = lev64 * 0x0101010101010101ull;      // byte L: skin entries of level <= L (cnt_out <= 255)
+    int cnt_out = (int)(incl >> 56);
+    bool levels = true;
+    if (nhit > 255) {   // the byte counters may have wrapped: count again, keep candidate order, every level "visit all"
+      levels = false;
+      cnt_out = 0;
+      for (int e = 0; e < nkeep; e++) { const int cls = s_hit[lane * HS + e] >> 12; cnt_out += (cls >= 1 && cls <= 8); }
+    }
+    const int total = (nhit > HS) ? nhit : cnt_in + cnt_out;   // an overfull list reports its (upper bound) length
+    if (have) {
+      int *row = neigh + (size_t)i * stride;
+      if (total <= stride) {
+        unsigned long long start = levels ? (incl << 8) : 0ull;         // byte L: entries of lower levels
+        int in_pos = 0, out_pos = cnt_in;
+        for (int e = 0; e < nkeep; e++) {
+          unsigned short v;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(sa_hit + 2u * (unsigned)e));
+          const int cls = v >> 12;
+          if (cls == 15) continue;
+          const int j = __float_as_int(s_c[v & 0xfff].w);
+          int p;
+          if (cls == 0) p = in_pos++;
+          else if (levels) { const int sh = 8 * (cls - 1); p = cnt_in + (int)((start >> sh) & 0xffull); start += 1ull << sh; }
+          else p = out_pos++;
+          row[rowslot(p)] = j;
+        }
+      }
+      unsigned lc[8];
+#pragma unroll
+      for (int L = 0; L < 8; L++) lc[L] = levels ? (unsigned)cnt_in + (unsigned)((incl >> (8 * L)) & 0xffull) : (unsigned)total;
+      numneigh[i] = min(total, stride);
+      if (total > stride) atomicMax(&flags[1], total);
+      levcnt[i] = make_uint4(lc[0] | (lc[1] << 16), lc[2] | (lc[3] << 16), lc[4] | (lc[5] << 16), lc[6] | (lc[7] << 16));
+    }
+    __syncwarp();
+  }
+}
+
 // [stock] Neighbor::check_distance: any owned atom moved > skin/2 since the last build
 __global__ void k_check_distance(const double4 *__restrict__ pos, const double4 *__restrict__ xhold, int n,
                                  double triggersq, int *__restrict__ flags, unsigned long long *__restrict__ maxdisp) {
@@ -1117,20 +1287,27 @@ static int read_flags(ucgb200_ctx *c) {
 static int build_rows(ucgb200_ctx *c) {
   int nlocal = c->nlocal;
   int na = c->n_actual + 1;
+  bool lanes_off = false;
   while (true) {
     UCG_CHECK(c, c->neigh.ensure((size_t)nlocal * c->neigh_stride));
     UCG_CHECK(c, c->levcnt.ensure(nlocal + 1));
-    UCG_CHECK(c, cudaMemsetAsync(c->d_flags.p + 1, 0, sizeof(int), c->stream));
+    UCG_CHECK(c, cudaMemsetAsync(c->d_flags.p + 1, 0, 2 * sizeof(int), c->stream));
     const int tiled = getenv("UCGB200_BUILD_TILED") ? atoi(getenv("UCGB200_BUILD_TILED")) : 1;
     int cap = getenv("UCGB200_TILE_CAP") ? atoi(getenv("UCGB200_TILE_CAP")) : TILE_CAP;   // small values exercise the chunked path
     cap = std::min(std::max(cap, 32), TILE_CAP);
     const int f32 = getenv("UCGB200_BUILD_F32") ? atoi(getenv("UCGB200_BUILD_F32")) : 1;
     if (tiled && f32 && na == 2 && c->h_pairinfo.size() == 4) {
-      // one actual type: single-precision prefilter, exact re-test inside the error band (k_build_rows_tiled_f32)
+      // one actual type: single-precision prefilter, exact re-test inside the error band
+      // (k_build_rows_lanes_f32: a lane per site; k_build_rows_tiled_f32: a warp per site, any cell population)
       const int ncell_owned = c->grid.ninner[0] * c->grid.ninner[1] * c->grid.ninner[2];
       const size_t smem = (size_t)TILE_CAP_F32 * sizeof(float4) + (TILE_BS / 32) * (size_t)c->neigh_stride * (3 * sizeof(int));
       UCG_CHECK(c, cudaFuncSetAttribute(k_build_rows_tiled_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       if (smem > 96 * 1024) return fail(c, "neighbor rows too long for the tiled build");
+      // measured (profiles/r02_build_rows_lanes_full.json): 0.89 G warp instructions instead of 1.41 G, but 16.5 KB of shared
+      // memory per one-warp block leave 13 warps per SM (issue slots 56 % busy): 1.76 ms per rebuild against 1.66 ms -> off
+      const int lanes_knob = getenv("UCGB200_BUILD_LANES") ? atoi(getenv("UCGB200_BUILD_LANES")) : 0;
+      const size_t smem_lanes = (size_t)LANE_CAP * sizeof(float4) + 32 * (size_t)(c->neigh_stride + 2) * sizeof(unsigned short);
+      const bool lanes = lanes_knob && !lanes_off && !getenv("UCGB200_TILE_CAP") && smem_lanes <= 96 * 1024 && c->nlocal + c->nghost < (1 << 30);
       const double cs = c->h_pairinfo[3].cutsq, cn = c->h_pairinfo[3].cutneighsq;   // the thresholds the FP64 kernels read
       const double rc = std::sqrt(cn);
       double edge = 0.0;
@@ -1149,11 +1326,17 @@ static int build_rows(ucgb200_ctx *c) {
       }
       int cap32 = getenv("UCGB200_TILE_CAP") ? atoi(getenv("UCGB200_TILE_CAP")) : TILE_CAP_F32;
       cap32 = (std::min(std::max(cap32, 32), TILE_CAP_F32) / 32) * 32;   // whole passes of 32 candidates
-      k_build_rows_tiled_f32<<<ncell_owned, TILE_BS, smem, c->stream>>>(
-          c->pos.p, nlocal, c->grid, c->cell_start.p, c->gcell_start.p, cn, cs, band, c->neigh.p, c->neigh_stride,
-          c->numneigh.p, c->d_flags.p, cap32, c->levcnt.p, c->skin,
-          (c->periodic[0] && c->periodic[1] && c->periodic[2] && !(getenv("UCGB200_BUILD_CULL") && atoi(getenv("UCGB200_BUILD_CULL")) == 0)) ? 1 : 0,
-          lvl);
+      const int cull = (c->periodic[0] && c->periodic[1] && c->periodic[2] && !(getenv("UCGB200_BUILD_CULL") && atoi(getenv("UCGB200_BUILD_CULL")) == 0)) ? 1 : 0;
+      if (lanes) {
+        UCG_CHECK(c, cudaFuncSetAttribute(k_build_rows_lanes_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        k_build_rows_lanes_f32<<<ncell_owned, 32, smem_lanes, c->stream>>>(
+            c->pos.p, nlocal, c->grid, c->cell_start.p, c->gcell_start.p, cn, cs, band, c->neigh.p, c->neigh_stride,
+            c->numneigh.p, c->d_flags.p, c->levcnt.p, cull, lvl);
+      } else {
+        k_build_rows_tiled_f32<<<ncell_owned, TILE_BS, smem, c->stream>>>(
+            c->pos.p, nlocal, c->grid, c->cell_start.p, c->gcell_start.p, cn, cs, band, c->neigh.p, c->neigh_stride,
+            c->numneigh.p, c->d_flags.p, cap32, c->levcnt.p, c->skin, cull, lvl);
+      }
     } else if (tiled) {
       const int ncell_owned = c->grid.ninner[0] * c->grid.ninner[1] * c->grid.ninner[2];
       const size_t smem = (size_t)TILE_CAP * (sizeof(double2) + sizeof(double) + 2 * sizeof(int)) +
@@ -1174,6 +1357,7 @@ static int build_rows(ucgb200_ctx *c) {
     UCG_LAUNCHED(c);
     int rc = read_flags(c);
     if (rc) return rc;
+    if (c->h_flags[2]) { lanes_off = true; continue; }   // a cell beyond LANE_CAP candidates: this build goes to the warp-per-site kernel
     if (c->h_flags[1] <= c->neigh_stride) break;
     // UCGB200_ERR_NEIGH_OVERFLOW handled internally: grow the row capacity and redo
     c->neigh_stride = ((c->h_flags[1] + c->h_flags[1] / 8 + 15) / 16) * 16;

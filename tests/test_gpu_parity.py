@@ -64,7 +64,7 @@ def _canonical_rows(nl):
     return key[o]
 
 
-@pytest.mark.parametrize("knobs", [dict(UCGB200_BUILD_TILED="0"), dict(UCGB200_TILE_CAP="64"), dict(UCGB200_TILE_CAP="200"),
+@pytest.mark.parametrize("knobs", [dict(UCGB200_BUILD_LANES="1"), dict(UCGB200_BUILD_TILED="0"), dict(UCGB200_TILE_CAP="64"), dict(UCGB200_TILE_CAP="200"),
                                    dict(UCGB200_BUILD_F32="0"), dict(UCGB200_BUILD_CULL="0"), dict(UCGB200_BUILD_F32="0", UCGB200_TILE_CAP="64"),
                                    dict(UCGB200_BUILD_F32="0", UCGB200_BUILD_DEFER_KEYS="0"),
                                    dict(UCGB200_BUILD_F32="0", UCGB200_BUILD_DEFER_KEYS="0", UCGB200_TILE_CAP="96")])
@@ -96,7 +96,8 @@ def test_neighbor_build_variants_give_identical_rows(pkg, fixtures, monkeypatch,
         nl["inner"] = (d * d).sum(1) < 2.5 ** 2
     assert np.array_equal(a["inner"], b["inner"])
     assert np.array_equal(a["neigh_tags"][a["inner"]], b["neigh_tags"][b["inner"]])
-    if ncell == 12 and knobs.get("UCGB200_BUILD_TILED") != "0" and "UCGB200_TILE_CAP" not in knobs and "UCGB200_BUILD_F32" not in knobs:
+    if "UCGB200_BUILD_LANES" in knobs or (ncell == 12 and knobs.get("UCGB200_BUILD_TILED") != "0" and "UCGB200_TILE_CAP" not in knobs and "UCGB200_BUILD_F32" not in knobs):
+        # a lane per site (UCGB200_BUILD_LANES=1) against a warp per site (default): the same rows entry for entry, whatever the cell population;
         # 20 sites per cell: both runs hold the whole stencil at once and group the skin entries by displacement level
         # (the FP64 build sorts them by distance instead: same sets, same level boundaries, another order inside a level)
         for key in ("neigh_tags", "neigh_shift"):
