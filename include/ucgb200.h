@@ -217,8 +217,9 @@ int ucgb200_pair_energy_virial(ucgb200_ctx *ctx, double *eng_vdwl, double virial
  * eatom[i] = sum_j E_ij / 2, vatom[i][0..5] = sum_j (d x d) fpair / 2 in LAMMPS' xx yy zz xy xz yz order — each site's
  * own half of every pair it is in, which is what [stock] Pair::ev_tally (pair_table_ucgld.cpp:531-533) leaves on the
  * owners after the reverse communication of the compute.  Host order; either pointer may be NULL.
- * Implemented for ucgb200_pair_ucgld and ucgb200_pair_bethe (every table style and type system); the two density
- * styles ignore the bits, and ucgb200_pair_peratom then fails. */
+ * Implemented for all four pair calls.  The two density styles run with newton off: there [stock] ev_tally gives half
+ * of every visit to the centre site and half to a LOCAL partner (pair_table_rleucg_interface.cpp:439, 488,
+ * pair_table_ucg_bethe_density.cpp:407, 510, 647, 729), and the virial of the CV back-force sweep is added. */
 int ucgb200_pair_peratom(ucgb200_ctx *ctx, int nlocal_capacity, double *eatom /*[n]*/, double *vatom /*[6n]*/);
 
 /* --------------------------------------------------------------------- fixes */

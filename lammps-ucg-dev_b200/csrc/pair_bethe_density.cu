@@ -56,6 +56,9 @@ struct BdArgs {
   double *ucgp;
   double *partials;
   ErrWord *err;
+  // per-atom tallies ([stock] ev_tally with newton off: half of every visit's energy / virial to the centre site, half to
+  // a LOCAL partner), nullptr: not asked for
+  double *eatom, *vatom;
   FastTable ft;   // shared-memory table path (W > 0)
   GatherTex gt;   // neighbor gathers through the texture pipe (0 = plain loads)
 };
@@ -113,7 +116,7 @@ __global__ void k_bd_ghost(double *__restrict__ a, int nlocal, int nlimg, const 
 
 // W = 0: tables through L1 (any type system, any table style); W = 3 / 4: the interleaved LINEAR tables
 // of the single 2-state type staged in shared memory, persistent CTAs (one per SM)
-template <int LPA, int BS, int W>
+template <int LPA, int BS, int W, bool PA>
 __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
   extern __shared__ double2 s_tab[];
   if (W) fast_table_stage<W, BS>(s_tab, p.ft);
@@ -137,6 +140,11 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
 
   double fx = 0, fy = 0, fz = 0, eacc = 0, S0 = 0, S1 = 0, pf0 = 0, pf1 = 0;
   double vir[6] = {0, 0, 0, 0, 0, 0};
+  // PA: this site's share of the tallies.  Symmetric visits (UCG-UCG, CG-CG): what the site accumulates anyway (we);
+  // a UCG centre keeps half of its visit of a CG neighbor, a CG centre receives the other half of the visit its LOCAL
+  // UCG neighbor makes (the reference skips the CG centre's own visit, :411-420)
+  double ea = 0;
+  double va[6] = {0, 0, 0, 0, 0, 0};
 
   RowWalk<LPA> rw(row, sub, jnum);
   for (int jj = sub; jj < jnum; jj += LPA, rw.advance()) {
@@ -168,6 +176,7 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
 #pragma unroll
       for (int k = 0; k < 4; k++) { u[k] *= factor_lj; f[k] *= factor_lj; }
       double e, fpair, wf, we;   // wf: weight of d*fpair in f_i; we: weight in the E / virial tally
+      double e_a = 0.0, wa = 0.0; // PA: energy of the visit this site has a share in, and the share
       if (ni == 2 && nj == 2) {
         const double pj0 = p.prob0[j], pj1 = 1.0 - pj0;
         const double J = u[3] + u[0] - u[1] - u[2];
@@ -182,6 +191,7 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
         e = p00 * u[0] + p01 * u[1] + p10 * u[2] + p11 * u[3];
         fpair = p00 * f[0] + p01 * f[1] + p10 * f[2] + p11 * f[3];
         wf = 1.0; we = 0.5;
+        e_a = e; wa = we;
         const int sj = (tsj >> 16) & 1;           // (:596-598) only the neighbor's current state is tallied
         S0 += sj ? u[1] : u[0];
         S1 += sj ? u[3] : u[2];
@@ -193,6 +203,7 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
         e = pi0 * u[0] + pi1 * u[2];
         fpair = pi0 * f[0] + pi1 * f[2];
         wf = 1.0; we = jlocal ? 1.0 : 0.5;
+        e_a = e; wa = 0.5;                         // the other half belongs to the CG neighbor
         S0 += u[0];
         S1 += u[2];
         if (bti.use_density == 1) {
@@ -206,10 +217,12 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
         e = 0.0;
         fpair = pj0 * f[0] + pj1 * f[1];
         wf = jlocal ? 1.0 : 0.0; we = 0.0;
+        e_a = pj0 * u[0] + pj1 * u[1]; wa = jlocal ? 0.5 : 0.0;   // half of the visit the local UCG neighbor makes
       } else {                                     // CG-CG (:331-405): half per visit, reaction to local j only
         e = u[0];
         fpair = 0.5 * f[0];
         wf = jlocal ? 2.0 : 1.0; we = jlocal ? 1.0 : 0.5;
+        e_a = e; wa = we;
       }
       eacc += we * e;
       const double ff = wf * fpair;
@@ -217,10 +230,25 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
       const double fv = we * fpair;
       vir[0] += dx * dx * fv; vir[1] += dy * dy * fv; vir[2] += dz * dz * fv;
       vir[3] += dx * dy * fv; vir[4] += dx * dz * fv; vir[5] += dy * dz * fv;
+      if (PA) {
+        ea += wa * e_a;
+        const double fa = wa * fpair;
+        va[0] += dx * dx * fa; va[1] += dy * dy * fa; va[2] += dz * dz * fa;
+        va[3] += dx * dy * fa; va[4] += dx * dz * fa; va[5] += dy * dz * fa;
+      }
     }
   }
   fx = group_sum<LPA>(fx); fy = group_sum<LPA>(fy); fz = group_sum<LPA>(fz);
   eacc = group_sum<LPA>(eacc);
+  if (PA) {
+    ea = group_sum<LPA>(ea);
+    if (active && sub == 0 && p.eatom) p.eatom[i] = ea;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const double a = group_sum<LPA>(va[k]);
+      if (active && sub == 0 && p.vatom) p.vatom[6 * (size_t)i + k] = a;
+    }
+  }
   S0 = group_sum<LPA>(S0); S1 = group_sum<LPA>(S1);
   pf0 = group_sum<LPA>(pf0); pf1 = group_sum<LPA>(pf1);
 #pragma unroll
@@ -254,7 +282,7 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
   block_reduce_store<7, BS>(evacc, p.partials);
 }
 
-template <int LPA, int BS>
+template <int LPA, int BS, bool PA>
 __global__ void __launch_bounds__(BS) k_bd_back(BdArgs p) {
   const int gid = (blockIdx.x * BS + threadIdx.x) / LPA;
   const int sub = threadIdx.x % LPA;
@@ -270,6 +298,7 @@ __global__ void __launch_bounds__(BS) k_bd_back(BdArgs p) {
   const PairInfo *prow = p.pinfo + ti * p.na;
   double fx = 0, fy = 0, fz = 0;
   double vir[6] = {0, 0, 0, 0, 0, 0};
+  double va[6] = {0, 0, 0, 0, 0, 0};
   for (int jj = sub; jj < jnum; jj += LPA) {
     const int j = row[rowslot(jj)] & UCG_NEIGHMASK;
     const double4 rj = p.pos[j];
@@ -290,6 +319,11 @@ __global__ void __launch_bounds__(BS) k_bd_back(BdArgs p) {
       const double w = (jlocal ? 1.0 : 0.5) * own;   // ev_tally(i,j,nlocal,newton=0,0,0,fpair,...) in i's loop (:722)
       vir[0] += w * dx * dx; vir[1] += w * dy * dy; vir[2] += w * dz * dz;
       vir[3] += w * dx * dy; vir[4] += w * dx * dz; vir[5] += w * dy * dz;
+      if (PA) {   // half of this site's visit, half of the visit of a local partner (oth is zero for a ghost)
+        const double wa = 0.5 * (own + oth);
+        va[0] += wa * dx * dx; va[1] += wa * dy * dy; va[2] += wa * dz * dz;
+        va[3] += wa * dx * dy; va[4] += wa * dx * dz; va[5] += wa * dy * dz;
+      }
     }
   }
   fx = group_sum<LPA>(fx); fy = group_sum<LPA>(fy); fz = group_sum<LPA>(fz);
@@ -298,6 +332,10 @@ __global__ void __launch_bounds__(BS) k_bd_back(BdArgs p) {
   for (int k = 0; k < 6; k++) {
     const double v = group_sum<LPA>(vir[k]);
     if (active && sub == 0) ev[1 + k] = v;
+    if (PA) {
+      const double a = group_sum<LPA>(va[k]);
+      if (active && sub == 0) p.vatom[6 * (size_t)i + k] += a;
+    }
   }
   if (active && sub == 0) {
     double4 f = p.frc[i];
@@ -344,7 +382,9 @@ extern "C" int ucgb200_pair_bethe_density(ucgb200_ctx *c, int eflag, int vflag) 
     c->ev_two_parts = false;
     return 0;
   }
-  (void)eflag; (void)vflag;
+  // energy and virial are always evaluated; bits 2 / 4 ask for the per-atom tallies (ucgb200_pair_peratom)
+  const bool want_eatom = (eflag & 2) != 0, want_vatom = (vflag & 4) != 0;
+  c->eatom_valid = c->vatom_valid = false;
   if (b.dirty) {
     std::vector<BdType> bt(b.n_actual + 1);
     for (int t = 0; t <= b.n_actual; t++) {
@@ -371,6 +411,9 @@ extern "C" int ucgb200_pair_bethe_density(ucgb200_ctx *c, int eflag, int vflag) 
   a.kT = c->kT; a.inv_kT = 1.0 / c->kT;
   a.prob0 = b.d_prob.p; a.partial0 = b.d_partial.p; a.cvf = b.d_cvf.p;
   a.frc = c->frc.p; a.scores = c->scores.p; a.ucgp = c->ucgp.p; a.partials = c->d_partials.p; a.err = c->d_err.p;
+  if (want_eatom) { UCG_CHECK(c, c->d_eatom.ensure((size_t)c->nlocal + 8)); a.eatom = c->d_eatom.p; }
+  if (want_vatom) { UCG_CHECK(c, c->d_vatom.ensure(6 * (size_t)c->nlocal + 8)); a.vatom = c->d_vatom.p; }
+  const bool pa = want_eatom || want_vatom;
   const auto &h = c->halo;
   if (c->timers_on) cudaEventRecord(c->ev_pair0, c->stream);
   k_bd_prior<LPA, BS><<<nblk, BS, 0, c->stream>>>(a);
@@ -382,7 +425,7 @@ extern "C" int ucgb200_pair_bethe_density(ucgb200_ctx *c, int eflag, int vflag) 
   if ((rc = ucg_mb_forward_scalars(c, a.prob0, nullptr, nullptr))) return rc;   // ghosts owned by other bricks
   int nblk_pair = nblk;
   const size_t tab_bytes = (size_t)c->fast_len * c->fast_ntab * sizeof(double2);
-  if (c->fast_uniform && tab_bytes <= 220 * 1024 && !(getenv("UCGB200_FORCE_GENERAL") && atoi(getenv("UCGB200_FORCE_GENERAL")))) {
+  if (!pa && c->fast_uniform && tab_bytes <= 220 * 1024 && !(getenv("UCGB200_FORCE_GENERAL") && atoi(getenv("UCGB200_FORCE_GENERAL")))) {
     // one 2-state type, LINEAR tables on one grid: interleaved rows in shared memory, persistent CTAs
     constexpr int FLPA = 4, FBS = 512;
     // a.gt stays 0: texture-pipe gathers were measured here and gave nothing (these sweeps are bound by FP64
@@ -397,25 +440,31 @@ extern "C" int ucgb200_pair_bethe_density(ucgb200_ctx *c, int eflag, int vflag) 
     UCG_CHECK(c, c->d_partials.ensure((size_t)std::max(nblk, nblk_pair) * 8 + 64));
     a.partials = c->d_partials.p;
     if (c->fast_ntab == 3) {
-      auto kern = k_bd_pair<FLPA, FBS, 3>;
+      auto kern = k_bd_pair<FLPA, FBS, 3, false>;
       UCG_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
       kern<<<nblk_pair, FBS, tab_bytes, c->stream>>>(a);
     } else {
-      auto kern = k_bd_pair<FLPA, FBS, 4>;
+      auto kern = k_bd_pair<FLPA, FBS, 4, false>;
       UCG_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
       kern<<<nblk_pair, FBS, tab_bytes, c->stream>>>(a);
     }
+  } else if (pa) {
+    // per-atom tallies are asked for on output steps only: the general kernel carries them
+    k_bd_pair<LPA, BS, 0, true><<<nblk, BS, 0, c->stream>>>(a);
   } else {
-    k_bd_pair<LPA, BS, 0><<<nblk, BS, 0, c->stream>>>(a);
+    k_bd_pair<LPA, BS, 0, false><<<nblk, BS, 0, c->stream>>>(a);
   }
   UCG_LAUNCHED(c);
   if ((rc = reduce_partials(c, nblk_pair, 7, 0))) return rc;
-  k_bd_back<LPA, BS><<<nblk, BS, 0, c->stream>>>(a);
+  if (want_vatom) k_bd_back<LPA, BS, true><<<nblk, BS, 0, c->stream>>>(a);
+  else k_bd_back<LPA, BS, false><<<nblk, BS, 0, c->stream>>>(a);
   UCG_LAUNCHED(c);
   if ((rc = reduce_partials(c, nblk, 7, 16))) return rc;   // second virial part -> d_ev[16..22]
   if (c->timers_on) { cudaEventRecord(c->ev_pair1, c->stream); c->pair_timed = true; }
   c->ev_valid = true;
   c->ev_two_parts = true;
+  c->eatom_valid = want_eatom;
+  c->vatom_valid = want_vatom;
   return 0;
 }
 

@@ -55,6 +55,9 @@ struct RleArgs {
   double4 *frc;
   double *partials;
   ErrWord *err;
+  // per-atom tallies ([stock] ev_tally with newton off: half of every visit's energy / virial to the centre site, half to
+  // a LOCAL partner), nullptr: not asked for.  The visits are symmetric, so a site's share is what it accumulates anyway.
+  double *eatom, *vatom;
   FastTable ft;   // shared-memory table path (SM = true): slot k of a row = table k
   GatherTex gt;   // neighbor gathers through the texture pipe (0 = plain loads)
 };
@@ -183,9 +186,10 @@ __global__ void __launch_bounds__(BS) k_rle_pair(RleArgs p) {
 #pragma unroll
   for (int k = 0; k < 6; k++) {
     const double v = group_sum<LPA>(vir[k]);
-    if (active && sub == 0) evacc[1 + k] += v;
+    if (active && sub == 0) { evacc[1 + k] += v; if (p.vatom) p.vatom[6 * (size_t)i + k] = v; }
   }
   if (active && sub == 0) {
+    if (p.eatom) p.eatom[i] = eacc;
     double cvf = 0.0;
     if (ni > 1) {
       // one-body terms (:296-322)
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(BS) k_rle_pair(RleArgs p) {
   block_reduce_store<7, BS>(evacc, p.partials);
 }
 
-template <int LPA, int BS>
+template <int LPA, int BS, bool PA>
 __global__ void __launch_bounds__(BS) k_rle_back(RleArgs p) {
   const int gid = (blockIdx.x * BS + threadIdx.x) / LPA;
   const int sub = threadIdx.x % LPA;
@@ -217,6 +221,7 @@ __global__ void __launch_bounds__(BS) k_rle_back(RleArgs p) {
   const PairInfo *prow = p.pinfo + ti * p.nt;
   double fx = 0, fy = 0, fz = 0;
   double vir[6] = {0, 0, 0, 0, 0, 0};
+  double va[6] = {0, 0, 0, 0, 0, 0};   // PA: this site's share of the tallies (own visits + visits of local partners)
   for (int jj = sub; jj < jnum; jj += LPA) {
     const int j = row[rowslot(jj)] & UCG_NEIGHMASK;
     const double4 rj = p.pos[j];
@@ -233,6 +238,11 @@ __global__ void __launch_bounds__(BS) k_rle_back(RleArgs p) {
       const double w = (j < p.nlocal ? 1.0 : 0.5) * own;   // ev_tally(i,j,...,fpair) in i's loop only (:488)
       vir[0] += w * dx * dx; vir[1] += w * dy * dy; vir[2] += w * dz * dz;
       vir[3] += w * dx * dy; vir[4] += w * dx * dz; vir[5] += w * dy * dz;
+      if (PA) {
+        const double wa = 0.5 * own + (j < p.nlocal ? 0.5 * oth : 0.0);
+        va[0] += wa * dx * dx; va[1] += wa * dy * dy; va[2] += wa * dz * dz;
+        va[3] += wa * dx * dy; va[4] += wa * dx * dz; va[5] += wa * dy * dz;
+      }
     }
   }
   fx = group_sum<LPA>(fx); fy = group_sum<LPA>(fy); fz = group_sum<LPA>(fz);
@@ -241,6 +251,10 @@ __global__ void __launch_bounds__(BS) k_rle_back(RleArgs p) {
   for (int k = 0; k < 6; k++) {
     const double v = group_sum<LPA>(vir[k]);
     if (active && sub == 0) ev[1 + k] = v;
+    if (PA) {
+      const double a = group_sum<LPA>(va[k]);
+      if (active && sub == 0) p.vatom[6 * (size_t)i + k] += a;
+    }
   }
   if (active && sub == 0) {
     double4 f = p.frc[i];
@@ -382,7 +396,9 @@ extern "C" int ucgb200_pair_rleucg(ucgb200_ctx *c, int eflag, int vflag) {
     c->ev_two_parts = false;
     return 0;
   }
-  (void)eflag; (void)vflag;
+  // the energy is always evaluated; bits 2 / 4 ask for the per-atom tallies (ucgb200_pair_peratom)
+  const bool want_eatom = (eflag & 2) != 0, want_vatom = (vflag & 4) != 0;
+  c->eatom_valid = c->vatom_valid = false;
   auto &d = c->dens;
   const int nall = c->nlocal + c->nghost;
   UCG_CHECK(c, d.d_prob.ensure(nall));
@@ -400,6 +416,8 @@ extern "C" int ucgb200_pair_rleucg(ucgb200_ctx *c, int eflag, int vflag) {
   a.kT = d.T;
   a.prob = d.d_prob.p; a.partial = d.d_partial.p; a.cvf = d.d_cvforce.p;
   a.frc = c->frc.p; a.partials = c->d_partials.p; a.err = c->d_err.p;
+  if (want_eatom) { UCG_CHECK(c, c->d_eatom.ensure((size_t)c->nlocal + 8)); a.eatom = c->d_eatom.p; }
+  if (want_vatom) { UCG_CHECK(c, c->d_vatom.ensure(6 * (size_t)c->nlocal + 8)); a.vatom = c->d_vatom.p; }
   const auto &h = c->halo;
   const int *lown = c->img_owner.p + h.nsend;
   if (c->timers_on) cudaEventRecord(c->ev_pair0, c->stream);
@@ -438,7 +456,8 @@ extern "C" int ucgb200_pair_rleucg(ucgb200_ctx *c, int eflag, int vflag) {
     UCG_LAUNCHED(c);
   }
   if ((rc = ucg_mb_forward_scalars(c, a.cvf, nullptr, nullptr))) return rc;
-  k_rle_back<LPA, BS><<<nblk, BS, 0, c->stream>>>(a);
+  if (want_vatom) k_rle_back<LPA, BS, true><<<nblk, BS, 0, c->stream>>>(a);
+  else k_rle_back<LPA, BS, false><<<nblk, BS, 0, c->stream>>>(a);
   UCG_LAUNCHED(c);
   if ((rc = reduce_partials(c, nblk, 7, 16))) return rc;   // second virial part -> d_ev[16..22]
   if (c->timers_on) { cudaEventRecord(c->ev_pair1, c->stream); c->pair_timed = true; }
@@ -446,6 +465,8 @@ extern "C" int ucgb200_pair_rleucg(ucgb200_ctx *c, int eflag, int vflag) {
   UCG_CHECK(c, cudaMemsetAsync(c->scores.p, 0, (size_t)c->nlocal * sizeof(double2), c->stream));
   c->ev_valid = true;
   c->ev_two_parts = true;
+  c->eatom_valid = want_eatom;
+  c->vatom_valid = want_vatom;
   return 0;
 }
 

@@ -209,15 +209,13 @@ bool PairTable_RLEUCG_INTERFACE::ucg_deck(ucgb200_deck &deck) {
 
 void PairTable_RLEUCG_INTERFACE::compute(int eflag, int vflag) {
   ev_init(eflag, vflag);
-  if (eflag_atom || vflag_atom)   // asked for, say so instead of leaving zeros in eatom / vatom
-    error->all(FLERR, "ucg-b200: per-atom energy / virial is implemented for pair_style table_ucgld and table_ucg_bethe only");
   if (!configured) configure_device();
   const int nlocal = atom->nlocal;
   dev->upload(lmp, UCGB200_F_X | UCGB200_F_UCGL | UCGB200_F_UCGSTATE | UCGB200_F_UCGP);
   dev->ensure_list(lmp);
   // the energy is always evaluated: the reference feeds a stale evdwl into the probability
   // force on steps without eflag
-  dev->check(lmp, ucgb200_pair_rleucg(dev->ctx, 1, 1), "pair_rleucg");
+  dev->check(lmp, ucgb200_pair_rleucg(dev->ctx, 1 | (eflag_atom ? 2 : 0), 1 | (vflag_atom ? 4 : 0)), "pair_rleucg");
   std::vector<double> f(3 * (size_t) nlocal);
   ucgb200_atoms h{};
   h.f = f.data();
@@ -229,6 +227,12 @@ void PairTable_RLEUCG_INTERFACE::compute(int eflag, int vflag) {
   }
   double **fh = atom->f;
   for (int i = 0; i < nlocal; i++) { fh[i][0] += f[3 * i]; fh[i][1] += f[3 * i + 1]; fh[i][2] += f[3 * i + 2]; }
+  if (eflag_atom || vflag_atom) {   // [stock] ev_tally's per-atom halves (compute pe/atom, stress/atom)
+    std::vector<double> ea(eflag_atom ? (size_t)nlocal : 0), va(vflag_atom ? 6 * (size_t)nlocal : 0);
+    dev->check(lmp, ucgb200_pair_peratom(dev->ctx, nlocal, eflag_atom ? ea.data() : nullptr, vflag_atom ? va.data() : nullptr), "pair_peratom");
+    if (eflag_atom) for (int i = 0; i < nlocal; i++) eatom[i] += ea[i];
+    if (vflag_atom) for (int i = 0; i < nlocal; i++) for (int k = 0; k < 6; k++) vatom[i][k] += va[6 * (size_t)i + k];
+  }
   double e, v[6];
   dev->check(lmp, ucgb200_pair_energy_virial(dev->ctx, &e, v), "pair_energy_virial");
   if (eflag_global) eng_vdwl += e;

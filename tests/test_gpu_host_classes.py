@@ -652,16 +652,52 @@ def test_per_atom_energy_and_virial(pkg, fixtures, tabstyle, tablength):
     assert abs(eb.sum() - Eb) <= 1e-10 * abs(Eb) and abs(Eb - Ea) <= 1e-8 * abs(Ea)
 
 
-def test_per_atom_tallies_refused_by_the_density_styles(pkg, fixtures, tmp_path):
-    """table_rleucg_interface / table_ucg_bethe_density carry no per-atom tallies on the device: asked for them, the
-    drop-in classes say so instead of leaving zeros in Pair::eatom / Pair::vatom"""
-    liq = _liq(5)
-    sf = tmp_path / "rle.conf"
-    sf.write_text("1 2\n2 density use_entropy\n12.0 1.5\n0.3\n")
+@pytest.mark.parametrize("style", ["rleucg", "rleucg_mixed_types", "bethe_density"])
+def test_per_atom_tallies_of_the_density_styles(pkg, fixtures, tmp_path, style):
+    """per-atom energy / virial of table_rleucg_interface and table_ucg_bethe_density: the reference delivers them
+    through [stock] ev_tally with newton off (pair_table_rleucg_interface.cpp:439, 488;
+    pair_table_ucg_bethe_density.cpp:407, 510, 647, 729): half of every visit to the centre site, half to a LOCAL
+    partner, nothing to a ghost.  The device keeps each site's share while it accumulates the global sums, the second
+    sweep (CV back-force) adds its virial part"""
     t = fixtures["table4096"]
-    lines = ["newton off", "neighbor 0.3 bin", "timestep 0.002", f"pair_style table_rleucg_interface linear 4096 {sf}",
-             f"pair_coeff 1 1 {t} UCG_00 2.5", f"pair_coeff 1 2 {t} UCG_01 2.5", f"pair_coeff 2 2 {t} UCG_11 2.5",
-             "fix 0 all ttarget/stub 1.0"]
-    s = _deck(rb.HostSim, liq, lines)
-    with pytest.raises(RuntimeError, match="per-atom energy / virial is implemented for pair_style table_ucgld and table_ucg_bethe only"):
+    ntypes = 2
+    if style == "rleucg":
+        liq = _liq(6)
+        sf = tmp_path / "rle.conf"
+        sf.write_text("1 2\n2 density use_entropy\n12.0 1.5\n0.3\n")
+        lines = ["newton off", "neighbor 0.3 bin", "timestep 0.002", f"pair_style table_rleucg_interface linear 4096 {sf}",
+                 f"pair_coeff 1 1 {t} UCG_00 2.5", f"pair_coeff 1 2 {t} UCG_01 2.5", f"pair_coeff 2 2 {t} UCG_11 2.5",
+                 "fix 0 all ttarget/stub 1.0"]
+    elif style == "rleucg_mixed_types":
+        import test_gpu_cluster_switch as T                  # the config-4 system: two-state sites among plain CG ones
+        liq, _ = T._system(6)
+        sf = tmp_path / "rle.conf"
+        sf.write_text(T.RLE_STATE)
+        ntypes = 4
+        lines = ["newton off", "neighbor 0.3 bin", "timestep 0.002", f"pair_style table_rleucg_interface linear 4096 {sf}"]
+        lines += [f"pair_coeff {i} {j} {t} {kw} 2.5" for i, j, kw in T.PAIRS]
+        lines += ["fix 0 all ttarget/stub 1.0"]
+    else:
+        liq = _liq(6)
+        sf = tmp_path / "bd.conf"
+        sf.write_text("1 2 2\n1 2\n1 2 density entropy \n12.0 1.5\n0.0 0.5\n")
+        lines = ["newton off", "neighbor 0.3 bin", "timestep 0.002", f"pair_style table_ucg_bethe_density linear 4096 {sf}",
+                 f"pair_coeff 1 1 2 2 {t} UCG_00 2.5 {t} UCG_01 2.5 {t} UCG_01 2.5 {t} UCG_11 2.5",
+                 "fix 0 all ttarget/stub 1.0"]
+    out = []
+    for cls in (rb.RefSim, rb.HostSim):
+        s = cls()
+        s.box(liq.box_lo, liq.box_hi, ntypes)
+        s.atoms(liq)
+        for c in lines:
+            s.command(c)
         s.compute_once(3)
+        e, v = s.pair_peratom()
+        out.append((e, v, s.eng_vdwl(), s.virial()))
+    (ea, va, Ea, Wa), (eb, vb, Eb, Wb) = out
+    assert np.abs(ea).max() > 0 and np.abs(va).max() > 0
+    assert rel_err(eb, ea) <= 1e-8, rel_err(eb, ea)
+    assert rel_err(vb, va) <= 1e-8, rel_err(vb, va)
+    assert abs(ea.sum() - Ea) <= 1e-10 * abs(Ea) and abs(eb.sum() - Eb) <= 1e-10 * abs(Eb)   # the shares add up to the totals
+    assert rel_err(vb.sum(0), Wb[0]) <= 1e-10
+    assert abs(Eb - Ea) <= 1e-8 * abs(Ea)
