@@ -257,7 +257,7 @@ def run_gpu(args):
     pair_avg = float(np.mean(pair_ms))
     # (b) the stages of the step: the SAME loop as the timed region (speculative launches on), event pairs recorded
     # without synchronisation and resolved afterwards (ucgb200_timers mode 3)
-    nstage = max(args.steps, 20)
+    nstage = min(max(args.steps, 20), 100)
     ctx.timers(3)
     ctx.run(nstage)
     tms, tl = ctx.timers(0)

@@ -447,7 +447,7 @@ def bench(args, rank, world, local, dist):
     # no speculative launch), every rank takes part in the exchanges
     stage = None
     if resident and os.environ.get("UCGB200_BENCH_STAGES", "1") != "0":
-        nst = max(args.steps, 20)
+        nst = min(max(args.steps, 20), 100)
         r0 = ctx.comm_stats()["rebuilds"]
         ctx.timers(3)          # non-blocking stage timers: the same loop as the timed region
         cl.run(nst)
