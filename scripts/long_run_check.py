@@ -26,3 +26,7 @@ for blk in range(int(os.environ.get("BLOCKS", "40"))):
         break
     t = ctx.thermo()
     print(100 * (blk + 1), "E", round(t[0], 3), "KE", round(t[7], 3), "lambdaKE", round(t[8], 3), "rebuilds", int(t[11]), flush=True)
+    if (blk + 1) % 5 == 0:
+        a = ctx.atoms_download(["ucgl", "ucgstate"])
+        print("    lambda min/mean/max", float(a["ucgl"].min()), float(a["ucgl"].mean()), float(a["ucgl"].max()),
+              "outside [0,1]:", int(((a["ucgl"] < 0) | (a["ucgl"] > 1)).sum()), "state 1:", int(a["ucgstate"].sum()), flush=True)
