@@ -136,7 +136,9 @@ __global__ void __launch_bounds__(BS) k_pair_bethe(BetheArgs p) {
         const double pj0 = 1.0 - pj1;
         double J = u[3] + u[0] - u[1] - u[2];
         if (J * p.inv_kT < -709.0) J = -700.0 * p.kT;
-        const double bij = exp(-J * p.inv_kT), aij = expm1(-J * p.inv_kT);
+        // the reference takes exp AND expm1 of the same argument (:550-551); one evaluation serves both: expm1(x) + 1
+        // is exp(x) to 1.1e-16 ABSOLUTE, and b enters p11 and D only through products with probabilities <= 1
+        const double aij = expm1(-J * p.inv_kT), bij = aij + 1.0;
         const double Q = (pi1 + pj1) * aij + 1.0;
         const double D = fmax(Q * Q - 4.0 * aij * bij * pi1 * pj1, 0.0);
         double p11;

@@ -145,6 +145,8 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
   // UCG neighbor makes (the reference skips the CG centre's own visit, :411-420)
   double ea = 0;
   double va[6] = {0, 0, 0, 0, 0, 0};
+  double lpi0 = 0.0, lpi1 = 0.0;                      // log of this site's priors, taken at the first CG neighbor
+  bool have_lpi = false;
 
   RowWalk<LPA> rw(row, sub, jnum);
   for (int jj = sub; jj < jnum; jj += LPA, rw.advance()) {
@@ -207,8 +209,9 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
         S0 += u[0];
         S1 += u[2];
         if (bti.use_density == 1) {
-          pf0 -= u[0] + p.kT * log(pi0);
-          pf1 -= u[2] + p.kT * log(pi1);
+          if (!have_lpi) { lpi0 = log(pi0); lpi1 = log(pi1); have_lpi = true; }
+          pf0 -= u[0] + p.kT * lpi0;
+          pf1 -= u[2] + p.kT * lpi1;
         }
       } else if (nj == 2) {                        // centre CG, neighbor UCG: the reference skips this visit
         // (:411-420) and lets the neighbor's own visit scatter -d*fpair here, which with newton off
@@ -308,12 +311,14 @@ __global__ void __launch_bounds__(BS) k_bd_back(BdArgs p) {
     if (rsq < prow[tj].cutsq) {
       const double r = sqrt(rsq);
       const bool jlocal = j < p.nlocal;
-      const double own = dens_i ? cvf_i * bd_prox(r, bti.r_th) / r : 0.0;               // i's loop (:713-716)
-      double oth = 0.0;                                                                   // j's loop scatters to i
-      if (jlocal) {
-        const BdType btj = p.bt[tj];
-        if (btj.use_density == 1 && p.tinfo[tj].nstates > 1) oth = p.cvf[j] * bd_prox(r, btj.r_th) / r;
-      }
+      // g(r) of both sites: ONE tanh when they share the threshold radius (sites of one actual type: the usual case)
+      const BdType btj = p.bt[tj];
+      const bool dens_j = jlocal && btj.use_density == 1 && p.tinfo[tj].nstates > 1;
+      const double rth_a = dens_i ? bti.r_th : btj.r_th;
+      const double g_a = (dens_i || dens_j) ? bd_prox(r, rth_a) : 0.0;
+      const double g_j = (dens_i && dens_j && btj.r_th != rth_a) ? bd_prox(r, btj.r_th) : g_a;
+      const double own = dens_i ? cvf_i * g_a / r : 0.0;    // i's loop (:713-716)
+      const double oth = dens_j ? p.cvf[j] * g_j / r : 0.0; // j's loop scatters to i
       const double fp = own + oth;
       fx += fp * dx; fy += fp * dy; fz += fp * dz;
       const double w = (jlocal ? 1.0 : 0.5) * own;   // ev_tally(i,j,nlocal,newton=0,0,0,fpair,...) in i's loop (:722)

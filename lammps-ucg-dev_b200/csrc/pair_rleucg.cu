@@ -231,8 +231,13 @@ __global__ void __launch_bounds__(BS) k_rle_back(RleArgs p) {
     if (rsq < prow[tj].cutsq) {
       const double r = sqrt(rsq);
       const RleType rtj = p.rt[tj];
-      const double own = rti.nstates > 1 ? cvf_i * prox_der(r, rti.r_th) / r : 0.0;     // i's loop (:478-481)
-      const double oth = rtj.nstates > 1 ? p.cvf[j] * prox_der(r, rtj.r_th) / r : 0.0;  // what j's loop scatters to i
+      // g(r) of both sites: ONE tanh when they share the threshold radius (sites of one actual type: the usual case)
+      const bool di = rti.nstates > 1, dj = rtj.nstates > 1;
+      const double rth_a = di ? rti.r_th : rtj.r_th;
+      const double g_a = (di || dj) ? prox_der(r, rth_a) : 0.0;
+      const double g_j = (di && dj && rtj.r_th != rth_a) ? prox_der(r, rtj.r_th) : g_a;
+      const double own = di ? cvf_i * g_a / r : 0.0;        // i's loop (:478-481)
+      const double oth = dj ? p.cvf[j] * g_j / r : 0.0;     // what j's loop scatters to i
       const double fp = own + oth;
       fx += fp * dx; fy += fp * dy; fz += fp * dz;
       const double w = (j < p.nlocal ? 1.0 : 0.5) * own;   // ev_tally(i,j,...,fpair) in i's loop only (:488)
