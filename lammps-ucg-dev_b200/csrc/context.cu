@@ -44,7 +44,10 @@ extern "C" int ucgb200_destroy(ucgb200_ctx *c) {
   ucgb200_comm_destroy(c);
   for (auto &e : c->stage_ring) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
   if (c->stream_dl) cudaStreamDestroy(c->stream_dl);
-  if (c->ev_dl) cudaEventDestroy(c->ev_dl);
+  if (c->stream_ul) cudaStreamDestroy(c->stream_ul);
+  for (cudaEvent_t e : c->ev_dl) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_ul) if (e) cudaEventDestroy(e);
+  if (c->ev_ul_start) cudaEventDestroy(c->ev_ul_start);
   for (auto *t : {&c->tex_pos[0], &c->tex_pos[1], &c->tex_sbits, &c->tex_ts[0], &c->tex_ts[1]}) if (t->tex) cudaDestroyTextureObject(t->tex);
   for (void *p : c->table_allocs) cudaFree(p);
   // Buf<> members are released explicitly (no destructors: buffers may be swapped)
@@ -546,8 +549,23 @@ extern "C" int ucgb200_atoms_upload(ucgb200_ctx *c, int nlocal, const ucgb200_at
   double *sd = c->stage_d.p;
   int *si = c->stage_i.p;
   const int *orig = c->orig.p;
-#define UP_D(ptr, cnt) UCG_CHECK(c, cudaMemcpyAsync(sd, (ptr), (cnt) * sizeof(double), cudaMemcpyHostToDevice, st))
-#define UP_I(ptr, cnt) UCG_CHECK(c, cudaMemcpyAsync(si, (ptr), (cnt) * sizeof(int), cudaMemcpyHostToDevice, st))
+  // the copies run on the upload stream, behind everything the context stream has queued so far (the staging slots
+  // may still be read by earlier work); each pack kernel waits for the event of its own copy
+  if (!c->stream_ul) UCG_CHECK(c, cudaStreamCreateWithFlags(&c->stream_ul, cudaStreamNonBlocking));
+  if (!c->ev_ul_start) UCG_CHECK(c, cudaEventCreateWithFlags(&c->ev_ul_start, cudaEventDisableTiming));
+  UCG_CHECK(c, cudaEventRecord(c->ev_ul_start, st));
+  UCG_CHECK(c, cudaStreamWaitEvent(c->stream_ul, c->ev_ul_start, 0));
+  int nev = 0;
+  auto copied = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream_ul);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t &ev = c->ev_ul[nev++];
+    if (!ev && (e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(ev, c->stream_ul)) != cudaSuccess) return e;
+    return cudaStreamWaitEvent(st, ev, 0);
+  };
+#define UP_D(ptr, cnt) UCG_CHECK(c, copied(sd, (ptr), (cnt) * sizeof(double)))
+#define UP_I(ptr, cnt) UCG_CHECK(c, copied(si, (ptr), (cnt) * sizeof(int)))
   if ((fields & UCGB200_F_X) && h->x) { c->maxdisp_valid = false; UP_D(h->x, 3 * n); k_pack_vec3<<<GRID1(nlocal)>>>(c->pos.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += 3 * n; c->list_valid = c->list_valid && !fresh; }
   if ((fields & UCGB200_F_UCGL) && h->ucgl) { UP_D(h->ucgl, n); k_pack_w<<<GRID1(nlocal)>>>(c->pos.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += n; }
   if ((fields & UCGB200_F_V) && h->v) { UP_D(h->v, 3 * n); k_pack_vec3<<<GRID1(nlocal)>>>(c->vel.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += 3 * n; }
@@ -621,28 +639,32 @@ int ucg_host_out_queue(ucgb200_ctx *c, unsigned mask) {
   const int nlocal = c->nlocal;
   const size_t n = nlocal;
   if (!c->stream_dl) UCG_CHECK(c, cudaStreamCreateWithFlags(&c->stream_dl, cudaStreamNonBlocking));
-  if (!c->ev_dl) UCG_CHECK(c, cudaEventCreateWithFlags(&c->ev_dl, cudaEventDisableTiming));
   // the brick's population may have grown during the step (migration): cudaFree inside ensure() waits for copies in flight
   UCG_CHECK(c, c->stage_d.ensure(16 * n + 64));
   UCG_CHECK(c, c->stage_i.ensure(6 * n + 64));
   double *sd = c->stage_d.p;
   int *si = c->stage_i.p;
   const int *orig = c->orig.p;
-  struct Copy { void *dst; const void *src; size_t bytes; };
-  std::vector<Copy> copies;
-  // slots: x 0, ucgl 3n, v 4n, ucgvl 7n, f 8n, ucgforce 11n, ucgp 12n, scores 13n (doubles); ucgstate 0 (ints)
-  if ((fields & UCGB200_F_X) && h->x) { k_unpack_vec3<<<GRID1(nlocal)>>>(sd, c->pos.p, orig, nlocal); UCG_LAUNCHED(c); copies.push_back({h->x, sd, 3 * n * sizeof(double)}); }
-  if ((fields & UCGB200_F_UCGL) && h->ucgl) { k_unpack_w<<<GRID1(nlocal)>>>(sd + 3 * n, c->pos.p, orig, nlocal); UCG_LAUNCHED(c); copies.push_back({h->ucgl, sd + 3 * n, n * sizeof(double)}); }
-  if ((fields & UCGB200_F_V) && h->v) { k_unpack_vec3<<<GRID1(nlocal)>>>(sd + 4 * n, c->vel.p, orig, nlocal); UCG_LAUNCHED(c); copies.push_back({h->v, sd + 4 * n, 3 * n * sizeof(double)}); }
-  if ((fields & UCGB200_F_UCGVL) && h->ucgvl) { k_unpack_w<<<GRID1(nlocal)>>>(sd + 7 * n, c->vel.p, orig, nlocal); UCG_LAUNCHED(c); copies.push_back({h->ucgvl, sd + 7 * n, n * sizeof(double)}); }
-  if ((fields & UCGB200_F_F) && h->f) { k_unpack_vec3<<<GRID1(nlocal)>>>(sd + 8 * n, c->frc.p, orig, nlocal); UCG_LAUNCHED(c); copies.push_back({h->f, sd + 8 * n, 3 * n * sizeof(double)}); }
-  if ((fields & UCGB200_F_UCGFORCE) && h->ucgforce) { k_unpack_w<<<GRID1(nlocal)>>>(sd + 11 * n, c->frc.p, orig, nlocal); UCG_LAUNCHED(c); copies.push_back({h->ucgforce, sd + 11 * n, n * sizeof(double)}); }
-  if ((fields & UCGB200_F_UCGP) && h->ucgp) { k_unpack_scalar_d<<<GRID1(nlocal)>>>(sd + 12 * n, c->ucgp.p, orig, nlocal); UCG_LAUNCHED(c); copies.push_back({h->ucgp, sd + 12 * n, n * sizeof(double)}); }
-  if ((fields & UCGB200_F_SCORES) && h->ucgsoftmaxscores) { k_unpack_d2<<<GRID1(nlocal)>>>(sd + 13 * n, c->scores.p, orig, nlocal); UCG_LAUNCHED(c); copies.push_back({h->ucgsoftmaxscores, sd + 13 * n, 2 * n * sizeof(double)}); }
-  if ((fields & UCGB200_F_UCGSTATE) && h->ucgstate) { k_unpack_ts<<<GRID1(nlocal)>>>(si, c->ts.p, orig, nlocal, 1, nullptr); UCG_LAUNCHED(c); copies.push_back({h->ucgstate, si, n * sizeof(int)}); }
-  UCG_CHECK(c, cudaEventRecord(c->ev_dl, c->stream));
-  UCG_CHECK(c, cudaStreamWaitEvent(c->stream_dl, c->ev_dl, 0));
-  for (const Copy &cp : copies) UCG_CHECK(c, cudaMemcpyAsync(cp.dst, cp.src, cp.bytes, cudaMemcpyDeviceToHost, c->stream_dl));
+  // slots: x 0, ucgl 3n, v 4n, ucgvl 7n, f 8n, ucgforce 11n, ucgp 12n, scores 13n (doubles); ucgstate 0 (ints).
+  // Every field's copy waits for its own gather only.
+  int nev = 0;
+  auto leave = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+    cudaEvent_t &ev = c->ev_dl[nev++];
+    cudaError_t e;
+    if (!ev && (e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(ev, c->stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(c->stream_dl, ev, 0)) != cudaSuccess) return e;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream_dl);
+  };
+  if ((fields & UCGB200_F_X) && h->x) { k_unpack_vec3<<<GRID1(nlocal)>>>(sd, c->pos.p, orig, nlocal); UCG_LAUNCHED(c); UCG_CHECK(c, leave(h->x, sd, 3 * n * sizeof(double))); }
+  if ((fields & UCGB200_F_UCGL) && h->ucgl) { k_unpack_w<<<GRID1(nlocal)>>>(sd + 3 * n, c->pos.p, orig, nlocal); UCG_LAUNCHED(c); UCG_CHECK(c, leave(h->ucgl, sd + 3 * n, n * sizeof(double))); }
+  if ((fields & UCGB200_F_V) && h->v) { k_unpack_vec3<<<GRID1(nlocal)>>>(sd + 4 * n, c->vel.p, orig, nlocal); UCG_LAUNCHED(c); UCG_CHECK(c, leave(h->v, sd + 4 * n, 3 * n * sizeof(double))); }
+  if ((fields & UCGB200_F_UCGVL) && h->ucgvl) { k_unpack_w<<<GRID1(nlocal)>>>(sd + 7 * n, c->vel.p, orig, nlocal); UCG_LAUNCHED(c); UCG_CHECK(c, leave(h->ucgvl, sd + 7 * n, n * sizeof(double))); }
+  if ((fields & UCGB200_F_F) && h->f) { k_unpack_vec3<<<GRID1(nlocal)>>>(sd + 8 * n, c->frc.p, orig, nlocal); UCG_LAUNCHED(c); UCG_CHECK(c, leave(h->f, sd + 8 * n, 3 * n * sizeof(double))); }
+  if ((fields & UCGB200_F_UCGFORCE) && h->ucgforce) { k_unpack_w<<<GRID1(nlocal)>>>(sd + 11 * n, c->frc.p, orig, nlocal); UCG_LAUNCHED(c); UCG_CHECK(c, leave(h->ucgforce, sd + 11 * n, n * sizeof(double))); }
+  if ((fields & UCGB200_F_UCGP) && h->ucgp) { k_unpack_scalar_d<<<GRID1(nlocal)>>>(sd + 12 * n, c->ucgp.p, orig, nlocal); UCG_LAUNCHED(c); UCG_CHECK(c, leave(h->ucgp, sd + 12 * n, n * sizeof(double))); }
+  if ((fields & UCGB200_F_SCORES) && h->ucgsoftmaxscores) { k_unpack_d2<<<GRID1(nlocal)>>>(sd + 13 * n, c->scores.p, orig, nlocal); UCG_LAUNCHED(c); UCG_CHECK(c, leave(h->ucgsoftmaxscores, sd + 13 * n, 2 * n * sizeof(double))); }
+  if ((fields & UCGB200_F_UCGSTATE) && h->ucgstate) { k_unpack_ts<<<GRID1(nlocal)>>>(si, c->ts.p, orig, nlocal, 1, nullptr); UCG_LAUNCHED(c); UCG_CHECK(c, leave(h->ucgstate, si, n * sizeof(int))); }
   c->host_out_done |= fields;
   return 0;
 }

@@ -268,7 +268,11 @@ struct ucgb200_ctx {
   ucgb200_atoms *host_out = nullptr;
   unsigned host_out_fields = 0, host_out_done = 0;
   cudaStream_t stream_dl = nullptr;
-  cudaEvent_t ev_dl = nullptr;
+  cudaEvent_t ev_dl[10] = {};      // one per result field: a field's copy starts as soon as its own gather has run
+  // uploads: the host->device copies queue back to back on their own stream, every pack kernel (context stream) waits
+  // for its own copy only, so the link never idles behind a pack kernel
+  cudaStream_t stream_ul = nullptr;
+  cudaEvent_t ev_ul_start = nullptr, ev_ul[16] = {};
   void *comm_state = nullptr;  // comm.cu: NCCL communicator + exchange buffers of a multi-brick run
   bool ev_two_parts = false;   // d_ev[16..22] holds a second virial part to be added (rleucg)
 };
