@@ -3,6 +3,7 @@
 #include "ucg_internal.cuh"
 
 #include <algorithm>
+#include <functional>
 #include <cmath>
 
 using namespace ucg;
@@ -514,7 +515,8 @@ static int ensure_atom_capacity(ucgb200_ctx *c, size_t nall, size_t nloc) {
 }
 int ucg_ensure_atom_capacity(ucgb200_ctx *c, size_t nall, size_t nloc) { return ensure_atom_capacity(c, nall, nloc); }
 
-extern "C" int ucgb200_atoms_upload(ucgb200_ctx *c, int nlocal, const ucgb200_atoms *h, unsigned fields) {
+// after_xv (ucgb200_step_host): called once the pack kernels of x and v are queued, before the other fields' packs
+static int upload_impl(ucgb200_ctx *c, int nlocal, const ucgb200_atoms *h, unsigned fields, const std::function<int()> *after_xv) {
   if (!c || !h || nlocal < 0) return -1;
   cudaSetDevice(c->device);
   cudaStream_t st = c->stream;
@@ -541,11 +543,13 @@ extern "C" int ucgb200_atoms_upload(ucgb200_ctx *c, int nlocal, const ucgb200_at
     UCG_CHECK(c, cudaStreamSynchronize(st));
   }
   if (nlocal == 0) return 0;
-  // device staging: every field gets its own slot, so the H2D copies queue back to back (true DMA
-  // when the host arrays are pinned) and each pack kernel only waits for its own copy
+  // device staging: every field has its own fixed slot (the same slots the result gathers of ucgb200_step_host use:
+  // x 0, ucgl 3n, v 4n, ucgvl 7n, f 8n, ucgforce 11n, ucgp 12n, scores 13n, ucgml 15n doubles; ucgstate 0, type n,
+  // mask 2n, tag 3n, molecule 4n ints), so the H2D copies queue back to back (true DMA when the host arrays are
+  // pinned) and each pack kernel only waits for its own copy
   size_t n = nlocal;
   UCG_CHECK(c, c->stage_d.ensure(16 * n + 64));
-  UCG_CHECK(c, c->stage_i.ensure(5 * n + 64));
+  UCG_CHECK(c, c->stage_i.ensure(6 * n + 64));
   double *sd = c->stage_d.p;
   int *si = c->stage_i.p;
   const int *orig = c->orig.p;
@@ -564,25 +568,30 @@ extern "C" int ucgb200_atoms_upload(ucgb200_ctx *c, int nlocal, const ucgb200_at
     if ((e = cudaEventRecord(ev, c->stream_ul)) != cudaSuccess) return e;
     return cudaStreamWaitEvent(st, ev, 0);
   };
-#define UP_D(ptr, cnt) UCG_CHECK(c, copied(sd, (ptr), (cnt) * sizeof(double)))
-#define UP_I(ptr, cnt) UCG_CHECK(c, copied(si, (ptr), (cnt) * sizeof(int)))
-  if ((fields & UCGB200_F_X) && h->x) { c->maxdisp_valid = false; UP_D(h->x, 3 * n); k_pack_vec3<<<GRID1(nlocal)>>>(c->pos.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += 3 * n; c->list_valid = c->list_valid && !fresh; }
-  if ((fields & UCGB200_F_UCGL) && h->ucgl) { UP_D(h->ucgl, n); k_pack_w<<<GRID1(nlocal)>>>(c->pos.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += n; }
-  if ((fields & UCGB200_F_V) && h->v) { UP_D(h->v, 3 * n); k_pack_vec3<<<GRID1(nlocal)>>>(c->vel.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += 3 * n; }
-  if ((fields & UCGB200_F_UCGVL) && h->ucgvl) { UP_D(h->ucgvl, n); k_pack_w<<<GRID1(nlocal)>>>(c->vel.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += n; }
-  if ((fields & UCGB200_F_F) && h->f) { UP_D(h->f, 3 * n); k_pack_vec3<<<GRID1(nlocal)>>>(c->frc.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += 3 * n; }
-  if ((fields & UCGB200_F_UCGFORCE) && h->ucgforce) { UP_D(h->ucgforce, n); k_pack_w<<<GRID1(nlocal)>>>(c->frc.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += n; }
-  if ((fields & UCGB200_F_SCORES) && h->ucgsoftmaxscores) { UP_D(h->ucgsoftmaxscores, 2 * n); k_pack_d2<<<GRID1(nlocal)>>>(c->scores.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += 2 * n; }
-  if ((fields & UCGB200_F_UCGML) && h->ucgml) { UP_D(h->ucgml, n); k_pack_scalar_d<<<GRID1(nlocal)>>>(c->ucgml.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += n; }
-  if ((fields & UCGB200_F_UCGP) && h->ucgp) { UP_D(h->ucgp, n); k_pack_scalar_d<<<GRID1(nlocal)>>>(c->ucgp.p, sd, orig, nlocal); UCG_LAUNCHED(c); sd += n; }
-  if ((fields & UCGB200_F_TYPE) && h->type) { UP_I(h->type, n); k_pack_ts<<<GRID1(nlocal)>>>(c->ts.p, si, orig, nlocal, 0); UCG_LAUNCHED(c); si += n; }
-  if ((fields & UCGB200_F_UCGSTATE) && h->ucgstate) { UP_I(h->ucgstate, n); k_pack_ts<<<GRID1(nlocal)>>>(c->ts.p, si, orig, nlocal, 1); UCG_LAUNCHED(c); si += n; }
-  if ((fields & UCGB200_F_MASK) && h->mask) { UP_I(h->mask, n); k_pack_scalar_i<<<GRID1(nlocal)>>>(c->mask.p, si, orig, nlocal); UCG_LAUNCHED(c); si += n; }
-  if ((fields & UCGB200_F_TAG) && h->tag) { UP_I(h->tag, n); k_pack_scalar_i<<<GRID1(nlocal)>>>(c->tag.p, si, orig, nlocal); UCG_LAUNCHED(c); si += n; }
-  if ((fields & UCGB200_F_MOLECULE) && h->molecule) { UP_I(h->molecule, n); k_pack_scalar_i<<<GRID1(nlocal)>>>(c->mol.p, si, orig, nlocal); UCG_LAUNCHED(c); si += n; }
+#define UP_D(slot, ptr, cnt) UCG_CHECK(c, copied(sd + (slot), (ptr), (cnt) * sizeof(double)))
+#define UP_I(slot, ptr, cnt) UCG_CHECK(c, copied(si + (slot), (ptr), (cnt) * sizeof(int)))
+  if ((fields & UCGB200_F_X) && h->x) { c->maxdisp_valid = false; UP_D(0, h->x, 3 * n); k_pack_vec3<<<GRID1(nlocal)>>>(c->pos.p, sd, orig, nlocal); UCG_LAUNCHED(c); c->list_valid = c->list_valid && !fresh; }
+  if ((fields & UCGB200_F_V) && h->v) { UP_D(4 * n, h->v, 3 * n); k_pack_vec3<<<GRID1(nlocal)>>>(c->vel.p, sd + 4 * n, orig, nlocal); UCG_LAUNCHED(c); }
+  if (after_xv) { int rc = (*after_xv)(); if (rc) return rc; }
+  if ((fields & UCGB200_F_UCGL) && h->ucgl) { UP_D(3 * n, h->ucgl, n); k_pack_w<<<GRID1(nlocal)>>>(c->pos.p, sd + 3 * n, orig, nlocal); UCG_LAUNCHED(c); }
+  if ((fields & UCGB200_F_UCGVL) && h->ucgvl) { UP_D(7 * n, h->ucgvl, n); k_pack_w<<<GRID1(nlocal)>>>(c->vel.p, sd + 7 * n, orig, nlocal); UCG_LAUNCHED(c); }
+  if ((fields & UCGB200_F_F) && h->f) { UP_D(8 * n, h->f, 3 * n); k_pack_vec3<<<GRID1(nlocal)>>>(c->frc.p, sd + 8 * n, orig, nlocal); UCG_LAUNCHED(c); }
+  if ((fields & UCGB200_F_UCGFORCE) && h->ucgforce) { UP_D(11 * n, h->ucgforce, n); k_pack_w<<<GRID1(nlocal)>>>(c->frc.p, sd + 11 * n, orig, nlocal); UCG_LAUNCHED(c); }
+  if ((fields & UCGB200_F_SCORES) && h->ucgsoftmaxscores) { UP_D(13 * n, h->ucgsoftmaxscores, 2 * n); k_pack_d2<<<GRID1(nlocal)>>>(c->scores.p, sd + 13 * n, orig, nlocal); UCG_LAUNCHED(c); }
+  if ((fields & UCGB200_F_UCGML) && h->ucgml) { UP_D(15 * n, h->ucgml, n); k_pack_scalar_d<<<GRID1(nlocal)>>>(c->ucgml.p, sd + 15 * n, orig, nlocal); UCG_LAUNCHED(c); }
+  if ((fields & UCGB200_F_UCGP) && h->ucgp) { UP_D(12 * n, h->ucgp, n); k_pack_scalar_d<<<GRID1(nlocal)>>>(c->ucgp.p, sd + 12 * n, orig, nlocal); UCG_LAUNCHED(c); }
+  if ((fields & UCGB200_F_TYPE) && h->type) { UP_I(n, h->type, n); k_pack_ts<<<GRID1(nlocal)>>>(c->ts.p, si + n, orig, nlocal, 0); UCG_LAUNCHED(c); }
+  if ((fields & UCGB200_F_UCGSTATE) && h->ucgstate) { UP_I(0, h->ucgstate, n); k_pack_ts<<<GRID1(nlocal)>>>(c->ts.p, si, orig, nlocal, 1); UCG_LAUNCHED(c); }
+  if ((fields & UCGB200_F_MASK) && h->mask) { UP_I(2 * n, h->mask, n); k_pack_scalar_i<<<GRID1(nlocal)>>>(c->mask.p, si + 2 * n, orig, nlocal); UCG_LAUNCHED(c); }
+  if ((fields & UCGB200_F_TAG) && h->tag) { UP_I(3 * n, h->tag, n); k_pack_scalar_i<<<GRID1(nlocal)>>>(c->tag.p, si + 3 * n, orig, nlocal); UCG_LAUNCHED(c); }
+  if ((fields & UCGB200_F_MOLECULE) && h->molecule) { UP_I(4 * n, h->molecule, n); k_pack_scalar_i<<<GRID1(nlocal)>>>(c->mol.p, si + 4 * n, orig, nlocal); UCG_LAUNCHED(c); }
 #undef UP_D
 #undef UP_I
   return 0;
+}
+
+extern "C" int ucgb200_atoms_upload(ucgb200_ctx *c, int nlocal, const ucgb200_atoms *h, unsigned fields) {
+  return upload_impl(c, nlocal, h, fields, nullptr);
 }
 
 extern "C" int ucgb200_atoms_download(ucgb200_ctx *c, int cap, ucgb200_atoms *h, unsigned fields) {
@@ -677,13 +686,37 @@ extern "C" int ucgb200_step_host(ucgb200_ctx *c, const ucgb200_atoms *in, unsign
                              UCGB200_F_UCGP | UCGB200_F_UCGFORCE | UCGB200_F_SCORES;
   if (out_fields & ~supported) return fail(c, "step_host: out_fields holds a field that a step does not produce");
   cudaSetDevice(c->device);
-  int rc = ucgb200_atoms_upload(c, c->nlocal, in, in_fields);
-  if (rc) return rc;
   // the staging slots of the results lie behind those of the inputs' pack kernels in stream order
   c->host_out = out;
   c->host_out_fields = out_fields;
   c->host_out_done = 0;
+  // One brick with an integrator fix: the {x, v} half of this step's initial_integrate runs as soon as x and v have
+  // landed, and the new positions start back to the host while lambda, v_lambda and the states are still crossing PCIe
+  // in the other direction; the {lambda, v_lambda} half follows their pack kernels (the halves are independent
+  // components: bit-identical to the one-kernel stage).  Positions that a rebuild then wraps into the box leave a second
+  // time after the build (run.cu).  Opt-in (UCGB200_E2E_SPLIT=1): measured SLOWER at 1 M sites, 3.72 against 3.59 ms per
+  // step — with both directions of the link busy each runs below its one-way rate, and the results' copies still end
+  // with v, which exists only after the last stage.
+  const ucgb200_deck &d = c->deck;
+  const bool split = d.nve && c->halo.nranks <= 1 && c->nlocal > 0 && (in_fields & UCGB200_F_X) && in->x && (in_fields & UCGB200_F_V) && in->v &&
+                     getenv("UCGB200_E2E_SPLIT") && atoi(getenv("UCGB200_E2E_SPLIT")) == 1;
+  const int gb = d.nve_groupbit ? d.nve_groupbit : 1;
+  const double dtv = c->dt, dtf = 0.5 * c->dt * c->ftm2v;
+  int rc;
+  if (split) {
+    const std::function<int()> after_xv = [&]() -> int {
+      int r = ucg_nve_initial_part(c, dtv, dtf, gb, d.nve == 2, 1);
+      if (!r) r = ucg_host_out_queue(c, UCGB200_F_X);
+      return r;
+    };
+    rc = upload_impl(c, c->nlocal, in, in_fields, &after_xv);
+    if (!rc) rc = ucg_nve_initial_part(c, dtv, dtf, gb, d.nve == 2, 2);
+    c->skip_initial_once = !rc;
+  } else
+    rc = ucgb200_atoms_upload(c, c->nlocal, in, in_fields);
+  if (rc) { c->host_out = nullptr; c->skip_initial_once = false; return rc; }
   rc = ucgb200_run(c, 1);
+  c->skip_initial_once = false;
   if (!rc) rc = ucg_host_out_queue(c, ~0u);     // everything that could not leave earlier
   c->host_out = nullptr;
   if (c->stream_dl) {

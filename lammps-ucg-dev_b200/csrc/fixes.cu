@@ -13,7 +13,10 @@ namespace {
 
 // v += dtf/m * f ; x += dtv * v ; vl += dtf/ml * fl ; l += dtv * vl      (fix_nve_ucgld.cpp:83-99)
 // wall: ucgstate = (l < 0.5) ? 0 : 1                     (fix_nve_ucgld_wall_hard.cpp:125-131)
-template <bool WALL>
+// PART: 0 the whole stage; 1 the {x, v} components only; 2 the {lambda, v_lambda} components (and the wall's state) only —
+// the components are independent, so 1 followed by 2 is the stage bit for bit (ucgb200_step_host starts on {x, v} while
+// lambda is still crossing PCIe)
+template <bool WALL, int PART>
 __global__ void k_nve_initial(double4 *__restrict__ pos, double4 *__restrict__ vel, const double4 *__restrict__ frc,
                               int *__restrict__ ts, const int *__restrict__ mask, const double *__restrict__ ucgml,
                               const TypeInfo *__restrict__ tinfo, int n, double dtv, double dtf, int groupbit) {
@@ -23,14 +26,18 @@ __global__ void k_nve_initial(double4 *__restrict__ pos, double4 *__restrict__ v
   double4 x = pos[i], v = vel[i];
   const double4 f = frc[i];
   int t = ts[i];
-  const double dtfm = dtf / tinfo[t & 0xffff].mass;
-  v.x += dtfm * f.x; v.y += dtfm * f.y; v.z += dtfm * f.z;
-  x.x += dtv * v.x; x.y += dtv * v.y; x.z += dtv * v.z;
-  const double dtflm = dtf / ucgml[i];
-  v.w += dtflm * f.w;
-  x.w += dtv * v.w;
+  if (PART != 2) {
+    const double dtfm = dtf / tinfo[t & 0xffff].mass;
+    v.x += dtfm * f.x; v.y += dtfm * f.y; v.z += dtfm * f.z;
+    x.x += dtv * v.x; x.y += dtv * v.y; x.z += dtv * v.z;
+  }
+  if (PART != 1) {
+    const double dtflm = dtf / ucgml[i];
+    v.w += dtflm * f.w;
+    x.w += dtv * v.w;
+  }
   pos[i] = x; vel[i] = v;
-  if (WALL) ts[i] = (t & 0xffff) | ((x.w < 0.5 ? 0 : 1) << 16);
+  if (WALL && PART != 1) ts[i] = (t & 0xffff) | ((x.w < 0.5 ? 0 : 1) << 16);
 }
 
 // v += dtf/m * f ; vl += dtf/ml * fl                                   (fix_nve_ucgld.cpp:139-151)
@@ -264,21 +271,24 @@ __global__ void __launch_bounds__(BS) k_kinetic(const double4 *__restrict__ vel,
 
 #define GRID1(n) nblocks((n), 256), 256, 0, c->stream
 
-extern "C" int ucgb200_fix_nve_initial(ucgb200_ctx *c, double dtv, double dtf, int groupbit, int wall) {
+int ucg_nve_initial_part(ucgb200_ctx *c, double dtv, double dtf, int groupbit, int wall, int part) {
   if (!c) return -1;
   cudaSetDevice(c->device);
   c->maxdisp_valid = false;   // sites move: the displacement bound is stale until the next check_distance
   int rc = rebuild_maps(c);
   if (rc) return rc;
   if (c->nlocal == 0) return 0;
-  if (wall)
-    k_nve_initial<true><<<GRID1(c->nlocal)>>>(c->pos.p, c->vel.p, c->frc.p, c->ts.p, c->mask.p, c->ucgml.p,
-                                              c->d_typeinfo.p, c->nlocal, dtv, dtf, groupbit);
-  else
-    k_nve_initial<false><<<GRID1(c->nlocal)>>>(c->pos.p, c->vel.p, c->frc.p, c->ts.p, c->mask.p, c->ucgml.p,
-                                               c->d_typeinfo.p, c->nlocal, dtv, dtf, groupbit);
+#define NVE_INITIAL(W, P) k_nve_initial<W, P><<<GRID1(c->nlocal)>>>(c->pos.p, c->vel.p, c->frc.p, c->ts.p, c->mask.p, c->ucgml.p, \
+                                                                   c->d_typeinfo.p, c->nlocal, dtv, dtf, groupbit)
+  if (wall) { if (part == 0) NVE_INITIAL(true, 0); else if (part == 1) NVE_INITIAL(true, 1); else NVE_INITIAL(true, 2); }
+  else { if (part == 0) NVE_INITIAL(false, 0); else if (part == 1) NVE_INITIAL(false, 1); else NVE_INITIAL(false, 2); }
+#undef NVE_INITIAL
   UCG_LAUNCHED(c);
   return 0;
+}
+
+extern "C" int ucgb200_fix_nve_initial(ucgb200_ctx *c, double dtv, double dtf, int groupbit, int wall) {
+  return ucg_nve_initial_part(c, dtv, dtf, groupbit, wall, 0);
 }
 
 extern "C" int ucgb200_fix_nve_final(ucgb200_ctx *c, double dtf, int groupbit, int wall) {

@@ -201,11 +201,12 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
   for (int n = 0; n < nsteps; n++) {
     c->ntimestep++;
     const int ev = d.thermo_every > 0 && (c->ntimestep % d.thermo_every == 0);
-    if (!pre_integrated) {
+    if (!pre_integrated && !(n == 0 && c->skip_initial_once)) {   // ucgb200_step_host may have run it under its uploads
       StageTimer t(c, 3);
       if (d.nve) { if ((rc = ucgb200_fix_nve_initial(c, dtv, dtf, gb, d.nve == 2))) return rc; }
       t.stop();
     }
+    c->skip_initial_once = false;
     int flag = 0;
     bool pair_in_flight = false, forward_done = false;
     const bool cluster_due = d.cluster_freq > 0 && c->cluster.set && c->cluster.next_reneighbor == c->ntimestep;
@@ -281,7 +282,11 @@ extern "C" int ucgb200_run_between(ucgb200_ctx *c, int nsteps, long long beginst
       flag = 1;
       t.stop();
     }
-    if (flag) { if ((rc = do_build(c))) return rc; c->last_maxdisp = 0.0; }
+    if (flag) {
+      if ((rc = do_build(c))) return rc;
+      c->last_maxdisp = 0.0;
+      c->host_out_done &= ~UCGB200_F_X;   // positions that left before the decision (ucgb200_step_host) leave again, wrapped
+    }
     else if (!pair_in_flight && !forward_done) {
       StageTimer t(c, 2);
       if ((rc = do_forward(c))) return rc;

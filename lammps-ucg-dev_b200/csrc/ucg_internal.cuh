@@ -267,6 +267,7 @@ struct ucgb200_ctx {
   // ucgb200_step_host: results leave on a second stream while the step is still running
   ucgb200_atoms *host_out = nullptr;
   unsigned host_out_fields = 0, host_out_done = 0;
+  bool skip_initial_once = false;  // ucgb200_step_host already ran this step's initial_integrate (in two parts, under the uploads)
   cudaStream_t stream_dl = nullptr;
   cudaEvent_t ev_dl[10] = {};      // one per result field: a field's copy starts as soon as its own gather has run
   // uploads: the host->device copies queue back to back on their own stream, every pack kernel (context stream) waits
@@ -433,6 +434,7 @@ struct UcgPushTargets {
 int ucg_classify_rows(ucgb200_ctx *c);                                // neighbor.cu: fills site_list / d_part of the current list
 int ucg_halo_push_forward(ucgb200_ctx *c, const UcgPushTargets &t);   // neighbor.cu
 int ucg_halo_wait_reduce(ucgb200_ctx *c, const UcgP2PCtl *ctl_mine, int nranks, int self, int seq);   // neighbor.cu
+int ucg_nve_initial_part(ucgb200_ctx *c, double dtv, double dtf, int groupbit, int wall, int part);   // fixes.cu: 1 {x,v}, 2 {lambda,v_lambda}
 int ucg_host_out_queue(ucgb200_ctx *c, unsigned mask);   // context.cu: gather + D2H of the not yet delivered fields in mask
 int ucg_dump_pack_device(ucgb200_ctx *c, const ucgb200_dump_spec *sp, long long *nrows);   // dump.cu
 int ucg_mb_forward_scalars(ucgb200_ctx *c, double *a0, double *a1, double *a2);   // comm.cu

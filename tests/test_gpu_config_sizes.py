@@ -199,3 +199,39 @@ def test_rleucg_at_1M_against_reference(pkg, fixtures, tmp_path):
     assert abs(e - ref.eng_vdwl()) <= E_TOL * abs(ref.eng_vdwl())
     assert rel_err(vir, ref.virial()[0]) <= E_TOL
     assert ctx.status()[0] == 0
+
+
+# ------------------------------------------------------------------ configs[0] at its full length: 1000 steps
+def test_config0_1000_steps_against_the_reference_golden(pkg, fixtures):
+    """BASELINE configs[0] as the reference runs it: 32 000 sites, table_ucgld + fix nve/ucgld + fix ucgstate, 1000 steps.
+    The golden vector (tests/golden/ucg_ref_config0_1000steps.npz, made by tests/golden/make_golden_config0.py from the
+    reference's own UCG/*.cpp) holds the reference's rebuild count, pair energy, every 16th site's final x / v / lambda /
+    ucgp and every site's state.  The deterministic deck relaxes lambda instead of thermalising it, so last-bit
+    differences stay small over the whole run (measured: energy 2e-13, positions 1e-11): the resident loop — 47 neighbor
+    rebuilds, 1000 pair evaluations and fused tails — must land on the reference's final state."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ucg_ref_config0_1000steps.npz"))
+    liq = _liq(int(g["ncell"]))
+    nsteps = int(g["nsteps"])
+    ctx = decks.gpu_single_type(pkg, liq, fixtures, tablength=int(g["tablength"]))
+    ctx.deck_configure(pair_style=0, nve=1, ucgstate=1, thermo_every=nsteps)
+    ctx.setup()
+    ctx.run(nsteps)
+    th = ctx.thermo()
+    assert ctx.status()[0] == 0
+    assert int(th[11]) == int(g["rebuilds"])            # Neighbor::decide fired on the same 47 steps
+    assert abs(th[0] - float(g["eng_vdwl"])) <= E_TOL * abs(float(g["eng_vdwl"]))
+    got = ctx.atoms_download(["x", "v", "ucgl", "ucgp", "ucgstate", "tag"])
+    order = np.argsort(got["tag"])
+    sub = order[::int(g["every"])]
+    assert np.array_equal(got["tag"][sub], g["tag"])
+    box = g["box_hi"] - g["box_lo"]
+    dx = got["x"][sub] - g["x"]
+    dx -= box * np.round(dx / box)
+    assert np.abs(dx).max() <= 1e-8
+    assert rel_err(got["v"][sub], g["v"]) <= 1e-7
+    assert np.abs(got["ucgl"][sub] - g["ucgl"]).max() <= 1e-9
+    assert np.abs(got["ucgp"][sub] - g["ucgp"]).max() <= 1e-9
+    ref_state = np.unpackbits(g["ucgstate_bits"])[:liq.n].astype(np.int32)
+    far = np.abs(got["ucgp"][order] - 0.5) > 1e-7             # a state may only differ where its probability sits on 1/2
+    assert np.array_equal(got["ucgstate"][order][far], ref_state[far])

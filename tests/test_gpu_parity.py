@@ -678,10 +678,13 @@ def test_neighbor_f32_prefilter_is_exact_at_the_thresholds(pkg, fixtures, monkey
 @pytest.mark.parametrize("deck", [dict(nve=1, langevin=1, t_start=1.0, t_stop=1.0, t_period=1.0, langevin_seed=5, ucgstate=2),
                                   dict(nve=2, wall_bias=1, wall_barrier=0.1, ucgstate=1),
                                   dict(nve=1, ucgstate=1)])
-def test_step_host_equals_upload_run_download(pkg, fixtures, deck):
+@pytest.mark.parametrize("split", ["0", "1"])
+def test_step_host_equals_upload_run_download(pkg, fixtures, deck, split, monkeypatch):
     """ucgb200_step_host (results leave on a second stream while the step still runs: x under the pair kernel, f under
     the fix stages) must deliver bit for bit what upload + run(1) + download deliver, over steps that include rebuilds,
-    for decks whose later stages do and do not rewrite lambda / the state"""
+    for decks whose later stages do and do not rewrite lambda / the state.  split = 1: the opt-in variant that runs
+    initial_integrate in two halves under the uploads and sends x back before the rebuild decision (again after a rebuild)"""
+    monkeypatch.setenv("UCGB200_E2E_SPLIT", split)
     liq = _liq(9, T=2.0)
     n = liq.n
     ins = ("x", "v", "ucgl", "ucgvl", "ucgstate")
