@@ -59,6 +59,7 @@ struct BdArgs {
   // per-atom tallies ([stock] ev_tally with newton off: half of every visit's energy / virial to the centre site, half to
   // a LOCAL partner), nullptr: not asked for
   double *eatom, *vatom;
+  int logsum;     // 0 one logarithm per ratio, 1 (default) running product with exponent renormalisation, 2 one logarithm per 4 ratios
   FastTable ft;   // shared-memory table path (W > 0)
   GatherTex gt;   // neighbor gathers through the texture pipe (0 = plain loads)
 };
@@ -145,6 +146,15 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
   // UCG neighbor makes (the reference skips the CG centre's own visit, :411-420)
   double ea = 0;
   double va[6] = {0, 0, 0, 0, 0, 0};
+  double R0 = 1.0, R1 = 1.0;
+  int E0 = 0, E1 = 0, nfac = 0;
+  auto renorm = [](double &r, int &e) {
+    const int hi = __double2hiint(r), ex = (hi >> 20) & 0x7ff;
+    if (ex != 0 && ex != 0x7ff) {
+      r = __hiloint2double((hi & (int)0x800fffff) | (1023 << 20), __double2loint(r));
+      e += ex - 1023;
+    }
+  };
   double lpi0 = 0.0, lpi1 = 0.0;                      // log of this site's priors, taken at the first CG neighbor
   bool have_lpi = false;
 
@@ -198,8 +208,21 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
         S0 += sj ? u[1] : u[0];
         S1 += sj ? u[3] : u[2];
         if (bti.use_density == 1) {
-          pf0 -= (u[2] - u[0] + p.kT * log(p10 / p00));
-          pf1 -= (u[3] - u[1] + p.kT * log(p11 / p01));
+          if (p.logsum == 0) {
+            pf0 -= (u[2] - u[0] + p.kT * log(p10 / p00));
+            pf1 -= (u[3] - u[1] + p.kT * log(p11 / p01));
+          } else if (p.logsum == 1) {
+            pf0 -= u[2] - u[0];
+            pf1 -= u[3] - u[1];
+            R0 *= p10 / p00; renorm(R0, E0);
+            R1 *= p11 / p01; renorm(R1, E1);
+          } else {
+            pf0 -= u[2] - u[0];
+            pf1 -= u[3] - u[1];
+            R0 *= p10 / p00;
+            R1 *= p11 / p01;
+            if (++nfac == 4) { pf0 -= p.kT * log(R0); pf1 -= p.kT * log(R1); R0 = R1 = 1.0; nfac = 0; }
+          }
         }
       } else if (ni == 2) {                        // centre UCG, neighbor CG (:423-517)
         e = pi0 * u[0] + pi1 * u[2];
@@ -240,6 +263,10 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
         va[3] += dx * dy * fa; va[4] += dx * dz * fa; va[5] += dy * dz * fa;
       }
     }
+  }
+  if (p.logsum && dens_i) {
+    pf0 -= p.kT * (log(R0) + (double)E0 * 0.69314718055994530942);
+    pf1 -= p.kT * (log(R1) + (double)E1 * 0.69314718055994530942);
   }
   fx = group_sum<LPA>(fx); fy = group_sum<LPA>(fy); fz = group_sum<LPA>(fz);
   eacc = group_sum<LPA>(eacc);
@@ -414,6 +441,12 @@ extern "C" int ucgb200_pair_bethe_density(ucgb200_ctx *c, int eflag, int vflag) 
   a.tables = c->d_tables.p;
   for (int k = 0; k < 4; k++) a.special_lj[k] = c->special_lj[k];
   a.kT = c->kT; a.inv_kT = 1.0 / c->kT;
+  // sum_j kT log(p10/p00) and sum_j kT log(p11/p01) of the probability force (:632-641) as ONE logarithm per lane: the ratios
+  // are multiplied up, the binary exponent moves into an integer after every factor (no overflow / underflow), and
+  // log(mantissa) + exponent ln 2 is subtracted after the loop.  The two logarithms per UCG-UCG visit were 39 % of the
+  // pair sweep's instructions (profiles/r02_k_bd_pair_lines.json); the sums differ from the per-visit ones by a few ulp
+  // (scripts/dbg_bd_logsum.py).  UCGB200_BD_LOGSUM=0: one logarithm per ratio, as the reference writes it.
+  a.logsum = getenv("UCGB200_BD_LOGSUM") ? atoi(getenv("UCGB200_BD_LOGSUM")) : 1;
   a.prob0 = b.d_prob.p; a.partial0 = b.d_partial.p; a.cvf = b.d_cvf.p;
   a.frc = c->frc.p; a.scores = c->scores.p; a.ucgp = c->ucgp.p; a.partials = c->d_partials.p; a.err = c->d_err.p;
   if (want_eatom) { UCG_CHECK(c, c->d_eatom.ensure((size_t)c->nlocal + 8)); a.eatom = c->d_eatom.p; }
