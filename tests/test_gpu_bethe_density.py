@@ -114,3 +114,18 @@ def test_bethe_density_rejects_density_types_other_than_1(pkg, fixtures, tmp_pat
     ctx.neigh_build()
     ctx.pair_bethe_density(1, 1)
     assert ctx.status()[0] == 4
+
+
+def test_bethe_density_log_sum_switch(pkg, fixtures, tmp_path, monkeypatch):
+    """UCGB200_BD_LOGSUM=0 (one logarithm per ratio, as the reference writes it, instead of one logarithm of the running
+    product per lane) agrees with the default to rounding"""
+    liq = _liq(6)
+    out = {}
+    for logsum in ("1", "0"):
+        monkeypatch.setenv("UCGB200_BD_LOGSUM", logsum)
+        _, ctx = _setup(pkg, fixtures, tmp_path, liq)
+        ctx.neigh_build()
+        ctx.pair_bethe_density(1, 1)
+        out[logsum] = (ctx.atoms_download(["f"])["f"], ctx.pair_energy_virial())
+    (fa, (ea, va)), (fc, (ec, vc)) = out["1"], out["0"]
+    assert rel_err(fa, fc) <= 1e-13 and abs(ea - ec) <= 1e-13 * abs(ec) and rel_err(va, vc) <= 1e-13
