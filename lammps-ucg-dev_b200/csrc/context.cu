@@ -53,6 +53,7 @@ extern "C" int ucgb200_destroy(ucgb200_ctx *c) {
   for (void *p : c->table_allocs) cudaFree(p);
   // Buf<> members are released explicitly (no destructors: buffers may be swapped)
   c->d_tables.release(); c->d_pairinfo.release(); c->d_typeinfo.release(); c->d_fast_table.release();
+  c->posc.release();
   c->pos.release(); c->pos_alt.release(); c->vel.release(); c->vel_alt.release();
   c->frc.release(); c->frc_alt.release(); c->xhold.release();
   c->scores.release(); c->scores_alt.release(); c->ucgp.release(); c->ucgp_alt.release();

@@ -312,6 +312,17 @@ __global__ void __launch_bounds__(BS) k_bd_pair(BdArgs p) {
   block_reduce_store<7, BS>(evacc, p.partials);
 }
 
+// posc[j] = {x, y, z, c_j} for the uniform back-force sweep (pair_common.cuh): c_j = cvf_j of an OWNED density site, else 0
+// (with newton off the reference's loop of a ghost never runs, and only density sites carry a CV force)
+__global__ void k_bd_posc(BdArgs p, int nall, double4 *__restrict__ posc) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nall) return;
+  double4 r = p.pos[j];
+  const int tj = p.ts[j] & 0xffff;
+  r.w = (j < p.nlocal && p.bt[tj].use_density == 1 && p.tinfo[tj].nstates > 1) ? p.cvf[j] : 0.0;
+  posc[j] = r;
+}
+
 template <int LPA, int BS, bool PA>
 __global__ void __launch_bounds__(BS) k_bd_back(BdArgs p) {
   const int gid = (blockIdx.x * BS + threadIdx.x) / LPA;
@@ -494,7 +505,25 @@ extern "C" int ucgb200_pair_bethe_density(ucgb200_ctx *c, int eflag, int vflag) 
   }
   UCG_LAUNCHED(c);
   if ((rc = reduce_partials(c, nblk_pair, 7, 0))) return rc;
-  if (want_vatom) k_bd_back<LPA, BS, true><<<nblk, BS, 0, c->stream>>>(a);
+  // uniform case (every density type has the same threshold radius, every pair the same cutoff — one 2-state type is):
+  // the back-force sweep gathers one packed record per neighbor (k_cv_back_fast, pair_common.cuh); UCGB200_CV_FAST=0 and
+  // per-atom virial requests take the general sweep (same bits)
+  double urth = -1.0, ucut = -1.0;
+  bool uniform = !want_vatom && !(getenv("UCGB200_CV_FAST") && atoi(getenv("UCGB200_CV_FAST")) == 0);
+  for (int t = 1; t <= b.n_actual && uniform; t++)
+    if (b.use_density[t] == 1) { if (urth < 0) urth = b.r_th[t]; else if (b.r_th[t] != urth) uniform = false; }
+  for (int i = 1; i < a.na && uniform; i++)
+    for (int j = 1; j < a.na && uniform; j++) {
+      const double cs = c->h_pairinfo[i * a.na + j].cutsq;
+      if (ucut < 0) ucut = cs; else if (cs != ucut) uniform = false;
+    }
+  if (uniform && urth > 0 && ucut > 0) {
+    UCG_CHECK(c, c->posc.ensure((size_t)nall + 8));
+    k_bd_posc<<<nblocks(nall, 256), 256, 0, c->stream>>>(a, nall, c->posc.p);
+    UCG_LAUNCHED(c);
+    CvBackArgs ba{c->posc.p, c->nlocal, a.neigh, a.stride, a.numneigh, ucut, urth, a.frc, a.partials};
+    k_cv_back_fast<LPA, BS, 0><<<nblk, BS, 0, c->stream>>>(ba);
+  } else if (want_vatom) k_bd_back<LPA, BS, true><<<nblk, BS, 0, c->stream>>>(a);
   else k_bd_back<LPA, BS, false><<<nblk, BS, 0, c->stream>>>(a);
   UCG_LAUNCHED(c);
   if ((rc = reduce_partials(c, nblk, 7, 16))) return rc;   // second virial part -> d_ev[16..22]

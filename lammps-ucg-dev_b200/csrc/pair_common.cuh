@@ -189,4 +189,76 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *part
   }
 }
 
+// ---- CV back-force sweep of the two density styles (pair_table_ucg_bethe_density.cpp:696-726,
+// pair_table_rleucg_interface.cpp:466-502) when every density type shares ONE threshold radius and every pair ONE cutoff:
+// the sweep then needs nothing of a neighbor but its position and "its CV force if it is a density site this sweep may react
+// to, else 0" — one 32-byte gather of posc[j] = {x, y, z, c_j} (packed once per evaluation by the style) instead of the
+// position, the type, the type's parameters and the CV force.  G = 0: g = 1/2 (1 - tanh y) (bethe_density, sic Q13);
+// G = 1: g = 1/2 (1 - tanh^2 y) / (0.1 r_th) (rleucg).  Same expressions in the same order as the general sweeps: with
+// LPA = 8 the sums are identical bit for bit.  Pairs whose two CV forces are both zero skip the special functions.
+struct CvBackArgs {
+  const double4 *posc;
+  int nlocal;
+  const int *neigh;
+  int stride;
+  const int *numneigh;
+  double cutsq, rth;
+  double4 *frc;
+  double *partials;
+};
+template <int LPA, int BS, int G>
+__global__ void __launch_bounds__(BS) k_cv_back_fast(CvBackArgs p) {
+  const int gid = (blockIdx.x * BS + threadIdx.x) / LPA;
+  const int sub = threadIdx.x % LPA;
+  const bool active = gid < p.nlocal;
+  const int i = active ? gid : 0;
+  const double4 ri = p.posc[i];
+  const double ci = ri.w;
+  const int jnum = active ? p.numneigh[i] : 0;
+  const int *row = p.neigh + (size_t)i * p.stride;
+  double fx = 0, fy = 0, fz = 0;
+  double vir[6] = {0, 0, 0, 0, 0, 0};
+  RowWalk<LPA> rw(row, sub, jnum);
+  int jj = sub;
+  int j = -1;
+  double4 rj = ri;
+  if (jj < jnum) { j = rw.raw(jj) & UCG_NEIGHMASK; rj = p.posc[j]; }
+  while (j >= 0) {
+    // the next entry's record is in flight while this pair is evaluated
+    int jn = -1;
+    double4 rn = rj;
+    jj += LPA;
+    rw.advance();
+    if (jj < jnum) { jn = rw.raw(jj) & UCG_NEIGHMASK; rn = p.posc[jn]; }
+    const double dx = ri.x - rj.x, dy = ri.y - rj.y, dz = ri.z - rj.z;
+    const double rsq = rsq_exact(dx, dy, dz);
+    if (rsq < p.cutsq && (ci != 0.0 || rj.w != 0.0)) {
+      const double r = sqrt(rsq);
+      const double t = tanh((r - p.rth) / (0.1 * p.rth));
+      const double g = G == 0 ? 0.5 * (1.0 - t) : 0.5 * (1.0 - t * t) / (0.1 * p.rth);
+      const double own = ci * g / r;        // i's loop
+      const double oth = rj.w * g / r;      // what j's loop scatters to i
+      const double fp = own + oth;
+      fx += fp * dx; fy += fp * dy; fz += fp * dz;
+      const double w = (j < p.nlocal ? 1.0 : 0.5) * own;   // ev_tally(i, j, nlocal, newton = 0, ...) in i's loop only
+      vir[0] += w * dx * dx; vir[1] += w * dy * dy; vir[2] += w * dz * dz;
+      vir[3] += w * dx * dy; vir[4] += w * dx * dz; vir[5] += w * dy * dz;
+    }
+    j = jn; rj = rn;
+  }
+  fx = group_sum<LPA>(fx); fy = group_sum<LPA>(fy); fz = group_sum<LPA>(fz);
+  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const double v = group_sum<LPA>(vir[k]);
+    if (active && sub == 0) ev[1 + k] = v;
+  }
+  if (active && sub == 0) {
+    double4 f = p.frc[i];
+    f.x += fx; f.y += fy; f.z += fz;
+    p.frc[i] = f;
+  }
+  block_reduce_store<7, BS>(ev, p.partials);
+}
+
 }  // namespace ucg

@@ -206,6 +206,16 @@ __global__ void __launch_bounds__(BS) k_rle_pair(RleArgs p) {
   block_reduce_store<7, BS>(evacc, p.partials);
 }
 
+// posc[j] = {x, y, z, c_j} for the uniform back-force sweep (pair_common.cuh): c_j = cvf_j of a 2-state site (owned or
+// ghost: the CV forces were forwarded to the ghosts), else 0
+__global__ void k_rle_posc(RleArgs p, int nall, double4 *__restrict__ posc) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nall) return;
+  double4 r = p.pos[j];
+  r.w = p.rt[p.ts[j] & 0xffff].nstates > 1 ? p.cvf[j] : 0.0;
+  posc[j] = r;
+}
+
 template <int LPA, int BS, bool PA>
 __global__ void __launch_bounds__(BS) k_rle_back(RleArgs p) {
   const int gid = (blockIdx.x * BS + threadIdx.x) / LPA;
@@ -461,7 +471,27 @@ extern "C" int ucgb200_pair_rleucg(ucgb200_ctx *c, int eflag, int vflag) {
     UCG_LAUNCHED(c);
   }
   if ((rc = ucg_mb_forward_scalars(c, a.cvf, nullptr, nullptr))) return rc;
-  if (want_vatom) k_rle_back<LPA, BS, true><<<nblk, BS, 0, c->stream>>>(a);
+  // uniform case (every 2-state type has the same threshold radius, every pair the same cutoff): the back-force sweep
+  // gathers one packed record per neighbor (k_cv_back_fast, pair_common.cuh); UCGB200_CV_FAST=0 and per-atom virial
+  // requests take the general sweep (same bits)
+  double urth = -1.0, ucut = -1.0;
+  bool uniform = !want_vatom && !(getenv("UCGB200_CV_FAST") && atoi(getenv("UCGB200_CV_FAST")) == 0);
+  for (int t = 1; t < a.nt && uniform; t++) {
+    const int act = d.actual_from_state[t];
+    if (d.n_states_of_type[act] > 1) { const double r = d.threshold_radius[act]; if (urth < 0) urth = r; else if (r != urth) uniform = false; }
+  }
+  for (int i = 1; i < a.nt && uniform; i++)
+    for (int j = 1; j < a.nt && uniform; j++) {
+      const double cs = c->h_pairinfo[i * a.nt + j].cutsq;
+      if (ucut < 0) ucut = cs; else if (cs != ucut) uniform = false;
+    }
+  if (uniform && urth > 0 && ucut > 0) {
+    UCG_CHECK(c, c->posc.ensure((size_t)nall + 8));
+    k_rle_posc<<<nblocks(nall, 256), 256, 0, c->stream>>>(a, nall, c->posc.p);
+    UCG_LAUNCHED(c);
+    CvBackArgs ba{c->posc.p, c->nlocal, a.neigh, a.stride, a.numneigh, ucut, urth, a.frc, a.partials};
+    k_cv_back_fast<LPA, BS, 1><<<nblk, BS, 0, c->stream>>>(ba);
+  } else if (want_vatom) k_rle_back<LPA, BS, true><<<nblk, BS, 0, c->stream>>>(a);
   else k_rle_back<LPA, BS, false><<<nblk, BS, 0, c->stream>>>(a);
   UCG_LAUNCHED(c);
   if ((rc = reduce_partials(c, nblk, 7, 16))) return rc;   // second virial part -> d_ev[16..22]

@@ -267,6 +267,7 @@ struct ucgb200_ctx {
   // ucgb200_step_host: results leave on a second stream while the step is still running
   ucgb200_atoms *host_out = nullptr;
   unsigned host_out_fields = 0, host_out_done = 0;
+  ucg::Buf<double4> posc;          // density styles, uniform case: {x, y, z, CV force a neighbor's sweep may react to} (pair_common.cuh)
   bool skip_initial_once = false;  // ucgb200_step_host already ran this step's initial_integrate (in two parts, under the uploads)
   cudaStream_t stream_dl = nullptr;
   cudaEvent_t ev_dl[10] = {};      // one per result field: a field's copy starts as soon as its own gather has run

@@ -100,3 +100,20 @@ def test_rleucg_rejects_density_types_other_than_1(pkg, fixtures, tmp_path):
     ctx.neigh_build()
     ctx.pair_rleucg(1, 1)
     assert ctx.status()[0] == 4
+
+
+def test_rleucg_uniform_back_force_sweep_changes_nothing(pkg, fixtures, tmp_path, monkeypatch):
+    """one threshold radius and one cutoff: the CV back-force sweep gathers one packed {x, y, z, cvf-or-0} record per
+    neighbor (k_cv_back_fast) instead of position, type, type parameters and CV force; UCGB200_CV_FAST=0 selects the
+    general sweep.  Same expressions in the same order: identical bits"""
+    liq = _liq(6)
+    out = []
+    for fast in ("1", "0"):
+        monkeypatch.setenv("UCGB200_CV_FAST", fast)
+        _, ctx = _setup(pkg, fixtures, tmp_path, liq)
+        ctx.neigh_build()
+        ctx.pair_rleucg(1, 1)
+        out.append((ctx.atoms_download(["f"])["f"], ctx.pair_energy_virial()))
+    (fa, (ea, va)), (fb, (eb, vb)) = out
+    assert np.abs(fa).max() > 0
+    assert np.array_equal(fa, fb) and ea == eb and np.array_equal(va, vb)
